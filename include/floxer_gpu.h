@@ -1,0 +1,197 @@
+/*
+ * floxer_gpu.h -- C ABI of the B200 (sm_100a) implementation of floxer's PEX hierarchical
+ * verification hot path.  Plain pointers and sizes only; no exception crosses this boundary;
+ * every function returns FXG_OK (0) or a negative FXG_ERR_* code and fxg_last_error() has
+ * the text.  All citations are file:line into the reference tree (floxer 0.2.0).
+ *
+ * What each entry point replaces:
+ *   fxg_set_references   the host-resident `input::references` (include/input.hpp:30-33,
+ *                        src/main/floxer.cpp:49-51) as seen by verification: packed once, kept in HBM.
+ *   fxg_align_batch      N independent calls of `alignment::align(reference_span, query_span, config)`
+ *                        (include/alignment.hpp:73-77, src/lib/alignment.cpp:83-181).
+ *   fxg_verify_reads     the anchor loop of a verification task for whole reads:
+ *                        `for anchor in package.anchors: query_verifier{...}.verify()`
+ *                        (src/lib/parallelization.cpp:230-249, include/verification.hpp:22-48,
+ *                        src/lib/verification.cpp:8-245), forward package(s) first, then reverse
+ *                        complement (src/lib/parallelization.cpp:14-43), including the shared
+ *                        verified-interval sets (src/lib/intervals.cpp:84-127).
+ *   *_stage/_run/_fetch  the same work split so that a caller can keep inputs resident in HBM.
+ *
+ * Struct layouts fxg_pex_node and fxg_anchor are byte-identical to pex::pex_tree::node
+ * (include/pex.hpp:59-70) and search::anchor_t (include/search.hpp:27-31) on LP64, so the
+ * reference's vectors can be passed without conversion.
+ */
+#ifndef FLOXER_GPU_H
+#define FLOXER_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FXG_OK 0
+#define FXG_ERR_INVALID_ARGUMENT (-1)  /* bad enum / rank > 5 / out-of-range span; maps onto the reference's std::runtime_error */
+#define FXG_ERR_CUDA (-2)              /* CUDA runtime failure (no device, OOM, launch error) */
+#define FXG_ERR_OUT_OF_MEMORY (-3)     /* host allocation failure */
+#define FXG_ERR_OVERFLOW (-4)          /* caller-provided output buffer too small; required size reported */
+#define FXG_ERR_STATE (-5)             /* call order violated (e.g. verify before set_references) */
+
+#define FXG_NULL_ID UINT64_MAX         /* pex::pex_tree::node::null_id, include/pex.hpp:60 */
+#define FXG_REF_INLINE UINT32_MAX      /* task reads its reference span from the inline pool */
+#define FXG_MAX_RANK 5                 /* alphabet ranks 0..5, include/input.hpp:63-66 */
+#define FXG_MAX_QUERY_LENGTH 100000    /* input::queries::MAX_ALLOWED_QUERY_LENGTH, include/input.hpp:42 */
+
+/* alignment::alignment_mode, include/alignment.hpp:53-55 */
+enum { FXG_MODE_EXISTS = 0, FXG_MODE_NO_CIGAR = 1, FXG_MODE_CIGAR = 2 };
+/* alignment::query_orientation, include/alignment.hpp:14-16 */
+enum { FXG_FORWARD = 0, FXG_REVERSE_COMPLEMENT = 1 };
+/* pex::verification_kind_t, include/pex.hpp:43-45 */
+enum { FXG_KIND_DIRECT_FULL = 0, FXG_KIND_HIERARCHICAL = 1 };
+/* BAM CIGAR op codes; an op is stored as (length << 4) | code.  seqan3 extended cigar, alignment.cpp:178 */
+enum { FXG_CIGAR_I = 1, FXG_CIGAR_D = 2, FXG_CIGAR_EQ = 7, FXG_CIGAR_X = 8 };
+
+typedef struct fxg_ctx fxg_ctx;
+typedef struct fxg_batch fxg_batch;     /* staged fxg_align_batch */
+typedef struct fxg_job fxg_job;         /* staged fxg_verify_reads */
+
+typedef struct { uint64_t parent_id, query_index_from, query_index_to, num_errors; } fxg_pex_node;
+typedef struct { uint64_t pex_leaf_index, reference_id, reference_position, num_errors; } fxg_anchor;
+
+/* one alignment::align call: the two spans + alignment_config (include/alignment.hpp:57-62) */
+typedef struct {
+    uint64_t ref_offset;             /* start of the reference span inside reference `ref_id` (or the inline pool) */
+    uint64_t reference_span_offset;  /* alignment_config::reference_span_offset (added to the begin position) */
+    uint64_t query_offset;           /* start of the query span inside the query pool */
+    uint32_t ref_len;                /* reference span length  (reference.size()) */
+    uint32_t query_len;              /* query span length      (query.size())     */
+    uint32_t ref_id;                 /* resident reference index, or FXG_REF_INLINE */
+    uint32_t max_errors;             /* alignment_config::num_allowed_errors */
+    uint8_t mode;                    /* FXG_MODE_*  */
+    uint8_t orientation;             /* passed through to the result */
+    uint8_t reserved[6];
+} fxg_align_task;
+
+/* alignment::alignment_result, include/alignment.hpp:64-71 */
+typedef struct {
+    uint64_t start_in_reference;     /* query_alignment::start_in_reference */
+    uint64_t cigar_offset;           /* first op in the cigar pool (uint32 elements) */
+    uint32_t cigar_len;              /* number of ops (0 unless FXG_MODE_CIGAR) */
+    uint32_t num_errors;             /* query_alignment::num_errors */
+    uint8_t exists;                  /* 1 = alignment_exists, 0 = no_adequate_alignment_exists */
+    uint8_t orientation;
+    uint8_t reserved[6];
+} fxg_align_result;
+
+/* one read with its PEX tree and anchors; mirrors parallelization::shared_verification_data
+ * (include/parallelization.hpp:41-66) + the anchor packages of one query */
+typedef struct {
+    uint64_t query_offset;           /* into BOTH the forward and the reverse-complement pool */
+    uint64_t node_offset;            /* into the node pool: num_inner inner nodes (root first), then num_leaves leaves */
+    uint64_t anchor_offset;          /* into the anchor pool: forward anchors, then reverse-complement anchors */
+    uint32_t query_len;
+    uint32_t num_inner;
+    uint32_t num_leaves;
+    uint32_t num_anchors_forward;
+    uint32_t num_anchors_reverse;
+    uint32_t reserved;
+} fxg_read;
+
+/* pex::pex_verification_config (include/pex.hpp:47-53) + cli without_cigar (include/floxer_cli.hpp:67) */
+typedef struct {
+    double extra_verification_ratio;
+    uint8_t verification_kind;       /* FXG_KIND_* */
+    uint8_t interval_optimization;   /* 0 / 1 */
+    uint8_t without_cigar;           /* 0 / 1 */
+    uint8_t reserved[5];
+} fxg_verify_config;
+
+/* alignment::query_alignment + the reference it was inserted for (alignments.insert(aln, reference.internal_id)) */
+typedef struct {
+    uint64_t start_in_reference;
+    uint64_t cigar_offset;
+    uint32_t cigar_len;
+    uint32_t num_errors;
+    uint32_t read_index;
+    uint32_t reference_id;
+    uint8_t orientation;
+    uint8_t reserved[7];
+} fxg_alignment;
+
+/* the three hot-path histograms (src/lib/verification.cpp:130,239,241) as count/sum, plus DP work */
+typedef struct {
+    uint64_t n_aligned_inner, sum_aligned_inner;
+    uint64_t n_aligned_root, sum_aligned_root;
+    uint64_t n_avoided_root, sum_avoided_root;
+    uint64_t cells_inner, cells_root;        /* sum of m' * n' over every align call of the reference walk */
+} fxg_stats;
+
+/* device-side accounting since the last fxg_reset_counters */
+typedef struct {
+    uint64_t kernel_launches;        /* launches of this library's kernels */
+    uint64_t dp_tasks;               /* bit-vector DP tasks executed (score passes + trace passes) */
+    uint64_t dp_word_steps;          /* 32-cell Myers word-steps issued by the DP kernels (band-limited) */
+    uint64_t dp_cells_full;          /* sum of m' * n' of those tasks (full-matrix convention) */
+    uint64_t trace_bytes;            /* bytes of trace bit-planes written by the traceback pass */
+    uint64_t h2d_bytes, d2h_bytes;
+    double dp_kernel_ms;             /* CUDA-event time of the DP kernels on the context's stream */
+    double trace_kernel_ms;          /* CUDA-event time of trace-store + walk kernels */
+    uint64_t waves;                  /* host scheduling rounds of fxg_verify_* */
+} fxg_counters;
+
+/* ---- life cycle ---- */
+int fxg_create(int device, fxg_ctx** out);
+void fxg_destroy(fxg_ctx* ctx);
+const char* fxg_last_error(const fxg_ctx* ctx);           /* valid until the next call on ctx */
+const char* fxg_version(void);
+
+/* packs (4 bit / base, ranks 0..5 exact) and uploads every reference once; replaces earlier ones */
+int fxg_set_references(fxg_ctx* ctx, size_t n_references, const uint8_t* const* rank_sequences,
+                       const uint64_t* lengths);
+
+/* ---- alignment::align, batched ---- */
+int fxg_align_batch(fxg_ctx* ctx, const fxg_align_task* tasks, size_t n_tasks,
+                    const uint8_t* query_pool, size_t query_pool_len,
+                    const uint8_t* inline_ref_pool, size_t inline_ref_pool_len,
+                    fxg_align_result* results, uint32_t* cigar_pool, size_t cigar_capacity,
+                    size_t* cigar_used);
+int fxg_align_batch_stage(fxg_ctx* ctx, const fxg_align_task* tasks, size_t n_tasks,
+                          const uint8_t* query_pool, size_t query_pool_len,
+                          const uint8_t* inline_ref_pool, size_t inline_ref_pool_len, fxg_batch** out);
+int fxg_align_batch_run(fxg_ctx* ctx, fxg_batch* batch);  /* device work only; returns after it completed */
+int fxg_align_batch_fetch(fxg_ctx* ctx, fxg_batch* batch, fxg_align_result* results,
+                          uint32_t* cigar_pool, size_t cigar_capacity, size_t* cigar_used);
+void fxg_batch_free(fxg_ctx* ctx, fxg_batch* batch);
+
+/* ---- query_verifier::verify for every anchor of every read ---- */
+int fxg_verify_stage(fxg_ctx* ctx, const fxg_verify_config* config,
+                     const fxg_read* reads, size_t n_reads,
+                     const uint8_t* forward_pool, const uint8_t* reverse_complement_pool, size_t pool_len,
+                     const fxg_pex_node* nodes, size_t n_nodes,
+                     const fxg_anchor* anchors, size_t n_anchors, fxg_job** out);
+int fxg_verify_run(fxg_ctx* ctx, fxg_job* job);
+size_t fxg_job_num_alignments(const fxg_job* job);
+const fxg_alignment* fxg_job_alignments(const fxg_job* job);   /* per read, in the reference's single-thread order */
+size_t fxg_job_cigar_len(const fxg_job* job);
+const uint32_t* fxg_job_cigar_pool(const fxg_job* job);
+const fxg_stats* fxg_job_stats(const fxg_job* job);
+void fxg_job_free(fxg_ctx* ctx, fxg_job* job);
+/* stage + run in one call */
+int fxg_verify_reads(fxg_ctx* ctx, const fxg_verify_config* config,
+                     const fxg_read* reads, size_t n_reads,
+                     const uint8_t* forward_pool, const uint8_t* reverse_complement_pool, size_t pool_len,
+                     const fxg_pex_node* nodes, size_t n_nodes,
+                     const fxg_anchor* anchors, size_t n_anchors, fxg_job** out);
+
+/* ---- accounting / measurement helpers ---- */
+int fxg_get_counters(const fxg_ctx* ctx, fxg_counters* out);
+int fxg_reset_counters(fxg_ctx* ctx);
+/* issue-rate microbenchmark: dependent-free LOP3/IADD3/SHF stream in the 8:1:2 mix of one Myers word-step;
+ * returns thread-instructions per second (the int32 roofline denominator) */
+int fxg_measure_int32_peak(fxg_ctx* ctx, double* thread_instructions_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
