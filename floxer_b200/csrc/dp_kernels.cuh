@@ -1,0 +1,448 @@
+// dp_kernels.cuh -- device code of the PEX verification path for sm_100a.
+//
+// One engine computes every alignment::align mode (src/lib/alignment.cpp:83-181 of the reference):
+// a banded, bit-parallel (Myers/Hyyroe) semi-global edit-distance pass in which a RING of G lanes
+// of one warp sweeps the DP matrix as a skewed wavefront.  Rows are cut into blocks of 32*W rows
+// (W 32-bit words held in registers per lane); lane r of the ring owns blocks r, r+G, r+2G, ...;
+// block b processes column j at step t = j + b, so the only cross-lane traffic is the two
+// horizontal-delta bits (and the running score) of the block above, handed down with warp shuffles.
+// Only the cells inside the diagonal band [dlo, dhi] that can lie on an alignment with <= k errors
+// are computed (a block is active for columns cs(b)..ce(b)); outside values are replaced by upper
+// bounds (+1 steps), which keeps every value <= k exact.
+//
+// Not a dense contraction: no tensor cores.  The hot loop is LOP3 / IADD3(.X) / SHF on the integer
+// pipes, Eq words and window characters come from shared memory, the carries from SHFL.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fxg {
+
+constexpr int kNumSymbols = 6;          // ranks 0..5, include/input.hpp:63-66 of the reference
+constexpr int kPeqFrontPadWords = 64;   // table words in front of position 0 (wildcard rows read there)
+constexpr int kPeqBackPadWords = 66;
+constexpr uint32_t kFlagReverse = 1u;   // run on reversed views (alignment.cpp:118-125)
+constexpr uint32_t kFlagInlineRef = 2u; // window comes from the per-batch inline pool
+constexpr int32_t kNoScore = 0x3fffffff;
+
+// One bit-vector DP pass.  All coordinates are in bases.
+struct DpTask {
+    uint64_t ref_base;     // position of window[0] in the packed reference store (or inline pool)
+    uint64_t query_base;   // position of query[0] in the pool the Peq table was built from
+    uint64_t trace_base;   // first 32-bit word of this task's trace planes (trace passes only)
+    uint32_t n;            // window length
+    uint32_t m;            // query length (>= 1)
+    int32_t dlo, dhi;      // band of diagonals j - i (1-based DP coordinates) that is computed
+    uint32_t flags;
+    uint32_t out;          // result slot
+};
+
+struct DpResult {
+    int32_t score;         // minimum of the last row inside the band (kNoScore if the last row was never reached)
+    uint32_t end_col;      // rightmost column (1-based, == exclusive end) attaining it
+};
+
+// ---------------------------------------------------------------------------------------------
+// Peq table: bit p of plane s is (pool[p] == s).  kPeqFrontPadWords zero words in front.
+// ---------------------------------------------------------------------------------------------
+__global__ void build_peq_kernel(const uint8_t* __restrict__ pool, uint64_t len, uint32_t* __restrict__ table,
+                                 uint64_t plane_words) {
+    uint64_t const n_words = (len + 31) / 32;
+    uint32_t const lane = threadIdx.x & 31;
+    uint64_t const warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    uint64_t const n_warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t w = warp; w < n_words; w += n_warps) {
+        uint64_t const p = w * 32 + lane;
+        uint32_t const c = p < len ? pool[p] : 0xffu;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int s = 0; s < kNumSymbols; ++s) {
+            uint32_t const bal = __ballot_sync(0xffffffffu, c == uint32_t(s));
+            if (lane == uint32_t(s)) mine = bal;
+        }
+        if (lane < kNumSymbols) table[uint64_t(lane) * plane_words + kPeqFrontPadWords + w] = mine;
+    }
+}
+
+// 32 bits of plane starting at (signed) bit position x
+__device__ __forceinline__ uint32_t peq_window(const uint32_t* __restrict__ plane, int64_t x) {
+    int64_t const X = x + int64_t(kPeqFrontPadWords) * 32;
+    uint32_t const lo = plane[X >> 5], hi = plane[(X >> 5) + 1];
+    return __funnelshift_r(lo, hi, uint32_t(X) & 31u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reference store: 4 bits per base (ranks 0..15 exact), 32 bases per 16-byte chunk
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_nibbles_kernel(const uint8_t* __restrict__ ranks, uint64_t len, uint32_t* __restrict__ packed) {
+    uint64_t const n_words = (len + 7) / 8;
+    for (uint64_t w = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; w < n_words; w += uint64_t(gridDim.x) * blockDim.x) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint64_t const p = w * 8 + i;
+            uint32_t const c = p < len ? ranks[p] : 0u;
+            x |= (c & 15u) << (4 * i);
+        }
+        packed[w] = x;
+    }
+}
+
+__device__ __forceinline__ uint32_t packed_base(const uint32_t* __restrict__ packed, uint64_t p) {
+    return (packed[p >> 3] >> (4 * (uint32_t(p) & 7u))) & 15u;
+}
+
+// 8 packed bases -> 8 bytes (two words, base order preserved)
+__device__ __forceinline__ void unpack8(uint32_t x, uint32_t& lo, uint32_t& hi) {
+    uint32_t const e = x & 0x0f0f0f0fu, o = (x >> 4) & 0x0f0f0f0fu;
+    lo = __byte_perm(e, o, 0x5140);
+    hi = __byte_perm(e, o, 0x7362);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the DP engine
+// ---------------------------------------------------------------------------------------------
+struct DpLaunch {
+    const DpTask* tasks;        // sorted so that the tasks of one warp have similar step counts
+    uint32_t n_tasks;
+    uint32_t group;             // G: lanes per task (1, 2, 4, 8, 16 or 32); 32 / G tasks per warp
+    uint32_t win_stride;        // bytes of shared memory per task window (multiple of 16)
+    uint32_t peq_stride;        // words per symbol row of the per-task Eq table
+    const uint32_t* ref_packed; // resident references
+    const uint32_t* inline_packed;
+    const uint32_t* peq_table;  // kNumSymbols planes
+    uint64_t peq_plane_words;
+    DpResult* results;
+    uint32_t* trace;            // trace planes [step][ring lane][word][hp, vp]
+};
+
+// S = T + P + carry over CH consecutive words with the hardware carry chain (IADD3.X); one asm
+// statement per chunk so that nothing can clobber CC in between.  cin / return value are 0 or 1.
+template <int CH, bool COUT> struct Chain;
+template <bool COUT> struct Chain<1, COUT> {
+    static __device__ __forceinline__ uint32_t run(uint32_t* S, const uint32_t* T, const uint32_t* P, uint32_t cin) {
+        uint32_t d, co = 0;
+        if (COUT) asm("add.cc.u32 %0, %3, 0xffffffff; addc.cc.u32 %1, %4, %5; addc.u32 %2, 0, 0;"
+                      : "=&r"(d), "=&r"(S[0]), "=&r"(co) : "r"(cin), "r"(T[0]), "r"(P[0]));
+        else asm("add.cc.u32 %0, %2, 0xffffffff; addc.u32 %1, %3, %4;" : "=&r"(d), "=&r"(S[0]) : "r"(cin), "r"(T[0]), "r"(P[0]));
+        return co;
+    }
+};
+template <bool COUT> struct Chain<2, COUT> {
+    static __device__ __forceinline__ uint32_t run(uint32_t* S, const uint32_t* T, const uint32_t* P, uint32_t cin) {
+        uint32_t d, co = 0;
+        if (COUT) asm("add.cc.u32 %0, %4, 0xffffffff; addc.cc.u32 %1, %5, %7; addc.cc.u32 %2, %6, %8; addc.u32 %3, 0, 0;"
+                      : "=&r"(d), "=&r"(S[0]), "=&r"(S[1]), "=&r"(co) : "r"(cin), "r"(T[0]), "r"(T[1]), "r"(P[0]), "r"(P[1]));
+        else asm("add.cc.u32 %0, %3, 0xffffffff; addc.cc.u32 %1, %4, %6; addc.u32 %2, %5, %7;"
+                 : "=&r"(d), "=&r"(S[0]), "=&r"(S[1]) : "r"(cin), "r"(T[0]), "r"(T[1]), "r"(P[0]), "r"(P[1]));
+        return co;
+    }
+};
+template <bool COUT> struct Chain<4, COUT> {
+    static __device__ __forceinline__ uint32_t run(uint32_t* S, const uint32_t* T, const uint32_t* P, uint32_t cin) {
+        uint32_t d, co = 0;
+        if (COUT) asm("add.cc.u32 %0, %6, 0xffffffff; addc.cc.u32 %1, %7, %11; addc.cc.u32 %2, %8, %12; addc.cc.u32 %3, %9, %13; "
+                      "addc.cc.u32 %4, %10, %14; addc.u32 %5, 0, 0;"
+                      : "=&r"(d), "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(co)
+                      : "r"(cin), "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]));
+        else asm("add.cc.u32 %0, %5, 0xffffffff; addc.cc.u32 %1, %6, %10; addc.cc.u32 %2, %7, %11; addc.cc.u32 %3, %8, %12; "
+                 "addc.u32 %4, %9, %13;"
+                 : "=&r"(d), "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3])
+                 : "r"(cin), "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]));
+        return co;
+    }
+};
+template <bool COUT> struct Chain<8, COUT> {
+    static __device__ __forceinline__ uint32_t run(uint32_t* S, const uint32_t* T, const uint32_t* P, uint32_t cin) {
+        uint32_t d, co = 0;
+        if (COUT) asm("add.cc.u32 %0, %10, 0xffffffff; addc.cc.u32 %1, %11, %19; addc.cc.u32 %2, %12, %20; addc.cc.u32 %3, %13, %21; "
+                      "addc.cc.u32 %4, %14, %22; addc.cc.u32 %5, %15, %23; addc.cc.u32 %6, %16, %24; addc.cc.u32 %7, %17, %25; "
+                      "addc.cc.u32 %8, %18, %26; addc.u32 %9, 0, 0;"
+                      : "=&r"(d), "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5]), "=&r"(S[6]), "=&r"(S[7]), "=&r"(co)
+                      : "r"(cin), "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]), "r"(T[7]),
+                        "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]), "r"(P[5]), "r"(P[6]), "r"(P[7]));
+        else asm("add.cc.u32 %0, %9, 0xffffffff; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20; "
+                 "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.cc.u32 %7, %16, %24; "
+                 "addc.u32 %8, %17, %25;"
+                 : "=&r"(d), "=&r"(S[0]), "=&r"(S[1]), "=&r"(S[2]), "=&r"(S[3]), "=&r"(S[4]), "=&r"(S[5]), "=&r"(S[6]), "=&r"(S[7])
+                 : "r"(cin), "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]), "r"(T[7]),
+                   "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]), "r"(P[5]), "r"(P[6]), "r"(P[7]));
+        return co;
+    }
+};
+
+template <int W, bool TRACE>
+__global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t const lane = threadIdx.x;
+    uint32_t const G = L.group;
+    uint32_t const tasks_per_warp = 32u / G;
+    uint32_t const slot = lane / G;                 // which task of this warp
+    uint32_t const r = lane % G;                    // ring position
+    uint32_t const task_id = blockIdx.x * tasks_per_warp + slot;
+    bool const have_task = task_id < L.n_tasks;
+
+    uint8_t* const win = smem + size_t(slot) * L.win_stride;
+    uint32_t* const peq = reinterpret_cast<uint32_t*>(smem + size_t(tasks_per_warp) * L.win_stride) +
+                          size_t(slot) * kNumSymbols * L.peq_stride;
+
+    DpTask T;
+    if (have_task) T = L.tasks[task_id];
+    else { T.n = 0; T.m = 1; T.dlo = 0; T.dhi = 0; T.flags = 0; T.ref_base = 0; T.query_base = 0; T.trace_base = 0; T.out = 0; }
+
+    constexpr int ROWS = 32 * W;
+    uint32_t const nb = (T.m + ROWS - 1) / ROWS;               // blocks of this task
+    uint32_t const pad = nb * ROWS - T.m;                      // wildcard rows in front, so that row m is the last bit
+    int32_t const dlo = T.dlo - int32_t(pad), dhi = T.dhi - int32_t(pad);
+    bool const reverse = (T.flags & kFlagReverse) != 0;
+
+    // ---- stage the window: 32 bases (16 bytes packed) per lane and iteration ----
+    uint32_t const phase = uint32_t(T.ref_base & 31u);
+    if (have_task) {
+        const uint4* src = reinterpret_cast<const uint4*>((T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed) + (T.ref_base >> 5);
+        uint32_t const n_chunks = (phase + T.n + 31) / 32;
+        for (uint32_t c = r; c < n_chunks; c += G) {
+            uint4 const v = __ldg(src + c);
+            uint4 a, b2;
+            unpack8(v.x, a.x, a.y); unpack8(v.y, a.z, a.w); unpack8(v.z, b2.x, b2.y); unpack8(v.w, b2.z, b2.w);
+            uint4* dst = reinterpret_cast<uint4*>(win + c * 32);
+            dst[0] = a; dst[1] = b2;
+        }
+        // ---- stage the Eq table of the query piece from the pool-level Peq planes ----
+        uint32_t const n_words = nb * W;
+        for (uint32_t w = r; w < n_words; w += G) {
+            int32_t const virt = int32_t(pad) - int32_t(32 * w);            // wildcard bits in this word
+            uint32_t const wild = virt >= 32 ? 0xffffffffu : (virt > 0 ? ((1u << virt) - 1u) : 0u);
+#pragma unroll
+            for (int s = 0; s < kNumSymbols; ++s) {
+                const uint32_t* plane = L.peq_table + uint64_t(s) * L.peq_plane_words;
+                uint32_t x;
+                if (!reverse) {
+                    x = peq_window(plane, int64_t(T.query_base) - int64_t(pad) + int64_t(32 * w));
+                } else {
+                    int64_t const y = int64_t(T.query_base) + int64_t(T.m) - 1 + int64_t(pad) - int64_t(32 * w);
+                    x = __brev(peq_window(plane, y - 31));
+                }
+                peq[s * L.peq_stride + w] = x | wild;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- per-lane block state ----
+    uint32_t Pv[W], Mv[W];
+    uint32_t b = r;                                  // current block
+    int32_t cs, ce;                                  // active column range of block b
+    auto set_block = [&](uint32_t blk) {
+        if (!have_task || blk >= nb) { cs = 0x7fffffff; ce = -1; return; }
+        int64_t const lo = int64_t(ROWS) * blk + 1 + dlo;
+        int64_t const hi = int64_t(ROWS) * (blk + 1) + dhi;
+        cs = lo < 1 ? 1 : (lo > 0x7ffffffe ? 0x7fffffff : int32_t(lo));
+        ce = hi > int64_t(T.n) ? int32_t(T.n) : int32_t(hi);
+        if (cs > ce) { cs = 0x7fffffff; ce = -1; }
+    };
+    set_block(b);
+
+    uint32_t o_hp = 0x80000000u, o_hn = 0;           // what an idle lane publishes: the boundary grows by +1 per column
+    int32_t score = 0;
+    int32_t best = kNoScore; uint32_t best_col = 0;
+    uint32_t const src_lane = slot * G + (r + G - 1) % G;
+
+    // number of steps of this warp: last block of the longest task
+    uint32_t my_end = have_task ? (T.n + nb - 1) : 0;
+    for (int off = 16; off > 0; off >>= 1) my_end = max(my_end, __shfl_xor_sync(0xffffffffu, my_end, off));
+
+    uint8_t const* const win0 = win + phase;
+    for (uint32_t t = 1; t <= my_end; ++t) {
+        uint32_t const r_hp = __shfl_sync(0xffffffffu, o_hp, src_lane);
+        uint32_t const r_hn = __shfl_sync(0xffffffffu, o_hn, src_lane);
+        int32_t const r_sc = __shfl_sync(0xffffffffu, score, src_lane);
+        int32_t const j = int32_t(t) - int32_t(b);
+        if (j >= cs && j <= ce) {
+            uint32_t in_hp = r_hp, in_hn = r_hn;
+            if (b == 0) { in_hp = 0; in_hn = 0; }    // row 0 of a semi-global matrix is all zeros
+            if (j == cs) {
+                // (re)start: column cs-1 of this block is (bottom of the block above at cs-1) + 1, 2, ...
+#pragma unroll
+                for (int i = 0; i < W; ++i) { Pv[i] = 0xffffffffu; Mv[i] = 0; }
+                if (b == 0) {
+                    // wildcard rows carry value 0: no vertical step there
+#pragma unroll
+                    for (int i = 0; i < W; ++i) {
+                        int32_t const virt = int32_t(pad) - 32 * i;
+                        Pv[i] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
+                    }
+                    score = int32_t(ROWS) - int32_t(pad);
+                } else {
+                    score = r_sc - int32_t(in_hp >> 31) + int32_t(in_hn >> 31) + ROWS;
+                }
+            }
+            uint32_t const c = reverse ? win0[T.n - uint32_t(j)] : win0[j - 1];
+            uint32_t const* eqrow = peq + c * L.peq_stride + b * W;
+            constexpr int CH = W < 8 ? W : 8;
+            uint32_t hp_prev = in_hp, hn_prev = in_hn;
+            uint32_t carry = in_hn >> 31;            // the adder's carry across a word boundary equals the HN bit there
+#pragma unroll
+            for (int c0 = 0; c0 < W; c0 += CH) {
+                uint32_t Eq[CH], X[CH], Tt[CH], S[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) Eq[i] = eqrow[c0 + i];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) { X[i] = Eq[i] | Mv[c0 + i]; Tt[i] = Eq[i] & Pv[c0 + i]; }
+                if (c0 + CH < W) carry = Chain<CH, true>::run(S, Tt, &Pv[c0], carry);
+                else Chain<CH, false>::run(S, Tt, &Pv[c0], carry);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    uint32_t const pv = Pv[c0 + i], mv = Mv[c0 + i];
+                    uint32_t const D0 = (S[i] ^ pv) | X[i];
+                    uint32_t const HN = pv & D0;
+                    uint32_t const HP = mv | ~(pv | D0);
+                    uint32_t const HPs = __funnelshift_l(hp_prev, HP, 1);
+                    uint32_t const HNs = __funnelshift_l(hn_prev, HN, 1);
+                    Mv[c0 + i] = HPs & D0;
+                    Pv[c0 + i] = HNs | ~(HPs | D0);
+                    hp_prev = HP; hn_prev = HN;
+                    if (TRACE) {
+                        // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
+                        uint32_t* tp = L.trace + T.trace_base + ((uint64_t(t - 1) * G + r) * W + (c0 + i)) * 2;
+                        *reinterpret_cast<uint2*>(tp) = make_uint2(HP, Pv[c0 + i]);
+                    }
+                }
+            }
+            o_hp = hp_prev; o_hn = hn_prev;
+            score += int32_t(hp_prev >> 31) - int32_t(hn_prev >> 31);
+            if (b == nb - 1 && score <= best) { best = score; best_col = uint32_t(j); }
+            if (j == ce) { b += G; set_block(b); }
+        } else {
+            o_hp = 0x80000000u; o_hn = 0;
+        }
+    }
+    // the lane that owned the last block reports
+    uint32_t const owner = (nb - 1) % G;
+    if (have_task && r == owner) {
+        DpResult res; res.score = best; res.end_col = best_col;
+        L.results[T.out] = res;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// traceback over the stored planes + run-length CIGAR (alignment.cpp:156-178 of the reference)
+// ---------------------------------------------------------------------------------------------
+struct WalkTask {
+    uint64_t trace_base;    // as in the DpTask of the trace pass
+    uint64_t ref_base;      // packed-store position of the trace pass' window[0]
+    uint64_t query_base;    // position of query[0] in the byte pool
+    uint32_t n, m;          // sub-window length (== end column) and query length
+    uint32_t group, words;  // G and W of the trace pass
+    uint32_t flags;
+    uint32_t cigar_cap;     // capacity of the per-task scratch (ops)
+    uint64_t scratch_base;  // per-task scratch in the cigar scratch buffer
+    uint32_t out;
+    uint32_t reserved;
+};
+
+struct WalkResult {
+    uint32_t begin_col;     // column where the traceback reached row 0 (sequence1_begin_position)
+    uint32_t cigar_len;     // 0xffffffff on overflow / inconsistency
+    uint64_t cigar_offset;  // position in the compact cigar pool
+};
+
+struct WalkLaunch {
+    const WalkTask* tasks; uint32_t n_tasks;
+    const uint32_t* trace;
+    const uint32_t* ref_packed; const uint32_t* inline_packed;
+    const uint8_t* query_pool;
+    uint32_t* scratch;            // per-task reversed runs
+    uint32_t* cigar_pool;         // compact output
+    unsigned long long* cigar_cursor;
+    uint64_t cigar_pool_cap;
+    WalkResult* results;
+};
+
+// trace priority: left > up > diagonal.  This is the ONE place on the device that encodes it
+// (oracle: FXO_TRACE_PRIORITY in oracle/floxer_oracle.h).
+__global__ void walk_kernel(WalkLaunch const L) {
+    uint32_t const id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= L.n_tasks) return;
+    WalkTask const T = L.tasks[id];
+    const uint32_t* ref = (T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed;
+    uint32_t const W = T.words, G = T.group, ROWS = 32 * W;
+    uint32_t const nb = (T.m + ROWS - 1) / ROWS;
+    uint32_t const pad = nb * ROWS - T.m;
+    uint32_t* const runs = L.scratch + T.scratch_base;
+    uint32_t n_runs = 0;
+    uint32_t cur_op = 0, cur_len = 0;
+    bool bad = false;
+    uint32_t i = T.m, j = T.n;
+    while (i > 0) {
+        uint32_t op;
+        if (j == 0) { op = 1; --i; }                                   // column 0: only "up"
+        else {
+            uint32_t const u = i - 1 + pad;
+            uint32_t const w = u >> 5, bit = u & 31u;
+            uint32_t const blk = w / W, iw = w % W;
+            uint64_t const t = uint64_t(j) + blk;                       // step at which (block, column j) was computed
+            uint2 const hv = *reinterpret_cast<const uint2*>(L.trace + T.trace_base + (((t - 1) * G + blk % G) * W + iw) * 2);
+            if ((hv.x >> bit) & 1u) { op = 2; --j; }                    // left  -> D
+            else if ((hv.y >> bit) & 1u) { op = 1; --i; }               // up    -> I
+            else {                                                     // diagonal -> '=' or X
+                uint32_t const qc = L.query_pool[T.query_base + i - 1];
+                uint32_t const rc = packed_base(ref, T.ref_base + j - 1);
+                op = (qc == rc) ? 7u : 8u;
+                --i; --j;
+            }
+        }
+        if (op == cur_op) ++cur_len;
+        else {
+            if (cur_len) { if (n_runs < T.cigar_cap) runs[n_runs] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
+            cur_op = op; cur_len = 1;
+        }
+    }
+    if (cur_len) { if (n_runs < T.cigar_cap) runs[n_runs] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
+    WalkResult R; R.begin_col = j; R.cigar_len = bad ? 0xffffffffu : n_runs; R.cigar_offset = 0;
+    if (!bad) {
+        unsigned long long const at = atomicAdd(L.cigar_cursor, (unsigned long long)n_runs);
+        if (at + n_runs <= L.cigar_pool_cap) {
+            for (uint32_t p = 0; p < n_runs; ++p) L.cigar_pool[at + p] = runs[n_runs - 1 - p];
+            R.cigar_offset = at;
+        } else {
+            R.cigar_len = 0xffffffffu;
+        }
+    }
+    L.results[T.out] = R;
+}
+
+// ---------------------------------------------------------------------------------------------
+// int32 issue-rate microbenchmark: the 8 LOP3 : 1 IADD3 : 2 SHF mix of one Myers word-step,
+// 8 independent chains per thread so that the pipes, not dependencies, limit the rate.
+// ---------------------------------------------------------------------------------------------
+__global__ void int32_peak_kernel(uint32_t* out, uint32_t iters, uint32_t seed) {
+    uint32_t a[8], b2[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = seed + threadIdx.x * 7 + i; b2[i] = seed * 3 + i * 11 + blockIdx.x; c[i] = ~seed + i; }
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t x = a[i], y = b2[i], z = c[i];
+            uint32_t t0 = (x & y) | z;            // LOP3
+            uint32_t t1 = (x ^ z) & ~y;           // LOP3
+            uint32_t t2 = t0 + t1 + y;            // IADD3
+            uint32_t t3 = (t2 ^ x) | t0;          // LOP3
+            uint32_t t4 = y & t3;                 // LOP3
+            uint32_t t5 = z | ~(y | t3);          // LOP3
+            uint32_t t6 = __funnelshift_l(t4, t5, 1);   // SHF
+            uint32_t t7 = __funnelshift_l(t5, t4, 1);   // SHF
+            uint32_t t8 = t6 & t3;                // LOP3
+            uint32_t t9 = t7 | ~(t6 | t3);        // LOP3
+            uint32_t t10 = (t8 ^ t9) | t1;        // LOP3
+            a[i] = t8; b2[i] = t9; c[i] = t10;
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc ^= a[i] ^ b2[i] ^ c[i];
+    if (acc == 0x12345678u) out[0] = acc;       // keep the result alive without a store in the common case
+}
+
+}  // namespace fxg

@@ -184,6 +184,14 @@ int fxg_verify_reads(fxg_ctx* ctx, const fxg_verify_config* config,
                      const fxg_pex_node* nodes, size_t n_nodes,
                      const fxg_anchor* anchors, size_t n_anchors, fxg_job** out);
 
+/* ---- PEX tree construction (host only; pex::pex_tree::pex_tree, src/lib/pex.cpp:84-256) ----
+ * build_strategy: 0 = recursive (default of the reference), 1 = bottom_up (include/pex.hpp:24-27).
+ * Writes malloc'ed arrays (release with fxg_pex_free): inner[0] is the root when n_inner > 0, otherwise the
+ * single leaf is the root; leaves are in left-to-right order; parent_id indexes inner. */
+int fxg_pex_build(uint64_t total_query_length, uint64_t query_num_errors, uint64_t leaf_max_num_errors,
+                  int build_strategy, fxg_pex_node** inner, size_t* n_inner, fxg_pex_node** leaves, size_t* n_leaves);
+void fxg_pex_free(fxg_pex_node* nodes);
+
 /* ---- accounting / measurement helpers ---- */
 int fxg_get_counters(const fxg_ctx* ctx, fxg_counters* out);
 int fxg_reset_counters(fxg_ctx* ctx);

@@ -1,0 +1,275 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200: run with -m gpu."""
+import numpy as np
+import pytest
+
+import golden_vectors as G
+from floxer_b200 import abi, synthetic
+from floxer_b200.batch import BatchBuilder, VerifyConfig, alignment_records
+from harness import (brute_force_anchors, oracle_align_tasks, oracle_verify_batch, random_align_tasks,
+                     results_as_tuples, revcomp, to_ranks)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from floxer_b200 import build, gpu as g
+    build.build_native()
+    g.lib()
+    return g
+
+
+@pytest.fixture(scope="module")
+def ctx(gpu):
+    c = gpu.Context(0)
+    yield c
+    c.close()
+
+
+# ----------------------------------------------------------------------------- alignment::align
+
+@pytest.mark.parametrize("mode", [abi.MODE_EXISTS, abi.MODE_NO_CIGAR, abi.MODE_CIGAR])
+@pytest.mark.parametrize("m_range,err_range,n_tasks", [
+    ((1, 40), (0.0, 0.3), 400),        # single word, k = 0, tiny queries
+    ((30, 140), (0.0, 0.2), 400),      # 1..5 words: one lane per task
+    ((120, 700), (0.0, 0.15), 300),    # rings of a few lanes
+    ((600, 2500), (0.02, 0.15), 120),  # microbench sizes (config 5)
+    ((2500, 6000), (0.03, 0.12), 24),  # root of a 5 kbp read
+])
+def test_align_matches_oracle(ctx, oracle, mode, m_range, err_range, n_tasks):
+    rng = np.random.default_rng(4242 + 13 * mode + m_range[0])
+    ref, tasks, pool = random_align_tasks(rng, n_tasks, m_range, err_range, mode, ref_len=60_000)
+    ctx.set_references([ref])
+    res, cig = ctx.align_batch(tasks, pool)
+    got = results_as_tuples(res, cig, tasks)
+    want = oracle_align_tasks(oracle, ref, tasks, pool)
+    bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert not bad, (bad[:5], [(got[i], want[i], tasks[i]) for i in bad[:2]])
+    assert (res["orientation"] == tasks["orientation"]).all()
+
+
+def test_align_inline_reference_and_all_ranks(ctx, oracle):
+    """Spans handed over as host bytes (the alignment::align shim) with ranks 0..5 incl. N == N matches."""
+    rng = np.random.default_rng(7)
+    v = G.ALIGNMENT_SMALL                                    # test/alignment_test.cpp:7-30
+    refs_inline = [np.array(v["reference"], dtype=np.uint8)]
+    queries = [np.array(v["query"], dtype=np.uint8)]
+    ks = [v["max_errors"]]
+    for _ in range(200):
+        n = int(rng.integers(5, 400))
+        r = rng.integers(0, 6, size=n, dtype=np.uint8)
+        m = int(rng.integers(1, n + 10))
+        q = rng.integers(0, 6, size=m, dtype=np.uint8)
+        if rng.random() < 0.6 and m <= n:                    # plant a noisy copy
+            at = int(rng.integers(0, n - m + 1))
+            q = r[at:at + m].copy()
+            flips = rng.integers(0, m, size=int(rng.integers(0, max(1, m // 8) + 1)))
+            q[flips] = rng.integers(0, 6, size=len(flips), dtype=np.uint8)
+        refs_inline.append(r); queries.append(q); ks.append(int(rng.integers(0, max(2, m // 5))))
+    ipool = np.concatenate(refs_inline); qpool = np.concatenate(queries)
+    roff = np.concatenate([[0], np.cumsum([len(r) for r in refs_inline])])
+    qoff = np.concatenate([[0], np.cumsum([len(q) for q in queries])])
+    for mode in (abi.MODE_EXISTS, abi.MODE_NO_CIGAR, abi.MODE_CIGAR):
+        tasks = np.array([(roff[i], 1000 + i, qoff[i], len(refs_inline[i]), len(queries[i]), abi.REF_INLINE, ks[i], mode, i & 1, (0,) * 6)
+                          for i in range(len(queries))], dtype=abi.ALIGN_TASK_DTYPE)
+        res, cig = ctx.align_batch(tasks, qpool, ipool)
+        got = results_as_tuples(res, cig, tasks)
+        want = oracle_align_tasks(oracle, ipool, tasks, qpool)
+        assert got == want
+    # the golden vector itself
+    assert got[0] == (True, v["num_errors"], 1000 + v["start"], v["cigar"])
+
+
+def test_rejects_bad_input(ctx, gpu):
+    ref = np.ones(100, dtype=np.uint8)
+    ctx.set_references([ref])
+    q = np.ones(10, dtype=np.uint8)
+    bad_mode = np.array([(0, 0, 0, 50, 10, 0, 1, 3, 0, (0,) * 6)], dtype=abi.ALIGN_TASK_DTYPE)
+    with pytest.raises(gpu.FloxerGpuError):
+        ctx.align_batch(bad_mode, q)
+    outside = np.array([(90, 90, 0, 50, 10, 0, 1, 0, 0, (0,) * 6)], dtype=abi.ALIGN_TASK_DTYPE)
+    with pytest.raises(gpu.FloxerGpuError):
+        ctx.align_batch(outside, q)
+    q_bad = q.copy(); q_bad[3] = 9
+    ok = np.array([(0, 0, 0, 50, 10, 0, 1, 0, 0, (0,) * 6)], dtype=abi.ALIGN_TASK_DTYPE)
+    with pytest.raises(gpu.FloxerGpuError):
+        ctx.align_batch(ok, q_bad)
+    res, _ = ctx.align_batch(ok, q)
+    assert res["exists"][0] == 1
+    empty = np.zeros(0, dtype=abi.ALIGN_TASK_DTYPE)
+    res, cig = ctx.align_batch(empty, q)
+    assert len(res) == 0 and len(cig) == 0
+
+
+# ----------------------------------------------------------------------------- query_verifier::verify
+
+def _one_read_batch(fwd, rc, inner, leaves, af, ar):
+    bb = BatchBuilder()
+    bb.add(fwd, rc, inner, leaves, np.array(af, dtype=abi.ANCHOR_DTYPE), np.array(ar, dtype=abi.ANCHOR_DTYPE))
+    return bb.build()
+
+
+def test_golden_verify(ctx, gpu):
+    # test/verification_test.cpp:11-123 through the GPU path
+    V = G.VERIFY
+    ref = np.array(G.VERIFY_REFERENCE, dtype=np.uint8)
+    q = np.array(G.VERIFY_QUERY, dtype=np.uint8)
+    t = V["tree"]
+    inner, leaves = gpu.pex_build(t["total_len"], t["num_errors"], t["leaf_max_errors"], 1)
+    a = V["anchor"]
+    anchor = (a["pex_leaf_index"], a["reference_id"], a["reference_position"], a["num_errors"])
+    ctx.set_references([ref])
+    e = V["expected"]
+    # the test verifies with orientation reverse_complement: put the query into the reverse pool
+    batch = _one_read_batch(q, q, inner, leaves, [], [anchor, anchor])
+    cfg = VerifyConfig(interval_optimization=True, extra_verification_ratio=V["extra_verification_ratio"])
+    job = ctx.verify_reads(batch, cfg)
+    al, cg = job.alignments()
+    assert alignment_records(al, cg) == [(0, 0, e["start"], e["num_errors"], e["orientation"], e["cigar"])]
+    assert job.stats()["n_avoided_root"] == 1              # second verify() is a no-op (:84-87)
+    direct = VerifyConfig(verification_kind=abi.KIND_DIRECT_FULL, interval_optimization=False,
+                          extra_verification_ratio=V["extra_verification_ratio"])
+    al, cg = ctx.verify_reads(_one_read_batch(q, q, inner, leaves, [], [anchor]), direct).alignments()
+    assert alignment_records(al, cg) == [(0, 0, e["start"], e["num_errors"], e["orientation"], e["cigar"])]
+    q2 = q.copy()
+    for pos, val in V["mutations"].items():
+        q2[pos] = val
+    al, cg = ctx.verify_reads(_one_read_batch(q2, q2, inner, leaves, [], [anchor]), direct).alignments()
+    assert len(al) == 0
+
+
+def test_golden_single_node(ctx):
+    # test/verification_test.cpp:163-261
+    n = G.NODE
+    ref = np.array(G.NODE_REFERENCE, dtype=np.uint8)
+    q = np.array(G.NODE_QUERY, dtype=np.uint8)
+    ctx.set_references([ref])
+    def task(mode, pool):
+        return np.array([(n["span_offset"], n["span_offset"], n["node_from"], n["span_length"],
+                          n["node_to"] - n["node_from"] + 1, 0, n["num_errors"], mode, 0, (0,) * 6)], dtype=abi.ALIGN_TASK_DTYPE)
+    res, _ = ctx.align_batch(task(abi.MODE_CIGAR, q), q)
+    assert res["exists"][0] and res["num_errors"][0] == n["expected"]["num_errors"]
+    assert res["start_in_reference"][0] == n["expected"]["start"]
+    res, _ = ctx.align_batch(task(abi.MODE_EXISTS, q), q)
+    assert res["exists"][0] == 1
+    pos, val = n["extra_mismatch"]
+    q2 = q.copy(); q2[pos] = val
+    res, _ = ctx.align_batch(task(abi.MODE_EXISTS, q2), q2)
+    assert res["exists"][0] == 0
+
+
+@pytest.mark.parametrize("seed_errors", G.WHOLE_FLAGS["seed_errors"])
+def test_golden_whole_program_fixture(ctx, gpu, oracle, seed_errors):
+    # config 1: test/floxer_whole_program_via_cli_test.cpp:47-93 (seeding replaced by the brute-force stand-in)
+    refs = [to_ranks(s) for s in G.WHOLE_REFERENCES.values()]
+    ctx.set_references(refs)
+    F = G.WHOLE_FLAGS
+    bb = BatchBuilder()
+    names = list(G.WHOLE_QUERIES)
+    for qid in names:
+        fwd = to_ranks(G.WHOLE_QUERIES[qid]); rc = revcomp(fwd)
+        inner, leaves = gpu.pex_build(len(fwd), F["query_errors"], seed_errors, 0)
+        bb.add(fwd, rc, inner, leaves,
+               np.array(brute_force_anchors(fwd, leaves, refs), dtype=abi.ANCHOR_DTYPE),
+               np.array(brute_force_anchors(rc, leaves, refs), dtype=abi.ANCHOR_DTYPE))
+    batch = bb.build()
+    cfg = VerifyConfig(interval_optimization=F["interval_optimization"], extra_verification_ratio=F["extra_verification_ratio"])
+    job = ctx.verify_reads(batch, cfg)
+    al, cg = job.alignments()
+    recs = alignment_records(al, cg)
+    want, want_stats = oracle_verify_batch(oracle, refs, batch, cfg)
+    assert recs == want and job.stats() == want_stats
+    by_query = {q: [r for r in recs if names[r[0]] == q] for q in names}
+    for qid in G.WHOLE_UNMAPPED:
+        assert by_query[qid] == []
+    for (qid, rev), (lo, hi, nm, cigar) in G.WHOLE_EXPECT.items():
+        rs = [r for r in by_query[qid] if bool(r[4]) == rev]
+        assert rs
+        for _, ref_id, start, errs, _, cig in rs:
+            assert ref_id == 0 and lo <= start <= hi and errs == nm and cig == cigar
+
+
+CONFIGS = [
+    VerifyConfig(interval_optimization=False),
+    VerifyConfig(interval_optimization=True),
+    VerifyConfig(interval_optimization=True, without_cigar=True),
+    VerifyConfig(interval_optimization=False, without_cigar=True),
+    VerifyConfig(verification_kind=abi.KIND_DIRECT_FULL, interval_optimization=False),
+    VerifyConfig(verification_kind=abi.KIND_DIRECT_FULL, interval_optimization=True),
+    VerifyConfig(interval_optimization=True, extra_verification_ratio=0.4),
+    VerifyConfig(interval_optimization=True, extra_verification_ratio=0.0),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_verify_reads_matches_oracle(ctx, gpu, oracle, cfg):
+    refs = [synthetic.random_reference(80_000, 21), synthetic.random_reference(30_000, 22)]
+    ctx.set_references(refs)
+    batch = synthetic.make_batch(refs, 10, 900, 0.07, 123, gpu.pex_build, seed_errors=1, decoy_fraction=0.4)
+    job = ctx.verify_reads(batch, cfg)
+    al, cg = job.alignments()
+    want, want_stats = oracle_verify_batch(oracle, refs, batch, cfg)
+    assert alignment_records(al, cg) == want
+    assert job.stats() == want_stats
+    assert len(want) > 0
+
+
+@pytest.mark.parametrize("bottom_up", [False, True])
+def test_verify_reads_repeats_and_dense_anchors(ctx, gpu, oracle, bottom_up):
+    """Repeat-seeded reference, many overlapping anchors per locus: stresses the interval-dependency scheduler."""
+    ref = synthetic.plant_repeats(synthetic.random_reference(120_000, 31), 32, families=6, unit=(300, 900), copies=(3, 8))
+    refs = [ref]
+    ctx.set_references(refs)
+    batch = synthetic.make_batch(refs, 8, 1200, 0.05, 77, gpu.pex_build, seed_errors=2, decoy_fraction=0.6, bottom_up=bottom_up)
+    # add shifted duplicates of every anchor so that root windows nest in both directions
+    rng = np.random.default_rng(3)
+    bb = BatchBuilder()
+    for R in batch.reads:
+        no, ni, nl = int(R["node_offset"]), int(R["num_inner"]), int(R["num_leaves"])
+        qo, ql = int(R["query_offset"]), int(R["query_len"])
+        ao, af, ar = int(R["anchor_offset"]), int(R["num_anchors_forward"]), int(R["num_anchors_reverse"])
+        def densify(a):
+            out = []
+            for x in a:
+                out.append(tuple(int(v) for v in x))
+                if rng.random() < 0.7:
+                    shift = int(rng.integers(-60, 61))
+                    out.append((int(x[0]), int(x[1]), max(0, min(len(ref) - 1, int(x[2]) + shift)), int(x[3])))
+            return np.array(sorted(out), dtype=abi.ANCHOR_DTYPE)
+        bb.add(batch.forward_pool[qo:qo + ql], batch.reverse_pool[qo:qo + ql], batch.nodes[no:no + ni], batch.nodes[no + ni:no + ni + nl],
+               densify(batch.anchors[ao:ao + af]), densify(batch.anchors[ao + af:ao + af + ar]))
+    dense = bb.build()
+    for cfg in (VerifyConfig(interval_optimization=True), VerifyConfig(interval_optimization=False)):
+        job = ctx.verify_reads(dense, cfg)
+        al, cg = job.alignments()
+        want, want_stats = oracle_verify_batch(oracle, refs, dense, cfg)
+        assert alignment_records(al, cg) == want
+        assert job.stats() == want_stats
+
+
+def test_config2_shape_against_cpu_port(ctx, gpu):
+    """5 kbp reads at 5 % (config 2 shape, fewer reads): the bit-vector CPU port (itself checked against the
+    oracle in the CPU suite) is the checker at this size."""
+    from oracle import cpu_baseline
+    refs = [synthetic.random_reference(2_000_000, 20240001)]
+    ctx.set_references(refs)
+    batch = synthetic.make_batch(refs, 6, 5000, 0.05, 9, gpu.pex_build, seed_errors=2, decoy_fraction=0.2)
+    for cfg in (VerifyConfig(interval_optimization=False), VerifyConfig(interval_optimization=True)):
+        job = ctx.verify_reads(batch, cfg)
+        al, cg = job.alignments()
+        wal, wcg, wstats = cpu_baseline.verify_reads(refs, batch, cfg, threads=8)
+        assert alignment_records(al, cg) == alignment_records(wal, wcg)
+        assert job.stats() == wstats
+        assert len(al) > 0
+
+
+def test_staged_run_is_repeatable(ctx, gpu):
+    refs = [synthetic.random_reference(100_000, 41)]
+    ctx.set_references(refs)
+    batch = synthetic.make_batch(refs, 4, 1500, 0.06, 5, gpu.pex_build)
+    job = ctx.stage_verify(batch, VerifyConfig())
+    a1 = job.run().alignments()
+    a2 = job.run().alignments()
+    assert np.array_equal(a1[0], a2[0]) and np.array_equal(a1[1], a2[1]) and len(a1[0]) > 0
+    c = ctx.counters()
+    assert c["kernel_launches"] > 0 and c["dp_word_steps"] > 0
