@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- PEX hierarchical verification throughput (BASELINE.json metric) on N B200s of one node.
+
+One "step" = one pass of the hot path over one batch of synthetic reads (config 2 of BASELINE.json:
+10 Mbp random reference, 1 000 simulated 5 kbp reads at 5 % error, floxer defaults) per GPU.  Reads shard
+across ranks with no data-path collective (weak scaling: every rank verifies its own 1 000-read batch).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference [...]                         CPU arm: the multithreaded CPU port of the
+                                                                 reference path (the reference binary cannot be
+                                                                 built offline) on a bounded sample
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (reference length, reads per GPU, read length, error rate, reference seed, read seed)
+    "config2": dict(ref_len=10_000_000, reads=1000, read_len=5000, error=0.05, ref_seed=20240001, read_seed=20240003),
+    "config2_small": dict(ref_len=2_000_000, reads=64, read_len=5000, error=0.05, ref_seed=20240001, read_seed=20240003),
+}
+MYERS_INSTR_PER_WORD_STEP = 11          # minimal LOP3/IADD3/SHF sequence of one 32-cell word-step
+
+
+def make_workload(name: str, rank: int, pex_build):
+    from floxer_b200 import synthetic
+    w = WORKLOADS[name]
+    refs = [synthetic.random_reference(w["ref_len"], w["ref_seed"])]
+    batch = synthetic.make_batch(refs, w["reads"], w["read_len"], w["error"], w["read_seed"] + 1000 * rank, pex_build,
+                                 seed_errors=2, decoy_fraction=0.25)
+    return refs, batch
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_sample_size(refs, batch, cfg, threads: int, target_s: float = 12.0) -> int:
+    """Sizes the CPU sample to about `target_s` seconds of wall time from a short probe."""
+    from oracle import cpu_baseline
+    probe = batch.slice(0, min(len(batch), max(4, threads // 2)))
+    t0 = time.perf_counter()
+    cpu_baseline.verify_reads(refs, probe, cfg, threads=threads)
+    rate = len(probe) / max(time.perf_counter() - t0, 1e-6)
+    return int(max(min(len(batch), rate * target_s), min(len(batch), threads)))
+
+
+def cpu_arm(refs, batch, cfg, sample_reads: int, threads: int, repeats: int = 1):
+    """Times the multithreaded CPU port on the first `sample_reads` reads; returns (seconds, stats)."""
+    from oracle import cpu_baseline
+    if not sample_reads:
+        sample_reads = cpu_sample_size(refs, batch, cfg, threads)
+    sample = batch.slice(0, min(sample_reads, len(batch)))
+    best, stats = None, None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        _, _, stats = cpu_baseline.verify_reads(refs, sample, cfg, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, stats, len(sample)
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--interval-optimization", action="store_true", help="floxer --interval-optimization (off by default, as in the reference)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU sample (0 = sized automatically)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+
+    from floxer_b200.batch import VerifyConfig
+    cfg = VerifyConfig(interval_optimization=args.interval_optimization)
+    W = WORKLOADS[args.workload]
+    config = {"workload": f"{args.workload}: {W['ref_len']} bp uniform random reference, {W['reads']} simulated reads x "
+                          f"{W['read_len']} bp at {int(W['error'] * 100)} % error per GPU, recursive PEX tree, seed errors 2, "
+                          f"hierarchical verification, interval optimization {'on' if cfg.interval_optimization else 'off'}, "
+                          f"extra verification ratio 0.05, CIGAR output; anchors from the ground-truth stand-in seeder",
+              "reads_per_gpu": W["reads"], "read_len": W["read_len"], "error_rate": W["error"],
+              "l2": "L2 flushed (256 MiB write) before every timed step"}
+
+    # ------------------------------------------------------------------ CPU arm ("reference")
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from floxer_b200 import build
+        from floxer_b200 import gpu as g          # host-side PEX builder only (no device needed)
+        build.build_native()
+        refs, batch = make_workload(args.workload, 0, g.pex_build)
+        n_sample = args.cpu_sample_reads or cpu_sample_size(refs, batch, cfg, threads, target_s=10.0)
+        times, stats = [], None
+        for _ in range(max(args.steps, 1)):
+            dt, stats, n_used = cpu_arm(refs, batch, cfg, n_sample, threads)
+            times.append(dt)
+        sec = sum(times) / len(times)
+        cells = stats["cells_inner"] + stats["cells_root"]
+        gcups = cells / sec / 1e9
+        line = {"impl": "reference", "metric": "pex_verification_gcups", "value": gcups, "unit": "GCUPS",
+                "reads_per_s": n_used / sec, "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port",
+                                 "sample": f"first {n_used} reads of the workload per step, all anchors, both strands, CIGARs",
+                                 "reads_per_s": n_used / sec},
+                "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "CPU port of floxer 0.2.0 + SeqAn3 edit-distance path (oracle/cpu_baseline.c); the reference binary "
+                        "cannot be built offline"}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from floxer_b200 import build
+    from floxer_b200 import gpu as g
+    build.build_native()
+    refs, batch = make_workload(args.workload, rank, g.pex_build)
+    ctx = g.Context(local_rank)
+    ctx.set_references(refs)
+    int32_peak = ctx.measure_int32_peak()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident arm: inputs staged once, each step = fxg_verify_run ----
+    job = ctx.stage_verify(batch, cfg)
+    for _ in range(args.warmup):
+        job.run()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms, kernel_ms, launches = [], [], 0
+    ctr0 = None
+    barrier()
+    ctx.reset_counters()
+    t_all0 = time.perf_counter()
+    for it in range(args.steps):
+        flush.fill_(it & 0xff)
+        torch.cuda.synchronize()
+        c0 = ctx.counters()
+        t0 = time.perf_counter()
+        job.run()
+        step_ms.append((time.perf_counter() - t0) * 1e3)
+        c1 = ctx.counters()
+        kernel_ms.append(c1["run_ms"] - c0["run_ms"])
+    barrier()
+    _ = time.perf_counter() - t_all0
+    ctr = ctx.counters()
+    clocks = sampler.stop()
+    stats = job.stats()
+    al, cg = job.alignments()
+    n_alignments = len(al)
+    job.free()
+
+    # ---- end-to-end arm: host buffers in, alignments + CIGARs out, every step ----
+    ctx.reset_counters()
+    e2e_ms = []
+    for it in range(max(1, min(args.steps, 3))):
+        flush.fill_(it & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        j2 = ctx.verify_reads(batch, cfg)
+        a2, c2 = j2.alignments()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        j2.free()
+    e2e_ctr = ctx.counters()
+    n_e2e = len(e2e_ms)
+
+    # max over ranks
+    my = torch.tensor([sum(step_ms), sum(e2e_ms) / n_e2e * args.steps, sum(kernel_ms)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(my, op=dist.ReduceOp.MAX)
+    total_ms, e2e_total_ms, dev_ms = [float(x) for x in my.cpu()]
+    cells_step = stats["cells_inner"] + stats["cells_root"]
+    units = torch.tensor([cells_step, len(batch)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    cells_all, reads_all = [float(x) for x in units.cpu()]
+
+    ms_per_step = total_ms / args.steps
+    gcups = cells_all / (ms_per_step * 1e-3) / 1e9
+    e2e_ms_per_step = e2e_total_ms / args.steps
+    e2e_gcups = cells_all / (e2e_ms_per_step * 1e-3) / 1e9
+
+    line = None
+    if rank == 0:
+        # roofline of the dominant kernel (the bit-vector DP engine): integer-ALU bound, SURVEY 8(d)
+        dp_s = ctr["dp_kernel_ms"] * 1e-3
+        ws = ctr["dp_word_steps"]
+        achieved = ws * MYERS_INSTR_PER_WORD_STEP / dp_s if dp_s > 0 else 0.0
+        roofline = {"bound": "int32_alu", "achieved": achieved / 1e9, "peak": int32_peak / 1e9, "unit": "Ginstr/s",
+                    "frac": achieved / int32_peak if int32_peak else None, "traffic": None,
+                    "kernel": "fxg::dp_kernel<W,false> (all launches of the timed region)",
+                    "how": "algorithmic 11 int32 instr per 32-cell word-step x word-steps issued (band-limited) / CUDA-event time "
+                           "of the DP launches; peak = LOP3/IADD3/SHF 8:1:2 issue-rate microbenchmark on this GPU in this run",
+                    "dp_word_steps_per_step": ws / args.steps, "cells_computed_per_step": ws * 32 / args.steps,
+                    "cells_full_matrix_per_step": cells_step,
+                    "dp_kernel_ms_per_step": ctr["dp_kernel_ms"] / args.steps,
+                    "trace_kernel_ms_per_step": ctr["trace_kernel_ms"] / args.steps,
+                    "trace_gb_per_s": (ctr["trace_bytes"] / 1e9) / (ctr["trace_kernel_ms"] * 1e-3) if ctr["trace_kernel_ms"] else None,
+                    "hbm_peak_gb_per_s": _measured_peak("hbm_gbs")}
+        cpu_sec, cpu_stats, n_used = cpu_arm(refs, batch, cfg, args.cpu_sample_reads, threads)
+        cpu_cells = cpu_stats["cells_inner"] + cpu_stats["cells_root"]
+        line = {"metric": "pex_verification_gcups", "value": gcups, "unit": "GCUPS", "reads_per_s": reads_all / (ms_per_step * 1e-3),
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": config,
+                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+                "e2e": {"value": e2e_gcups, "unit": "GCUPS", "reads_per_s": reads_all / (e2e_ms_per_step * 1e-3),
+                        "ms_per_step": e2e_ms_per_step,
+                        "h2d_bytes_per_step": e2e_ctr["h2d_bytes"] // n_e2e, "d2h_bytes_per_step": e2e_ctr["d2h_bytes"] // n_e2e},
+                "gpu_launches": int(ctr["kernel_launches"]),
+                "roofline": roofline,
+                "cpu_baseline": {"value": cpu_cells / cpu_sec / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
+                                 "sample": f"first {n_used} reads of rank 0's batch, all anchors, both strands, CIGARs",
+                                 "reads_per_s": n_used / cpu_sec},
+                "device_ms_per_step": dev_ms / args.steps,
+                "waves_per_step": ctr["waves"] / args.steps,
+                "alignments_per_step": n_alignments,
+                "stats_per_step": stats}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def _measured_peak(key: str):
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f).get(key)
+    except (OSError, ValueError):
+        return None
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -55,7 +55,8 @@ class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("dp_tasks", C.c_uint64), ("dp_word_steps", C.c_uint64),
                 ("dp_cells_full", C.c_uint64), ("trace_bytes", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("dp_kernel_ms", C.c_double), ("trace_kernel_ms", C.c_double), ("waves", C.c_uint64)]
+                ("dp_kernel_ms", C.c_double), ("trace_kernel_ms", C.c_double), ("waves", C.c_uint64),
+                ("run_ms", C.c_double)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

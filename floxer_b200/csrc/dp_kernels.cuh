@@ -25,6 +25,7 @@ constexpr int kPeqBackPadWords = 66;
 constexpr uint32_t kFlagReverse = 1u;   // run on reversed views (alignment.cpp:118-125)
 constexpr uint32_t kFlagInlineRef = 2u; // window comes from the per-batch inline pool
 constexpr int32_t kNoScore = 0x3fffffff;
+constexpr uint32_t kWalkPrefetch = 24;  // traceback steps between a prefetch and the use of its line
 
 // One bit-vector DP pass.  All coordinates are in bases.
 struct DpTask {
@@ -383,7 +384,15 @@ __global__ void walk_kernel(WalkLaunch const L) {
             uint32_t const w = u >> 5, bit = u & 31u;
             uint32_t const blk = w / W, iw = w % W;
             uint64_t const t = uint64_t(j) + blk;                       // step at which (block, column j) was computed
-            uint2 const hv = *reinterpret_cast<const uint2*>(L.trace + T.trace_base + (((t - 1) * G + blk % G) * W + iw) * 2);
+            const uint32_t* const cell = L.trace + T.trace_base + (((t - 1) * G + blk % G) * W + iw) * 2;
+            // the path hugs a diagonal: fetch the lines it will need kPrefetch steps from now into L2 already
+            if (i > kWalkPrefetch && j > kWalkPrefetch) {
+                uint32_t const u2 = u - kWalkPrefetch, w2 = u2 >> 5, blk2 = w2 / W;
+                uint64_t const t2 = uint64_t(j - kWalkPrefetch) + blk2;
+                const uint32_t* const ahead = L.trace + T.trace_base + (((t2 - 1) * G + blk2 % G) * W + w2 % W) * 2;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead));
+            }
+            uint2 const hv = *reinterpret_cast<const uint2*>(cell);
             if ((hv.x >> bit) & 1u) { op = 2; --j; }                    // left  -> D
             else if ((hv.y >> bit) & 1u) { op = 1; --i; }               // up    -> I
             else {                                                     // diagonal -> '=' or X

@@ -138,6 +138,7 @@ typedef struct {
     double dp_kernel_ms;             /* CUDA-event time of the DP kernels on the context's stream */
     double trace_kernel_ms;          /* CUDA-event time of trace-store + walk kernels */
     uint64_t waves;                  /* host scheduling rounds of fxg_verify_* */
+    double run_ms;                   /* CUDA-event time from the first to the last device operation of *_run calls */
 } fxg_counters;
 
 /* ---- life cycle ---- */
