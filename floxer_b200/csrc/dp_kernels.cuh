@@ -173,6 +173,83 @@ template <bool COUT> struct Chain<8, COUT> {
     }
 };
 
+// Per-lane state of the ring.  Everything lives in registers (all loops over W are unrolled).
+template <int W>
+struct LaneState {
+    uint32_t Pv[W], Mv[W];      // vertical +1 / -1 deltas of the W words of the current block
+    uint32_t b;                 // current block
+    int32_t cs, ce;             // its active column range (cs > ce: none)
+    uint32_t o_hp, o_hn;        // HP / HN of the block's last word after the latest step (bit 31 = bottom row)
+    int32_t score;              // value of the block's bottom row after the latest step
+    int32_t best;               // last block only: minimum of the last row so far ...
+    uint32_t best_col;          // ... and the rightmost column attaining it
+    const uint8_t* wp;          // next window character of this lane
+    const uint32_t* eqb;        // Eq rows of the current block (symbol 0)
+};
+
+template <int W>
+__device__ __forceinline__ void load_eq(uint32_t (&Eq)[W], const uint32_t* row) {
+    if constexpr (W % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < W; i += 4) {
+            uint4 const v = *reinterpret_cast<const uint4*>(row + i);
+            Eq[i] = v.x; Eq[i + 1] = v.y; Eq[i + 2] = v.z; Eq[i + 3] = v.w;
+        }
+    } else if constexpr (W == 2) {
+        uint2 const v = *reinterpret_cast<const uint2*>(row);
+        Eq[0] = v.x; Eq[1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) Eq[i] = row[i];
+    }
+}
+
+// One column of one block: the Myers/Hyyroe word-step over W words with the carries of the block above.
+// FIRST: some lane of the warp may be on block 0 (whose upper boundary is row 0: no carries);
+// LAST:  some lane may be on the last block (track the minimum of the last row).
+template <int W, bool TRACE, bool FIRST, bool LAST>
+__device__ __forceinline__ void block_step(LaneState<W>& S, uint32_t r_hp, uint32_t r_hn, uint32_t t, uint32_t peq_stride,
+                                           uint32_t last_block, uint32_t* trace_row) {
+    uint32_t in_hp = r_hp, in_hn = r_hn;
+    if (FIRST && S.b == 0) { in_hp = 0; in_hn = 0; }      // row 0 of a semi-global matrix is all zeros
+    uint32_t const c = *S.wp++;
+    const uint32_t* const eqrow = S.eqb + c * peq_stride;
+    uint32_t Eq[W];
+    load_eq<W>(Eq, eqrow);
+    constexpr int CH = W < 8 ? W : 8;
+    uint32_t hp_prev = in_hp, hn_prev = in_hn;
+    uint32_t carry = in_hn >> 31;                         // the adder's carry across a word boundary equals the HN bit there
+#pragma unroll
+    for (int c0 = 0; c0 < W; c0 += CH) {
+        uint32_t X[CH], Tt[CH], Sm[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) { X[i] = Eq[c0 + i] | S.Mv[c0 + i]; Tt[i] = Eq[c0 + i] & S.Pv[c0 + i]; }
+        if (c0 + CH < W) carry = Chain<CH, true>::run(Sm, Tt, &S.Pv[c0], carry);
+        else Chain<CH, false>::run(Sm, Tt, &S.Pv[c0], carry);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            uint32_t const pv = S.Pv[c0 + i], mv = S.Mv[c0 + i];
+            uint32_t const D0 = (Sm[i] ^ pv) | X[i];
+            uint32_t const HN = pv & D0;
+            uint32_t const HP = mv | ~(pv | D0);
+            uint32_t const HPs = __funnelshift_l(hp_prev, HP, 1);
+            uint32_t const HNs = __funnelshift_l(hn_prev, HN, 1);
+            S.Mv[c0 + i] = HPs & D0;
+            S.Pv[c0 + i] = HNs | ~(HPs | D0);
+            hp_prev = HP; hn_prev = HN;
+            if (TRACE) {
+                // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
+                *reinterpret_cast<uint2*>(trace_row + (c0 + i) * 2) = make_uint2(HP, S.Pv[c0 + i]);
+            }
+        }
+    }
+    S.o_hp = hp_prev; S.o_hn = hn_prev;
+    S.score += int32_t(hp_prev >> 31) - int32_t(hn_prev >> 31);
+    if (LAST) {
+        if (S.b == last_block && S.score <= S.best) { S.best = S.score; S.best_col = t - S.b; }
+    }
+}
+
 template <int W, bool TRACE>
 __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -198,7 +275,8 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     int32_t const dlo = T.dlo - int32_t(pad), dhi = T.dhi - int32_t(pad);
     bool const reverse = (T.flags & kFlagReverse) != 0;
 
-    // ---- stage the window: 32 bases (16 bytes packed) per lane and iteration ----
+    // ---- stage the window: 32 bases (16 bytes packed) per lane and iteration.  Reverse passes
+    //      (alignment.cpp:118-125) store the window back to front so that the sweep below is always forward.
     uint32_t const phase = uint32_t(T.ref_base & 31u);
     if (have_task) {
         const uint4* src = reinterpret_cast<const uint4*>((T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed) + (T.ref_base >> 5);
@@ -207,8 +285,17 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
             uint4 const v = __ldg(src + c);
             uint4 a, b2;
             unpack8(v.x, a.x, a.y); unpack8(v.y, a.z, a.w); unpack8(v.z, b2.x, b2.y); unpack8(v.w, b2.z, b2.w);
-            uint4* dst = reinterpret_cast<uint4*>(win + c * 32);
-            dst[0] = a; dst[1] = b2;
+            if (!reverse) {
+                uint4* dst = reinterpret_cast<uint4*>(win + c * 32);
+                dst[0] = a; dst[1] = b2;
+            } else {
+                uint32_t const words[8] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    int32_t const idx = int32_t(c * 32 + e) - int32_t(phase);            // window index of this base
+                    if (idx >= 0 && idx < int32_t(T.n)) win[T.n - 1 - uint32_t(idx)] = uint8_t(words[e >> 2] >> (8 * (e & 3)));
+                }
+            }
         }
         // ---- stage the Eq table of the query piece from the pool-level Peq planes ----
         uint32_t const n_words = nb * W;
@@ -231,98 +318,95 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     }
     __syncwarp();
 
-    // ---- per-lane block state ----
-    uint32_t Pv[W], Mv[W];
-    uint32_t b = r;                                  // current block
-    int32_t cs, ce;                                  // active column range of block b
+    uint8_t const* const win0 = reverse ? win : win + phase;   // character of column j is win0[j - 1]
+    uint32_t const last_block = nb - 1;
+    LaneState<W> S;
+#pragma unroll
+    for (int i = 0; i < W; ++i) { S.Pv[i] = 0; S.Mv[i] = 0; }
+    S.b = r; S.o_hp = 0x80000000u; S.o_hn = 0;      // an idle lane publishes "the boundary grows by +1 per column"
+    S.score = 0; S.best = kNoScore; S.best_col = 0;
+    S.wp = win0; S.eqb = peq;
     auto set_block = [&](uint32_t blk) {
-        if (!have_task || blk >= nb) { cs = 0x7fffffff; ce = -1; return; }
+        S.cs = 0x7fffffff; S.ce = -1;
+        if (!have_task || blk >= nb) return;
         int64_t const lo = int64_t(ROWS) * blk + 1 + dlo;
         int64_t const hi = int64_t(ROWS) * (blk + 1) + dhi;
-        cs = lo < 1 ? 1 : (lo > 0x7ffffffe ? 0x7fffffff : int32_t(lo));
-        ce = hi > int64_t(T.n) ? int32_t(T.n) : int32_t(hi);
-        if (cs > ce) { cs = 0x7fffffff; ce = -1; }
+        int32_t const cs = lo < 1 ? 1 : (lo > 0x7ffffffe ? 0x7fffffff : int32_t(lo));
+        int32_t const ce = hi > int64_t(T.n) ? int32_t(T.n) : int32_t(hi);
+        if (cs <= ce) { S.cs = cs; S.ce = ce; }
     };
-    set_block(b);
-
-    uint32_t o_hp = 0x80000000u, o_hn = 0;           // what an idle lane publishes: the boundary grows by +1 per column
-    int32_t score = 0;
-    int32_t best = kNoScore; uint32_t best_col = 0;
+    set_block(S.b);
     uint32_t const src_lane = slot * G + (r + G - 1) % G;
 
     // number of steps of this warp: last block of the longest task
-    uint32_t my_end = have_task ? (T.n + nb - 1) : 0;
-    for (int off = 16; off > 0; off >>= 1) my_end = max(my_end, __shfl_xor_sync(0xffffffffu, my_end, off));
+    uint32_t const my_end = __reduce_max_sync(0xffffffffu, have_task ? (T.n + nb - 1) : 0u);
+    constexpr uint32_t kNever = 0x7fffffffu;
 
-    uint8_t const* const win0 = win + phase;
-    for (uint32_t t = 1; t <= my_end; ++t) {
-        uint32_t const r_hp = __shfl_sync(0xffffffffu, o_hp, src_lane);
-        uint32_t const r_hn = __shfl_sync(0xffffffffu, o_hn, src_lane);
-        int32_t const r_sc = __shfl_sync(0xffffffffu, score, src_lane);
-        int32_t const j = int32_t(t) - int32_t(b);
-        if (j >= cs && j <= ce) {
-            uint32_t in_hp = r_hp, in_hn = r_hn;
-            if (b == 0) { in_hp = 0; in_hn = 0; }    // row 0 of a semi-global matrix is all zeros
-            if (j == cs) {
-                // (re)start: column cs-1 of this block is (bottom of the block above at cs-1) + 1, 2, ...
+    uint32_t t = 1;
+    while (t <= my_end) {
+        // ---------------- event step: block starts / ends are handled here, with every check in place ----------------
+        {
+            uint32_t const r_hp = __shfl_sync(0xffffffffu, S.o_hp, src_lane);
+            uint32_t const r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);
+            int32_t const r_sc = __shfl_sync(0xffffffffu, S.score, src_lane);
+            int32_t const j = int32_t(t) - int32_t(S.b);
+            if (j >= S.cs && j <= S.ce) {
+                if (j == S.cs) {
+                    // (re)start: column cs-1 of this block is (bottom of the block above at cs-1) + 1, 2, ...
 #pragma unroll
-                for (int i = 0; i < W; ++i) { Pv[i] = 0xffffffffu; Mv[i] = 0; }
-                if (b == 0) {
-                    // wildcard rows carry value 0: no vertical step there
+                    for (int i = 0; i < W; ++i) { S.Pv[i] = 0xffffffffu; S.Mv[i] = 0; }
+                    if (S.b == 0) {
+                        // wildcard rows carry value 0: no vertical step there
 #pragma unroll
-                    for (int i = 0; i < W; ++i) {
-                        int32_t const virt = int32_t(pad) - 32 * i;
-                        Pv[i] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
+                        for (int i = 0; i < W; ++i) {
+                            int32_t const virt = int32_t(pad) - 32 * i;
+                            S.Pv[i] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
+                        }
+                        S.score = int32_t(ROWS) - int32_t(pad);
+                    } else {
+                        S.score = r_sc - int32_t(r_hp >> 31) + int32_t(r_hn >> 31) + ROWS;
                     }
-                    score = int32_t(ROWS) - int32_t(pad);
-                } else {
-                    score = r_sc - int32_t(in_hp >> 31) + int32_t(in_hn >> 31) + ROWS;
+                    S.wp = win0 + (j - 1);
+                    S.eqb = peq + S.b * W;
                 }
+                uint32_t* trace_row = TRACE ? (L.trace + T.trace_base + (uint64_t(t - 1) * G + r) * (2 * W)) : nullptr;
+                block_step<W, TRACE, true, true>(S, r_hp, r_hn, t, L.peq_stride, last_block, trace_row);
+                if (j == S.ce) { S.b += G; set_block(S.b); }
+            } else {
+                S.o_hp = 0x80000000u; S.o_hn = 0;
             }
-            uint32_t const c = reverse ? win0[T.n - uint32_t(j)] : win0[j - 1];
-            uint32_t const* eqrow = peq + c * L.peq_stride + b * W;
-            constexpr int CH = W < 8 ? W : 8;
-            uint32_t hp_prev = in_hp, hn_prev = in_hn;
-            uint32_t carry = in_hn >> 31;            // the adder's carry across a word boundary equals the HN bit there
-#pragma unroll
-            for (int c0 = 0; c0 < W; c0 += CH) {
-                uint32_t Eq[CH], X[CH], Tt[CH], S[CH];
-#pragma unroll
-                for (int i = 0; i < CH; ++i) Eq[i] = eqrow[c0 + i];
-#pragma unroll
-                for (int i = 0; i < CH; ++i) { X[i] = Eq[i] | Mv[c0 + i]; Tt[i] = Eq[i] & Pv[c0 + i]; }
-                if (c0 + CH < W) carry = Chain<CH, true>::run(S, Tt, &Pv[c0], carry);
-                else Chain<CH, false>::run(S, Tt, &Pv[c0], carry);
-#pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                    uint32_t const pv = Pv[c0 + i], mv = Mv[c0 + i];
-                    uint32_t const D0 = (S[i] ^ pv) | X[i];
-                    uint32_t const HN = pv & D0;
-                    uint32_t const HP = mv | ~(pv | D0);
-                    uint32_t const HPs = __funnelshift_l(hp_prev, HP, 1);
-                    uint32_t const HNs = __funnelshift_l(hn_prev, HN, 1);
-                    Mv[c0 + i] = HPs & D0;
-                    Pv[c0 + i] = HNs | ~(HPs | D0);
-                    hp_prev = HP; hn_prev = HN;
-                    if (TRACE) {
-                        // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
-                        uint32_t* tp = L.trace + T.trace_base + ((uint64_t(t - 1) * G + r) * W + (c0 + i)) * 2;
-                        *reinterpret_cast<uint2*>(tp) = make_uint2(HP, Pv[c0 + i]);
-                    }
-                }
+        }
+        ++t;
+        // ---------------- steps until the next event of any lane: nothing but the recurrence ----------------
+        int32_t const jn = int32_t(t) - int32_t(S.b);
+        bool const active = jn > S.cs && jn <= S.ce;           // already started (a start is an event of its own)
+        // an active lane's next event is its last column; a lane that just finished must publish the boundary next step
+        uint32_t my_evt;
+        if (active) my_evt = uint32_t(S.ce) + S.b;
+        else if (S.o_hp != 0x80000000u || S.o_hn != 0u) my_evt = t;
+        else my_evt = S.cs == 0x7fffffff ? kNever : uint32_t(S.cs) + S.b;
+        uint32_t const evt = min(__reduce_min_sync(0xffffffffu, my_evt), my_end + 1);
+        if (evt > t) {
+            bool const any_first = __any_sync(0xffffffffu, active && S.b == 0);
+            bool const any_last = __any_sync(0xffffffffu, active && S.b == last_block);
+            uint32_t* trace_row = TRACE ? (L.trace + T.trace_base + (uint64_t(t - 1) * G + r) * (2 * W)) : nullptr;
+            uint32_t const trace_step = G * 2 * W;
+#define FXG_FAST_LOOP(FIRST, LAST)                                                                         \
+            for (; t < evt; ++t) {                                                                         \
+                uint32_t const r_hp = __shfl_sync(0xffffffffu, S.o_hp, src_lane);                          \
+                uint32_t const r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);                          \
+                if (active) block_step<W, TRACE, FIRST, LAST>(S, r_hp, r_hn, t, L.peq_stride, last_block, trace_row); \
+                if (TRACE) trace_row += trace_step;                                                        \
             }
-            o_hp = hp_prev; o_hn = hn_prev;
-            score += int32_t(hp_prev >> 31) - int32_t(hn_prev >> 31);
-            if (b == nb - 1 && score <= best) { best = score; best_col = uint32_t(j); }
-            if (j == ce) { b += G; set_block(b); }
-        } else {
-            o_hp = 0x80000000u; o_hn = 0;
+            if (any_first) { if (any_last) { FXG_FAST_LOOP(true, true) } else { FXG_FAST_LOOP(true, false) } }
+            else { if (any_last) { FXG_FAST_LOOP(false, true) } else { FXG_FAST_LOOP(false, false) } }
+#undef FXG_FAST_LOOP
         }
     }
     // the lane that owned the last block reports
-    uint32_t const owner = (nb - 1) % G;
+    uint32_t const owner = last_block % G;
     if (have_task && r == owner) {
-        DpResult res; res.score = best; res.end_col = best_col;
+        DpResult res; res.score = S.best; res.end_col = S.best_col;
         L.results[T.out] = res;
     }
 }

@@ -289,6 +289,7 @@ cudaError_t set_all_smem_attrs(size_t bytes) {
 
 inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
 inline size_t win_stride_for(uint32_t n) { return (size_t(n + 63) / 32 + 1) * 32; }
+inline uint32_t peq_stride_for(uint32_t words) { return (words + 3u) & ~3u; }   // rows stay 16-byte aligned for LDS.128
 
 // word-steps the engine issues for a pass: block b is active for columns cs(b)..ce(b)
 uint64_t word_steps_of(Pass const& p, uint32_t W, uint32_t nb) {
@@ -323,7 +324,7 @@ bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
             if (g > 32) continue;
             G = pow2_ceil(uint32_t(std::max<int64_t>(g, 2)));
         }
-        size_t const smem = size_t(32 / G) * (win_stride_for(p.n) + size_t(kNumSymbols) * nb * W * 4);
+        size_t const smem = size_t(32 / G) * (win_stride_for(p.n) + size_t(kNumSymbols) * peq_stride_for(nb * W) * 4);
         if (smem > smem_limit) continue;
         uint64_t const steps = uint64_t(p.n) + nb - 1;
         double const cost = double(G) * double(steps) * (10.0 * W + 16.0);
@@ -432,7 +433,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
         L.n_tasks = uint32_t(j - i);
         L.group = G;
         L.win_stride = uint32_t(win_stride_for(max_n));
-        L.peq_stride = max_words;
+        L.peq_stride = peq_stride_for(max_words);
         L.ref_packed = c->refs.packed.as<uint32_t>();
         L.inline_packed = pool.inline_packed.as<uint32_t>();
         L.peq_table = pool.peq.as<uint32_t>();
@@ -678,12 +679,22 @@ struct PartOut {
 // unresolved, and it is skipped if an EARLIER walk inserted a window containing its trimmed root window.
 void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, uint64_t trace_budget, PartOut& out) {
     cudaSetDevice(c->device);
+    auto const part_t0 = std::chrono::steady_clock::now();
+    struct PartReport {
+        Worker& w; std::chrono::steady_clock::time_point t0; size_t* n_walks;
+        ~PartReport() {
+            if (g_prof.on) fprintf(stderr, "[fxg] worker %d: %zu walks, %.3f ms, %llu waves\n", w.id, *n_walks,
+                                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
+                                   (unsigned long long)w.ctr.waves);
+        }
+    };
     g_prof.start(w);
     bool const ivopt = J->cfg.interval_optimization != 0;
     uint32_t const w_lo = J->read_walk_begin[read_lo], w_hi = J->read_walk_begin[read_hi];
     uint32_t const g_lo = J->read_group_begin[read_lo], g_hi = J->read_group_begin[read_hi];
     std::vector<Walk> walks(J->walks.begin() + w_lo, J->walks.begin() + w_hi);      // local copy, indices shifted by w_lo
-    size_t const n_walks = walks.size();
+    size_t n_walks = walks.size();
+    PartReport part_report{w, part_t0, &n_walks};
     struct GroupState { uint32_t first_open = 0; std::vector<uint32_t> inserted; };
     std::vector<GroupState> gstate(g_hi - g_lo);
     w.cigar_pool.clear();
@@ -1153,7 +1164,10 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
     }
     cut[n_parts] = uint32_t(n_reads);
     std::vector<PartOut> outs(n_parts);
+    auto const vt0 = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - vt0).count(); };
     uint64_t const budget = trace_budget_bytes(c, n_parts);
+    double const t_budget = since();
     for (size_t p = 0; p < n_parts; ++p) c->workers[p]->ctr = fxg_counters{};
     {
         RunTimer run_timer(c);
@@ -1163,6 +1177,7 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
         verify_part(c, *c->workers[0], J, cut[0], cut[1], budget, outs[0]);
         for (auto& t : threads) t.join();
     }
+    double const t_join = since();
     g_prof.report();
     for (size_t p = 0; p < n_parts; ++p) {
         add_counters(c->ctr, c->workers[p]->ctr);
@@ -1177,6 +1192,7 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
         for (size_t f = 0; f < sizeof(fxg_stats) / sizeof(uint64_t); ++f) d[f] += s[f];
     }
     J->ran = true;
+    if (g_prof.on) fprintf(stderr, "[fxg] verify_run: budget query %.3f ms, parts done %.3f ms, merged %.3f ms\n", t_budget, t_join, since());
     return FXG_OK;
 }
 
