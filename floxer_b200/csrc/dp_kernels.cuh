@@ -107,7 +107,7 @@ __device__ __forceinline__ void unpack8(uint32_t x, uint32_t& lo, uint32_t& hi) 
 struct DpLaunch {
     const DpTask* tasks;        // sorted so that the tasks of one warp have similar step counts
     uint32_t n_tasks;
-    uint32_t group;             // G: lanes per task (1, 2, 4, 8, 16 or 32); 32 / G tasks per warp
+    uint32_t group;             // G: lanes per task (1..32); floor(32 / G) tasks per warp
     uint32_t win_stride;        // bytes of shared memory per task window (multiple of 16)
     uint32_t peq_stride;        // words per symbol row of the per-task Eq table
     const uint32_t* ref_packed; // resident references
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     uint32_t const slot = lane / G;                 // which task of this warp
     uint32_t const r = lane % G;                    // ring position
     uint32_t const task_id = blockIdx.x * tasks_per_warp + slot;
-    bool const have_task = task_id < L.n_tasks;
+    bool const have_task = slot < tasks_per_warp && task_id < L.n_tasks;     // G need not divide 32: spare lanes idle
 
     uint8_t* const win = smem + size_t(slot) * L.win_stride;
     uint32_t* const peq = reinterpret_cast<uint32_t*>(smem + size_t(tasks_per_warp) * L.win_stride) +
@@ -447,63 +447,124 @@ struct WalkLaunch {
 
 // trace priority: left > up > diagonal.  This is the ONE place on the device that encodes it
 // (oracle: FXO_TRACE_PRIORITY in oracle/floxer_oracle.h).
-__global__ void walk_kernel(WalkLaunch const L) {
-    uint32_t const id = blockIdx.x * blockDim.x + threadIdx.x;
+//
+// One warp per alignment.  The walk itself is sequential, but the memory side is not: the warp loads a
+// tile of the trace planes (32 columns x the 2 words around the current row) with one coalesced round of
+// loads (each lane keeps one column in registers), advances over whole diagonal runs at once (one ballot tells
+// how far the path follows the diagonal), and prefetches the tile it will most likely need next.
+constexpr int kWalkWarps = 4;
+
+__global__ void __launch_bounds__(32 * kWalkWarps) walk_kernel(WalkLaunch const L) {
+    __shared__ uint8_t s_qry[kWalkWarps][64];      // query characters of the tile's rows
+    uint32_t const warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint32_t const id = blockIdx.x * kWalkWarps + warp;
     if (id >= L.n_tasks) return;
     WalkTask const T = L.tasks[id];
     const uint32_t* ref = (T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed;
+    const uint32_t* const trace = L.trace + T.trace_base;
     uint32_t const W = T.words, G = T.group, ROWS = 32 * W;
     uint32_t const nb = (T.m + ROWS - 1) / ROWS;
     uint32_t const pad = nb * ROWS - T.m;
     uint32_t* const runs = L.scratch + T.scratch_base;
-    uint32_t n_runs = 0;
-    uint32_t cur_op = 0, cur_len = 0;
+    uint32_t n_runs = 0, cur_op = 0, cur_len = 0;
     bool bad = false;
     uint32_t i = T.m, j = T.n;
+    uint32_t j0 = 0, w0 = 0, i0 = 0;
+    bool have_tile = false;
+
+    auto cell_ptr = [&](uint32_t col, uint32_t word) -> const uint32_t* {
+        uint32_t const blk = word / W, iw = word % W;
+        uint64_t const t = uint64_t(col) + blk;                       // step at which (block, column) was computed
+        return trace + (((t - 1) * G + blk % G) * W + iw) * 2;
+    };
+
+    // emit `len` copies of `op` (uniform across the warp)
+    auto emit = [&](uint32_t op, uint32_t len) {
+        if (op == cur_op) { cur_len += len; return; }
+        if (cur_len) { if (n_runs < T.cigar_cap) { if (lane == 0) runs[n_runs] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
+        cur_op = op; cur_len = len;
+    };
+    uint4 v = make_uint4(0, 0, 0, 0);          // this lane's column of the tile: hp, vp of word w0 and of word w0 - 1
+    uint32_t rc = 0;                           // and its reference character
     while (i > 0) {
-        uint32_t op;
-        if (j == 0) { op = 1; --i; }                                   // column 0: only "up"
-        else {
-            uint32_t const u = i - 1 + pad;
-            uint32_t const w = u >> 5, bit = u & 31u;
-            uint32_t const blk = w / W, iw = w % W;
-            uint64_t const t = uint64_t(j) + blk;                       // step at which (block, column j) was computed
-            const uint32_t* const cell = L.trace + T.trace_base + (((t - 1) * G + blk % G) * W + iw) * 2;
-            // the path hugs a diagonal: fetch the lines it will need kPrefetch steps from now into L2 already
-            if (i > kWalkPrefetch && j > kWalkPrefetch) {
-                uint32_t const u2 = u - kWalkPrefetch, w2 = u2 >> 5, blk2 = w2 / W;
-                uint64_t const t2 = uint64_t(j - kWalkPrefetch) + blk2;
-                const uint32_t* const ahead = L.trace + T.trace_base + (((t2 - 1) * G + blk2 % G) * W + w2 % W) * 2;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ahead));
+        if (j == 0) { emit(1, i); i = 0; break; }                      // column 0: only "up" remains
+        uint32_t const u = i - 1 + pad;
+        uint32_t const w = u >> 5;
+        if (!have_tile || j0 - j > 31u || w0 - w > 1u || i0 - i > 63u) {
+            j0 = j; w0 = w; i0 = i;
+            __syncwarp();
+            v = make_uint4(0, 0, 0, 0); rc = 0;
+            if (lane < j0) {                                           // column j0 - lane >= 1
+                uint32_t const col = j0 - lane;
+                uint2 const a = *reinterpret_cast<const uint2*>(cell_ptr(col, w0));
+                v.x = a.x; v.y = a.y;
+                if (w0 >= 1) { uint2 const c2 = *reinterpret_cast<const uint2*>(cell_ptr(col, w0 - 1)); v.z = c2.x; v.w = c2.y; }
+                rc = packed_base(ref, T.ref_base + col - 1);
+                // the tile after this one, if the path keeps to its diagonal
+                if (col > 32 && i0 > 32) {
+                    uint32_t const w2 = (i0 - 33 + pad) >> 5;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_ptr(col - 32, w2)));
+                    if (w2 >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_ptr(col - 32, w2 - 1)));
+                }
             }
-            uint2 const hv = *reinterpret_cast<const uint2*>(cell);
-            if ((hv.x >> bit) & 1u) { op = 2; --j; }                    // left  -> D
-            else if ((hv.y >> bit) & 1u) { op = 1; --i; }               // up    -> I
-            else {                                                     // diagonal -> '=' or X
-                uint32_t const qc = L.query_pool[T.query_base + i - 1];
-                uint32_t const rc = packed_base(ref, T.ref_base + j - 1);
-                op = (qc == rc) ? 7u : 8u;
-                --i; --j;
+            if (lane < i0) s_qry[warp][lane] = L.query_pool[T.query_base + i0 - lane - 1];
+            if (lane + 32 < i0) s_qry[warp][lane + 32] = L.query_pool[T.query_base + i0 - lane - 33];
+            __syncwarp();
+            have_tile = true;
+        }
+        // Lane l looks at the cell s = l - d0 steps down the diagonal from (i, j): row i - s, column j0 - l (its own column).
+        uint32_t const d0 = j0 - j;
+        int32_t const sdiag = int32_t(lane) - int32_t(d0);
+        bool valid = sdiag >= 0 && uint32_t(sdiag) < i && lane < j0;
+        uint32_t hpb = 0, vpb = 0; bool match = false;
+        if (valid) {
+            uint32_t const us = u - uint32_t(sdiag);                   // >= pad because row i - s >= 1
+            uint32_t const ws = us >> 5, bs = us & 31u;
+            uint32_t const dw = w0 - ws;
+            uint32_t const row = i - uint32_t(sdiag);
+            valid = dw <= 1u && i0 - row <= 63u;
+            if (valid) {
+                hpb = ((dw ? v.z : v.x) >> bs) & 1u;
+                vpb = ((dw ? v.w : v.y) >> bs) & 1u;
+                match = s_qry[warp][i0 - row] == uint8_t(rc);
             }
         }
-        if (op == cur_op) ++cur_len;
-        else {
-            if (cur_len) { if (n_runs < T.cigar_cap) runs[n_runs] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
-            cur_op = op; cur_len = 1;
+        // trace priority at every cell: left (hp) first, then up (vp), else diagonal
+        uint32_t const diag_bits = __ballot_sync(0xffffffffu, valid && !hpb && !vpb) >> d0;
+        uint32_t const run = diag_bits == 0xffffffffu ? 32u : uint32_t(__ffs(~diag_bits) - 1);   // consecutive diagonal cells from (i, j)
+        if (run == 0) {
+            uint32_t const left_here = (__ballot_sync(0xffffffffu, valid && hpb) >> d0) & 1u;
+            if (left_here) { emit(2, 1); --j; }                        // left  -> D
+            else { emit(1, 1); --i; }                                  // up    -> I  (the current cell is always valid)
+        } else {
+            uint32_t mbits = __ballot_sync(0xffffffffu, match) >> d0;
+            uint32_t left = run;
+            while (left) {                                             // run-length encode '=' / X along the diagonal run
+                uint32_t const is_eq = mbits & 1u;
+                uint32_t len = __ffs(is_eq ? ~mbits : mbits) - 1;       // ffs(0) - 1 = 0xffffffff -> clamped below
+                len = len > left ? left : len;
+                emit(is_eq ? 7u : 8u, len);
+                mbits = len >= 32u ? 0u : mbits >> len; left -= len;
+            }
+            i -= run; j -= run;
         }
     }
-    if (cur_len) { if (n_runs < T.cigar_cap) runs[n_runs] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
+    if (cur_len) { if (n_runs < T.cigar_cap) { if (lane == 0) runs[n_runs] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
+    __syncwarp();
     WalkResult R; R.begin_col = j; R.cigar_len = bad ? 0xffffffffu : n_runs; R.cigar_offset = 0;
     if (!bad) {
-        unsigned long long const at = atomicAdd(L.cigar_cursor, (unsigned long long)n_runs);
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(L.cigar_cursor, (unsigned long long)n_runs);
+        at = __shfl_sync(0xffffffffu, at, 0);
         if (at + n_runs <= L.cigar_pool_cap) {
-            for (uint32_t p = 0; p < n_runs; ++p) L.cigar_pool[at + p] = runs[n_runs - 1 - p];
+            __threadfence_block();
+            for (uint32_t p = lane; p < n_runs; p += 32) L.cigar_pool[at + p] = runs[n_runs - 1 - p];
             R.cigar_offset = at;
         } else {
             R.cigar_len = 0xffffffffu;
         }
     }
-    L.results[T.out] = R;
+    if (lane == 0) L.results[T.out] = R;
 }
 
 // ---------------------------------------------------------------------------------------------

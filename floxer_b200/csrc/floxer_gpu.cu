@@ -230,7 +230,7 @@ int fail(std::string& err, int code, const char* fmt, ...) {
 void add_counters(fxg_counters& a, fxg_counters const& b) {
     a.kernel_launches += b.kernel_launches; a.dp_tasks += b.dp_tasks; a.dp_word_steps += b.dp_word_steps;
     a.dp_cells_full += b.dp_cells_full; a.trace_bytes += b.trace_bytes; a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
-    a.dp_kernel_ms += b.dp_kernel_ms; a.trace_kernel_ms += b.trace_kernel_ms; a.waves += b.waves; a.run_ms += b.run_ms;
+    a.trace_word_steps += b.trace_word_steps; a.dp_kernel_ms += b.dp_kernel_ms; a.trace_kernel_ms += b.trace_kernel_ms; a.waves += b.waves; a.run_ms += b.run_ms;
 }
 
 // brackets a *_run call with events on worker 0's stream (the stream the first kernels are launched on)
@@ -320,14 +320,21 @@ bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
         if (nb == 1) G = 1;
         else {
             int64_t const need = (B > 4 ? (B - 4) / (32 * int64_t(W) + 1) : 0) + 3;
-            int64_t const g = std::min<int64_t>(need, nb);
+            int64_t const g = std::max<int64_t>(std::min<int64_t>(need, nb), 2);
             if (g > 32) continue;
-            G = pow2_ceil(uint32_t(std::max<int64_t>(g, 2)));
+            G = uint32_t(g);
         }
-        size_t const smem = size_t(32 / G) * (win_stride_for(p.n) + size_t(kNumSymbols) * peq_stride_for(nb * W) * 4);
+        uint32_t const tpw = 32 / G;
+        size_t const smem = size_t(tpw) * (win_stride_for(p.n) + size_t(kNumSymbols) * peq_stride_for(nb * W) * 4);
         if (smem > smem_limit) continue;
+        // warps that fit on an SM next to each other vs. warps needed to hide the shuffle / shared-memory latency of a
+        // step (about 100 cycles) behind the issue time of the other warps' steps ((12 W + 10) instructions, 2 cycles each)
+        double const resident = std::min<double>(32.0, std::floor(double(227 * 1024) / double(smem + 1024)));
+        double const needed = 4.0 * (100.0 / ((12.0 * W + 10.0) * 2.0) + 1.0);
+        double const eff = std::min(1.0, resident / needed);
         uint64_t const steps = uint64_t(p.n) + nb - 1;
-        double const cost = double(G) * double(steps) * (10.0 * W + 16.0);
+        // lane-steps spent per task (idle lanes of a partly filled warp included) x instructions per step
+        double const cost = (32.0 / tpw) * double(steps) * (10.0 * W + 14.0) / eff;
         if (cost < best_cost) { best_cost = cost; out = Config{uint8_t(wi), uint8_t(G), nb, 0}; found = true; }
     }
     if (found) out.word_steps = word_steps_of(p, uint32_t(kWidths[out.widx]), out.nb);
@@ -380,11 +387,11 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
                         passes[i].m, passes[i].n, passes[i].dlo, passes[i].dhi);
         uint64_t const steps = std::min<uint64_t>(uint64_t(passes[i].n) + cf.nb - 1, (1u << 19) - 1);
-        uint64_t const cls = uint64_t(5 - cf.widx) * 8 + (5 - (31 - __builtin_clz(uint32_t(cf.G))));   // 0 = W 32, G 32
+        uint64_t const cls = uint64_t(5 - cf.widx) * 32 + (32 - cf.G);                                  // 0 = W 32, G 32
         w.keys[i] = (cls << 51) | ((((1ull << 19) - 1) - steps) << 32) | uint64_t(i);
     }
     g_prof.lap(w, 3);
-    radix_sort(w.keys, w.keys_tmp, 32, 32 + 22 + 3);
+    radix_sort(w.keys, w.keys_tmp, 32, 64);
     g_prof.lap(w, 4);
 
     CUDA_TRY(w.err, w.h_tasks.ensure(N * sizeof(DpTask)));
@@ -399,7 +406,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
         t.ref_base = p.ref_base; t.query_base = p.query_base;
         t.trace_base = trace ? trace_bases[idx] : 0;
         t.n = p.n; t.m = p.m; t.dlo = p.dlo; t.dhi = p.dhi; t.flags = p.flags; t.out = idx;
-        w.ctr.dp_word_steps += w.cfgs[idx].word_steps;
+        if (trace) w.ctr.trace_word_steps += w.cfgs[idx].word_steps; else w.ctr.dp_word_steps += w.cfgs[idx].word_steps;
         w.ctr.dp_cells_full += uint64_t(p.m) * p.n;
     }
     w.ctr.dp_tasks += N;
@@ -527,7 +534,7 @@ int run_traces(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<TraceReq> co
         WL.cigar_pool = w.d_cig_pool.as<uint32_t>(); WL.cigar_cursor = w.d_cursor.as<unsigned long long>();
         WL.cigar_pool_cap = cig_cap_total; WL.results = w.d_wresults.as<WalkResult>();
         CUDA_TRY(w.err, cudaEventRecord(w.ev0, w.stream));
-        walk_kernel<<<uint32_t((M + 31) / 32), 32, 0, w.stream>>>(WL);
+        walk_kernel<<<uint32_t((M + kWalkWarps - 1) / kWalkWarps), 32 * kWalkWarps, 0, w.stream>>>(WL);
         CUDA_TRY(w.err, cudaGetLastError());
         CUDA_TRY(w.err, cudaEventRecord(w.ev1, w.stream));
         w.ctr.kernel_launches++;
@@ -540,17 +547,18 @@ int run_traces(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<TraceReq> co
         CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
         w.ctr.trace_kernel_ms += ms;
         size_t const n_ops = size_t(*cursor);
-        size_t const pool_at = w.cigar_pool.size();
         if (n_ops) {
             CUDA_TRY(w.err, w.h_cigars.ensure(n_ops * 4));
             CUDA_TRY(w.err, cudaMemcpyAsync(w.h_cigars.p, w.d_cig_pool.p, n_ops * 4, cudaMemcpyDeviceToHost, w.stream));
             CUDA_TRY(w.err, cudaStreamSynchronize(w.stream));
-            w.cigar_pool.insert(w.cigar_pool.end(), w.h_cigars.as<uint32_t>(), w.h_cigars.as<uint32_t>() + n_ops);
         }
         w.ctr.d2h_bytes += M * sizeof(WalkResult) + n_ops * 4;
+        // the device hands out pool space with an atomic counter; re-pack in task order so that results are deterministic
+        const uint32_t* const dev_pool = w.h_cigars.as<uint32_t>();
         for (size_t q = 0; q < M; ++q) {
             if (wr[q].cigar_len == 0xffffffffu) return fail(w.err, FXG_ERR_CUDA, "internal: traceback overflowed its CIGAR scratch");
-            outs[i + q] = TraceOut{wr[q].begin_col, pool_at + wr[q].cigar_offset, wr[q].cigar_len};
+            outs[i + q] = TraceOut{wr[q].begin_col, w.cigar_pool.size(), wr[q].cigar_len};
+            w.cigar_pool.insert(w.cigar_pool.end(), dev_pool + wr[q].cigar_offset, dev_pool + wr[q].cigar_offset + wr[q].cigar_len);
         }
         i = j;
         g_prof.lap(w, 12);

@@ -131,7 +131,7 @@ typedef struct {
 typedef struct {
     uint64_t kernel_launches;        /* launches of this library's kernels */
     uint64_t dp_tasks;               /* bit-vector DP tasks executed (score passes + trace passes) */
-    uint64_t dp_word_steps;          /* 32-cell Myers word-steps issued by the DP kernels (band-limited) */
+    uint64_t dp_word_steps;          /* 32-cell Myers word-steps issued by the score passes (band-limited) */
     uint64_t dp_cells_full;          /* sum of m' * n' of those tasks (full-matrix convention) */
     uint64_t trace_bytes;            /* bytes of trace bit-planes written by the traceback pass */
     uint64_t h2d_bytes, d2h_bytes;
@@ -139,6 +139,7 @@ typedef struct {
     double trace_kernel_ms;          /* CUDA-event time of trace-store + walk kernels */
     uint64_t waves;                  /* host scheduling rounds of fxg_verify_* */
     double run_ms;                   /* CUDA-event time from the first to the last device operation of *_run calls */
+    uint64_t trace_word_steps;       /* word-steps issued by the trace passes (their time is in trace_kernel_ms) */
 } fxg_counters;
 
 /* ---- life cycle ---- */
