@@ -160,6 +160,8 @@ struct fxg_ctx {
     std::vector<std::unique_ptr<Worker>> workers;
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
     DevBuf d_tmp;
+    uint64_t trace_budget = 0;
+    std::vector<Pool> spare_pools;       // device buffers of freed batches / jobs, reused by the next stage call
     std::mutex mu;
 };
 
@@ -200,11 +202,7 @@ struct fxg_job {
     std::vector<fxg_anchor> anchors;
     uint64_t pool_len = 0;
     Pool pool;                           // forward pool followed by the reverse-complement pool
-    // schedule template built at stage time
-    std::vector<Walk> walks;             // in the reference's order: read, forward package, reverse package
-    std::vector<Group> groups;
-    std::vector<uint32_t> group_members; // walk indices, ascending inside a group
-    std::vector<uint32_t> read_walk_begin, read_group_begin;   // per read (+1 sentinel)
+    std::vector<uint32_t> read_walk_begin;   // per read (+1 sentinel): index of its first walk (= anchor) in job order
     // results
     std::vector<fxg_alignment> alignments;
     std::vector<uint32_t> cigars;
@@ -566,21 +564,45 @@ int run_traces(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<TraceReq> co
     return FXG_OK;
 }
 
-uint64_t trace_budget_bytes(fxg_ctx* c, size_t n_parts) {
+// Trace planes may take up to about half of what is free on the device (at most 64 GiB), shared by the parts of a
+// run.  cudaMemGetInfo costs milliseconds, so the figure is refreshed only when the resident set changes.
+void refresh_trace_budget(fxg_ctx* c) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(8) << 30;
     uint64_t held = 0;
     for (auto const& w : c->workers) held += w->d_trace.cap;
-    uint64_t const budget = std::min<uint64_t>((uint64_t(free_b) + held) / 2, uint64_t(64) << 30);
-    return budget / std::max<size_t>(n_parts, 1);
+    c->trace_budget = std::min<uint64_t>((uint64_t(free_b) + held) / 2, uint64_t(64) << 30);
+}
+uint64_t trace_budget_bytes(fxg_ctx* c, size_t n_parts) {
+    if (c->trace_budget == 0) refresh_trace_budget(c);
+    return c->trace_budget / std::max<size_t>(n_parts, 1);
 }
 
 // ------------------------------------------------------------------------------------------------ pools
 
+// cudaMalloc / cudaFree synchronise the device and cost milliseconds: staged pools are recycled instead
+Pool take_pool(fxg_ctx* c) {
+    Pool p;
+    if (!c->spare_pools.empty()) { p = c->spare_pools.back(); c->spare_pools.pop_back(); }
+    p.len = p.plane_words = p.inline_len = 0;
+    return p;
+}
+void give_pool(fxg_ctx* c, Pool& p) {
+    if (c->spare_pools.size() < 4) c->spare_pools.push_back(p); else p.release();
+    p = Pool{};
+}
+
 int check_ranks(std::string& err, const uint8_t* p, size_t n, const char* what) {
-    uint8_t worst = 0;
-    for (size_t i = 0; i < n; ++i) worst = p[i] > worst ? p[i] : worst;
-    if (worst > FXG_MAX_RANK) return fail(err, FXG_ERR_INVALID_ARGUMENT, "%s contains rank %u (allowed 0..%d)", what, unsigned(worst), FXG_MAX_RANK);
+    // any byte above FXG_MAX_RANK?  eight bytes at a time: (b & 0x7f) + 0x7a has its top bit set iff (b & 0x7f) >= 6
+    uint64_t bad = 0;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t x;
+        std::memcpy(&x, p + i, 8);
+        bad |= (((x & 0x7f7f7f7f7f7f7f7full) + 0x7a7a7a7a7a7a7a7aull) | x) & 0x8080808080808080ull;
+    }
+    for (; i < n; ++i) bad |= p[i] > FXG_MAX_RANK;
+    if (bad) return fail(err, FXG_ERR_INVALID_ARGUMENT, "%s contains a rank above %d (allowed 0..%d)", what, FXG_MAX_RANK, FXG_MAX_RANK);
     return FXG_OK;
 }
 
@@ -675,6 +697,54 @@ inline void trim(uint64_t& start, uint64_t& end, uint64_t amount) {
 
 // ------------------------------------------------------------------------------------------------ verify, one part
 
+// One Walk per anchor of reads [read_lo, read_hi) in the reference's order (read, forward package, reverse package);
+// anchors of one (read, orientation, reference) share a verified_intervals set (parallelization.cpp:224-226).
+void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_hi, std::vector<Walk>& walks,
+                 std::vector<Group>& groups, std::vector<uint32_t>& group_members) {
+    bool const direct = J->cfg.verification_kind == FXG_KIND_DIRECT_FULL;
+    bool const ivopt = J->cfg.interval_optimization != 0;
+    double const ratio = J->cfg.extra_verification_ratio;
+    walks.clear(); groups.clear(); group_members.clear();
+    walks.reserve(J->read_walk_begin[read_hi] - J->read_walk_begin[read_lo]);
+    std::vector<std::vector<uint32_t>> tmp_groups;
+    std::vector<int64_t> ref_to_group;
+    for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
+        fxg_read const& R = J->reads[ri];
+        const fxg_pex_node* inner = J->nodes.data() + R.node_offset;
+        const fxg_pex_node* leaves = inner + R.num_inner;
+        fxg_pex_node const& root = R.num_inner ? inner[0] : leaves[0];
+        for (int orient = 0; orient < 2; ++orient) {
+            uint32_t const a0 = uint32_t(R.anchor_offset) + (orient ? R.num_anchors_forward : 0);
+            uint32_t const na = orient ? R.num_anchors_reverse : R.num_anchors_forward;
+            if (ivopt) { tmp_groups.clear(); ref_to_group.assign(c->refs.len.size(), -1); }
+            uint32_t const group_base = uint32_t(groups.size());
+            for (uint32_t q = 0; q < na; ++q) {
+                fxg_anchor const& A = J->anchors[a0 + q];
+                fxg_pex_node const& leaf = leaves[A.pex_leaf_index];
+                Walk wk{};
+                wk.read = ri; wk.anchor = a0 + q; wk.orient = uint8_t(orient); wk.state = W_WAITING;
+                wk.root_span = compute_span(A.reference_position, root, leaf.query_index_from, c->refs.len[A.reference_id], ratio);
+                wk.r_start = wk.root_span.offset; wk.r_end = wk.root_span.offset + wk.root_span.length;
+                wk.t_start = wk.r_start; wk.t_end = wk.r_end;
+                trim(wk.t_start, wk.t_end, wk.root_span.extra);
+                wk.node = (direct || leaf.parent_id == FXG_NULL_ID) ? &root : &inner[leaf.parent_id];
+                if (ivopt) {
+                    if (ref_to_group[A.reference_id] < 0) { ref_to_group[A.reference_id] = int64_t(tmp_groups.size()); tmp_groups.emplace_back(); }
+                    wk.group = group_base + uint32_t(ref_to_group[A.reference_id]);
+                    tmp_groups[size_t(ref_to_group[A.reference_id])].push_back(uint32_t(walks.size()));
+                }
+                walks.push_back(wk);
+            }
+            if (ivopt) {
+                for (auto const& g : tmp_groups) {
+                    groups.push_back(Group{uint32_t(group_members.size()), uint32_t(g.size())});
+                    group_members.insert(group_members.end(), g.begin(), g.end());
+                }
+            }
+        }
+    }
+}
+
 struct PartOut {
     std::vector<fxg_alignment> alignments;   // cigar offsets index the worker's cigar pool
     fxg_stats stats{};
@@ -698,13 +768,12 @@ void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t r
     };
     g_prof.start(w);
     bool const ivopt = J->cfg.interval_optimization != 0;
-    uint32_t const w_lo = J->read_walk_begin[read_lo], w_hi = J->read_walk_begin[read_hi];
-    uint32_t const g_lo = J->read_group_begin[read_lo], g_hi = J->read_group_begin[read_hi];
-    std::vector<Walk> walks(J->walks.begin() + w_lo, J->walks.begin() + w_hi);      // local copy, indices shifted by w_lo
+    std::vector<Walk> walks; std::vector<Group> groups; std::vector<uint32_t> group_members;   // indices local to this part
+    build_walks(c, J, read_lo, read_hi, walks, groups, group_members);
     size_t n_walks = walks.size();
     PartReport part_report{w, part_t0, &n_walks};
     struct GroupState { uint32_t first_open = 0; std::vector<uint32_t> inserted; };
-    std::vector<GroupState> gstate(g_hi - g_lo);
+    std::vector<GroupState> gstate(groups.size());
     w.cigar_pool.clear();
 
     std::vector<uint32_t> active, next_active;
@@ -721,13 +790,13 @@ void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t r
         if (!ivopt) {
             if (first_wave) { active.resize(n_walks); for (uint32_t i = 0; i < n_walks; ++i) { active[i] = i; walks[i].state = W_WALKING; } }
         } else {
-            for (uint32_t g = g_lo; g < g_hi; ++g) {
-                Group const& G = J->groups[g];
-                GroupState& S = gstate[g - g_lo];
-                const uint32_t* mem = J->group_members.data() + G.first;
-                while (S.first_open < G.count && walks[mem[S.first_open] - w_lo].state == W_DONE) ++S.first_open;
+            for (uint32_t g = 0; g < groups.size(); ++g) {
+                Group const& G = groups[g];
+                GroupState& S = gstate[g];
+                const uint32_t* mem = group_members.data() + G.first;
+                while (S.first_open < G.count && walks[mem[S.first_open]].state == W_DONE) ++S.first_open;
                 for (uint32_t q = S.first_open; q < G.count; ++q) {
-                    uint32_t const wi = mem[q] - w_lo;
+                    uint32_t const wi = mem[q];
                     Walk& wk = walks[wi];
                     if (wk.state != W_WAITING) continue;
                     bool skip = false, blocked = false;
@@ -737,7 +806,7 @@ void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t r
                     }
                     if (!skip) {
                         for (uint32_t e = S.first_open; e < q; ++e) {
-                            Walk const& u = walks[mem[e] - w_lo];
+                            Walk const& u = walks[mem[e]];
                             if (u.state != W_DONE && u.r_start <= wk.t_start && u.r_end >= wk.t_end) { blocked = true; break; }
                         }
                     }
@@ -792,7 +861,7 @@ void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t r
             Walk& wk = walks[wi];
             if (is_root) {
                 // verified_intervals.insert, verification.cpp:106-109 / :40-41 (also when the root alignment failed)
-                if (ivopt) gstate[wk.group - g_lo].inserted.push_back(wi);
+                if (ivopt) gstate[wk.group].inserted.push_back(wi);
                 if (exists) {
                     wk.hit = true; wk.num_errors = uint32_t(r->score);
                     if (J->cfg.without_cigar) wk.start_in_reference = wk.root_span.offset + (wk.root_span.length - r->end_col);
@@ -889,6 +958,7 @@ void fxg_destroy(fxg_ctx* c) {
     cudaDeviceSynchronize();
     c->refs.packed.release();
     c->d_tmp.release();
+    for (Pool& p : c->spare_pools) p.release();
     for (auto& w : c->workers) w->release();
     if (c->ev_run0) cudaEventDestroy(c->ev_run0);
     if (c->ev_run1) cudaEventDestroy(c->ev_run1);
@@ -926,6 +996,7 @@ int fxg_set_references(fxg_ctx* c, size_t n_refs, const uint8_t* const* ranks, c
     }
     c->d_tmp.release();
     c->have_refs = true;
+    refresh_trace_budget(c);
     return FXG_OK;
 }
 
@@ -955,6 +1026,7 @@ int fxg_align_batch_stage(fxg_ctx* c, const fxg_align_task* tasks, size_t n_task
     fxg_batch* b = new (std::nothrow) fxg_batch();
     if (!b) return FXG_ERR_OUT_OF_MEMORY;
     b->tasks.assign(tasks, tasks + n_tasks);
+    b->pool = take_pool(c);
     rc = stage_pool(c, b->pool, query_pool, query_pool_len, nullptr, 0);
     if (rc == FXG_OK && inline_ref_pool_len) {
         b->pool.inline_len = inline_ref_pool_len;
@@ -966,7 +1038,7 @@ int fxg_align_batch_stage(fxg_ctx* c, const fxg_align_task* tasks, size_t n_task
         }
     }
     if (rc == FXG_OK && cudaStreamSynchronize(c->workers[0]->stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
-    if (rc != FXG_OK) { b->pool.release(); delete b; return rc; }
+    if (rc != FXG_OK) { give_pool(c, b->pool); delete b; return rc; }
     *out = b;
     return FXG_OK;
 }
@@ -1046,7 +1118,7 @@ int fxg_align_batch_fetch(fxg_ctx* c, fxg_batch* b, fxg_align_result* results, u
 
 void fxg_batch_free(fxg_ctx* c, fxg_batch* b) {
     if (!b) return;
-    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); b->pool.release(); }
+    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); give_pool(c, b->pool); }
     delete b;
 }
 
@@ -1102,54 +1174,19 @@ int fxg_verify_stage(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     j->nodes.assign(nodes, nodes + n_nodes);
     j->anchors.assign(anchors, anchors + n_anchors);
     j->pool_len = pool_len;
+    j->pool = take_pool(c);
 
-    // ---- schedule template: one Walk per anchor in the reference's order (read, forward package, reverse package);
-    //      anchors of one (read, orientation, reference) share a verified_intervals set (parallelization.cpp:224-226)
-    bool const direct = cfg->verification_kind == FXG_KIND_DIRECT_FULL;
-    double const ratio = cfg->extra_verification_ratio;
-    j->walks.reserve(n_anchors);
-    j->read_walk_begin.reserve(n_reads + 1); j->read_group_begin.reserve(n_reads + 1);
-    std::vector<std::vector<uint32_t>> tmp_groups;
-    std::vector<int64_t> ref_to_group;
+    j->read_walk_begin.resize(n_reads + 1);
+    uint32_t n_walks_total = 0;
     for (size_t ri = 0; ri < n_reads; ++ri) {
-        fxg_read const& R = j->reads[ri];
-        j->read_walk_begin.push_back(uint32_t(j->walks.size()));
-        j->read_group_begin.push_back(uint32_t(j->groups.size()));
-        const fxg_pex_node* inner = j->nodes.data() + R.node_offset;
-        const fxg_pex_node* leaves = inner + R.num_inner;
-        fxg_pex_node const& root = R.num_inner ? inner[0] : leaves[0];
-        for (int orient = 0; orient < 2; ++orient) {
-            uint32_t const a0 = uint32_t(R.anchor_offset) + (orient ? R.num_anchors_forward : 0);
-            uint32_t const na = orient ? R.num_anchors_reverse : R.num_anchors_forward;
-            tmp_groups.clear(); ref_to_group.assign(c->refs.len.size(), -1);
-            uint32_t const group_base = uint32_t(j->groups.size());
-            for (uint32_t q = 0; q < na; ++q) {
-                fxg_anchor const& A = j->anchors[a0 + q];
-                fxg_pex_node const& leaf = leaves[A.pex_leaf_index];
-                Walk wk{};
-                wk.read = uint32_t(ri); wk.anchor = a0 + q; wk.orient = uint8_t(orient); wk.state = W_WAITING;
-                wk.root_span = compute_span(A.reference_position, root, leaf.query_index_from, c->refs.len[A.reference_id], ratio);
-                wk.r_start = wk.root_span.offset; wk.r_end = wk.root_span.offset + wk.root_span.length;
-                wk.t_start = wk.r_start; wk.t_end = wk.r_end;
-                trim(wk.t_start, wk.t_end, wk.root_span.extra);
-                wk.node = (direct || leaf.parent_id == FXG_NULL_ID) ? &root : &inner[leaf.parent_id];
-                if (ref_to_group[A.reference_id] < 0) { ref_to_group[A.reference_id] = int64_t(tmp_groups.size()); tmp_groups.emplace_back(); }
-                wk.group = group_base + uint32_t(ref_to_group[A.reference_id]);
-                tmp_groups[size_t(ref_to_group[A.reference_id])].push_back(uint32_t(j->walks.size()));
-                j->walks.push_back(wk);
-            }
-            for (auto const& g : tmp_groups) {
-                j->groups.push_back(Group{uint32_t(j->group_members.size()), uint32_t(g.size())});
-                j->group_members.insert(j->group_members.end(), g.begin(), g.end());
-            }
-        }
+        j->read_walk_begin[ri] = n_walks_total;
+        n_walks_total += j->reads[ri].num_anchors_forward + j->reads[ri].num_anchors_reverse;
     }
-    j->read_walk_begin.push_back(uint32_t(j->walks.size()));
-    j->read_group_begin.push_back(uint32_t(j->groups.size()));
+    j->read_walk_begin[n_reads] = n_walks_total;
 
     rc = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len);
     if (rc == FXG_OK && cudaStreamSynchronize(c->workers[0]->stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
-    if (rc != FXG_OK) { j->pool.release(); delete j; return rc; }
+    if (rc != FXG_OK) { give_pool(c, j->pool); delete j; return rc; }
     *out = j;
     return FXG_OK;
 }
@@ -1163,10 +1200,10 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
     if (n_reads == 0) { J->ran = true; return FXG_OK; }
 
     // ---- split the reads into contiguous parts with similar numbers of anchors, one part per worker ----
-    size_t const n_parts = std::min<size_t>(c->workers.size(), std::max<size_t>(1, std::min<size_t>(n_reads, J->walks.size() / 256 + 1)));
+    size_t const n_parts = std::min<size_t>(c->workers.size(), std::max<size_t>(1, std::min<size_t>(n_reads, size_t(J->read_walk_begin[n_reads]) / 256 + 1)));
     std::vector<uint32_t> cut(n_parts + 1, 0);
     for (size_t p = 1; p < n_parts; ++p) {
-        uint64_t const target = uint64_t(J->walks.size()) * p / n_parts;
+        uint64_t const target = uint64_t(J->read_walk_begin[n_reads]) * p / n_parts;
         auto it = std::lower_bound(J->read_walk_begin.begin(), J->read_walk_begin.begin() + n_reads, uint32_t(target));
         cut[p] = std::max(cut[p - 1], uint32_t(it - J->read_walk_begin.begin()));
     }
@@ -1191,6 +1228,11 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
         add_counters(c->ctr, c->workers[p]->ctr);
         if (outs[p].rc != FXG_OK) { c->err = c->workers[p]->err; return outs[p].rc; }
     }
+    {
+        size_t n_al = 0, n_cig = 0;
+        for (size_t p = 0; p < n_parts; ++p) { n_al += outs[p].alignments.size(); n_cig += c->workers[p]->cigar_pool.size(); }
+        J->alignments.reserve(n_al); J->cigars.reserve(n_cig);
+    }
     for (size_t p = 0; p < n_parts; ++p) {
         uint64_t const shift = J->cigars.size();
         std::vector<uint32_t> const& pool = c->workers[p]->cigar_pool;
@@ -1212,7 +1254,7 @@ const fxg_stats* fxg_job_stats(const fxg_job* j) { return j ? &j->stats : nullpt
 
 void fxg_job_free(fxg_ctx* c, fxg_job* j) {
     if (!j) return;
-    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); j->pool.release(); }
+    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); give_pool(c, j->pool); }
     delete j;
 }
 

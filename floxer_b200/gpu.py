@@ -111,13 +111,16 @@ class Job:
         return self
 
     def alignments(self):
+        """(alignments[abi.ALIGNMENT_DTYPE], cigar_pool[uint32]) copied out of the job (one copy each)."""
         L = lib()
         n = L.fxg_job_num_alignments(self._h)
-        al = np.frombuffer(C.string_at(L.fxg_job_alignments(self._h), n * abi.ALIGNMENT_DTYPE.itemsize),
-                           dtype=abi.ALIGNMENT_DTYPE).copy() if n else np.zeros(0, dtype=abi.ALIGNMENT_DTYPE)
         nc = L.fxg_job_cigar_len(self._h)
-        cg = np.frombuffer(C.string_at(L.fxg_job_cigar_pool(self._h), nc * 4), dtype=np.uint32).copy() if nc \
-            else np.zeros(0, dtype=np.uint32)
+        al = np.empty(n, dtype=abi.ALIGNMENT_DTYPE)
+        cg = np.empty(nc, dtype=np.uint32)
+        if n:
+            C.memmove(al.ctypes.data, L.fxg_job_alignments(self._h), n * abi.ALIGNMENT_DTYPE.itemsize)
+        if nc:
+            C.memmove(cg.ctypes.data, L.fxg_job_cigar_pool(self._h), nc * 4)
         return al, cg
 
     def stats(self) -> dict:
