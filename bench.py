@@ -217,15 +217,22 @@ def main() -> int:
     job.free()
 
     # ---- end-to-end arm: host buffers in, alignments + CIGARs out, every step ----
-    ctx.reset_counters()
     e2e_ms = []
-    for it in range(max(1, min(args.steps, 3))):
+    checksum = 0
+    n_e2e_steps = max(1, min(args.steps, 5))
+    for it in range(1 + n_e2e_steps):                    # the first pass is warm-up (page-locked pools are allocated once)
+        if it == 1:
+            ctx.reset_counters()
         flush.fill_(it & 0xff)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        j2 = ctx.verify_reads(batch, cfg)
-        a2, c2 = j2.alignments()
-        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        j2 = ctx.verify_reads(batch, cfg)                # host buffers in: H2D, all waves, tracebacks, D2H of alignments + CIGARs
+        a2, c2 = j2.alignments(copy=False)               # what a C caller reads: the job's own result arrays
+        checksum ^= int(a2["start_in_reference"].sum()) ^ int(a2["num_errors"].sum()) ^ len(c2)
+        dt = (time.perf_counter() - t0) * 1e3
+        if it:
+            e2e_ms.append(dt)
+        del a2, c2
         j2.free()
     e2e_ctr = ctx.counters()
     n_e2e = len(e2e_ms)

@@ -421,16 +421,15 @@ struct WalkTask {
     uint32_t n, m;          // sub-window length (== end column) and query length
     uint32_t group, words;  // G and W of the trace pass
     uint32_t flags;
-    uint32_t cigar_cap;     // capacity of the per-task scratch (ops)
-    uint64_t scratch_base;  // per-task scratch in the cigar scratch buffer
+    uint32_t cigar_cap;     // size of this task's slot in the cigar buffer (ops)
+    uint64_t cigar_base;    // first op of the slot; the cigar ends at cigar_base + cigar_cap
     uint32_t out;
     uint32_t reserved;
 };
 
 struct WalkResult {
     uint32_t begin_col;     // column where the traceback reached row 0 (sequence1_begin_position)
-    uint32_t cigar_len;     // 0xffffffff on overflow / inconsistency
-    uint64_t cigar_offset;  // position in the compact cigar pool
+    uint32_t cigar_len;     // 0xffffffff on overflow / inconsistency; the ops are the LAST cigar_len entries of the slot
 };
 
 struct WalkLaunch {
@@ -438,10 +437,7 @@ struct WalkLaunch {
     const uint32_t* trace;
     const uint32_t* ref_packed; const uint32_t* inline_packed;
     const uint8_t* query_pool;
-    uint32_t* scratch;            // per-task reversed runs
-    uint32_t* cigar_pool;         // compact output
-    unsigned long long* cigar_cursor;
-    uint64_t cigar_pool_cap;
+    uint32_t* cigars;             // per-task slots; the traceback runs backwards, so each slot is filled from its end
     WalkResult* results;
 };
 
@@ -465,7 +461,7 @@ __global__ void __launch_bounds__(32 * kWalkWarps) walk_kernel(WalkLaunch const 
     uint32_t const W = T.words, G = T.group, ROWS = 32 * W;
     uint32_t const nb = (T.m + ROWS - 1) / ROWS;
     uint32_t const pad = nb * ROWS - T.m;
-    uint32_t* const runs = L.scratch + T.scratch_base;
+    uint32_t* const slot_end = L.cigars + T.cigar_base + T.cigar_cap;      // run q (counted from the alignment's end) lives at slot_end[-1 - q]
     uint32_t n_runs = 0, cur_op = 0, cur_len = 0;
     bool bad = false;
     uint32_t i = T.m, j = T.n;
@@ -481,7 +477,7 @@ __global__ void __launch_bounds__(32 * kWalkWarps) walk_kernel(WalkLaunch const 
     // emit `len` copies of `op` (uniform across the warp)
     auto emit = [&](uint32_t op, uint32_t len) {
         if (op == cur_op) { cur_len += len; return; }
-        if (cur_len) { if (n_runs < T.cigar_cap) { if (lane == 0) runs[n_runs] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
+        if (cur_len) { if (n_runs < T.cigar_cap) { if (lane == 0) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
         cur_op = op; cur_len = len;
     };
     uint4 v = make_uint4(0, 0, 0, 0);          // this lane's column of the tile: hp, vp of word w0 and of word w0 - 1
@@ -549,22 +545,8 @@ __global__ void __launch_bounds__(32 * kWalkWarps) walk_kernel(WalkLaunch const 
             i -= run; j -= run;
         }
     }
-    if (cur_len) { if (n_runs < T.cigar_cap) { if (lane == 0) runs[n_runs] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
-    __syncwarp();
-    WalkResult R; R.begin_col = j; R.cigar_len = bad ? 0xffffffffu : n_runs; R.cigar_offset = 0;
-    if (!bad) {
-        unsigned long long at = 0;
-        if (lane == 0) at = atomicAdd(L.cigar_cursor, (unsigned long long)n_runs);
-        at = __shfl_sync(0xffffffffu, at, 0);
-        if (at + n_runs <= L.cigar_pool_cap) {
-            __threadfence_block();
-            for (uint32_t p = lane; p < n_runs; p += 32) L.cigar_pool[at + p] = runs[n_runs - 1 - p];
-            R.cigar_offset = at;
-        } else {
-            R.cigar_len = 0xffffffffu;
-        }
-    }
-    if (lane == 0) L.results[T.out] = R;
+    if (cur_len) { if (n_runs < T.cigar_cap) { if (lane == 0) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
+    if (lane == 0) { WalkResult R; R.begin_col = j; R.cigar_len = bad ? 0xffffffffu : n_runs; L.results[T.out] = R; }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -107,17 +108,16 @@ struct Worker {
     int id = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf d_tasks, d_results, d_trace, d_wtasks, d_wresults, d_cig_scratch, d_cig_pool, d_cursor;
-    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults, h_cigars;
+    DevBuf d_tasks, d_results, d_trace, d_wtasks, d_wresults, d_cigars;
+    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults;
     fxg_counters ctr{};
     std::string err;
     std::vector<ConfigCacheEntry> cfg_cache = std::vector<ConfigCacheEntry>(8192);
     std::vector<uint64_t> keys, keys_tmp;
     std::vector<Config> cfgs;
-    std::vector<uint32_t> cigar_pool;    // host copy of the cigars of the current run
     void release() {
-        for (DevBuf* b : {&d_tasks, &d_results, &d_trace, &d_wtasks, &d_wresults, &d_cig_scratch, &d_cig_pool, &d_cursor}) b->release();
-        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults, &h_cigars}) b->release();
+        for (DevBuf* b : {&d_tasks, &d_results, &d_trace, &d_wtasks, &d_wresults, &d_cigars}) b->release();
+        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults}) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -162,6 +162,7 @@ struct fxg_ctx {
     DevBuf d_tmp;
     uint64_t trace_budget = 0;
     std::vector<Pool> spare_pools;       // device buffers of freed batches / jobs, reused by the next stage call
+    std::vector<PinnedBuf> spare_pinned; // page-locked cigar pools of freed batches / jobs (cudaHostAlloc costs milliseconds)
     std::mutex mu;
 };
 
@@ -169,7 +170,8 @@ struct fxg_batch {
     std::vector<fxg_align_task> tasks;
     Pool pool;
     std::vector<fxg_align_result> results;
-    std::vector<uint32_t> cigars;
+    PinnedBuf cigars;                    // the device writes the cigars of a run straight into this pool
+    size_t cigars_len = 0;
     bool ran = false;
 };
 
@@ -205,7 +207,8 @@ struct fxg_job {
     std::vector<uint32_t> read_walk_begin;   // per read (+1 sentinel): index of its first walk (= anchor) in job order
     // results
     std::vector<fxg_alignment> alignments;
-    std::vector<uint32_t> cigars;
+    PinnedBuf cigars;                    // page-locked; every worker's cigars arrive here directly from the device
+    size_t cigars_len = 0;
     fxg_stats stats{};
     bool ran = false;
 };
@@ -465,10 +468,15 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     return FXG_OK;
 }
 
-// Trace passes + walks for `reqs`; fills outs[i] and appends the cigars to w.cigar_pool (offsets index
-// that pool).  Works in chunks bounded by `budget_bytes` of trace planes.
+// ops reserved for the cigar of an alignment with s errors: at most s error runs and s + 1 match runs
+inline uint64_t cigar_cap_for(uint32_t s) { return uint64_t(2) * s + 3; }
+
+// Trace passes + walks for `reqs`; fills outs[i].  The cigar of request i is written by the device into its slot of
+// cigar_cap_for(s) ops; slots follow each other in request order, and the whole region is copied straight into
+// host_cigars (page-locked, region_base = index of its first op in the pool the offsets refer to).
+// Works in chunks bounded by `budget_bytes` of trace planes.
 int run_traces(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<TraceReq> const& reqs, uint64_t budget_bytes,
-               std::vector<TraceOut>& outs) {
+               uint32_t* host_cigars, uint64_t region_base, std::vector<TraceOut>& outs) {
     size_t const N = reqs.size();
     outs.assign(N, TraceOut{0, 0, 0});
     if (N == 0) return FXG_OK;
@@ -485,13 +493,14 @@ int run_traces(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<TraceReq> co
         if (words[i] > budget_words) budget_words = words[i];
     }
     std::vector<Pass> passes; std::vector<uint64_t> tbase, sbase;
+    uint64_t region_at = 0;                 // ops of the region used by earlier chunks
     size_t i = 0;
     while (i < N) {
         size_t j = i; uint64_t used = 0, cig_cap_total = 0;
         passes.clear(); tbase.clear(); sbase.clear();
         while (j < N && (j == i || used + words[j] <= budget_words)) {
             passes.push_back(reqs[j].pass); tbase.push_back(used); used += words[j];
-            sbase.push_back(cig_cap_total); cig_cap_total += uint64_t(2) * reqs[j].s_star + 3;
+            sbase.push_back(cig_cap_total); cig_cap_total += cigar_cap_for(reqs[j].s_star);
             ++j;
         }
         size_t const M = j - i;
@@ -504,7 +513,7 @@ int run_traces(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<TraceReq> co
         g_prof.start(w);
         // walks
         CUDA_TRY(w.err, w.h_wtasks.ensure(M * sizeof(WalkTask)));
-        CUDA_TRY(w.err, w.h_wresults.ensure(M * sizeof(WalkResult) + 8));
+        CUDA_TRY(w.err, w.h_wresults.ensure(M * sizeof(WalkResult)));
         WalkTask* wt = w.h_wtasks.as<WalkTask>();
         for (size_t q = 0; q < M; ++q) {
             TraceReq const& R = reqs[i + q];
@@ -515,49 +524,36 @@ int run_traces(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<TraceReq> co
             WalkTask& t = wt[q];
             t.trace_base = tbase[q]; t.ref_base = R.pass.ref_base; t.query_base = R.pass.query_base;
             t.n = R.pass.n; t.m = R.pass.m; t.group = cfgs[i + q].G; t.words = uint32_t(kWidths[cfgs[i + q].widx]);
-            t.flags = R.pass.flags; t.cigar_cap = 2 * R.s_star + 3; t.scratch_base = sbase[q]; t.out = uint32_t(q); t.reserved = 0;
+            t.flags = R.pass.flags; t.cigar_cap = uint32_t(cigar_cap_for(R.s_star)); t.cigar_base = sbase[q]; t.out = uint32_t(q); t.reserved = 0;
         }
         CUDA_TRY(w.err, w.d_wtasks.ensure(M * sizeof(WalkTask)));
         CUDA_TRY(w.err, w.d_wresults.ensure(M * sizeof(WalkResult)));
-        CUDA_TRY(w.err, w.d_cig_scratch.ensure(cig_cap_total * 4));
-        CUDA_TRY(w.err, w.d_cig_pool.ensure(cig_cap_total * 4));
-        CUDA_TRY(w.err, w.d_cursor.ensure(8));
+        CUDA_TRY(w.err, w.d_cigars.ensure(cig_cap_total * 4));
         CUDA_TRY(w.err, cudaMemcpyAsync(w.d_wtasks.p, wt, M * sizeof(WalkTask), cudaMemcpyHostToDevice, w.stream));
-        CUDA_TRY(w.err, cudaMemsetAsync(w.d_cursor.p, 0, 8, w.stream));
         w.ctr.h2d_bytes += M * sizeof(WalkTask);
         WalkLaunch WL{};
         WL.tasks = w.d_wtasks.as<WalkTask>(); WL.n_tasks = uint32_t(M); WL.trace = w.d_trace.as<uint32_t>();
         WL.ref_packed = c->refs.packed.as<uint32_t>(); WL.inline_packed = pool.inline_packed.as<uint32_t>();
-        WL.query_pool = pool.bytes.as<uint8_t>(); WL.scratch = w.d_cig_scratch.as<uint32_t>();
-        WL.cigar_pool = w.d_cig_pool.as<uint32_t>(); WL.cigar_cursor = w.d_cursor.as<unsigned long long>();
-        WL.cigar_pool_cap = cig_cap_total; WL.results = w.d_wresults.as<WalkResult>();
+        WL.query_pool = pool.bytes.as<uint8_t>(); WL.cigars = w.d_cigars.as<uint32_t>();
+        WL.results = w.d_wresults.as<WalkResult>();
         CUDA_TRY(w.err, cudaEventRecord(w.ev0, w.stream));
         walk_kernel<<<uint32_t((M + kWalkWarps - 1) / kWalkWarps), 32 * kWalkWarps, 0, w.stream>>>(WL);
         CUDA_TRY(w.err, cudaGetLastError());
         CUDA_TRY(w.err, cudaEventRecord(w.ev1, w.stream));
         w.ctr.kernel_launches++;
         WalkResult* wr = w.h_wresults.as<WalkResult>();
-        unsigned long long* cursor = reinterpret_cast<unsigned long long*>(wr + M);
         CUDA_TRY(w.err, cudaMemcpyAsync(wr, w.d_wresults.p, M * sizeof(WalkResult), cudaMemcpyDeviceToHost, w.stream));
-        CUDA_TRY(w.err, cudaMemcpyAsync(cursor, w.d_cursor.p, 8, cudaMemcpyDeviceToHost, w.stream));
+        CUDA_TRY(w.err, cudaMemcpyAsync(host_cigars + region_at, w.d_cigars.p, cig_cap_total * 4, cudaMemcpyDeviceToHost, w.stream));
         CUDA_TRY(w.err, cudaStreamSynchronize(w.stream));
         float ms = 0;
         CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
         w.ctr.trace_kernel_ms += ms;
-        size_t const n_ops = size_t(*cursor);
-        if (n_ops) {
-            CUDA_TRY(w.err, w.h_cigars.ensure(n_ops * 4));
-            CUDA_TRY(w.err, cudaMemcpyAsync(w.h_cigars.p, w.d_cig_pool.p, n_ops * 4, cudaMemcpyDeviceToHost, w.stream));
-            CUDA_TRY(w.err, cudaStreamSynchronize(w.stream));
-        }
-        w.ctr.d2h_bytes += M * sizeof(WalkResult) + n_ops * 4;
-        // the device hands out pool space with an atomic counter; re-pack in task order so that results are deterministic
-        const uint32_t* const dev_pool = w.h_cigars.as<uint32_t>();
+        w.ctr.d2h_bytes += M * sizeof(WalkResult) + cig_cap_total * 4;
         for (size_t q = 0; q < M; ++q) {
-            if (wr[q].cigar_len == 0xffffffffu) return fail(w.err, FXG_ERR_CUDA, "internal: traceback overflowed its CIGAR scratch");
-            outs[i + q] = TraceOut{wr[q].begin_col, w.cigar_pool.size(), wr[q].cigar_len};
-            w.cigar_pool.insert(w.cigar_pool.end(), dev_pool + wr[q].cigar_offset, dev_pool + wr[q].cigar_offset + wr[q].cigar_len);
+            if (wr[q].cigar_len == 0xffffffffu) return fail(w.err, FXG_ERR_CUDA, "internal: traceback overflowed its CIGAR slot");
+            outs[i + q] = TraceOut{wr[q].begin_col, region_base + region_at + sbase[q] + wt[q].cigar_cap - wr[q].cigar_len, wr[q].cigar_len};
         }
+        region_at += cig_cap_total;
         i = j;
         g_prof.lap(w, 12);
     }
@@ -590,6 +586,21 @@ Pool take_pool(fxg_ctx* c) {
 void give_pool(fxg_ctx* c, Pool& p) {
     if (c->spare_pools.size() < 4) c->spare_pools.push_back(p); else p.release();
     p = Pool{};
+}
+
+PinnedBuf take_pinned(fxg_ctx* c) {
+    PinnedBuf b;
+    if (!c->spare_pinned.empty()) {          // the largest one: the next run most likely needs as much as the last
+        size_t best = 0;
+        for (size_t i = 1; i < c->spare_pinned.size(); ++i) if (c->spare_pinned[i].cap > c->spare_pinned[best].cap) best = i;
+        b = c->spare_pinned[best];
+        c->spare_pinned.erase(c->spare_pinned.begin() + long(best));
+    }
+    return b;
+}
+void give_pinned(fxg_ctx* c, PinnedBuf& b) {
+    if (b.p && c->spare_pinned.size() < 4) c->spare_pinned.push_back(b); else b.release();
+    b = PinnedBuf{};
 }
 
 int check_ranks(std::string& err, const uint8_t* p, size_t n, const char* what) {
@@ -746,49 +757,78 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
 }
 
 struct PartOut {
-    std::vector<fxg_alignment> alignments;   // cigar offsets index the worker's cigar pool
+    std::vector<fxg_alignment> alignments;   // cigar offsets index the job's cigar pool
     fxg_stats stats{};
     int rc = FXG_OK;
 };
 
-// query_verifier::verify() for every anchor of reads [read_lo, read_hi), level-synchronously.
-// Sequential semantics of the verified-interval sets are preserved exactly: a walk starts only when no
+// what one part carries from its score phase to its traceback phase
+struct PartState {
+    std::vector<Walk> walks; std::vector<Group> groups; std::vector<uint32_t> group_members;   // indices local to this part
+    std::vector<TraceReq> reqs; std::vector<uint32_t> req_walk;
+    uint64_t cigar_cap = 0;                  // ops this part needs in the job's cigar pool
+    std::chrono::steady_clock::time_point t0;
+    PartOut out;
+};
+
+// hops from an inner node to the root, memoised per read (the trees are small)
+uint8_t node_dist(const fxg_pex_node* inner, std::vector<uint8_t>& memo, uint64_t id) {
+    if (memo[id] != 0xff) return memo[id];
+    uint8_t d = 0;
+    if (inner[id].parent_id != FXG_NULL_ID) d = uint8_t(std::min<int>(254, node_dist(inner, memo, inner[id].parent_id) + 1));
+    return memo[id] = d;
+}
+
+// query_verifier::verify() for every anchor of reads [read_lo, read_hi), level-synchronously: every score pass.
+// Without the interval optimisation the walks are advanced deepest node first, so that all alignments of one tree level
+// (in particular every root alignment) end up in the same wave and fill the machine together.
+// With it, the sequential semantics of the verified-interval sets are preserved exactly: a walk starts only when no
 // earlier walk of its (read, orientation, reference) group that could still verify its root window is
 // unresolved, and it is skipped if an EARLIER walk inserted a window containing its trimmed root window.
-void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, uint64_t trace_budget, PartOut& out) {
+void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, PartState& P) {
     cudaSetDevice(c->device);
-    auto const part_t0 = std::chrono::steady_clock::now();
-    struct PartReport {
-        Worker& w; std::chrono::steady_clock::time_point t0; size_t* n_walks;
-        ~PartReport() {
-            if (g_prof.on) fprintf(stderr, "[fxg] worker %d: %zu walks, %.3f ms, %llu waves\n", w.id, *n_walks,
-                                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
-                                   (unsigned long long)w.ctr.waves);
-        }
-    };
+    P.t0 = std::chrono::steady_clock::now();
+    PartOut& out = P.out;
     g_prof.start(w);
     bool const ivopt = J->cfg.interval_optimization != 0;
-    std::vector<Walk> walks; std::vector<Group> groups; std::vector<uint32_t> group_members;   // indices local to this part
+    std::vector<Walk>& walks = P.walks; std::vector<Group>& groups = P.groups; std::vector<uint32_t>& group_members = P.group_members;
     build_walks(c, J, read_lo, read_hi, walks, groups, group_members);
-    size_t n_walks = walks.size();
-    PartReport part_report{w, part_t0, &n_walks};
+    size_t const n_walks = walks.size();
     struct GroupState { uint32_t first_open = 0; std::vector<uint32_t> inserted; };
     std::vector<GroupState> gstate(groups.size());
-    w.cigar_pool.clear();
+
+    // ---- tree level of every walk's first node ----
+    std::vector<std::vector<uint32_t>> level;            // !ivopt: walks waiting for the wave of their node's level
+    if (!ivopt) {
+        std::vector<uint8_t> memo;
+        std::vector<uint8_t> dist(n_walks, 0);
+        uint32_t cur_read = UINT32_MAX; uint8_t max_dist = 0;
+        for (uint32_t i = 0; i < n_walks; ++i) {
+            Walk const& wk = walks[i];
+            fxg_read const& R = J->reads[wk.read];
+            const fxg_pex_node* inner = J->nodes.data() + R.node_offset;
+            if (wk.read != cur_read) { cur_read = wk.read; memo.assign(R.num_inner, 0xff); }
+            if (R.num_inner && wk.node >= inner && wk.node < inner + R.num_inner) dist[i] = node_dist(inner, memo, uint64_t(wk.node - inner));
+            max_dist = std::max(max_dist, dist[i]);
+        }
+        level.resize(size_t(max_dist) + 1);
+        for (uint32_t i = 0; i < n_walks; ++i) { level[dist[i]].push_back(i); walks[i].state = W_WALKING; }
+    }
+    int cur_level = int(level.size()) - 1;
 
     std::vector<uint32_t> active, next_active;
     std::vector<Pass> passes; std::vector<uint32_t> pass_walk;
     std::vector<std::pair<uint32_t, bool>> no_pass;
-    std::vector<TraceReq> reqs; std::vector<uint32_t> req_walk;
+    std::vector<TraceReq>& reqs = P.reqs; std::vector<uint32_t>& req_walk = P.req_walk;
     size_t n_done = 0;
-    bool first_wave = true;
     g_prof.lap(w, 0);
 
     while (n_done < n_walks) {
         g_prof.start(w);
         // ---- admission ----
         if (!ivopt) {
-            if (first_wave) { active.resize(n_walks); for (uint32_t i = 0; i < n_walks; ++i) { active[i] = i; walks[i].state = W_WALKING; } }
+            while (cur_level >= 0 && level[size_t(cur_level)].empty()) --cur_level;
+            if (cur_level >= 0) { active.swap(level[size_t(cur_level)]); level[size_t(cur_level)].clear(); }
         } else {
             for (uint32_t g = 0; g < groups.size(); ++g) {
                 Group const& G = groups[g];
@@ -819,7 +859,6 @@ void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t r
                 }
             }
         }
-        first_wave = false;
         if (active.empty()) {
             if (n_done < n_walks) { out.rc = fail(w.err, FXG_ERR_STATE, "internal: verification scheduler stalled"); return; }
             break;
@@ -865,7 +904,7 @@ void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t r
                 if (exists) {
                     wk.hit = true; wk.num_errors = uint32_t(r->score);
                     if (J->cfg.without_cigar) wk.start_in_reference = wk.root_span.offset + (wk.root_span.length - r->end_col);
-                    else { reqs.push_back(trace_req_for(*p, uint32_t(r->score), r->end_col)); req_walk.push_back(wi); }
+                    else { reqs.push_back(trace_req_for(*p, uint32_t(r->score), r->end_col)); req_walk.push_back(wi); P.cigar_cap += cigar_cap_for(uint32_t(r->score)); }
                 }
                 wk.state = W_DONE; ++n_done;
             } else if (exists) {
@@ -883,22 +922,36 @@ void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t r
             finish(pass_walk[q], is_root, exists, &res[q], &passes[q]);
         }
         for (auto const& np : no_pass) finish(np.first, np.second, false, nullptr, nullptr);
-        active.swap(next_active);
+        if (!ivopt) {
+            // survivors moved one level up: they join the walks that start there
+            active.clear();
+            if (!next_active.empty()) {
+                if (cur_level == 0) { out.rc = fail(w.err, FXG_ERR_STATE, "internal: a walk survived above the root"); return; }
+                std::vector<uint32_t>& up = level[size_t(cur_level) - 1];
+                up.insert(up.end(), next_active.begin(), next_active.end());
+            }
+            --cur_level;
+        } else {
+            active.swap(next_active);
+        }
         g_prof.lap(w, 9);
     }
+}
 
-    // ---- tracebacks for accepted roots ----
+// tracebacks for the accepted roots of a part, cigars straight into the job's pool, then the part's alignments
+void verify_part_trace(fxg_ctx* c, Worker& w, fxg_job* J, uint64_t trace_budget, uint32_t* host_cigars, uint64_t region_base, PartState& P) {
+    PartOut& out = P.out;
     std::vector<TraceOut> touts;
-    out.rc = run_traces(c, w, J->pool, reqs, trace_budget, touts);
+    out.rc = run_traces(c, w, J->pool, P.reqs, trace_budget, host_cigars, region_base, touts);
     if (out.rc != FXG_OK) return;
-    for (size_t q = 0; q < reqs.size(); ++q) {
-        Walk& wk = walks[req_walk[q]];
-        wk.start_in_reference = wk.root_span.offset + reqs[q].col0 + touts[q].begin_col;
+    for (size_t q = 0; q < P.reqs.size(); ++q) {
+        Walk& wk = P.walks[P.req_walk[q]];
+        wk.start_in_reference = wk.root_span.offset + P.reqs[q].col0 + touts[q].begin_col;
         wk.cigar_offset = touts[q].cigar_offset; wk.cigar_len = touts[q].cigar_len;
     }
     // ---- emit in anchor order (= insertion order of the reference's single-thread run) ----
     g_prof.start(w);
-    for (Walk const& wk : walks) {
+    for (Walk const& wk : P.walks) {
         if (!wk.hit) continue;
         fxg_alignment a{};
         a.start_in_reference = wk.start_in_reference; a.cigar_offset = wk.cigar_offset; a.cigar_len = wk.cigar_len;
@@ -907,7 +960,34 @@ void verify_part(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t r
         out.alignments.push_back(a);
     }
     g_prof.lap(w, 13);
+    if (g_prof.on) fprintf(stderr, "[fxg] worker %d: %zu walks, %.3f ms, %llu waves\n", w.id, P.walks.size(),
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count(),
+                           (unsigned long long)w.ctr.waves);
 }
+
+// Meeting point of the parts between their score and traceback phases: the last part to arrive sizes the job's
+// page-locked cigar pool and hands every part its region.
+struct TracePlan {
+    std::mutex mu; std::condition_variable cv;
+    size_t arrived = 0, n_parts = 0;
+    std::vector<uint64_t> caps, bases;
+    PinnedBuf* pool = nullptr; size_t* pool_len = nullptr;
+    bool failed = false; std::string err;
+    void arrive_and_wait(size_t part, uint64_t cap) {
+        std::unique_lock<std::mutex> lock(mu);
+        caps[part] = cap;
+        if (++arrived == n_parts) {
+            uint64_t total = 0;
+            for (size_t p = 0; p < n_parts; ++p) { bases[p] = total; total += caps[p]; }
+            cudaError_t const e = pool->ensure(std::max<uint64_t>(total, 1) * 4);
+            if (e != cudaSuccess) { failed = true; err = std::string("cigar pool allocation: ") + cudaGetErrorString(e); }
+            *pool_len = size_t(total);
+            cv.notify_all();
+        } else {
+            cv.wait(lock, [&] { return arrived == n_parts; });
+        }
+    }
+};
 
 int default_workers() {
     if (const char* e = std::getenv("FXG_WORKERS")) { int v = std::atoi(e); if (v >= 1 && v <= 64) return v; }
@@ -959,6 +1039,7 @@ void fxg_destroy(fxg_ctx* c) {
     c->refs.packed.release();
     c->d_tmp.release();
     for (Pool& p : c->spare_pools) p.release();
+    for (PinnedBuf& b : c->spare_pinned) b.release();
     for (auto& w : c->workers) w->release();
     if (c->ev_run0) cudaEventDestroy(c->ev_run0);
     if (c->ev_run1) cudaEventDestroy(c->ev_run1);
@@ -1027,6 +1108,7 @@ int fxg_align_batch_stage(fxg_ctx* c, const fxg_align_task* tasks, size_t n_task
     if (!b) return FXG_ERR_OUT_OF_MEMORY;
     b->tasks.assign(tasks, tasks + n_tasks);
     b->pool = take_pool(c);
+    b->cigars = take_pinned(c);
     rc = stage_pool(c, b->pool, query_pool, query_pool_len, nullptr, 0);
     if (rc == FXG_OK && inline_ref_pool_len) {
         b->pool.inline_len = inline_ref_pool_len;
@@ -1038,7 +1120,7 @@ int fxg_align_batch_stage(fxg_ctx* c, const fxg_align_task* tasks, size_t n_task
         }
     }
     if (rc == FXG_OK && cudaStreamSynchronize(c->workers[0]->stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
-    if (rc != FXG_OK) { give_pool(c, b->pool); delete b; return rc; }
+    if (rc != FXG_OK) { give_pool(c, b->pool); give_pinned(c, b->cigars); delete b; return rc; }
     *out = b;
     return FXG_OK;
 }
@@ -1054,7 +1136,7 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
         RunTimer run_timer(c);
         size_t const N = b->tasks.size();
         b->results.assign(N, fxg_align_result{});
-        b->cigars.clear();
+        b->cigars_len = 0;
         std::vector<Pass> passes; passes.reserve(N);
         std::vector<uint32_t> owner; owner.reserve(N);
         for (size_t i = 0; i < N; ++i) {
@@ -1076,6 +1158,7 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
         rc = run_passes(c, w, b->pool, passes, nullptr, &res);
         std::vector<TraceReq> reqs; std::vector<uint32_t> req_owner;
         if (rc == FXG_OK) {
+            uint64_t cap = 0;
             for (size_t q = 0; q < passes.size(); ++q) {
                 fxg_align_task const& t = b->tasks[owner[q]];
                 fxg_align_result& r = b->results[owner[q]];
@@ -1084,13 +1167,14 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
                 if (t.mode == FXG_MODE_EXISTS) continue;
                 r.num_errors = uint32_t(res[q].score);
                 if (t.mode == FXG_MODE_NO_CIGAR) r.start_in_reference = t.reference_span_offset + (t.ref_len - res[q].end_col);   // alignment.cpp:135-139
-                else { reqs.push_back(trace_req_for(passes[q], uint32_t(res[q].score), res[q].end_col)); req_owner.push_back(owner[q]); }
+                else { reqs.push_back(trace_req_for(passes[q], uint32_t(res[q].score), res[q].end_col)); req_owner.push_back(owner[q]); cap += cigar_cap_for(uint32_t(res[q].score)); }
             }
-            w.cigar_pool.clear();
+            cudaError_t const e = b->cigars.ensure(std::max<uint64_t>(cap, 1) * 4);
+            if (e != cudaSuccess) rc = fail(w.err, FXG_ERR_CUDA, "cigar pool allocation: %s", cudaGetErrorString(e));
             std::vector<TraceOut> touts;
-            rc = run_traces(c, w, b->pool, reqs, trace_budget_bytes(c, 1), touts);
+            if (rc == FXG_OK) rc = run_traces(c, w, b->pool, reqs, trace_budget_bytes(c, 1), b->cigars.as<uint32_t>(), 0, touts);
             if (rc == FXG_OK) {
-                b->cigars = w.cigar_pool;
+                b->cigars_len = size_t(cap);
                 for (size_t q = 0; q < reqs.size(); ++q) {
                     fxg_align_task const& t = b->tasks[req_owner[q]];
                     fxg_align_result& r = b->results[req_owner[q]];
@@ -1109,16 +1193,17 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
 int fxg_align_batch_fetch(fxg_ctx* c, fxg_batch* b, fxg_align_result* results, uint32_t* cigar_pool, size_t cigar_capacity, size_t* cigar_used) {
     if (!c) return FXG_ERR_INVALID_ARGUMENT;
     if (!b || !b->ran || (b->tasks.size() && !results)) return fail(c->err, FXG_ERR_STATE, "batch has not been run");
-    if (cigar_used) *cigar_used = b->cigars.size();
-    if (b->cigars.size() > cigar_capacity) return fail(c->err, FXG_ERR_OVERFLOW, "cigar pool needs %zu entries, capacity is %zu", b->cigars.size(), cigar_capacity);
+    if (cigar_used) *cigar_used = b->cigars_len;
+    if (b->cigars_len > cigar_capacity) return fail(c->err, FXG_ERR_OVERFLOW, "cigar pool needs %zu entries, capacity is %zu", b->cigars_len, cigar_capacity);
     if (!b->results.empty()) std::memcpy(results, b->results.data(), b->results.size() * sizeof(fxg_align_result));
-    if (!b->cigars.empty()) std::memcpy(cigar_pool, b->cigars.data(), b->cigars.size() * 4);
+    if (b->cigars_len) std::memcpy(cigar_pool, b->cigars.p, b->cigars_len * 4);
     return FXG_OK;
 }
 
 void fxg_batch_free(fxg_ctx* c, fxg_batch* b) {
     if (!b) return;
-    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); give_pool(c, b->pool); }
+    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); give_pool(c, b->pool); give_pinned(c, b->cigars); }
+    else b->cigars.release();
     delete b;
 }
 
@@ -1175,6 +1260,7 @@ int fxg_verify_stage(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     j->anchors.assign(anchors, anchors + n_anchors);
     j->pool_len = pool_len;
     j->pool = take_pool(c);
+    j->cigars = take_pinned(c);
 
     j->read_walk_begin.resize(n_reads + 1);
     uint32_t n_walks_total = 0;
@@ -1186,7 +1272,7 @@ int fxg_verify_stage(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
 
     rc = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len);
     if (rc == FXG_OK && cudaStreamSynchronize(c->workers[0]->stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
-    if (rc != FXG_OK) { give_pool(c, j->pool); delete j; return rc; }
+    if (rc != FXG_OK) { give_pool(c, j->pool); give_pinned(c, j->cigars); delete j; return rc; }
     *out = j;
     return FXG_OK;
 }
@@ -1195,7 +1281,7 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
     if (!c || !J) return FXG_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(c->mu);
     CUDA_TRY(c->err, cudaSetDevice(c->device));
-    J->alignments.clear(); J->cigars.clear(); J->stats = fxg_stats{};
+    J->alignments.clear(); J->cigars_len = 0; J->stats = fxg_stats{};
     size_t const n_reads = J->reads.size();
     if (n_reads == 0) { J->ran = true; return FXG_OK; }
 
@@ -1208,53 +1294,61 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
         cut[p] = std::max(cut[p - 1], uint32_t(it - J->read_walk_begin.begin()));
     }
     cut[n_parts] = uint32_t(n_reads);
-    std::vector<PartOut> outs(n_parts);
+    std::vector<PartState> parts(n_parts);
+    TracePlan plan;
+    plan.n_parts = n_parts; plan.caps.assign(n_parts, 0); plan.bases.assign(n_parts, 0);
+    plan.pool = &J->cigars; plan.pool_len = &J->cigars_len;
     auto const vt0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - vt0).count(); };
     uint64_t const budget = trace_budget_bytes(c, n_parts);
-    double const t_budget = since();
     for (size_t p = 0; p < n_parts; ++p) c->workers[p]->ctr = fxg_counters{};
+    auto run_part = [&](size_t p) {
+        Worker& w = *c->workers[p];
+        PartState& P = parts[p];
+        verify_part_score(c, w, J, cut[p], cut[p + 1], P);
+        plan.arrive_and_wait(p, P.out.rc == FXG_OK ? P.cigar_cap : 0);       // every part arrives, also a failed one
+        if (P.out.rc != FXG_OK) return;
+        if (plan.failed) { w.err = plan.err; P.out.rc = FXG_ERR_CUDA; return; }
+        verify_part_trace(c, w, J, budget, J->cigars.as<uint32_t>() + plan.bases[p], plan.bases[p], P);
+    };
     {
         RunTimer run_timer(c);
         std::vector<std::thread> threads;
-        for (size_t p = 1; p < n_parts; ++p)
-            threads.emplace_back([&, p] { verify_part(c, *c->workers[p], J, cut[p], cut[p + 1], budget, outs[p]); });
-        verify_part(c, *c->workers[0], J, cut[0], cut[1], budget, outs[0]);
+        for (size_t p = 1; p < n_parts; ++p) threads.emplace_back(run_part, p);
+        run_part(0);
         for (auto& t : threads) t.join();
     }
     double const t_join = since();
     g_prof.report();
     for (size_t p = 0; p < n_parts; ++p) {
         add_counters(c->ctr, c->workers[p]->ctr);
-        if (outs[p].rc != FXG_OK) { c->err = c->workers[p]->err; return outs[p].rc; }
+        if (parts[p].out.rc != FXG_OK) { c->err = c->workers[p]->err; return parts[p].out.rc; }
     }
     {
-        size_t n_al = 0, n_cig = 0;
-        for (size_t p = 0; p < n_parts; ++p) { n_al += outs[p].alignments.size(); n_cig += c->workers[p]->cigar_pool.size(); }
-        J->alignments.reserve(n_al); J->cigars.reserve(n_cig);
+        size_t n_al = 0;
+        for (size_t p = 0; p < n_parts; ++p) n_al += parts[p].out.alignments.size();
+        J->alignments.reserve(n_al);
     }
     for (size_t p = 0; p < n_parts; ++p) {
-        uint64_t const shift = J->cigars.size();
-        std::vector<uint32_t> const& pool = c->workers[p]->cigar_pool;
-        J->cigars.insert(J->cigars.end(), pool.begin(), pool.end());
-        for (fxg_alignment a : outs[p].alignments) { if (a.cigar_len) a.cigar_offset += shift; J->alignments.push_back(a); }
-        uint64_t* d = reinterpret_cast<uint64_t*>(&J->stats); const uint64_t* s = reinterpret_cast<const uint64_t*>(&outs[p].stats);
-        for (size_t f = 0; f < sizeof(fxg_stats) / sizeof(uint64_t); ++f) d[f] += s[f];
+        J->alignments.insert(J->alignments.end(), parts[p].out.alignments.begin(), parts[p].out.alignments.end());
+        uint64_t* d = reinterpret_cast<uint64_t*>(&J->stats); const uint64_t* sp = reinterpret_cast<const uint64_t*>(&parts[p].out.stats);
+        for (size_t f = 0; f < sizeof(fxg_stats) / sizeof(uint64_t); ++f) d[f] += sp[f];
     }
     J->ran = true;
-    if (g_prof.on) fprintf(stderr, "[fxg] verify_run: budget query %.3f ms, parts done %.3f ms, merged %.3f ms\n", t_budget, t_join, since());
+    if (g_prof.on) fprintf(stderr, "[fxg] verify_run: parts done %.3f ms, merged %.3f ms\n", t_join, since());
     return FXG_OK;
 }
 
 size_t fxg_job_num_alignments(const fxg_job* j) { return j ? j->alignments.size() : 0; }
 const fxg_alignment* fxg_job_alignments(const fxg_job* j) { return j ? j->alignments.data() : nullptr; }
-size_t fxg_job_cigar_len(const fxg_job* j) { return j ? j->cigars.size() : 0; }
-const uint32_t* fxg_job_cigar_pool(const fxg_job* j) { return j ? j->cigars.data() : nullptr; }
+size_t fxg_job_cigar_len(const fxg_job* j) { return j ? j->cigars_len : 0; }
+const uint32_t* fxg_job_cigar_pool(const fxg_job* j) { return j ? j->cigars.as<uint32_t>() : nullptr; }
 const fxg_stats* fxg_job_stats(const fxg_job* j) { return j ? &j->stats : nullptr; }
 
 void fxg_job_free(fxg_ctx* c, fxg_job* j) {
     if (!j) return;
-    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); give_pool(c, j->pool); }
+    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); give_pool(c, j->pool); give_pinned(c, j->cigars); }
+    else j->cigars.release();
     delete j;
 }
 

@@ -110,18 +110,25 @@ class Job:
         self._ctx._check(lib().fxg_verify_run(self._ctx._h, self._h))
         return self
 
-    def alignments(self):
-        """(alignments[abi.ALIGNMENT_DTYPE], cigar_pool[uint32]) copied out of the job (one copy each)."""
+    def alignments(self, copy: bool = True):
+        """(alignments[abi.ALIGNMENT_DTYPE], cigar_pool[uint32]).
+
+        cigar_offset indexes cigar_pool; the pool may hold unused gaps between cigars.  With copy=False the arrays are
+        views of the job's own (page-locked) memory -- what a C caller reads through fxg_job_alignments /
+        fxg_job_cigar_pool -- and are valid until free()."""
         L = lib()
         n = L.fxg_job_num_alignments(self._h)
         nc = L.fxg_job_cigar_len(self._h)
-        al = np.empty(n, dtype=abi.ALIGNMENT_DTYPE)
-        cg = np.empty(nc, dtype=np.uint32)
         if n:
-            C.memmove(al.ctypes.data, L.fxg_job_alignments(self._h), n * abi.ALIGNMENT_DTYPE.itemsize)
+            buf = (C.c_char * (n * abi.ALIGNMENT_DTYPE.itemsize)).from_address(L.fxg_job_alignments(self._h))
+            al = np.frombuffer(buf, dtype=abi.ALIGNMENT_DTYPE)
+        else:
+            al = np.empty(0, dtype=abi.ALIGNMENT_DTYPE)
         if nc:
-            C.memmove(cg.ctypes.data, L.fxg_job_cigar_pool(self._h), nc * 4)
-        return al, cg
+            cg = np.frombuffer((C.c_uint32 * nc).from_address(L.fxg_job_cigar_pool(self._h)), dtype=np.uint32)
+        else:
+            cg = np.empty(0, dtype=np.uint32)
+        return (al.copy(), cg.copy()) if copy else (al, cg)
 
     def stats(self) -> dict:
         return lib().fxg_job_stats(self._h).contents.as_dict()
