@@ -183,8 +183,7 @@ struct LaneState {
     int32_t score;              // value of the block's bottom row after the latest step
     int32_t best;               // last block only: minimum of the last row so far ...
     uint32_t best_col;          // ... and the rightmost column attaining it
-    const uint8_t* wp;          // next window character of this lane
-    const uint32_t* eqb;        // Eq rows of the current block (symbol 0)
+    const uint32_t* eqb;        // Eq rows of the current block: symbol s at eqb + s * W
 };
 
 template <int W>
@@ -204,18 +203,11 @@ __device__ __forceinline__ void load_eq(uint32_t (&Eq)[W], const uint32_t* row) 
     }
 }
 
-// One column of one block: the Myers/Hyyroe word-step over W words with the carries of the block above.
-// FIRST: some lane of the warp may be on block 0 (whose upper boundary is row 0: no carries);
-// LAST:  some lane may be on the last block (track the minimum of the last row).
-template <int W, bool TRACE, bool FIRST, bool LAST>
-__device__ __forceinline__ void block_step(LaneState<W>& S, uint32_t r_hp, uint32_t r_hn, uint32_t t, uint32_t peq_stride,
-                                           uint32_t last_block, uint32_t* trace_row) {
-    uint32_t in_hp = r_hp, in_hn = r_hn;
-    if (FIRST && S.b == 0) { in_hp = 0; in_hn = 0; }      // row 0 of a semi-global matrix is all zeros
-    uint32_t const c = *S.wp++;
-    const uint32_t* const eqrow = S.eqb + c * peq_stride;
-    uint32_t Eq[W];
-    load_eq<W>(Eq, eqrow);
+// One column of one block: the Myers/Hyyroe word-step over W words with the horizontal deltas (in_hp, in_hn: bit 31 =
+// the row above the block) of the block above.  Returns HP / HN of the last word (bit 31 = the block's bottom row).
+template <int W, bool TRACE>
+__device__ __forceinline__ void block_column(uint32_t (&Pv)[W], uint32_t (&Mv)[W], const uint32_t (&Eq)[W], uint32_t in_hp, uint32_t in_hn,
+                                             uint32_t& out_hp, uint32_t& out_hn, uint32_t* trace_row, bool store) {
     constexpr int CH = W < 8 ? W : 8;
     uint32_t hp_prev = in_hp, hn_prev = in_hn;
     uint32_t carry = in_hn >> 31;                         // the adder's carry across a word boundary equals the HN bit there
@@ -223,31 +215,64 @@ __device__ __forceinline__ void block_step(LaneState<W>& S, uint32_t r_hp, uint3
     for (int c0 = 0; c0 < W; c0 += CH) {
         uint32_t X[CH], Tt[CH], Sm[CH];
 #pragma unroll
-        for (int i = 0; i < CH; ++i) { X[i] = Eq[c0 + i] | S.Mv[c0 + i]; Tt[i] = Eq[c0 + i] & S.Pv[c0 + i]; }
-        if (c0 + CH < W) carry = Chain<CH, true>::run(Sm, Tt, &S.Pv[c0], carry);
-        else Chain<CH, false>::run(Sm, Tt, &S.Pv[c0], carry);
+        for (int i = 0; i < CH; ++i) { X[i] = Eq[c0 + i] | Mv[c0 + i]; Tt[i] = Eq[c0 + i] & Pv[c0 + i]; }
+        if (c0 + CH < W) carry = Chain<CH, true>::run(Sm, Tt, &Pv[c0], carry);
+        else Chain<CH, false>::run(Sm, Tt, &Pv[c0], carry);
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-            uint32_t const pv = S.Pv[c0 + i], mv = S.Mv[c0 + i];
+            uint32_t const pv = Pv[c0 + i], mv = Mv[c0 + i];
             uint32_t const D0 = (Sm[i] ^ pv) | X[i];
             uint32_t const HN = pv & D0;
             uint32_t const HP = mv | ~(pv | D0);
             uint32_t const HPs = __funnelshift_l(hp_prev, HP, 1);
             uint32_t const HNs = __funnelshift_l(hn_prev, HN, 1);
-            S.Mv[c0 + i] = HPs & D0;
-            S.Pv[c0 + i] = HNs | ~(HPs | D0);
+            Mv[c0 + i] = HPs & D0;
+            Pv[c0 + i] = HNs | ~(HPs | D0);
             hp_prev = HP; hn_prev = HN;
             if (TRACE) {
                 // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
-                *reinterpret_cast<uint2*>(trace_row + (c0 + i) * 2) = make_uint2(HP, S.Pv[c0 + i]);
+                if (store) *reinterpret_cast<uint2*>(trace_row + (c0 + i) * 2) = make_uint2(HP, Pv[c0 + i]);
             }
         }
     }
-    S.o_hp = hp_prev; S.o_hn = hn_prev;
-    S.score += int32_t(hp_prev >> 31) - int32_t(hn_prev >> 31);
-    if (LAST) {
-        if (S.b == last_block && S.score <= S.best) { S.best = S.score; S.best_col = t - S.b; }
+    out_hp = hp_prev; out_hn = hn_prev;
+}
+
+// Steps t .. evt-1 of every lane of the warp: no block starts or ends in this range, so the loop is the recurrence
+// and nothing else -- no divergent branch (inactive lanes run the same instructions on dead state and keep publishing
+// the "+1 per column" boundary), window characters two steps and Eq rows one step ahead of their use.
+// FIRST: some lane is on block 0 (its upper boundary is row 0: no carries come in);
+// LAST:  some lane is on the last block (tracks the minimum of the last row).
+template <int W, bool TRACE, bool FIRST, bool LAST>
+__device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t const evt, bool const active, uint32_t const src_lane,
+                                          uint32_t const last_block, const uint8_t* const win0, uint32_t* trace_row, uint32_t const trace_step) {
+    uint32_t const inc = active ? 1u : 0u;
+    bool const first = FIRST && S.b == 0;
+    bool const track = LAST && active && S.b == last_block;
+    const uint8_t* wp = active ? win0 + (int32_t(t) - int32_t(S.b) - 1) : win0;     // character of column j is win0[j - 1]
+    const uint32_t* const eqb = S.eqb;
+    uint32_t EqA[W], EqB[W];
+    load_eq<W>(EqA, eqb + uint32_t(wp[0]) * W);
+    wp += inc;
+    uint32_t cn = *wp;                                    // character of step t + 1
+#define FXG_STEP(EQ_USE, EQ_LOAD)                                                                          \
+    {                                                                                                      \
+        load_eq<W>(EQ_LOAD, eqb + cn * W);                /* Eq of the next step */                        \
+        wp += inc; cn = *wp;                              /* character of the step after it */             \
+        uint32_t r_hp = __shfl_sync(0xffffffffu, S.o_hp, src_lane);                                        \
+        uint32_t r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);                                        \
+        if (first) { r_hp = 0; r_hn = 0; }                /* row 0 of a semi-global matrix is all zeros */ \
+        uint32_t hp, hn;                                                                                   \
+        block_column<W, TRACE>(S.Pv, S.Mv, EQ_USE, r_hp, r_hn, hp, hn, trace_row, active);                 \
+        S.o_hp = active ? hp : 0x80000000u; S.o_hn = active ? hn : 0u;                                     \
+        S.score += int32_t(hp >> 31) - int32_t(hn >> 31);                                                  \
+        if (LAST) { if (track && S.score <= S.best) { S.best = S.score; S.best_col = t - S.b; } }          \
+        if (TRACE) trace_row += trace_step;                                                                \
+        ++t;                                                                                               \
     }
+    while (t + 1 < evt) { FXG_STEP(EqA, EqB) FXG_STEP(EqB, EqA) }
+    if (t < evt) FXG_STEP(EqA, EqB)
+#undef FXG_STEP
 }
 
 template <int W, bool TRACE>
@@ -261,9 +286,9 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     uint32_t const task_id = blockIdx.x * tasks_per_warp + slot;
     bool const have_task = slot < tasks_per_warp && task_id < L.n_tasks;     // G need not divide 32: spare lanes idle
 
-    uint8_t* const win = smem + size_t(slot) * L.win_stride;
+    uint8_t* const win = smem + size_t(have_task ? slot : 0) * L.win_stride;
     uint32_t* const peq = reinterpret_cast<uint32_t*>(smem + size_t(tasks_per_warp) * L.win_stride) +
-                          size_t(slot) * kNumSymbols * L.peq_stride;
+                          size_t(have_task ? slot : 0) * kNumSymbols * L.peq_stride;
 
     DpTask T;
     if (have_task) T = L.tasks[task_id];
@@ -275,12 +300,13 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     int32_t const dlo = T.dlo - int32_t(pad), dhi = T.dhi - int32_t(pad);
     bool const reverse = (T.flags & kFlagReverse) != 0;
 
-    // ---- stage the window: 32 bases (16 bytes packed) per lane and iteration.  Reverse passes
-    //      (alignment.cpp:118-125) store the window back to front so that the sweep below is always forward.
+    // ---- stage the window: 32 bases (16 bytes packed) per lane and iteration, two characters past the end included
+    //      (the sweep reads ahead).  Reverse passes (alignment.cpp:118-125) store the window back to front so that
+    //      the sweep below is always forward.
     uint32_t const phase = uint32_t(T.ref_base & 31u);
     if (have_task) {
         const uint4* src = reinterpret_cast<const uint4*>((T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed) + (T.ref_base >> 5);
-        uint32_t const n_chunks = (phase + T.n + 31) / 32;
+        uint32_t const n_chunks = (phase + T.n + 2 + 31) / 32;
         for (uint32_t c = r; c < n_chunks; c += G) {
             uint4 const v = __ldg(src + c);
             uint4 a, b2;
@@ -297,11 +323,13 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
                 }
             }
         }
-        // ---- stage the Eq table of the query piece from the pool-level Peq planes ----
+        if (reverse && r == 0) { win[T.n] = 0; win[T.n + 1] = 0; }
+        // ---- stage the Eq table of the query piece from the pool-level Peq planes: block-major, then symbol, then word ----
         uint32_t const n_words = nb * W;
         for (uint32_t w = r; w < n_words; w += G) {
             int32_t const virt = int32_t(pad) - int32_t(32 * w);            // wildcard bits in this word
             uint32_t const wild = virt >= 32 ? 0xffffffffu : (virt > 0 ? ((1u << virt) - 1u) : 0u);
+            uint32_t* const dst = peq + (w / W) * (kNumSymbols * W) + (w % W);
 #pragma unroll
             for (int s = 0; s < kNumSymbols; ++s) {
                 const uint32_t* plane = L.peq_table + uint64_t(s) * L.peq_plane_words;
@@ -312,20 +340,20 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
                     int64_t const y = int64_t(T.query_base) + int64_t(T.m) - 1 + int64_t(pad) - int64_t(32 * w);
                     x = __brev(peq_window(plane, y - 31));
                 }
-                peq[s * L.peq_stride + w] = x | wild;
+                dst[s * W] = x | wild;
             }
         }
     }
     __syncwarp();
 
-    uint8_t const* const win0 = reverse ? win : win + phase;   // character of column j is win0[j - 1]
+    uint8_t const* const win0 = (reverse || !have_task) ? win : win + phase;   // character of column j is win0[j - 1]
     uint32_t const last_block = nb - 1;
     LaneState<W> S;
 #pragma unroll
     for (int i = 0; i < W; ++i) { S.Pv[i] = 0; S.Mv[i] = 0; }
     S.b = r; S.o_hp = 0x80000000u; S.o_hn = 0;      // an idle lane publishes "the boundary grows by +1 per column"
     S.score = 0; S.best = kNoScore; S.best_col = 0;
-    S.wp = win0; S.eqb = peq;
+    S.eqb = peq;
     auto set_block = [&](uint32_t blk) {
         S.cs = 0x7fffffff; S.ce = -1;
         if (!have_task || blk >= nb) return;
@@ -341,67 +369,48 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     // number of steps of this warp: last block of the longest task
     uint32_t const my_end = __reduce_max_sync(0xffffffffu, have_task ? (T.n + nb - 1) : 0u);
     constexpr uint32_t kNever = 0x7fffffffu;
+    uint32_t const trace_step = G * 2 * W;
 
     uint32_t t = 1;
     while (t <= my_end) {
-        // ---------------- event step: block starts / ends are handled here, with every check in place ----------------
-        {
-            uint32_t const r_hp = __shfl_sync(0xffffffffu, S.o_hp, src_lane);
-            uint32_t const r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);
-            int32_t const r_sc = __shfl_sync(0xffffffffu, S.score, src_lane);
-            int32_t const j = int32_t(t) - int32_t(S.b);
-            if (j >= S.cs && j <= S.ce) {
-                if (j == S.cs) {
-                    // (re)start: column cs-1 of this block is (bottom of the block above at cs-1) + 1, 2, ...
+        // ---------------- between steps t-1 and t: blocks that ended move on, blocks that begin are set up ----------------
+        uint32_t const r_hp = __shfl_sync(0xffffffffu, S.o_hp, src_lane);
+        uint32_t const r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);
+        int32_t const r_sc = __shfl_sync(0xffffffffu, S.score, src_lane);
+        if (S.ce >= 0 && int32_t(t) - int32_t(S.b) > S.ce) { S.b += G; set_block(S.b); }
+        int32_t const j = int32_t(t) - int32_t(S.b);
+        if (j == S.cs) {
+            // (re)start: column cs-1 of this block is (bottom of the block above at cs-1) + 1, 2, ...
 #pragma unroll
-                    for (int i = 0; i < W; ++i) { S.Pv[i] = 0xffffffffu; S.Mv[i] = 0; }
-                    if (S.b == 0) {
-                        // wildcard rows carry value 0: no vertical step there
+            for (int i = 0; i < W; ++i) { S.Pv[i] = 0xffffffffu; S.Mv[i] = 0; }
+            if (S.b == 0) {
+                // wildcard rows carry value 0: no vertical step there
 #pragma unroll
-                        for (int i = 0; i < W; ++i) {
-                            int32_t const virt = int32_t(pad) - 32 * i;
-                            S.Pv[i] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
-                        }
-                        S.score = int32_t(ROWS) - int32_t(pad);
-                    } else {
-                        S.score = r_sc - int32_t(r_hp >> 31) + int32_t(r_hn >> 31) + ROWS;
-                    }
-                    S.wp = win0 + (j - 1);
-                    S.eqb = peq + S.b * W;
+                for (int i = 0; i < W; ++i) {
+                    int32_t const virt = int32_t(pad) - 32 * i;
+                    S.Pv[i] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
                 }
-                uint32_t* trace_row = TRACE ? (L.trace + T.trace_base + (uint64_t(t - 1) * G + r) * (2 * W)) : nullptr;
-                block_step<W, TRACE, true, true>(S, r_hp, r_hn, t, L.peq_stride, last_block, trace_row);
-                if (j == S.ce) { S.b += G; set_block(S.b); }
+                S.score = int32_t(ROWS) - int32_t(pad);
             } else {
-                S.o_hp = 0x80000000u; S.o_hn = 0;
+                S.score = r_sc - int32_t(r_hp >> 31) + int32_t(r_hn >> 31) + ROWS;
             }
+            S.eqb = peq + S.b * (kNumSymbols * W);
         }
-        ++t;
-        // ---------------- steps until the next event of any lane: nothing but the recurrence ----------------
-        int32_t const jn = int32_t(t) - int32_t(S.b);
-        bool const active = jn > S.cs && jn <= S.ce;           // already started (a start is an event of its own)
-        // an active lane's next event is its last column; a lane that just finished must publish the boundary next step
-        uint32_t my_evt;
-        if (active) my_evt = uint32_t(S.ce) + S.b;
-        else if (S.o_hp != 0x80000000u || S.o_hn != 0u) my_evt = t;
-        else my_evt = S.cs == 0x7fffffff ? kNever : uint32_t(S.cs) + S.b;
+        bool const active = j >= S.cs && j <= S.ce;
+        // next step at which some lane's block ends (it moves on before the step after) or begins
+        uint32_t const my_evt = active ? uint32_t(S.ce) + S.b + 1u : (S.cs == 0x7fffffff ? kNever : uint32_t(S.cs) + S.b);
         uint32_t const evt = min(__reduce_min_sync(0xffffffffu, my_evt), my_end + 1);
-        if (evt > t) {
-            bool const any_first = __any_sync(0xffffffffu, active && S.b == 0);
-            bool const any_last = __any_sync(0xffffffffu, active && S.b == last_block);
-            uint32_t* trace_row = TRACE ? (L.trace + T.trace_base + (uint64_t(t - 1) * G + r) * (2 * W)) : nullptr;
-            uint32_t const trace_step = G * 2 * W;
-#define FXG_FAST_LOOP(FIRST, LAST)                                                                         \
-            for (; t < evt; ++t) {                                                                         \
-                uint32_t const r_hp = __shfl_sync(0xffffffffu, S.o_hp, src_lane);                          \
-                uint32_t const r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);                          \
-                if (active) block_step<W, TRACE, FIRST, LAST>(S, r_hp, r_hn, t, L.peq_stride, last_block, trace_row); \
-                if (TRACE) trace_row += trace_step;                                                        \
-            }
-            if (any_first) { if (any_last) { FXG_FAST_LOOP(true, true) } else { FXG_FAST_LOOP(true, false) } }
-            else { if (any_last) { FXG_FAST_LOOP(false, true) } else { FXG_FAST_LOOP(false, false) } }
-#undef FXG_FAST_LOOP
+        bool const any_first = __any_sync(0xffffffffu, active && S.b == 0);
+        bool const any_last = __any_sync(0xffffffffu, active && S.b == last_block);
+        uint32_t* const trace_row = TRACE ? (L.trace + T.trace_base + (uint64_t(t - 1) * G + r) * (2 * W)) : nullptr;
+        if (any_first) {
+            if (any_last) run_steps<W, TRACE, true, true>(S, t, evt, active, src_lane, last_block, win0, trace_row, trace_step);
+            else run_steps<W, TRACE, true, false>(S, t, evt, active, src_lane, last_block, win0, trace_row, trace_step);
+        } else {
+            if (any_last) run_steps<W, TRACE, false, true>(S, t, evt, active, src_lane, last_block, win0, trace_row, trace_step);
+            else run_steps<W, TRACE, false, false>(S, t, evt, active, src_lane, last_block, win0, trace_row, trace_step);
         }
+        t = evt;
     }
     // the lane that owned the last block reports
     uint32_t const owner = last_block % G;
