@@ -25,7 +25,9 @@ constexpr int kPeqBackPadWords = 66;
 constexpr uint32_t kFlagReverse = 1u;   // run on reversed views (alignment.cpp:118-125)
 constexpr uint32_t kFlagInlineRef = 2u; // window comes from the per-batch inline pool
 constexpr int32_t kNoScore = 0x3fffffff;
-constexpr uint32_t kWalkPrefetch = 24;  // traceback steps between a prefetch and the use of its line
+constexpr int32_t kPoisonScore = 0x7ffffff0;   // the engine found its own bookkeeping inconsistent (host turns it into an error)
+constexpr uint32_t kWinChunks = 8;      // 32-base chunks of the window a ring keeps in shared memory at a time
+constexpr uint32_t kWinBytes = 2 * kWinChunks * 32;   // every chunk is stored twice (slot and slot + kWinChunks): reads never wrap
 
 // One bit-vector DP pass.  All coordinates are in bases.
 struct DpTask {
@@ -108,10 +110,12 @@ struct DpLaunch {
     const DpTask* tasks;        // sorted so that the tasks of one warp have similar step counts
     uint32_t n_tasks;
     uint32_t group;             // G: lanes per task (1..32); floor(32 / G) tasks per warp
-    uint32_t win_stride;        // bytes of shared memory per task window (multiple of 16)
+    uint32_t win_stride;        // bytes of shared memory per task window buffer (kWinBytes)
     uint32_t peq_stride;        // words per symbol row of the per-task Eq table
     const uint32_t* ref_packed; // resident references
     const uint32_t* inline_packed;
+    uint64_t ref_chunks, inline_chunks;   // 16-byte chunks that may be read from each store
+    uint32_t two;               // the constant 2, kept opaque to the compiler (see run_steps)
     const uint32_t* peq_table;  // kNumSymbols planes
     uint64_t peq_plane_words;
     DpResult* results;
@@ -186,56 +190,86 @@ struct LaneState {
     const uint32_t* eqb;        // Eq rows of the current block: symbol s at eqb + s * W
 };
 
+// shared-memory loads by 32-bit shared-space address (keeps the address arithmetic in one register and off the ALU pipe)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 template <int W>
-__device__ __forceinline__ void load_eq(uint32_t (&Eq)[W], const uint32_t* row) {
+__device__ __forceinline__ void load_eq(uint32_t (&Eq)[W], uint32_t addr) {
     if constexpr (W % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < W; i += 4) {
-            uint4 const v = *reinterpret_cast<const uint4*>(row + i);
-            Eq[i] = v.x; Eq[i + 1] = v.y; Eq[i + 2] = v.z; Eq[i + 3] = v.w;
-        }
+        for (int i = 0; i < W; i += 4)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(Eq[i]), "=r"(Eq[i + 1]), "=r"(Eq[i + 2]), "=r"(Eq[i + 3]) : "r"(addr + 4 * i));
     } else if constexpr (W == 2) {
-        uint2 const v = *reinterpret_cast<const uint2*>(row);
-        Eq[0] = v.x; Eq[1] = v.y;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(Eq[0]), "=r"(Eq[1]) : "r"(addr));
     } else {
 #pragma unroll
-        for (int i = 0; i < W; ++i) Eq[i] = row[i];
+        for (int i = 0; i < W; ++i) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq[i]) : "r"(addr + 4 * i));
     }
+}
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+// integer multiply-add pipe (IMAD / IMAD.HI), which the recurrence itself leaves idle
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
 // One column of one block: the Myers/Hyyroe word-step over W words with the horizontal deltas (in_hp, in_hn: bit 31 =
 // the row above the block) of the block above.  Returns HP / HN of the last word (bit 31 = the block's bottom row).
+//
+// Per word, on the ALU pipe: T = Eq & Pv;  S = T + Pv + carry (one carry chain through the block);
+//   HN<<1 = S ^ T ^ Pv      -- the carries INTO every bit of that sum are exactly the shifted HN vector
+//                              (carry out of bit i = Pv_i & (Eq_i | carry_i) = Pv_i & D0_i = HN_i), word boundaries included;
+//   D0' = (S ^ Pv) | Eq  (D0 = D0' | Mv);  HP = Mv | ~(Pv | D0');  Mv' = HP<<1 & D0;  Pv' = HN<<1 | ~(HP<<1 | D0).
+// (Measured on B200: IMAD / IMAD.HI share their issue slots with the ALU pipe, so shifting HP with multiply-adds
+// instead of one funnel shift gains nothing.)
 template <int W, bool TRACE>
 __device__ __forceinline__ void block_column(uint32_t (&Pv)[W], uint32_t (&Mv)[W], const uint32_t (&Eq)[W], uint32_t in_hp, uint32_t in_hn,
-                                             uint32_t& out_hp, uint32_t& out_hn, uint32_t* trace_row, bool store) {
+                                             uint32_t& out_hp, uint32_t& out_hn, uint32_t* trace_row, bool store, uint32_t const two) {
     constexpr int CH = W < 8 ? W : 8;
-    uint32_t hp_prev = in_hp, hn_prev = in_hn;
+    uint32_t hp_prev = in_hp;
+    uint32_t hp_last = in_hp, hn_last = in_hn;
     uint32_t carry = in_hn >> 31;                         // the adder's carry across a word boundary equals the HN bit there
 #pragma unroll
     for (int c0 = 0; c0 < W; c0 += CH) {
-        uint32_t X[CH], Tt[CH], Sm[CH];
+        uint32_t Tt[CH], Sm[CH];
 #pragma unroll
-        for (int i = 0; i < CH; ++i) { X[i] = Eq[c0 + i] | Mv[c0 + i]; Tt[i] = Eq[c0 + i] & Pv[c0 + i]; }
+        for (int i = 0; i < CH; ++i) Tt[i] = Eq[c0 + i] & Pv[c0 + i];
         if (c0 + CH < W) carry = Chain<CH, true>::run(Sm, Tt, &Pv[c0], carry);
         else Chain<CH, false>::run(Sm, Tt, &Pv[c0], carry);
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
             uint32_t const pv = Pv[c0 + i], mv = Mv[c0 + i];
-            uint32_t const D0 = (Sm[i] ^ pv) | X[i];
-            uint32_t const HN = pv & D0;
-            uint32_t const HP = mv | ~(pv | D0);
+            // (LOP3 by hand: left to itself the compiler expands D0p again and spends an extra instruction per word)
+            uint32_t const HNs = lop3<0x96>(Sm[i], Tt[i], pv);                // S ^ T ^ Pv
+            uint32_t const D0p = lop3<0xBE>(Sm[i], pv, Eq[c0 + i]);           // (S ^ Pv) | Eq;  D0 = D0p | Mv
+            uint32_t const HP = lop3<0xF1>(mv, pv, D0p);                      // Mv | ~(Pv | D0p)
             uint32_t const HPs = __funnelshift_l(hp_prev, HP, 1);
-            uint32_t const HNs = __funnelshift_l(hn_prev, HN, 1);
-            Mv[c0 + i] = HPs & D0;
-            Pv[c0 + i] = HNs | ~(HPs | D0);
-            hp_prev = HP; hn_prev = HN;
+            hp_prev = HP;
+            if (c0 + i == W - 1) { hp_last = HP; hn_last = pv & D0p; }        // Pv & Mv == 0
+            Mv[c0 + i] = lop3<0xE0>(HPs, D0p, mv);                            // HPs & (D0p | Mv)
+            uint32_t const u = lop3<0xFE>(HPs, D0p, mv);                      // HPs | D0
+            Pv[c0 + i] = lop3<0xF3>(HNs, u, 0u);                              // HNs | ~(HPs | D0)
             if (TRACE) {
                 // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
                 if (store) *reinterpret_cast<uint2*>(trace_row + (c0 + i) * 2) = make_uint2(HP, Pv[c0 + i]);
             }
         }
     }
-    out_hp = hp_prev; out_hn = hn_prev;
+    out_hp = hp_last; out_hn = hn_last;
 }
 
 // Steps t .. evt-1 of every lane of the warp: no block starts or ends in this range, so the loop is the recurrence
@@ -245,34 +279,68 @@ __device__ __forceinline__ void block_column(uint32_t (&Pv)[W], uint32_t (&Mv)[W
 // LAST:  some lane is on the last block (tracks the minimum of the last row).
 template <int W, bool TRACE, bool FIRST, bool LAST>
 __device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t const evt, bool const active, uint32_t const src_lane,
-                                          uint32_t const last_block, const uint8_t* const win0, uint32_t* trace_row, uint32_t const trace_step) {
+                                          uint32_t const last_block, const uint8_t* const win0, const uint8_t* const idle_chars, uint32_t* trace_row,
+                                          uint32_t const trace_step, uint32_t const two) {
     uint32_t const inc = active ? 1u : 0u;
     bool const first = FIRST && S.b == 0;
     bool const track = LAST && active && S.b == last_block;
-    const uint8_t* wp = active ? win0 + (int32_t(t) - int32_t(S.b) - 1) : win0;     // character of column j is win0[j - 1]
-    const uint32_t* const eqb = S.eqb;
+    // character of column j is win0[j - 1] (inside the ring buffer); idle lanes keep reading one valid character
+    uint32_t wp = uint32_t(__cvta_generic_to_shared(active ? win0 + (int32_t(t) - int32_t(S.b) - 1) : idle_chars));
+    uint32_t const eqb = uint32_t(__cvta_generic_to_shared(S.eqb));
+    // published deltas: a * x + b with (a, b) = (1, 0) for a working lane and (0, boundary) for an idle one
+    uint32_t const pub_a = inc, pub_hp_b = active ? 0u : 0x80000000u;
+    // bottom-row value = base + (#steps with HP) - (#steps with HN), the two counts kept by the multiply-add pipe
+    int32_t const score_base = S.score;
+    uint32_t n_hp = 0, n_hn = 0;
+    // `two` (= 2) comes in as a kernel parameter: as a literal, mad.hi(x, 2, c) is turned back into an ALU-pipe LEA.HI
     uint32_t EqA[W], EqB[W];
-    load_eq<W>(EqA, eqb + uint32_t(wp[0]) * W);
+    load_eq<W>(EqA, mad_lo(lds_u8(wp), 4 * W, eqb));
     wp += inc;
-    uint32_t cn = *wp;                                    // character of step t + 1
+    uint32_t cn = lds_u8(wp);                             // character of step t + 1
 #define FXG_STEP(EQ_USE, EQ_LOAD)                                                                          \
     {                                                                                                      \
-        load_eq<W>(EQ_LOAD, eqb + cn * W);                /* Eq of the next step */                        \
-        wp += inc; cn = *wp;                              /* character of the step after it */             \
+        load_eq<W>(EQ_LOAD, mad_lo(cn, 4 * W, eqb));      /* Eq of the next step */                        \
+        wp += inc; cn = lds_u8(wp);                       /* character of the step after it */             \
         uint32_t r_hp = __shfl_sync(0xffffffffu, S.o_hp, src_lane);                                        \
         uint32_t r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);                                        \
         if (first) { r_hp = 0; r_hn = 0; }                /* row 0 of a semi-global matrix is all zeros */ \
         uint32_t hp, hn;                                                                                   \
-        block_column<W, TRACE>(S.Pv, S.Mv, EQ_USE, r_hp, r_hn, hp, hn, trace_row, active);                 \
-        S.o_hp = active ? hp : 0x80000000u; S.o_hn = active ? hn : 0u;                                     \
-        S.score += int32_t(hp >> 31) - int32_t(hn >> 31);                                                  \
-        if (LAST) { if (track && S.score <= S.best) { S.best = S.score; S.best_col = t - S.b; } }          \
+        block_column<W, TRACE>(S.Pv, S.Mv, EQ_USE, r_hp, r_hn, hp, hn, trace_row, active, two);                 \
+        S.o_hp = mad_lo(hp, pub_a, pub_hp_b); S.o_hn = mad_lo(hn, pub_a, 0u);                              \
+        n_hp = mad_hi(hp, two, n_hp); n_hn = mad_hi(hn, two, n_hn);                                          \
+        if (LAST) {                                                                                        \
+            int32_t const sc = score_base + int32_t(n_hp) - int32_t(n_hn);                                 \
+            if (track && sc <= S.best) { S.best = sc; S.best_col = t - S.b; }                              \
+        }                                                                                                  \
         if (TRACE) trace_row += trace_step;                                                                \
         ++t;                                                                                               \
     }
     while (t + 1 < evt) { FXG_STEP(EqA, EqB) FXG_STEP(EqB, EqA) }
     if (t < evt) FXG_STEP(EqA, EqB)
 #undef FXG_STEP
+    S.score = score_base + int32_t(n_hp) - int32_t(n_hn);
+}
+
+// 32 consecutive window characters (one 16-byte chunk of the packed store) as bytes.  `logical` counts chunks in sweep
+// order: forward passes read the store upwards from the chunk of window[0]; reverse passes (alignment.cpp:118-125)
+// read it downwards from the chunk of window[n-1], each chunk back to front, so that the sweep is always forward.
+__device__ __forceinline__ void load_window_chunk(const uint4* __restrict__ packed, int64_t n_chunks, int64_t first_chunk, bool reverse,
+                                                  uint32_t logical, uint8_t* buf) {
+    int64_t g = reverse ? first_chunk - int64_t(logical) : first_chunk + int64_t(logical);
+    if (g < 0) g = 0;                                     // only characters past the window's end can come from here
+    if (g >= n_chunks) g = n_chunks - 1;
+    uint4 const v = __ldg(packed + g);
+    uint4 a, b2;
+    unpack8(v.x, a.x, a.y); unpack8(v.y, a.z, a.w); unpack8(v.z, b2.x, b2.y); unpack8(v.w, b2.z, b2.w);
+    if (reverse) {
+        uint4 const ra = make_uint4(__byte_perm(b2.w, 0, 0x0123), __byte_perm(b2.z, 0, 0x0123), __byte_perm(b2.y, 0, 0x0123), __byte_perm(b2.x, 0, 0x0123));
+        uint4 const rb = make_uint4(__byte_perm(a.w, 0, 0x0123), __byte_perm(a.z, 0, 0x0123), __byte_perm(a.y, 0, 0x0123), __byte_perm(a.x, 0, 0x0123));
+        a = ra; b2 = rb;
+    }
+    uint32_t const slot = logical % kWinChunks;
+    uint4* d0 = reinterpret_cast<uint4*>(buf + slot * 32);
+    uint4* d1 = reinterpret_cast<uint4*>(buf + (slot + kWinChunks) * 32);
+    d0[0] = a; d0[1] = b2; d1[0] = a; d1[1] = b2;
 }
 
 template <int W, bool TRACE>
@@ -284,10 +352,12 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     uint32_t const slot = lane / G;                 // which task of this warp
     uint32_t const r = lane % G;                    // ring position
     uint32_t const task_id = blockIdx.x * tasks_per_warp + slot;
-    bool const have_task = slot < tasks_per_warp && task_id < L.n_tasks;     // G need not divide 32: spare lanes idle
+    bool const in_ring = slot < tasks_per_warp;     // G need not divide 32: spare lanes idle
+    bool const have_task = in_ring && task_id < L.n_tasks;
 
-    uint8_t* const win = smem + size_t(have_task ? slot : 0) * L.win_stride;
-    uint32_t* const peq = reinterpret_cast<uint32_t*>(smem + size_t(tasks_per_warp) * L.win_stride) +
+    // lanes without a task idle on the (always present) first task's buffers: whatever they read there is valid
+    uint8_t* const win = smem + size_t(have_task ? slot : 0) * kWinBytes;
+    uint32_t* const peq = reinterpret_cast<uint32_t*>(smem + size_t(tasks_per_warp) * kWinBytes) +
                           size_t(have_task ? slot : 0) * kNumSymbols * L.peq_stride;
 
     DpTask T;
@@ -300,30 +370,17 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     int32_t const dlo = T.dlo - int32_t(pad), dhi = T.dhi - int32_t(pad);
     bool const reverse = (T.flags & kFlagReverse) != 0;
 
-    // ---- stage the window: 32 bases (16 bytes packed) per lane and iteration, two characters past the end included
-    //      (the sweep reads ahead).  Reverse passes (alignment.cpp:118-125) store the window back to front so that
-    //      the sweep below is always forward.
-    uint32_t const phase = uint32_t(T.ref_base & 31u);
+    // ---- the window streams through a small ring buffer: character i (0-based, sweep order) sits in logical chunk
+    //      (phase + i) / 32; the buffer holds chunks [c_base, c_base + kWinChunks)
+    const uint4* const packed = reinterpret_cast<const uint4*>((T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed);
+    int64_t const store_chunks = int64_t((T.flags & kFlagInlineRef) ? L.inline_chunks : L.ref_chunks);
+    uint64_t const w_last = T.ref_base + (T.n ? T.n - 1 : 0);  // store position of window[n-1]
+    int64_t const first_chunk = reverse ? int64_t(w_last >> 5) : int64_t(T.ref_base >> 5);
+    uint32_t const phase = reverse ? 31u - uint32_t(w_last & 31u) : uint32_t(T.ref_base & 31u);
+    uint32_t c_base = 0;
+    bool dead = false;                                         // internal inconsistency: the task reports kPoisonScore
     if (have_task) {
-        const uint4* src = reinterpret_cast<const uint4*>((T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed) + (T.ref_base >> 5);
-        uint32_t const n_chunks = (phase + T.n + 2 + 31) / 32;
-        for (uint32_t c = r; c < n_chunks; c += G) {
-            uint4 const v = __ldg(src + c);
-            uint4 a, b2;
-            unpack8(v.x, a.x, a.y); unpack8(v.y, a.z, a.w); unpack8(v.z, b2.x, b2.y); unpack8(v.w, b2.z, b2.w);
-            if (!reverse) {
-                uint4* dst = reinterpret_cast<uint4*>(win + c * 32);
-                dst[0] = a; dst[1] = b2;
-            } else {
-                uint32_t const words[8] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w};
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    int32_t const idx = int32_t(c * 32 + e) - int32_t(phase);            // window index of this base
-                    if (idx >= 0 && idx < int32_t(T.n)) win[T.n - 1 - uint32_t(idx)] = uint8_t(words[e >> 2] >> (8 * (e & 3)));
-                }
-            }
-        }
-        if (reverse && r == 0) { win[T.n] = 0; win[T.n + 1] = 0; }
+        for (uint32_t c = r; c < kWinChunks; c += G) load_window_chunk(packed, store_chunks, first_chunk, reverse, c, win);
         // ---- stage the Eq table of the query piece from the pool-level Peq planes: block-major, then symbol, then word ----
         uint32_t const n_words = nb * W;
         for (uint32_t w = r; w < n_words; w += G) {
@@ -346,7 +403,6 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     }
     __syncwarp();
 
-    uint8_t const* const win0 = (reverse || !have_task) ? win : win + phase;   // character of column j is win0[j - 1]
     uint32_t const last_block = nb - 1;
     LaneState<W> S;
 #pragma unroll
@@ -364,7 +420,7 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
         if (cs <= ce) { S.cs = cs; S.ce = ce; }
     };
     set_block(S.b);
-    uint32_t const src_lane = slot * G + (r + G - 1) % G;
+    uint32_t const src_lane = in_ring ? slot * G + (r + G - 1) % G : lane;
 
     // number of steps of this warp: last block of the longest task
     uint32_t const my_end = __reduce_max_sync(0xffffffffu, have_task ? (T.n + nb - 1) : 0u);
@@ -396,26 +452,67 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
             }
             S.eqb = peq + S.b * (kNumSymbols * W);
         }
-        bool const active = j >= S.cs && j <= S.ce;
-        // next step at which some lane's block ends (it moves on before the step after) or begins
-        uint32_t const my_evt = active ? uint32_t(S.ce) + S.b + 1u : (S.cs == 0x7fffffff ? kNever : uint32_t(S.cs) + S.b);
+        bool const active = j >= S.cs && j <= S.ce && !dead;
+        // ---------------- window ring buffer: the blocks of a ring read characters t-1-b .. t+1-b (two ahead) ----------------
+        // Computed from the band geometry alone, identically by every lane of the ring (no voting):
+        //   b_top = first block that has not ended yet (it reads furthest ahead: ce(b) + b grows with b),
+        //   b_low = last block that has begun (blocks that begin later start at or beyond its position).
+        uint32_t my_refill = kNever;
+        uint32_t new_base = c_base;
+        uint32_t i_hi = 0;
+        bool reading = false;
+        if (have_task && !dead) {
+            // (all quantities are far below 2^31: n, m <= a few 100 000)
+            int32_t const ti = int32_t(t);
+            int32_t const e1 = ti - int32_t(T.n);                                               // n + b >= t
+            int32_t const e2n = ti - dhi - ROWS;                                                // ROWS (b+1) + dhi + b >= t
+            int32_t const e2 = e2n > 0 ? (e2n + ROWS) / (ROWS + 1) : 0;
+            int32_t const b_top = e1 > e2 ? e1 : e2;
+            int32_t const s1 = ti - 1 - dlo;                                                    // ROWS b + 1 + dlo + b <= t
+            int32_t b_low = s1 > 0 ? s1 / (ROWS + 1) : 0;
+            if (b_low > ti - 1) b_low = ti - 1;                                                 // blocks clipped to column 1 begin at step 1 + b
+            if (b_low > int32_t(last_block)) b_low = int32_t(last_block);
+            reading = b_top <= int32_t(last_block);
+            if (reading) {
+                i_hi = uint32_t(int32_t(phase) + ti + 1 - b_top);                               // buffer position of the furthest read of step t
+                if (i_hi >= 32 * (c_base + kWinChunks)) {
+                    int32_t const lo = ti - 3 - b_low;                                          // everything before it is done with
+                    new_base = uint32_t(int32_t(phase) + (lo > 0 ? lo : 0)) >> 5;
+                    if (new_base <= c_base || i_hi >= 32 * (new_base + kWinChunks)) { dead = true; new_base = c_base; }   // cannot happen: a ring spans < 40 characters
+                }
+            }
+        }
+        // the refill itself in warp-uniform control flow (the hot loops below rely on a converged warp)
+        uint32_t const rounds = __reduce_max_sync(0xffffffffu, (new_base - c_base + G - 1) / G);
+        for (uint32_t k = 0; k < rounds; ++k) {
+            uint32_t const c = c_base + kWinChunks + r + k * G;
+            if (c < new_base + kWinChunks) load_window_chunk(packed, store_chunks, first_chunk, reverse, c, win);
+        }
+        c_base = new_base;
+        if (reading && !dead) my_refill = t + (32 * (c_base + kWinChunks) - i_hi);              // first step that would read past the buffer
+        __syncwarp();
+        // character of column j is win0[j - 1]: chunk c lives at slot c % kWinChunks (and kWinChunks above it)
+        uint8_t const* const win0 = win + phase - 32 * kWinChunks * (c_base / kWinChunks);
+        // next step at which some lane's block ends (it moves on before the step after) or begins, or a buffer runs out
+        uint32_t my_evt = active ? uint32_t(S.ce) + S.b + 1u : (S.cs == 0x7fffffff ? kNever : uint32_t(S.cs) + S.b);
+        my_evt = min(my_evt, my_refill);
         uint32_t const evt = min(__reduce_min_sync(0xffffffffu, my_evt), my_end + 1);
         bool const any_first = __any_sync(0xffffffffu, active && S.b == 0);
         bool const any_last = __any_sync(0xffffffffu, active && S.b == last_block);
         uint32_t* const trace_row = TRACE ? (L.trace + T.trace_base + (uint64_t(t - 1) * G + r) * (2 * W)) : nullptr;
         if (any_first) {
-            if (any_last) run_steps<W, TRACE, true, true>(S, t, evt, active, src_lane, last_block, win0, trace_row, trace_step);
-            else run_steps<W, TRACE, true, false>(S, t, evt, active, src_lane, last_block, win0, trace_row, trace_step);
+            if (any_last) run_steps<W, TRACE, true, true>(S, t, evt, active, src_lane, last_block, win0, win, trace_row, trace_step, L.two);
+            else run_steps<W, TRACE, true, false>(S, t, evt, active, src_lane, last_block, win0, win, trace_row, trace_step, L.two);
         } else {
-            if (any_last) run_steps<W, TRACE, false, true>(S, t, evt, active, src_lane, last_block, win0, trace_row, trace_step);
-            else run_steps<W, TRACE, false, false>(S, t, evt, active, src_lane, last_block, win0, trace_row, trace_step);
+            if (any_last) run_steps<W, TRACE, false, true>(S, t, evt, active, src_lane, last_block, win0, win, trace_row, trace_step, L.two);
+            else run_steps<W, TRACE, false, false>(S, t, evt, active, src_lane, last_block, win0, win, trace_row, trace_step, L.two);
         }
         t = evt;
     }
     // the lane that owned the last block reports
     uint32_t const owner = last_block % G;
     if (have_task && r == owner) {
-        DpResult res; res.score = S.best; res.end_col = S.best_col;
+        DpResult res; res.score = dead ? kPoisonScore : S.best; res.end_col = S.best_col;
         L.results[T.out] = res;
     }
 }

@@ -101,12 +101,15 @@ constexpr int kWidths[6] = {1, 2, 4, 8, 16, 32};
 
 struct Config { uint8_t widx; uint8_t G; uint32_t nb; uint64_t word_steps; };
 
-struct ConfigCacheEntry { uint32_t n, m; int32_t dlo, dhi; Config cfg; bool ok; bool valid; };
+struct ConfigCacheEntry { uint32_t n, m; int32_t dlo, dhi; Config cfg; bool ok; bool valid; bool trace; };
 
 // Everything one host worker needs to run passes on its own stream.
 struct Worker {
     int id = 0;
     cudaStream_t stream = nullptr;
+    static constexpr int kSide = 3;      // the launches of one wave are independent: the smaller ones run beside the largest
+    cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf d_tasks, d_results, d_trace, d_wtasks, d_wresults, d_cigars;
     PinnedBuf h_tasks, h_results, h_wtasks, h_wresults;
@@ -120,8 +123,14 @@ struct Worker {
         for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults}) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (int i = 0; i < kSide; ++i) {
+            if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+            if (side[i]) cudaStreamDestroy(side[i]);
+            ev_join[i] = nullptr; side[i] = nullptr;
+        }
         if (stream) cudaStreamDestroy(stream);
-        ev0 = ev1 = nullptr; stream = nullptr;
+        ev0 = ev1 = ev_fork = nullptr; stream = nullptr;
     }
 };
 
@@ -288,8 +297,6 @@ cudaError_t set_all_smem_attrs(size_t bytes) {
 
 // ------------------------------------------------------------------------------------------------ configuration choice
 
-inline uint32_t pow2_ceil(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
-inline size_t win_stride_for(uint32_t n) { return (size_t(n + 63) / 32 + 1) * 32; }
 inline uint32_t peq_stride_for(uint32_t words) { return (words + 3u) & ~3u; }   // rows stay 16-byte aligned for LDS.128
 
 // word-steps the engine issues for a pass: block b is active for columns cs(b)..ce(b)
@@ -309,7 +316,7 @@ uint64_t word_steps_of(Pass const& p, uint32_t W, uint32_t nb) {
 // Picks words-per-lane W and ring size G for one pass.  The ring must be long enough that a lane is idle
 // (and publishes the +1 boundary) whenever the block below still needs a boundary from it:
 //   G > (B - 4) / (32 W + 1) + 2,  B = number of diagonals in the band  (derivation in DESIGN.md).
-bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
+bool choose_config(Pass const& p, bool trace, size_t smem_limit, Config& out) {
     uint32_t const nw = (p.m + 31) / 32;
     int64_t const B = int64_t(p.dhi) - int64_t(p.dlo) + 1;
     double best_cost = 1e300;
@@ -326,16 +333,25 @@ bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
             G = uint32_t(g);
         }
         uint32_t const tpw = 32 / G;
-        size_t const smem = size_t(tpw) * (win_stride_for(p.n) + size_t(kNumSymbols) * peq_stride_for(nb * W) * 4);
+        G = 32 / tpw;                        // the lanes a smaller ring would leave idle cost nothing, and fewer classes mean fuller launches
+        size_t const smem = size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * peq_stride_for(nb * W) * 4);
         if (smem > smem_limit) continue;
-        // warps that fit on an SM next to each other vs. warps needed to hide the shuffle / shared-memory latency of a
-        // step (about 100 cycles) behind the issue time of the other warps' steps ((12 W + 10) instructions, 2 cycles each)
+        // The engine is bound by the ALU pipe: a warp step issues about 10 W + 6 instructions there, two cycles each on one
+        // of the SM's four schedulers, whatever the number of lanes that do useful work.  Wide blocks need many registers
+        // (fewer warps to hide the shuffle latency behind); many tables per SM cost occupancy as well.
         double const resident = std::min<double>(32.0, std::floor(double(227 * 1024) / double(smem + 1024)));
-        double const needed = 4.0 * (100.0 / ((12.0 * W + 10.0) * 2.0) + 1.0);
-        double const eff = std::min(1.0, resident / needed);
+        double const reg_eff = W <= 8 ? 1.0 : (W == 16 ? 0.85 : 0.7);
+        double const occ_eff = std::min(1.0, resident / 12.0);
         uint64_t const steps = uint64_t(p.n) + nb - 1;
-        // lane-steps spent per task (idle lanes of a partly filled warp included) x instructions per step
-        double const cost = (32.0 / tpw) * double(steps) * (10.0 * W + 14.0) / eff;
+        double cost = double(steps) * (10.0 * W + 6.0) * 2.0 / 4.0 / (reg_eff * occ_eff) / tpw;      // SM cycles per task
+        // every block start / end interrupts the warp for a few hundred issue slots; the rings of a warp mostly, but not
+        // always, have the same shape and then share these interruptions
+        cost += 2.0 * nb * 100.0 / std::sqrt(double(tpw));
+        if (trace) {
+            // trace passes also write 8 bytes per lane, word and step: about 22 bytes per SM and cycle
+            double const bytes = double(steps) * G * W * 8.0;
+            cost = std::max(cost, bytes / 22.0);
+        }
         if (cost < best_cost) { best_cost = cost; out = Config{uint8_t(wi), uint8_t(G), nb, 0}; found = true; }
     }
     if (found) out.word_steps = word_steps_of(p, uint32_t(kWidths[out.widx]), out.nb);
@@ -343,13 +359,13 @@ bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
 }
 
 // the same (m, n, band) recurs for every anchor of a read at one tree level: memoise
-bool cached_config(Worker& w, Pass const& p, size_t smem_limit, Config& out) {
-    uint64_t h = (uint64_t(p.n) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(p.m) * 0xC2B2AE3D27D4EB4Full) ^ (uint64_t(uint32_t(p.dlo)) << 21) ^ uint64_t(uint32_t(p.dhi));
+bool cached_config(Worker& w, Pass const& p, bool trace, size_t smem_limit, Config& out) {
+    uint64_t h = (uint64_t(p.n) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(p.m) * 0xC2B2AE3D27D4EB4Full) ^ (uint64_t(uint32_t(p.dlo)) << 21) ^ uint64_t(uint32_t(p.dhi)) ^ (trace ? 0x5555555555ull : 0);
     h ^= h >> 29;
     ConfigCacheEntry& e = w.cfg_cache[h & (w.cfg_cache.size() - 1)];
-    if (e.valid && e.n == p.n && e.m == p.m && e.dlo == p.dlo && e.dhi == p.dhi) { out = e.cfg; return e.ok; }
-    e.valid = true; e.n = p.n; e.m = p.m; e.dlo = p.dlo; e.dhi = p.dhi;
-    e.ok = choose_config(p, smem_limit, e.cfg);
+    if (e.valid && e.trace == trace && e.n == p.n && e.m == p.m && e.dlo == p.dlo && e.dhi == p.dhi) { out = e.cfg; return e.ok; }
+    e.valid = true; e.trace = trace; e.n = p.n; e.m = p.m; e.dlo = p.dlo; e.dhi = p.dhi;
+    e.ok = choose_config(p, trace, smem_limit, e.cfg);
     out = e.cfg;
     return e.ok;
 }
@@ -384,7 +400,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     w.keys.resize(N);
     for (size_t i = 0; i < N; ++i) {
         Config& cf = w.cfgs[i];
-        if (!cached_config(w, passes[i], c->smem_limit, cf))
+        if (!cached_config(w, passes[i], trace, c->smem_limit, cf))
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
                         passes[i].m, passes[i].n, passes[i].dlo, passes[i].dhi);
         uint64_t const steps = std::min<uint64_t>(uint64_t(passes[i].n) + cf.nb - 1, (1u << 19) - 1);
@@ -416,31 +432,33 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     g_prof.lap(w, 5);
 
     CUDA_TRY(w.err, cudaEventRecord(w.ev0, w.stream));
+    struct Launch { DpLaunch L; int widx; uint32_t grid; size_t smem; uint64_t work; };
+    std::vector<Launch> launches;
     size_t i = 0;
     while (i < N) {
-        // one launch: same (W, G); window lengths within a factor of two so that shared memory is not wasted
+        // one launch: same (W, G)
         Config const& c0 = w.cfgs[uint32_t(w.keys[i])];
         int const widx = c0.widx; uint32_t const G = c0.G;
         uint32_t const W = uint32_t(kWidths[widx]);
         uint32_t const tpw = 32 / G;
         size_t j = i;
-        uint32_t max_n = 0, max_words = 0;
-        uint32_t const first_n = passes[uint32_t(w.keys[i])].n;
+        uint32_t max_words = 0;
+        uint64_t work = 0;
         while (j < N) {
             uint32_t const idx = uint32_t(w.keys[j]);
             Config const& cj = w.cfgs[idx];
             if (cj.widx != widx || cj.G != G) break;
-            uint32_t const n = passes[idx].n;
-            if (j > i && size_t(n) * 2 < first_n && (j - i) % tpw == 0 && j - i >= 2048) break;
-            max_n = std::max(max_n, n);
             max_words = std::max(max_words, cj.nb * W);
+            work += (uint64_t(passes[idx].n) + cj.nb) * (10 * W + 6);
             ++j;
         }
-        DpLaunch L{};
+        Launch X{};
+        DpLaunch& L = X.L;
         L.tasks = w.d_tasks.as<DpTask>() + i;
         L.n_tasks = uint32_t(j - i);
         L.group = G;
-        L.win_stride = uint32_t(win_stride_for(max_n));
+        L.win_stride = kWinBytes; L.two = 2;
+        L.ref_chunks = c->refs.total / 32 + 1; L.inline_chunks = pool.inline_len / 32 + 1;
         L.peq_stride = peq_stride_for(max_words);
         L.ref_packed = c->refs.packed.as<uint32_t>();
         L.inline_packed = pool.inline_packed.as<uint32_t>();
@@ -448,12 +466,31 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
         L.peq_plane_words = pool.plane_words;
         L.results = w.d_results.as<DpResult>();
         L.trace = w.d_trace.as<uint32_t>();
-        size_t const smem = size_t(tpw) * (L.win_stride + size_t(kNumSymbols) * L.peq_stride * 4);
-        if (smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", smem);
-        uint32_t const grid = uint32_t((L.n_tasks + tpw - 1) / tpw);
-        CUDA_TRY(w.err, launch_dp(widx, trace, L, grid, smem, w.stream));
-        w.ctr.kernel_launches++;
+        X.smem = size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
+        if (X.smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", X.smem);
+        X.grid = uint32_t((L.n_tasks + tpw - 1) / tpw);
+        X.widx = widx; X.work = work / tpw;
+        launches.push_back(X);
         i = j;
+    }
+    // largest first on the worker's own stream, the rest spread over the side streams so that they fill the machine together
+    std::sort(launches.begin(), launches.end(), [](Launch const& a, Launch const& b) { return a.work > b.work; });
+    bool const fan_out = launches.size() > 1;
+    if (fan_out) {
+        CUDA_TRY(w.err, cudaEventRecord(w.ev_fork, w.stream));
+        for (int q = 0; q < Worker::kSide; ++q) CUDA_TRY(w.err, cudaStreamWaitEvent(w.side[q], w.ev_fork, 0));
+    }
+    for (size_t q = 0; q < launches.size(); ++q) {
+        Launch const& X = launches[q];
+        cudaStream_t const st = q == 0 ? w.stream : w.side[(q - 1) % Worker::kSide];
+        CUDA_TRY(w.err, launch_dp(X.widx, trace, X.L, X.grid, X.smem, st));
+        w.ctr.kernel_launches++;
+    }
+    if (fan_out) {
+        for (int q = 0; q < Worker::kSide; ++q) {
+            CUDA_TRY(w.err, cudaEventRecord(w.ev_join[q], w.side[q]));
+            CUDA_TRY(w.err, cudaStreamWaitEvent(w.stream, w.ev_join[q], 0));
+        }
     }
     CUDA_TRY(w.err, cudaEventRecord(w.ev1, w.stream));
     g_prof.lap(w, 6);
@@ -465,6 +502,8 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     if (trace) w.ctr.trace_kernel_ms += ms; else w.ctr.dp_kernel_ms += ms;
     g_prof.lap(w, trace ? 11 : 8);
     *results = w.h_results.as<DpResult>();
+    for (size_t q = 0; q < N; ++q)
+        if ((*results)[q].score == kPoisonScore) return fail(w.err, FXG_ERR_CUDA, "internal: the DP engine lost track of its window buffer");
     return FXG_OK;
 }
 
@@ -486,7 +525,7 @@ int run_traces(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<TraceReq> co
     std::vector<Config> cfgs(N);
     std::vector<uint64_t> words(N);
     for (size_t i = 0; i < N; ++i) {
-        if (!cached_config(w, reqs[i].pass, c->smem_limit, cfgs[i]))
+        if (!cached_config(w, reqs[i].pass, true, c->smem_limit, cfgs[i]))
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "traceback band of query length %u exceeds the supported size", reqs[i].pass.m);
         uint64_t const W = uint64_t(kWidths[cfgs[i].widx]);
         words[i] = ((uint64_t(reqs[i].pass.n) + cfgs[i].nb) * cfgs[i].G * W * 2 + 3) & ~uint64_t(3);
@@ -1024,7 +1063,11 @@ int fxg_create(int device, fxg_ctx** out) {
         if (!w) { ok = false; break; }
         w->id = i;
         ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess;
+             cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess &&
+             cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int q = 0; ok && q < Worker::kSide; ++q)
+            ok = cudaStreamCreateWithFlags(&w->side[q], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&w->ev_join[q], cudaEventDisableTiming) == cudaSuccess;
         c->workers.push_back(std::move(w));
     }
     if (!ok) { fxg_destroy(c); return FXG_ERR_CUDA; }
