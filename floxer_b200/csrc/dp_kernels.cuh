@@ -188,7 +188,24 @@ struct LaneState {
     int32_t best;               // last block only: minimum of the last row so far ...
     uint32_t best_col;          // ... and the rightmost column attaining it
     const uint32_t* eqb;        // Eq rows of the current block: symbol s at eqb + s * W
+    // checkpoint passes only: the horizontal deltas of the block's bottom row, one bit per step (latest step in bit 0),
+    // and where the block's next checkpoint record goes
+    uint32_t acc_hp, acc_hn;
+    uint32_t* ckp;
 };
+
+// ---- checkpoints (root alignments whose CIGAR is wanted) ----
+// Instead of trace planes for every cell, the score pass leaves just enough behind for the traceback to recompute any
+// (block x 32 steps) tile of the matrix exactly: every 32 steps each working block writes one record
+//   [ Pv[W] | Mv[W] | HP bits | HN bits | 0 | 0 ]   (ck_record_words(W) words)
+// -- its vertical deltas after step t = 32 q (block b is at column t - b then), and the horizontal deltas of its bottom
+// row for the steps 32 (q - 1) + 1 .. 32 q (bit p = step 32 (q - 1) + 1 + p), which are the upper boundary of the block
+// below.  A block's records follow each other, the first one being q_first = ceil(first step / 32); a block that ends
+// between two multiples of 32 adds a last record with the remaining boundary bits.
+constexpr uint32_t kCkExtra = 4;
+__host__ __device__ constexpr uint32_t ck_record_words(uint32_t W) { return W == 1 ? 8u : 2 * W + kCkExtra; }   // a multiple of 16 bytes
+// records reserved per block: a block works for at most (band width + rows) steps
+__host__ __device__ inline uint32_t ck_records_per_block(int64_t band_width, uint32_t rows) { return uint32_t((band_width + rows) / 32 + 3); }
 
 // shared-memory loads by 32-bit shared-space address (keeps the address arithmetic in one register and off the ALU pipe)
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
@@ -236,9 +253,10 @@ __device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {
 //   D0' = (S ^ Pv) | Eq  (D0 = D0' | Mv);  HP = Mv | ~(Pv | D0');  Mv' = HP<<1 & D0;  Pv' = HN<<1 | ~(HP<<1 | D0).
 // (Measured on B200: IMAD / IMAD.HI share their issue slots with the ALU pipe, so shifting HP with multiply-adds
 // instead of one funnel shift gains nothing.)
-template <int W, bool TRACE>
+// KEEP_HP: also hand back HP of every word (the traceback wants HP and the new Pv of each cell).
+template <int W, bool KEEP_HP>
 __device__ __forceinline__ void block_column(uint32_t (&Pv)[W], uint32_t (&Mv)[W], const uint32_t (&Eq)[W], uint32_t in_hp, uint32_t in_hn,
-                                             uint32_t& out_hp, uint32_t& out_hn, uint32_t* trace_row, bool store, uint32_t const two) {
+                                             uint32_t& out_hp, uint32_t& out_hn, uint32_t (&hp_all)[KEEP_HP ? W : 1]) {
     constexpr int CH = W < 8 ? W : 8;
     uint32_t hp_prev = in_hp;
     uint32_t hp_last = in_hp, hn_last = in_hn;
@@ -263,24 +281,39 @@ __device__ __forceinline__ void block_column(uint32_t (&Pv)[W], uint32_t (&Mv)[W
             Mv[c0 + i] = lop3<0xE0>(HPs, D0p, mv);                            // HPs & (D0p | Mv)
             uint32_t const u = lop3<0xFE>(HPs, D0p, mv);                      // HPs | D0
             Pv[c0 + i] = lop3<0xF3>(HNs, u, 0u);                              // HNs | ~(HPs | D0)
-            if (TRACE) {
-                // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
-                if (store) *reinterpret_cast<uint2*>(trace_row + (c0 + i) * 2) = make_uint2(HP, Pv[c0 + i]);
-            }
+            if (KEEP_HP) hp_all[c0 + i] = HP;
         }
     }
     out_hp = hp_last; out_hn = hn_last;
+}
+
+template <int W>
+__device__ __forceinline__ void write_checkpoint(uint32_t* rec, const uint32_t (&Pv)[W], const uint32_t (&Mv)[W], uint32_t hp_bits, uint32_t hn_bits) {
+    if constexpr (W == 1) {
+        *reinterpret_cast<uint4*>(rec) = make_uint4(Pv[0], Mv[0], hp_bits, hn_bits);
+    } else if constexpr (W == 2) {
+        *reinterpret_cast<uint4*>(rec) = make_uint4(Pv[0], Pv[1], Mv[0], Mv[1]);
+        *reinterpret_cast<uint4*>(rec + 4) = make_uint4(hp_bits, hn_bits, 0u, 0u);
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; i += 4) {
+            *reinterpret_cast<uint4*>(rec + i) = make_uint4(Pv[i], Pv[i + 1], Pv[i + 2], Pv[i + 3]);
+            *reinterpret_cast<uint4*>(rec + W + i) = make_uint4(Mv[i], Mv[i + 1], Mv[i + 2], Mv[i + 3]);
+        }
+        *reinterpret_cast<uint4*>(rec + 2 * W) = make_uint4(hp_bits, hn_bits, 0u, 0u);
+    }
 }
 
 // Steps t .. evt-1 of every lane of the warp: no block starts or ends in this range, so the loop is the recurrence
 // and nothing else -- no divergent branch (inactive lanes run the same instructions on dead state and keep publishing
 // the "+1 per column" boundary), window characters two steps and Eq rows one step ahead of their use.
 // FIRST: some lane is on block 0 (its upper boundary is row 0: no carries come in);
-// LAST:  some lane is on the last block (tracks the minimum of the last row).
-template <int W, bool TRACE, bool FIRST, bool LAST>
+// LAST:  some lane is on the last block (tracks the minimum of the last row);
+// CKPT:  working blocks leave a checkpoint record after every step that is a multiple of 32 (the loop is cut there, so
+//        that the stores stay out of the recurrence).
+template <int W, bool CKPT, bool FIRST, bool LAST>
 __device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t const evt, bool const active, uint32_t const src_lane,
-                                          uint32_t const last_block, const uint8_t* const win0, const uint8_t* const idle_chars, uint32_t* trace_row,
-                                          uint32_t const trace_step, uint32_t const two) {
+                                          uint32_t const last_block, const uint8_t* const win0, const uint8_t* const idle_chars, uint32_t const two) {
     uint32_t const inc = active ? 1u : 0u;
     bool const first = FIRST && S.b == 0;
     bool const track = LAST && active && S.b == last_block;
@@ -289,11 +322,12 @@ __device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t 
     uint32_t const eqb = uint32_t(__cvta_generic_to_shared(S.eqb));
     // published deltas: a * x + b with (a, b) = (1, 0) for a working lane and (0, boundary) for an idle one
     uint32_t const pub_a = inc, pub_hp_b = active ? 0u : 0x80000000u;
-    // bottom-row value = base + (#steps with HP) - (#steps with HN), the two counts kept by the multiply-add pipe
+    // bottom-row value = base + (#steps with HP) - (#steps with HN), the two counts kept by multiply-adds
+    // (`two` = 2 comes in as a kernel parameter: as a literal, mad.hi(x, 2, c) is turned back into an ALU-pipe LEA.HI)
     int32_t const score_base = S.score;
     uint32_t n_hp = 0, n_hn = 0;
-    // `two` (= 2) comes in as a kernel parameter: as a literal, mad.hi(x, 2, c) is turned back into an ALU-pipe LEA.HI
     uint32_t EqA[W], EqB[W];
+    uint32_t no_hp[1];
     load_eq<W>(EqA, mad_lo(lds_u8(wp), 4 * W, eqb));
     wp += inc;
     uint32_t cn = lds_u8(wp);                             // character of step t + 1
@@ -305,18 +339,29 @@ __device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t 
         uint32_t r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);                                        \
         if (first) { r_hp = 0; r_hn = 0; }                /* row 0 of a semi-global matrix is all zeros */ \
         uint32_t hp, hn;                                                                                   \
-        block_column<W, TRACE>(S.Pv, S.Mv, EQ_USE, r_hp, r_hn, hp, hn, trace_row, active, two);                 \
+        block_column<W, false>(S.Pv, S.Mv, EQ_USE, r_hp, r_hn, hp, hn, no_hp);                             \
         S.o_hp = mad_lo(hp, pub_a, pub_hp_b); S.o_hn = mad_lo(hn, pub_a, 0u);                              \
-        n_hp = mad_hi(hp, two, n_hp); n_hn = mad_hi(hn, two, n_hn);                                          \
+        n_hp = mad_hi(hp, two, n_hp); n_hn = mad_hi(hn, two, n_hn);                                        \
         if (LAST) {                                                                                        \
             int32_t const sc = score_base + int32_t(n_hp) - int32_t(n_hn);                                 \
             if (track && sc <= S.best) { S.best = sc; S.best_col = t - S.b; }                              \
         }                                                                                                  \
-        if (TRACE) trace_row += trace_step;                                                                \
+        if (CKPT) { S.acc_hp = __funnelshift_l(hp, S.acc_hp, 1); S.acc_hn = __funnelshift_l(hn, S.acc_hn, 1); } \
         ++t;                                                                                               \
     }
-    while (t + 1 < evt) { FXG_STEP(EqA, EqB) FXG_STEP(EqB, EqA) }
-    if (t < evt) FXG_STEP(EqA, EqB)
+    while (t < evt) {
+        // up to and including the next multiple of 32 (checkpoint passes), or all the way
+        uint32_t const seg = CKPT ? min(evt, ((t + 31u) & ~31u) + 1u) : evt;
+        while (t + 1 < seg) { FXG_STEP(EqA, EqB) FXG_STEP(EqB, EqA) }
+        if (t < seg) {
+            FXG_STEP(EqA, EqB)
+#pragma unroll
+            for (int i = 0; i < W; ++i) EqA[i] = EqB[i];
+        }
+        if (CKPT) {
+            if (((t - 1) & 31u) == 0 && active) { write_checkpoint<W>(S.ckp, S.Pv, S.Mv, __brev(S.acc_hp), __brev(S.acc_hn)); S.ckp += ck_record_words(W); }
+        }
+    }
 #undef FXG_STEP
     S.score = score_base + int32_t(n_hp) - int32_t(n_hn);
 }
@@ -343,7 +388,7 @@ __device__ __forceinline__ void load_window_chunk(const uint4* __restrict__ pack
     d0[0] = a; d0[1] = b2; d1[0] = a; d1[1] = b2;
 }
 
-template <int W, bool TRACE>
+template <int W, bool CKPT>
 __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t const lane = threadIdx.x;
@@ -404,7 +449,9 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     __syncwarp();
 
     uint32_t const last_block = nb - 1;
+    uint32_t const ck_per_block = ck_records_per_block(int64_t(T.dhi) - int64_t(T.dlo) + 1, ROWS);
     LaneState<W> S;
+    S.acc_hp = 0; S.acc_hn = 0; S.ckp = nullptr;
 #pragma unroll
     for (int i = 0; i < W; ++i) { S.Pv[i] = 0; S.Mv[i] = 0; }
     S.b = r; S.o_hp = 0x80000000u; S.o_hn = 0;      // an idle lane publishes "the boundary grows by +1 per column"
@@ -425,7 +472,6 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     // number of steps of this warp: last block of the longest task
     uint32_t const my_end = __reduce_max_sync(0xffffffffu, have_task ? (T.n + nb - 1) : 0u);
     constexpr uint32_t kNever = 0x7fffffffu;
-    uint32_t const trace_step = G * 2 * W;
 
     uint32_t t = 1;
     while (t <= my_end) {
@@ -433,7 +479,18 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
         uint32_t const r_hp = __shfl_sync(0xffffffffu, S.o_hp, src_lane);
         uint32_t const r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);
         int32_t const r_sc = __shfl_sync(0xffffffffu, S.score, src_lane);
-        if (S.ce >= 0 && int32_t(t) - int32_t(S.b) > S.ce) { S.b += G; set_block(S.b); }
+        if (S.ce >= 0 && int32_t(t) - int32_t(S.b) > S.ce) {
+            if (CKPT) {
+                // the block ended with step t - 1; boundary bits since the last multiple of 32 go into one more record
+                uint32_t const left_over = (t - 1) & 31u;
+                if (left_over) {
+                    uint32_t const hb = __brev(S.acc_hp) >> (32 - left_over), nbits = __brev(S.acc_hn) >> (32 - left_over);
+                    if constexpr (W == 1) *reinterpret_cast<uint2*>(S.ckp + 2) = make_uint2(hb, nbits);
+                    else *reinterpret_cast<uint4*>(S.ckp + 2 * W) = make_uint4(hb, nbits, 0u, 0u);
+                }
+            }
+            S.b += G; set_block(S.b);
+        }
         int32_t const j = int32_t(t) - int32_t(S.b);
         if (j == S.cs) {
             // (re)start: column cs-1 of this block is (bottom of the block above at cs-1) + 1, 2, ...
@@ -451,6 +508,11 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
                 S.score = r_sc - int32_t(r_hp >> 31) + int32_t(r_hn >> 31) + ROWS;
             }
             S.eqb = peq + S.b * (kNumSymbols * W);
+            if (CKPT) {
+                // steps before the block's first one read as "boundary grows by +1 per column", like an idle lane's output
+                S.acc_hp = 0xffffffffu; S.acc_hn = 0;
+                S.ckp = L.trace + T.trace_base + uint64_t(S.b) * ck_per_block * ck_record_words(W);
+            }
         }
         bool const active = j >= S.cs && j <= S.ce && !dead;
         // ---------------- window ring buffer: the blocks of a ring read characters t-1-b .. t+1-b (two ahead) ----------------
@@ -499,13 +561,12 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
         uint32_t const evt = min(__reduce_min_sync(0xffffffffu, my_evt), my_end + 1);
         bool const any_first = __any_sync(0xffffffffu, active && S.b == 0);
         bool const any_last = __any_sync(0xffffffffu, active && S.b == last_block);
-        uint32_t* const trace_row = TRACE ? (L.trace + T.trace_base + (uint64_t(t - 1) * G + r) * (2 * W)) : nullptr;
         if (any_first) {
-            if (any_last) run_steps<W, TRACE, true, true>(S, t, evt, active, src_lane, last_block, win0, win, trace_row, trace_step, L.two);
-            else run_steps<W, TRACE, true, false>(S, t, evt, active, src_lane, last_block, win0, win, trace_row, trace_step, L.two);
+            if (any_last) run_steps<W, CKPT, true, true>(S, t, evt, active, src_lane, last_block, win0, win, L.two);
+            else run_steps<W, CKPT, true, false>(S, t, evt, active, src_lane, last_block, win0, win, L.two);
         } else {
-            if (any_last) run_steps<W, TRACE, false, true>(S, t, evt, active, src_lane, last_block, win0, win, trace_row, trace_step, L.two);
-            else run_steps<W, TRACE, false, false>(S, t, evt, active, src_lane, last_block, win0, win, trace_row, trace_step, L.two);
+            if (any_last) run_steps<W, CKPT, false, true>(S, t, evt, active, src_lane, last_block, win0, win, L.two);
+            else run_steps<W, CKPT, false, false>(S, t, evt, active, src_lane, last_block, win0, win, L.two);
         }
         t = evt;
     }
@@ -517,142 +578,240 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// traceback over the stored planes + run-length CIGAR (alignment.cpp:156-178 of the reference)
-// ---------------------------------------------------------------------------------------------
-struct WalkTask {
-    uint64_t trace_base;    // as in the DpTask of the trace pass
-    uint64_t ref_base;      // packed-store position of the trace pass' window[0]
-    uint64_t query_base;    // position of query[0] in the byte pool
-    uint32_t n, m;          // sub-window length (== end column) and query length
-    uint32_t group, words;  // G and W of the trace pass
-    uint32_t flags;
-    uint32_t cigar_cap;     // size of this task's slot in the cigar buffer (ops)
-    uint64_t cigar_base;    // first op of the slot; the cigar ends at cigar_base + cigar_cap
-    uint32_t out;
-    uint32_t reserved;
-};
-
 struct WalkResult {
     uint32_t begin_col;     // column where the traceback reached row 0 (sequence1_begin_position)
     uint32_t cigar_len;     // 0xffffffff on overflow / inconsistency; the ops are the LAST cigar_len entries of the slot
 };
 
-struct WalkLaunch {
-    const WalkTask* tasks; uint32_t n_tasks;
-    const uint32_t* trace;
-    const uint32_t* ref_packed; const uint32_t* inline_packed;
-    const uint8_t* query_pool;
-    uint32_t* cigars;             // per-task slots; the traceback runs backwards, so each slot is filled from its end
-    WalkResult* results;
+// ---------------------------------------------------------------------------------------------
+// traceback from checkpoints (alignment.cpp:156-178 of the reference): one LANE per alignment.
+//
+// The score pass of a root alignment left one record per block and 32 steps (see ck_record_words).  The cell the
+// traceback stands on belongs to exactly one tile = (block b) x (steps 32 (q-1)+1 .. 32 q, i.e. columns t - b); the lane
+// recomputes that tile with the engine's own word-step -- from the block's record at step 32 (q-1) and the boundary bits
+// of the block above, exactly as the score pass computed it -- keeps its HP / VP' bits in local memory, follows the path
+// until it leaves the tile, and repeats.  No trace planes ever reach HBM.
+// ---------------------------------------------------------------------------------------------
+struct Walk2Task {
+    uint64_t ck_base;       // first word of the task's checkpoint records
+    uint64_t ref_base;      // packed-store position of the score pass' window[0]
+    uint64_t query_base;    // position of query[0] in the pool (bytes and Peq planes)
+    uint64_t cigar_base;    // first op of the task's slot; the cigar ends at cigar_base + cigar_cap
+    uint32_t n, m;          // window and query length of the score pass
+    int32_t dlo, dhi;       // its band
+    uint32_t end_col;       // column of the alignment's last cell (row m)
+    uint32_t score;         // its number of errors
+    uint32_t flags;
+    uint32_t cigar_cap;
+    uint32_t out;
+    uint32_t reserved;
 };
 
-// trace priority: left > up > diagonal.  This is the ONE place on the device that encodes it
-// (oracle: FXO_TRACE_PRIORITY in oracle/floxer_oracle.h).
-//
-// One warp per alignment.  The walk itself is sequential, but the memory side is not: the warp loads a
-// tile of the trace planes (32 columns x the 2 words around the current row) with one coalesced round of
-// loads (each lane keeps one column in registers), advances over whole diagonal runs at once (one ballot tells
-// how far the path follows the diagonal), and prefetches the tile it will most likely need next.
-constexpr int kWalkWarps = 4;
+struct Walk2Launch {
+    const Walk2Task* tasks; uint32_t n_tasks;
+    const uint32_t* ck;
+    const uint32_t* ref_packed; const uint32_t* inline_packed;
+    const uint32_t* peq_table; uint64_t peq_plane_words;
+    const uint8_t* query_pool;
+    uint32_t* cigars;
+    WalkResult* results;
+    uint32_t two;
+};
 
-__global__ void __launch_bounds__(32 * kWalkWarps) walk_kernel(WalkLaunch const L) {
-    __shared__ uint8_t s_qry[kWalkWarps][64];      // query characters of the tile's rows
-    uint32_t const warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    uint32_t const id = blockIdx.x * kWalkWarps + warp;
-    if (id >= L.n_tasks) return;
-    WalkTask const T = L.tasks[id];
-    const uint32_t* ref = (T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed;
-    const uint32_t* const trace = L.trace + T.trace_base;
-    uint32_t const W = T.words, G = T.group, ROWS = 32 * W;
+// alignments per walk2 CTA (one lane each) and its block size; wide blocks need so much shared memory per lane that
+// fewer lanes share a CTA
+__host__ __device__ constexpr uint32_t walk2_lanes(uint32_t W) { return W <= 8 ? 64u : (W == 16 ? 32u : 16u); }
+__host__ __device__ constexpr uint32_t walk2_threads(uint32_t W) { return walk2_lanes(W) < 32u ? 32u : walk2_lanes(W); }
+// shared memory of a walk2 CTA: per lane the Eq rows of its current block (6 W words) and the HP / VP' bits of its
+// current tile (32 steps x 2 W words), both laid out [word][lane] so that any per-lane index is conflict-free
+__host__ __device__ constexpr size_t walk2_smem_bytes(uint32_t W) { return size_t(kNumSymbols * W + 64 * W) * walk2_lanes(W) * 4; }
+
+template <int W>
+__global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch const L) {
+    extern __shared__ __align__(16) uint32_t w2_smem[];
+    constexpr int ROWS = 32 * W;
+    constexpr uint32_t RECW = ck_record_words(W);
+    constexpr uint32_t kWalk2Threads = walk2_lanes(W);                      // stride of the per-lane tables
+    uint32_t const tid = threadIdx.x < kWalk2Threads ? threadIdx.x : 0u;
+    uint32_t* const eq_s = w2_smem + tid;                                    // Eq[sym][w]  at eq_s[(sym * W + w) * kWalk2Threads]
+    uint32_t* const bits = w2_smem + kNumSymbols * W * kWalk2Threads + tid;  // HP / VP' of step p, word w at bits[((p * W + w) * 2 + {0, 1}) * kWalk2Threads]
+    uint32_t const id = blockIdx.x * kWalk2Threads + threadIdx.x;
+    bool const mine = threadIdx.x < kWalk2Threads && id < L.n_tasks;
+    bool done = !mine;
+    Walk2Task T;
+    if (!done) T = L.tasks[id];
+    else { T = Walk2Task{}; T.m = 1; }
+    const uint32_t* const ref = (T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed;
     uint32_t const nb = (T.m + ROWS - 1) / ROWS;
     uint32_t const pad = nb * ROWS - T.m;
-    uint32_t* const slot_end = L.cigars + T.cigar_base + T.cigar_cap;      // run q (counted from the alignment's end) lives at slot_end[-1 - q]
-    uint32_t n_runs = 0, cur_op = 0, cur_len = 0;
-    bool bad = false;
-    uint32_t i = T.m, j = T.n;
-    uint32_t j0 = 0, w0 = 0, i0 = 0;
-    bool have_tile = false;
+    int32_t const dlo = T.dlo - int32_t(pad), dhi = T.dhi - int32_t(pad);
+    uint32_t const ck_per_block = ck_records_per_block(int64_t(T.dhi) - int64_t(T.dlo) + 1, ROWS);
+    const uint32_t* const ck = L.ck + T.ck_base;
+    uint32_t* const slot_end = L.cigars + T.cigar_base + T.cigar_cap;
 
-    auto cell_ptr = [&](uint32_t col, uint32_t word) -> const uint32_t* {
-        uint32_t const blk = word / W, iw = word % W;
-        uint64_t const t = uint64_t(col) + blk;                       // step at which (block, column) was computed
-        return trace + (((t - 1) * G + blk % G) * W + iw) * 2;
+    // first / last step of block b in the score pass (block b is at column t - b at step t)
+    auto block_steps = [&](uint32_t b, int32_t& ts, int32_t& te) {
+        int32_t const lo = int32_t(ROWS) * int32_t(b) + 1 + dlo, hi = int32_t(ROWS) * int32_t(b + 1) + dhi;
+        ts = (lo < 1 ? 1 : lo) + int32_t(b);
+        te = (hi > int32_t(T.n) ? int32_t(T.n) : hi) + int32_t(b);
     };
 
-    // emit `len` copies of `op` (uniform across the warp)
+    uint32_t i = T.m, j = T.end_col;                             // the cell the traceback stands on (row, column; 1-based)
+    uint32_t n_runs = 0, cur_op = 0, cur_len = 0, errors = 0;
+    bool bad = false;
+    uint32_t eq_block = 0xffffffffu;                             // block whose Eq rows are in shared memory
+    uint32_t chars[5] = {0, 0, 0, 0, 0};                         // window characters of the tile's columns, 4 bits each, step p at nibble p
     auto emit = [&](uint32_t op, uint32_t len) {
         if (op == cur_op) { cur_len += len; return; }
-        if (cur_len) { if (n_runs < T.cigar_cap) { if (lane == 0) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
+        if (cur_len) { if (n_runs < T.cigar_cap) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
         cur_op = op; cur_len = len;
     };
-    uint4 v = make_uint4(0, 0, 0, 0);          // this lane's column of the tile: hp, vp of word w0 and of word w0 - 1
-    uint32_t rc = 0;                           // and its reference character
-    while (i > 0) {
-        if (j == 0) { emit(1, i); i = 0; break; }                      // column 0: only "up" remains
-        uint32_t const u = i - 1 + pad;
-        uint32_t const w = u >> 5;
-        if (!have_tile || j0 - j > 31u || w0 - w > 1u || i0 - i > 63u) {
-            j0 = j; w0 = w; i0 = i;
-            __syncwarp();
-            v = make_uint4(0, 0, 0, 0); rc = 0;
-            if (lane < j0) {                                           // column j0 - lane >= 1
-                uint32_t const col = j0 - lane;
-                uint2 const a = *reinterpret_cast<const uint2*>(cell_ptr(col, w0));
-                v.x = a.x; v.y = a.y;
-                if (w0 >= 1) { uint2 const c2 = *reinterpret_cast<const uint2*>(cell_ptr(col, w0 - 1)); v.z = c2.x; v.w = c2.y; }
-                rc = packed_base(ref, T.ref_base + col - 1);
-                // the tile after this one, if the path keeps to its diagonal
-                if (col > 32 && i0 > 32) {
-                    uint32_t const w2 = (i0 - 33 + pad) >> 5;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_ptr(col - 32, w2)));
-                    if (w2 >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_ptr(col - 32, w2 - 1)));
+    auto tile_char = [&](uint32_t p) -> uint32_t {               // p in 0 .. 31
+        uint32_t const w = p < 8 ? chars[0] : (p < 16 ? chars[1] : (p < 24 ? chars[2] : chars[3]));
+        return (w >> (4 * (p & 7u))) & 15u;
+    };
+
+    while (!__all_sync(0xffffffffu, done)) {
+        uint32_t b = 0, q = 0;
+        if (!done) {
+            if (i == 0) done = true;
+            else if (j == 0) { emit(1, i); errors += i; i = 0; done = true; }     // column 0: only "up" remains
+        }
+        if (!done) {
+            // ---------------- recompute the tile of (i, j) ----------------
+            uint32_t const u = i + pad;                                          // row in the padded numbering (1-based)
+            b = (u - 1) / ROWS;
+            uint32_t const t_cell = j + b;
+            q = (t_cell + 31) >> 5;
+            int32_t ts, te; block_steps(b, ts, te);
+            int32_t const t0 = 32 * int32_t(q - 1);                              // the tile covers steps t0 + 1 .. t0 + 32
+            // the path only moves up and left: nothing after the step of (i, j) is needed
+            int32_t const t_lo = t0 + 1 > ts ? t0 + 1 : ts, t_hi = int32_t(t_cell) < te ? int32_t(t_cell) : te;
+            // window characters of steps t0 + 1 .. t0 + 32: columns t0 + 1 - b .. (store positions may start before the window: never used)
+            {
+                int64_t const pos0 = int64_t(T.ref_base) + int64_t(t0) - int64_t(b);      // store position of step t0 + 1 (column - 1)
+                int64_t const w0 = pos0 >= 0 ? (pos0 >> 3) : -((7 - pos0) >> 3);          // floor(pos0 / 8)
+                uint32_t const sh = uint32_t(pos0 - w0 * 8) * 4;
+                uint32_t raw[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) raw[k] = w0 + k >= 0 ? __ldg(ref + (w0 + k)) : 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) chars[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
+            }
+            uint32_t Pv[W], Mv[W];
+            if (t0 >= ts) {
+                const uint32_t* rec = ck + (uint64_t(b) * ck_per_block + uint32_t(int32_t(q - 1) - ((ts + 31) >> 5))) * RECW;
+                if constexpr (W == 1) { uint2 const v = *reinterpret_cast<const uint2*>(rec); Pv[0] = v.x; Mv[0] = v.y; }
+                else if constexpr (W == 2) { uint4 const v = *reinterpret_cast<const uint4*>(rec); Pv[0] = v.x; Pv[1] = v.y; Mv[0] = v.z; Mv[1] = v.w; }
+                else {
+#pragma unroll
+                    for (int w = 0; w < W; w += 4) {
+                        uint4 const a = *reinterpret_cast<const uint4*>(rec + w), m4 = *reinterpret_cast<const uint4*>(rec + W + w);
+                        Pv[w] = a.x; Pv[w + 1] = a.y; Pv[w + 2] = a.z; Pv[w + 3] = a.w;
+                        Mv[w] = m4.x; Mv[w + 1] = m4.y; Mv[w + 2] = m4.z; Mv[w + 3] = m4.w;
+                    }
+                }
+            } else {
+                // the block begins inside the tile: "block above + 1, 2, ..." (wildcard rows of block 0 carry value 0)
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    int32_t const virt = b == 0 ? int32_t(pad) - 32 * w : 0;
+                    Pv[w] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
+                    Mv[w] = 0;
                 }
             }
-            if (lane < i0) s_qry[warp][lane] = L.query_pool[T.query_base + i0 - lane - 1];
-            if (lane + 32 < i0) s_qry[warp][lane + 32] = L.query_pool[T.query_base + i0 - lane - 33];
-            __syncwarp();
-            have_tile = true;
-        }
-        // Lane l looks at the cell s = l - d0 steps down the diagonal from (i, j): row i - s, column j0 - l (its own column).
-        uint32_t const d0 = j0 - j;
-        int32_t const sdiag = int32_t(lane) - int32_t(d0);
-        bool valid = sdiag >= 0 && uint32_t(sdiag) < i && lane < j0;
-        uint32_t hpb = 0, vpb = 0; bool match = false;
-        if (valid) {
-            uint32_t const us = u - uint32_t(sdiag);                   // >= pad because row i - s >= 1
-            uint32_t const ws = us >> 5, bs = us & 31u;
-            uint32_t const dw = w0 - ws;
-            uint32_t const row = i - uint32_t(sdiag);
-            valid = dw <= 1u && i0 - row <= 63u;
-            if (valid) {
-                hpb = ((dw ? v.z : v.x) >> bs) & 1u;
-                vpb = ((dw ? v.w : v.y) >> bs) & 1u;
-                match = s_qry[warp][i0 - row] == uint8_t(rc);
+            // upper boundary: bit p = horizontal delta of the row above the block at step t0 + 1 + p
+            uint32_t top_hp = 0, top_hn = 0;
+            if (b > 0) {
+                int32_t us, ue; block_steps(b - 1, us, ue);                      // the block above is one step ahead: its step t - 1
+                int32_t const uq_first = (us + 31) >> 5, uq_last = (ue + 31) >> 5;
+                uint32_t hpA = 0xffffffffu, hnA = 0, hpB = 0xffffffffu, hnB = 0;
+                const uint32_t* const urec = ck + uint64_t(b - 1) * ck_per_block * RECW;
+                constexpr int BO = W == 1 ? 2 : 2 * W;                           // where a record keeps its boundary bits
+                if (int32_t(q) >= uq_first && int32_t(q) <= uq_last) { uint2 const v = *reinterpret_cast<const uint2*>(urec + uint64_t(int32_t(q) - uq_first) * RECW + BO); hpA = v.x; hnA = v.y; }
+                if (int32_t(q) - 1 >= uq_first && int32_t(q) - 1 <= uq_last) { uint2 const v = *reinterpret_cast<const uint2*>(urec + uint64_t(int32_t(q) - 1 - uq_first) * RECW + BO); hpB = v.x; hnB = v.y; }
+                top_hp = (hpA << 1) | (hpB >> 31);
+                top_hn = (hnA << 1) | (hnB >> 31);
+                // steps of the block above outside its working range publish the "+1" boundary
+                int32_t const p_lo = us - t0, p_hi = ue - t0;                    // bit p <-> upper step t0 + p
+                uint32_t valid = 0;
+                if (p_hi >= 0 && p_lo <= 31) {
+                    uint32_t const lo = p_lo > 0 ? uint32_t(p_lo) : 0u, hi = p_hi < 31 ? uint32_t(p_hi) : 31u;
+                    valid = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                }
+                top_hp = (top_hp & valid) | ~valid;
+                top_hn &= valid;
+            }
+            // Eq rows of this block
+            if (eq_block != b) {
+                eq_block = b;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    uint32_t const gw = b * W + w;
+                    int32_t const virt = int32_t(pad) - int32_t(32 * gw);
+                    uint32_t const wild = virt >= 32 ? 0xffffffffu : (virt > 0 ? ((1u << virt) - 1u) : 0u);
+#pragma unroll
+                    for (int sym = 0; sym < kNumSymbols; ++sym) {
+                        const uint32_t* plane = L.peq_table + uint64_t(sym) * L.peq_plane_words;
+                        eq_s[(sym * W + w) * kWalk2Threads] = peq_window(plane, int64_t(T.query_base) - int64_t(pad) + int64_t(32 * gw)) | wild;
+                    }
+                }
+            }
+            for (int32_t t = t_lo; t <= t_hi; ++t) {
+                uint32_t const p = uint32_t(t - t0 - 1);
+                uint32_t const c = tile_char(p);
+                uint32_t Eq[W], hp_all[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) Eq[w] = eq_s[(c * W + w) * kWalk2Threads];
+                uint32_t hp, hn;
+                block_column<W, true>(Pv, Mv, Eq, ((top_hp >> p) & 1u) << 31, ((top_hn >> p) & 1u) << 31, hp, hn, hp_all);
+                // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    bits[((p * W + w) * 2) * kWalk2Threads] = hp_all[w];
+                    bits[((p * W + w) * 2 + 1) * kWalk2Threads] = Pv[w];
+                }
             }
         }
-        // trace priority at every cell: left (hp) first, then up (vp), else diagonal
-        uint32_t const diag_bits = __ballot_sync(0xffffffffu, valid && !hpb && !vpb) >> d0;
-        uint32_t const run = diag_bits == 0xffffffffu ? 32u : uint32_t(__ffs(~diag_bits) - 1);   // consecutive diagonal cells from (i, j)
-        if (run == 0) {
-            uint32_t const left_here = (__ballot_sync(0xffffffffu, valid && hpb) >> d0) & 1u;
-            if (left_here) { emit(2, 1); --j; }                        // left  -> D
-            else { emit(1, 1); --i; }                                  // up    -> I  (the current cell is always valid)
-        } else {
-            uint32_t mbits = __ballot_sync(0xffffffffu, match) >> d0;
-            uint32_t left = run;
-            while (left) {                                             // run-length encode '=' / X along the diagonal run
-                uint32_t const is_eq = mbits & 1u;
-                uint32_t len = __ffs(is_eq ? ~mbits : mbits) - 1;       // ffs(0) - 1 = 0xffffffff -> clamped below
-                len = len > left ? left : len;
-                emit(is_eq ? 7u : 8u, len);
-                mbits = len >= 32u ? 0u : mbits >> len; left -= len;
+        // ---------------- follow the path while it stays inside the tile ----------------
+        // trace priority: left > up > diagonal (the one place that encodes it; oracle: FXO_TRACE_PRIORITY)
+        if (!done) {
+            // position inside the tile: step p (column), row r of the block (0-based); the tile is left when p < 0 (column
+            // before the tile), r < 0 (row of the block above), or the matrix' row 0 / column 0 is reached
+            uint32_t const u0 = i + pad;
+            int32_t p = int32_t(j + b) - 32 * int32_t(q - 1) - 1;
+            int32_t r = int32_t((u0 - 1) % ROWS);
+            int32_t const r_min = b == 0 ? int32_t(pad) : 0;                       // first real row of the block
+            int32_t const p_min = (int32_t(b) + 1 - 32 * int32_t(q - 1) - 1) > 0 ? (int32_t(b) + 1 - 32 * int32_t(q - 1) - 1) : 0;   // step of column 1
+            uint32_t ops_err = 0;
+            while (p >= p_min && r >= r_min) {
+                uint32_t const wi = uint32_t(r) >> 5, bit = uint32_t(r) & 31u;
+                uint32_t const hpb = (bits[((uint32_t(p) * W + wi) * 2) * kWalk2Threads] >> bit) & 1u;
+                uint32_t const vpb = (bits[((uint32_t(p) * W + wi) * 2 + 1) * kWalk2Threads] >> bit) & 1u;
+                // query[i-1] == window[j-1] is the Eq bit of that row for the column's character
+                uint32_t const match = (eq_s[(tile_char(uint32_t(p)) * W + wi) * kWalk2Threads] >> bit) & 1u;
+                uint32_t const op = hpb ? 2u : (vpb ? 1u : (match ? 7u : 8u));     // D, I, =, X
+                ops_err += op != 7u;
+                if (op == cur_op) ++cur_len;
+                else {
+                    if (cur_len) { if (n_runs < T.cigar_cap) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
+                    cur_op = op; cur_len = 1;
+                }
+                p -= op != 1u;                                                     // left and diagonal move one column back
+                r -= op != 2u;                                                     // up and diagonal move one row up
             }
-            i -= run; j -= run;
+            // back to matrix coordinates
+            int32_t const p0 = int32_t(j + b) - 32 * int32_t(q - 1) - 1, r0 = int32_t((u0 - 1) % ROWS);
+            j -= uint32_t(p0 - p); i -= uint32_t(r0 - r);
+            errors += ops_err;
         }
     }
-    if (cur_len) { if (n_runs < T.cigar_cap) { if (lane == 0) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
-    if (lane == 0) { WalkResult R; R.begin_col = j; R.cigar_len = bad ? 0xffffffffu : n_runs; L.results[T.out] = R; }
+    if (mine) {
+        if (cur_len) { if (n_runs < T.cigar_cap) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
+        if (errors != T.score) bad = true;                                       // the path must cost exactly what the score pass found
+        WalkResult R; R.begin_col = j; R.cigar_len = bad ? 0xffffffffu : n_runs;
+        L.results[T.out] = R;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -48,6 +48,22 @@ struct DevBuf {
         cap = want;
         return e;
     }
+    // grows the buffer keeping its first `keep` bytes
+    cudaError_t ensure_preserving(size_t bytes, size_t keep, cudaStream_t stream) {
+        if (bytes <= cap) return cudaSuccess;
+        void* np = nullptr;
+        size_t const want = bytes + bytes / 2 + 256;
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) return e;
+        if (p && keep) {
+            e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
+        }
+        if (p) cudaFree(p);
+        p = np; cap = want;
+        return cudaSuccess;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -89,19 +105,11 @@ struct Pass {                            // one DP pass of the engine
     uint32_t flags;
 };
 
-struct TraceReq {                        // traceback request for an accepted CIGAR-mode alignment
-    Pass pass;                           // sub-window pass (band around the end diagonal)
-    uint32_t s_star;                     // score found by the score pass
-    uint32_t col0;                       // sub-window start inside the original window
-};
-
-struct TraceOut { uint32_t begin_col; uint64_t cigar_offset; uint32_t cigar_len; };
-
 constexpr int kWidths[6] = {1, 2, 4, 8, 16, 32};
 
 struct Config { uint8_t widx; uint8_t G; uint32_t nb; uint64_t word_steps; };
 
-struct ConfigCacheEntry { uint32_t n, m; int32_t dlo, dhi; Config cfg; bool ok; bool valid; bool trace; };
+struct ConfigCacheEntry { uint32_t n, m; int32_t dlo, dhi; Config cfg; bool ok; bool valid; };
 
 // Everything one host worker needs to run passes on its own stream.
 struct Worker {
@@ -111,15 +119,29 @@ struct Worker {
     cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf d_tasks, d_results, d_trace, d_wtasks, d_wresults, d_cigars;
+    // tracebacks are long chains of dependent steps: the root alignments of a wave are cut into chunks, each chunk's
+    // tracebacks run on a stream of their own beside the score passes (and tracebacks) of the other chunks
+    static constexpr int kWalkSlots = 4;
+    DevBuf d_tasks, d_results, d_ck[kWalkSlots], d_wtasks, d_wresults, d_cigars;
+    cudaStream_t walk_stream[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_walk_done[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr}, ev_w0 = nullptr, ev_w1[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
     PinnedBuf h_tasks, h_results, h_wtasks, h_wresults;
     fxg_counters ctr{};
     std::string err;
     std::vector<ConfigCacheEntry> cfg_cache = std::vector<ConfigCacheEntry>(8192);
     std::vector<uint64_t> keys, keys_tmp;
     std::vector<Config> cfgs;
+    uint64_t cig_used = 0;               // ops of d_cigars filled by the current run
     void release() {
-        for (DevBuf* b : {&d_tasks, &d_results, &d_trace, &d_wtasks, &d_wresults, &d_cigars}) b->release();
+        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars}) b->release();
+        if (ev_w0) { cudaEventDestroy(ev_w0); ev_w0 = nullptr; }
+        for (int q = 0; q < kWalkSlots; ++q) {
+            d_ck[q].release();
+            if (ev_walk_done[q]) cudaEventDestroy(ev_walk_done[q]);
+            if (ev_w1[q]) cudaEventDestroy(ev_w1[q]);
+            if (walk_stream[q]) cudaStreamDestroy(walk_stream[q]);
+            ev_walk_done[q] = ev_w1[q] = nullptr; walk_stream[q] = nullptr;
+        }
         for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults}) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -138,8 +160,8 @@ struct Worker {
 struct HostProf {
     bool on = std::getenv("FXG_PROFILE") != nullptr;
     double acc[16] = {0};
-    const char* names[16] = {"setup", "admission", "build_passes", "plan", "sort", "tasks+h2d", "launch", "", "sync+d2h", "finish",
-                             "trace_plan", "trace_dp", "walk", "emit", "", ""};
+    const char* names[16] = {"setup", "admission", "build_passes", "plan", "sort", "tasks+h2d", "launch", "root prep", "sync+d2h", "finish",
+                             "root chunk", "root sync", "walk issue", "emit", "barrier", "cigars d2h"};
     std::chrono::steady_clock::time_point t0;
     void start(Worker const& w) { if (on && w.id == 0) t0 = std::chrono::steady_clock::now(); }
     void lap(Worker const& w, int i) {
@@ -150,7 +172,7 @@ struct HostProf {
     }
     void report() {
         if (!on) return;
-        for (int i = 0; i < 14; ++i) if (names[i][0]) fprintf(stderr, "[fxg] %-14s %8.3f ms\n", names[i], acc[i]);
+        for (int i = 0; i < 16; ++i) if (names[i][0]) fprintf(stderr, "[fxg] %-14s %8.3f ms\n", names[i], acc[i]);
         for (double& a : acc) a = 0;
     }
 };
@@ -254,16 +276,21 @@ struct RunTimer {
     }
 };
 
+int env_int(const char* name, int dflt, int lo, int hi) {
+    if (const char* e = std::getenv(name)) { int const v = std::atoi(e); if (v >= lo && v <= hi) return v; }
+    return dflt;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel dispatch
 
-template <int W, bool TR>
+template <int W, bool CKPT>
 cudaError_t launch_one(DpLaunch const& L, uint32_t grid, size_t smem, cudaStream_t s) {
-    dp_kernel<W, TR><<<grid, 32, smem, s>>>(L);
+    dp_kernel<W, CKPT><<<grid, 32, smem, s>>>(L);
     return cudaGetLastError();
 }
 
-cudaError_t launch_dp(int widx, bool trace, DpLaunch const& L, uint32_t grid, size_t smem, cudaStream_t s) {
-    switch (widx * 2 + (trace ? 1 : 0)) {
+cudaError_t launch_dp(int widx, bool checkpoints, DpLaunch const& L, uint32_t grid, size_t smem, cudaStream_t s) {
+    switch (widx * 2 + (checkpoints ? 1 : 0)) {
         case 0: return launch_one<1, false>(L, grid, smem, s);
         case 1: return launch_one<1, true>(L, grid, smem, s);
         case 2: return launch_one<2, false>(L, grid, smem, s);
@@ -280,16 +307,36 @@ cudaError_t launch_dp(int widx, bool trace, DpLaunch const& L, uint32_t grid, si
     return cudaErrorInvalidValue;
 }
 
-template <int W, bool TR>
+template <int W>
+cudaError_t launch_walk_one(Walk2Launch const& L, cudaStream_t s) {
+    size_t const smem = walk2_smem_bytes(W);
+    walk2_kernel<W><<<(L.n_tasks + walk2_lanes(W) - 1) / walk2_lanes(W), walk2_threads(W), smem, s>>>(L);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_walk(int widx, Walk2Launch const& L, cudaStream_t s) {
+    switch (widx) {
+        case 0: return launch_walk_one<1>(L, s);
+        case 1: return launch_walk_one<2>(L, s);
+        case 2: return launch_walk_one<4>(L, s);
+        case 3: return launch_walk_one<8>(L, s);
+        case 4: return launch_walk_one<16>(L, s);
+        case 5: return launch_walk_one<32>(L, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int W>
 cudaError_t set_smem_attr(size_t bytes) {
-    return cudaFuncSetAttribute(dp_kernel<W, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    cudaError_t e = cudaFuncSetAttribute(dp_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dp_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (e == cudaSuccess && walk2_smem_bytes(W) <= bytes) e = cudaFuncSetAttribute(walk2_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(walk2_smem_bytes(W)));
+    return e;
 }
 
 cudaError_t set_all_smem_attrs(size_t bytes) {
     cudaError_t e;
-#define FXG_SET(W)                                                        \
-    if ((e = set_smem_attr<W, false>(bytes)) != cudaSuccess) return e;    \
-    if ((e = set_smem_attr<W, true>(bytes)) != cudaSuccess) return e;
+#define FXG_SET(W) if ((e = set_smem_attr<W>(bytes)) != cudaSuccess) return e;
     FXG_SET(1) FXG_SET(2) FXG_SET(4) FXG_SET(8) FXG_SET(16) FXG_SET(32)
 #undef FXG_SET
     return cudaSuccess;
@@ -316,7 +363,7 @@ uint64_t word_steps_of(Pass const& p, uint32_t W, uint32_t nb) {
 // Picks words-per-lane W and ring size G for one pass.  The ring must be long enough that a lane is idle
 // (and publishes the +1 boundary) whenever the block below still needs a boundary from it:
 //   G > (B - 4) / (32 W + 1) + 2,  B = number of diagonals in the band  (derivation in DESIGN.md).
-bool choose_config(Pass const& p, bool trace, size_t smem_limit, Config& out) {
+bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
     uint32_t const nw = (p.m + 31) / 32;
     int64_t const B = int64_t(p.dhi) - int64_t(p.dlo) + 1;
     double best_cost = 1e300;
@@ -347,11 +394,6 @@ bool choose_config(Pass const& p, bool trace, size_t smem_limit, Config& out) {
         // every block start / end interrupts the warp for a few hundred issue slots; the rings of a warp mostly, but not
         // always, have the same shape and then share these interruptions
         cost += 2.0 * nb * 100.0 / std::sqrt(double(tpw));
-        if (trace) {
-            // trace passes also write 8 bytes per lane, word and step: about 22 bytes per SM and cycle
-            double const bytes = double(steps) * G * W * 8.0;
-            cost = std::max(cost, bytes / 22.0);
-        }
         if (cost < best_cost) { best_cost = cost; out = Config{uint8_t(wi), uint8_t(G), nb, 0}; found = true; }
     }
     if (found) out.word_steps = word_steps_of(p, uint32_t(kWidths[out.widx]), out.nb);
@@ -359,13 +401,13 @@ bool choose_config(Pass const& p, bool trace, size_t smem_limit, Config& out) {
 }
 
 // the same (m, n, band) recurs for every anchor of a read at one tree level: memoise
-bool cached_config(Worker& w, Pass const& p, bool trace, size_t smem_limit, Config& out) {
-    uint64_t h = (uint64_t(p.n) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(p.m) * 0xC2B2AE3D27D4EB4Full) ^ (uint64_t(uint32_t(p.dlo)) << 21) ^ uint64_t(uint32_t(p.dhi)) ^ (trace ? 0x5555555555ull : 0);
+bool cached_config(Worker& w, Pass const& p, size_t smem_limit, Config& out) {
+    uint64_t h = (uint64_t(p.n) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(p.m) * 0xC2B2AE3D27D4EB4Full) ^ (uint64_t(uint32_t(p.dlo)) << 21) ^ uint64_t(uint32_t(p.dhi));
     h ^= h >> 29;
     ConfigCacheEntry& e = w.cfg_cache[h & (w.cfg_cache.size() - 1)];
-    if (e.valid && e.trace == trace && e.n == p.n && e.m == p.m && e.dlo == p.dlo && e.dhi == p.dhi) { out = e.cfg; return e.ok; }
-    e.valid = true; e.trace = trace; e.n = p.n; e.m = p.m; e.dlo = p.dlo; e.dhi = p.dhi;
-    e.ok = choose_config(p, trace, smem_limit, e.cfg);
+    if (e.valid && e.n == p.n && e.m == p.m && e.dlo == p.dlo && e.dhi == p.dhi) { out = e.cfg; return e.ok; }
+    e.valid = true; e.n = p.n; e.m = p.m; e.dlo = p.dlo; e.dhi = p.dhi;
+    e.ok = choose_config(p, smem_limit, e.cfg);
     out = e.cfg;
     return e.ok;
 }
@@ -385,14 +427,15 @@ void radix_sort(std::vector<uint64_t>& keys, std::vector<uint64_t>& tmp, int lo_
 
 // ------------------------------------------------------------------------------------------------ running passes
 
-// Runs `passes` (score passes, or trace passes when trace_bases != nullptr) on the worker's stream.
+// Runs `passes` on the worker's streams: plain score passes, or (ck_bases != nullptr) score passes that leave checkpoint
+// records at those offsets of the worker's checkpoint buffer.
 // results points to pinned memory owned by the worker and stays valid until its next call.
-int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const& passes, const uint64_t* trace_bases,
+int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const& passes, const uint64_t* ck_bases, uint32_t* ck_buffer,
                const DpResult** results) {
     size_t const N = passes.size();
     *results = nullptr;
     if (N == 0) return FXG_OK;
-    bool const trace = trace_bases != nullptr;
+    bool const trace = ck_bases != nullptr;
 
     g_prof.start(w);
     // sort key: configuration (descending cost class), then steps descending, then the pass index
@@ -400,7 +443,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     w.keys.resize(N);
     for (size_t i = 0; i < N; ++i) {
         Config& cf = w.cfgs[i];
-        if (!cached_config(w, passes[i], trace, c->smem_limit, cf))
+        if (!cached_config(w, passes[i], c->smem_limit, cf))
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
                         passes[i].m, passes[i].n, passes[i].dlo, passes[i].dhi);
         uint64_t const steps = std::min<uint64_t>(uint64_t(passes[i].n) + cf.nb - 1, (1u << 19) - 1);
@@ -421,9 +464,9 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
         Pass const& p = passes[idx];
         DpTask& t = tasks[i];
         t.ref_base = p.ref_base; t.query_base = p.query_base;
-        t.trace_base = trace ? trace_bases[idx] : 0;
+        t.trace_base = trace ? ck_bases[idx] : 0;
         t.n = p.n; t.m = p.m; t.dlo = p.dlo; t.dhi = p.dhi; t.flags = p.flags; t.out = idx;
-        if (trace) w.ctr.trace_word_steps += w.cfgs[idx].word_steps; else w.ctr.dp_word_steps += w.cfgs[idx].word_steps;
+        w.ctr.dp_word_steps += w.cfgs[idx].word_steps;
         w.ctr.dp_cells_full += uint64_t(p.m) * p.n;
     }
     w.ctr.dp_tasks += N;
@@ -465,7 +508,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
         L.peq_table = pool.peq.as<uint32_t>();
         L.peq_plane_words = pool.plane_words;
         L.results = w.d_results.as<DpResult>();
-        L.trace = w.d_trace.as<uint32_t>();
+        L.trace = ck_buffer;
         X.smem = size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
         if (X.smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", X.smem);
         X.grid = uint32_t((L.n_tasks + tpw - 1) / tpw);
@@ -499,7 +542,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     CUDA_TRY(w.err, cudaStreamSynchronize(w.stream));
     float ms = 0;
     CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
-    if (trace) w.ctr.trace_kernel_ms += ms; else w.ctr.dp_kernel_ms += ms;
+    w.ctr.dp_kernel_ms += ms;
     g_prof.lap(w, trace ? 11 : 8);
     *results = w.h_results.as<DpResult>();
     for (size_t q = 0; q < N; ++q)
@@ -510,92 +553,154 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
 // ops reserved for the cigar of an alignment with s errors: at most s error runs and s + 1 match runs
 inline uint64_t cigar_cap_for(uint32_t s) { return uint64_t(2) * s + 3; }
 
-// Trace passes + walks for `reqs`; fills outs[i].  The cigar of request i is written by the device into its slot of
-// cigar_cap_for(s) ops; slots follow each other in request order, and the whole region is copied straight into
-// host_cigars (page-locked, region_base = index of its first op in the pool the offsets refer to).
-// Works in chunks bounded by `budget_bytes` of trace planes.
-int run_traces(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<TraceReq> const& reqs, uint64_t budget_bytes,
-               uint32_t* host_cigars, uint64_t region_base, std::vector<TraceOut>& outs) {
-    size_t const N = reqs.size();
-    outs.assign(N, TraceOut{0, 0, 0});
+// result of a root alignment whose CIGAR is wanted
+struct RootOut {
+    int32_t score; uint32_t end_col;     // as DpResult
+    uint32_t begin_col;                  // column where the traceback reached row 0
+    uint64_t cigar_offset;               // first op, counted in the worker's cigar buffer (w.d_cigars)
+    uint32_t cigar_len;
+};
+
+// Score passes with checkpoints + tracebacks for `passes` (alignment.cpp:147-180): pass i is accepted when its score is
+// at most max_errors[i]; accepted passes get their CIGAR, written by the device into a slot of cigar_cap_for(score) ops
+// of the worker's cigar buffer (slots follow each other from w.cig_used on).  Works in chunks bounded by `budget_bytes`
+// of checkpoint records.
+int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const& passes, std::vector<uint32_t> const& max_errors,
+                    uint64_t budget_bytes, std::vector<RootOut>& outs) {
+    size_t const N = passes.size();
+    outs.assign(N, RootOut{kNoScore, 0, 0, 0, 0});
     if (N == 0) return FXG_OK;
     g_prof.start(w);
-    uint64_t budget_words = std::max<uint64_t>(budget_bytes, uint64_t(64) << 20) / 4;
+    // kWalkSlots checkpoint buffers: the tracebacks of a chunk read one while the score passes of the next chunks fill the others
+    uint64_t budget_words = std::max<uint64_t>(budget_bytes / Worker::kWalkSlots, uint64_t(64) << 20) / 4;
 
     std::vector<Config> cfgs(N);
     std::vector<uint64_t> words(N);
+    uint64_t total_words = 0, cigar_bound = 0;
     for (size_t i = 0; i < N; ++i) {
-        if (!cached_config(w, reqs[i].pass, true, c->smem_limit, cfgs[i]))
-            return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "traceback band of query length %u exceeds the supported size", reqs[i].pass.m);
-        uint64_t const W = uint64_t(kWidths[cfgs[i].widx]);
-        words[i] = ((uint64_t(reqs[i].pass.n) + cfgs[i].nb) * cfgs[i].G * W * 2 + 3) & ~uint64_t(3);
+        if (!cached_config(w, passes[i], c->smem_limit, cfgs[i]))
+            return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
+                        passes[i].m, passes[i].n, passes[i].dlo, passes[i].dhi);
+        uint32_t const W = uint32_t(kWidths[cfgs[i].widx]);
+        uint64_t const per_block = ck_records_per_block(int64_t(passes[i].dhi) - int64_t(passes[i].dlo) + 1, 32 * W);
+        words[i] = (uint64_t(cfgs[i].nb) * per_block * ck_record_words(W) + 3) & ~uint64_t(3);
         if (words[i] > budget_words) budget_words = words[i];
+        total_words += words[i];
+        cigar_bound += cigar_cap_for(max_errors[i]);
     }
-    std::vector<Pass> passes; std::vector<uint64_t> tbase, sbase;
-    uint64_t region_at = 0;                 // ops of the region used by earlier chunks
+    // optionally cut a large batch into chunks whose tracebacks run beside the next chunk's score passes (measured on
+    // config 2: no gain -- a traceback is one long chain of dependent steps, so the last chunk's tail stays, and the
+    // tracebacks' shared memory takes occupancy from the score passes -- hence one chunk unless memory forces more)
+    static int const n_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64), chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
+    if (N >= size_t(chunk_min) && n_chunks > 1)
+        budget_words = std::min(budget_words, std::max<uint64_t>(total_words / uint64_t(n_chunks) + 1, *std::max_element(words.begin(), words.end())));
+    // no reallocation while tracebacks are in flight: everything they write to is sized up front
+    CUDA_TRY(w.err, w.d_cigars.ensure_preserving((w.cig_used + cigar_bound) * 4, w.cig_used * 4, w.stream));
+    CUDA_TRY(w.err, w.h_wtasks.ensure(N * sizeof(Walk2Task)));
+    CUDA_TRY(w.err, w.h_wresults.ensure(N * sizeof(WalkResult)));
+    CUDA_TRY(w.err, w.d_wtasks.ensure(N * sizeof(Walk2Task)));
+    CUDA_TRY(w.err, w.d_wresults.ensure(N * sizeof(WalkResult)));
+    Walk2Task* const wt = w.h_wtasks.as<Walk2Task>();
+    WalkResult* const wr = w.h_wresults.as<WalkResult>();
+
+    g_prof.lap(w, 7);
+    std::vector<Pass> chunk; std::vector<uint64_t> ck_base;
+    std::vector<uint32_t> hit_pass;          // accepted passes in traceback order (index into passes)
+    uint64_t cig_at = w.cig_used;
+    size_t H = 0;                            // tracebacks issued so far
     size_t i = 0;
+    int k = 0;
+    bool walk_timed = false;
     while (i < N) {
-        size_t j = i; uint64_t used = 0, cig_cap_total = 0;
-        passes.clear(); tbase.clear(); sbase.clear();
+        size_t j = i; uint64_t used = 0;
+        chunk.clear(); ck_base.clear();
         while (j < N && (j == i || used + words[j] <= budget_words)) {
-            passes.push_back(reqs[j].pass); tbase.push_back(used); used += words[j];
-            sbase.push_back(cig_cap_total); cig_cap_total += cigar_cap_for(reqs[j].s_star);
+            chunk.push_back(passes[j]); ck_base.push_back(used); used += words[j];
             ++j;
         }
         size_t const M = j - i;
-        CUDA_TRY(w.err, w.d_trace.ensure(used * 4));
+        int const slot = k % Worker::kWalkSlots;
+        DevBuf& ckb = w.d_ck[slot];
+        cudaStream_t const ws = w.walk_stream[slot];
+        if (k >= Worker::kWalkSlots) CUDA_TRY(w.err, cudaEventSynchronize(w.ev_walk_done[slot]));       // the tracebacks that read this buffer
+        CUDA_TRY(w.err, ckb.ensure(used * 4));
         g_prof.lap(w, 10);
         const DpResult* res = nullptr;
-        int rc = run_passes(c, w, pool, passes, tbase.data(), &res);
+        int rc = run_passes(c, w, pool, chunk, ck_base.data(), ckb.as<uint32_t>(), &res);
         if (rc != FXG_OK) return rc;
         w.ctr.trace_bytes += used * 4;
         g_prof.start(w);
-        // walks
-        CUDA_TRY(w.err, w.h_wtasks.ensure(M * sizeof(WalkTask)));
-        CUDA_TRY(w.err, w.h_wresults.ensure(M * sizeof(WalkResult)));
-        WalkTask* wt = w.h_wtasks.as<WalkTask>();
-        for (size_t q = 0; q < M; ++q) {
-            TraceReq const& R = reqs[i + q];
-            // the sub-window ends at the alignment's end column, whose value must be the score found before
-            if (res[q].score != int32_t(R.s_star) || res[q].end_col != R.pass.n)
-                return fail(w.err, FXG_ERR_CUDA, "internal: trace pass disagrees with score pass (%d@%u vs %u@%u)",
-                            res[q].score, res[q].end_col, R.s_star, R.pass.n);
-            WalkTask& t = wt[q];
-            t.trace_base = tbase[q]; t.ref_base = R.pass.ref_base; t.query_base = R.pass.query_base;
-            t.n = R.pass.n; t.m = R.pass.m; t.group = cfgs[i + q].G; t.words = uint32_t(kWidths[cfgs[i + q].widx]);
-            t.flags = R.pass.flags; t.cigar_cap = uint32_t(cigar_cap_for(R.s_star)); t.cigar_base = sbase[q]; t.out = uint32_t(q); t.reserved = 0;
+        // ---- tracebacks of the accepted ones on their own stream, one launch per block width ----
+        size_t const H0 = H;
+        for (size_t q = 0; q < M; ++q) { outs[i + q].score = res[q].score; outs[i + q].end_col = res[q].end_col; }
+        for (int wi = 0; wi < 6; ++wi) {
+            for (size_t q = 0; q < M; ++q) {
+                if (cfgs[i + q].widx != wi || res[q].score > int32_t(max_errors[i + q])) continue;
+                Pass const& P = chunk[q];
+                Walk2Task& t = wt[H];
+                t.ck_base = ck_base[q]; t.ref_base = P.ref_base; t.query_base = P.query_base;
+                t.cigar_cap = uint32_t(cigar_cap_for(uint32_t(res[q].score))); t.cigar_base = cig_at; cig_at += t.cigar_cap;
+                t.n = P.n; t.m = P.m; t.dlo = P.dlo; t.dhi = P.dhi; t.end_col = res[q].end_col; t.score = uint32_t(res[q].score);
+                t.flags = P.flags; t.out = uint32_t(H); t.reserved = 0;
+                hit_pass.push_back(uint32_t(i + q));
+                ++H;
+            }
         }
-        CUDA_TRY(w.err, w.d_wtasks.ensure(M * sizeof(WalkTask)));
-        CUDA_TRY(w.err, w.d_wresults.ensure(M * sizeof(WalkResult)));
-        CUDA_TRY(w.err, w.d_cigars.ensure(cig_cap_total * 4));
-        CUDA_TRY(w.err, cudaMemcpyAsync(w.d_wtasks.p, wt, M * sizeof(WalkTask), cudaMemcpyHostToDevice, w.stream));
-        w.ctr.h2d_bytes += M * sizeof(WalkTask);
-        WalkLaunch WL{};
-        WL.tasks = w.d_wtasks.as<WalkTask>(); WL.n_tasks = uint32_t(M); WL.trace = w.d_trace.as<uint32_t>();
-        WL.ref_packed = c->refs.packed.as<uint32_t>(); WL.inline_packed = pool.inline_packed.as<uint32_t>();
-        WL.query_pool = pool.bytes.as<uint8_t>(); WL.cigars = w.d_cigars.as<uint32_t>();
-        WL.results = w.d_wresults.as<WalkResult>();
-        CUDA_TRY(w.err, cudaEventRecord(w.ev0, w.stream));
-        walk_kernel<<<uint32_t((M + kWalkWarps - 1) / kWalkWarps), 32 * kWalkWarps, 0, w.stream>>>(WL);
-        CUDA_TRY(w.err, cudaGetLastError());
-        CUDA_TRY(w.err, cudaEventRecord(w.ev1, w.stream));
-        w.ctr.kernel_launches++;
-        WalkResult* wr = w.h_wresults.as<WalkResult>();
-        CUDA_TRY(w.err, cudaMemcpyAsync(wr, w.d_wresults.p, M * sizeof(WalkResult), cudaMemcpyDeviceToHost, w.stream));
-        CUDA_TRY(w.err, cudaMemcpyAsync(host_cigars + region_at, w.d_cigars.p, cig_cap_total * 4, cudaMemcpyDeviceToHost, w.stream));
-        CUDA_TRY(w.err, cudaStreamSynchronize(w.stream));
-        float ms = 0;
-        CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
-        w.ctr.trace_kernel_ms += ms;
-        w.ctr.d2h_bytes += M * sizeof(WalkResult) + cig_cap_total * 4;
-        for (size_t q = 0; q < M; ++q) {
-            if (wr[q].cigar_len == 0xffffffffu) return fail(w.err, FXG_ERR_CUDA, "internal: traceback overflowed its CIGAR slot");
-            outs[i + q] = TraceOut{wr[q].begin_col, region_base + region_at + sbase[q] + wt[q].cigar_cap - wr[q].cigar_len, wr[q].cigar_len};
+        if (H > H0) {
+            CUDA_TRY(w.err, cudaMemcpyAsync(w.d_wtasks.as<Walk2Task>() + H0, wt + H0, (H - H0) * sizeof(Walk2Task), cudaMemcpyHostToDevice, ws));
+            w.ctr.h2d_bytes += (H - H0) * sizeof(Walk2Task);
+            if (!walk_timed) { CUDA_TRY(w.err, cudaEventRecord(w.ev_w0, ws)); walk_timed = true; }
+            size_t h0 = H0;
+            while (h0 < H) {
+                int const widx = cfgs[hit_pass[h0]].widx;
+                size_t h1 = h0;
+                while (h1 < H && cfgs[hit_pass[h1]].widx == widx) ++h1;
+                Walk2Launch WL{};
+                WL.tasks = w.d_wtasks.as<Walk2Task>() + h0; WL.n_tasks = uint32_t(h1 - h0); WL.ck = ckb.as<uint32_t>();
+                WL.ref_packed = c->refs.packed.as<uint32_t>(); WL.inline_packed = pool.inline_packed.as<uint32_t>();
+                WL.peq_table = pool.peq.as<uint32_t>(); WL.peq_plane_words = pool.plane_words;
+                WL.query_pool = pool.bytes.as<uint8_t>(); WL.cigars = w.d_cigars.as<uint32_t>();
+                WL.results = w.d_wresults.as<WalkResult>(); WL.two = 2;
+                CUDA_TRY(w.err, launch_walk(widx, WL, ws));
+                w.ctr.kernel_launches++;
+                h0 = h1;
+            }
+            CUDA_TRY(w.err, cudaMemcpyAsync(wr + H0, w.d_wresults.as<WalkResult>() + H0, (H - H0) * sizeof(WalkResult), cudaMemcpyDeviceToHost, ws));
+            w.ctr.d2h_bytes += (H - H0) * sizeof(WalkResult);
         }
-        region_at += cig_cap_total;
-        i = j;
+        CUDA_TRY(w.err, cudaEventRecord(w.ev_walk_done[slot], ws));
+        CUDA_TRY(w.err, cudaEventRecord(w.ev_w1[slot], ws));
+        i = j; ++k;
         g_prof.lap(w, 12);
     }
+    for (int q = 0; q < std::min(k, int(Worker::kWalkSlots)); ++q) CUDA_TRY(w.err, cudaStreamSynchronize(w.walk_stream[q]));
+    if (walk_timed) {
+        // first traceback launch to last traceback done (they run beside score passes)
+        float best = 0;
+        for (int q = 0; q < std::min(k, int(Worker::kWalkSlots)); ++q) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, w.ev_w0, w.ev_w1[q]) == cudaSuccess) best = std::max(best, ms);
+        }
+        w.ctr.trace_kernel_ms += best;
+    }
+    for (size_t h = 0; h < H; ++h) {
+        if (wr[h].cigar_len == 0xffffffffu)
+            return fail(w.err, FXG_ERR_CUDA, "internal: the traceback of an alignment disagrees with its score pass");
+        RootOut& o = outs[hit_pass[h]];
+        o.begin_col = wr[h].begin_col; o.cigar_len = wr[h].cigar_len;
+        o.cigar_offset = wt[h].cigar_base + wt[h].cigar_cap - wr[h].cigar_len;
+    }
+    w.cig_used = cig_at;
+    g_prof.lap(w, 12);
+    return FXG_OK;
+}
+
+// copies the worker's cigars (w.d_cigars[0 .. w.cig_used)) to `dst` (page-locked)
+int fetch_cigars(Worker& w, uint32_t* dst) {
+    if (!w.cig_used) return FXG_OK;
+    CUDA_TRY(w.err, cudaMemcpyAsync(dst, w.d_cigars.p, w.cig_used * 4, cudaMemcpyDeviceToHost, w.stream));
+    CUDA_TRY(w.err, cudaStreamSynchronize(w.stream));
+    w.ctr.d2h_bytes += w.cig_used * 4;
     return FXG_OK;
 }
 
@@ -605,7 +710,7 @@ void refresh_trace_budget(fxg_ctx* c) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(8) << 30;
     uint64_t held = 0;
-    for (auto const& w : c->workers) held += w->d_trace.cap;
+    for (auto const& w : c->workers) for (DevBuf const& b : w->d_ck) held += b.cap;
     c->trace_budget = std::min<uint64_t>((uint64_t(free_b) + held) / 2, uint64_t(64) << 30);
 }
 uint64_t trace_budget_bytes(fxg_ctx* c, size_t n_parts) {
@@ -706,22 +811,6 @@ inline bool score_pass_for(uint64_t ref_base, uint64_t query_base, uint32_t n, u
     return true;
 }
 
-// sub-window + band of the trace pass for an alignment with score s ending in column end_col (1-based, exclusive end)
-inline TraceReq trace_req_for(Pass const& score_pass, uint32_t s, uint32_t end_col) {
-    TraceReq r;
-    int64_t const c0 = std::max<int64_t>(0, int64_t(end_col) - int64_t(score_pass.m) - int64_t(s) - 1);
-    r.col0 = uint32_t(c0);
-    r.s_star = s;
-    r.pass = score_pass;
-    r.pass.ref_base = score_pass.ref_base + uint64_t(c0);
-    r.pass.n = end_col - uint32_t(c0);
-    int64_t const d_end = int64_t(r.pass.n) - int64_t(score_pass.m);
-    r.pass.dlo = int32_t(d_end - int64_t(s) - 1);
-    r.pass.dhi = int32_t(d_end + int64_t(s) + 1);
-    r.pass.flags = score_pass.flags & ~kFlagReverse;
-    return r;
-}
-
 // math::floating_point_error_aware_ceil, include/math.hpp:22-27
 inline uint64_t ceil_eps(double v) { return uint64_t(std::ceil(v - 0.000000001) + 0.000000001); }
 
@@ -804,8 +893,7 @@ struct PartOut {
 // what one part carries from its score phase to its traceback phase
 struct PartState {
     std::vector<Walk> walks; std::vector<Group> groups; std::vector<uint32_t> group_members;   // indices local to this part
-    std::vector<TraceReq> reqs; std::vector<uint32_t> req_walk;
-    uint64_t cigar_cap = 0;                  // ops this part needs in the job's cigar pool
+    uint64_t trace_budget = 0;               // bytes of checkpoint records the part may hold at a time
     std::chrono::steady_clock::time_point t0;
     PartOut out;
 };
@@ -858,7 +946,9 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     std::vector<uint32_t> active, next_active;
     std::vector<Pass> passes; std::vector<uint32_t> pass_walk;
     std::vector<std::pair<uint32_t, bool>> no_pass;
-    std::vector<TraceReq>& reqs = P.reqs; std::vector<uint32_t>& req_walk = P.req_walk;
+    std::vector<Pass> root_passes; std::vector<uint32_t> root_walk, root_k;   // root alignments whose CIGAR is wanted
+    std::vector<RootOut> root_outs;
+    w.cig_used = 0;
     size_t n_done = 0;
     g_prof.lap(w, 0);
 
@@ -905,6 +995,7 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
         g_prof.lap(w, 1);
         // ---- one DP pass per active walk ----
         passes.clear(); pass_walk.clear(); no_pass.clear(); next_active.clear();
+        root_passes.clear(); root_walk.clear(); root_k.clear();
         for (uint32_t wi : active) {
             Walk& wk = walks[wi];
             fxg_anchor const& A = J->anchors[wk.anchor];
@@ -924,18 +1015,19 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
             else { out.stats.n_aligned_inner++; out.stats.sum_aligned_inner += sp.length; out.stats.cells_inner += uint64_t(m) * sp.length; }
             Pass p;
             if (score_pass_for(c->refs.base[A.reference_id] + sp.offset, qbase, uint32_t(sp.length), m, uint32_t(wk.node->num_errors), flags, p)) {
-                passes.push_back(p); pass_walk.push_back(wi);
+                if (is_root && !J->cfg.without_cigar) { root_passes.push_back(p); root_walk.push_back(wi); root_k.push_back(uint32_t(wk.node->num_errors)); }
+                else { passes.push_back(p); pass_walk.push_back(wi); }
             } else {
                 no_pass.emplace_back(wi, is_root);
             }
         }
         g_prof.lap(w, 2);
         const DpResult* res = nullptr;
-        out.rc = run_passes(c, w, J->pool, passes, nullptr, &res);
+        out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
         if (out.rc != FXG_OK) return;
         w.ctr.waves++;
         g_prof.start(w);
-        auto finish = [&](uint32_t wi, bool is_root, bool exists, DpResult const* r, Pass const* p) {
+        auto finish = [&](uint32_t wi, bool is_root, bool exists, DpResult const* r, RootOut const* ro) {
             Walk& wk = walks[wi];
             if (is_root) {
                 // verified_intervals.insert, verification.cpp:106-109 / :40-41 (also when the root alignment failed)
@@ -943,7 +1035,10 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
                 if (exists) {
                     wk.hit = true; wk.num_errors = uint32_t(r->score);
                     if (J->cfg.without_cigar) wk.start_in_reference = wk.root_span.offset + (wk.root_span.length - r->end_col);
-                    else { reqs.push_back(trace_req_for(*p, uint32_t(r->score), r->end_col)); req_walk.push_back(wi); P.cigar_cap += cigar_cap_for(uint32_t(r->score)); }
+                    else {
+                        wk.start_in_reference = wk.root_span.offset + ro->begin_col;               // alignment.cpp:175
+                        wk.cigar_offset = ro->cigar_offset; wk.cigar_len = ro->cigar_len;          // relative to this part's region for now
+                    }
                 }
                 wk.state = W_DONE; ++n_done;
             } else if (exists) {
@@ -958,7 +1053,15 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
             Walk const& wk = walks[pass_walk[q]];
             bool const is_root = wk.node->parent_id == FXG_NULL_ID;
             bool const exists = res[q].score <= int32_t(wk.node->num_errors);
-            finish(pass_walk[q], is_root, exists, &res[q], &passes[q]);
+            finish(pass_walk[q], is_root, exists, &res[q], nullptr);
+        }
+        // root alignments with CIGAR: score pass with checkpoints, then the traceback of the accepted ones
+        // (after the loop above: `res` lives in the worker's staging memory, which the next passes reuse)
+        out.rc = run_root_passes(c, w, J->pool, root_passes, root_k, P.trace_budget, root_outs);
+        if (out.rc != FXG_OK) return;
+        for (size_t q = 0; q < root_passes.size(); ++q) {
+            DpResult const r{root_outs[q].score, root_outs[q].end_col};
+            finish(root_walk[q], true, r.score <= int32_t(root_k[q]), &r, &root_outs[q]);
         }
         for (auto const& np : no_pass) finish(np.first, np.second, false, nullptr, nullptr);
         if (!ivopt) {
@@ -977,17 +1080,15 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     }
 }
 
-// tracebacks for the accepted roots of a part, cigars straight into the job's pool, then the part's alignments
-void verify_part_trace(fxg_ctx* c, Worker& w, fxg_job* J, uint64_t trace_budget, uint32_t* host_cigars, uint64_t region_base, PartState& P) {
+// the part's cigars go straight from the device into its region of the job's pool; then the part's alignments
+void verify_part_finish(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t* host_cigars, uint64_t region_base, PartState& P) {
+    (void)c;
     PartOut& out = P.out;
-    std::vector<TraceOut> touts;
-    out.rc = run_traces(c, w, J->pool, P.reqs, trace_budget, host_cigars, region_base, touts);
+    g_prof.start(w);
+    out.rc = fetch_cigars(w, host_cigars);
+    g_prof.lap(w, 15);
     if (out.rc != FXG_OK) return;
-    for (size_t q = 0; q < P.reqs.size(); ++q) {
-        Walk& wk = P.walks[P.req_walk[q]];
-        wk.start_in_reference = wk.root_span.offset + P.reqs[q].col0 + touts[q].begin_col;
-        wk.cigar_offset = touts[q].cigar_offset; wk.cigar_len = touts[q].cigar_len;
-    }
+    for (Walk& wk : P.walks) if (wk.hit && wk.cigar_len) wk.cigar_offset += region_base;
     // ---- emit in anchor order (= insertion order of the reference's single-thread run) ----
     g_prof.start(w);
     for (Walk const& wk : P.walks) {
@@ -1065,6 +1166,11 @@ int fxg_create(int device, fxg_ctx** out) {
         ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess &&
              cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreate(&w->ev_w0) == cudaSuccess;
+        for (int q = 0; ok && q < Worker::kWalkSlots; ++q)
+            ok = cudaStreamCreateWithFlags(&w->walk_stream[q], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&w->ev_walk_done[q], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreate(&w->ev_w1[q]) == cudaSuccess;
         for (int q = 0; ok && q < Worker::kSide; ++q)
             ok = cudaStreamCreateWithFlags(&w->side[q], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&w->ev_join[q], cudaEventDisableTiming) == cudaSuccess;
@@ -1180,8 +1286,8 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
         size_t const N = b->tasks.size();
         b->results.assign(N, fxg_align_result{});
         b->cigars_len = 0;
-        std::vector<Pass> passes; passes.reserve(N);
-        std::vector<uint32_t> owner; owner.reserve(N);
+        std::vector<Pass> passes, root_passes; passes.reserve(N);
+        std::vector<uint32_t> owner, root_owner, root_k; owner.reserve(N);
         for (size_t i = 0; i < N; ++i) {
             fxg_align_task const& t = b->tasks[i];
             b->results[i].orientation = t.orientation;
@@ -1195,13 +1301,13 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
                 else if (t.mode == FXG_MODE_NO_CIGAR) b->results[i].start_in_reference = t.reference_span_offset;
                 continue;
             }
-            if (score_pass_for(ref_base, t.query_offset, t.ref_len, t.query_len, t.max_errors, flags, p)) { passes.push_back(p); owner.push_back(uint32_t(i)); }
+            if (!score_pass_for(ref_base, t.query_offset, t.ref_len, t.query_len, t.max_errors, flags, p)) continue;
+            if (t.mode == FXG_MODE_CIGAR) { root_passes.push_back(p); root_owner.push_back(uint32_t(i)); root_k.push_back(t.max_errors); }
+            else { passes.push_back(p); owner.push_back(uint32_t(i)); }
         }
         const DpResult* res = nullptr;
-        rc = run_passes(c, w, b->pool, passes, nullptr, &res);
-        std::vector<TraceReq> reqs; std::vector<uint32_t> req_owner;
+        rc = run_passes(c, w, b->pool, passes, nullptr, nullptr, &res);
         if (rc == FXG_OK) {
-            uint64_t cap = 0;
             for (size_t q = 0; q < passes.size(); ++q) {
                 fxg_align_task const& t = b->tasks[owner[q]];
                 fxg_align_result& r = b->results[owner[q]];
@@ -1209,20 +1315,25 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
                 r.exists = 1;
                 if (t.mode == FXG_MODE_EXISTS) continue;
                 r.num_errors = uint32_t(res[q].score);
-                if (t.mode == FXG_MODE_NO_CIGAR) r.start_in_reference = t.reference_span_offset + (t.ref_len - res[q].end_col);   // alignment.cpp:135-139
-                else { reqs.push_back(trace_req_for(passes[q], uint32_t(res[q].score), res[q].end_col)); req_owner.push_back(owner[q]); cap += cigar_cap_for(uint32_t(res[q].score)); }
+                r.start_in_reference = t.reference_span_offset + (t.ref_len - res[q].end_col);   // alignment.cpp:135-139
             }
-            cudaError_t const e = b->cigars.ensure(std::max<uint64_t>(cap, 1) * 4);
-            if (e != cudaSuccess) rc = fail(w.err, FXG_ERR_CUDA, "cigar pool allocation: %s", cudaGetErrorString(e));
-            std::vector<TraceOut> touts;
-            if (rc == FXG_OK) rc = run_traces(c, w, b->pool, reqs, trace_budget_bytes(c, 1), b->cigars.as<uint32_t>(), 0, touts);
+            w.cig_used = 0;
+            std::vector<RootOut> outs;
+            rc = run_root_passes(c, w, b->pool, root_passes, root_k, trace_budget_bytes(c, 1), outs);
             if (rc == FXG_OK) {
-                b->cigars_len = size_t(cap);
-                for (size_t q = 0; q < reqs.size(); ++q) {
-                    fxg_align_task const& t = b->tasks[req_owner[q]];
-                    fxg_align_result& r = b->results[req_owner[q]];
-                    r.start_in_reference = t.reference_span_offset + reqs[q].col0 + touts[q].begin_col;   // alignment.cpp:175
-                    r.cigar_offset = touts[q].cigar_offset; r.cigar_len = touts[q].cigar_len;
+                cudaError_t const e = b->cigars.ensure(std::max<uint64_t>(w.cig_used, 1) * 4);
+                if (e != cudaSuccess) rc = fail(w.err, FXG_ERR_CUDA, "cigar pool allocation: %s", cudaGetErrorString(e));
+            }
+            if (rc == FXG_OK) rc = fetch_cigars(w, b->cigars.as<uint32_t>());
+            if (rc == FXG_OK) {
+                b->cigars_len = size_t(w.cig_used);
+                for (size_t q = 0; q < root_passes.size(); ++q) {
+                    if (outs[q].score > int32_t(root_k[q])) continue;
+                    fxg_align_task const& t = b->tasks[root_owner[q]];
+                    fxg_align_result& r = b->results[root_owner[q]];
+                    r.exists = 1; r.num_errors = uint32_t(outs[q].score);
+                    r.start_in_reference = t.reference_span_offset + outs[q].begin_col;   // alignment.cpp:175
+                    r.cigar_offset = outs[q].cigar_offset; r.cigar_len = outs[q].cigar_len;
                 }
             }
         }
@@ -1348,11 +1459,14 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
     auto run_part = [&](size_t p) {
         Worker& w = *c->workers[p];
         PartState& P = parts[p];
+        P.trace_budget = budget;
         verify_part_score(c, w, J, cut[p], cut[p + 1], P);
-        plan.arrive_and_wait(p, P.out.rc == FXG_OK ? P.cigar_cap : 0);       // every part arrives, also a failed one
+        g_prof.start(w);
+        plan.arrive_and_wait(p, P.out.rc == FXG_OK ? w.cig_used : 0);        // every part arrives, also a failed one
+        g_prof.lap(w, 14);
         if (P.out.rc != FXG_OK) return;
         if (plan.failed) { w.err = plan.err; P.out.rc = FXG_ERR_CUDA; return; }
-        verify_part_trace(c, w, J, budget, J->cigars.as<uint32_t>() + plan.bases[p], plan.bases[p], P);
+        verify_part_finish(c, w, J, J->cigars.as<uint32_t>() + plan.bases[p], plan.bases[p], P);
     };
     {
         RunTimer run_timer(c);
