@@ -118,7 +118,7 @@ struct Worker {
     static constexpr int kSide = 3;      // the launches of one wave are independent: the smaller ones run beside the largest
     cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
     // tracebacks are long chains of dependent steps: the root alignments of a wave are cut into chunks, each chunk's
     // tracebacks run on a stream of their own beside the score passes (and tracebacks) of the other chunks
     static constexpr int kWalkSlots = 4;
@@ -135,6 +135,8 @@ struct Worker {
     void release() {
         for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars}) b->release();
         if (ev_w0) { cudaEventDestroy(ev_w0); ev_w0 = nullptr; }
+        if (ev_b0) { cudaEventDestroy(ev_b0); ev_b0 = nullptr; }
+        if (ev_b1) { cudaEventDestroy(ev_b1); ev_b1 = nullptr; }
         for (int q = 0; q < kWalkSlots; ++q) {
             d_ck[q].release();
             if (ev_walk_done[q]) cudaEventDestroy(ev_walk_done[q]);
@@ -262,6 +264,7 @@ int fail(std::string& err, int code, const char* fmt, ...) {
 void add_counters(fxg_counters& a, fxg_counters const& b) {
     a.kernel_launches += b.kernel_launches; a.dp_tasks += b.dp_tasks; a.dp_word_steps += b.dp_word_steps;
     a.dp_cells_full += b.dp_cells_full; a.trace_bytes += b.trace_bytes; a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
+    a.root_launch_ms += b.root_launch_ms; a.root_launch_word_steps += b.root_launch_word_steps;
     a.trace_word_steps += b.trace_word_steps; a.dp_kernel_ms += b.dp_kernel_ms; a.trace_kernel_ms += b.trace_kernel_ms; a.waves += b.waves; a.run_ms += b.run_ms;
 }
 
@@ -475,7 +478,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     g_prof.lap(w, 5);
 
     CUDA_TRY(w.err, cudaEventRecord(w.ev0, w.stream));
-    struct Launch { DpLaunch L; int widx; uint32_t grid; size_t smem; uint64_t work; };
+    struct Launch { DpLaunch L; int widx; uint32_t grid; size_t smem; uint64_t work, word_steps; };
     std::vector<Launch> launches;
     size_t i = 0;
     while (i < N) {
@@ -486,13 +489,14 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
         uint32_t const tpw = 32 / G;
         size_t j = i;
         uint32_t max_words = 0;
-        uint64_t work = 0;
+        uint64_t work = 0, ws = 0;
         while (j < N) {
             uint32_t const idx = uint32_t(w.keys[j]);
             Config const& cj = w.cfgs[idx];
             if (cj.widx != widx || cj.G != G) break;
             max_words = std::max(max_words, cj.nb * W);
             work += (uint64_t(passes[idx].n) + cj.nb) * (10 * W + 6);
+            ws += cj.word_steps;
             ++j;
         }
         Launch X{};
@@ -512,7 +516,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
         X.smem = size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
         if (X.smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", X.smem);
         X.grid = uint32_t((L.n_tasks + tpw - 1) / tpw);
-        X.widx = widx; X.work = work / tpw;
+        X.widx = widx; X.work = work / tpw; X.word_steps = ws;
         launches.push_back(X);
         i = j;
     }
@@ -526,7 +530,9 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     for (size_t q = 0; q < launches.size(); ++q) {
         Launch const& X = launches[q];
         cudaStream_t const st = q == 0 ? w.stream : w.side[(q - 1) % Worker::kSide];
+        if (q == 0 && trace) CUDA_TRY(w.err, cudaEventRecord(w.ev_b0, w.stream));
         CUDA_TRY(w.err, launch_dp(X.widx, trace, X.L, X.grid, X.smem, st));
+        if (q == 0 && trace) CUDA_TRY(w.err, cudaEventRecord(w.ev_b1, w.stream));
         w.ctr.kernel_launches++;
     }
     if (fan_out) {
@@ -543,6 +549,11 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     float ms = 0;
     CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
     w.ctr.dp_kernel_ms += ms;
+    if (trace) {
+        // the largest launch of a root wave is the engine's dominant launch: timed on its own for the roofline
+        CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev_b0, w.ev_b1));
+        w.ctr.root_launch_ms += ms; w.ctr.root_launch_word_steps += launches[0].word_steps;
+    }
     g_prof.lap(w, trace ? 11 : 8);
     *results = w.h_results.as<DpResult>();
     for (size_t q = 0; q < N; ++q)
@@ -650,7 +661,11 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
             CUDA_TRY(w.err, cudaMemcpyAsync(w.d_wtasks.as<Walk2Task>() + H0, wt + H0, (H - H0) * sizeof(Walk2Task), cudaMemcpyHostToDevice, ws));
             w.ctr.h2d_bytes += (H - H0) * sizeof(Walk2Task);
             if (!walk_timed) { CUDA_TRY(w.err, cudaEventRecord(w.ev_w0, ws)); walk_timed = true; }
+            // every traceback is one long chain of dependent steps, so launches of different block widths must not queue
+            // behind each other: the first runs on the chunk's stream, the others fork onto side streams and join it again
+            CUDA_TRY(w.err, cudaEventRecord(w.ev_fork, ws));
             size_t h0 = H0;
+            int n_launch = 0;
             while (h0 < H) {
                 int const widx = cfgs[hit_pass[h0]].widx;
                 size_t h1 = h0;
@@ -661,8 +676,19 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
                 WL.peq_table = pool.peq.as<uint32_t>(); WL.peq_plane_words = pool.plane_words;
                 WL.query_pool = pool.bytes.as<uint8_t>(); WL.cigars = w.d_cigars.as<uint32_t>();
                 WL.results = w.d_wresults.as<WalkResult>(); WL.two = 2;
-                CUDA_TRY(w.err, launch_walk(widx, WL, ws));
+                cudaStream_t st = ws;
+                if (n_launch > 0) {
+                    st = w.side[(n_launch - 1) % Worker::kSide];
+                    CUDA_TRY(w.err, cudaStreamWaitEvent(st, w.ev_fork, 0));
+                }
+                CUDA_TRY(w.err, launch_walk(widx, WL, st));
+                if (n_launch > 0) {
+                    int const sq = (n_launch - 1) % Worker::kSide;
+                    CUDA_TRY(w.err, cudaEventRecord(w.ev_join[sq], st));
+                    CUDA_TRY(w.err, cudaStreamWaitEvent(ws, w.ev_join[sq], 0));
+                }
                 w.ctr.kernel_launches++;
+                ++n_launch;
                 h0 = h1;
             }
             CUDA_TRY(w.err, cudaMemcpyAsync(wr + H0, w.d_wresults.as<WalkResult>() + H0, (H - H0) * sizeof(WalkResult), cudaMemcpyDeviceToHost, ws));
@@ -1166,7 +1192,7 @@ int fxg_create(int device, fxg_ctx** out) {
         ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess &&
              cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreate(&w->ev_w0) == cudaSuccess;
+        ok = ok && cudaEventCreate(&w->ev_w0) == cudaSuccess && cudaEventCreate(&w->ev_b0) == cudaSuccess && cudaEventCreate(&w->ev_b1) == cudaSuccess;
         for (int q = 0; ok && q < Worker::kWalkSlots; ++q)
             ok = cudaStreamCreateWithFlags(&w->walk_stream[q], cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreateWithFlags(&w->ev_walk_done[q], cudaEventDisableTiming) == cudaSuccess &&

@@ -133,13 +133,15 @@ typedef struct {
     uint64_t dp_tasks;               /* bit-vector DP tasks executed (score passes + trace passes) */
     uint64_t dp_word_steps;          /* 32-cell Myers word-steps issued by the score passes (band-limited) */
     uint64_t dp_cells_full;          /* sum of m' * n' of those tasks (full-matrix convention) */
-    uint64_t trace_bytes;            /* bytes of trace bit-planes written by the traceback pass */
+    uint64_t trace_bytes;            /* bytes of checkpoint records the root score passes may write for the traceback */
     uint64_t h2d_bytes, d2h_bytes;
     double dp_kernel_ms;             /* CUDA-event time of the DP kernels on the context's stream */
-    double trace_kernel_ms;          /* CUDA-event time of trace-store + walk kernels */
+    double trace_kernel_ms;          /* CUDA-event time of the traceback kernels */
     uint64_t waves;                  /* host scheduling rounds of fxg_verify_* */
     double run_ms;                   /* CUDA-event time from the first to the last device operation of *_run calls */
-    uint64_t trace_word_steps;       /* word-steps issued by the trace passes (their time is in trace_kernel_ms) */
+    uint64_t trace_word_steps;       /* unused (the traceback recomputes tiles from checkpoints; no trace passes) */
+    double root_launch_ms;           /* CUDA-event time of the largest launch of every root wave (the dominant launch) ... */
+    uint64_t root_launch_word_steps; /* ... and the word-steps those launches issued */
 } fxg_counters;
 
 /* ---- life cycle ---- */
