@@ -194,6 +194,7 @@ struct fxg_ctx {
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
     DevBuf d_tmp;
     uint64_t trace_budget = 0;
+    int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
     std::vector<Pool> spare_pools;       // device buffers of freed batches / jobs, reused by the next stage call
     std::vector<PinnedBuf> spare_pinned; // page-locked cigar pools of freed batches / jobs (cudaHostAlloc costs milliseconds)
     std::mutex mu;
@@ -602,7 +603,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
     // optionally cut a large batch into chunks whose tracebacks run beside the next chunk's score passes (measured on
     // config 2: no gain -- a traceback is one long chain of dependent steps, so the last chunk's tail stays, and the
     // tracebacks' shared memory takes occupancy from the score passes -- hence one chunk unless memory forces more)
-    static int const n_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64), chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
+    int const n_chunks = c->root_chunks, chunk_min = c->root_chunk_min;
     if (N >= size_t(chunk_min) && n_chunks > 1)
         budget_words = std::min(budget_words, std::max<uint64_t>(total_words / uint64_t(n_chunks) + 1, *std::max_element(words.begin(), words.end())));
     // no reallocation while tracebacks are in flight: everything they write to is sized up front
@@ -1184,6 +1185,8 @@ int fxg_create(int device, fxg_ctx** out) {
     c->smem_limit = prop.sharedMemPerBlockOptin;
     bool ok = cudaEventCreate(&c->ev_run0) == cudaSuccess && cudaEventCreate(&c->ev_run1) == cudaSuccess &&
               set_all_smem_attrs(c->smem_limit) == cudaSuccess;
+    c->root_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64);
+    c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
     int const nw = default_workers();
     for (int i = 0; ok && i < nw; ++i) {
         std::unique_ptr<Worker> w(new (std::nothrow) Worker());

@@ -273,3 +273,119 @@ def test_staged_run_is_repeatable(ctx, gpu):
     assert np.array_equal(a1[0], a2[0]) and np.array_equal(a1[1], a2[1]) and len(a1[0]) > 0
     c = ctx.counters()
     assert c["kernel_launches"] > 0 and c["dp_word_steps"] > 0
+
+
+# ----------------------------------------------------------------------------- larger shapes, chunking, properties
+
+def _thin_anchors(batch, keep_every: int):
+    """Keeps every `keep_every`-th anchor of each orientation (root alignments of long reads are expensive for the CPU checker)."""
+    bb = BatchBuilder()
+    for R in batch.reads:
+        no, ni, nl = int(R["node_offset"]), int(R["num_inner"]), int(R["num_leaves"])
+        qo, ql = int(R["query_offset"]), int(R["query_len"])
+        ao, af, ar = int(R["anchor_offset"]), int(R["num_anchors_forward"]), int(R["num_anchors_reverse"])
+        bb.add(batch.forward_pool[qo:qo + ql], batch.reverse_pool[qo:qo + ql], batch.nodes[no:no + ni], batch.nodes[no + ni:no + ni + nl],
+               batch.anchors[ao:ao + af][::keep_every], batch.anchors[ao + af:ao + af + ar][::keep_every])
+    return bb.build()
+
+
+@pytest.mark.parametrize("length,err,seed,keep", [(15000, 0.08, 11, 40), (20000, 0.10, 12, 60)])
+def test_long_reads_config3_config4_shapes(ctx, gpu, length, err, seed, keep):
+    """15 kbp at 8 % and 20 kbp at 10 % (configs 3 and 4): wide blocks (W = 8, 16), bands of thousands of diagonals,
+    tracebacks over hundreds of checkpoint tiles; the bit-vector CPU port is the checker at this size."""
+    from oracle import cpu_baseline
+    ref = synthetic.plant_repeats(synthetic.random_reference(1_200_000, 20240002), 33, families=4, unit=(500, 3000), copies=(3, 6))
+    refs = [ref]
+    ctx.set_references(refs)
+    batch = _thin_anchors(synthetic.make_batch(refs, 2, length, err, seed, gpu.pex_build, seed_errors=2, decoy_fraction=0.1), keep)
+    for cfg in (VerifyConfig(), VerifyConfig(without_cigar=True), VerifyConfig(verification_kind=abi.KIND_DIRECT_FULL)):
+        job = ctx.verify_reads(batch, cfg)
+        al, cg = job.alignments()
+        wal, wcg, wstats = cpu_baseline.verify_reads(refs, batch, cfg, threads=8)
+        assert alignment_records(al, cg) == alignment_records(wal, wcg)
+        assert job.stats() == wstats
+        assert len(al) > 0
+        job.free()
+
+
+def test_checkpoint_chunks_and_small_budget(gpu, oracle, monkeypatch):
+    """Root alignments cut into several chunks (checkpoint buffers reused while tracebacks are in flight) give the same answer."""
+    monkeypatch.setenv("FXG_ROOT_CHUNKS", "7")
+    monkeypatch.setenv("FXG_ROOT_CHUNK_MIN", "1")
+    monkeypatch.setenv("FXG_WORKERS", "2")
+    c2 = gpu.Context(0)
+    try:
+        refs = [synthetic.random_reference(150_000, 51)]
+        c2.set_references(refs)
+        batch = synthetic.make_batch(refs, 30, 1100, 0.06, 61, gpu.pex_build, seed_errors=1, decoy_fraction=0.3)
+        for cfg in (VerifyConfig(), VerifyConfig(interval_optimization=True), VerifyConfig(verification_kind=abi.KIND_DIRECT_FULL)):
+            job = c2.verify_reads(batch, cfg)
+            al, cg = job.alignments()
+            want, want_stats = oracle_verify_batch(oracle, refs, batch, cfg)
+            assert alignment_records(al, cg) == want and job.stats() == want_stats and len(want) > 10
+            job.free()
+    finally:
+        c2.close()
+
+
+def _check_alignment_against_sequences(a, cigar_pool, batch, refs):
+    """Size-independent property: the CIGAR, applied to the read and the reference, consumes the whole read, says '='
+    exactly where the bases agree and 'X' where they differ, and its I/D/X total is the reported number of errors."""
+    R = batch.reads[int(a["read_index"])]
+    qo, ql = int(R["query_offset"]), int(R["query_len"])
+    pool = batch.reverse_pool if int(a["orientation"]) else batch.forward_pool
+    q = pool[qo:qo + ql]
+    ops = cigar_pool[int(a["cigar_offset"]): int(a["cigar_offset"]) + int(a["cigar_len"])]
+    lens, codes = (ops >> 4).astype(np.int64), (ops & 15).astype(np.int64)
+    assert set(np.unique(codes)) <= {1, 2, 7, 8} and (lens > 0).all()
+    assert (codes[1:] != codes[:-1]).all(), "adjacent runs of the same operation"
+    per = np.repeat(codes, lens)
+    q_use, r_use = per != 2, per != 1
+    assert int(q_use.sum()) == ql
+    qi = np.cumsum(q_use) - 1
+    ri = int(a["start_in_reference"]) + np.cumsum(r_use) - 1
+    ref = refs[int(a["reference_id"])]
+    assert ri[-1] < len(ref) or not r_use[-1]
+    both = q_use & r_use
+    same = q[qi[both]] == ref[ri[both]]
+    assert np.array_equal(same, per[both] == 7)
+    assert int((per != 7).sum()) == int(a["num_errors"])
+
+
+def test_bench_workload_properties_and_sample_parity(gpu):
+    """BASELINE config 2 at full size (10 Mbp reference, 1 000 reads x 5 kbp at 5 %): every 7th alignment is checked against
+    the sequences, the counts against the simulation's ground truth, and the first reads bit for bit against the CPU port."""
+    import bench
+    from oracle import cpu_baseline
+    refs, batch = bench.make_workload("config2", 0, gpu.pex_build)
+    c2 = gpu.Context(0)
+    try:
+        c2.set_references(refs)
+        cfg = VerifyConfig()
+        job = c2.stage_verify(batch, cfg)
+        al, cg = job.run().alignments()
+        k = int(np.ceil(5000 * 0.05)) + 14
+        assert len(al) > 10 * len(batch) and (al["num_errors"] <= k).all()
+        # every read is found on the strand and near the position it was simulated from
+        for ri, (rid, start, on_reverse) in enumerate(batch.meta["truth"][:200]):
+            mine = al[al["read_index"] == ri]
+            assert len(mine) and (mine["orientation"] == int(on_reverse)).any()
+            assert (np.abs(mine["start_in_reference"].astype(np.int64) - start) <= 600).any()
+        for a in al[::7]:
+            _check_alignment_against_sequences(a, cg, batch, refs)
+        st = job.stats()
+        assert st["n_aligned_root"] == len(al) + int(((al["num_errors"] < 0)).sum())     # every root alignment of this workload succeeds
+        # a second run of the staged job is bit-identical
+        al2, cg2 = job.run().alignments()
+        assert np.array_equal(al[["start_in_reference", "num_errors", "read_index", "orientation", "cigar_len"]],
+                              al2[["start_in_reference", "num_errors", "read_index", "orientation", "cigar_len"]])
+        job.free()
+        # bit-for-bit against the CPU port on the first reads
+        sample = batch.slice(0, 12)
+        job = c2.verify_reads(sample, cfg)
+        sal, scg = job.alignments()
+        wal, wcg, wstats = cpu_baseline.verify_reads(refs, sample, cfg, threads=8)
+        assert alignment_records(sal, scg) == alignment_records(wal, wcg) and job.stats() == wstats
+        job.free()
+    finally:
+        c2.close()
