@@ -191,7 +191,7 @@ struct fxg_ctx {
     int num_sms = 0;
     size_t smem_limit = 0;
     std::vector<std::unique_ptr<Worker>> workers;
-    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;
+    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr, ev_staged = nullptr;
     DevBuf d_tmp;
     uint64_t trace_budget = 0;
     int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
@@ -233,9 +233,14 @@ struct Group { uint32_t first, count; };   // members are consecutive entries of
 
 struct fxg_job {
     fxg_verify_config cfg{};
+    // the batch: either the job's own copies (fxg_verify_stage) or the caller's arrays, borrowed for the duration of
+    // the one call that uses them (fxg_verify_reads)
     std::vector<fxg_read> reads;
     std::vector<fxg_pex_node> nodes;
     std::vector<fxg_anchor> anchors;
+    const fxg_read* reads_p = nullptr; const fxg_pex_node* nodes_p = nullptr; const fxg_anchor* anchors_p = nullptr;
+    size_t n_reads = 0, n_nodes = 0, n_anchors = 0;
+    bool borrowed = false;
     uint64_t pool_len = 0;
     Pool pool;                           // forward pool followed by the reverse-complement pool
     std::vector<uint32_t> read_walk_begin;   // per read (+1 sentinel): index of its first walk (= anchor) in job order
@@ -804,23 +809,24 @@ int upload_packed(fxg_ctx* c, const uint8_t* ranks, uint64_t len, DevBuf& dst, u
     return FXG_OK;
 }
 
-// uploads up to two byte ranges back to back (forward / reverse pools) and builds the Peq planes
-int stage_pool(fxg_ctx* c, Pool& pool, const uint8_t* a, size_t a_len, const uint8_t* b, size_t b_len) {
+// uploads up to two byte ranges back to back (forward / reverse pools) and builds the Peq planes; errors and
+// accounting go to the caller's objects (fxg_verify_reads runs this beside the workers)
+int stage_pool(fxg_ctx* c, Pool& pool, const uint8_t* a, size_t a_len, const uint8_t* b, size_t b_len, std::string& err, fxg_counters& ctr) {
     Worker& w = *c->workers[0];
     pool.len = a_len + b_len;
     pool.plane_words = (pool.len + 31) / 32 + kPeqFrontPadWords + kPeqBackPadWords;
-    CUDA_TRY(c->err, pool.bytes.ensure(pool.len + 64));
-    CUDA_TRY(c->err, pool.peq.ensure(pool.plane_words * kNumSymbols * 4));
-    if (a_len) CUDA_TRY(c->err, cudaMemcpyAsync(pool.bytes.p, a, a_len, cudaMemcpyHostToDevice, w.stream));
-    if (b_len) CUDA_TRY(c->err, cudaMemcpyAsync(pool.bytes.as<uint8_t>() + a_len, b, b_len, cudaMemcpyHostToDevice, w.stream));
-    c->ctr.h2d_bytes += pool.len;
-    CUDA_TRY(c->err, cudaMemsetAsync(pool.peq.p, 0, pool.plane_words * kNumSymbols * 4, w.stream));
+    CUDA_TRY(err, pool.bytes.ensure(pool.len + 64));
+    CUDA_TRY(err, pool.peq.ensure(pool.plane_words * kNumSymbols * 4));
+    if (a_len) CUDA_TRY(err, cudaMemcpyAsync(pool.bytes.p, a, a_len, cudaMemcpyHostToDevice, w.stream));
+    if (b_len) CUDA_TRY(err, cudaMemcpyAsync(pool.bytes.as<uint8_t>() + a_len, b, b_len, cudaMemcpyHostToDevice, w.stream));
+    ctr.h2d_bytes += pool.len;
+    CUDA_TRY(err, cudaMemsetAsync(pool.peq.p, 0, pool.plane_words * kNumSymbols * 4, w.stream));
     if (pool.len) {
         uint64_t const n_words = (pool.len + 31) / 32;
         uint32_t const grid = uint32_t(std::min<uint64_t>((n_words + 7) / 8, uint64_t(c->num_sms) * 16));
         build_peq_kernel<<<grid, 256, 0, w.stream>>>(pool.bytes.as<uint8_t>(), pool.len, pool.peq.as<uint32_t>(), pool.plane_words);
-        CUDA_TRY(c->err, cudaGetLastError());
-        c->ctr.kernel_launches++;
+        CUDA_TRY(err, cudaGetLastError());
+        ctr.kernel_launches++;
     }
     return FXG_OK;
 }
@@ -875,8 +881,8 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
     std::vector<std::vector<uint32_t>> tmp_groups;
     std::vector<int64_t> ref_to_group;
     for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
-        fxg_read const& R = J->reads[ri];
-        const fxg_pex_node* inner = J->nodes.data() + R.node_offset;
+        fxg_read const& R = J->reads_p[ri];
+        const fxg_pex_node* inner = J->nodes_p + R.node_offset;
         const fxg_pex_node* leaves = inner + R.num_inner;
         fxg_pex_node const& root = R.num_inner ? inner[0] : leaves[0];
         for (int orient = 0; orient < 2; ++orient) {
@@ -885,7 +891,7 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
             if (ivopt) { tmp_groups.clear(); ref_to_group.assign(c->refs.len.size(), -1); }
             uint32_t const group_base = uint32_t(groups.size());
             for (uint32_t q = 0; q < na; ++q) {
-                fxg_anchor const& A = J->anchors[a0 + q];
+                fxg_anchor const& A = J->anchors_p[a0 + q];
                 fxg_pex_node const& leaf = leaves[A.pex_leaf_index];
                 Walk wk{};
                 wk.read = ri; wk.anchor = a0 + q; wk.orient = uint8_t(orient); wk.state = W_WAITING;
@@ -909,6 +915,41 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
             }
         }
     }
+}
+
+// fxg_verify_reads uploads the query pools while the parts already prepare their first wave on the host: a part waits
+// here before its first launch
+struct StageGate {
+    std::mutex mu; std::condition_variable cv;
+    bool ready = false; int rc = FXG_OK; std::string err;
+    void open(int code, std::string const& message) {
+        { std::lock_guard<std::mutex> lock(mu); ready = true; rc = code; err = message; }
+        cv.notify_all();
+    }
+    int wait() { std::unique_lock<std::mutex> lock(mu); cv.wait(lock, [&] { return ready; }); return rc; }
+};
+
+int validate_reads(fxg_ctx* c, std::string& err, const fxg_read* reads, size_t lo, size_t hi, size_t pool_len,
+                   const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors) {
+    for (size_t i = lo; i < hi; ++i) {
+        fxg_read const& R = reads[i];
+        if (R.query_offset + R.query_len > pool_len) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: query outside the pool", i);
+        if (R.query_len > FXG_MAX_QUERY_LENGTH) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: longer than %d", i, FXG_MAX_QUERY_LENGTH);
+        if (R.node_offset + R.num_inner + R.num_leaves > n_nodes || R.num_leaves == 0) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: bad node range", i);
+        if (R.anchor_offset + R.num_anchors_forward + R.num_anchors_reverse > n_anchors) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: bad anchor range", i);
+        const fxg_pex_node* nd = nodes + R.node_offset;
+        for (uint32_t q = 0; q < R.num_inner + R.num_leaves; ++q) {
+            if (nd[q].query_index_to < nd[q].query_index_from || nd[q].query_index_to >= R.query_len) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: node %u outside the query", i, q);
+            if (nd[q].parent_id != FXG_NULL_ID && nd[q].parent_id >= R.num_inner) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: node %u has a bad parent", i, q);
+        }
+        const fxg_anchor* an = anchors + R.anchor_offset;
+        for (uint32_t q = 0; q < R.num_anchors_forward + R.num_anchors_reverse; ++q) {
+            if (an[q].pex_leaf_index >= R.num_leaves) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: anchor %u names leaf %llu", i, q, (unsigned long long)an[q].pex_leaf_index);
+            if (an[q].reference_id >= c->refs.len.size()) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: anchor %u names reference %llu", i, q, (unsigned long long)an[q].reference_id);
+            if (an[q].reference_position >= c->refs.len[an[q].reference_id]) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: anchor %u outside its reference", i, q);
+        }
+    }
+    return FXG_OK;
 }
 
 struct PartOut {
@@ -939,7 +980,7 @@ uint8_t node_dist(const fxg_pex_node* inner, std::vector<uint8_t>& memo, uint64_
 // With it, the sequential semantics of the verified-interval sets are preserved exactly: a walk starts only when no
 // earlier walk of its (read, orientation, reference) group that could still verify its root window is
 // unresolved, and it is skipped if an EARLIER walk inserted a window containing its trimmed root window.
-void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, PartState& P) {
+void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, PartState& P, StageGate* gate) {
     cudaSetDevice(c->device);
     P.t0 = std::chrono::steady_clock::now();
     PartOut& out = P.out;
@@ -959,8 +1000,8 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
         uint32_t cur_read = UINT32_MAX; uint8_t max_dist = 0;
         for (uint32_t i = 0; i < n_walks; ++i) {
             Walk const& wk = walks[i];
-            fxg_read const& R = J->reads[wk.read];
-            const fxg_pex_node* inner = J->nodes.data() + R.node_offset;
+            fxg_read const& R = J->reads_p[wk.read];
+            const fxg_pex_node* inner = J->nodes_p + R.node_offset;
             if (wk.read != cur_read) { cur_read = wk.read; memo.assign(R.num_inner, 0xff); }
             if (R.num_inner && wk.node >= inner && wk.node < inner + R.num_inner) dist[i] = node_dist(inner, memo, uint64_t(wk.node - inner));
             max_dist = std::max(max_dist, dist[i]);
@@ -1025,18 +1066,18 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
         root_passes.clear(); root_walk.clear(); root_k.clear();
         for (uint32_t wi : active) {
             Walk& wk = walks[wi];
-            fxg_anchor const& A = J->anchors[wk.anchor];
+            fxg_anchor const& A = J->anchors_p[wk.anchor];
             bool const is_root = wk.node->parent_id == FXG_NULL_ID;
             Span sp;
             if (is_root) sp = wk.root_span;
             else {
-                fxg_read const& R = J->reads[wk.read];
-                const fxg_pex_node* leaves = J->nodes.data() + R.node_offset + R.num_inner;
+                fxg_read const& R = J->reads_p[wk.read];
+                const fxg_pex_node* leaves = J->nodes_p + R.node_offset + R.num_inner;
                 sp = compute_span(A.reference_position, *wk.node, leaves[A.pex_leaf_index].query_index_from, c->refs.len[A.reference_id], 0.0);
             }
             uint32_t const m = uint32_t(wk.node->query_index_to - wk.node->query_index_from + 1);
             uint32_t const flags = (is_root && J->cfg.without_cigar) ? kFlagReverse : 0u;
-            uint64_t const qbase = (wk.orient ? J->pool_len : 0) + J->reads[wk.read].query_offset + wk.node->query_index_from;
+            uint64_t const qbase = (wk.orient ? J->pool_len : 0) + J->reads_p[wk.read].query_offset + wk.node->query_index_from;
             // statistics, verification.cpp:238-242
             if (is_root) { out.stats.n_aligned_root++; out.stats.sum_aligned_root += sp.length; out.stats.cells_root += uint64_t(m) * sp.length; }
             else { out.stats.n_aligned_inner++; out.stats.sum_aligned_inner += sp.length; out.stats.cells_inner += uint64_t(m) * sp.length; }
@@ -1049,6 +1090,12 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
             }
         }
         g_prof.lap(w, 2);
+        if (gate) {
+            // the query pools and their Peq planes are being uploaded by the caller's thread: order this worker's stream behind them
+            if (gate->wait() != FXG_OK) { out.rc = gate->rc; w.err = gate->err; return; }
+            if (cudaStreamWaitEvent(w.stream, c->ev_staged, 0) != cudaSuccess) { out.rc = fail(w.err, FXG_ERR_CUDA, "cannot order the worker behind the upload"); return; }
+            gate = nullptr;
+        }
         const DpResult* res = nullptr;
         out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
         if (out.rc != FXG_OK) return;
@@ -1069,8 +1116,8 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
                 }
                 wk.state = W_DONE; ++n_done;
             } else if (exists) {
-                fxg_read const& R = J->reads[wk.read];
-                wk.node = &J->nodes[R.node_offset + wk.node->parent_id];      // pex_tree::get_parent_of_child, pex.cpp:70-76
+                fxg_read const& R = J->reads_p[wk.read];
+                wk.node = &J->nodes_p[R.node_offset + wk.node->parent_id];      // pex_tree::get_parent_of_child, pex.cpp:70-76
                 next_active.push_back(wi);
             } else {
                 wk.state = W_DONE; ++n_done;
@@ -1122,7 +1169,7 @@ void verify_part_finish(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t* host_cigars
         if (!wk.hit) continue;
         fxg_alignment a{};
         a.start_in_reference = wk.start_in_reference; a.cigar_offset = wk.cigar_offset; a.cigar_len = wk.cigar_len;
-        a.num_errors = wk.num_errors; a.read_index = wk.read; a.reference_id = uint32_t(J->anchors[wk.anchor].reference_id);
+        a.num_errors = wk.num_errors; a.read_index = wk.read; a.reference_id = uint32_t(J->anchors_p[wk.anchor].reference_id);
         a.orientation = wk.orient;
         out.alignments.push_back(a);
     }
@@ -1184,6 +1231,7 @@ int fxg_create(int device, fxg_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->smem_limit = prop.sharedMemPerBlockOptin;
     bool ok = cudaEventCreate(&c->ev_run0) == cudaSuccess && cudaEventCreate(&c->ev_run1) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming) == cudaSuccess &&
               set_all_smem_attrs(c->smem_limit) == cudaSuccess;
     c->root_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64);
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
@@ -1221,6 +1269,7 @@ void fxg_destroy(fxg_ctx* c) {
     for (auto& w : c->workers) w->release();
     if (c->ev_run0) cudaEventDestroy(c->ev_run0);
     if (c->ev_run1) cudaEventDestroy(c->ev_run1);
+    if (c->ev_staged) cudaEventDestroy(c->ev_staged);
     delete c;
 }
 
@@ -1287,7 +1336,7 @@ int fxg_align_batch_stage(fxg_ctx* c, const fxg_align_task* tasks, size_t n_task
     b->tasks.assign(tasks, tasks + n_tasks);
     b->pool = take_pool(c);
     b->cigars = take_pinned(c);
-    rc = stage_pool(c, b->pool, query_pool, query_pool_len, nullptr, 0);
+    rc = stage_pool(c, b->pool, query_pool, query_pool_len, nullptr, 0, c->err, c->ctr);
     if (rc == FXG_OK && inline_ref_pool_len) {
         b->pool.inline_len = inline_ref_pool_len;
         cudaError_t e = b->pool.inline_packed.ensure(inline_ref_pool_len / 2 + 64);
@@ -1404,68 +1453,24 @@ int fxg_align_batch(fxg_ctx* c, const fxg_align_task* tasks, size_t n_tasks, con
 
 // ------------------------------------------------------------------------------------------------ verify
 
-int fxg_verify_stage(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* reads, size_t n_reads,
-                     const uint8_t* fwd, const uint8_t* rc_pool, size_t pool_len,
-                     const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors, fxg_job** out) {
-    if (!c || !cfg || !out) return FXG_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(c->mu);
-    *out = nullptr;
-    if (!c->have_refs) return fail(c->err, FXG_ERR_STATE, "fxg_set_references must be called first");
-    if (cfg->verification_kind != FXG_KIND_DIRECT_FULL && cfg->verification_kind != FXG_KIND_HIERARCHICAL)
-        return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "Internal bug in verification kind (should not happen)");   // verification.cpp:19
-    CUDA_TRY(c->err, cudaSetDevice(c->device));
-    for (size_t i = 0; i < n_reads; ++i) {
-        fxg_read const& R = reads[i];
-        if (R.query_offset + R.query_len > pool_len) return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "read %zu: query outside the pool", i);
-        if (R.query_len > FXG_MAX_QUERY_LENGTH) return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "read %zu: longer than %d", i, FXG_MAX_QUERY_LENGTH);
-        if (R.node_offset + R.num_inner + R.num_leaves > n_nodes || R.num_leaves == 0) return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "read %zu: bad node range", i);
-        if (R.anchor_offset + R.num_anchors_forward + R.num_anchors_reverse > n_anchors) return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "read %zu: bad anchor range", i);
-        const fxg_pex_node* nd = nodes + R.node_offset;
-        for (uint32_t q = 0; q < R.num_inner + R.num_leaves; ++q) {
-            if (nd[q].query_index_to < nd[q].query_index_from || nd[q].query_index_to >= R.query_len) return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "read %zu: node %u outside the query", i, q);
-            if (nd[q].parent_id != FXG_NULL_ID && nd[q].parent_id >= R.num_inner) return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "read %zu: node %u has a bad parent", i, q);
-        }
-        const fxg_anchor* an = anchors + R.anchor_offset;
-        for (uint32_t q = 0; q < R.num_anchors_forward + R.num_anchors_reverse; ++q) {
-            if (an[q].pex_leaf_index >= R.num_leaves) return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "read %zu: anchor %u names leaf %llu", i, q, (unsigned long long)an[q].pex_leaf_index);
-            if (an[q].reference_id >= c->refs.len.size()) return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "read %zu: anchor %u names reference %llu", i, q, (unsigned long long)an[q].reference_id);
-            if (an[q].reference_position >= c->refs.len[an[q].reference_id]) return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "read %zu: anchor %u outside its reference", i, q);
-        }
-    }
-    int rc = check_ranks(c->err, fwd, pool_len, "forward pool");
-    if (rc == FXG_OK) rc = check_ranks(c->err, rc_pool, pool_len, "reverse-complement pool");
-    if (rc != FXG_OK) return rc;
-    fxg_job* j = new (std::nothrow) fxg_job();
-    if (!j) return FXG_ERR_OUT_OF_MEMORY;
-    j->cfg = *cfg;
-    j->reads.assign(reads, reads + n_reads);
-    j->nodes.assign(nodes, nodes + n_nodes);
-    j->anchors.assign(anchors, anchors + n_anchors);
-    j->pool_len = pool_len;
-    j->pool = take_pool(c);
-    j->cigars = take_pinned(c);
+namespace {
 
-    j->read_walk_begin.resize(n_reads + 1);
+// reads -> first walk (= anchor) of every read in job order
+void index_walks(fxg_job* j) {
+    j->read_walk_begin.resize(j->n_reads + 1);
     uint32_t n_walks_total = 0;
-    for (size_t ri = 0; ri < n_reads; ++ri) {
+    for (size_t ri = 0; ri < j->n_reads; ++ri) {
         j->read_walk_begin[ri] = n_walks_total;
-        n_walks_total += j->reads[ri].num_anchors_forward + j->reads[ri].num_anchors_reverse;
+        n_walks_total += j->reads_p[ri].num_anchors_forward + j->reads_p[ri].num_anchors_reverse;
     }
-    j->read_walk_begin[n_reads] = n_walks_total;
-
-    rc = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len);
-    if (rc == FXG_OK && cudaStreamSynchronize(c->workers[0]->stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
-    if (rc != FXG_OK) { give_pool(c, j->pool); give_pinned(c, j->cigars); delete j; return rc; }
-    *out = j;
-    return FXG_OK;
+    j->read_walk_begin[j->n_reads] = n_walks_total;
 }
 
-int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
-    if (!c || !J) return FXG_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(c->mu);
-    CUDA_TRY(c->err, cudaSetDevice(c->device));
+// fxg_verify_run without the context lock.  With a gate the parts validate their own reads first and wait at the gate
+// before their first launch (fxg_verify_reads: the upload runs beside their host-side preparation).
+int verify_run_locked(fxg_ctx* c, fxg_job* J, StageGate* gate, size_t pool_len) {
     J->alignments.clear(); J->cigars_len = 0; J->stats = fxg_stats{};
-    size_t const n_reads = J->reads.size();
+    size_t const n_reads = J->n_reads;
     if (n_reads == 0) { J->ran = true; return FXG_OK; }
 
     // ---- split the reads into contiguous parts with similar numbers of anchors, one part per worker ----
@@ -1489,7 +1494,8 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
         Worker& w = *c->workers[p];
         PartState& P = parts[p];
         P.trace_budget = budget;
-        verify_part_score(c, w, J, cut[p], cut[p + 1], P);
+        if (gate) P.out.rc = validate_reads(c, w.err, J->reads_p, cut[p], cut[p + 1], pool_len, J->nodes_p, J->n_nodes, J->anchors_p, J->n_anchors);
+        if (P.out.rc == FXG_OK) verify_part_score(c, w, J, cut[p], cut[p + 1], P, gate);
         g_prof.start(w);
         plan.arrive_and_wait(p, P.out.rc == FXG_OK ? w.cig_used : 0);        // every part arrives, also a failed one
         g_prof.lap(w, 14);
@@ -1525,6 +1531,56 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
     return FXG_OK;
 }
 
+int check_verify_call(fxg_ctx* c, const fxg_verify_config* cfg) {
+    if (!c->have_refs) return fail(c->err, FXG_ERR_STATE, "fxg_set_references must be called first");
+    if (cfg->verification_kind != FXG_KIND_DIRECT_FULL && cfg->verification_kind != FXG_KIND_HIERARCHICAL)
+        return fail(c->err, FXG_ERR_INVALID_ARGUMENT, "Internal bug in verification kind (should not happen)");   // verification.cpp:19
+    return FXG_OK;
+}
+
+}  // namespace
+
+int fxg_verify_stage(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* reads, size_t n_reads,
+                     const uint8_t* fwd, const uint8_t* rc_pool, size_t pool_len,
+                     const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors, fxg_job** out) {
+    if (!c || !cfg || !out) return FXG_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(c->mu);
+    *out = nullptr;
+    int rc = check_verify_call(c, cfg);
+    if (rc != FXG_OK) return rc;
+    CUDA_TRY(c->err, cudaSetDevice(c->device));
+    rc = validate_reads(c, c->err, reads, 0, n_reads, pool_len, nodes, n_nodes, anchors, n_anchors);
+    if (rc == FXG_OK) rc = check_ranks(c->err, fwd, pool_len, "forward pool");
+    if (rc == FXG_OK) rc = check_ranks(c->err, rc_pool, pool_len, "reverse-complement pool");
+    if (rc != FXG_OK) return rc;
+    fxg_job* j = new (std::nothrow) fxg_job();
+    if (!j) return FXG_ERR_OUT_OF_MEMORY;
+    j->cfg = *cfg;
+    j->reads.assign(reads, reads + n_reads);
+    j->nodes.assign(nodes, nodes + n_nodes);
+    j->anchors.assign(anchors, anchors + n_anchors);
+    j->reads_p = j->reads.data(); j->nodes_p = j->nodes.data(); j->anchors_p = j->anchors.data();
+    j->n_reads = n_reads; j->n_nodes = n_nodes; j->n_anchors = n_anchors;
+    j->pool_len = pool_len;
+    j->pool = take_pool(c);
+    j->cigars = take_pinned(c);
+    index_walks(j);
+
+    rc = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, c->err, c->ctr);
+    if (rc == FXG_OK && cudaStreamSynchronize(c->workers[0]->stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
+    if (rc != FXG_OK) { give_pool(c, j->pool); give_pinned(c, j->cigars); delete j; return rc; }
+    *out = j;
+    return FXG_OK;
+}
+
+int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
+    if (!c || !J) return FXG_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (J->borrowed) return fail(c->err, FXG_ERR_STATE, "a job made by fxg_verify_reads cannot be run again (its inputs belonged to the caller)");
+    CUDA_TRY(c->err, cudaSetDevice(c->device));
+    return verify_run_locked(c, J, nullptr, J->pool_len);
+}
+
 size_t fxg_job_num_alignments(const fxg_job* j) { return j ? j->alignments.size() : 0; }
 const fxg_alignment* fxg_job_alignments(const fxg_job* j) { return j ? j->alignments.data() : nullptr; }
 size_t fxg_job_cigar_len(const fxg_job* j) { return j ? j->cigars_len : 0; }
@@ -1538,14 +1594,46 @@ void fxg_job_free(fxg_ctx* c, fxg_job* j) {
     delete j;
 }
 
+// stage + run in one call.  The caller's arrays are used in place (they only have to live until the call returns), the
+// query pools go up on the caller's thread while the workers validate their reads and prepare their first wave.
 int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* reads, size_t n_reads,
                      const uint8_t* fwd, const uint8_t* rc_pool, size_t pool_len,
                      const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors, fxg_job** out) {
-    fxg_job* j = nullptr;
-    int rc = fxg_verify_stage(c, cfg, reads, n_reads, fwd, rc_pool, pool_len, nodes, n_nodes, anchors, n_anchors, &j);
+    if (!c || !cfg || !out) return FXG_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(c->mu);
+    *out = nullptr;
+    int rc = check_verify_call(c, cfg);
     if (rc != FXG_OK) return rc;
-    rc = fxg_verify_run(c, j);
-    if (rc != FXG_OK) { fxg_job_free(c, j); return rc; }
+    CUDA_TRY(c->err, cudaSetDevice(c->device));
+    fxg_job* j = new (std::nothrow) fxg_job();
+    if (!j) return FXG_ERR_OUT_OF_MEMORY;
+    j->cfg = *cfg;
+    j->reads_p = reads; j->nodes_p = nodes; j->anchors_p = anchors;
+    j->n_reads = n_reads; j->n_nodes = n_nodes; j->n_anchors = n_anchors;
+    j->borrowed = true;
+    j->pool_len = pool_len;
+    j->pool = take_pool(c);
+    j->cigars = take_pinned(c);
+    index_walks(j);
+
+    StageGate gate;
+    fxg_counters stage_ctr{};
+    std::thread stager([&] {
+        cudaSetDevice(c->device);
+        std::string err;
+        int r = check_ranks(err, fwd, pool_len, "forward pool");
+        if (r == FXG_OK) r = check_ranks(err, rc_pool, pool_len, "reverse-complement pool");
+        if (r == FXG_OK) r = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, err, stage_ctr);
+        if (r == FXG_OK && cudaEventRecord(c->ev_staged, c->workers[0]->stream) != cudaSuccess) r = fail(err, FXG_ERR_CUDA, "staging failed");
+        gate.open(r, err);
+    });
+    rc = verify_run_locked(c, j, &gate, pool_len);
+    stager.join();
+    add_counters(c->ctr, stage_ctr);
+    if (gate.rc != FXG_OK) { rc = gate.rc; c->err = gate.err; }
+    // the caller's arrays are not looked at after this point
+    j->reads_p = nullptr; j->nodes_p = nullptr; j->anchors_p = nullptr;
+    if (rc != FXG_OK) { cudaDeviceSynchronize(); give_pool(c, j->pool); give_pinned(c, j->cigars); delete j; return rc; }
     *out = j;
     return FXG_OK;
 }
