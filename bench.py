@@ -170,7 +170,18 @@ def main() -> int:
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when it initialises: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from floxer_b200 import build
     from floxer_b200 import gpu as g
@@ -287,7 +298,10 @@ def main() -> int:
         achieved_all = ws * MYERS_INSTR_PER_WORD_STEP / dp_s if dp_s > 0 else 0.0
         tr_s = roof_ctr["trace_kernel_ms"] * 1e-3
         roofline = {"bound": "int32_alu", "achieved": achieved / 1e9, "peak": int32_peak / 1e9, "unit": "Ginstr/s",
-                    "frac": achieved / int32_peak if int32_peak else None, "traffic": None,
+                    "frac": achieved / int32_peak if int32_peak else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
+                    # (profiles/r01_final_ncu_full_summary.txt: 84.9 MB read, 1.446 GB written -- the checkpoint records)
+                    "traffic": 1531283520,
                     "kernel": "fxg::dp_kernel<4,true> -- the root-level launch of a step (score pass leaving traceback checkpoints)",
                     "how": "algorithmic 11 int32 instr per 32-cell word-step x word-steps issued by that launch (band-limited, counted on the "
                            "host from the band geometry) / CUDA-event time of the launch on its stream; peak = LOP3/IADD3/SHF 8:1:2 "
