@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
     uint32_t n_runs = 0, cur_op = 0, cur_len = 0, errors = 0;
     bool bad = false;
     uint32_t eq_block = 0xffffffffu;                             // block whose Eq rows are in shared memory
-    uint32_t chars[5] = {0, 0, 0, 0, 0};                         // window characters of the tile's columns, 4 bits each, step p at nibble p
+    uint32_t chars[4] = {0, 0, 0, 0};                            // window characters of the tile's columns, 4 bits each, step p at nibble p
     auto emit = [&](uint32_t op, uint32_t len) {
         if (op == cur_op) { cur_len += len; return; }
         if (cur_len) { if (n_runs < T.cigar_cap) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
@@ -669,6 +669,42 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
     auto tile_char = [&](uint32_t p) -> uint32_t {               // p in 0 .. 31
         uint32_t const w = p < 8 ? chars[0] : (p < 16 ? chars[1] : (p < 24 ? chars[2] : chars[3]));
         return (w >> (4 * (p & 7u))) & 15u;
+    };
+
+    // inputs of a tile, as loaded: window characters, the block's record at the step before the tile, boundary bits of the
+    // block above for the tile's steps (A) and the 32 steps before (B)
+    struct TileIn { uint32_t raw[5]; uint32_t sh; uint32_t st[2 * W]; uint32_t hpA, hnA, hpB, hnB; };
+    TileIn X;
+    bool pf_valid = false; uint32_t pf_b = 0, pf_q = 0;
+    auto fetch_tile = [&](uint32_t b, uint32_t q, TileIn& Y) {
+        int32_t ts, te; block_steps(b, ts, te);
+        int32_t const t0 = 32 * int32_t(q - 1);
+        int64_t const pos0 = int64_t(T.ref_base) + int64_t(t0) - int64_t(b);      // store position of step t0 + 1 (column - 1)
+        int64_t const w0 = pos0 >= 0 ? (pos0 >> 3) : -((7 - pos0) >> 3);          // floor(pos0 / 8); positions before the window are never used
+        Y.sh = uint32_t(pos0 - w0 * 8) * 4;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) Y.raw[k] = w0 + k >= 0 ? __ldg(ref + (w0 + k)) : 0u;
+        if (t0 >= ts) {
+            const uint32_t* rec = ck + (uint64_t(b) * ck_per_block + uint32_t(int32_t(q - 1) - ((ts + 31) >> 5))) * RECW;
+            if constexpr (W == 1) { uint2 const v = *reinterpret_cast<const uint2*>(rec); Y.st[0] = v.x; Y.st[1] = v.y; }
+            else if constexpr (W == 2) { uint4 const v = *reinterpret_cast<const uint4*>(rec); Y.st[0] = v.x; Y.st[1] = v.y; Y.st[2] = v.z; Y.st[3] = v.w; }
+            else {
+#pragma unroll
+                for (int w = 0; w < 2 * W; w += 4) {
+                    uint4 const a = *reinterpret_cast<const uint4*>(rec + w);
+                    Y.st[w] = a.x; Y.st[w + 1] = a.y; Y.st[w + 2] = a.z; Y.st[w + 3] = a.w;
+                }
+            }
+        }
+        Y.hpA = 0xffffffffu; Y.hnA = 0; Y.hpB = 0xffffffffu; Y.hnB = 0;
+        if (b > 0) {
+            int32_t us, ue; block_steps(b - 1, us, ue);
+            int32_t const uq_first = (us + 31) >> 5, uq_last = (ue + 31) >> 5;
+            const uint32_t* const urec = ck + uint64_t(b - 1) * ck_per_block * RECW;
+            constexpr int BO = W == 1 ? 2 : 2 * W;                           // where a record keeps its boundary bits
+            if (int32_t(q) >= uq_first && int32_t(q) <= uq_last) { uint2 const v = *reinterpret_cast<const uint2*>(urec + uint64_t(int32_t(q) - uq_first) * RECW + BO); Y.hpA = v.x; Y.hnA = v.y; }
+            if (int32_t(q) - 1 >= uq_first && int32_t(q) - 1 <= uq_last) { uint2 const v = *reinterpret_cast<const uint2*>(urec + uint64_t(int32_t(q) - 1 - uq_first) * RECW + BO); Y.hpB = v.x; Y.hnB = v.y; }
+        }
     };
 
     while (!__all_sync(0xffffffffu, done)) {
@@ -687,30 +723,16 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
             int32_t const t0 = 32 * int32_t(q - 1);                              // the tile covers steps t0 + 1 .. t0 + 32
             // the path only moves up and left: nothing after the step of (i, j) is needed
             int32_t const t_lo = t0 + 1 > ts ? t0 + 1 : ts, t_hi = int32_t(t_cell) < te ? int32_t(t_cell) : te;
-            // window characters of steps t0 + 1 .. t0 + 32: columns t0 + 1 - b .. (store positions may start before the window: never used)
-            {
-                int64_t const pos0 = int64_t(T.ref_base) + int64_t(t0) - int64_t(b);      // store position of step t0 + 1 (column - 1)
-                int64_t const w0 = pos0 >= 0 ? (pos0 >> 3) : -((7 - pos0) >> 3);          // floor(pos0 / 8)
-                uint32_t const sh = uint32_t(pos0 - w0 * 8) * 4;
-                uint32_t raw[5];
+            // what the tile is computed from: fetched while the previous tile was being walked, if the guess was right
+            if (!(pf_valid && pf_b == b && pf_q == q)) fetch_tile(b, q, X);
+            pf_valid = false;
+            // window characters of steps t0 + 1 .. t0 + 32 (columns t0 + 1 - b ..), 4 bits each, step p at nibble p
 #pragma unroll
-                for (int k = 0; k < 5; ++k) raw[k] = w0 + k >= 0 ? __ldg(ref + (w0 + k)) : 0u;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) chars[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
-            }
+            for (int k = 0; k < 4; ++k) chars[k] = __funnelshift_r(X.raw[k], X.raw[k + 1], X.sh);
             uint32_t Pv[W], Mv[W];
             if (t0 >= ts) {
-                const uint32_t* rec = ck + (uint64_t(b) * ck_per_block + uint32_t(int32_t(q - 1) - ((ts + 31) >> 5))) * RECW;
-                if constexpr (W == 1) { uint2 const v = *reinterpret_cast<const uint2*>(rec); Pv[0] = v.x; Mv[0] = v.y; }
-                else if constexpr (W == 2) { uint4 const v = *reinterpret_cast<const uint4*>(rec); Pv[0] = v.x; Pv[1] = v.y; Mv[0] = v.z; Mv[1] = v.w; }
-                else {
 #pragma unroll
-                    for (int w = 0; w < W; w += 4) {
-                        uint4 const a = *reinterpret_cast<const uint4*>(rec + w), m4 = *reinterpret_cast<const uint4*>(rec + W + w);
-                        Pv[w] = a.x; Pv[w + 1] = a.y; Pv[w + 2] = a.z; Pv[w + 3] = a.w;
-                        Mv[w] = m4.x; Mv[w + 1] = m4.y; Mv[w + 2] = m4.z; Mv[w + 3] = m4.w;
-                    }
-                }
+                for (int w = 0; w < W; ++w) { Pv[w] = X.st[w]; Mv[w] = X.st[W + w]; }
             } else {
                 // the block begins inside the tile: "block above + 1, 2, ..." (wildcard rows of block 0 carry value 0)
 #pragma unroll
@@ -724,14 +746,8 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
             uint32_t top_hp = 0, top_hn = 0;
             if (b > 0) {
                 int32_t us, ue; block_steps(b - 1, us, ue);                      // the block above is one step ahead: its step t - 1
-                int32_t const uq_first = (us + 31) >> 5, uq_last = (ue + 31) >> 5;
-                uint32_t hpA = 0xffffffffu, hnA = 0, hpB = 0xffffffffu, hnB = 0;
-                const uint32_t* const urec = ck + uint64_t(b - 1) * ck_per_block * RECW;
-                constexpr int BO = W == 1 ? 2 : 2 * W;                           // where a record keeps its boundary bits
-                if (int32_t(q) >= uq_first && int32_t(q) <= uq_last) { uint2 const v = *reinterpret_cast<const uint2*>(urec + uint64_t(int32_t(q) - uq_first) * RECW + BO); hpA = v.x; hnA = v.y; }
-                if (int32_t(q) - 1 >= uq_first && int32_t(q) - 1 <= uq_last) { uint2 const v = *reinterpret_cast<const uint2*>(urec + uint64_t(int32_t(q) - 1 - uq_first) * RECW + BO); hpB = v.x; hnB = v.y; }
-                top_hp = (hpA << 1) | (hpB >> 31);
-                top_hn = (hnA << 1) | (hnB >> 31);
+                top_hp = (X.hpA << 1) | (X.hpB >> 31);
+                top_hn = (X.hnA << 1) | (X.hnB >> 31);
                 // steps of the block above outside its working range publish the "+1" boundary
                 int32_t const p_lo = us - t0, p_hi = ue - t0;                    // bit p <-> upper step t0 + p
                 uint32_t valid = 0;
@@ -757,21 +773,32 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
                     }
                 }
             }
-            for (int32_t t = t_lo; t <= t_hi; ++t) {
-                uint32_t const p = uint32_t(t - t0 - 1);
-                uint32_t const c = tile_char(p);
-                uint32_t Eq[W], hp_all[W];
+            {
+                uint32_t EqN[W];
+                uint32_t const c0 = tile_char(uint32_t(t_lo - t0 - 1));
 #pragma unroll
-                for (int w = 0; w < W; ++w) Eq[w] = eq_s[(c * W + w) * kWalk2Threads];
-                uint32_t hp, hn;
-                block_column<W, true>(Pv, Mv, Eq, ((top_hp >> p) & 1u) << 31, ((top_hn >> p) & 1u) << 31, hp, hn, hp_all);
-                // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
+                for (int w = 0; w < W; ++w) EqN[w] = eq_s[(c0 * W + w) * kWalk2Threads];
+                for (int32_t t = t_lo; t <= t_hi; ++t) {
+                    uint32_t const p = uint32_t(t - t0 - 1);
+                    uint32_t Eq[W], hp_all[W];
 #pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    bits[((p * W + w) * 2) * kWalk2Threads] = hp_all[w];
-                    bits[((p * W + w) * 2 + 1) * kWalk2Threads] = Pv[w];
+                    for (int w = 0; w < W; ++w) Eq[w] = EqN[w];
+                    uint32_t const cn = tile_char((p + 1) & 31u);                // Eq row of the next step, fetched ahead
+#pragma unroll
+                    for (int w = 0; w < W; ++w) EqN[w] = eq_s[(cn * W + w) * kWalk2Threads];
+                    uint32_t hp, hn;
+                    block_column<W, true>(Pv, Mv, Eq, ((top_hp >> p) & 1u) << 31, ((top_hn >> p) & 1u) << 31, hp, hn, hp_all);
+                    // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        bits[((p * W + w) * 2) * kWalk2Threads] = hp_all[w];
+                        bits[((p * W + w) * 2 + 1) * kWalk2Threads] = Pv[w];
+                    }
                 }
             }
+            // the path most likely continues into the same block's previous 32 steps: get that tile's inputs on their
+            // way now, they arrive while this tile is being walked
+            if (q >= 2 && 32 * int32_t(q - 1) >= ts) { fetch_tile(b, q - 1, X); pf_valid = true; pf_b = b; pf_q = q - 1; }
         }
         // ---------------- follow the path while it stays inside the tile ----------------
         // trace priority: left > up > diagonal (the one place that encodes it; oracle: FXO_TRACE_PRIORITY)

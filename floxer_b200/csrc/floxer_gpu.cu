@@ -224,6 +224,7 @@ struct Walk {                 // one query_verifier::verify() call
     uint64_t r_start, r_end;  // root window
     uint64_t t_start, t_end;  // root window trimmed by the extra length (root_was_already_verified)
     Span root_span;
+    bool have_root_span;
     uint64_t start_in_reference; uint32_t num_errors; uint64_t cigar_offset; uint32_t cigar_len;
 };
 
@@ -895,11 +896,16 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
                 fxg_pex_node const& leaf = leaves[A.pex_leaf_index];
                 Walk wk{};
                 wk.read = ri; wk.anchor = a0 + q; wk.orient = uint8_t(orient); wk.state = W_WAITING;
-                wk.root_span = compute_span(A.reference_position, root, leaf.query_index_from, c->refs.len[A.reference_id], ratio);
-                wk.r_start = wk.root_span.offset; wk.r_end = wk.root_span.offset + wk.root_span.length;
-                wk.t_start = wk.r_start; wk.t_end = wk.r_end;
-                trim(wk.t_start, wk.t_end, wk.root_span.extra);
                 wk.node = (direct || leaf.parent_id == FXG_NULL_ID) ? &root : &inner[leaf.parent_id];
+                // the root window is needed up front only by the interval optimisation (and by walks that start at the
+                // root); otherwise it is computed when -- and if -- the walk gets there
+                if (ivopt || wk.node == &root) {
+                    wk.root_span = compute_span(A.reference_position, root, leaf.query_index_from, c->refs.len[A.reference_id], ratio);
+                    wk.r_start = wk.root_span.offset; wk.r_end = wk.root_span.offset + wk.root_span.length;
+                    wk.t_start = wk.r_start; wk.t_end = wk.r_end;
+                    trim(wk.t_start, wk.t_end, wk.root_span.extra);
+                    wk.have_root_span = true;
+                }
                 if (ivopt) {
                     if (ref_to_group[A.reference_id] < 0) { ref_to_group[A.reference_id] = int64_t(tmp_groups.size()); tmp_groups.emplace_back(); }
                     wk.group = group_base + uint32_t(ref_to_group[A.reference_id]);
@@ -1069,10 +1075,16 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
             fxg_anchor const& A = J->anchors_p[wk.anchor];
             bool const is_root = wk.node->parent_id == FXG_NULL_ID;
             Span sp;
-            if (is_root) sp = wk.root_span;
-            else {
-                fxg_read const& R = J->reads_p[wk.read];
-                const fxg_pex_node* leaves = J->nodes_p + R.node_offset + R.num_inner;
+            fxg_read const& R = J->reads_p[wk.read];
+            const fxg_pex_node* leaves = J->nodes_p + R.node_offset + R.num_inner;
+            if (is_root) {
+                if (!wk.have_root_span) {
+                    wk.root_span = compute_span(A.reference_position, *wk.node, leaves[A.pex_leaf_index].query_index_from, c->refs.len[A.reference_id],
+                                                J->cfg.extra_verification_ratio);
+                    wk.have_root_span = true;
+                }
+                sp = wk.root_span;
+            } else {
                 sp = compute_span(A.reference_position, *wk.node, leaves[A.pex_leaf_index].query_index_from, c->refs.len[A.reference_id], 0.0);
             }
             uint32_t const m = uint32_t(wk.node->query_index_to - wk.node->query_index_from + 1);
