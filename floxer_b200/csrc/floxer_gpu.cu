@@ -225,6 +225,7 @@ struct Walk {                 // one query_verifier::verify() call
     uint64_t t_start, t_end;  // root window trimmed by the extra length (root_was_already_verified)
     Span root_span;
     bool have_root_span;
+    uint32_t n_inner; uint64_t sum_inner, cells_inner;   // its inner-node alignments so far (verification.cpp:238-242)
     uint64_t start_in_reference; uint32_t num_errors; uint64_t cigar_offset; uint32_t cigar_len;
 };
 
@@ -980,12 +981,20 @@ uint8_t node_dist(const fxg_pex_node* inner, std::vector<uint8_t>& memo, uint64_
     return memo[id] = d;
 }
 
-// query_verifier::verify() for every anchor of reads [read_lo, read_hi), level-synchronously: every score pass.
-// Without the interval optimisation the walks are advanced deepest node first, so that all alignments of one tree level
-// (in particular every root alignment) end up in the same wave and fill the machine together.
-// With it, the sequential semantics of the verified-interval sets are preserved exactly: a walk starts only when no
-// earlier walk of its (read, orientation, reference) group that could still verify its root window is
-// unresolved, and it is skipped if an EARLIER walk inserted a window containing its trimmed root window.
+// query_verifier::verify() for every anchor of reads [read_lo, read_hi), level-synchronously.
+//
+// 1. Inner levels.  The walks are advanced deepest node first, so that all alignments of one tree level land in the same
+//    wave and fill the machine together; a walk stops at its first failing level (verification.cpp:95-100) or arrives
+//    at the root.
+// 2. Interval optimisation (verification.cpp:62-64, 106-109, 119-136), exactly as the reference's sequential loop
+//    would have it.  Whether a walk reaches the root depends on its inner alignments alone, and the root window is inserted
+//    whenever the root is reached (even if the root alignment then fails) -- so once step 1 has run for EVERY walk
+//    (speculatively: the sequential loop would not even have started some of them), one pass over each (read, strand,
+//    reference) group in anchor order decides everything: a walk whose trimmed root window lies inside the window of an
+//    earlier walk that reached the root is avoided (its speculative alignments are discarded, statistics included), any
+//    other walk counts, and inserts its window if it reached the root.
+// 3. Root level: one wave for the walks that count and reached the root (with checkpoints + tracebacks when CIGARs
+//    are wanted).
 void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, PartState& P, StageGate* gate) {
     cudaSetDevice(c->device);
     P.t0 = std::chrono::steady_clock::now();
@@ -995,12 +1004,10 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     std::vector<Walk>& walks = P.walks; std::vector<Group>& groups = P.groups; std::vector<uint32_t>& group_members = P.group_members;
     build_walks(c, J, read_lo, read_hi, walks, groups, group_members);
     size_t const n_walks = walks.size();
-    struct GroupState { uint32_t first_open = 0; std::vector<uint32_t> inserted; };
-    std::vector<GroupState> gstate(groups.size());
 
     // ---- tree level of every walk's first node ----
-    std::vector<std::vector<uint32_t>> level;            // !ivopt: walks waiting for the wave of their node's level
-    if (!ivopt) {
+    std::vector<std::vector<uint32_t>> level;            // walks waiting for the wave of their node's level (0 = root)
+    {
         std::vector<uint8_t> memo;
         std::vector<uint8_t> dist(n_walks, 0);
         uint32_t cur_read = UINT32_MAX; uint8_t max_dist = 0;
@@ -1015,154 +1022,160 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
         level.resize(size_t(max_dist) + 1);
         for (uint32_t i = 0; i < n_walks; ++i) { level[dist[i]].push_back(i); walks[i].state = W_WALKING; }
     }
-    int cur_level = int(level.size()) - 1;
 
-    std::vector<uint32_t> active, next_active;
+    std::vector<uint32_t> active;
     std::vector<Pass> passes; std::vector<uint32_t> pass_walk;
-    std::vector<std::pair<uint32_t, bool>> no_pass;
-    std::vector<Pass> root_passes; std::vector<uint32_t> root_walk, root_k;   // root alignments whose CIGAR is wanted
-    std::vector<RootOut> root_outs;
     w.cig_used = 0;
-    size_t n_done = 0;
     g_prof.lap(w, 0);
 
-    while (n_done < n_walks) {
+    auto pass_through_gate = [&]() -> bool {
+        if (!gate) return true;
+        // the query pools and their Peq planes are being uploaded by the caller's thread: order this worker's stream behind them
+        if (gate->wait() != FXG_OK) { out.rc = gate->rc; w.err = gate->err; return false; }
+        if (cudaStreamWaitEvent(w.stream, c->ev_staged, 0) != cudaSuccess) { out.rc = fail(w.err, FXG_ERR_CUDA, "cannot order the worker behind the upload"); return false; }
+        gate = nullptr;
+        return true;
+    };
+    auto span_of = [&](Walk& wk, bool is_root) -> Span {
+        fxg_anchor const& A = J->anchors_p[wk.anchor];
+        fxg_read const& R = J->reads_p[wk.read];
+        const fxg_pex_node* leaves = J->nodes_p + R.node_offset + R.num_inner;
+        if (!is_root) return compute_span(A.reference_position, *wk.node, leaves[A.pex_leaf_index].query_index_from, c->refs.len[A.reference_id], 0.0);
+        if (!wk.have_root_span) {
+            wk.root_span = compute_span(A.reference_position, *wk.node, leaves[A.pex_leaf_index].query_index_from, c->refs.len[A.reference_id],
+                                        J->cfg.extra_verification_ratio);
+            wk.have_root_span = true;
+        }
+        return wk.root_span;
+    };
+
+    // ---------------- 1. inner levels, deepest first ----------------
+    for (int cur_level = int(level.size()) - 1; cur_level >= 1; --cur_level) {
         g_prof.start(w);
-        // ---- admission ----
-        if (!ivopt) {
-            while (cur_level >= 0 && level[size_t(cur_level)].empty()) --cur_level;
-            if (cur_level >= 0) { active.swap(level[size_t(cur_level)]); level[size_t(cur_level)].clear(); }
-        } else {
-            for (uint32_t g = 0; g < groups.size(); ++g) {
-                Group const& G = groups[g];
-                GroupState& S = gstate[g];
-                const uint32_t* mem = group_members.data() + G.first;
-                while (S.first_open < G.count && walks[mem[S.first_open]].state == W_DONE) ++S.first_open;
-                for (uint32_t q = S.first_open; q < G.count; ++q) {
-                    uint32_t const wi = mem[q];
-                    Walk& wk = walks[wi];
-                    if (wk.state != W_WAITING) continue;
-                    bool skip = false, blocked = false;
-                    // verified_intervals::contains over the windows inserted by EARLIER anchors (intervals.cpp:94-127)
-                    for (uint32_t ins : S.inserted) {
-                        if (ins < wi && walks[ins].r_start <= wk.t_start && walks[ins].r_end >= wk.t_end) { skip = true; break; }
-                    }
-                    if (!skip) {
-                        for (uint32_t e = S.first_open; e < q; ++e) {
-                            Walk const& u = walks[mem[e]];
-                            if (u.state != W_DONE && u.r_start <= wk.t_start && u.r_end >= wk.t_end) { blocked = true; break; }
-                        }
-                    }
-                    if (skip) {                                  // root_was_already_verified, verification.cpp:119-136
-                        out.stats.n_avoided_root++; out.stats.sum_avoided_root += wk.root_span.length;
-                        wk.state = W_DONE; ++n_done;
-                    } else if (!blocked) {
-                        wk.state = W_WALKING; active.push_back(wi);
-                    }
-                }
-            }
-        }
-        if (active.empty()) {
-            if (n_done < n_walks) { out.rc = fail(w.err, FXG_ERR_STATE, "internal: verification scheduler stalled"); return; }
-            break;
-        }
-        g_prof.lap(w, 1);
-        // ---- one DP pass per active walk ----
-        passes.clear(); pass_walk.clear(); no_pass.clear(); next_active.clear();
-        root_passes.clear(); root_walk.clear(); root_k.clear();
+        active.swap(level[size_t(cur_level)]);
+        level[size_t(cur_level)].clear();
+        if (active.empty()) continue;
+        passes.clear(); pass_walk.clear();
+        std::vector<uint32_t>& up = level[size_t(cur_level) - 1];
         for (uint32_t wi : active) {
             Walk& wk = walks[wi];
             fxg_anchor const& A = J->anchors_p[wk.anchor];
-            bool const is_root = wk.node->parent_id == FXG_NULL_ID;
-            Span sp;
-            fxg_read const& R = J->reads_p[wk.read];
-            const fxg_pex_node* leaves = J->nodes_p + R.node_offset + R.num_inner;
-            if (is_root) {
-                if (!wk.have_root_span) {
-                    wk.root_span = compute_span(A.reference_position, *wk.node, leaves[A.pex_leaf_index].query_index_from, c->refs.len[A.reference_id],
-                                                J->cfg.extra_verification_ratio);
-                    wk.have_root_span = true;
-                }
-                sp = wk.root_span;
-            } else {
-                sp = compute_span(A.reference_position, *wk.node, leaves[A.pex_leaf_index].query_index_from, c->refs.len[A.reference_id], 0.0);
-            }
+            Span const sp = span_of(wk, false);
             uint32_t const m = uint32_t(wk.node->query_index_to - wk.node->query_index_from + 1);
-            uint32_t const flags = (is_root && J->cfg.without_cigar) ? kFlagReverse : 0u;
             uint64_t const qbase = (wk.orient ? J->pool_len : 0) + J->reads_p[wk.read].query_offset + wk.node->query_index_from;
-            // statistics, verification.cpp:238-242
-            if (is_root) { out.stats.n_aligned_root++; out.stats.sum_aligned_root += sp.length; out.stats.cells_root += uint64_t(m) * sp.length; }
-            else { out.stats.n_aligned_inner++; out.stats.sum_aligned_inner += sp.length; out.stats.cells_inner += uint64_t(m) * sp.length; }
+            // statistics, verification.cpp:238-242 (kept per walk: with the interval optimisation the walk may turn out not to count)
+            wk.n_inner++; wk.sum_inner += sp.length; wk.cells_inner += uint64_t(m) * sp.length;
             Pass p;
-            if (score_pass_for(c->refs.base[A.reference_id] + sp.offset, qbase, uint32_t(sp.length), m, uint32_t(wk.node->num_errors), flags, p)) {
-                if (is_root && !J->cfg.without_cigar) { root_passes.push_back(p); root_walk.push_back(wi); root_k.push_back(uint32_t(wk.node->num_errors)); }
-                else { passes.push_back(p); pass_walk.push_back(wi); }
+            if (score_pass_for(c->refs.base[A.reference_id] + sp.offset, qbase, uint32_t(sp.length), m, uint32_t(wk.node->num_errors), 0u, p)) {
+                passes.push_back(p); pass_walk.push_back(wi);
             } else {
-                no_pass.emplace_back(wi, is_root);
+                wk.state = W_DONE;                       // more insertions needed than errors allowed: no alignment
             }
         }
         g_prof.lap(w, 2);
-        if (gate) {
-            // the query pools and their Peq planes are being uploaded by the caller's thread: order this worker's stream behind them
-            if (gate->wait() != FXG_OK) { out.rc = gate->rc; w.err = gate->err; return; }
-            if (cudaStreamWaitEvent(w.stream, c->ev_staged, 0) != cudaSuccess) { out.rc = fail(w.err, FXG_ERR_CUDA, "cannot order the worker behind the upload"); return; }
-            gate = nullptr;
-        }
+        if (g_prof.on && w.id == 0 && std::getenv("FXG_TRACE_WAVES"))
+            fprintf(stderr, "[fxg] level %d: %zu walks, %zu passes\n", cur_level, active.size(), passes.size());
+        if (!pass_through_gate()) return;
         const DpResult* res = nullptr;
         out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
         if (out.rc != FXG_OK) return;
         w.ctr.waves++;
         g_prof.start(w);
-        auto finish = [&](uint32_t wi, bool is_root, bool exists, DpResult const* r, RootOut const* ro) {
-            Walk& wk = walks[wi];
-            if (is_root) {
-                // verified_intervals.insert, verification.cpp:106-109 / :40-41 (also when the root alignment failed)
-                if (ivopt) gstate[wk.group].inserted.push_back(wi);
-                if (exists) {
-                    wk.hit = true; wk.num_errors = uint32_t(r->score);
-                    if (J->cfg.without_cigar) wk.start_in_reference = wk.root_span.offset + (wk.root_span.length - r->end_col);
-                    else {
-                        wk.start_in_reference = wk.root_span.offset + ro->begin_col;               // alignment.cpp:175
-                        wk.cigar_offset = ro->cigar_offset; wk.cigar_len = ro->cigar_len;          // relative to this part's region for now
-                    }
-                }
-                wk.state = W_DONE; ++n_done;
-            } else if (exists) {
+        for (size_t q = 0; q < passes.size(); ++q) {
+            Walk& wk = walks[pass_walk[q]];
+            if (res[q].score <= int32_t(wk.node->num_errors)) {
                 fxg_read const& R = J->reads_p[wk.read];
                 wk.node = &J->nodes_p[R.node_offset + wk.node->parent_id];      // pex_tree::get_parent_of_child, pex.cpp:70-76
-                next_active.push_back(wi);
+                up.push_back(pass_walk[q]);                                      // joins the walks that start one level up
             } else {
-                wk.state = W_DONE; ++n_done;
+                wk.state = W_DONE;
             }
-        };
-        for (size_t q = 0; q < passes.size(); ++q) {
-            Walk const& wk = walks[pass_walk[q]];
-            bool const is_root = wk.node->parent_id == FXG_NULL_ID;
-            bool const exists = res[q].score <= int32_t(wk.node->num_errors);
-            finish(pass_walk[q], is_root, exists, &res[q], nullptr);
         }
-        // root alignments with CIGAR: score pass with checkpoints, then the traceback of the accepted ones
-        // (after the loop above: `res` lives in the worker's staging memory, which the next passes reuse)
-        out.rc = run_root_passes(c, w, J->pool, root_passes, root_k, P.trace_budget, root_outs);
-        if (out.rc != FXG_OK) return;
-        for (size_t q = 0; q < root_passes.size(); ++q) {
-            DpResult const r{root_outs[q].score, root_outs[q].end_col};
-            finish(root_walk[q], true, r.score <= int32_t(root_k[q]), &r, &root_outs[q]);
-        }
-        for (auto const& np : no_pass) finish(np.first, np.second, false, nullptr, nullptr);
-        if (!ivopt) {
-            // survivors moved one level up: they join the walks that start there
-            active.clear();
-            if (!next_active.empty()) {
-                if (cur_level == 0) { out.rc = fail(w.err, FXG_ERR_STATE, "internal: a walk survived above the root"); return; }
-                std::vector<uint32_t>& up = level[size_t(cur_level) - 1];
-                up.insert(up.end(), next_active.begin(), next_active.end());
-            }
-            --cur_level;
-        } else {
-            active.swap(next_active);
-        }
+        active.clear();
         g_prof.lap(w, 9);
+    }
+
+    // ---------------- 2. which walks count, and which of them verify their root ----------------
+    g_prof.start(w);
+    std::vector<uint32_t> roots;                         // walks standing at the root that count, in walk order
+    if (!ivopt) {
+        roots.swap(level[0]);
+        std::sort(roots.begin(), roots.end());
+        for (Walk const& wk : walks) { out.stats.n_aligned_inner += wk.n_inner; out.stats.sum_aligned_inner += wk.sum_inner; out.stats.cells_inner += wk.cells_inner; }
+    } else {
+        std::vector<uint8_t> at_root(n_walks, 0);
+        for (uint32_t wi : level[0]) at_root[wi] = 1;
+        std::vector<uint32_t> inserted;
+        for (Group const& G : groups) {
+            inserted.clear();
+            const uint32_t* mem = group_members.data() + G.first;
+            for (uint32_t q = 0; q < G.count; ++q) {
+                uint32_t const wi = mem[q];
+                Walk& wk = walks[wi];
+                bool avoided = false;
+                // verified_intervals::contains over the windows inserted by earlier anchors (intervals.cpp:94-127)
+                for (uint32_t ins : inserted)
+                    if (walks[ins].r_start <= wk.t_start && walks[ins].r_end >= wk.t_end) { avoided = true; break; }
+                if (avoided) {                               // root_was_already_verified, verification.cpp:119-136
+                    out.stats.n_avoided_root++; out.stats.sum_avoided_root += wk.root_span.length;
+                    wk.state = W_DONE;
+                    continue;
+                }
+                out.stats.n_aligned_inner += wk.n_inner; out.stats.sum_aligned_inner += wk.sum_inner; out.stats.cells_inner += wk.cells_inner;
+                if (at_root[wi]) { inserted.push_back(wi); roots.push_back(wi); }      // verified_intervals.insert, verification.cpp:106-109 / :40-41
+            }
+        }
+        std::sort(roots.begin(), roots.end());
+    }
+    g_prof.lap(w, 1);
+
+    // ---------------- 3. root level ----------------
+    g_prof.start(w);
+    passes.clear(); pass_walk.clear();
+    std::vector<uint32_t> root_k;
+    bool const want_cigar = !J->cfg.without_cigar;
+    for (uint32_t wi : roots) {
+        Walk& wk = walks[wi];
+        fxg_anchor const& A = J->anchors_p[wk.anchor];
+        Span const sp = span_of(wk, true);
+        uint32_t const m = uint32_t(wk.node->query_index_to - wk.node->query_index_from + 1);
+        uint64_t const qbase = (wk.orient ? J->pool_len : 0) + J->reads_p[wk.read].query_offset + wk.node->query_index_from;
+        out.stats.n_aligned_root++; out.stats.sum_aligned_root += sp.length; out.stats.cells_root += uint64_t(m) * sp.length;
+        Pass p;
+        if (score_pass_for(c->refs.base[A.reference_id] + sp.offset, qbase, uint32_t(sp.length), m, uint32_t(wk.node->num_errors),
+                           want_cigar ? 0u : kFlagReverse, p)) {
+            passes.push_back(p); pass_walk.push_back(wi); root_k.push_back(uint32_t(wk.node->num_errors));
+        }
+        wk.state = W_DONE;
+    }
+    g_prof.lap(w, 2);
+    if (g_prof.on && w.id == 0 && std::getenv("FXG_TRACE_WAVES")) fprintf(stderr, "[fxg] root level: %zu walks, %zu passes\n", roots.size(), passes.size());
+    if (!passes.empty()) {
+        if (!pass_through_gate()) return;
+        if (want_cigar) {
+            // score pass with checkpoints, then the traceback of the accepted ones
+            std::vector<RootOut> root_outs;
+            out.rc = run_root_passes(c, w, J->pool, passes, root_k, P.trace_budget, root_outs);
+            if (out.rc != FXG_OK) return;
+            for (size_t q = 0; q < passes.size(); ++q) {
+                if (root_outs[q].score > int32_t(root_k[q])) continue;
+                Walk& wk = walks[pass_walk[q]];
+                wk.hit = true; wk.num_errors = uint32_t(root_outs[q].score);
+                wk.start_in_reference = wk.root_span.offset + root_outs[q].begin_col;                 // alignment.cpp:175
+                wk.cigar_offset = root_outs[q].cigar_offset; wk.cigar_len = root_outs[q].cigar_len;    // relative to this part's region for now
+            }
+        } else {
+            const DpResult* res = nullptr;
+            out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
+            if (out.rc != FXG_OK) return;
+            for (size_t q = 0; q < passes.size(); ++q) {
+                if (res[q].score > int32_t(root_k[q])) continue;
+                Walk& wk = walks[pass_walk[q]];
+                wk.hit = true; wk.num_errors = uint32_t(res[q].score);
+                wk.start_in_reference = wk.root_span.offset + (wk.root_span.length - res[q].end_col);   // alignment.cpp:135-139
+            }
+        }
+        w.ctr.waves++;
     }
 }
 
