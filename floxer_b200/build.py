@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("floxer_gpu.cu", "pex_tree.cpp")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("floxer_gpu.cu", "pex_tree.cpp", "sam_output.cpp")]
 HEADERS = [os.path.join(HERE, "csrc", "dp_kernels.cuh"), os.path.join(os.path.dirname(HERE), "include", "floxer_gpu.h")]
 OUTPUT = os.path.join(HERE, "libfloxer_gpu.so")
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "fxg_verify_stage", "fxg_verify_run", "fxg_job_num_alignments", "fxg_job_alignments", "fxg_job_cigar_len",
     "fxg_job_cigar_pool", "fxg_job_stats", "fxg_job_free", "fxg_verify_reads",
     "fxg_get_counters", "fxg_reset_counters", "fxg_measure_int32_peak",
-    "fxg_pex_build", "fxg_pex_free",
+    "fxg_pex_build", "fxg_pex_free", "fxg_job_write_sam", "fxg_free",
 ]
 
 _lib = None
@@ -76,6 +76,9 @@ def lib() -> C.CDLL:
                                 C.POINTER(vp), C.POINTER(sz)]
     L.fxg_pex_free.argtypes = [vp]
     L.fxg_pex_free.restype = None
+    L.fxg_job_write_sam.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+    L.fxg_free.argtypes = [vp]
+    L.fxg_free.restype = None
     _lib = L
     return L
 
@@ -132,6 +135,29 @@ class Job:
 
     def stats(self) -> dict:
         return lib().fxg_job_stats(self._h).contents.as_dict()
+
+    def sam(self, batch: ReadBatch, reference_ids, reference_lengths, query_ids, qualities=None, header: bool = True) -> str:
+        """SAM text of the job's alignments (output::alignment_output::write_alignments_for_query, src/lib/output.cpp:49-108)."""
+        L = lib()
+        n_ref, n = len(reference_ids), len(batch.reads)
+        ref_ids = (C.c_char_p * max(n_ref, 1))(*[r.encode() for r in reference_ids])
+        ref_lens = (C.c_uint64 * max(n_ref, 1))(*[int(x) for x in reference_lengths])
+
+        class SamQuery(C.Structure):
+            _fields_ = [("id", C.c_char_p), ("quality", C.c_char_p)]
+        qs = (SamQuery * max(n, 1))()
+        for i in range(n):
+            qs[i].id = query_ids[i].encode()
+            qs[i].quality = (qualities[i] if qualities is not None else "").encode()
+        text, length = C.c_void_p(), C.c_size_t(0)
+        rc = L.fxg_job_write_sam(self._h, n_ref, ref_ids, ref_lens, batch.reads.ctypes.data, n, batch.forward_pool.ctypes.data,
+                                 qs, int(header), C.byref(text), C.byref(length))
+        if rc != 0:
+            raise FloxerGpuError(rc, "fxg_job_write_sam failed")
+        try:
+            return C.string_at(text, length.value).decode()
+        finally:
+            L.fxg_free(text)
 
     def free(self):
         if self._h:

@@ -196,6 +196,17 @@ int fxg_pex_build(uint64_t total_query_length, uint64_t query_num_errors, uint64
                   int build_strategy, fxg_pex_node** inner, size_t* n_inner, fxg_pex_node** leaves, size_t* n_leaves);
 void fxg_pex_free(fxg_pex_node* nodes);
 
+/* ---- SAM records for a verified job (host only; row N3 of the scope table) ----
+ * Replaces output::alignment_output::write_alignments_for_query (src/lib/output.cpp:49-108) for every read of the job,
+ * plus the @HD / @SQ header (src/lib/output.cpp:197-212).  `reads` / `forward_pool` are the arrays the job was made
+ * from, `queries[i]` holds the id and the quality string of read i (input::query_record, include/input.hpp:22-28).
+ * Writes a malloc'ed, NUL-terminated buffer; release it with fxg_free. */
+typedef struct { const char* id; const char* quality; } fxg_sam_query;
+int fxg_job_write_sam(const fxg_job* job, size_t n_references, const char* const* reference_ids, const uint64_t* reference_lengths,
+                      const fxg_read* reads, size_t n_reads, const uint8_t* forward_pool, const fxg_sam_query* queries,
+                      int with_header, char** text, size_t* text_len);
+void fxg_free(void* p);
+
 /* ---- accounting / measurement helpers ---- */
 int fxg_get_counters(const fxg_ctx* ctx, fxg_counters* out);
 int fxg_reset_counters(fxg_ctx* ctx);

@@ -183,3 +183,27 @@ def test_which_tie_breaks_the_golden_vectors_admit(oracle):
     admitted = sorted(p for (p, rm), g in ok.items() if g and rm)
     assert admitted == ["LUD", "UDL", "ULD"]
     assert not any(g for (p, rm), g in ok.items() if not rm)
+
+
+@pytest.mark.parametrize("seed_errors", G.WHOLE_FLAGS["seed_errors"])
+def test_whole_program_fixture_sam_records(oracle, seed_errors):
+    """The restatement of output.cpp:49-108 (oracle/sam_oracle.py) on the oracle's alignments gives the records that
+    test/floxer_whole_program_via_cli_test.cpp:38-93 reads back: unmapped flag for query1/6, every query mentioned,
+    one primary record per mapped query carrying SEQ, secondaries flagged 256 with SEQ '*'."""
+    from oracle import sam_oracle
+    records = _whole_program(oracle, seed_errors)
+    ref_ids = list(G.WHOLE_REFERENCES)
+    seen = set()
+    for qid, seq in G.WHOLE_QUERIES.items():
+        recs = sam_oracle.sam_records(qid, to_ranks(seq), "I" * len(seq), records[qid], ref_ids)
+        seen.add(qid)
+        if qid in G.WHOLE_UNMAPPED:
+            assert [r[1] for r in recs] == [4] and recs[0][2] == "*" and recs[0][6] == seq.upper()
+            continue
+        assert sum(1 for r in recs if not r[1] & 256) == 1
+        for qname, flag, rname, pos1, mapq, cigar, s, q, nm in recs:
+            lo, hi, want_nm, want_cigar = G.WHOLE_EXPECT[(qid, bool(flag & 16))]
+            assert not flag & 4 and mapq == 255 and rname == ref_ids[0]
+            assert lo <= pos1 - 1 <= hi and nm == want_nm and cigar == want_cigar
+            assert (s == "*") == bool(flag & 256)
+    assert seen == set(G.WHOLE_QUERIES)
