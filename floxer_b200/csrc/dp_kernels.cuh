@@ -460,10 +460,11 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     auto set_block = [&](uint32_t blk) {
         S.cs = 0x7fffffff; S.ce = -1;
         if (!have_task || blk >= nb) return;
-        int64_t const lo = int64_t(ROWS) * blk + 1 + dlo;
-        int64_t const hi = int64_t(ROWS) * (blk + 1) + dhi;
-        int32_t const cs = lo < 1 ? 1 : (lo > 0x7ffffffe ? 0x7fffffff : int32_t(lo));
-        int32_t const ce = hi > int64_t(T.n) ? int32_t(T.n) : int32_t(hi);
+        // (all quantities are far below 2^31: queries are at most FXG_MAX_QUERY_LENGTH long)
+        int32_t const lo = int32_t(ROWS) * int32_t(blk) + 1 + dlo;
+        int32_t const hi = int32_t(ROWS) * int32_t(blk + 1) + dhi;
+        int32_t const cs = lo < 1 ? 1 : lo;
+        int32_t const ce = hi > int32_t(T.n) ? int32_t(T.n) : hi;
         if (cs <= ce) { S.cs = cs; S.ce = ce; }
     };
     set_block(S.b);
@@ -473,6 +474,7 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     uint32_t const my_end = __reduce_max_sync(0xffffffffu, have_task ? (T.n + nb - 1) : 0u);
     constexpr uint32_t kNever = 0x7fffffffu;
 
+    uint32_t my_refill = 0;                                    // first step that would read past this ring's window buffer (0: not planned yet)
     uint32_t t = 1;
     while (t <= my_end) {
         // ---------------- between steps t-1 and t: blocks that ended move on, blocks that begin are set up ----------------
@@ -519,39 +521,43 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
         // Computed from the band geometry alone, identically by every lane of the ring (no voting):
         //   b_top = first block that has not ended yet (it reads furthest ahead: ce(b) + b grows with b),
         //   b_low = last block that has begun (blocks that begin later start at or beyond its position).
-        uint32_t my_refill = kNever;
-        uint32_t new_base = c_base;
-        uint32_t i_hi = 0;
-        bool reading = false;
-        if (have_task && !dead) {
-            // (all quantities are far below 2^31: n, m <= a few 100 000)
-            int32_t const ti = int32_t(t);
-            int32_t const e1 = ti - int32_t(T.n);                                               // n + b >= t
-            int32_t const e2n = ti - dhi - ROWS;                                                // ROWS (b+1) + dhi + b >= t
-            int32_t const e2 = e2n > 0 ? (e2n + ROWS) / (ROWS + 1) : 0;
-            int32_t const b_top = e1 > e2 ? e1 : e2;
-            int32_t const s1 = ti - 1 - dlo;                                                    // ROWS b + 1 + dlo + b <= t
-            int32_t b_low = s1 > 0 ? s1 / (ROWS + 1) : 0;
-            if (b_low > ti - 1) b_low = ti - 1;                                                 // blocks clipped to column 1 begin at step 1 + b
-            if (b_low > int32_t(last_block)) b_low = int32_t(last_block);
-            reading = b_top <= int32_t(last_block);
-            if (reading) {
-                i_hi = uint32_t(int32_t(phase) + ti + 1 - b_top);                               // buffer position of the furthest read of step t
-                if (i_hi >= 32 * (c_base + kWinChunks)) {
-                    int32_t const lo = ti - 3 - b_low;                                          // everything before it is done with
-                    new_base = uint32_t(int32_t(phase) + (lo > 0 ? lo : 0)) >> 5;
-                    if (new_base <= c_base || i_hi >= 32 * (new_base + kWinChunks)) { dead = true; new_base = c_base; }   // cannot happen: a ring spans < 40 characters
+        // (looked at only when some ring's buffer runs out with this step: until then the step computed at the last
+        //  look stays valid -- the first unfinished block only moves down, so reads never reach further ahead than planned)
+        if (__any_sync(0xffffffffu, t >= my_refill)) {
+            my_refill = kNever;
+            uint32_t new_base = c_base;
+            uint32_t i_hi = 0;
+            bool reading = false;
+            if (have_task && !dead) {
+                // (all quantities are far below 2^31: n, m <= a few 100 000)
+                int32_t const ti = int32_t(t);
+                int32_t const e1 = ti - int32_t(T.n);                                               // n + b >= t
+                int32_t const e2n = ti - dhi - ROWS;                                                // ROWS (b+1) + dhi + b >= t
+                int32_t const e2 = e2n > 0 ? (e2n + ROWS) / (ROWS + 1) : 0;
+                int32_t const b_top = e1 > e2 ? e1 : e2;
+                int32_t const s1 = ti - 1 - dlo;                                                    // ROWS b + 1 + dlo + b <= t
+                int32_t b_low = s1 > 0 ? s1 / (ROWS + 1) : 0;
+                if (b_low > ti - 1) b_low = ti - 1;                                                 // blocks clipped to column 1 begin at step 1 + b
+                if (b_low > int32_t(last_block)) b_low = int32_t(last_block);
+                reading = b_top <= int32_t(last_block);
+                if (reading) {
+                    i_hi = uint32_t(int32_t(phase) + ti + 1 - b_top);                               // buffer position of the furthest read of step t
+                    if (i_hi >= 32 * (c_base + kWinChunks)) {
+                        int32_t const lo = ti - 3 - b_low;                                          // everything before it is done with
+                        new_base = uint32_t(int32_t(phase) + (lo > 0 ? lo : 0)) >> 5;
+                        if (new_base <= c_base || i_hi >= 32 * (new_base + kWinChunks)) { dead = true; new_base = c_base; }   // cannot happen: a ring spans < 40 characters
+                    }
                 }
             }
+            // the refill itself in warp-uniform control flow (the hot loops below rely on a converged warp)
+            uint32_t const rounds = __reduce_max_sync(0xffffffffu, (new_base - c_base + G - 1) / G);
+            for (uint32_t k = 0; k < rounds; ++k) {
+                uint32_t const c = c_base + kWinChunks + r + k * G;
+                if (c < new_base + kWinChunks) load_window_chunk(packed, store_chunks, first_chunk, reverse, c, win);
+            }
+            c_base = new_base;
+            if (reading && !dead) my_refill = t + (32 * (c_base + kWinChunks) - i_hi);              // first step that would read past the buffer
         }
-        // the refill itself in warp-uniform control flow (the hot loops below rely on a converged warp)
-        uint32_t const rounds = __reduce_max_sync(0xffffffffu, (new_base - c_base + G - 1) / G);
-        for (uint32_t k = 0; k < rounds; ++k) {
-            uint32_t const c = c_base + kWinChunks + r + k * G;
-            if (c < new_base + kWinChunks) load_window_chunk(packed, store_chunks, first_chunk, reverse, c, win);
-        }
-        c_base = new_base;
-        if (reading && !dead) my_refill = t + (32 * (c_base + kWinChunks) - i_hi);              // first step that would read past the buffer
         __syncwarp();
         // character of column j is win0[j - 1]: chunk c lives at slot c % kWinChunks (and kWinChunks above it)
         uint8_t const* const win0 = win + phase - 32 * kWinChunks * (c_base / kWinChunks);
