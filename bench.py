@@ -109,12 +109,13 @@ def cpu_arm(refs, batch, cfg, sample_reads: int, threads: int, repeats: int = 1)
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--interval-optimization", action="store_true", help="floxer --interval-optimization (off by default, as in the reference)")
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU sample (0 = sized automatically)")
+    ap.add_argument("--pipeline", type=int, default=4, help="batches in flight per GPU (1..4): the library serves up to four *_run calls at a time")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -130,7 +131,8 @@ def main() -> int:
                           f"hierarchical verification, interval optimization {'on' if cfg.interval_optimization else 'off'}, "
                           f"extra verification ratio 0.05, CIGAR output; anchors from the ground-truth stand-in seeder",
               "reads_per_gpu": W["reads"], "read_len": W["read_len"], "error_rate": W["error"],
-              "l2": "L2 flushed (256 MiB write) before every timed step"}
+              "l2": "256 MiB written to HBM between steps (each step also streams 1.5 GB of checkpoint records, 12x the L2)",
+              "batches_in_flight": max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "4"))))}
 
     # ------------------------------------------------------------------ CPU arm ("reference")
     if args.impl == "reference":
@@ -198,63 +200,98 @@ def main() -> int:
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident arm: inputs staged once, each step = fxg_verify_run ----
-    job = ctx.stage_verify(batch, cfg)
-    for _ in range(args.warmup):
-        job.run()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    step_ms, kernel_ms, launches = [], [], 0
-    ctr0 = None
-    barrier()
-    ctx.reset_counters()
-    t_all0 = time.perf_counter()
-    for it in range(args.steps):
+    depth = max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "4"))))
+
+    def run_lanes(step_fns, n_steps):
+        """n_steps steps, dealt round-robin to len(step_fns) host threads (batches in flight); returns wall seconds."""
+        counts = [n_steps // len(step_fns) + (1 if i < n_steps % len(step_fns) else 0) for i in range(len(step_fns))]
+        errors = []
+
+        def lane(i):
+            try:
+                for _ in range(counts[i]):
+                    step_fns[i]()
+            except Exception as e:                       # noqa: BLE001 -- re-raised by the main thread
+                errors.append(e)
+        threads = [threading.Thread(target=lane, args=(i,)) for i in range(len(step_fns))]
+        t0 = time.perf_counter()
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        dt = time.perf_counter() - t0
+        if errors:
+            raise errors[0]
+        return dt
+
+    # ---- device-resident arm: inputs staged once (one staged copy per batch in flight), each step = fxg_verify_run ----
+    jobs = [ctx.stage_verify(batch, cfg) for _ in range(depth)]
+    run_lanes([j.run for j in jobs], args.warmup * depth)    # both worker groups warm (their buffers are allocated on first use)
+
+    def resident_step(j):
+        def f():
+            flush.fill_(1)                               # 256 MiB written between steps (queued on torch's stream, no host sync)
+            j.run()
+        return f
+    # one step at a time first: the latency of a step, and its device time between the run's first and last operation
+    lat_ms, kernel_ms = [], []
+    for it in range(3):
         flush.fill_(it & 0xff)
         torch.cuda.synchronize()
         c0 = ctx.counters()
         t0 = time.perf_counter()
-        job.run()
-        step_ms.append((time.perf_counter() - t0) * 1e3)
-        c1 = ctx.counters()
-        kernel_ms.append(c1["run_ms"] - c0["run_ms"])
+        jobs[0].run()
+        lat_ms.append((time.perf_counter() - t0) * 1e3)
+        kernel_ms.append(ctx.counters()["run_ms"] - c0["run_ms"])
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     barrier()
-    _ = time.perf_counter() - t_all0
+    ctx.reset_counters()
+    total_s = run_lanes([resident_step(j) for j in jobs], args.steps)
+    barrier()
+    step_ms = [total_s * 1e3 / args.steps] * args.steps
     ctr = ctx.counters()
     clocks = sampler.stop()
-    stats = job.stats()
-    al, cg = job.alignments()
+    stats = jobs[0].stats()
+    al, cg = jobs[0].alignments()
     n_alignments = len(al)
-    job.free()
+    for j in jobs:
+        j.free()
 
     # ---- end-to-end arm: host buffers in, alignments + CIGARs out, every step ----
-    e2e_ms = []
-    checksum = 0
-    n_e2e_steps = max(1, min(args.steps, 5))
-    for it in range(1 + n_e2e_steps):                    # the first pass is warm-up (page-locked pools are allocated once)
-        if it == 1:
-            ctx.reset_counters()
-        flush.fill_(it & 0xff)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        j2 = ctx.verify_reads(batch, cfg)                # host buffers in: H2D, all waves, tracebacks, D2H of alignments + CIGARs
-        a2, c2 = j2.alignments(copy=False)               # what a C caller reads: the job's own result arrays
-        checksum ^= int(a2["start_in_reference"].sum()) ^ int(a2["num_errors"].sum()) ^ len(c2)
-        dt = (time.perf_counter() - t0) * 1e3
-        if it:
-            e2e_ms.append(dt)
-        del a2, c2
-        j2.free()
+    checksum = [0] * depth
+
+    def e2e_step(i):
+        def f():
+            flush.fill_(2)
+            j2 = ctx.verify_reads(batch, cfg)            # host buffers in: H2D, all waves, tracebacks, D2H of alignments + CIGARs
+            a2, c2 = j2.alignments(copy=False)           # what a C caller reads: the job's own result arrays
+            checksum[i] ^= int(a2["start_in_reference"].sum()) ^ int(a2["num_errors"].sum()) ^ len(c2)
+            del a2, c2
+            j2.free()
+        return f
+    run_lanes([e2e_step(i) for i in range(depth)], 2 * depth)   # warm-up (page-locked pools are allocated once)
+    torch.cuda.synchronize()
+    ctx.reset_counters()
+    n_e2e = max(depth, min(args.steps, 6))
+    e2e_s = run_lanes([e2e_step(i) for i in range(depth)], n_e2e)
+    torch.cuda.synchronize()
+    e2e_ms = [e2e_s * 1e3 / n_e2e] * n_e2e
     e2e_ctr = ctx.counters()
-    n_e2e = len(e2e_ms)
 
     # ---- roofline pass (rank 0): one host worker / one stream, so that kernels do not overlap and the
     #      CUDA-event time of the DP launches is the time of those launches alone ----
     roof_ctr = None
     if rank == 0:
+        saved_env = {k: os.environ.get(k) for k in ("FXG_WORKERS", "FXG_GROUPS")}
         os.environ["FXG_WORKERS"] = "1"
+        os.environ["FXG_GROUPS"] = "1"
         ctx1 = g.Context(local_rank)
-        os.environ.pop("FXG_WORKERS", None)
+        for k, v in saved_env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
         ctx1.set_references(refs)
         job1 = ctx1.stage_verify(batch, cfg)
         job1.run()
@@ -332,8 +369,8 @@ def main() -> int:
                 "cpu_baseline": {"value": cpu_cells / cpu_sec / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
                                  "sample": f"first {n_used} reads of rank 0's batch, all anchors, both strands, CIGARs",
                                  "reads_per_s": n_used / cpu_sec},
-                "device_ms_per_step": dev_ms / args.steps, "step_ms": [round(x, 3) for x in step_ms],
-                "e2e_step_ms": [round(x, 3) for x in e2e_ms], "host_workers": len(os.sched_getaffinity(0)),
+                "step_latency_ms": [round(x, 3) for x in lat_ms], "step_latency_device_ms": [round(x, 3) for x in kernel_ms],
+                "host_cores": len(os.sched_getaffinity(0)),
                 "waves_per_step": ctr["waves"] / args.steps,
                 "alignments_per_step": n_alignments,
                 "stats_per_step": stats}

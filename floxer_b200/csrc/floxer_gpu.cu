@@ -112,8 +112,10 @@ struct Config { uint8_t widx; uint8_t G; uint32_t nb; uint64_t word_steps; };
 struct ConfigCacheEntry { uint32_t n, m; int32_t dlo, dhi; Config cfg; bool ok; bool valid; };
 
 // Everything one host worker needs to run passes on its own stream.
+struct WorkerGroup;
 struct Worker {
     int id = 0;
+    WorkerGroup* group = nullptr;
     cudaStream_t stream = nullptr;
     static constexpr int kSide = 3;      // the launches of one wave are independent: the smaller ones run beside the largest
     cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
@@ -158,6 +160,14 @@ struct Worker {
     }
 };
 
+// The workers that serve one *_run call.  A context has two groups, so that two batches can be in flight: the host-side
+// preparation and the latency-bound tracebacks of one batch hide behind the score passes of the other.
+struct WorkerGroup {
+    std::vector<std::unique_ptr<Worker>> workers;
+    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr, ev_staged = nullptr;
+    bool busy = false;
+};
+
 // host-side phase timing, printed when FXG_PROFILE is set (development aid; worker 0 only)
 struct HostProf {
     bool on = std::getenv("FXG_PROFILE") != nullptr;
@@ -190,8 +200,11 @@ struct fxg_ctx {
     fxg_counters ctr{};
     int num_sms = 0;
     size_t smem_limit = 0;
-    std::vector<std::unique_ptr<Worker>> workers;
-    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr, ev_staged = nullptr;
+    static constexpr int kMaxGroups = 4;
+    int n_groups = 4;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
+    WorkerGroup groups[kMaxGroups];
+    cudaStream_t stage_stream = nullptr; // uploads of references / query pools, Peq construction
+    std::condition_variable group_free;
     DevBuf d_tmp;
     uint64_t trace_budget = 0;
     int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
@@ -276,16 +289,25 @@ void add_counters(fxg_counters& a, fxg_counters const& b) {
     a.trace_word_steps += b.trace_word_steps; a.dp_kernel_ms += b.dp_kernel_ms; a.trace_kernel_ms += b.trace_kernel_ms; a.waves += b.waves; a.run_ms += b.run_ms;
 }
 
-// brackets a *_run call with events on worker 0's stream (the stream the first kernels are launched on)
+// brackets a *_run call with events on the stream of the group's first worker (the first kernels are launched there)
 struct RunTimer {
-    fxg_ctx* c;
-    explicit RunTimer(fxg_ctx* ctx) : c(ctx) { cudaEventRecord(c->ev_run0, c->workers[0]->stream); }
+    WorkerGroup& g; fxg_counters& ctr;
+    RunTimer(WorkerGroup& group, fxg_counters& counters) : g(group), ctr(counters) { cudaEventRecord(g.ev_run0, g.workers[0]->stream); }
     ~RunTimer() {
-        if (cudaEventRecord(c->ev_run1, c->workers[0]->stream) != cudaSuccess || cudaEventSynchronize(c->ev_run1) != cudaSuccess) return;
+        if (cudaEventRecord(g.ev_run1, g.workers[0]->stream) != cudaSuccess || cudaEventSynchronize(g.ev_run1) != cudaSuccess) return;
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, c->ev_run0, c->ev_run1) == cudaSuccess) c->ctr.run_ms += ms;
+        if (cudaEventElapsedTime(&ms, g.ev_run0, g.ev_run1) == cudaSuccess) ctr.run_ms += ms;
     }
 };
+
+// a free worker group, waiting for one if both are busy; call with c->mu held through `lock`
+WorkerGroup& acquire_group(fxg_ctx* c, std::unique_lock<std::mutex>& lock) {
+    for (;;) {
+        for (int i = 0; i < c->n_groups; ++i) if (!c->groups[i].busy) { c->groups[i].busy = true; return c->groups[i]; }
+        c->group_free.wait(lock);
+    }
+}
+void release_group(fxg_ctx* c, WorkerGroup& g) { g.busy = false; c->group_free.notify_one(); }
 
 int env_int(const char* name, int dflt, int lo, int hi) {
     if (const char* e = std::getenv(name)) { int const v = std::atoi(e); if (v >= lo && v <= hi) return v; }
@@ -557,6 +579,11 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     float ms = 0;
     CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
     w.ctr.dp_kernel_ms += ms;
+    if (g_prof.on && std::getenv("FXG_TRACE_WAVES")) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, w.group->ev_run0, w.ev0); cudaEventElapsedTime(&b, w.group->ev_run0, w.ev1);
+        fprintf(stderr, "[fxg] timeline worker %d %s %zu passes: device %.3f .. %.3f ms\n", w.id, trace ? "root" : "wave", N, a, b);
+    }
     if (trace) {
         // the largest launch of a root wave is the engine's dominant launch: timed on its own for the roofline
         CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev_b0, w.ev_b1));
@@ -744,12 +771,12 @@ void refresh_trace_budget(fxg_ctx* c) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(8) << 30;
     uint64_t held = 0;
-    for (auto const& w : c->workers) for (DevBuf const& b : w->d_ck) held += b.cap;
+    for (WorkerGroup const& g : c->groups) for (auto const& w : g.workers) for (DevBuf const& b : w->d_ck) held += b.cap;
     c->trace_budget = std::min<uint64_t>((uint64_t(free_b) + held) / 2, uint64_t(64) << 30);
 }
 uint64_t trace_budget_bytes(fxg_ctx* c, size_t n_parts) {
     if (c->trace_budget == 0) refresh_trace_budget(c);
-    return c->trace_budget / std::max<size_t>(n_parts, 1);
+    return c->trace_budget / (std::max<size_t>(n_parts, 1) * size_t(c->n_groups));
 }
 
 // ------------------------------------------------------------------------------------------------ pools
@@ -798,35 +825,35 @@ int check_ranks(std::string& err, const uint8_t* p, size_t n, const char* what) 
 int upload_packed(fxg_ctx* c, const uint8_t* ranks, uint64_t len, DevBuf& dst, uint64_t word_offset) {
     // pack on the device: upload bytes to a temporary, 8 bases per output word
     if (len == 0) return FXG_OK;
-    Worker& w = *c->workers[0];
+    cudaStream_t const st = c->stage_stream;
     CUDA_TRY(c->err, c->d_tmp.ensure(len));
-    CUDA_TRY(c->err, cudaMemcpyAsync(c->d_tmp.p, ranks, len, cudaMemcpyHostToDevice, w.stream));
+    CUDA_TRY(c->err, cudaMemcpyAsync(c->d_tmp.p, ranks, len, cudaMemcpyHostToDevice, st));
     c->ctr.h2d_bytes += len;
     uint64_t const n_words = (len + 7) / 8;
     uint32_t const grid = uint32_t(std::min<uint64_t>((n_words + 255) / 256, uint64_t(c->num_sms) * 16));
-    pack_nibbles_kernel<<<grid, 256, 0, w.stream>>>(c->d_tmp.as<uint8_t>(), len, dst.as<uint32_t>() + word_offset);
+    pack_nibbles_kernel<<<grid, 256, 0, st>>>(c->d_tmp.as<uint8_t>(), len, dst.as<uint32_t>() + word_offset);
     CUDA_TRY(c->err, cudaGetLastError());
     c->ctr.kernel_launches++;
-    CUDA_TRY(c->err, cudaStreamSynchronize(w.stream));
+    CUDA_TRY(c->err, cudaStreamSynchronize(st));
     return FXG_OK;
 }
 
 // uploads up to two byte ranges back to back (forward / reverse pools) and builds the Peq planes; errors and
 // accounting go to the caller's objects (fxg_verify_reads runs this beside the workers)
 int stage_pool(fxg_ctx* c, Pool& pool, const uint8_t* a, size_t a_len, const uint8_t* b, size_t b_len, std::string& err, fxg_counters& ctr) {
-    Worker& w = *c->workers[0];
+    cudaStream_t const st = c->stage_stream;
     pool.len = a_len + b_len;
     pool.plane_words = (pool.len + 31) / 32 + kPeqFrontPadWords + kPeqBackPadWords;
     CUDA_TRY(err, pool.bytes.ensure(pool.len + 64));
     CUDA_TRY(err, pool.peq.ensure(pool.plane_words * kNumSymbols * 4));
-    if (a_len) CUDA_TRY(err, cudaMemcpyAsync(pool.bytes.p, a, a_len, cudaMemcpyHostToDevice, w.stream));
-    if (b_len) CUDA_TRY(err, cudaMemcpyAsync(pool.bytes.as<uint8_t>() + a_len, b, b_len, cudaMemcpyHostToDevice, w.stream));
+    if (a_len) CUDA_TRY(err, cudaMemcpyAsync(pool.bytes.p, a, a_len, cudaMemcpyHostToDevice, st));
+    if (b_len) CUDA_TRY(err, cudaMemcpyAsync(pool.bytes.as<uint8_t>() + a_len, b, b_len, cudaMemcpyHostToDevice, st));
     ctr.h2d_bytes += pool.len;
-    CUDA_TRY(err, cudaMemsetAsync(pool.peq.p, 0, pool.plane_words * kNumSymbols * 4, w.stream));
+    CUDA_TRY(err, cudaMemsetAsync(pool.peq.p, 0, pool.plane_words * kNumSymbols * 4, st));
     if (pool.len) {
         uint64_t const n_words = (pool.len + 31) / 32;
         uint32_t const grid = uint32_t(std::min<uint64_t>((n_words + 7) / 8, uint64_t(c->num_sms) * 16));
-        build_peq_kernel<<<grid, 256, 0, w.stream>>>(pool.bytes.as<uint8_t>(), pool.len, pool.peq.as<uint32_t>(), pool.plane_words);
+        build_peq_kernel<<<grid, 256, 0, st>>>(pool.bytes.as<uint8_t>(), pool.len, pool.peq.as<uint32_t>(), pool.plane_words);
         CUDA_TRY(err, cudaGetLastError());
         ctr.kernel_launches++;
     }
@@ -1032,7 +1059,7 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
         if (!gate) return true;
         // the query pools and their Peq planes are being uploaded by the caller's thread: order this worker's stream behind them
         if (gate->wait() != FXG_OK) { out.rc = gate->rc; w.err = gate->err; return false; }
-        if (cudaStreamWaitEvent(w.stream, c->ev_staged, 0) != cudaSuccess) { out.rc = fail(w.err, FXG_ERR_CUDA, "cannot order the worker behind the upload"); return false; }
+        if (cudaStreamWaitEvent(w.stream, w.group->ev_staged, 0) != cudaSuccess) { out.rc = fail(w.err, FXG_ERR_CUDA, "cannot order the worker behind the upload"); return false; }
         gate = nullptr;
         return true;
     };
@@ -1228,10 +1255,13 @@ struct TracePlan {
     }
 };
 
-int default_workers() {
+// Host workers per group: the groups of all ranks on this host together should not oversubscribe its cores
+// (torchrun exports LOCAL_WORLD_SIZE).  FXG_WORKERS overrides.
+int default_workers(int n_groups) {
     if (const char* e = std::getenv("FXG_WORKERS")) { int v = std::atoi(e); if (v >= 1 && v <= 64) return v; }
-    unsigned const hc = std::thread::hardware_concurrency();
-    return int(std::max(1u, std::min(8u, hc / 2)));
+    unsigned const hc = std::max(1u, std::thread::hardware_concurrency());
+    int const ranks = env_int("LOCAL_WORLD_SIZE", 1, 1, 64);
+    return int(std::max(2u, std::min(8u, hc / unsigned(n_groups * ranks))));
 }
 
 }  // namespace
@@ -1255,28 +1285,32 @@ int fxg_create(int device, fxg_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return FXG_ERR_CUDA; }
     c->num_sms = prop.multiProcessorCount;
     c->smem_limit = prop.sharedMemPerBlockOptin;
-    bool ok = cudaEventCreate(&c->ev_run0) == cudaSuccess && cudaEventCreate(&c->ev_run1) == cudaSuccess &&
-              cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming) == cudaSuccess &&
-              set_all_smem_attrs(c->smem_limit) == cudaSuccess;
+    bool ok = cudaStreamCreateWithFlags(&c->stage_stream, cudaStreamNonBlocking) == cudaSuccess && set_all_smem_attrs(c->smem_limit) == cudaSuccess;
     c->root_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64);
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
-    int const nw = default_workers();
-    for (int i = 0; ok && i < nw; ++i) {
-        std::unique_ptr<Worker> w(new (std::nothrow) Worker());
-        if (!w) { ok = false; break; }
-        w->id = i;
-        ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess &&
-             cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreate(&w->ev_w0) == cudaSuccess && cudaEventCreate(&w->ev_b0) == cudaSuccess && cudaEventCreate(&w->ev_b1) == cudaSuccess;
-        for (int q = 0; ok && q < Worker::kWalkSlots; ++q)
-            ok = cudaStreamCreateWithFlags(&w->walk_stream[q], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&w->ev_walk_done[q], cudaEventDisableTiming) == cudaSuccess &&
-                 cudaEventCreate(&w->ev_w1[q]) == cudaSuccess;
-        for (int q = 0; ok && q < Worker::kSide; ++q)
-            ok = cudaStreamCreateWithFlags(&w->side[q], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&w->ev_join[q], cudaEventDisableTiming) == cudaSuccess;
-        c->workers.push_back(std::move(w));
+    c->n_groups = env_int("FXG_GROUPS", 4, 1, fxg_ctx::kMaxGroups);
+    int const nw = default_workers(c->n_groups);
+    for (int gi = 0; gi < c->n_groups; ++gi) {
+        WorkerGroup& g = c->groups[gi];
+        ok = ok && cudaEventCreate(&g.ev_run0) == cudaSuccess && cudaEventCreate(&g.ev_run1) == cudaSuccess &&
+             cudaEventCreateWithFlags(&g.ev_staged, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < nw; ++i) {
+            std::unique_ptr<Worker> w(new (std::nothrow) Worker());
+            if (!w) { ok = false; break; }
+            w->id = i; w->group = &g;
+            ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreate(&w->ev_w0) == cudaSuccess && cudaEventCreate(&w->ev_b0) == cudaSuccess && cudaEventCreate(&w->ev_b1) == cudaSuccess;
+            for (int q = 0; ok && q < Worker::kWalkSlots; ++q)
+                ok = cudaStreamCreateWithFlags(&w->walk_stream[q], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&w->ev_walk_done[q], cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreate(&w->ev_w1[q]) == cudaSuccess;
+            for (int q = 0; ok && q < Worker::kSide; ++q)
+                ok = cudaStreamCreateWithFlags(&w->side[q], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&w->ev_join[q], cudaEventDisableTiming) == cudaSuccess;
+            g.workers.push_back(std::move(w));
+        }
     }
     if (!ok) { fxg_destroy(c); return FXG_ERR_CUDA; }
     *out = c;
@@ -1291,10 +1325,13 @@ void fxg_destroy(fxg_ctx* c) {
     c->d_tmp.release();
     for (Pool& p : c->spare_pools) p.release();
     for (PinnedBuf& b : c->spare_pinned) b.release();
-    for (auto& w : c->workers) w->release();
-    if (c->ev_run0) cudaEventDestroy(c->ev_run0);
-    if (c->ev_run1) cudaEventDestroy(c->ev_run1);
-    if (c->ev_staged) cudaEventDestroy(c->ev_staged);
+    for (WorkerGroup& g : c->groups) {
+        for (auto& w : g.workers) w->release();
+        if (g.ev_run0) cudaEventDestroy(g.ev_run0);
+        if (g.ev_run1) cudaEventDestroy(g.ev_run1);
+        if (g.ev_staged) cudaEventDestroy(g.ev_staged);
+    }
+    if (c->stage_stream) cudaStreamDestroy(c->stage_stream);
     delete c;
 }
 
@@ -1318,7 +1355,7 @@ int fxg_set_references(fxg_ctx* c, size_t n_refs, const uint8_t* const* ranks, c
     }
     R.total = total;
     CUDA_TRY(c->err, R.packed.ensure(total / 2 + 64));
-    CUDA_TRY(c->err, cudaMemsetAsync(R.packed.p, 0, total / 2 + 64, c->workers[0]->stream));
+    CUDA_TRY(c->err, cudaMemsetAsync(R.packed.p, 0, total / 2 + 64, c->stage_stream));
     for (size_t i = 0; i < n_refs; ++i) {
         uint64_t const slice = uint64_t(256) << 20;            // upload in slices so that the temporary stays small
         for (uint64_t at = 0; at < lens[i]; at += slice) {
@@ -1367,11 +1404,11 @@ int fxg_align_batch_stage(fxg_ctx* c, const fxg_align_task* tasks, size_t n_task
         cudaError_t e = b->pool.inline_packed.ensure(inline_ref_pool_len / 2 + 64);
         if (e != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "inline pool allocation: %s", cudaGetErrorString(e));
         else {
-            cudaMemsetAsync(b->pool.inline_packed.p, 0, inline_ref_pool_len / 2 + 64, c->workers[0]->stream);
+            cudaMemsetAsync(b->pool.inline_packed.p, 0, inline_ref_pool_len / 2 + 64, c->stage_stream);
             rc = upload_packed(c, inline_ref_pool, inline_ref_pool_len, b->pool.inline_packed, 0);
         }
     }
-    if (rc == FXG_OK && cudaStreamSynchronize(c->workers[0]->stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
+    if (rc == FXG_OK && cudaStreamSynchronize(c->stage_stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
     if (rc != FXG_OK) { give_pool(c, b->pool); give_pinned(c, b->cigars); delete b; return rc; }
     *out = b;
     return FXG_OK;
@@ -1379,13 +1416,15 @@ int fxg_align_batch_stage(fxg_ctx* c, const fxg_align_task* tasks, size_t n_task
 
 int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
     if (!c || !b) return FXG_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(c->mu);
+    std::unique_lock<std::mutex> lock(c->mu);
     CUDA_TRY(c->err, cudaSetDevice(c->device));
-    Worker& w = *c->workers[0];
+    WorkerGroup& grp = acquire_group(c, lock);
+    struct Release { fxg_ctx* c; WorkerGroup& g; ~Release() { release_group(c, g); } } release{c, grp};   // (the lock is still held when it runs)
+    Worker& w = *grp.workers[0];
     w.ctr = fxg_counters{};
     int rc;
     {
-        RunTimer run_timer(c);
+        RunTimer run_timer(grp, w.ctr);
         size_t const N = b->tasks.size();
         b->results.assign(N, fxg_align_result{});
         b->cigars_len = 0;
@@ -1491,15 +1530,16 @@ void index_walks(fxg_job* j) {
     j->read_walk_begin[j->n_reads] = n_walks_total;
 }
 
-// fxg_verify_run without the context lock.  With a gate the parts validate their own reads first and wait at the gate
+// The body of fxg_verify_run on one worker group, without the context lock (errors and accounting go to the caller's
+// objects).  With a gate the parts validate their own reads first and wait at the gate
 // before their first launch (fxg_verify_reads: the upload runs beside their host-side preparation).
-int verify_run_locked(fxg_ctx* c, fxg_job* J, StageGate* gate, size_t pool_len) {
+int verify_run_group(fxg_ctx* c, WorkerGroup& grp, fxg_job* J, StageGate* gate, size_t pool_len, std::string& err, fxg_counters& ctr) {
     J->alignments.clear(); J->cigars_len = 0; J->stats = fxg_stats{};
     size_t const n_reads = J->n_reads;
     if (n_reads == 0) { J->ran = true; return FXG_OK; }
 
     // ---- split the reads into contiguous parts with similar numbers of anchors, one part per worker ----
-    size_t const n_parts = std::min<size_t>(c->workers.size(), std::max<size_t>(1, std::min<size_t>(n_reads, size_t(J->read_walk_begin[n_reads]) / 256 + 1)));
+    size_t const n_parts = std::min<size_t>(grp.workers.size(), std::max<size_t>(1, std::min<size_t>(n_reads, size_t(J->read_walk_begin[n_reads]) / 256 + 1)));
     std::vector<uint32_t> cut(n_parts + 1, 0);
     for (size_t p = 1; p < n_parts; ++p) {
         uint64_t const target = uint64_t(J->read_walk_begin[n_reads]) * p / n_parts;
@@ -1514,9 +1554,9 @@ int verify_run_locked(fxg_ctx* c, fxg_job* J, StageGate* gate, size_t pool_len) 
     auto const vt0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - vt0).count(); };
     uint64_t const budget = trace_budget_bytes(c, n_parts);
-    for (size_t p = 0; p < n_parts; ++p) c->workers[p]->ctr = fxg_counters{};
+    for (size_t p = 0; p < n_parts; ++p) grp.workers[p]->ctr = fxg_counters{};
     auto run_part = [&](size_t p) {
-        Worker& w = *c->workers[p];
+        Worker& w = *grp.workers[p];
         PartState& P = parts[p];
         P.trace_budget = budget;
         if (gate) P.out.rc = validate_reads(c, w.err, J->reads_p, cut[p], cut[p + 1], pool_len, J->nodes_p, J->n_nodes, J->anchors_p, J->n_anchors);
@@ -1529,7 +1569,7 @@ int verify_run_locked(fxg_ctx* c, fxg_job* J, StageGate* gate, size_t pool_len) 
         verify_part_finish(c, w, J, J->cigars.as<uint32_t>() + plan.bases[p], plan.bases[p], P);
     };
     {
-        RunTimer run_timer(c);
+        RunTimer run_timer(grp, ctr);
         std::vector<std::thread> threads;
         for (size_t p = 1; p < n_parts; ++p) threads.emplace_back(run_part, p);
         run_part(0);
@@ -1538,8 +1578,8 @@ int verify_run_locked(fxg_ctx* c, fxg_job* J, StageGate* gate, size_t pool_len) 
     double const t_join = since();
     g_prof.report();
     for (size_t p = 0; p < n_parts; ++p) {
-        add_counters(c->ctr, c->workers[p]->ctr);
-        if (parts[p].out.rc != FXG_OK) { c->err = c->workers[p]->err; return parts[p].out.rc; }
+        add_counters(ctr, grp.workers[p]->ctr);
+        if (parts[p].out.rc != FXG_OK) { err = grp.workers[p]->err; return parts[p].out.rc; }
     }
     {
         size_t n_al = 0;
@@ -1592,7 +1632,7 @@ int fxg_verify_stage(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     index_walks(j);
 
     rc = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, c->err, c->ctr);
-    if (rc == FXG_OK && cudaStreamSynchronize(c->workers[0]->stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
+    if (rc == FXG_OK && cudaStreamSynchronize(c->stage_stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
     if (rc != FXG_OK) { give_pool(c, j->pool); give_pinned(c, j->cigars); delete j; return rc; }
     *out = j;
     return FXG_OK;
@@ -1600,10 +1640,18 @@ int fxg_verify_stage(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
 
 int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
     if (!c || !J) return FXG_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(c->mu);
+    std::unique_lock<std::mutex> lock(c->mu);
     if (J->borrowed) return fail(c->err, FXG_ERR_STATE, "a job made by fxg_verify_reads cannot be run again (its inputs belonged to the caller)");
     CUDA_TRY(c->err, cudaSetDevice(c->device));
-    return verify_run_locked(c, J, nullptr, J->pool_len);
+    WorkerGroup& grp = acquire_group(c, lock);
+    lock.unlock();                                   // two runs (of different jobs) may be in flight, one per worker group
+    std::string err; fxg_counters ctr{};
+    int const rc = verify_run_group(c, grp, J, nullptr, J->pool_len, err, ctr);
+    lock.lock();
+    add_counters(c->ctr, ctr);
+    if (rc != FXG_OK) c->err = err;
+    release_group(c, grp);
+    return rc;
 }
 
 size_t fxg_job_num_alignments(const fxg_job* j) { return j ? j->alignments.size() : 0; }
@@ -1625,7 +1673,7 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
                      const uint8_t* fwd, const uint8_t* rc_pool, size_t pool_len,
                      const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors, fxg_job** out) {
     if (!c || !cfg || !out) return FXG_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(c->mu);
+    std::unique_lock<std::mutex> lock(c->mu);
     *out = nullptr;
     int rc = check_verify_call(c, cfg);
     if (rc != FXG_OK) return rc;
@@ -1640,25 +1688,32 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     j->pool = take_pool(c);
     j->cigars = take_pinned(c);
     index_walks(j);
+    WorkerGroup& grp = acquire_group(c, lock);
+    lock.unlock();                                   // two calls may be in flight, one per worker group
 
     StageGate gate;
-    fxg_counters stage_ctr{};
+    fxg_counters stage_ctr{}, ctr{};
+    std::string err;
     std::thread stager([&] {
         cudaSetDevice(c->device);
-        std::string err;
-        int r = check_ranks(err, fwd, pool_len, "forward pool");
-        if (r == FXG_OK) r = check_ranks(err, rc_pool, pool_len, "reverse-complement pool");
-        if (r == FXG_OK) r = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, err, stage_ctr);
-        if (r == FXG_OK && cudaEventRecord(c->ev_staged, c->workers[0]->stream) != cudaSuccess) r = fail(err, FXG_ERR_CUDA, "staging failed");
-        gate.open(r, err);
+        std::string serr;
+        int r = check_ranks(serr, fwd, pool_len, "forward pool");
+        if (r == FXG_OK) r = check_ranks(serr, rc_pool, pool_len, "reverse-complement pool");
+        if (r == FXG_OK) r = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, serr, stage_ctr);
+        if (r == FXG_OK && cudaEventRecord(grp.ev_staged, c->stage_stream) != cudaSuccess) r = fail(serr, FXG_ERR_CUDA, "staging failed");
+        gate.open(r, serr);
     });
-    rc = verify_run_locked(c, j, &gate, pool_len);
+    rc = verify_run_group(c, grp, j, &gate, pool_len, err, ctr);
     stager.join();
-    add_counters(c->ctr, stage_ctr);
-    if (gate.rc != FXG_OK) { rc = gate.rc; c->err = gate.err; }
+    if (gate.rc != FXG_OK) { rc = gate.rc; err = gate.err; }
     // the caller's arrays are not looked at after this point
     j->reads_p = nullptr; j->nodes_p = nullptr; j->anchors_p = nullptr;
-    if (rc != FXG_OK) { cudaDeviceSynchronize(); give_pool(c, j->pool); give_pinned(c, j->cigars); delete j; return rc; }
+    if (rc != FXG_OK) cudaDeviceSynchronize();
+    lock.lock();
+    add_counters(c->ctr, stage_ctr);
+    add_counters(c->ctr, ctr);
+    release_group(c, grp);
+    if (rc != FXG_OK) { c->err = err; give_pool(c, j->pool); give_pinned(c, j->cigars); delete j; return rc; }
     *out = j;
     return FXG_OK;
 }
@@ -1667,9 +1722,11 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
 
 int fxg_measure_int32_peak(fxg_ctx* c, double* out) {
     if (!c || !out) return FXG_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(c->mu);
+    std::unique_lock<std::mutex> lock(c->mu);
     CUDA_TRY(c->err, cudaSetDevice(c->device));
-    Worker& w = *c->workers[0];
+    WorkerGroup& grp = acquire_group(c, lock);
+    struct Release { fxg_ctx* c; WorkerGroup& g; ~Release() { release_group(c, g); } } release{c, grp};
+    Worker& w = *grp.workers[0];
     CUDA_TRY(c->err, c->d_tmp.ensure(64));
     uint32_t const iters = 4096, threads = 256, grid = uint32_t(c->num_sms) * 8;
     double best = 0;

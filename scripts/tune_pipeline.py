@@ -1,0 +1,19 @@
+"""Development aid: throughput of fxg_verify_run with several batches in flight (FXG_GROUPS / FXG_WORKERS knobs)."""
+import sys, os, time, threading
+sys.path.insert(0, os.getcwd())
+import bench
+from floxer_b200 import gpu as g
+from floxer_b200.batch import VerifyConfig
+depth = int(os.environ.get("FXG_GROUPS", "2"))
+refs, batch = bench.make_workload("config2", 0, g.pex_build)
+ctx = g.Context(0); ctx.set_references(refs)
+jobs = [ctx.stage_verify(batch, VerifyConfig()) for _ in range(depth)]
+def lanes(n):
+    ts = [threading.Thread(target=lambda j=j: [j.run() for _ in range(n)]) for j in jobs]
+    t0 = time.perf_counter()
+    for t in ts: t.start()
+    for t in ts: t.join()
+    return (time.perf_counter() - t0) * 1e3 / (n * depth)
+lanes(3)
+res = [lanes(6) for _ in range(3)]
+print({k: os.environ[k] for k in os.environ if k.startswith("FXG_")}, "ms per step", ["%.2f" % r for r in res])

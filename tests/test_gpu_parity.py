@@ -389,3 +389,36 @@ def test_bench_workload_properties_and_sample_parity(gpu):
         job.free()
     finally:
         c2.close()
+
+
+def test_two_batches_in_flight(ctx, gpu, oracle):
+    """Two jobs run from two threads at the same time (one per worker group) give what they give one after the other."""
+    import threading
+    refs = [synthetic.random_reference(120_000, 81)]
+    ctx.set_references(refs)
+    batches = [synthetic.make_batch(refs, 10, 1000, 0.06, s, gpu.pex_build, seed_errors=1, decoy_fraction=0.3) for s in (91, 92)]
+    cfgs = [VerifyConfig(), VerifyConfig(interval_optimization=True)]
+    want = [oracle_verify_batch(oracle, refs, b, c) for b, c in zip(batches, cfgs)]
+    staged = [ctx.stage_verify(b, c) for b, c in zip(batches, cfgs)]
+    errors = []
+
+    def lane(i):
+        try:
+            for _ in range(4):
+                al, cg = staged[i].run().alignments()
+                assert alignment_records(al, cg) == want[i][0] and staged[i].stats() == want[i][1]
+                j = ctx.verify_reads(batches[i], cfgs[i])           # the one-call path as well
+                al, cg = j.alignments()
+                assert alignment_records(al, cg) == want[i][0] and j.stats() == want[i][1]
+                j.free()
+        except Exception as e:                                      # noqa: BLE001 -- reported by the main thread
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=lane, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for s in staged:
+        s.free()
