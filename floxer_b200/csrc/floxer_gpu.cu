@@ -200,7 +200,7 @@ struct fxg_ctx {
     fxg_counters ctr{};
     int num_sms = 0;
     size_t smem_limit = 0;
-    static constexpr int kMaxGroups = 4;
+    static constexpr int kMaxGroups = 8;
     int n_groups = 4;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
     WorkerGroup groups[kMaxGroups];
     cudaStream_t stage_stream = nullptr; // uploads of references / query pools, Peq construction
