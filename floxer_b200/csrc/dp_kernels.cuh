@@ -243,6 +243,10 @@ __device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {
     asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// acc += hi(a * b), in place (no copy of the accumulator)
+__device__ __forceinline__ void mad_hi_acc(uint32_t& acc, uint32_t a, uint32_t b) {
+    asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(a), "r"(b));
+}
 
 // One column of one block: the Myers/Hyyroe word-step over W words with the horizontal deltas (in_hp, in_hn: bit 31 =
 // the row above the block) of the block above.  Returns HP / HN of the last word (bit 31 = the block's bottom row).
@@ -341,7 +345,7 @@ __device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t 
         uint32_t hp, hn;                                                                                   \
         block_column<W, false>(S.Pv, S.Mv, EQ_USE, r_hp, r_hn, hp, hn, no_hp);                             \
         S.o_hp = mad_lo(hp, pub_a, pub_hp_b); S.o_hn = mad_lo(hn, pub_a, 0u);                              \
-        n_hp = mad_hi(hp, two, n_hp); n_hn = mad_hi(hn, two, n_hn);                                        \
+        mad_hi_acc(n_hp, hp, two); mad_hi_acc(n_hn, hn, two);                                        \
         if (LAST) {                                                                                        \
             int32_t const sc = score_base + int32_t(n_hp) - int32_t(n_hn);                                 \
             if (track && sc <= S.best) { S.best = sc; S.best_col = t - S.b; }                              \
