@@ -22,6 +22,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 using namespace fxg;
@@ -285,7 +286,7 @@ int fail(std::string& err, int code, const char* fmt, ...) {
 void add_counters(fxg_counters& a, fxg_counters const& b) {
     a.kernel_launches += b.kernel_launches; a.dp_tasks += b.dp_tasks; a.dp_word_steps += b.dp_word_steps;
     a.dp_cells_full += b.dp_cells_full; a.trace_bytes += b.trace_bytes; a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
-    a.root_launch_ms += b.root_launch_ms; a.root_launch_word_steps += b.root_launch_word_steps;
+    a.root_launch_ms += b.root_launch_ms; a.root_launch_word_steps += b.root_launch_word_steps; a.shared_tracebacks += b.shared_tracebacks;
     a.trace_word_steps += b.trace_word_steps; a.dp_kernel_ms += b.dp_kernel_ms; a.trace_kernel_ms += b.trace_kernel_ms; a.waves += b.waves; a.run_ms += b.run_ms;
 }
 
@@ -652,6 +653,19 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
     g_prof.lap(w, 7);
     std::vector<Pass> chunk; std::vector<uint64_t> ck_base;
     std::vector<uint32_t> hit_pass;          // accepted passes in traceback order (index into passes)
+    constexpr uint32_t kOwnTraceback = 0xfffffffeu, kNotAccepted = 0xffffffffu;
+    std::vector<uint32_t> dup_of(N, kNotAccepted);   // pass whose traceback this one shares, or one of the two marks
+    struct DupKey {
+        uint64_t query_base, end_abs; uint32_t m, score, flags;
+        bool operator==(DupKey const& o) const { return query_base == o.query_base && end_abs == o.end_abs && m == o.m && score == o.score && flags == o.flags; }
+    };
+    struct DupHash {
+        size_t operator()(DupKey const& k) const {
+            uint64_t h = k.query_base * 0x9E3779B97F4A7C15ull ^ (k.end_abs + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full ^ (uint64_t(k.m) << 32 | k.score) ^ k.flags;
+            return size_t(h ^ (h >> 31));
+        }
+    };
+    std::unordered_map<DupKey, uint32_t, DupHash> dup_key;
     uint64_t cig_at = w.cig_used;
     size_t H = 0;                            // tracebacks issued so far
     size_t i = 0;
@@ -679,9 +693,28 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         // ---- tracebacks of the accepted ones on their own stream, one launch per block width ----
         size_t const H0 = H;
         for (size_t q = 0; q < M; ++q) { outs[i + q].score = res[q].score; outs[i + q].end_col = res[q].end_col; }
+        // Alignments of the same query piece that end at the same reference position with the same score -- the usual case:
+        // every true anchor of a read leads to the same locus -- have the same traceback, provided every optimal alignment
+        // ending there starts inside each of their windows: an alignment of cost s ending at column e spans at least
+        // m - s columns... and at most m + s, so its first column is >= e - m - s (in store coordinates); windows that
+        // begin at or before that bound contain every such alignment, the DP values along them agree, and so does every
+        // "left / up / diagonal" decision.  One member of such a group is traced back, the others
+        // share its begin position and its cigar.
+        dup_key.clear();
+        for (size_t q = 0; q < M; ++q) {
+            if (res[q].score > int32_t(max_errors[i + q])) { dup_of[i + q] = kNotAccepted; continue; }
+            Pass const& P = chunk[q];
+            uint64_t const end_abs = P.ref_base + res[q].end_col;
+            bool const safe = int64_t(end_abs) - int64_t(P.m) - int64_t(res[q].score) >= int64_t(P.ref_base);
+            dup_of[i + q] = kOwnTraceback;
+            if (!safe) continue;
+            DupKey const key{P.query_base, end_abs, P.m, uint32_t(res[q].score), P.flags};
+            auto const ins = dup_key.emplace(key, uint32_t(i + q));
+            if (!ins.second) dup_of[i + q] = ins.first->second;          // shares the traceback of an earlier pass of this chunk
+        }
         for (int wi = 0; wi < 6; ++wi) {
             for (size_t q = 0; q < M; ++q) {
-                if (cfgs[i + q].widx != wi || res[q].score > int32_t(max_errors[i + q])) continue;
+                if (cfgs[i + q].widx != wi || dup_of[i + q] != kOwnTraceback) continue;
                 Pass const& P = chunk[q];
                 Walk2Task& t = wt[H];
                 t.ck_base = ck_base[q]; t.ref_base = P.ref_base; t.query_base = P.query_base;
@@ -750,6 +783,15 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         RootOut& o = outs[hit_pass[h]];
         o.begin_col = wr[h].begin_col; o.cigar_len = wr[h].cigar_len;
         o.cigar_offset = wt[h].cigar_base + wt[h].cigar_cap - wr[h].cigar_len;
+    }
+    for (size_t q = 0; q < N; ++q) {
+        if (dup_of[q] >= kOwnTraceback) continue;
+        RootOut const& rep = outs[dup_of[q]];
+        RootOut& o = outs[q];
+        // same alignment, seen from this pass' window: its begin column moves by the distance between the windows' starts
+        o.begin_col = uint32_t(passes[dup_of[q]].ref_base + rep.begin_col - passes[q].ref_base);
+        o.cigar_offset = rep.cigar_offset; o.cigar_len = rep.cigar_len;
+        w.ctr.shared_tracebacks++;
     }
     w.cig_used = cig_at;
     g_prof.lap(w, 12);

@@ -142,6 +142,7 @@ typedef struct {
     uint64_t trace_word_steps;       /* unused (the traceback recomputes tiles from checkpoints; no trace passes) */
     double root_launch_ms;           /* CUDA-event time of the largest launch of every root wave (the dominant launch) ... */
     uint64_t root_launch_word_steps; /* ... and the word-steps those launches issued */
+    uint64_t shared_tracebacks;      /* accepted root alignments that took begin position and CIGAR from an identical one */
 } fxg_counters;
 
 /* ---- life cycle ---- */
