@@ -50,14 +50,16 @@ struct DpResult {
 // Peq table: bit p of plane s is (pool[p] == s).  kPeqFrontPadWords zero words in front.
 // ---------------------------------------------------------------------------------------------
 __global__ void build_peq_kernel(const uint8_t* __restrict__ pool, uint64_t len, uint32_t* __restrict__ table,
-                                 uint64_t plane_words) {
+                                 uint64_t plane_words, uint32_t* __restrict__ bad_rank_flag) {
     uint64_t const n_words = (len + 31) / 32;
     uint32_t const lane = threadIdx.x & 31;
     uint64_t const warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     uint64_t const n_warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    bool bad = false;
     for (uint64_t w = warp; w < n_words; w += n_warps) {
         uint64_t const p = w * 32 + lane;
         uint32_t const c = p < len ? pool[p] : 0xffu;
+        bad |= p < len && c >= uint32_t(kNumSymbols);       // such a byte matches no plane (harmless here); the host reports it
         uint32_t mine = 0;
 #pragma unroll
         for (int s = 0; s < kNumSymbols; ++s) {
@@ -66,6 +68,7 @@ __global__ void build_peq_kernel(const uint8_t* __restrict__ pool, uint64_t len,
         }
         if (lane < kNumSymbols) table[uint64_t(lane) * plane_words + kPeqFrontPadWords + w] = mine;
     }
+    if (bad_rank_flag && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(bad_rank_flag, 1u);
 }
 
 // 32 bits of plane starting at (signed) bit position x

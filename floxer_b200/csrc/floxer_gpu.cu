@@ -93,9 +93,9 @@ struct RefStore {
 
 // one staged pool of query bytes with its Peq planes (+ optional inline reference pool)
 struct Pool {
-    DevBuf bytes, peq, inline_packed;
+    DevBuf bytes, peq, inline_packed, bad_rank;   // bad_rank: one word the Peq builder sets when it meets a rank above 5
     uint64_t len = 0, plane_words = 0, inline_len = 0;
-    void release() { bytes.release(); peq.release(); inline_packed.release(); }
+    void release() { bytes.release(); peq.release(); inline_packed.release(); bad_rank.release(); }
 };
 
 struct Pass {                            // one DP pass of the engine
@@ -882,20 +882,24 @@ int upload_packed(fxg_ctx* c, const uint8_t* ranks, uint64_t len, DevBuf& dst, u
 
 // uploads up to two byte ranges back to back (forward / reverse pools) and builds the Peq planes; errors and
 // accounting go to the caller's objects (fxg_verify_reads runs this beside the workers)
-int stage_pool(fxg_ctx* c, Pool& pool, const uint8_t* a, size_t a_len, const uint8_t* b, size_t b_len, std::string& err, fxg_counters& ctr) {
+int stage_pool(fxg_ctx* c, Pool& pool, const uint8_t* a, size_t a_len, const uint8_t* b, size_t b_len, std::string& err, fxg_counters& ctr,
+               bool check_ranks_on_device = false) {
     cudaStream_t const st = c->stage_stream;
     pool.len = a_len + b_len;
     pool.plane_words = (pool.len + 31) / 32 + kPeqFrontPadWords + kPeqBackPadWords;
     CUDA_TRY(err, pool.bytes.ensure(pool.len + 64));
     CUDA_TRY(err, pool.peq.ensure(pool.plane_words * kNumSymbols * 4));
+    CUDA_TRY(err, pool.bad_rank.ensure(4));
     if (a_len) CUDA_TRY(err, cudaMemcpyAsync(pool.bytes.p, a, a_len, cudaMemcpyHostToDevice, st));
     if (b_len) CUDA_TRY(err, cudaMemcpyAsync(pool.bytes.as<uint8_t>() + a_len, b, b_len, cudaMemcpyHostToDevice, st));
     ctr.h2d_bytes += pool.len;
     CUDA_TRY(err, cudaMemsetAsync(pool.peq.p, 0, pool.plane_words * kNumSymbols * 4, st));
+    CUDA_TRY(err, cudaMemsetAsync(pool.bad_rank.p, 0, 4, st));
     if (pool.len) {
         uint64_t const n_words = (pool.len + 31) / 32;
         uint32_t const grid = uint32_t(std::min<uint64_t>((n_words + 7) / 8, uint64_t(c->num_sms) * 16));
-        build_peq_kernel<<<grid, 256, 0, st>>>(pool.bytes.as<uint8_t>(), pool.len, pool.peq.as<uint32_t>(), pool.plane_words);
+        build_peq_kernel<<<grid, 256, 0, st>>>(pool.bytes.as<uint8_t>(), pool.len, pool.peq.as<uint32_t>(), pool.plane_words,
+                                               check_ranks_on_device ? pool.bad_rank.as<uint32_t>() : nullptr);
         CUDA_TRY(err, cudaGetLastError());
         ctr.kernel_launches++;
     }
@@ -1739,15 +1743,21 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     std::thread stager([&] {
         cudaSetDevice(c->device);
         std::string serr;
-        int r = check_ranks(serr, fwd, pool_len, "forward pool");
-        if (r == FXG_OK) r = check_ranks(serr, rc_pool, pool_len, "reverse-complement pool");
-        if (r == FXG_OK) r = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, serr, stage_ctr);
+        // (ranks above 5 in the query pools are detected by the Peq builder on the device and reported after the run:
+        //  such a byte simply matches nothing, so no kernel can be led astray by it in the meantime)
+        int r = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, serr, stage_ctr, true);
         if (r == FXG_OK && cudaEventRecord(grp.ev_staged, c->stage_stream) != cudaSuccess) r = fail(serr, FXG_ERR_CUDA, "staging failed");
         gate.open(r, serr);
     });
     rc = verify_run_group(c, grp, j, &gate, pool_len, err, ctr);
     stager.join();
     if (gate.rc != FXG_OK) { rc = gate.rc; err = gate.err; }
+    if (rc == FXG_OK) {
+        uint32_t bad = 0;
+        if (cudaMemcpyAsync(&bad, j->pool.bad_rank.p, 4, cudaMemcpyDeviceToHost, c->stage_stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stage_stream) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "staging failed");
+        else if (bad) rc = fail(err, FXG_ERR_INVALID_ARGUMENT, "query pools contain a rank above %d (allowed 0..%d)", FXG_MAX_RANK, FXG_MAX_RANK);
+    }
     // the caller's arrays are not looked at after this point
     j->reads_p = nullptr; j->nodes_p = nullptr; j->anchors_p = nullptr;
     if (rc != FXG_OK) cudaDeviceSynchronize();

@@ -422,3 +422,18 @@ def test_two_batches_in_flight(ctx, gpu, oracle):
     assert not errors, errors
     for s in staged:
         s.free()
+
+
+def test_verify_reads_rejects_bad_ranks(ctx, gpu):
+    """A rank above 5 in a query pool is an error of fxg_verify_reads (found on the device, reported with the call)."""
+    refs = [synthetic.random_reference(50_000, 5)]
+    ctx.set_references(refs)
+    batch = synthetic.make_batch(refs, 3, 600, 0.05, 6, gpu.pex_build)
+    batch.reverse_pool = batch.reverse_pool.copy()
+    batch.reverse_pool[100] = 7
+    with pytest.raises(gpu.FloxerGpuError):
+        ctx.verify_reads(batch, VerifyConfig())
+    with pytest.raises(gpu.FloxerGpuError):
+        ctx.stage_verify(batch, VerifyConfig())
+    batch.reverse_pool[100] = 1
+    assert len(ctx.verify_reads(batch, VerifyConfig()).alignments()[0]) >= 0
