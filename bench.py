@@ -27,6 +27,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# the library asks for 32 hardware work queues when it is loaded (floxer_gpu.cu, fxg_on_load); torch may create the CUDA
+# context before that, so the same default is set here, before torch is imported
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
@@ -52,7 +56,11 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
+
+    def window(self, t0: float, t1: float):
+        """A timed region (time.perf_counter values): only samples taken inside one count, if any were."""
+        self.windows.append((t0, t1))
 
     def start(self):
         try:
@@ -64,7 +72,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self) -> dict:
         if self.proc:
@@ -73,10 +81,12 @@ class ClockSampler:
                 self.proc.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if any(a <= t <= b + 0.1 for a, b in self.windows)]
+        rows = inside if inside else [r for _, r in self.rows]      # a region shorter than the sampling period: the warm-up's
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -109,13 +119,13 @@ def cpu_arm(refs, batch, cfg, sample_reads: int, threads: int, repeats: int = 1)
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--interval-optimization", action="store_true", help="floxer --interval-optimization (off by default, as in the reference)")
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU sample (0 = sized automatically)")
-    ap.add_argument("--pipeline", type=int, default=4, help="batches in flight per GPU (1..4): the library serves up to four *_run calls at a time")
+    ap.add_argument("--pipeline", type=int, default=8, help="batches in flight per GPU (1..8): the library serves up to eight *_run calls at a time")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -132,7 +142,7 @@ def main() -> int:
                           f"extra verification ratio 0.05, CIGAR output; anchors from the ground-truth stand-in seeder",
               "reads_per_gpu": W["reads"], "read_len": W["read_len"], "error_rate": W["error"],
               "l2": "256 MiB written to HBM between steps (each step also streams 1.5 GB of checkpoint records, 12x the L2)",
-              "batches_in_flight": max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "4"))))}
+              "batches_in_flight": max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "8"))))}
 
     # ------------------------------------------------------------------ CPU arm ("reference")
     if args.impl == "reference":
@@ -203,7 +213,7 @@ def main() -> int:
             dist.barrier()
             torch.cuda.synchronize()
 
-    depth = max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "4"))))
+    depth = max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "8"))))
 
     def run_lanes(step_fns, n_steps):
         """n_steps steps, dealt round-robin to len(step_fns) host threads (batches in flight); returns wall seconds."""
@@ -228,6 +238,8 @@ def main() -> int:
         return dt
 
     # ---- device-resident arm: inputs staged once (one staged copy per batch in flight), each step = fxg_verify_run ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     jobs = [ctx.stage_verify(batch, cfg) for _ in range(depth)]
     run_lanes([j.run for j in jobs], args.warmup * depth)    # both worker groups warm (their buffers are allocated on first use)
 
@@ -246,15 +258,14 @@ def main() -> int:
         jobs[0].run()
         lat_ms.append((time.perf_counter() - t0) * 1e3)
         kernel_ms.append(ctx.counters()["run_ms"] - c0["run_ms"])
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     ctx.reset_counters()
+    t_region = time.perf_counter()
     total_s = run_lanes([resident_step(j) for j in jobs], args.steps)
     barrier()
+    sampler.window(t_region, time.perf_counter())
     step_ms = [total_s * 1e3 / args.steps] * args.steps
     ctr = ctx.counters()
-    clocks = sampler.stop()
     stats = jobs[0].stats()
     al, cg = jobs[0].alignments()
     n_alignments = len(al)
@@ -276,9 +287,12 @@ def main() -> int:
     run_lanes([e2e_step(i) for i in range(depth)], 2 * depth)   # warm-up (page-locked pools are allocated once)
     torch.cuda.synchronize()
     ctx.reset_counters()
-    n_e2e = max(depth, min(args.steps, 6))
+    n_e2e = args.steps
+    t_region = time.perf_counter()
     e2e_s = run_lanes([e2e_step(i) for i in range(depth)], n_e2e)
     torch.cuda.synchronize()
+    sampler.window(t_region, time.perf_counter())
+    clocks = sampler.stop()
     e2e_ms = [e2e_s * 1e3 / n_e2e] * n_e2e
     e2e_ctr = ctx.counters()
 

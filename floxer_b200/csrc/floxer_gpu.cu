@@ -122,6 +122,22 @@ struct Worker {
     cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
+    cudaEvent_t ev_sleep = nullptr;
+    // Waits for everything queued on `s` so far.  cudaStreamSynchronize spins (measured: 94 ms of CPU per batch, 13 cores'
+    // worth, taken from the other workers and the other ranks of the host); a blocking event alone adds its wake-up
+    // latency to every wave (a batch took 14.8 instead of 11.5 ms).  So: poll for a short while, handing the core over
+    // between polls -- most waves of the inner levels end within that -- then sleep on the event.
+    int spin_us = 150;
+    cudaError_t wait_for(cudaStream_t s) {
+        cudaError_t e = cudaEventRecord(ev_sleep, s);
+        if (e != cudaSuccess) return e;
+        auto const t0 = std::chrono::steady_clock::now();
+        while ((e = cudaEventQuery(ev_sleep)) == cudaErrorNotReady) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us)) return cudaEventSynchronize(ev_sleep);
+            std::this_thread::yield();
+        }
+        return e;
+    }
     // tracebacks are long chains of dependent steps: the root alignments of a wave are cut into chunks, each chunk's
     // tracebacks run on a stream of their own beside the score passes (and tracebacks) of the other chunks
     static constexpr int kWalkSlots = 4;
@@ -140,6 +156,7 @@ struct Worker {
         if (ev_w0) { cudaEventDestroy(ev_w0); ev_w0 = nullptr; }
         if (ev_b0) { cudaEventDestroy(ev_b0); ev_b0 = nullptr; }
         if (ev_b1) { cudaEventDestroy(ev_b1); ev_b1 = nullptr; }
+        if (ev_sleep) { cudaEventDestroy(ev_sleep); ev_sleep = nullptr; }
         for (int q = 0; q < kWalkSlots; ++q) {
             d_ck[q].release();
             if (ev_walk_done[q]) cudaEventDestroy(ev_walk_done[q]);
@@ -161,10 +178,14 @@ struct Worker {
     }
 };
 
-// The workers that serve one *_run call.  A context has two groups, so that two batches can be in flight: the host-side
-// preparation and the latency-bound tracebacks of one batch hide behind the score passes of the other.
+// The workers that serve one *_run call.  A context has several groups, so that several batches can be in flight: the
+// host-side preparation and the latency-bound tracebacks of one batch hide behind the score passes of the others.
+// A group owns twice the workers it uses when the context is busy: a batch that runs (nearly) alone is split over all
+// of them, which shortens its latency (config 2: 12 instead of 16 ms), while with many batches in flight fewer, larger
+// launches per batch are the better deal.
 struct WorkerGroup {
     std::vector<std::unique_ptr<Worker>> workers;
+    size_t use_workers = 0;              // decided when the group is acquired
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr, ev_staged = nullptr;
     bool busy = false;
 };
@@ -201,13 +222,15 @@ struct fxg_ctx {
     fxg_counters ctr{};
     int num_sms = 0;
     size_t smem_limit = 0;
-    static constexpr int kMaxGroups = 8;
-    int n_groups = 4;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
+    static constexpr int kMaxGroups = 16;
+    int n_groups = 8;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
     WorkerGroup groups[kMaxGroups];
     cudaStream_t stage_stream = nullptr; // uploads of references / query pools, Peq construction
     std::condition_variable group_free;
     DevBuf d_tmp;
     uint64_t trace_budget = 0;
+    int workers_busy = 4;                        // workers a group uses when more than a quarter of the groups are busy
+    bool infer_inner = true;                     // FXG_INFER_INNER=0 computes every inner window (development knob)
     int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
     std::vector<Pool> spare_pools;       // device buffers of freed batches / jobs, reused by the next stage call
     std::vector<PinnedBuf> spare_pinned; // page-locked cigar pools of freed batches / jobs (cudaHostAlloc costs milliseconds)
@@ -286,7 +309,7 @@ int fail(std::string& err, int code, const char* fmt, ...) {
 void add_counters(fxg_counters& a, fxg_counters const& b) {
     a.kernel_launches += b.kernel_launches; a.dp_tasks += b.dp_tasks; a.dp_word_steps += b.dp_word_steps;
     a.dp_cells_full += b.dp_cells_full; a.trace_bytes += b.trace_bytes; a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
-    a.root_launch_ms += b.root_launch_ms; a.root_launch_word_steps += b.root_launch_word_steps; a.shared_tracebacks += b.shared_tracebacks;
+    a.root_launch_ms += b.root_launch_ms; a.root_launch_word_steps += b.root_launch_word_steps; a.shared_tracebacks += b.shared_tracebacks; a.inferred_inner += b.inferred_inner;
     a.trace_word_steps += b.trace_word_steps; a.dp_kernel_ms += b.dp_kernel_ms; a.trace_kernel_ms += b.trace_kernel_ms; a.waves += b.waves; a.run_ms += b.run_ms;
 }
 
@@ -304,7 +327,14 @@ struct RunTimer {
 // a free worker group, waiting for one if both are busy; call with c->mu held through `lock`
 WorkerGroup& acquire_group(fxg_ctx* c, std::unique_lock<std::mutex>& lock) {
     for (;;) {
-        for (int i = 0; i < c->n_groups; ++i) if (!c->groups[i].busy) { c->groups[i].busy = true; return c->groups[i]; }
+        int busy = 0;
+        for (int i = 0; i < c->n_groups; ++i) busy += c->groups[i].busy;
+        for (int i = 0; i < c->n_groups; ++i) if (!c->groups[i].busy) {
+            WorkerGroup& g = c->groups[i];
+            g.busy = true;
+            g.use_workers = busy + 1 <= std::max(1, c->n_groups / 4) ? g.workers.size() : size_t(c->workers_busy);
+            return g;
+        }
         c->group_free.wait(lock);
     }
 }
@@ -576,7 +606,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     g_prof.lap(w, 6);
     CUDA_TRY(w.err, cudaMemcpyAsync(w.h_results.p, w.d_results.p, N * sizeof(DpResult), cudaMemcpyDeviceToHost, w.stream));
     w.ctr.d2h_bytes += N * sizeof(DpResult);
-    CUDA_TRY(w.err, cudaStreamSynchronize(w.stream));
+    CUDA_TRY(w.err, w.wait_for(w.stream));
     float ms = 0;
     CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
     w.ctr.dp_kernel_ms += ms;
@@ -767,7 +797,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         i = j; ++k;
         g_prof.lap(w, 12);
     }
-    for (int q = 0; q < std::min(k, int(Worker::kWalkSlots)); ++q) CUDA_TRY(w.err, cudaStreamSynchronize(w.walk_stream[q]));
+    for (int q = 0; q < std::min(k, int(Worker::kWalkSlots)); ++q) CUDA_TRY(w.err, w.wait_for(w.walk_stream[q]));
     if (walk_timed) {
         // first traceback launch to last traceback done (they run beside score passes)
         float best = 0;
@@ -802,7 +832,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
 int fetch_cigars(Worker& w, uint32_t* dst) {
     if (!w.cig_used) return FXG_OK;
     CUDA_TRY(w.err, cudaMemcpyAsync(dst, w.d_cigars.p, w.cig_used * 4, cudaMemcpyDeviceToHost, w.stream));
-    CUDA_TRY(w.err, cudaStreamSynchronize(w.stream));
+    CUDA_TRY(w.err, w.wait_for(w.stream));
     w.ctr.d2h_bytes += w.cig_used * 4;
     return FXG_OK;
 }
@@ -831,7 +861,7 @@ Pool take_pool(fxg_ctx* c) {
     return p;
 }
 void give_pool(fxg_ctx* c, Pool& p) {
-    if (c->spare_pools.size() < 4) c->spare_pools.push_back(p); else p.release();
+    if (c->spare_pools.size() < size_t(2 * c->n_groups)) c->spare_pools.push_back(p); else p.release();   // one per batch in flight and one being staged
     p = Pool{};
 }
 
@@ -846,7 +876,7 @@ PinnedBuf take_pinned(fxg_ctx* c) {
     return b;
 }
 void give_pinned(fxg_ctx* c, PinnedBuf& b) {
-    if (b.p && c->spare_pinned.size() < 4) c->spare_pinned.push_back(b); else b.release();
+    if (b.p && c->spare_pinned.size() < size_t(2 * c->n_groups)) c->spare_pinned.push_back(b); else b.release();
     b = PinnedBuf{};
 }
 
@@ -1123,13 +1153,26 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     };
 
     // ---------------- 1. inner levels, deepest first ----------------
+    // Walks of one read and strand that stand at the same tree node (anchors from the same subtree) ask the same question
+    // about windows that are a few bases apart -- and an inner alignment is only ever asked whether it EXISTS
+    // (alignment.cpp:98-112).  So per node the walk with the rightmost window start goes first; if it finds an alignment
+    // (cost <= k, ending at reference position E), every walk of that node whose window ends at or after E has it as
+    // well: their windows begin at or before the first one's, so the alignment -- which began somewhere inside the first
+    // window -- lies inside theirs.  Identical windows share the answer either way.  Only the walks that remain undecided
+    // are computed in a second launch of the level.
+    struct Ask { uint64_t key, ws, we; uint32_t wi; uint32_t pass; };   // pass: index into asks' Pass array, or none
+    constexpr uint32_t kNoPass = 0xffffffffu;
+    std::vector<Ask> asks; std::vector<Pass> ask_pass;
+    std::vector<uint32_t> first, second, second_ask;                    // asks computed in the first / second launch
+    std::vector<int8_t> verdict;                                         // per ask: -1 undecided, 0 no alignment, 1 alignment exists
+    std::vector<uint64_t> rep_end;                                       // per ask: reference position where the alignment found ends
     for (int cur_level = int(level.size()) - 1; cur_level >= 1; --cur_level) {
         g_prof.start(w);
         active.swap(level[size_t(cur_level)]);
         level[size_t(cur_level)].clear();
         if (active.empty()) continue;
-        passes.clear(); pass_walk.clear();
         std::vector<uint32_t>& up = level[size_t(cur_level) - 1];
+        asks.clear(); ask_pass.clear();
         for (uint32_t wi : active) {
             Walk& wk = walks[wi];
             fxg_anchor const& A = J->anchors_p[wk.anchor];
@@ -1138,28 +1181,60 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
             uint64_t const qbase = (wk.orient ? J->pool_len : 0) + J->reads_p[wk.read].query_offset + wk.node->query_index_from;
             // statistics, verification.cpp:238-242 (kept per walk: with the interval optimisation the walk may turn out not to count)
             wk.n_inner++; wk.sum_inner += sp.length; wk.cells_inner += uint64_t(m) * sp.length;
+            Ask a;
+            a.key = (uint64_t(wk.node - J->nodes_p) << 1) | wk.orient;   // the node identifies the read as well
+            a.ws = c->refs.base[A.reference_id] + sp.offset; a.we = a.ws + sp.length;
+            a.wi = wi; a.pass = kNoPass;
             Pass p;
-            if (score_pass_for(c->refs.base[A.reference_id] + sp.offset, qbase, uint32_t(sp.length), m, uint32_t(wk.node->num_errors), 0u, p)) {
-                passes.push_back(p); pass_walk.push_back(wi);
-            } else {
-                wk.state = W_DONE;                       // more insertions needed than errors allowed: no alignment
-            }
+            if (score_pass_for(a.ws, qbase, uint32_t(sp.length), m, uint32_t(wk.node->num_errors), 0u, p)) { a.pass = uint32_t(ask_pass.size()); ask_pass.push_back(p); }
+            asks.push_back(a);
+        }
+        // groups: same node and strand, rightmost window first
+        std::sort(asks.begin(), asks.end(), [](Ask const& x, Ask const& y) { return x.key != y.key ? x.key < y.key : (x.ws != y.ws ? x.ws > y.ws : x.wi < y.wi); });
+        size_t const NA = asks.size();
+        verdict.assign(NA, -1); rep_end.assign(NA, 0);
+        first.clear(); passes.clear();
+        for (size_t q = 0; q < NA; ++q) {
+            if (asks[q].pass == kNoPass) { verdict[q] = 0; continue; }     // more insertions needed than errors allowed: no alignment
+            if (!c->infer_inner || q == 0 || asks[q].key != asks[q - 1].key) { first.push_back(uint32_t(q)); passes.push_back(ask_pass[asks[q].pass]); }
         }
         g_prof.lap(w, 2);
         if (g_prof.on && w.id == 0 && std::getenv("FXG_TRACE_WAVES"))
-            fprintf(stderr, "[fxg] level %d: %zu walks, %zu passes\n", cur_level, active.size(), passes.size());
+            fprintf(stderr, "[fxg] level %d: %zu walks, %zu computed first\n", cur_level, active.size(), passes.size());
         if (!pass_through_gate()) return;
         const DpResult* res = nullptr;
         out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
         if (out.rc != FXG_OK) return;
         w.ctr.waves++;
         g_prof.start(w);
-        for (size_t q = 0; q < passes.size(); ++q) {
-            Walk& wk = walks[pass_walk[q]];
-            if (res[q].score <= int32_t(wk.node->num_errors)) {
+        for (size_t f = 0; f < first.size(); ++f) {
+            uint32_t const q = first[f];
+            bool const ok = res[f].score <= int32_t(walks[asks[q].wi].node->num_errors);
+            verdict[q] = ok ? 1 : 0;
+            rep_end[q] = asks[q].ws + res[f].end_col;
+        }
+        // what follows from the first walk of each group
+        second.clear(); second_ask.clear(); passes.clear();
+        size_t rep = 0;
+        for (size_t q = 0; q < NA; ++q) {
+            if (q == 0 || asks[q].key != asks[q - 1].key) { rep = q; continue; }
+            if (verdict[q] != -1) continue;
+            if (verdict[rep] != -1 && asks[q].ws == asks[rep].ws && asks[q].we == asks[rep].we) verdict[q] = verdict[rep];      // the same window
+            else if (verdict[rep] == 1 && asks[q].we >= rep_end[rep]) { verdict[q] = 1; w.ctr.inferred_inner++; }               // (ws <= the first one's by the order)
+            else { second.push_back(uint32_t(q)); passes.push_back(ask_pass[asks[q].pass]); }
+        }
+        if (!passes.empty()) {
+            out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
+            if (out.rc != FXG_OK) return;
+            for (size_t f = 0; f < second.size(); ++f)
+                verdict[second[f]] = res[f].score <= int32_t(walks[asks[second[f]].wi].node->num_errors) ? 1 : 0;
+        }
+        for (size_t q = 0; q < NA; ++q) {
+            Walk& wk = walks[asks[q].wi];
+            if (verdict[q] == 1) {
                 fxg_read const& R = J->reads_p[wk.read];
                 wk.node = &J->nodes_p[R.node_offset + wk.node->parent_id];      // pex_tree::get_parent_of_child, pex.cpp:70-76
-                up.push_back(pass_walk[q]);                                      // joins the walks that start one level up
+                up.push_back(asks[q].wi);                                        // joins the walks that start one level up
             } else {
                 wk.state = W_DONE;
             }
@@ -1301,18 +1376,25 @@ struct TracePlan {
     }
 };
 
-// Host workers per group: the groups of all ranks on this host together should not oversubscribe its cores
-// (torchrun exports LOCAL_WORLD_SIZE).  FXG_WORKERS overrides.
+// Host workers per group.  A worker mostly waits for its own launches (polling, and yielding the core between polls),
+// so two workers per core across the groups of all ranks on this host (torchrun exports LOCAL_WORLD_SIZE) is what
+// measured best: 8 groups x 4 workers on the 16 cores of a one-GPU box.  FXG_WORKERS overrides.
 int default_workers(int n_groups) {
     if (const char* e = std::getenv("FXG_WORKERS")) { int v = std::atoi(e); if (v >= 1 && v <= 64) return v; }
     unsigned const hc = std::max(1u, std::thread::hardware_concurrency());
     int const ranks = env_int("LOCAL_WORLD_SIZE", 1, 1, 64);
-    return int(std::max(2u, std::min(8u, hc / unsigned(n_groups * ranks))));
+    return int(std::max(2u, std::min(4u, 2 * hc / unsigned(n_groups * ranks))));
 }
 
 }  // namespace
 
 // ================================================================================================ C ABI
+
+// Each worker drives its own streams (32 workers and more per context).  With the default of 8 hardware work queues
+// the streams share queues and launches of different batches wait for each other without reason (measured on
+// config 2: 6.2 -> 5.6 ms per batch with 32 queues).  The variable is read when the CUDA context is created, so it is
+// set when the library is loaded, and only if the host application has not chosen a value itself.
+__attribute__((constructor)) static void fxg_on_load() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 
 extern "C" {
 
@@ -1333,9 +1415,11 @@ int fxg_create(int device, fxg_ctx** out) {
     c->smem_limit = prop.sharedMemPerBlockOptin;
     bool ok = cudaStreamCreateWithFlags(&c->stage_stream, cudaStreamNonBlocking) == cudaSuccess && set_all_smem_attrs(c->smem_limit) == cudaSuccess;
     c->root_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64);
+    c->infer_inner = env_int("FXG_INFER_INNER", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
-    c->n_groups = env_int("FXG_GROUPS", 4, 1, fxg_ctx::kMaxGroups);
-    int const nw = default_workers(c->n_groups);
+    c->n_groups = env_int("FXG_GROUPS", 8, 1, fxg_ctx::kMaxGroups);
+    c->workers_busy = default_workers(c->n_groups);
+    int const nw = std::getenv("FXG_WORKERS") ? c->workers_busy : std::min(8, 2 * c->workers_busy);   // an explicit count is taken literally
     for (int gi = 0; gi < c->n_groups; ++gi) {
         WorkerGroup& g = c->groups[gi];
         ok = ok && cudaEventCreate(&g.ev_run0) == cudaSuccess && cudaEventCreate(&g.ev_run1) == cudaSuccess &&
@@ -1347,7 +1431,9 @@ int fxg_create(int device, fxg_ctx** out) {
             ok = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) == cudaSuccess &&
                  cudaEventCreate(&w->ev0) == cudaSuccess && cudaEventCreate(&w->ev1) == cudaSuccess &&
                  cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-            ok = ok && cudaEventCreate(&w->ev_w0) == cudaSuccess && cudaEventCreate(&w->ev_b0) == cudaSuccess && cudaEventCreate(&w->ev_b1) == cudaSuccess;
+            ok = ok && cudaEventCreate(&w->ev_w0) == cudaSuccess && cudaEventCreate(&w->ev_b0) == cudaSuccess && cudaEventCreate(&w->ev_b1) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&w->ev_sleep, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
+            w->spin_us = env_int("FXG_SPIN_US", 150, 0, 1000000);
             for (int q = 0; ok && q < Worker::kWalkSlots; ++q)
                 ok = cudaStreamCreateWithFlags(&w->walk_stream[q], cudaStreamNonBlocking) == cudaSuccess &&
                      cudaEventCreateWithFlags(&w->ev_walk_done[q], cudaEventDisableTiming) == cudaSuccess &&
@@ -1585,7 +1671,7 @@ int verify_run_group(fxg_ctx* c, WorkerGroup& grp, fxg_job* J, StageGate* gate, 
     if (n_reads == 0) { J->ran = true; return FXG_OK; }
 
     // ---- split the reads into contiguous parts with similar numbers of anchors, one part per worker ----
-    size_t const n_parts = std::min<size_t>(grp.workers.size(), std::max<size_t>(1, std::min<size_t>(n_reads, size_t(J->read_walk_begin[n_reads]) / 256 + 1)));
+    size_t const n_parts = std::min<size_t>(grp.use_workers, std::max<size_t>(1, std::min<size_t>(n_reads, size_t(J->read_walk_begin[n_reads]) / 256 + 1)));
     std::vector<uint32_t> cut(n_parts + 1, 0);
     for (size_t p = 1; p < n_parts; ++p) {
         uint64_t const target = uint64_t(J->read_walk_begin[n_reads]) * p / n_parts;

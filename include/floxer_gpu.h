@@ -143,6 +143,7 @@ typedef struct {
     double root_launch_ms;           /* CUDA-event time of the largest launch of every root wave (the dominant launch) ... */
     uint64_t root_launch_word_steps; /* ... and the word-steps those launches issued */
     uint64_t shared_tracebacks;      /* accepted root alignments that took begin position and CIGAR from an identical one */
+    uint64_t inferred_inner;         /* inner-node alignments whose existence followed from another walk of the same node */
 } fxg_counters;
 
 /* ---- life cycle ---- */

@@ -1,4 +1,5 @@
-"""Development aid: throughput of fxg_verify_run with several batches in flight (FXG_GROUPS / FXG_WORKERS knobs)."""
+"""Development aid: throughput of fxg_verify_run with several batches in flight (FXG_GROUPS / FXG_WORKERS knobs);
+prints wall and process-CPU milliseconds per step."""
 import sys, os, time, threading
 sys.path.insert(0, os.getcwd())
 import bench
@@ -10,10 +11,10 @@ ctx = g.Context(0); ctx.set_references(refs)
 jobs = [ctx.stage_verify(batch, VerifyConfig()) for _ in range(depth)]
 def lanes(n):
     ts = [threading.Thread(target=lambda j=j: [j.run() for _ in range(n)]) for j in jobs]
-    t0 = time.perf_counter()
+    c0 = time.process_time(); t0 = time.perf_counter()
     for t in ts: t.start()
     for t in ts: t.join()
-    return (time.perf_counter() - t0) * 1e3 / (n * depth)
+    dt = time.perf_counter() - t0; dc = time.process_time() - c0
+    return round(dt * 1e3 / (n * depth), 2), round(dc * 1e3 / (n * depth), 1)
 lanes(3)
-res = [lanes(6) for _ in range(3)]
-print({k: os.environ[k] for k in os.environ if k.startswith("FXG_")}, "ms per step", ["%.2f" % r for r in res])
+print({k: os.environ[k] for k in os.environ if k.startswith("FXG_")}, "ms per step (wall, cpu)", [lanes(6) for _ in range(3)])
