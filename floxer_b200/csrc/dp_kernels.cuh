@@ -855,6 +855,69 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Last-row minimum over a range of columns, from the checkpoint records of a score pass.
+//
+// Several root windows of one query piece that nearly coincide are scored by ONE pass over their union (host side:
+// run_root_passes).  The records of the pass' last block hold the horizontal deltas of row m for every column the block
+// worked on, and the pass reported one (value, column) of that row; so the values of row m at all those columns follow by
+// summing deltas, and each member window gets the minimum over its own columns and the rightmost column attaining it
+// (alignment.cpp:128-139 / the engine's `sc <= best`).  One thread per member window.
+// ---------------------------------------------------------------------------------------------
+struct RangeMinTask {
+    uint64_t ck_base;                  // first word of the pass' checkpoint records
+    uint32_t n, m; int32_t dlo, dhi;   // the pass
+    uint32_t W;                        // its block width (words per lane)
+    uint32_t col_from, col_to;         // the member's columns in the pass' numbering (1-based, inclusive)
+    int32_t known_score; uint32_t known_col;   // what the pass reported
+    uint32_t out;
+};
+
+__global__ void range_min_kernel(const RangeMinTask* __restrict__ tasks, uint32_t n_tasks, const uint32_t* __restrict__ ck_all, DpResult* __restrict__ results) {
+    uint32_t const id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_tasks) return;
+    RangeMinTask const T = tasks[id];
+    uint32_t const W = T.W, ROWS = 32 * W, RECW = ck_record_words(W), BO = W == 1 ? 2 : 2 * W;
+    uint32_t const nb = (T.m + ROWS - 1) / ROWS, lb = nb - 1;
+    uint32_t const pad = nb * ROWS - T.m;
+    int32_t const dlo = T.dlo - int32_t(pad), dhi = T.dhi - int32_t(pad);
+    int32_t const lo = int32_t(ROWS) * int32_t(lb) + 1 + dlo, hi = int32_t(ROWS) * int32_t(nb) + dhi;
+    int32_t const cs = lo < 1 ? 1 : lo, ce = hi > int32_t(T.n) ? int32_t(T.n) : hi;       // columns the last block worked on
+    uint32_t const ck_per_block = ck_records_per_block(int64_t(T.dhi) - int64_t(T.dlo) + 1, ROWS);
+    uint32_t const q_first = uint32_t(cs + int32_t(lb) + 31) >> 5;
+    const uint32_t* const recs = ck_all + T.ck_base + uint64_t(lb) * ck_per_block * RECW + BO;
+    // deltas of step t (column t - lb): bit (t - 1) % 32 of record (t + 31) / 32
+    auto rec_of = [&](uint32_t t) { return reinterpret_cast<const uint2*>(recs + uint64_t(((t + 31) >> 5) - q_first) * RECW); };
+    // sum of the deltas of columns cs .. x (0 for x < cs)
+    auto prefix = [&](int32_t x) -> int32_t {
+        if (x < cs) return 0;
+        uint32_t const t0 = uint32_t(cs) + lb, t1 = uint32_t(x) + lb;
+        int32_t sum = 0;
+        for (uint32_t q = (t0 + 31) >> 5; q <= (t1 + 31) >> 5; ++q) {
+            uint2 const v = *rec_of(32 * (q - 1) + 1);
+            uint32_t const first = 32 * (q - 1) + 1;                  // step of bit 0
+            uint32_t mask = 0xffffffffu;
+            if (t0 > first) mask &= 0xffffffffu << (t0 - first);
+            if (t1 < first + 31) mask &= 0xffffffffu >> (first + 31 - t1);
+            sum += __popc(v.x & mask) - __popc(v.y & mask);
+        }
+        return sum;
+    };
+    DpResult R; R.score = kNoScore; R.end_col = 0;
+    int32_t const a = int32_t(T.col_from) > cs ? int32_t(T.col_from) : cs, b = int32_t(T.col_to) < ce ? int32_t(T.col_to) : ce;
+    if (a <= b && T.known_score < kNoScore && int32_t(T.known_col) >= cs && int32_t(T.known_col) <= ce) {
+        int32_t sc = T.known_score - prefix(int32_t(T.known_col)) + prefix(a - 1);        // row m at column a - 1
+        uint2 v = make_uint2(0u, 0u);
+        for (int32_t col = a; col <= b; ++col) {
+            uint32_t const t = uint32_t(col) + lb, bit = (t - 1) & 31u;
+            if (col == a || bit == 0) v = *rec_of(t);
+            sc += int32_t((v.x >> bit) & 1u) - int32_t((v.y >> bit) & 1u);
+            if (sc <= R.score) { R.score = sc; R.end_col = uint32_t(col); }
+        }
+    }
+    results[T.out] = R;
+}
+
+// ---------------------------------------------------------------------------------------------
 // int32 issue-rate microbenchmark: the 8 LOP3 : 1 IADD3 : 2 SHF mix of one Myers word-step,
 // 8 independent chains per thread so that the pipes, not dependencies, limit the rate.
 // ---------------------------------------------------------------------------------------------

@@ -141,10 +141,10 @@ struct Worker {
     // tracebacks are long chains of dependent steps: the root alignments of a wave are cut into chunks, each chunk's
     // tracebacks run on a stream of their own beside the score passes (and tracebacks) of the other chunks
     static constexpr int kWalkSlots = 4;
-    DevBuf d_tasks, d_results, d_ck[kWalkSlots], d_wtasks, d_wresults, d_cigars;
+    DevBuf d_tasks, d_results, d_ck[kWalkSlots], d_wtasks, d_wresults, d_cigars, d_rtasks, d_rresults;
     cudaStream_t walk_stream[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_walk_done[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr}, ev_w0 = nullptr, ev_w1[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
-    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults;
+    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults, h_rtasks, h_rresults;
     fxg_counters ctr{};
     std::string err;
     std::vector<ConfigCacheEntry> cfg_cache = std::vector<ConfigCacheEntry>(8192);
@@ -152,7 +152,7 @@ struct Worker {
     std::vector<Config> cfgs;
     uint64_t cig_used = 0;               // ops of d_cigars filled by the current run
     void release() {
-        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars}) b->release();
+        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults}) b->release();
         if (ev_w0) { cudaEventDestroy(ev_w0); ev_w0 = nullptr; }
         if (ev_b0) { cudaEventDestroy(ev_b0); ev_b0 = nullptr; }
         if (ev_b1) { cudaEventDestroy(ev_b1); ev_b1 = nullptr; }
@@ -164,7 +164,7 @@ struct Worker {
             if (walk_stream[q]) cudaStreamDestroy(walk_stream[q]);
             ev_walk_done[q] = ev_w1[q] = nullptr; walk_stream[q] = nullptr;
         }
-        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults}) b->release();
+        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults, &h_rtasks, &h_rresults}) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -230,6 +230,7 @@ struct fxg_ctx {
     DevBuf d_tmp;
     uint64_t trace_budget = 0;
     int workers_busy = 4;                        // workers a group uses when more than a quarter of the groups are busy
+    bool share_root_passes = true;               // FXG_SHARE_ROOTS=0 scores every root window on its own (development knob)
     bool infer_inner = true;                     // FXG_INFER_INNER=0 computes every inner window (development knob)
     int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
     std::vector<Pool> spare_pools;       // device buffers of freed batches / jobs, reused by the next stage call
@@ -310,6 +311,7 @@ void add_counters(fxg_counters& a, fxg_counters const& b) {
     a.kernel_launches += b.kernel_launches; a.dp_tasks += b.dp_tasks; a.dp_word_steps += b.dp_word_steps;
     a.dp_cells_full += b.dp_cells_full; a.trace_bytes += b.trace_bytes; a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
     a.root_launch_ms += b.root_launch_ms; a.root_launch_word_steps += b.root_launch_word_steps; a.shared_tracebacks += b.shared_tracebacks; a.inferred_inner += b.inferred_inner;
+    a.shared_score_passes += b.shared_score_passes; a.rescored_roots += b.rescored_roots;
     a.trace_word_steps += b.trace_word_steps; a.dp_kernel_ms += b.dp_kernel_ms; a.trace_kernel_ms += b.trace_kernel_ms; a.waves += b.waves; a.run_ms += b.run_ms;
 }
 
@@ -642,6 +644,18 @@ struct RootOut {
 // at most max_errors[i]; accepted passes get their CIGAR, written by the device into a slot of cigar_cap_for(score) ops
 // of the worker's cigar buffer (slots follow each other from w.cig_used on).  Works in chunks bounded by `budget_bytes`
 // of checkpoint records.
+//
+// Shared score passes.  The anchors of one true locus lead to root windows of the same query piece that nearly coincide
+// (they differ by the indels between the seeds).  Such windows are scored by ONE pass over their union U: for a member
+// window B inside U, row m of B's own matrix is >= row m of U's at every column of B (B allows fewer start positions),
+// with equality wherever some optimal alignment of U's cell starts inside B.  So with (L, e) = the minimum of U's row m
+// over B's columns and the rightmost column attaining it (range_min_kernel):
+//   * L > k: B holds no alignment with <= k errors either;
+//   * L <= k and e - m - L >= (start of B - start of U): every alignment of cost L ending at e spans at most m + L
+//     columns, hence starts inside B; B's matrix then agrees with U's on every cell such an alignment touches, B's
+//     minimum is L, no column right of e attains it, and the traceback takes the same decisions (the argument of the
+//     shared tracebacks below) -- B's result is read off U's pass, shifted by the windows' distance;
+//   * otherwise B is scored again on its own.
 int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const& passes, std::vector<uint32_t> const& max_errors,
                     uint64_t budget_bytes, std::vector<RootOut>& outs) {
     size_t const N = passes.size();
@@ -651,26 +665,92 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
     // kWalkSlots checkpoint buffers: the tracebacks of a chunk read one while the score passes of the next chunks fill the others
     uint64_t budget_words = std::max<uint64_t>(budget_bytes / Worker::kWalkSlots, uint64_t(64) << 20) / 4;
 
-    std::vector<Config> cfgs(N);
-    std::vector<uint64_t> words(N);
-    uint64_t total_words = 0, cigar_bound = 0;
-    for (size_t i = 0; i < N; ++i) {
-        if (!cached_config(w, passes[i], c->smem_limit, cfgs[i]))
+    // ---- units: the passes that are actually run, each serving one or more member windows ----
+    struct Unit { Pass p; uint32_t k; uint32_t first, count; Config cfg; uint64_t words; };
+    std::vector<Unit> units;
+    std::vector<uint32_t> unit_members;
+    auto finish_unit = [&](Unit& u) -> int {
+        if (!cached_config(w, u.p, c->smem_limit, u.cfg))
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
-                        passes[i].m, passes[i].n, passes[i].dlo, passes[i].dhi);
-        uint32_t const W = uint32_t(kWidths[cfgs[i].widx]);
-        uint64_t const per_block = ck_records_per_block(int64_t(passes[i].dhi) - int64_t(passes[i].dlo) + 1, 32 * W);
-        words[i] = (uint64_t(cfgs[i].nb) * per_block * ck_record_words(W) + 3) & ~uint64_t(3);
-        if (words[i] > budget_words) budget_words = words[i];
-        total_words += words[i];
-        cigar_bound += cigar_cap_for(max_errors[i]);
+                        u.p.m, u.p.n, u.p.dlo, u.p.dhi);
+        uint32_t const W = uint32_t(kWidths[u.cfg.widx]);
+        uint64_t const per_block = ck_records_per_block(int64_t(u.p.dhi) - int64_t(u.p.dlo) + 1, 32 * W);
+        u.words = (uint64_t(u.cfg.nb) * per_block * ck_record_words(W) + 3) & ~uint64_t(3);
+        return FXG_OK;
+    };
+    auto add_single = [&](uint32_t q) -> int {
+        Unit u{passes[q], max_errors[q], uint32_t(unit_members.size()), 1, Config{}, 0};
+        unit_members.push_back(q);
+        int const rc = finish_unit(u);
+        if (rc == FXG_OK) units.push_back(u);
+        return rc;
+    };
+    {
+        std::vector<uint32_t> order(N);
+        for (size_t i = 0; i < N; ++i) order[i] = uint32_t(i);
+        if (c->share_root_passes)
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                Pass const& x = passes[a]; Pass const& y = passes[b];
+                if (x.query_base != y.query_base) return x.query_base < y.query_base;
+                if (x.m != y.m) return x.m < y.m;
+                if (x.ref_base != y.ref_base) return x.ref_base < y.ref_base;
+                return a < b;
+            });
+        // cost of a pass ~ columns x (diagonals of the band + one block of rows)
+        auto cost = [](uint64_t n, uint64_t m, uint64_t k) { return double(n) * double(int64_t(n) - int64_t(m) + 2 * int64_t(k) + 256); };
+        size_t i = 0;
+        while (i < N) {
+            uint32_t const q0 = order[i];
+            Pass const& P0 = passes[q0];
+            uint64_t const k0 = max_errors[q0];
+            uint64_t u_start = P0.ref_base, u_end = P0.ref_base + P0.n;
+            size_t j = i + 1;
+            if (c->share_root_passes && P0.flags == 0) {
+                while (j < N) {
+                    Pass const& B = passes[order[j]];
+                    if (B.query_base != P0.query_base || B.m != P0.m || B.flags != 0 || max_errors[order[j]] != k0 || B.ref_base > u_end) break;
+                    uint64_t const new_end = std::max(u_end, B.ref_base + B.n);
+                    if (cost(new_end - u_start, P0.m, k0) > cost(u_end - u_start, P0.m, k0) + 0.75 * cost(B.n, B.m, k0)) break;
+                    u_end = new_end;
+                    ++j;
+                }
+            }
+            if (j - i == 1) {
+                int const rc = add_single(q0);
+                if (rc != FXG_OK) return rc;
+            } else {
+                Unit u{};
+                u.k = uint32_t(k0); u.first = uint32_t(unit_members.size()); u.count = uint32_t(j - i);
+                for (size_t q = i; q < j; ++q) unit_members.push_back(order[q]);
+                // the union as a window of its own: same band rule as score_pass_for
+                u.p = P0; u.p.n = uint32_t(u_end - u_start);
+                u.p.dlo = -int32_t(k0); u.p.dhi = int32_t(int64_t(u.p.n) - int64_t(u.p.m) + int64_t(k0));
+                int const rc = finish_unit(u);
+                if (rc != FXG_OK) return rc;
+                units.push_back(u);
+            }
+            i = j;
+        }
     }
+    units.reserve(units.size() + N); unit_members.reserve(unit_members.size() + N);      // members scored again are appended while units are referenced
+    uint64_t total_words = 0, max_words = 0, cigar_bound = 0;
+    for (Unit const& u : units) { total_words += u.words; max_words = std::max(max_words, u.words); }
+    for (size_t i = 0; i < N; ++i) {
+        cigar_bound += cigar_cap_for(max_errors[i]);
+        // a member that has to be scored again on its own must fit the budget as well
+        Config cf;
+        if (cached_config(w, passes[i], c->smem_limit, cf)) {
+            uint32_t const W = uint32_t(kWidths[cf.widx]);
+            max_words = std::max(max_words, (uint64_t(cf.nb) * ck_records_per_block(int64_t(passes[i].dhi) - int64_t(passes[i].dlo) + 1, 32 * W) * ck_record_words(W) + 3) & ~uint64_t(3));
+        }
+    }
+    if (max_words > budget_words) budget_words = max_words;
     // optionally cut a large batch into chunks whose tracebacks run beside the next chunk's score passes (measured on
     // config 2: no gain -- a traceback is one long chain of dependent steps, so the last chunk's tail stays, and the
     // tracebacks' shared memory takes occupancy from the score passes -- hence one chunk unless memory forces more)
     int const n_chunks = c->root_chunks, chunk_min = c->root_chunk_min;
-    if (N >= size_t(chunk_min) && n_chunks > 1)
-        budget_words = std::min(budget_words, std::max<uint64_t>(total_words / uint64_t(n_chunks) + 1, *std::max_element(words.begin(), words.end())));
+    if (units.size() >= size_t(chunk_min) && n_chunks > 1)
+        budget_words = std::min(budget_words, std::max<uint64_t>(total_words / uint64_t(n_chunks) + 1, max_words));
     // no reallocation while tracebacks are in flight: everything they write to is sized up front
     CUDA_TRY(w.err, w.d_cigars.ensure_preserving((w.cig_used + cigar_bound) * 4, w.cig_used * 4, w.stream));
     CUDA_TRY(w.err, w.h_wtasks.ensure(N * sizeof(Walk2Task)));
@@ -682,9 +762,13 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
 
     g_prof.lap(w, 7);
     std::vector<Pass> chunk; std::vector<uint64_t> ck_base;
-    std::vector<uint32_t> hit_pass;          // accepted passes in traceback order (index into passes)
+    std::vector<uint32_t> hit_pass;          // accepted members in traceback order (index into passes) ...
+    std::vector<uint64_t> hit_shift;         // ... and how far their window starts behind the window of the pass that was traced
+    std::vector<uint8_t> hit_widx;
+    struct Accepted { uint32_t member, unit_in_chunk; uint32_t end_col_u; uint32_t score; };
+    std::vector<Accepted> accepted;
     constexpr uint32_t kOwnTraceback = 0xfffffffeu, kNotAccepted = 0xffffffffu;
-    std::vector<uint32_t> dup_of(N, kNotAccepted);   // pass whose traceback this one shares, or one of the two marks
+    std::vector<uint32_t> dup_of(N, kNotAccepted);   // member whose traceback this one shares, or one of the two marks
     struct DupKey {
         uint64_t query_base, end_abs; uint32_t m, score, flags;
         bool operator==(DupKey const& o) const { return query_base == o.query_base && end_abs == o.end_abs && m == o.m && score == o.score && flags == o.flags; }
@@ -701,11 +785,13 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
     size_t i = 0;
     int k = 0;
     bool walk_timed = false;
-    while (i < N) {
+    while (i < units.size()) {
         size_t j = i; uint64_t used = 0;
         chunk.clear(); ck_base.clear();
-        while (j < N && (j == i || used + words[j] <= budget_words)) {
-            chunk.push_back(passes[j]); ck_base.push_back(used); used += words[j];
+        size_t n_shared = 0;                 // members of this chunk that read their result off a shared pass
+        while (j < units.size() && (j == i || used + units[j].words <= budget_words)) {
+            chunk.push_back(units[j].p); ck_base.push_back(used); used += units[j].words;
+            if (units[j].count > 1) n_shared += units[j].count;
             ++j;
         }
         size_t const M = j - i;
@@ -720,9 +806,38 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         if (rc != FXG_OK) return rc;
         w.ctr.trace_bytes += used * 4;
         g_prof.start(w);
+        // ---- the members of shared passes: minimum of the last row over their own columns ----
+        const DpResult* mres = nullptr;
+        if (n_shared) {
+            CUDA_TRY(w.err, w.h_rtasks.ensure(n_shared * sizeof(RangeMinTask)));
+            CUDA_TRY(w.err, w.d_rtasks.ensure(n_shared * sizeof(RangeMinTask)));
+            CUDA_TRY(w.err, w.h_rresults.ensure(n_shared * sizeof(DpResult)));
+            CUDA_TRY(w.err, w.d_rresults.ensure(n_shared * sizeof(DpResult)));
+            RangeMinTask* rt = w.h_rtasks.as<RangeMinTask>();
+            size_t r = 0;
+            for (size_t u = 0; u < M; ++u) {
+                Unit const& U = units[i + u];
+                if (U.count < 2) continue;
+                for (uint32_t q = 0; q < U.count; ++q) {
+                    Pass const& B = passes[unit_members[U.first + q]];
+                    RangeMinTask& t = rt[r];
+                    t.ck_base = ck_base[u]; t.n = U.p.n; t.m = U.p.m; t.dlo = U.p.dlo; t.dhi = U.p.dhi; t.W = uint32_t(kWidths[U.cfg.widx]);
+                    t.col_from = uint32_t(B.ref_base - U.p.ref_base) + 1; t.col_to = uint32_t(B.ref_base - U.p.ref_base) + B.n;
+                    t.known_score = res[u].score; t.known_col = res[u].end_col; t.out = uint32_t(r);
+                    ++r;
+                }
+            }
+            CUDA_TRY(w.err, cudaMemcpyAsync(w.d_rtasks.p, rt, n_shared * sizeof(RangeMinTask), cudaMemcpyHostToDevice, w.stream));
+            range_min_kernel<<<uint32_t((n_shared + 63) / 64), 64, 0, w.stream>>>(w.d_rtasks.as<RangeMinTask>(), uint32_t(n_shared), ckb.as<uint32_t>(),
+                                                                                 w.d_rresults.as<DpResult>());
+            CUDA_TRY(w.err, cudaGetLastError());
+            CUDA_TRY(w.err, cudaMemcpyAsync(w.h_rresults.p, w.d_rresults.p, n_shared * sizeof(DpResult), cudaMemcpyDeviceToHost, w.stream));
+            CUDA_TRY(w.err, w.wait_for(w.stream));
+            w.ctr.kernel_launches++;
+            w.ctr.h2d_bytes += n_shared * sizeof(RangeMinTask); w.ctr.d2h_bytes += n_shared * sizeof(DpResult);
+            mres = w.h_rresults.as<DpResult>();
+        }
         // ---- tracebacks of the accepted ones on their own stream, one launch per block width ----
-        size_t const H0 = H;
-        for (size_t q = 0; q < M; ++q) { outs[i + q].score = res[q].score; outs[i + q].end_col = res[q].end_col; }
         // Alignments of the same query piece that end at the same reference position with the same score -- the usual case:
         // every true anchor of a read leads to the same locus -- have the same traceback, provided every optimal alignment
         // ending there starts inside each of their windows: an alignment of cost s ending at column e spans at least
@@ -730,28 +845,52 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         // begin at or before that bound contain every such alignment, the DP values along them agree, and so does every
         // "left / up / diagonal" decision.  One member of such a group is traced back, the others
         // share its begin position and its cigar.
-        dup_key.clear();
-        for (size_t q = 0; q < M; ++q) {
-            if (res[q].score > int32_t(max_errors[i + q])) { dup_of[i + q] = kNotAccepted; continue; }
-            Pass const& P = chunk[q];
-            uint64_t const end_abs = P.ref_base + res[q].end_col;
-            bool const safe = int64_t(end_abs) - int64_t(P.m) - int64_t(res[q].score) >= int64_t(P.ref_base);
-            dup_of[i + q] = kOwnTraceback;
-            if (!safe) continue;
-            DupKey const key{P.query_base, end_abs, P.m, uint32_t(res[q].score), P.flags};
-            auto const ins = dup_key.emplace(key, uint32_t(i + q));
-            if (!ins.second) dup_of[i + q] = ins.first->second;          // shares the traceback of an earlier pass of this chunk
+        size_t const H0 = H;
+        accepted.clear();
+        {
+            size_t r = 0;
+            for (size_t u = 0; u < M; ++u) {
+                Unit const& U = units[i + u];
+                for (uint32_t q = 0; q < U.count; ++q) {
+                    uint32_t const mem = unit_members[U.first + q];
+                    Pass const& B = passes[mem];
+                    DpResult const R = U.count > 1 ? mres[r++] : res[u];
+                    uint64_t const shift = B.ref_base - U.p.ref_base;
+                    outs[mem].score = R.score; outs[mem].end_col = uint32_t(R.end_col - shift);
+                    dup_of[mem] = kNotAccepted;
+                    if (R.score > int32_t(max_errors[mem])) { if (U.count > 1) w.ctr.shared_score_passes++; continue; }
+                    // (store coordinates: the alignment's first base is at or after end - m - score)
+                    bool const safe = int64_t(R.end_col) - int64_t(B.m) - int64_t(R.score) >= int64_t(shift);
+                    if (U.count > 1) {
+                        if (!safe) {                             // scored again on its own, in a later chunk
+                            outs[mem] = RootOut{kNoScore, 0, 0, 0, 0};
+                            rc = add_single(mem);
+                            if (rc != FXG_OK) return rc;
+                            w.ctr.rescored_roots++;
+                            continue;
+                        }
+                        w.ctr.shared_score_passes++;
+                    }
+                    dup_of[mem] = kOwnTraceback;
+                    if (safe) {
+                        DupKey const key{B.query_base, U.p.ref_base + R.end_col, B.m, uint32_t(R.score), B.flags};
+                        auto const ins = dup_key.emplace(key, mem);
+                        if (!ins.second) { dup_of[mem] = ins.first->second; continue; }      // shares the traceback of an earlier member
+                    }
+                    accepted.push_back(Accepted{mem, uint32_t(u), R.end_col, uint32_t(R.score)});
+                }
+            }
         }
         for (int wi = 0; wi < 6; ++wi) {
-            for (size_t q = 0; q < M; ++q) {
-                if (cfgs[i + q].widx != wi || dup_of[i + q] != kOwnTraceback) continue;
-                Pass const& P = chunk[q];
+            for (Accepted const& a : accepted) {
+                Unit const& U = units[i + a.unit_in_chunk];
+                if (U.cfg.widx != wi) continue;
                 Walk2Task& t = wt[H];
-                t.ck_base = ck_base[q]; t.ref_base = P.ref_base; t.query_base = P.query_base;
-                t.cigar_cap = uint32_t(cigar_cap_for(uint32_t(res[q].score))); t.cigar_base = cig_at; cig_at += t.cigar_cap;
-                t.n = P.n; t.m = P.m; t.dlo = P.dlo; t.dhi = P.dhi; t.end_col = res[q].end_col; t.score = uint32_t(res[q].score);
-                t.flags = P.flags; t.out = uint32_t(H); t.reserved = 0;
-                hit_pass.push_back(uint32_t(i + q));
+                t.ck_base = ck_base[a.unit_in_chunk]; t.ref_base = U.p.ref_base; t.query_base = U.p.query_base;
+                t.cigar_cap = uint32_t(cigar_cap_for(a.score)); t.cigar_base = cig_at; cig_at += t.cigar_cap;
+                t.n = U.p.n; t.m = U.p.m; t.dlo = U.p.dlo; t.dhi = U.p.dhi; t.end_col = a.end_col_u; t.score = a.score;
+                t.flags = U.p.flags; t.out = uint32_t(H); t.reserved = 0;
+                hit_pass.push_back(a.member); hit_shift.push_back(passes[a.member].ref_base - U.p.ref_base); hit_widx.push_back(uint8_t(wi));
                 ++H;
             }
         }
@@ -765,9 +904,9 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
             size_t h0 = H0;
             int n_launch = 0;
             while (h0 < H) {
-                int const widx = cfgs[hit_pass[h0]].widx;
+                int const widx = hit_widx[h0];
                 size_t h1 = h0;
-                while (h1 < H && cfgs[hit_pass[h1]].widx == widx) ++h1;
+                while (h1 < H && hit_widx[h1] == widx) ++h1;
                 Walk2Launch WL{};
                 WL.tasks = w.d_wtasks.as<Walk2Task>() + h0; WL.n_tasks = uint32_t(h1 - h0); WL.ck = ckb.as<uint32_t>();
                 WL.ref_packed = c->refs.packed.as<uint32_t>(); WL.inline_packed = pool.inline_packed.as<uint32_t>();
@@ -808,10 +947,10 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         w.ctr.trace_kernel_ms += best;
     }
     for (size_t h = 0; h < H; ++h) {
-        if (wr[h].cigar_len == 0xffffffffu)
+        if (wr[h].cigar_len == 0xffffffffu || wr[h].begin_col < hit_shift[h])
             return fail(w.err, FXG_ERR_CUDA, "internal: the traceback of an alignment disagrees with its score pass");
         RootOut& o = outs[hit_pass[h]];
-        o.begin_col = wr[h].begin_col; o.cigar_len = wr[h].cigar_len;
+        o.begin_col = uint32_t(wr[h].begin_col - hit_shift[h]); o.cigar_len = wr[h].cigar_len;     // seen from the member's own window
         o.cigar_offset = wt[h].cigar_base + wt[h].cigar_cap - wr[h].cigar_len;
     }
     for (size_t q = 0; q < N; ++q) {
@@ -1160,44 +1299,58 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     // well: their windows begin at or before the first one's, so the alignment -- which began somewhere inside the first
     // window -- lies inside theirs.  Identical windows share the answer either way.  Only the walks that remain undecided
     // are computed in a second launch of the level.
-    struct Ask { uint64_t key, ws, we; uint32_t wi; uint32_t pass; };   // pass: index into asks' Pass array, or none
-    constexpr uint32_t kNoPass = 0xffffffffu;
-    std::vector<Ask> asks; std::vector<Pass> ask_pass;
-    std::vector<uint32_t> first, second, second_ask;                    // asks computed in the first / second launch
+    struct Ask { uint64_t ws, qbase; uint32_t len, m, k, wi, key; bool feasible; };
+    auto pass_of = [](Ask const& a) {
+        Pass p;
+        p.ref_base = a.ws; p.query_base = a.qbase; p.n = a.len; p.m = a.m;
+        p.dlo = -int32_t(a.k); p.dhi = int32_t(int64_t(a.len) - int64_t(a.m) + int64_t(a.k)); p.flags = 0;   // score_pass_for
+        return p;
+    };
+    // (node, strand) -> the ask that goes first, in a table over the node indices this part's reads use
+    uint64_t node_lo = UINT64_MAX, node_hi = 0;
+    for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
+        fxg_read const& R = J->reads_p[ri];
+        node_lo = std::min<uint64_t>(node_lo, R.node_offset); node_hi = std::max<uint64_t>(node_hi, R.node_offset + R.num_inner + R.num_leaves);
+    }
+    bool const infer = c->infer_inner && node_hi > node_lo && (node_hi - node_lo) < (uint64_t(1) << 26);
+    std::vector<uint32_t> rep_of, rep_stamp;
+    if (infer) { rep_of.assign(size_t(node_hi - node_lo) * 2, 0); rep_stamp.assign(size_t(node_hi - node_lo) * 2, 0); }
+    uint32_t stamp = 0;
+    std::vector<Ask> asks;
+    std::vector<uint32_t> first, second;                                // asks computed in the first / second launch
     std::vector<int8_t> verdict;                                         // per ask: -1 undecided, 0 no alignment, 1 alignment exists
-    std::vector<uint64_t> rep_end;                                       // per ask: reference position where the alignment found ends
+    std::vector<uint64_t> rep_end;                                       // per ask computed first: reference position where the alignment found ends
     for (int cur_level = int(level.size()) - 1; cur_level >= 1; --cur_level) {
         g_prof.start(w);
         active.swap(level[size_t(cur_level)]);
         level[size_t(cur_level)].clear();
         if (active.empty()) continue;
         std::vector<uint32_t>& up = level[size_t(cur_level) - 1];
-        asks.clear(); ask_pass.clear();
-        for (uint32_t wi : active) {
+        size_t const NA = active.size();
+        asks.resize(NA); verdict.assign(NA, -1); rep_end.resize(NA);
+        ++stamp;
+        for (size_t q = 0; q < NA; ++q) {
+            uint32_t const wi = active[q];
             Walk& wk = walks[wi];
             fxg_anchor const& A = J->anchors_p[wk.anchor];
             Span const sp = span_of(wk, false);
-            uint32_t const m = uint32_t(wk.node->query_index_to - wk.node->query_index_from + 1);
-            uint64_t const qbase = (wk.orient ? J->pool_len : 0) + J->reads_p[wk.read].query_offset + wk.node->query_index_from;
+            Ask& a = asks[q];
+            a.m = uint32_t(wk.node->query_index_to - wk.node->query_index_from + 1);
+            a.k = uint32_t(wk.node->num_errors);
+            a.qbase = (wk.orient ? J->pool_len : 0) + J->reads_p[wk.read].query_offset + wk.node->query_index_from;
+            a.ws = c->refs.base[A.reference_id] + sp.offset; a.len = uint32_t(sp.length); a.wi = wi;
             // statistics, verification.cpp:238-242 (kept per walk: with the interval optimisation the walk may turn out not to count)
-            wk.n_inner++; wk.sum_inner += sp.length; wk.cells_inner += uint64_t(m) * sp.length;
-            Ask a;
-            a.key = (uint64_t(wk.node - J->nodes_p) << 1) | wk.orient;   // the node identifies the read as well
-            a.ws = c->refs.base[A.reference_id] + sp.offset; a.we = a.ws + sp.length;
-            a.wi = wi; a.pass = kNoPass;
-            Pass p;
-            if (score_pass_for(a.ws, qbase, uint32_t(sp.length), m, uint32_t(wk.node->num_errors), 0u, p)) { a.pass = uint32_t(ask_pass.size()); ask_pass.push_back(p); }
-            asks.push_back(a);
+            wk.n_inner++; wk.sum_inner += sp.length; wk.cells_inner += uint64_t(a.m) * sp.length;
+            a.feasible = a.m != 0 && int64_t(a.m) - int64_t(a.len) <= int64_t(a.k);          // else more insertions needed than errors allowed
+            if (!a.feasible) { verdict[q] = 0; continue; }
+            if (infer) {
+                a.key = uint32_t(uint64_t(wk.node - J->nodes_p) - node_lo) * 2 + wk.orient;   // the node identifies the read as well
+                if (rep_stamp[a.key] != stamp || a.ws > asks[rep_of[a.key]].ws) { rep_stamp[a.key] = stamp; rep_of[a.key] = uint32_t(q); }
+            }
         }
-        // groups: same node and strand, rightmost window first
-        std::sort(asks.begin(), asks.end(), [](Ask const& x, Ask const& y) { return x.key != y.key ? x.key < y.key : (x.ws != y.ws ? x.ws > y.ws : x.wi < y.wi); });
-        size_t const NA = asks.size();
-        verdict.assign(NA, -1); rep_end.assign(NA, 0);
         first.clear(); passes.clear();
-        for (size_t q = 0; q < NA; ++q) {
-            if (asks[q].pass == kNoPass) { verdict[q] = 0; continue; }     // more insertions needed than errors allowed: no alignment
-            if (!c->infer_inner || q == 0 || asks[q].key != asks[q - 1].key) { first.push_back(uint32_t(q)); passes.push_back(ask_pass[asks[q].pass]); }
-        }
+        for (size_t q = 0; q < NA; ++q)
+            if (asks[q].feasible && (!infer || rep_of[asks[q].key] == q)) { first.push_back(uint32_t(q)); passes.push_back(pass_of(asks[q])); }
         g_prof.lap(w, 2);
         if (g_prof.on && w.id == 0 && std::getenv("FXG_TRACE_WAVES"))
             fprintf(stderr, "[fxg] level %d: %zu walks, %zu computed first\n", cur_level, active.size(), passes.size());
@@ -1209,25 +1362,25 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
         g_prof.start(w);
         for (size_t f = 0; f < first.size(); ++f) {
             uint32_t const q = first[f];
-            bool const ok = res[f].score <= int32_t(walks[asks[q].wi].node->num_errors);
-            verdict[q] = ok ? 1 : 0;
+            verdict[q] = res[f].score <= int32_t(asks[q].k) ? 1 : 0;
             rep_end[q] = asks[q].ws + res[f].end_col;
         }
-        // what follows from the first walk of each group
-        second.clear(); second_ask.clear(); passes.clear();
-        size_t rep = 0;
-        for (size_t q = 0; q < NA; ++q) {
-            if (q == 0 || asks[q].key != asks[q - 1].key) { rep = q; continue; }
-            if (verdict[q] != -1) continue;
-            if (verdict[rep] != -1 && asks[q].ws == asks[rep].ws && asks[q].we == asks[rep].we) verdict[q] = verdict[rep];      // the same window
-            else if (verdict[rep] == 1 && asks[q].we >= rep_end[rep]) { verdict[q] = 1; w.ctr.inferred_inner++; }               // (ws <= the first one's by the order)
-            else { second.push_back(uint32_t(q)); passes.push_back(ask_pass[asks[q].pass]); }
+        // what follows from the walk that went first for its node
+        second.clear(); passes.clear();
+        if (infer) {
+            for (size_t q = 0; q < NA; ++q) {
+                if (verdict[q] != -1) continue;
+                Ask const& a = asks[q];
+                uint32_t const rep = rep_of[a.key];
+                if (a.ws == asks[rep].ws && a.len == asks[rep].len) verdict[q] = verdict[rep];                              // the same window
+                else if (verdict[rep] == 1 && a.ws + a.len >= rep_end[rep]) { verdict[q] = 1; w.ctr.inferred_inner++; }      // (ws <= the first one's by choice)
+                else { second.push_back(uint32_t(q)); passes.push_back(pass_of(a)); }
+            }
         }
         if (!passes.empty()) {
             out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
             if (out.rc != FXG_OK) return;
-            for (size_t f = 0; f < second.size(); ++f)
-                verdict[second[f]] = res[f].score <= int32_t(walks[asks[second[f]].wi].node->num_errors) ? 1 : 0;
+            for (size_t f = 0; f < second.size(); ++f) verdict[second[f]] = res[f].score <= int32_t(asks[second[f]].k) ? 1 : 0;
         }
         for (size_t q = 0; q < NA; ++q) {
             Walk& wk = walks[asks[q].wi];
@@ -1416,6 +1569,7 @@ int fxg_create(int device, fxg_ctx** out) {
     bool ok = cudaStreamCreateWithFlags(&c->stage_stream, cudaStreamNonBlocking) == cudaSuccess && set_all_smem_attrs(c->smem_limit) == cudaSuccess;
     c->root_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64);
     c->infer_inner = env_int("FXG_INFER_INNER", 1, 0, 1) != 0;
+    c->share_root_passes = env_int("FXG_SHARE_ROOTS", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
     c->n_groups = env_int("FXG_GROUPS", 8, 1, fxg_ctx::kMaxGroups);
     c->workers_busy = default_workers(c->n_groups);

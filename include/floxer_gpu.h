@@ -144,6 +144,8 @@ typedef struct {
     uint64_t root_launch_word_steps; /* ... and the word-steps those launches issued */
     uint64_t shared_tracebacks;      /* accepted root alignments that took begin position and CIGAR from an identical one */
     uint64_t inferred_inner;         /* inner-node alignments whose existence followed from another walk of the same node */
+    uint64_t shared_score_passes;    /* root windows whose result was read off a score pass over the union of several windows */
+    uint64_t rescored_roots;         /* root windows scored again on their own because the shared pass could not vouch for them */
 } fxg_counters;
 
 /* ---- life cycle ---- */
