@@ -141,7 +141,7 @@ def main() -> int:
                           f"hierarchical verification, interval optimization {'on' if cfg.interval_optimization else 'off'}, "
                           f"extra verification ratio 0.05, CIGAR output; anchors from the ground-truth stand-in seeder",
               "reads_per_gpu": W["reads"], "read_len": W["read_len"], "error_rate": W["error"],
-              "l2": "256 MiB written to HBM between steps (each step also streams 1.5 GB of checkpoint records, 12x the L2)",
+              "l2": "256 MiB written to HBM between steps (twice the 126 MB L2); the batches in flight run concurrently, so a step never finds its own data in L2",
               "batches_in_flight": max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "8"))))}
 
     # ------------------------------------------------------------------ CPU arm ("reference")
@@ -296,13 +296,14 @@ def main() -> int:
     e2e_ms = [e2e_s * 1e3 / n_e2e] * n_e2e
     e2e_ctr = ctx.counters()
 
-    # ---- roofline pass (rank 0): one host worker / one stream, so that kernels do not overlap and the
+    # ---- roofline passes (rank 0): one host worker / one stream, so that kernels do not overlap and the
     #      CUDA-event time of the DP launches is the time of those launches alone ----
-    roof_ctr = None
-    if rank == 0:
-        saved_env = {k: os.environ.get(k) for k in ("FXG_WORKERS", "FXG_GROUPS")}
-        os.environ["FXG_WORKERS"] = "1"
-        os.environ["FXG_GROUPS"] = "1"
+    n_roof = 3
+
+    def roofline_pass(extra_env):
+        env = {"FXG_WORKERS": "1", "FXG_GROUPS": "1", **extra_env}
+        saved_env = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
         ctx1 = g.Context(local_rank)
         for k, v in saved_env.items():
             if v is None:
@@ -313,14 +314,22 @@ def main() -> int:
         job1 = ctx1.stage_verify(batch, cfg)
         job1.run()
         ctx1.reset_counters()
-        n_roof = 3
         for it in range(n_roof):
             flush.fill_(it & 0xff)
             torch.cuda.synchronize()
             job1.run()
-        roof_ctr = ctx1.counters()
+        out = ctx1.counters()
         job1.free()
         ctx1.close()
+        return out
+
+    roof_ctr = prod_ctr = None
+    if rank == 0:
+        # the engine on a launch that fills the machine: every root window scored on its own, as when the windows of a
+        # batch do not coincide (14 542 score passes in one launch) ...
+        roof_ctr = roofline_pass({"FXG_SHARE_ROOTS": "0", "FXG_INFER_INNER": "0"})
+        # ... and the launches of the step as benchmarked (coinciding windows share one pass: 7x fewer word-steps)
+        prod_ctr = roofline_pass({})
 
     # max over ranks
     my = torch.tensor([sum(step_ms), sum(e2e_ms) / n_e2e * args.steps, sum(kernel_ms)], dtype=torch.float64, device="cuda")
@@ -341,9 +350,12 @@ def main() -> int:
     line = None
     if rank == 0:
         # roofline of the dominant kernel (the bit-vector DP engine): integer-ALU bound, SURVEY 8(d).
-        # `frac` is that of the engine's dominant launch -- the root-level dp_kernel launch of a step, which issues two
-        # thirds of all word-steps -- timed alone with its own CUDA event pair on its stream; `all_launches` is every
-        # score-pass launch of the step over the event time of the waves (small launches and their tails included).
+        # `frac` is that of the engine's root-level dp_kernel launch with every root window of the batch scored on its own
+        # (a launch that fills the machine), timed alone with its own CUDA event pair on its stream; `all_launches` is
+        # every score-pass launch of that step over the event time of the waves (small launches and their tails included);
+        # `as_benchmarked` is the same pair of figures for the step the headline numbers time, where coinciding windows
+        # share one pass: one batch alone then leaves most of the machine idle (the launches are chains of dependent
+        # steps, a few hundred warps wide), and the eight batches in flight fill it together.
         dp_s = roof_ctr["dp_kernel_ms"] * 1e-3
         ws = roof_ctr["dp_word_steps"]
         root_s = roof_ctr["root_launch_ms"] * 1e-3
@@ -356,7 +368,8 @@ def main() -> int:
                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
                     # (profiles/r01_final_ncu_full_summary.txt: 84.9 MB read, 1.446 GB written -- the checkpoint records)
                     "traffic": 1535876896,
-                    "kernel": "fxg::dp_kernel<4,true> -- the root-level launch of a step (score pass leaving traceback checkpoints)",
+                    "kernel": "fxg::dp_kernel<4,true> -- the root-level launch of a step (score pass leaving traceback checkpoints), "
+                              "every root window of the batch scored on its own (FXG_SHARE_ROOTS=0 FXG_INFER_INNER=0): the launch that fills the machine",
                     "how": "algorithmic 11 int32 instr per 32-cell word-step x word-steps issued by that launch (band-limited, counted on the "
                            "host from the band geometry) / CUDA-event time of the launch on its stream; peak = LOP3/IADD3/SHF 8:1:2 "
                            "issue-rate microbenchmark on this GPU in this run; HBM traffic is negligible (window + Eq words in, "
@@ -370,7 +383,26 @@ def main() -> int:
                                   "kernel_ms_per_step": roof_ctr["trace_kernel_ms"] / n_roof,
                                   "checkpoint_bytes_per_step": roof_ctr["trace_bytes"] / n_roof,
                                   "note": "latency-bound chain of dependent steps per alignment, not a bandwidth kernel"},
-                    "single_stream_device_ms_per_step": roof_ctr["run_ms"] / n_roof}
+                    "single_stream_device_ms_per_step": roof_ctr["run_ms"] / n_roof,
+                    "as_benchmarked": {
+                        "note": "one batch on one stream with window sharing on (the production path): launches too small to fill 148 SMs "
+                                "on their own, run concurrently with those of the other batches in flight",
+                        "root_launch_frac": (prod_ctr["root_launch_word_steps"] * MYERS_INSTR_PER_WORD_STEP / (prod_ctr["root_launch_ms"] * 1e-3) / int32_peak)
+                        if int32_peak and prod_ctr["root_launch_ms"] > 0 else None,
+                        "root_launch_ms": prod_ctr["root_launch_ms"] / n_roof,
+                        "root_launch_word_steps": prod_ctr["root_launch_word_steps"] / n_roof,
+                        "all_launches_frac": (prod_ctr["dp_word_steps"] * MYERS_INSTR_PER_WORD_STEP / (prod_ctr["dp_kernel_ms"] * 1e-3) / int32_peak)
+                        if int32_peak and prod_ctr["dp_kernel_ms"] > 0 else None,
+                        "dp_word_steps_per_step": prod_ctr["dp_word_steps"] / n_roof,
+                        "dp_kernel_ms_per_step": prod_ctr["dp_kernel_ms"] / n_roof,
+                        "cells_computed_per_step": prod_ctr["dp_word_steps"] * 32 / n_roof,
+                        "traceback_kernel_ms_per_step": prod_ctr["trace_kernel_ms"] / n_roof,
+                        "checkpoint_bytes_per_step": prod_ctr["trace_bytes"] / n_roof,
+                        "shared_score_passes_per_step": prod_ctr["shared_score_passes"] / n_roof,
+                        "rescored_roots_per_step": prod_ctr["rescored_roots"] / n_roof,
+                        "inferred_inner_per_step": prod_ctr["inferred_inner"] / n_roof,
+                        "shared_tracebacks_per_step": prod_ctr["shared_tracebacks"] / n_roof,
+                        "single_stream_device_ms_per_step": prod_ctr["run_ms"] / n_roof}}
         cpu_sec, cpu_stats, n_used = cpu_arm(refs, batch, cfg, args.cpu_sample_reads, threads)
         cpu_cells = cpu_stats["cells_inner"] + cpu_stats["cells_root"]
         line = {"metric": "pex_verification_gcups", "value": gcups, "unit": "GCUPS", "reads_per_s": reads_all / (ms_per_step * 1e-3),

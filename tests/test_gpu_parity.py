@@ -247,6 +247,71 @@ def test_verify_reads_repeats_and_dense_anchors(ctx, gpu, oracle, bottom_up):
         assert job.stats() == want_stats
 
 
+def _densified(batch, ref_lens, rng, spread, prob):
+    """every anchor followed (with probability prob) by a copy shifted by up to +-spread bases"""
+    bb = BatchBuilder()
+    for R in batch.reads:
+        no, ni, nl = int(R["node_offset"]), int(R["num_inner"]), int(R["num_leaves"])
+        qo, ql = int(R["query_offset"]), int(R["query_len"])
+        ao, af, ar = int(R["anchor_offset"]), int(R["num_anchors_forward"]), int(R["num_anchors_reverse"])
+
+        def densify(a):
+            out = []
+            for x in a:
+                out.append(tuple(int(v) for v in x))
+                if rng.random() < prob:
+                    shift = int(rng.integers(-spread, spread + 1))
+                    out.append((int(x[0]), int(x[1]), max(0, min(ref_lens[int(x[1])] - 1, int(x[2]) + shift)), int(x[3])))
+            return np.array(sorted(out), dtype=abi.ANCHOR_DTYPE)
+        bb.add(batch.forward_pool[qo:qo + ql], batch.reverse_pool[qo:qo + ql], batch.nodes[no:no + ni], batch.nodes[no + ni:no + ni + nl],
+               densify(batch.anchors[ao:ao + af]), densify(batch.anchors[ao + af:ao + af + ar]))
+    return bb.build()
+
+
+@pytest.mark.parametrize("ratio", [0.0, 0.05, 0.3])
+def test_shared_root_passes_and_rescoring(ctx, gpu, oracle, ratio):
+    """Root windows of one locus are scored by one pass over their union; a window the shared pass cannot vouch for
+    (tight windows, alignments that begin before it) is scored again on its own.  Same answers as window by window."""
+    refs = [synthetic.random_reference(90_000, 71), synthetic.random_reference(40_000, 72)]
+    ctx.set_references(refs)
+    base = synthetic.make_batch(refs, 12, 1000, 0.08, 73, gpu.pex_build, seed_errors=1, decoy_fraction=0.3)
+    dense = _densified(base, [90_000, 40_000], np.random.default_rng(5), 70, 0.8)
+    for cfg in (VerifyConfig(extra_verification_ratio=ratio), VerifyConfig(extra_verification_ratio=ratio, verification_kind=abi.KIND_DIRECT_FULL)):
+        ctx.reset_counters()
+        job = ctx.verify_reads(dense, cfg)
+        al, cg = job.alignments()
+        want, want_stats = oracle_verify_batch(oracle, refs, dense, cfg)
+        assert alignment_records(al, cg) == want and job.stats() == want_stats and len(want) > 20
+        c = ctx.counters()
+        assert c["shared_score_passes"] > 0
+        if ratio == 0.0:
+            assert c["rescored_roots"] > 0           # the tight windows make some members fall back
+        job.free()
+
+
+def test_sharing_knobs_do_not_change_results(gpu, monkeypatch):
+    refs = [synthetic.random_reference(120_000, 81)]
+    batch = _densified(synthetic.make_batch(refs, 10, 1500, 0.06, 83, gpu.pex_build, seed_errors=2, decoy_fraction=0.3),
+                       [120_000], np.random.default_rng(7), 40, 0.7)
+    results = []
+    for share, infer in (("1", "1"), ("0", "0")):
+        monkeypatch.setenv("FXG_SHARE_ROOTS", share)
+        monkeypatch.setenv("FXG_INFER_INNER", infer)
+        c2 = gpu.Context(0)
+        try:
+            c2.set_references(refs)
+            for cfg in (VerifyConfig(), VerifyConfig(interval_optimization=True)):
+                job = c2.verify_reads(batch, cfg)
+                al, cg = job.alignments()
+                results.append((alignment_records(al, cg), job.stats()))
+                cnt = c2.counters()
+                assert (cnt["shared_score_passes"] > 0) == (share == "1")
+                job.free()
+        finally:
+            c2.close()
+    assert results[0] == results[2] and results[1] == results[3] and len(results[0][0]) > 0
+
+
 def test_config2_shape_against_cpu_port(ctx, gpu):
     """5 kbp reads at 5 % (config 2 shape, fewer reads): the bit-vector CPU port (itself checked against the
     oracle in the CPU suite) is the checker at this size."""
