@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <ctime>
 #include <condition_variable>
 #include <cmath>
 #include <cstdarg>
@@ -189,6 +190,12 @@ struct WorkerGroup {
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr, ev_staged = nullptr;
     bool busy = false;
 };
+
+inline double thread_cpu_ms() {
+    timespec ts{};
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return double(ts.tv_sec) * 1e3 + double(ts.tv_nsec) * 1e-6;
+}
 
 // host-side phase timing, printed when FXG_PROFILE is set (development aid; worker 0 only)
 struct HostProf {
@@ -1121,7 +1128,8 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
     bool const ivopt = J->cfg.interval_optimization != 0;
     double const ratio = J->cfg.extra_verification_ratio;
     walks.clear(); groups.clear(); group_members.clear();
-    walks.reserve(J->read_walk_begin[read_hi] - J->read_walk_begin[read_lo]);
+    walks.resize(J->read_walk_begin[read_hi] - J->read_walk_begin[read_lo]);       // zeroed; filled in place
+    size_t n_out = 0;
     std::vector<std::vector<uint32_t>> tmp_groups;
     std::vector<int64_t> ref_to_group;
     for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
@@ -1137,7 +1145,7 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
             for (uint32_t q = 0; q < na; ++q) {
                 fxg_anchor const& A = J->anchors_p[a0 + q];
                 fxg_pex_node const& leaf = leaves[A.pex_leaf_index];
-                Walk wk{};
+                Walk& wk = walks[n_out];
                 wk.read = ri; wk.anchor = a0 + q; wk.orient = uint8_t(orient); wk.state = W_WAITING;
                 wk.node = (direct || leaf.parent_id == FXG_NULL_ID) ? &root : &inner[leaf.parent_id];
                 // the root window is needed up front only by the interval optimisation (and by walks that start at the
@@ -1152,9 +1160,9 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
                 if (ivopt) {
                     if (ref_to_group[A.reference_id] < 0) { ref_to_group[A.reference_id] = int64_t(tmp_groups.size()); tmp_groups.emplace_back(); }
                     wk.group = group_base + uint32_t(ref_to_group[A.reference_id]);
-                    tmp_groups[size_t(ref_to_group[A.reference_id])].push_back(uint32_t(walks.size()));
+                    tmp_groups[size_t(ref_to_group[A.reference_id])].push_back(uint32_t(n_out));
                 }
-                walks.push_back(wk);
+                ++n_out;
             }
             if (ivopt) {
                 for (auto const& g : tmp_groups) {
@@ -1212,6 +1220,7 @@ struct PartState {
     std::vector<Walk> walks; std::vector<Group> groups; std::vector<uint32_t> group_members;   // indices local to this part
     uint64_t trace_budget = 0;               // bytes of checkpoint records the part may hold at a time
     std::chrono::steady_clock::time_point t0;
+    double cpu0 = 0;                         // the part's thread CPU time at its start (FXG_PROFILE)
     PartOut out;
 };
 
@@ -1240,6 +1249,7 @@ uint8_t node_dist(const fxg_pex_node* inner, std::vector<uint8_t>& memo, uint64_
 void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, PartState& P, StageGate* gate) {
     cudaSetDevice(c->device);
     P.t0 = std::chrono::steady_clock::now();
+    if (g_prof.on) P.cpu0 = thread_cpu_ms();
     PartOut& out = P.out;
     g_prof.start(w);
     bool const ivopt = J->cfg.interval_optimization != 0;
@@ -1500,8 +1510,8 @@ void verify_part_finish(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t* host_cigars
         out.alignments.push_back(a);
     }
     g_prof.lap(w, 13);
-    if (g_prof.on) fprintf(stderr, "[fxg] worker %d: %zu walks, %.3f ms, %llu waves\n", w.id, P.walks.size(),
-                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count(),
+    if (g_prof.on) fprintf(stderr, "[fxg] worker %d: %zu walks, %.3f ms (%.3f ms of CPU), %llu waves\n", w.id, P.walks.size(),
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count(), thread_cpu_ms() - P.cpu0,
                            (unsigned long long)w.ctr.waves);
 }
 
