@@ -123,6 +123,8 @@ struct DpLaunch {
     uint64_t peq_plane_words;
     DpResult* results;
     uint32_t* trace;            // trace planes [step][ring lane][word][hp, vp]
+    const uint32_t* n_tasks_dev;// if set: the number of tasks is read from here (tasks built on the device; the grid is
+                                // sized for an upper bound and surplus CTAs leave at once)
 };
 
 // S = T + P + carry over CH consecutive words with the hardware carry chain (IADD3.X); one asm
@@ -405,7 +407,9 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     uint32_t const r = lane % G;                    // ring position
     uint32_t const task_id = blockIdx.x * tasks_per_warp + slot;
     bool const in_ring = slot < tasks_per_warp;     // G need not divide 32: spare lanes idle
-    bool const have_task = in_ring && task_id < L.n_tasks;
+    uint32_t const n_tasks = L.n_tasks_dev ? __ldg(L.n_tasks_dev) : L.n_tasks;
+    if (blockIdx.x * tasks_per_warp >= n_tasks) return;
+    bool const have_task = in_ring && task_id < n_tasks;
 
     // lanes without a task idle on the (always present) first task's buffers: whatever they read there is valid
     uint8_t* const win = smem + size_t(have_task ? slot : 0) * kWinBytes;
@@ -852,6 +856,138 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
         WalkResult R; R.begin_col = j; R.cigar_len = bad ? 0xffffffffu : n_runs;
         L.results[T.out] = R;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inner tree levels on the device (query_verifier::hierarchical_verification, verification.cpp:66-104).
+//
+// The walks of a part climb their trees level by level without the host: per level one kernel computes every waiting
+// walk's window (compute_reference_span_start_and_length, verification.cpp:157-184, extra length 0) and elects per
+// (node, strand) the walk with the rightmost window start; the elected ones become engine tasks, appended per
+// configuration class; after the engine ran, the others take the elected walk's answer where it carries over
+// (host comment in verify_part_score: identical window, or alignment found that ends inside their window) or become
+// tasks of a second engine launch; a last kernel moves the survivors to their parent node.  The host only enqueues
+// kernels -- the engine reads its task counts from device memory -- and synchronises once, before the root level.
+// ---------------------------------------------------------------------------------------------
+struct NodeRec {                       // an inner node of a read's tree
+    uint32_t from, m, k;               // query_index_from, piece length, num_errors
+    uint16_t parent;                   // inner index of the parent within the read's tree (unused for the root)
+    uint8_t depth;                     // hops to the root
+    uint8_t cls;                       // configuration class of its score passes
+};
+struct WalkRec {
+    int64_t diag;                      // anchor position - first query index of its leaf (reference coordinates)
+    uint64_t qoff;                     // pool position of query[0] in the walk's orientation
+    uint32_t node;                     // first node to align (index into the part's NodeRec array), or kDeadNode
+    uint32_t node_base;                // where the read's NodeRecs begin
+    uint32_t ref_id;
+    uint32_t orient;
+};
+constexpr uint32_t kDeadNode = 0xffffffffu;
+constexpr uint32_t kMaxDeviceWalks = 1u << 24;      // a walk's index shares a 64-bit word with its window start
+
+struct LevelCtx {
+    const WalkRec* walks; const NodeRec* nodes; uint32_t n_walks;
+    const uint64_t* ref_base; const uint64_t* ref_len;
+    uint32_t* node;                    // per walk: node to align next
+    uint64_t* ask_ws; uint32_t* ask_len; uint8_t* flag;
+    unsigned long long* rep;           // per (node, strand): (window start << 24 | walk) of the elected walk, 0 = none
+    uint32_t* n_inner; uint64_t* sum_inner; uint64_t* cells_inner;     // statistics per walk, verification.cpp:238-242
+    DpTask* tasks; uint32_t* counts;   // class c: tasks + c * n_walks, counts[c]
+    const DpResult* results;           // per walk
+    unsigned long long* totals;        // [0] engine tasks, [1] their word-steps, [2] answers inferred
+    uint32_t level, infer;
+    uint8_t cls_W[16];                 // block width of every class (for the word-step count)
+};
+constexpr int kMaxLevelClasses = 16;
+enum : uint8_t { kWalkActive = 1, kWalkComputed = 2, kWalkYes = 4 };
+
+__device__ __forceinline__ void emit_level_task(LevelCtx const& C, uint32_t i, NodeRec const& N, uint64_t qoff) {
+    uint32_t const slot = atomicAdd(C.counts + N.cls, 1u);
+    DpTask t;
+    t.ref_base = C.ask_ws[i]; t.query_base = qoff + N.from; t.trace_base = 0;
+    t.n = C.ask_len[i]; t.m = N.m; t.dlo = -int32_t(N.k); t.dhi = int32_t(t.n) - int32_t(N.m) + int32_t(N.k);
+    t.flags = 0; t.out = i;
+    C.tasks[size_t(N.cls) * C.n_walks + slot] = t;
+    // word-steps the engine issues for it (host: word_steps_of): block b works on columns cs(b)..ce(b)
+    uint32_t const W = C.cls_W[N.cls], rows = 32 * W, nb = (N.m + rows - 1) / rows;
+    int64_t const pad = int64_t(nb) * rows - N.m;
+    unsigned long long ws = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+        int64_t lo = int64_t(rows) * b + 1 + t.dlo - pad, hi = int64_t(rows) * (b + 1) + t.dhi - pad;
+        if (lo < 1) lo = 1;
+        if (hi > int64_t(t.n)) hi = t.n;
+        if (hi >= lo) ws += (unsigned long long)(hi - lo + 1) * W;
+    }
+    atomicAdd(C.totals, 1ull);
+    atomicAdd(C.totals + 1, ws);
+}
+
+__global__ void level_begin_kernel(LevelCtx const C) {
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_walks) return;
+    uint32_t const nd = C.node[i];
+    uint8_t f = 0;
+    if (nd != kDeadNode) {
+        NodeRec const N = C.nodes[nd];
+        if (N.depth == C.level) {
+            WalkRec const Wk = C.walks[i];
+            int64_t const s = Wk.diag + int64_t(N.from) - int64_t(N.k);
+            uint64_t const offset = s >= 0 ? uint64_t(s) : 0;
+            uint64_t const base = uint64_t(N.m) + 2ull * N.k + 1;
+            uint64_t const room = C.ref_len[Wk.ref_id] - offset;
+            uint64_t const len = base < room ? base : room;
+            C.n_inner[i] += 1; C.sum_inner[i] += len; C.cells_inner[i] += uint64_t(N.m) * len;
+            if (int64_t(N.m) - int64_t(len) > int64_t(N.k)) {
+                C.node[i] = kDeadNode;                   // more insertions needed than errors allowed: no alignment
+            } else {
+                uint64_t const ws = C.ref_base[Wk.ref_id] + offset;
+                C.ask_ws[i] = ws; C.ask_len[i] = uint32_t(len);
+                f = kWalkActive;
+                if (C.infer) atomicMax(C.rep + (size_t(nd) * 2 + Wk.orient), (unsigned long long)((ws << 24) | i));
+            }
+        }
+    }
+    C.flag[i] = f;
+}
+
+__global__ void level_first_kernel(LevelCtx const C) {
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_walks || !(C.flag[i] & kWalkActive)) return;
+    uint32_t const nd = C.node[i];
+    WalkRec const Wk = C.walks[i];
+    if (C.infer && uint32_t(C.rep[size_t(nd) * 2 + Wk.orient] & 0xffffffull) != i) return;
+    emit_level_task(C, i, C.nodes[nd], Wk.qoff);
+    C.flag[i] |= kWalkComputed;
+}
+
+__global__ void level_second_kernel(LevelCtx const C) {
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_walks) return;
+    uint8_t const f = C.flag[i];
+    if (!(f & kWalkActive) || (f & kWalkComputed)) return;
+    uint32_t const nd = C.node[i];
+    NodeRec const N = C.nodes[nd];
+    WalkRec const Wk = C.walks[i];
+    uint32_t const r = uint32_t(C.rep[size_t(nd) * 2 + Wk.orient] & 0xffffffull);
+    DpResult const R = C.results[r];
+    bool const rep_yes = R.score <= int32_t(N.k);
+    uint64_t const ws = C.ask_ws[i]; uint32_t const len = C.ask_len[i];
+    if (ws == C.ask_ws[r] && len == C.ask_len[r]) { if (rep_yes) C.flag[i] = f | kWalkYes; return; }                        // the same window
+    if (rep_yes && ws + len >= C.ask_ws[r] + R.end_col) { C.flag[i] = f | kWalkYes; atomicAdd(C.totals + 2, 1ull); return; }   // (ws <= the elected one's)
+    emit_level_task(C, i, N, Wk.qoff);
+    C.flag[i] = f | kWalkComputed;
+}
+
+__global__ void level_advance_kernel(LevelCtx const C) {
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_walks) return;
+    uint8_t const f = C.flag[i];
+    if (!(f & kWalkActive)) return;
+    uint32_t const nd = C.node[i];
+    NodeRec const N = C.nodes[nd];
+    bool const yes = (f & kWalkComputed) ? C.results[i].score <= int32_t(N.k) : (f & kWalkYes) != 0;
+    C.node[i] = yes ? C.walks[i].node_base + N.parent : kDeadNode;      // pex_tree::get_parent_of_child, pex.cpp:70-76
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <ctime>
 #include <condition_variable>
 #include <cmath>
@@ -89,6 +90,7 @@ struct PinnedBuf {                       // page-locked host staging memory
 struct RefStore {
     DevBuf packed;                       // 4 bits per base, every reference starts at a multiple of 32 bases
     std::vector<uint64_t> base, len;
+    DevBuf d_base, d_len;                // the same two tables on the device (level kernels)
     uint64_t total = 0;
 };
 
@@ -142,10 +144,10 @@ struct Worker {
     // tracebacks are long chains of dependent steps: the root alignments of a wave are cut into chunks, each chunk's
     // tracebacks run on a stream of their own beside the score passes (and tracebacks) of the other chunks
     static constexpr int kWalkSlots = 4;
-    DevBuf d_tasks, d_results, d_ck[kWalkSlots], d_wtasks, d_wresults, d_cigars, d_rtasks, d_rresults;
+    DevBuf d_tasks, d_results, d_ck[kWalkSlots], d_wtasks, d_wresults, d_cigars, d_rtasks, d_rresults, d_lv;
     cudaStream_t walk_stream[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_walk_done[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr}, ev_w0 = nullptr, ev_w1[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
-    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults, h_rtasks, h_rresults;
+    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults, h_rtasks, h_rresults, h_lv, h_lv_back;
     fxg_counters ctr{};
     std::string err;
     std::vector<ConfigCacheEntry> cfg_cache = std::vector<ConfigCacheEntry>(8192);
@@ -153,7 +155,7 @@ struct Worker {
     std::vector<Config> cfgs;
     uint64_t cig_used = 0;               // ops of d_cigars filled by the current run
     void release() {
-        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults}) b->release();
+        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults, &d_lv}) b->release();
         if (ev_w0) { cudaEventDestroy(ev_w0); ev_w0 = nullptr; }
         if (ev_b0) { cudaEventDestroy(ev_b0); ev_b0 = nullptr; }
         if (ev_b1) { cudaEventDestroy(ev_b1); ev_b1 = nullptr; }
@@ -165,7 +167,7 @@ struct Worker {
             if (walk_stream[q]) cudaStreamDestroy(walk_stream[q]);
             ev_walk_done[q] = ev_w1[q] = nullptr; walk_stream[q] = nullptr;
         }
-        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults, &h_rtasks, &h_rresults}) b->release();
+        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults, &h_rtasks, &h_rresults, &h_lv, &h_lv_back}) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -237,6 +239,7 @@ struct fxg_ctx {
     DevBuf d_tmp;
     uint64_t trace_budget = 0;
     int workers_busy = 4;                        // workers a group uses when more than a quarter of the groups are busy
+    bool device_levels = true;                   // FXG_DEVICE_LEVELS=0 runs the inner tree levels from the host (development knob)
     bool share_root_passes = true;               // FXG_SHARE_ROOTS=0 scores every root window on its own (development knob)
     bool infer_inner = true;                     // FXG_INFER_INNER=0 computes every inner window (development knob)
     int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
@@ -1232,6 +1235,229 @@ uint8_t node_dist(const fxg_pex_node* inner, std::vector<uint8_t>& memo, uint64_
     return memo[id] = d;
 }
 
+// The inner levels of a part on the device (dp_kernels.cuh: level_*_kernel): the host writes one record per inner node and
+// per walk, enqueues the kernels of every level and synchronises once.  `level[d]` lists the walks that start d hops below
+// the root; on return every walk of level[>= 1] is either done or stands at its root (and has joined level[0]).
+// Returns FXG_OK, an error, or kNotOnDevice when the part does not fit the device path's limits (the host loop then runs).
+constexpr int kNotOnDevice = 1;
+int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, std::vector<Walk>& walks,
+                         std::vector<std::vector<uint32_t>>& level, std::function<bool()> const& before_first_launch, int& gate_rc) {
+    size_t const n_walks = walks.size();
+    size_t const n_levels = level.size();
+    if (n_levels < 2 || n_walks == 0 || n_walks >= kMaxDeviceWalks) return kNotOnDevice;
+    g_prof.start(w);
+    // ---- node records (inner nodes of the part's reads, read after read) and their configuration classes ----
+    struct Cls { uint8_t widx, G; uint32_t max_words; };
+    std::vector<Cls> classes;
+    std::vector<uint32_t> level_mask(n_levels, 0);
+    std::vector<uint32_t> node_base(read_hi - read_lo + 1, 0);
+    size_t n_nodes = 0;
+    for (uint32_t ri = read_lo; ri < read_hi; ++ri) { node_base[ri - read_lo] = uint32_t(n_nodes); n_nodes += J->reads_p[ri].num_inner; }
+    node_base[read_hi - read_lo] = uint32_t(n_nodes);
+    if (n_nodes == 0 || n_nodes >= (size_t(1) << 30)) return kNotOnDevice;
+    size_t const bytes_nodes = n_nodes * sizeof(NodeRec), bytes_walks = n_walks * sizeof(WalkRec), bytes_init = n_walks * 4;
+    if (w.h_lv.ensure(bytes_nodes + bytes_walks + bytes_init + 64) != cudaSuccess) return fail(w.err, FXG_ERR_OUT_OF_MEMORY, "cannot allocate staging for the tree levels");
+    NodeRec* const nrec = w.h_lv.as<NodeRec>();
+    WalkRec* const wrec = reinterpret_cast<WalkRec*>(w.h_lv.as<uint8_t>() + bytes_nodes);
+    uint32_t* const ninit = reinterpret_cast<uint32_t*>(w.h_lv.as<uint8_t>() + bytes_nodes + bytes_walks);
+    {
+        std::vector<uint8_t> memo;
+        const fxg_pex_node* prev = nullptr; uint32_t prev_n = 0, prev_base = 0;
+        for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
+            fxg_read const& R = J->reads_p[ri];
+            if (R.num_inner >= 0xffff) return kNotOnDevice;
+            const fxg_pex_node* inner = J->nodes_p + R.node_offset;
+            uint32_t const base = node_base[ri - read_lo];
+            if (prev && prev_n == R.num_inner && std::memcmp(prev, inner, size_t(R.num_inner) * sizeof(fxg_pex_node)) == 0) {
+                std::memcpy(nrec + base, nrec + prev_base, size_t(R.num_inner) * sizeof(NodeRec));   // the same tree as the read before
+            } else {
+                memo.assign(R.num_inner, 0xff);
+                for (uint32_t q = 0; q < R.num_inner; ++q) {
+                    fxg_pex_node const& nd = inner[q];
+                    NodeRec& r = nrec[base + q];
+                    r.from = uint32_t(nd.query_index_from); r.m = uint32_t(nd.query_index_to - nd.query_index_from + 1); r.k = uint32_t(nd.num_errors);
+                    r.parent = nd.parent_id == FXG_NULL_ID ? uint16_t(0) : uint16_t(nd.parent_id);
+                    r.depth = node_dist(inner, memo, q);
+                    Pass p;
+                    uint64_t const n_full = uint64_t(r.m) + 2ull * r.k + 1;
+                    if (!score_pass_for(0, 0, uint32_t(n_full), r.m, r.k, 0, p)) return kNotOnDevice;
+                    Config cf;
+                    if (!cached_config(w, p, c->smem_limit, cf)) return kNotOnDevice;
+                    size_t ci = 0;
+                    while (ci < classes.size() && !(classes[ci].widx == cf.widx && classes[ci].G == cf.G)) ++ci;
+                    if (ci == classes.size()) { if (ci == size_t(kMaxLevelClasses)) return kNotOnDevice; classes.push_back(Cls{cf.widx, cf.G, 0}); }
+                    r.cls = uint8_t(ci);
+                }
+            }
+            for (uint32_t q = 0; q < R.num_inner; ++q) {                   // (cheap; also covers copied trees)
+                NodeRec const& r = nrec[base + q];
+                uint32_t const W = uint32_t(kWidths[classes[r.cls].widx]);
+                classes[r.cls].max_words = std::max(classes[r.cls].max_words, (r.m + 32 * W - 1) / (32 * W) * W);
+                if (r.depth < n_levels) level_mask[r.depth] |= 1u << r.cls;      // (deeper nodes: no walk of this part starts that low)
+            }
+            prev = inner; prev_n = R.num_inner; prev_base = base;
+        }
+    }
+    // ---- walk records ----
+    for (size_t i = 0; i < n_walks; ++i) {
+        Walk const& wk = walks[i];
+        fxg_read const& R = J->reads_p[wk.read];
+        fxg_anchor const& A = J->anchors_p[wk.anchor];
+        const fxg_pex_node* inner = J->nodes_p + R.node_offset;
+        const fxg_pex_node* leaves = inner + R.num_inner;
+        WalkRec& r = wrec[i];
+        r.diag = int64_t(A.reference_position) - int64_t(leaves[A.pex_leaf_index].query_index_from);
+        r.qoff = (wk.orient ? J->pool_len : 0) + R.query_offset;
+        r.node_base = node_base[wk.read - read_lo];
+        r.ref_id = uint32_t(A.reference_id); r.orient = wk.orient;
+        bool const below_root = R.num_inner && wk.node > inner && wk.node < inner + R.num_inner;       // inner[0] is the root
+        r.node = below_root ? r.node_base + uint32_t(wk.node - inner) : kDeadNode;
+        ninit[i] = r.node;
+    }
+    g_prof.lap(w, 2);
+    // ---- device buffers: one allocation, carved up ----
+    size_t const n_cls = classes.size();
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t const at = off; off += (bytes + 255) & ~size_t(255); return at; };
+    size_t const o_nodes = carve(bytes_nodes), o_walks = carve(bytes_walks), o_node = carve(bytes_init);
+    size_t const o_ws = carve(n_walks * 8), o_len = carve(n_walks * 4), o_flag = carve(n_walks);
+    size_t const o_rep = carve(n_nodes * 2 * 8);
+    size_t const o_stats = carve(n_walks * 4 + n_walks * 8 * 2 + 64);            // n_inner | sum_inner | cells_inner | totals
+    size_t const o_tasks = carve(n_cls * n_walks * sizeof(DpTask));
+    size_t const o_counts = carve(size_t(kMaxLevelClasses) * 4);
+    size_t const o_results = carve(n_walks * sizeof(DpResult));
+    CUDA_TRY(w.err, w.d_lv.ensure(off));
+    uint8_t* const D = w.d_lv.as<uint8_t>();
+    size_t const stats_bytes = n_walks * 4 + n_walks * 8 * 2 + 64;
+    size_t const o_sum = o_stats + ((n_walks * 4 + 7) & ~size_t(7));
+    size_t const o_cells = o_sum + n_walks * 8, o_totals = o_cells + n_walks * 8;
+    if (o_totals + 24 > o_stats + ((stats_bytes + 255) & ~size_t(255))) return fail(w.err, FXG_ERR_CUDA, "internal: statistics layout");
+    cudaStream_t const st = w.stream;
+    if (!before_first_launch()) { gate_rc = FXG_ERR_STATE; return FXG_ERR_STATE; }      // (the caller has set the part's error)
+    // (one copy: node records, walk records and the walks' first nodes lie back to back on both sides only if the
+    //  carving kept them so; they are copied separately)
+    CUDA_TRY(w.err, cudaMemcpyAsync(D + o_nodes, nrec, bytes_nodes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(w.err, cudaMemcpyAsync(D + o_walks, wrec, bytes_walks, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(w.err, cudaMemcpyAsync(D + o_node, ninit, bytes_init, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(w.err, cudaMemsetAsync(D + o_stats, 0, (stats_bytes + 255) & ~size_t(255), st));
+    w.ctr.h2d_bytes += bytes_nodes + bytes_walks + bytes_init;
+
+    LevelCtx C{};
+    C.walks = reinterpret_cast<const WalkRec*>(D + o_walks); C.nodes = reinterpret_cast<const NodeRec*>(D + o_nodes); C.n_walks = uint32_t(n_walks);
+    C.ref_base = c->refs.d_base.as<uint64_t>(); C.ref_len = c->refs.d_len.as<uint64_t>();
+    C.node = reinterpret_cast<uint32_t*>(D + o_node);
+    C.ask_ws = reinterpret_cast<uint64_t*>(D + o_ws); C.ask_len = reinterpret_cast<uint32_t*>(D + o_len); C.flag = D + o_flag;
+    C.rep = reinterpret_cast<unsigned long long*>(D + o_rep);
+    C.n_inner = reinterpret_cast<uint32_t*>(D + o_stats); C.sum_inner = reinterpret_cast<uint64_t*>(D + o_sum); C.cells_inner = reinterpret_cast<uint64_t*>(D + o_cells);
+    C.tasks = reinterpret_cast<DpTask*>(D + o_tasks); C.counts = reinterpret_cast<uint32_t*>(D + o_counts);
+    C.results = reinterpret_cast<const DpResult*>(D + o_results);
+    C.totals = reinterpret_cast<unsigned long long*>(D + o_totals);
+    C.infer = c->infer_inner ? 1u : 0u;
+    for (size_t ci = 0; ci < n_cls; ++ci) C.cls_W[ci] = uint8_t(kWidths[classes[ci].widx]);
+
+    // walks that can stand at level d or deeper: the engine's grids are sized for them
+    std::vector<size_t> at_or_below(n_levels + 1, 0);
+    for (size_t d = n_levels; d-- > 0;) at_or_below[d] = at_or_below[d + 1] + level[d].size();
+
+    uint32_t const wgrid = uint32_t((n_walks + 255) / 256);
+    auto engine = [&](uint32_t mask, size_t cap) -> int {
+        // the classes of a level are independent: the first on the worker's stream, the others beside it
+        int n_launch = 0;
+        bool forked = false;
+        for (size_t ci = 0; ci < n_cls; ++ci) {
+            if (!(mask >> ci & 1u)) continue;
+            Cls const& K = classes[ci];
+            uint32_t const tpw = 32u / K.G;
+            DpLaunch L{};
+            L.tasks = C.tasks + ci * n_walks; L.n_tasks = uint32_t(cap); L.n_tasks_dev = C.counts + ci;
+            L.group = K.G; L.win_stride = kWinBytes; L.two = 2;
+            L.ref_chunks = c->refs.total / 32 + 1; L.inline_chunks = J->pool.inline_len / 32 + 1;
+            L.peq_stride = peq_stride_for(K.max_words);
+            L.ref_packed = c->refs.packed.as<uint32_t>(); L.inline_packed = J->pool.inline_packed.as<uint32_t>();
+            L.peq_table = J->pool.peq.as<uint32_t>(); L.peq_plane_words = J->pool.plane_words;
+            L.results = reinterpret_cast<DpResult*>(D + o_results); L.trace = nullptr;
+            size_t const smem = size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
+            if (smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", smem);
+            cudaStream_t s2 = st;
+            if (n_launch > 0) {
+                if (!forked) { CUDA_TRY(w.err, cudaEventRecord(w.ev_fork, st)); forked = true; }
+                s2 = w.side[(n_launch - 1) % Worker::kSide];
+                if (n_launch <= Worker::kSide) CUDA_TRY(w.err, cudaStreamWaitEvent(s2, w.ev_fork, 0));
+            }
+            CUDA_TRY(w.err, launch_dp(K.widx, false, L, uint32_t((cap + tpw - 1) / tpw), smem, s2));
+            w.ctr.kernel_launches++;
+            ++n_launch;
+        }
+        for (int q = 0; q < std::min(n_launch - 1, int(Worker::kSide)); ++q) {
+            CUDA_TRY(w.err, cudaEventRecord(w.ev_join[q], w.side[q]));
+            CUDA_TRY(w.err, cudaStreamWaitEvent(st, w.ev_join[q], 0));
+        }
+        return FXG_OK;
+    };
+    CUDA_TRY(w.err, cudaEventRecord(w.ev0, st));
+    for (size_t lv = n_levels - 1; lv >= 1; --lv) {
+        size_t const cap = at_or_below[lv];
+        if (cap == 0 || level_mask[lv] == 0) continue;
+        C.level = uint32_t(lv);
+        if (C.infer) CUDA_TRY(w.err, cudaMemsetAsync(C.rep, 0, n_nodes * 2 * 8, st));
+        CUDA_TRY(w.err, cudaMemsetAsync(C.counts, 0, size_t(kMaxLevelClasses) * 4, st));
+        level_begin_kernel<<<wgrid, 256, 0, st>>>(C);
+        level_first_kernel<<<wgrid, 256, 0, st>>>(C);
+        CUDA_TRY(w.err, cudaGetLastError());
+        int rc = engine(level_mask[lv], cap);
+        if (rc != FXG_OK) return rc;
+        w.ctr.kernel_launches += 2;
+        if (C.infer) {
+            CUDA_TRY(w.err, cudaMemsetAsync(C.counts, 0, size_t(kMaxLevelClasses) * 4, st));
+            level_second_kernel<<<wgrid, 256, 0, st>>>(C);
+            CUDA_TRY(w.err, cudaGetLastError());
+            rc = engine(level_mask[lv], cap);
+            if (rc != FXG_OK) return rc;
+            w.ctr.kernel_launches++;
+        }
+        level_advance_kernel<<<wgrid, 256, 0, st>>>(C);
+        CUDA_TRY(w.err, cudaGetLastError());
+        w.ctr.kernel_launches++;
+        w.ctr.waves++;
+    }
+    CUDA_TRY(w.err, cudaEventRecord(w.ev1, st));
+    // ---- the one synchronisation: where every walk ended up, and its statistics ----
+    size_t const back_stats = (bytes_init + 15) & ~size_t(15);
+    size_t const back_bytes = back_stats + stats_bytes;
+    CUDA_TRY(w.err, w.h_lv_back.ensure(back_bytes + 64));
+    uint8_t* const B = w.h_lv_back.as<uint8_t>();
+    CUDA_TRY(w.err, cudaMemcpyAsync(B, D + o_node, bytes_init, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(w.err, cudaMemcpyAsync(B + back_stats, D + o_stats, o_totals + 24 - o_stats, cudaMemcpyDeviceToHost, st));
+    w.ctr.d2h_bytes += back_bytes;
+    g_prof.lap(w, 6);
+    CUDA_TRY(w.err, w.wait_for(st));
+    float ms = 0;
+    CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
+    w.ctr.dp_kernel_ms += ms;
+    g_prof.lap(w, 8);
+    const uint32_t* const end_node = reinterpret_cast<const uint32_t*>(B);
+    const uint8_t* const S = B + back_stats;
+    const uint32_t* const n_inner = reinterpret_cast<const uint32_t*>(S);
+    const uint64_t* const sum_inner = reinterpret_cast<const uint64_t*>(S + (o_sum - o_stats));
+    const uint64_t* const cells_inner = reinterpret_cast<const uint64_t*>(S + (o_cells - o_stats));
+    const uint64_t* const totals = reinterpret_cast<const uint64_t*>(S + (o_totals - o_stats));
+    w.ctr.dp_tasks += totals[0]; w.ctr.dp_word_steps += totals[1]; w.ctr.inferred_inner += totals[2];
+    for (size_t d = 1; d < n_levels; ++d) {
+        for (uint32_t wi : level[d]) {
+            Walk& wk = walks[wi];
+            wk.n_inner = n_inner[wi]; wk.sum_inner = sum_inner[wi]; wk.cells_inner = cells_inner[wi];
+            if (end_node[wi] == kDeadNode) { wk.state = W_DONE; continue; }
+            fxg_read const& R = J->reads_p[wk.read];
+            if (end_node[wi] != node_base[wk.read - read_lo]) return fail(w.err, FXG_ERR_CUDA, "internal: a walk stopped below its root");
+            wk.node = J->nodes_p + R.node_offset;                           // the root
+            level[0].push_back(wi);
+        }
+        level[d].clear();
+    }
+    g_prof.lap(w, 9);
+    return FXG_OK;
+}
+
 // query_verifier::verify() for every anchor of reads [read_lo, read_hi), level-synchronously.
 //
 // 1. Inner levels.  The walks are advanced deepest node first, so that all alignments of one tree level land in the same
@@ -1327,10 +1553,18 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     if (infer) { rep_of.assign(size_t(node_hi - node_lo) * 2, 0); rep_stamp.assign(size_t(node_hi - node_lo) * 2, 0); }
     uint32_t stamp = 0;
     std::vector<Ask> asks;
+    bool levels_done = false;
+    if (c->device_levels && level.size() > 1) {
+        int gate_rc = FXG_OK;
+        int const rc = run_levels_on_device(c, w, J, read_lo, read_hi, walks, level, pass_through_gate, gate_rc);
+        if (gate_rc != FXG_OK) return;                                   // out.rc / w.err set by the gate
+        if (rc == FXG_OK) levels_done = true;
+        else if (rc != kNotOnDevice) { out.rc = rc; return; }
+    }
     std::vector<uint32_t> first, second;                                // asks computed in the first / second launch
     std::vector<int8_t> verdict;                                         // per ask: -1 undecided, 0 no alignment, 1 alignment exists
     std::vector<uint64_t> rep_end;                                       // per ask computed first: reference position where the alignment found ends
-    for (int cur_level = int(level.size()) - 1; cur_level >= 1; --cur_level) {
+    for (int cur_level = int(level.size()) - 1; cur_level >= 1 && !levels_done; --cur_level) {
         g_prof.start(w);
         active.swap(level[size_t(cur_level)]);
         level[size_t(cur_level)].clear();
@@ -1580,6 +1814,7 @@ int fxg_create(int device, fxg_ctx** out) {
     c->root_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64);
     c->infer_inner = env_int("FXG_INFER_INNER", 1, 0, 1) != 0;
     c->share_root_passes = env_int("FXG_SHARE_ROOTS", 1, 0, 1) != 0;
+    c->device_levels = env_int("FXG_DEVICE_LEVELS", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
     c->n_groups = env_int("FXG_GROUPS", 8, 1, fxg_ctx::kMaxGroups);
     c->workers_busy = default_workers(c->n_groups);
@@ -1659,6 +1894,13 @@ int fxg_set_references(fxg_ctx* c, size_t n_refs, const uint8_t* const* ranks, c
             int rc = upload_packed(c, ranks[i] + at, n, R.packed, (R.base[i] + at) / 8);
             if (rc != FXG_OK) return rc;
         }
+    }
+    if (n_refs) {
+        CUDA_TRY(c->err, R.d_base.ensure(n_refs * 8));
+        CUDA_TRY(c->err, R.d_len.ensure(n_refs * 8));
+        CUDA_TRY(c->err, cudaMemcpyAsync(R.d_base.p, R.base.data(), n_refs * 8, cudaMemcpyHostToDevice, c->stage_stream));
+        CUDA_TRY(c->err, cudaMemcpyAsync(R.d_len.p, R.len.data(), n_refs * 8, cudaMemcpyHostToDevice, c->stage_stream));
+        CUDA_TRY(c->err, cudaStreamSynchronize(c->stage_stream));
     }
     c->d_tmp.release();
     c->have_refs = true;
