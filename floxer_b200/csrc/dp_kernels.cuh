@@ -883,7 +883,8 @@ struct WalkRec {
     uint32_t ref_id;
     uint32_t orient;
 };
-constexpr uint32_t kDeadNode = 0xffffffffu;
+constexpr uint32_t kDeadNode = 0xffffffffu;        // the walk failed at an inner level
+constexpr uint32_t kAtRootNode = 0xfffffffeu;      // the walk starts at its root: nothing to do below it
 constexpr uint32_t kMaxDeviceWalks = 1u << 24;      // a walk's index shares a 64-bit word with its window start
 
 struct LevelCtx {
@@ -928,7 +929,7 @@ __global__ void level_begin_kernel(LevelCtx const C) {
     if (i >= C.n_walks) return;
     uint32_t const nd = C.node[i];
     uint8_t f = 0;
-    if (nd != kDeadNode) {
+    if (nd < kAtRootNode) {
         NodeRec const N = C.nodes[nd];
         if (N.depth == C.level) {
             WalkRec const Wk = C.walks[i];

@@ -1236,20 +1236,25 @@ uint8_t node_dist(const fxg_pex_node* inner, std::vector<uint8_t>& memo, uint64_
 }
 
 // The inner levels of a part on the device (dp_kernels.cuh: level_*_kernel): the host writes one record per inner node and
-// per walk, enqueues the kernels of every level and synchronises once.  `level[d]` lists the walks that start d hops below
-// the root; on return every walk of level[>= 1] is either done or stands at its root (and has joined level[0]).
+// per walk, enqueues the kernels of every level and synchronises once.
+// General mode (`walks` filled by build_walks, `level[d]` = the walks that start d hops below the root): on return every
+// walk of level[>= 1] is either done or stands at its root and has joined level[0].
+// Compact mode (`walks` empty; no interval optimisation, so every walk counts and no walk needs another's window): the
+// walk records come straight from the anchors, and only the walks that stand at their root afterwards -- one in six in
+// config 2 -- ever get a Walk object; the statistics of all walks go to `out`.
 // Returns FXG_OK, an error, or kNotOnDevice when the part does not fit the device path's limits (the host loop then runs).
 constexpr int kNotOnDevice = 1;
 int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, std::vector<Walk>& walks,
-                         std::vector<std::vector<uint32_t>>& level, std::function<bool()> const& before_first_launch, int& gate_rc) {
-    size_t const n_walks = walks.size();
-    size_t const n_levels = level.size();
-    if (n_levels < 2 || n_walks == 0 || n_walks >= kMaxDeviceWalks) return kNotOnDevice;
+                         std::vector<std::vector<uint32_t>>& level, bool compact, PartOut& out,
+                         std::function<bool()> const& before_first_launch, int& gate_rc) {
+    size_t const n_walks = J->read_walk_begin[read_hi] - J->read_walk_begin[read_lo];
+    if (n_walks == 0 || n_walks >= kMaxDeviceWalks) return kNotOnDevice;
+    if (!compact && (level.size() < 2 || walks.size() != n_walks)) return kNotOnDevice;
     g_prof.start(w);
     // ---- node records (inner nodes of the part's reads, read after read) and their configuration classes ----
     struct Cls { uint8_t widx, G; uint32_t max_words; };
     std::vector<Cls> classes;
-    std::vector<uint32_t> level_mask(n_levels, 0);
+    uint32_t level_mask[256] = {0};
     std::vector<uint32_t> node_base(read_hi - read_lo + 1, 0);
     size_t n_nodes = 0;
     for (uint32_t ri = read_lo; ri < read_hi; ++ri) { node_base[ri - read_lo] = uint32_t(n_nodes); n_nodes += J->reads_p[ri].num_inner; }
@@ -1288,54 +1293,84 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
                     if (ci == classes.size()) { if (ci == size_t(kMaxLevelClasses)) return kNotOnDevice; classes.push_back(Cls{cf.widx, cf.G, 0}); }
                     r.cls = uint8_t(ci);
                 }
-            }
-            for (uint32_t q = 0; q < R.num_inner; ++q) {                   // (cheap; also covers copied trees)
-                NodeRec const& r = nrec[base + q];
-                uint32_t const W = uint32_t(kWidths[classes[r.cls].widx]);
-                classes[r.cls].max_words = std::max(classes[r.cls].max_words, (r.m + 32 * W - 1) / (32 * W) * W);
-                if (r.depth < n_levels) level_mask[r.depth] |= 1u << r.cls;      // (deeper nodes: no walk of this part starts that low)
+                for (uint32_t q = 0; q < R.num_inner; ++q) {               // (copied trees add nothing new here)
+                    NodeRec const& r = nrec[base + q];
+                    uint32_t const W = uint32_t(kWidths[classes[r.cls].widx]);
+                    classes[r.cls].max_words = std::max(classes[r.cls].max_words, (r.m + 32 * W - 1) / (32 * W) * W);
+                    level_mask[r.depth] |= 1u << r.cls;
+                }
             }
             prev = inner; prev_n = R.num_inner; prev_base = base;
         }
     }
-    // ---- walk records ----
-    for (size_t i = 0; i < n_walks; ++i) {
-        Walk const& wk = walks[i];
-        fxg_read const& R = J->reads_p[wk.read];
-        fxg_anchor const& A = J->anchors_p[wk.anchor];
-        const fxg_pex_node* inner = J->nodes_p + R.node_offset;
-        const fxg_pex_node* leaves = inner + R.num_inner;
-        WalkRec& r = wrec[i];
-        r.diag = int64_t(A.reference_position) - int64_t(leaves[A.pex_leaf_index].query_index_from);
-        r.qoff = (wk.orient ? J->pool_len : 0) + R.query_offset;
-        r.node_base = node_base[wk.read - read_lo];
-        r.ref_id = uint32_t(A.reference_id); r.orient = wk.orient;
-        bool const below_root = R.num_inner && wk.node > inner && wk.node < inner + R.num_inner;       // inner[0] is the root
-        r.node = below_root ? r.node_base + uint32_t(wk.node - inner) : kDeadNode;
-        ninit[i] = r.node;
+    // ---- walk records; start_count[d] = walks that start d hops below the root ----
+    size_t start_count[256] = {0};
+    size_t n_levels = 1;
+    if (!compact) {
+        n_levels = level.size();
+        for (size_t d = 0; d < n_levels; ++d) start_count[std::min<size_t>(d, 255)] += level[d].size();
+        for (size_t i = 0; i < n_walks; ++i) {
+            Walk const& wk = walks[i];
+            fxg_read const& R = J->reads_p[wk.read];
+            fxg_anchor const& A = J->anchors_p[wk.anchor];
+            const fxg_pex_node* inner = J->nodes_p + R.node_offset;
+            const fxg_pex_node* leaves = inner + R.num_inner;
+            WalkRec& r = wrec[i];
+            r.diag = int64_t(A.reference_position) - int64_t(leaves[A.pex_leaf_index].query_index_from);
+            r.qoff = (wk.orient ? J->pool_len : 0) + R.query_offset;
+            r.node_base = node_base[wk.read - read_lo];
+            r.ref_id = uint32_t(A.reference_id); r.orient = wk.orient;
+            bool const below_root = R.num_inner && wk.node > inner && wk.node < inner + R.num_inner;       // inner[0] is the root
+            r.node = below_root ? r.node_base + uint32_t(wk.node - inner) : kAtRootNode;
+            ninit[i] = r.node;
+        }
+    } else {
+        size_t i = 0;
+        for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
+            fxg_read const& R = J->reads_p[ri];
+            const fxg_pex_node* leaves = J->nodes_p + R.node_offset + R.num_inner;
+            uint32_t const nb = node_base[ri - read_lo];
+            for (uint32_t orient = 0; orient < 2; ++orient) {
+                uint32_t const a0 = uint32_t(R.anchor_offset) + (orient ? R.num_anchors_forward : 0);
+                uint32_t const na = orient ? R.num_anchors_reverse : R.num_anchors_forward;
+                uint64_t const qoff = (orient ? J->pool_len : 0) + R.query_offset;
+                for (uint32_t q = 0; q < na; ++q, ++i) {
+                    fxg_anchor const& A = J->anchors_p[a0 + q];
+                    fxg_pex_node const& leaf = leaves[A.pex_leaf_index];
+                    WalkRec& r = wrec[i];
+                    r.diag = int64_t(A.reference_position) - int64_t(leaf.query_index_from);
+                    r.qoff = qoff; r.node_base = nb; r.ref_id = uint32_t(A.reference_id); r.orient = orient;
+                    // first node: the leaf's parent (verification.cpp:66-70); the root itself is not an inner level
+                    bool const below_root = leaf.parent_id != FXG_NULL_ID && leaf.parent_id != 0;
+                    r.node = below_root ? nb + uint32_t(leaf.parent_id) : kAtRootNode;
+                    ninit[i] = r.node;
+                    size_t const d = below_root ? nrec[r.node].depth : 0;
+                    start_count[d]++;
+                    n_levels = std::max(n_levels, d + 1);
+                }
+            }
+        }
+        if (n_levels < 2) return kNotOnDevice;
     }
     g_prof.lap(w, 2);
     // ---- device buffers: one allocation, carved up ----
     size_t const n_cls = classes.size();
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t const at = off; off += (bytes + 255) & ~size_t(255); return at; };
+    size_t const stats_bytes = n_walks * 4 + n_walks * 8 * 2 + 64;                // n_inner | sum_inner | cells_inner | totals
     size_t const o_nodes = carve(bytes_nodes), o_walks = carve(bytes_walks), o_node = carve(bytes_init);
     size_t const o_ws = carve(n_walks * 8), o_len = carve(n_walks * 4), o_flag = carve(n_walks);
     size_t const o_rep = carve(n_nodes * 2 * 8);
-    size_t const o_stats = carve(n_walks * 4 + n_walks * 8 * 2 + 64);            // n_inner | sum_inner | cells_inner | totals
+    size_t const o_stats = carve(stats_bytes);
     size_t const o_tasks = carve(n_cls * n_walks * sizeof(DpTask));
     size_t const o_counts = carve(size_t(kMaxLevelClasses) * 4);
     size_t const o_results = carve(n_walks * sizeof(DpResult));
     CUDA_TRY(w.err, w.d_lv.ensure(off));
     uint8_t* const D = w.d_lv.as<uint8_t>();
-    size_t const stats_bytes = n_walks * 4 + n_walks * 8 * 2 + 64;
     size_t const o_sum = o_stats + ((n_walks * 4 + 7) & ~size_t(7));
     size_t const o_cells = o_sum + n_walks * 8, o_totals = o_cells + n_walks * 8;
-    if (o_totals + 24 > o_stats + ((stats_bytes + 255) & ~size_t(255))) return fail(w.err, FXG_ERR_CUDA, "internal: statistics layout");
     cudaStream_t const st = w.stream;
     if (!before_first_launch()) { gate_rc = FXG_ERR_STATE; return FXG_ERR_STATE; }      // (the caller has set the part's error)
-    // (one copy: node records, walk records and the walks' first nodes lie back to back on both sides only if the
-    //  carving kept them so; they are copied separately)
     CUDA_TRY(w.err, cudaMemcpyAsync(D + o_nodes, nrec, bytes_nodes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(w.err, cudaMemcpyAsync(D + o_walks, wrec, bytes_walks, cudaMemcpyHostToDevice, st));
     CUDA_TRY(w.err, cudaMemcpyAsync(D + o_node, ninit, bytes_init, cudaMemcpyHostToDevice, st));
@@ -1357,7 +1392,7 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
 
     // walks that can stand at level d or deeper: the engine's grids are sized for them
     std::vector<size_t> at_or_below(n_levels + 1, 0);
-    for (size_t d = n_levels; d-- > 0;) at_or_below[d] = at_or_below[d + 1] + level[d].size();
+    for (size_t d = n_levels; d-- > 0;) at_or_below[d] = at_or_below[d + 1] + start_count[d];
 
     uint32_t const wgrid = uint32_t((n_walks + 255) / 256);
     auto engine = [&](uint32_t mask, size_t cap) -> int {
@@ -1442,17 +1477,45 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
     const uint64_t* const cells_inner = reinterpret_cast<const uint64_t*>(S + (o_cells - o_stats));
     const uint64_t* const totals = reinterpret_cast<const uint64_t*>(S + (o_totals - o_stats));
     w.ctr.dp_tasks += totals[0]; w.ctr.dp_word_steps += totals[1]; w.ctr.inferred_inner += totals[2];
-    for (size_t d = 1; d < n_levels; ++d) {
-        for (uint32_t wi : level[d]) {
-            Walk& wk = walks[wi];
-            wk.n_inner = n_inner[wi]; wk.sum_inner = sum_inner[wi]; wk.cells_inner = cells_inner[wi];
-            if (end_node[wi] == kDeadNode) { wk.state = W_DONE; continue; }
-            fxg_read const& R = J->reads_p[wk.read];
-            if (end_node[wi] != node_base[wk.read - read_lo]) return fail(w.err, FXG_ERR_CUDA, "internal: a walk stopped below its root");
-            wk.node = J->nodes_p + R.node_offset;                           // the root
-            level[0].push_back(wi);
+    if (!compact) {
+        for (size_t d = 1; d < n_levels; ++d) {
+            for (uint32_t wi : level[d]) {
+                Walk& wk = walks[wi];
+                wk.n_inner = n_inner[wi]; wk.sum_inner = sum_inner[wi]; wk.cells_inner = cells_inner[wi];
+                if (end_node[wi] == kDeadNode) { wk.state = W_DONE; continue; }
+                fxg_read const& R = J->reads_p[wk.read];
+                if (end_node[wi] != node_base[wk.read - read_lo]) return fail(w.err, FXG_ERR_CUDA, "internal: a walk stopped below its root");
+                wk.node = J->nodes_p + R.node_offset;                           // the root
+                level[0].push_back(wi);
+            }
+            level[d].clear();
         }
-        level[d].clear();
+    } else {
+        // every walk counts (verification.cpp:238-242); only those standing at their root go on
+        uint64_t n_sum = 0, len_sum = 0, cell_sum = 0;
+        for (size_t i = 0; i < n_walks; ++i) { n_sum += n_inner[i]; len_sum += sum_inner[i]; cell_sum += cells_inner[i]; }
+        out.stats.n_aligned_inner += n_sum; out.stats.sum_aligned_inner += len_sum; out.stats.cells_inner += cell_sum;
+        walks.clear();
+        level.assign(1, std::vector<uint32_t>());
+        size_t i = 0;
+        for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
+            fxg_read const& R = J->reads_p[ri];
+            uint32_t const nb = node_base[ri - read_lo];
+            for (uint32_t orient = 0; orient < 2; ++orient) {
+                uint32_t const a0 = uint32_t(R.anchor_offset) + (orient ? R.num_anchors_forward : 0);
+                uint32_t const na = orient ? R.num_anchors_reverse : R.num_anchors_forward;
+                for (uint32_t q = 0; q < na; ++q, ++i) {
+                    uint32_t const e = end_node[i];
+                    if (e == kDeadNode) continue;
+                    if (e != kAtRootNode && e != nb) return fail(w.err, FXG_ERR_CUDA, "internal: a walk stopped below its root");
+                    Walk wk{};
+                    wk.read = ri; wk.anchor = a0 + q; wk.orient = uint8_t(orient); wk.state = W_WALKING;
+                    wk.node = J->nodes_p + R.node_offset;                       // the root (inner[0], or the only leaf)
+                    level[0].push_back(uint32_t(walks.size()));
+                    walks.push_back(wk);
+                }
+            }
+        }
     }
     g_prof.lap(w, 9);
     return FXG_OK;
@@ -1480,31 +1543,10 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     g_prof.start(w);
     bool const ivopt = J->cfg.interval_optimization != 0;
     std::vector<Walk>& walks = P.walks; std::vector<Group>& groups = P.groups; std::vector<uint32_t>& group_members = P.group_members;
-    build_walks(c, J, read_lo, read_hi, walks, groups, group_members);
-    size_t const n_walks = walks.size();
-
-    // ---- tree level of every walk's first node ----
     std::vector<std::vector<uint32_t>> level;            // walks waiting for the wave of their node's level (0 = root)
-    {
-        std::vector<uint8_t> memo;
-        std::vector<uint8_t> dist(n_walks, 0);
-        uint32_t cur_read = UINT32_MAX; uint8_t max_dist = 0;
-        for (uint32_t i = 0; i < n_walks; ++i) {
-            Walk const& wk = walks[i];
-            fxg_read const& R = J->reads_p[wk.read];
-            const fxg_pex_node* inner = J->nodes_p + R.node_offset;
-            if (wk.read != cur_read) { cur_read = wk.read; memo.assign(R.num_inner, 0xff); }
-            if (R.num_inner && wk.node >= inner && wk.node < inner + R.num_inner) dist[i] = node_dist(inner, memo, uint64_t(wk.node - inner));
-            max_dist = std::max(max_dist, dist[i]);
-        }
-        level.resize(size_t(max_dist) + 1);
-        for (uint32_t i = 0; i < n_walks; ++i) { level[dist[i]].push_back(i); walks[i].state = W_WALKING; }
-    }
-
     std::vector<uint32_t> active;
     std::vector<Pass> passes; std::vector<uint32_t> pass_walk;
     w.cig_used = 0;
-    g_prof.lap(w, 0);
 
     auto pass_through_gate = [&]() -> bool {
         if (!gate) return true;
@@ -1514,6 +1556,39 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
         gate = nullptr;
         return true;
     };
+
+    // Without the interval optimisation no walk needs to know another's root window and every walk counts: the inner levels
+    // run on the device straight from the anchors, and only the walks that reach their root get a Walk object.
+    bool levels_done = false;
+    if (c->device_levels && !ivopt && J->cfg.verification_kind == FXG_KIND_HIERARCHICAL) {
+        walks.clear(); groups.clear(); group_members.clear();
+        int gate_rc = FXG_OK;
+        int const rc = run_levels_on_device(c, w, J, read_lo, read_hi, walks, level, true, out, pass_through_gate, gate_rc);
+        if (gate_rc != FXG_OK) return;                                   // out.rc / w.err set by the gate
+        if (rc == FXG_OK) levels_done = true;
+        else if (rc != kNotOnDevice) { out.rc = rc; return; }
+    }
+    if (!levels_done) {
+        build_walks(c, J, read_lo, read_hi, walks, groups, group_members);
+        // ---- tree level of every walk's first node ----
+        size_t const n_all = walks.size();
+        std::vector<uint8_t> memo;
+        std::vector<uint8_t> dist(n_all, 0);
+        uint32_t cur_read = UINT32_MAX; uint8_t max_dist = 0;
+        for (uint32_t i = 0; i < n_all; ++i) {
+            Walk const& wk = walks[i];
+            fxg_read const& R = J->reads_p[wk.read];
+            const fxg_pex_node* inner = J->nodes_p + R.node_offset;
+            if (wk.read != cur_read) { cur_read = wk.read; memo.assign(R.num_inner, 0xff); }
+            if (R.num_inner && wk.node >= inner && wk.node < inner + R.num_inner) dist[i] = node_dist(inner, memo, uint64_t(wk.node - inner));
+            max_dist = std::max(max_dist, dist[i]);
+        }
+        level.assign(size_t(max_dist) + 1, std::vector<uint32_t>());
+        for (uint32_t i = 0; i < n_all; ++i) { level[dist[i]].push_back(i); walks[i].state = W_WALKING; }
+    }
+    size_t const n_walks = walks.size();
+    g_prof.lap(w, 0);
+
     auto span_of = [&](Walk& wk, bool is_root) -> Span {
         fxg_anchor const& A = J->anchors_p[wk.anchor];
         fxg_read const& R = J->reads_p[wk.read];
@@ -1553,10 +1628,9 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     if (infer) { rep_of.assign(size_t(node_hi - node_lo) * 2, 0); rep_stamp.assign(size_t(node_hi - node_lo) * 2, 0); }
     uint32_t stamp = 0;
     std::vector<Ask> asks;
-    bool levels_done = false;
-    if (c->device_levels && level.size() > 1) {
+    if (!levels_done && c->device_levels && level.size() > 1) {
         int gate_rc = FXG_OK;
-        int const rc = run_levels_on_device(c, w, J, read_lo, read_hi, walks, level, pass_through_gate, gate_rc);
+        int const rc = run_levels_on_device(c, w, J, read_lo, read_hi, walks, level, false, out, pass_through_gate, gate_rc);
         if (gate_rc != FXG_OK) return;                                   // out.rc / w.err set by the gate
         if (rc == FXG_OK) levels_done = true;
         else if (rc != kNotOnDevice) { out.rc = rc; return; }
