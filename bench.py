@@ -119,13 +119,13 @@ def cpu_arm(refs, batch, cfg, sample_reads: int, threads: int, repeats: int = 1)
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--interval-optimization", action="store_true", help="floxer --interval-optimization (off by default, as in the reference)")
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU sample (0 = sized automatically)")
-    ap.add_argument("--pipeline", type=int, default=8, help="batches in flight per GPU (1..8): the library serves up to eight *_run calls at a time")
+    ap.add_argument("--pipeline", type=int, default=16, help="batches in flight per GPU: the library serves FXG_GROUPS (default 16, at most 32) *_run calls at a time")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -142,7 +142,7 @@ def main() -> int:
                           f"extra verification ratio 0.05, CIGAR output; anchors from the ground-truth stand-in seeder",
               "reads_per_gpu": W["reads"], "read_len": W["read_len"], "error_rate": W["error"],
               "l2": "256 MiB written to HBM between steps (twice the 126 MB L2); the batches in flight run concurrently, so a step never finds its own data in L2",
-              "batches_in_flight": max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "8"))))}
+              "batches_in_flight": max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "16"))))}
 
     # ------------------------------------------------------------------ CPU arm ("reference")
     if args.impl == "reference":
@@ -213,7 +213,7 @@ def main() -> int:
             dist.barrier()
             torch.cuda.synchronize()
 
-    depth = max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "8"))))
+    depth = max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "16"))))
 
     def run_lanes(step_fns, n_steps):
         """n_steps steps, dealt round-robin to len(step_fns) host threads (batches in flight); returns wall seconds."""

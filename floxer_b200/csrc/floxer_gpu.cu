@@ -231,8 +231,8 @@ struct fxg_ctx {
     fxg_counters ctr{};
     int num_sms = 0;
     size_t smem_limit = 0;
-    static constexpr int kMaxGroups = 16;
-    int n_groups = 8;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
+    static constexpr int kMaxGroups = 32;
+    int n_groups = 16;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
     WorkerGroup groups[kMaxGroups];
     cudaStream_t stage_stream = nullptr; // uploads of references / query pools, Peq construction
     std::condition_variable group_free;
@@ -344,7 +344,7 @@ WorkerGroup& acquire_group(fxg_ctx* c, std::unique_lock<std::mutex>& lock) {
         for (int i = 0; i < c->n_groups; ++i) if (!c->groups[i].busy) {
             WorkerGroup& g = c->groups[i];
             g.busy = true;
-            g.use_workers = busy + 1 <= std::max(1, c->n_groups / 4) ? g.workers.size() : size_t(c->workers_busy);
+            g.use_workers = busy + 1 <= std::max(1, c->n_groups / 4) ? g.workers.size() : std::min(g.workers.size(), size_t(c->workers_busy));
             return g;
         }
         c->group_free.wait(lock);
@@ -1854,7 +1854,7 @@ int default_workers(int n_groups) {
     if (const char* e = std::getenv("FXG_WORKERS")) { int v = std::atoi(e); if (v >= 1 && v <= 64) return v; }
     unsigned const hc = std::max(1u, std::thread::hardware_concurrency());
     int const ranks = env_int("LOCAL_WORLD_SIZE", 1, 1, 64);
-    return int(std::max(2u, std::min(4u, 2 * hc / unsigned(n_groups * ranks))));
+    return int(std::max(1u, std::min(4u, 2 * hc / unsigned(n_groups * ranks))));
 }
 
 }  // namespace
@@ -1890,13 +1890,16 @@ int fxg_create(int device, fxg_ctx** out) {
     c->share_root_passes = env_int("FXG_SHARE_ROOTS", 1, 0, 1) != 0;
     c->device_levels = env_int("FXG_DEVICE_LEVELS", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
-    c->n_groups = env_int("FXG_GROUPS", 8, 1, fxg_ctx::kMaxGroups);
+    c->n_groups = env_int("FXG_GROUPS", 16, 1, fxg_ctx::kMaxGroups);
     c->workers_busy = default_workers(c->n_groups);
-    int const nw = std::getenv("FXG_WORKERS") ? c->workers_busy : std::min(8, 2 * c->workers_busy);   // an explicit count is taken literally
+    // a batch that runs (nearly) alone is split over 8 workers; only the first quarter of the groups can be acquired in
+    // that state (the lowest free group is taken), so only they own that many.  An explicit FXG_WORKERS is taken literally.
+    int const nw_wide = std::getenv("FXG_WORKERS") ? c->workers_busy : std::max(8, c->workers_busy);
     for (int gi = 0; gi < c->n_groups; ++gi) {
         WorkerGroup& g = c->groups[gi];
         ok = ok && cudaEventCreate(&g.ev_run0) == cudaSuccess && cudaEventCreate(&g.ev_run1) == cudaSuccess &&
              cudaEventCreateWithFlags(&g.ev_staged, cudaEventDisableTiming) == cudaSuccess;
+        int const nw = gi < std::max(1, c->n_groups / 4) ? nw_wide : c->workers_busy;
         for (int i = 0; ok && i < nw; ++i) {
             std::unique_ptr<Worker> w(new (std::nothrow) Worker());
             if (!w) { ok = false; break; }
