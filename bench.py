@@ -355,7 +355,7 @@ def main() -> int:
         # every score-pass launch of that step over the event time of the waves (small launches and their tails included);
         # `as_benchmarked` is the same pair of figures for the step the headline numbers time, where coinciding windows
         # share one pass: one batch alone then leaves most of the machine idle (the launches are chains of dependent
-        # steps, a few hundred warps wide), and the eight batches in flight fill it together.
+        # steps, a few hundred warps wide), and the batches in flight fill it together.
         dp_s = roof_ctr["dp_kernel_ms"] * 1e-3
         ws = roof_ctr["dp_word_steps"]
         root_s = roof_ctr["root_launch_ms"] * 1e-3
