@@ -397,18 +397,16 @@ __device__ __forceinline__ void load_window_chunk(const uint4* __restrict__ pack
     d0[0] = a; d0[1] = b2; d1[0] = a; d1[1] = b2;
 }
 
+// the tasks_per_warp tasks number `group_index` of a launch, on one warp
 template <int W, bool CKPT>
-__global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
-    extern __shared__ __align__(16) uint8_t smem[];
+__device__ __forceinline__ void dp_task_group(DpLaunch const& L, uint32_t const group_index, uint32_t const n_tasks, uint8_t* const smem) {
     uint32_t const lane = threadIdx.x;
     uint32_t const G = L.group;
     uint32_t const tasks_per_warp = 32u / G;
     uint32_t const slot = lane / G;                 // which task of this warp
     uint32_t const r = lane % G;                    // ring position
-    uint32_t const task_id = blockIdx.x * tasks_per_warp + slot;
+    uint32_t const task_id = group_index * tasks_per_warp + slot;
     bool const in_ring = slot < tasks_per_warp;     // G need not divide 32: spare lanes idle
-    uint32_t const n_tasks = L.n_tasks_dev ? __ldg(L.n_tasks_dev) : L.n_tasks;
-    if (blockIdx.x * tasks_per_warp >= n_tasks) return;
     bool const have_task = in_ring && task_id < n_tasks;
 
     // lanes without a task idle on the (always present) first task's buffers: whatever they read there is valid
@@ -592,6 +590,23 @@ __global__ void __launch_bounds__(32) dp_kernel(DpLaunch const L) {
     if (have_task && r == owner) {
         DpResult res; res.score = dead ? kPoisonScore : S.best; res.end_col = S.best_col;
         L.results[T.out] = res;
+    }
+}
+
+// One warp per CTA.  Launches whose task count is known on the host have one CTA per group of tasks; launches whose tasks
+// were built on the device (n_tasks_dev) get a grid that is only an upper bound, capped by the host at what the machine
+// can hold at once: CTAs take the groups in turn and leave when none is left.
+// (the second launch bound keeps the register count where it was before the loop around the task groups: 25 warps per SM
+//  for W = 4 with checkpoints instead of 23)
+__host__ __device__ constexpr int dp_min_ctas(int W) { return W <= 2 ? 28 : (W == 4 ? 25 : (W == 8 ? 19 : (W == 16 ? 14 : 8))); }
+template <int W, bool CKPT>
+__global__ void __launch_bounds__(32, dp_min_ctas(W)) dp_kernel(DpLaunch const L) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t const tasks_per_warp = 32u / L.group;
+    uint32_t const n_tasks = L.n_tasks_dev ? __ldg(L.n_tasks_dev) : L.n_tasks;
+    for (uint32_t g = blockIdx.x; g * tasks_per_warp < n_tasks; g += gridDim.x) {
+        dp_task_group<W, CKPT>(L, g, n_tasks, smem);
+        __syncwarp();                               // the next group reuses the window and Eq buffers
     }
 }
 

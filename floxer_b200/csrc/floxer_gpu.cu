@@ -183,9 +183,9 @@ struct Worker {
 
 // The workers that serve one *_run call.  A context has several groups, so that several batches can be in flight: the
 // host-side preparation and the latency-bound tracebacks of one batch hide behind the score passes of the others.
-// A group owns twice the workers it uses when the context is busy: a batch that runs (nearly) alone is split over all
-// of them, which shortens its latency (config 2: 12 instead of 16 ms), while with many batches in flight fewer, larger
-// launches per batch are the better deal.
+// The first group owns more workers than a group uses when the context is busy: a batch that runs alone is split over
+// all of them, which shortens its latency, while with many batches in flight fewer, larger launches per batch are the
+// better deal.
 struct WorkerGroup {
     std::vector<std::unique_ptr<Worker>> workers;
     size_t use_workers = 0;              // decided when the group is acquired
@@ -344,7 +344,7 @@ WorkerGroup& acquire_group(fxg_ctx* c, std::unique_lock<std::mutex>& lock) {
         for (int i = 0; i < c->n_groups; ++i) if (!c->groups[i].busy) {
             WorkerGroup& g = c->groups[i];
             g.busy = true;
-            g.use_workers = busy + 1 <= std::max(1, c->n_groups / 4) ? g.workers.size() : std::min(g.workers.size(), size_t(c->workers_busy));
+            g.use_workers = busy == 0 ? g.workers.size() : std::min(g.workers.size(), size_t(c->workers_busy));
             return g;
         }
         c->group_free.wait(lock);
@@ -439,6 +439,10 @@ uint64_t word_steps_of(Pass const& p, uint32_t W, uint32_t nb) {
 // Picks words-per-lane W and ring size G for one pass.  The ring must be long enough that a lane is idle
 // (and publishes the +1 boundary) whenever the block below still needs a boundary from it:
 //   G > (B - 4) / (32 W + 1) + 2,  B = number of diagonals in the band  (derivation in DESIGN.md).
+// FXG_LATENCY_WEIGHT > 0 makes the chooser prefer narrower blocks (development knob; measured with 0.3 on config 2: a batch
+// running alone 7.4 -> 6.9 ms, 16 batches in flight unchanged, a machine-filling launch 0.61 -> 0.48 of the issue peak)
+double g_latency_weight = [] { const char* e = std::getenv("FXG_LATENCY_WEIGHT"); return e ? std::atof(e) : 0.0; }();
+
 bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
     uint32_t const nw = (p.m + 31) / 32;
     int64_t const B = int64_t(p.dhi) - int64_t(p.dlo) + 1;
@@ -470,6 +474,8 @@ bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
         // every block start / end interrupts the warp for a few hundred issue slots; the rings of a warp mostly, but not
         // always, have the same shape and then share these interruptions
         cost += 2.0 * nb * 100.0 / std::sqrt(double(tpw));
+        // a task is also a chain of `steps` dependent steps, each as long as the dependent instructions of one column
+        cost += g_latency_weight * double(steps) * (30.0 + 12.0 * W);
         if (cost < best_cost) { best_cost = cost; out = Config{uint8_t(wi), uint8_t(G), nb, 0}; found = true; }
     }
     if (found) out.word_steps = word_steps_of(p, uint32_t(kWidths[out.widx]), out.nb);
@@ -1419,7 +1425,9 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
                 s2 = w.side[(n_launch - 1) % Worker::kSide];
                 if (n_launch <= Worker::kSide) CUDA_TRY(w.err, cudaStreamWaitEvent(s2, w.ev_fork, 0));
             }
-            CUDA_TRY(w.err, launch_dp(K.widx, false, L, uint32_t((cap + tpw - 1) / tpw), smem, s2));
+            // (no more CTAs than a few waves of the machine: the CTAs take the task groups in turn)
+            uint32_t const grid = uint32_t(std::min<size_t>((cap + tpw - 1) / tpw, size_t(c->num_sms) * 16));
+            CUDA_TRY(w.err, launch_dp(K.widx, false, L, grid, smem, s2));
             w.ctr.kernel_launches++;
             ++n_launch;
         }
@@ -1695,6 +1703,13 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
                 else { second.push_back(uint32_t(q)); passes.push_back(pass_of(a)); }
             }
         }
+        if (g_prof.on && w.id == 0 && std::getenv("FXG_TRACE_WAVES")) {
+            size_t yes = 0, same_no = 0;
+            for (size_t f = 0; f < first.size(); ++f) yes += verdict[first[f]] == 1;
+            for (uint32_t q : second) same_no += verdict[rep_of[asks[q].key]] == 0;
+            fprintf(stderr, "[fxg] level %d: %zu of %zu elected found an alignment; %zu computed second, %zu of them because the elected walk found none\n",
+                    cur_level, yes, first.size(), second.size(), same_no);
+        }
         if (!passes.empty()) {
             out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
             if (out.rc != FXG_OK) return;
@@ -1892,14 +1907,14 @@ int fxg_create(int device, fxg_ctx** out) {
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
     c->n_groups = env_int("FXG_GROUPS", 16, 1, fxg_ctx::kMaxGroups);
     c->workers_busy = default_workers(c->n_groups);
-    // a batch that runs (nearly) alone is split over 8 workers; only the first quarter of the groups can be acquired in
-    // that state (the lowest free group is taken), so only they own that many.  An explicit FXG_WORKERS is taken literally.
+    // a batch that runs alone is split over 8 workers; the lowest free group is taken, so that is always group 0 and only
+    // it owns that many.  An explicit FXG_WORKERS is taken literally.
     int const nw_wide = std::getenv("FXG_WORKERS") ? c->workers_busy : std::max(8, c->workers_busy);
     for (int gi = 0; gi < c->n_groups; ++gi) {
         WorkerGroup& g = c->groups[gi];
         ok = ok && cudaEventCreate(&g.ev_run0) == cudaSuccess && cudaEventCreate(&g.ev_run1) == cudaSuccess &&
              cudaEventCreateWithFlags(&g.ev_staged, cudaEventDisableTiming) == cudaSuccess;
-        int const nw = gi < std::max(1, c->n_groups / 4) ? nw_wide : c->workers_busy;
+        int const nw = gi == 0 ? nw_wide : c->workers_busy;
         for (int i = 0; ok && i < nw; ++i) {
             std::unique_ptr<Worker> w(new (std::nothrow) Worker());
             if (!w) { ok = false; break; }
