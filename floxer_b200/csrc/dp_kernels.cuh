@@ -908,6 +908,7 @@ struct LevelCtx {
     uint32_t* node;                    // per walk: node to align next
     uint64_t* ask_ws; uint32_t* ask_len; uint8_t* flag;
     unsigned long long* rep;           // per (node, strand): (window start << 24 | walk) of the elected walk, 0 = none
+    unsigned long long* rep_min;       // the same for the walk with the leftmost window start (all ones = none)
     uint32_t* n_inner; uint64_t* sum_inner; uint64_t* cells_inner;     // statistics per walk, verification.cpp:238-242
     DpTask* tasks; uint32_t* counts;   // class c: tasks + c * n_walks, counts[c]
     const DpResult* results;           // per walk
@@ -916,7 +917,7 @@ struct LevelCtx {
     uint8_t cls_W[16];                 // block width of every class (for the word-step count)
 };
 constexpr int kMaxLevelClasses = 16;
-enum : uint8_t { kWalkActive = 1, kWalkComputed = 2, kWalkYes = 4 };
+enum : uint8_t { kWalkActive = 1, kWalkComputed = 2, kWalkYes = 4, kWalkAsksLeftmost = 8 };
 
 __device__ __forceinline__ void emit_level_task(LevelCtx const& C, uint32_t i, NodeRec const& N, uint64_t qoff) {
     uint32_t const slot = atomicAdd(C.counts + N.cls, 1u);
@@ -960,7 +961,10 @@ __global__ void level_begin_kernel(LevelCtx const C) {
                 uint64_t const ws = C.ref_base[Wk.ref_id] + offset;
                 C.ask_ws[i] = ws; C.ask_len[i] = uint32_t(len);
                 f = kWalkActive;
-                if (C.infer) atomicMax(C.rep + (size_t(nd) * 2 + Wk.orient), (unsigned long long)((ws << 24) | i));
+                if (C.infer) {
+                    atomicMax(C.rep + (size_t(nd) * 2 + Wk.orient), (unsigned long long)((ws << 24) | i));
+                    atomicMin(C.rep_min + (size_t(nd) * 2 + Wk.orient), (unsigned long long)((ws << 24) | i));
+                }
             }
         }
     }
@@ -977,6 +981,14 @@ __global__ void level_first_kernel(LevelCtx const C) {
     C.flag[i] |= kWalkComputed;
 }
 
+// After the elected walks (rightmost window start per node and strand) have their answers.  A = the elected walk's
+// window, B = this walk's (B starts at or before A, both on the same reference or nothing is inferred):
+//  * A holds an alignment: B holds it too if it is A's window or ends at or after the alignment's end; else B is computed;
+//  * A holds none: neither does the same window.  Otherwise let C be the node's leftmost window.  If A and C start at most
+//    k + 1 apart, every alignment inside B (at most m + k columns, starting at or after C's start) lies inside A (when it
+//    starts at or after A's start: B ends at or before A) or inside C (when it starts before A's start: it ends before
+//    A.start + m + k <= C.start + m + 2k + 1 = C's end, or C is clipped by the reference's end and B with it) -- so C is
+//    computed, and the others wait for its answer (level_third_kernel); if the windows spread further, B is computed.
 __global__ void level_second_kernel(LevelCtx const C) {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C.n_walks) return;
@@ -985,12 +997,44 @@ __global__ void level_second_kernel(LevelCtx const C) {
     uint32_t const nd = C.node[i];
     NodeRec const N = C.nodes[nd];
     WalkRec const Wk = C.walks[i];
-    uint32_t const r = uint32_t(C.rep[size_t(nd) * 2 + Wk.orient] & 0xffffffull);
-    DpResult const R = C.results[r];
-    bool const rep_yes = R.score <= int32_t(N.k);
+    size_t const key = size_t(nd) * 2 + Wk.orient;
+    uint32_t const a = uint32_t(C.rep[key] & 0xffffffull);
+    DpResult const R = C.results[a];
+    bool const a_yes = R.score <= int32_t(N.k);
     uint64_t const ws = C.ask_ws[i]; uint32_t const len = C.ask_len[i];
-    if (ws == C.ask_ws[r] && len == C.ask_len[r]) { if (rep_yes) C.flag[i] = f | kWalkYes; return; }                        // the same window
-    if (rep_yes && ws + len >= C.ask_ws[r] + R.end_col) { C.flag[i] = f | kWalkYes; atomicAdd(C.totals + 2, 1ull); return; }   // (ws <= the elected one's)
+    if (ws == C.ask_ws[a] && len == C.ask_len[a]) { if (a_yes) C.flag[i] = f | kWalkYes; return; }                           // the same window
+    bool const same_ref = C.walks[a].ref_id == Wk.ref_id;
+    if (a_yes) {
+        if (same_ref && ws + len >= C.ask_ws[a] + R.end_col) { C.flag[i] = f | kWalkYes; atomicAdd(C.totals + 2, 1ull); return; }
+    } else if (same_ref) {
+        uint32_t const c = uint32_t(C.rep_min[key] & 0xffffffull);
+        if (C.walks[c].ref_id == Wk.ref_id && C.ask_ws[a] - C.ask_ws[c] <= uint64_t(N.k) + 1) {
+            if (i != c) { C.flag[i] = f | kWalkAsksLeftmost; return; }
+        }
+    }
+    emit_level_task(C, i, N, Wk.qoff);
+    C.flag[i] = f | kWalkComputed;
+}
+
+// After the leftmost windows have their answers: none there either means none in between (see above); an alignment there
+// carries over to B if it is the same window or the alignment provably lies inside B; what is left is computed.
+__global__ void level_third_kernel(LevelCtx const C) {
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C.n_walks) return;
+    uint8_t const f = C.flag[i];
+    if (!(f & kWalkAsksLeftmost)) return;
+    uint32_t const nd = C.node[i];
+    NodeRec const N = C.nodes[nd];
+    WalkRec const Wk = C.walks[i];
+    uint32_t const c = uint32_t(C.rep_min[size_t(nd) * 2 + Wk.orient] & 0xffffffull);
+    DpResult const R = C.results[c];
+    if (R.score > int32_t(N.k)) { atomicAdd(C.totals + 2, 1ull); return; }                    // no alignment in A, none in C: none in B
+    uint64_t const ws = C.ask_ws[i]; uint32_t const len = C.ask_len[i];
+    uint64_t const end = C.ask_ws[c] + R.end_col;                                             // exclusive end of C's alignment
+    if ((ws == C.ask_ws[c] && len == C.ask_len[c]) ||
+        (end <= ws + len && int64_t(end) - int64_t(N.m) - int64_t(R.score) >= int64_t(ws))) {
+        C.flag[i] = f | kWalkYes; atomicAdd(C.totals + 2, 1ull); return;
+    }
     emit_level_task(C, i, N, Wk.qoff);
     C.flag[i] = f | kWalkComputed;
 }

@@ -1366,7 +1366,7 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
     size_t const stats_bytes = n_walks * 4 + n_walks * 8 * 2 + 64;                // n_inner | sum_inner | cells_inner | totals
     size_t const o_nodes = carve(bytes_nodes), o_walks = carve(bytes_walks), o_node = carve(bytes_init);
     size_t const o_ws = carve(n_walks * 8), o_len = carve(n_walks * 4), o_flag = carve(n_walks);
-    size_t const o_rep = carve(n_nodes * 2 * 8);
+    size_t const o_rep = carve(n_nodes * 2 * 8), o_rep_min = carve(n_nodes * 2 * 8);
     size_t const o_stats = carve(stats_bytes);
     size_t const o_tasks = carve(n_cls * n_walks * sizeof(DpTask));
     size_t const o_counts = carve(size_t(kMaxLevelClasses) * 4);
@@ -1388,7 +1388,7 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
     C.ref_base = c->refs.d_base.as<uint64_t>(); C.ref_len = c->refs.d_len.as<uint64_t>();
     C.node = reinterpret_cast<uint32_t*>(D + o_node);
     C.ask_ws = reinterpret_cast<uint64_t*>(D + o_ws); C.ask_len = reinterpret_cast<uint32_t*>(D + o_len); C.flag = D + o_flag;
-    C.rep = reinterpret_cast<unsigned long long*>(D + o_rep);
+    C.rep = reinterpret_cast<unsigned long long*>(D + o_rep); C.rep_min = reinterpret_cast<unsigned long long*>(D + o_rep_min);
     C.n_inner = reinterpret_cast<uint32_t*>(D + o_stats); C.sum_inner = reinterpret_cast<uint64_t*>(D + o_sum); C.cells_inner = reinterpret_cast<uint64_t*>(D + o_cells);
     C.tasks = reinterpret_cast<DpTask*>(D + o_tasks); C.counts = reinterpret_cast<uint32_t*>(D + o_counts);
     C.results = reinterpret_cast<const DpResult*>(D + o_results);
@@ -1442,7 +1442,10 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
         size_t const cap = at_or_below[lv];
         if (cap == 0 || level_mask[lv] == 0) continue;
         C.level = uint32_t(lv);
-        if (C.infer) CUDA_TRY(w.err, cudaMemsetAsync(C.rep, 0, n_nodes * 2 * 8, st));
+        if (C.infer) {
+            CUDA_TRY(w.err, cudaMemsetAsync(C.rep, 0, n_nodes * 2 * 8, st));
+            CUDA_TRY(w.err, cudaMemsetAsync(C.rep_min, 0xff, n_nodes * 2 * 8, st));
+        }
         CUDA_TRY(w.err, cudaMemsetAsync(C.counts, 0, size_t(kMaxLevelClasses) * 4, st));
         level_begin_kernel<<<wgrid, 256, 0, st>>>(C);
         level_first_kernel<<<wgrid, 256, 0, st>>>(C);
@@ -1456,7 +1459,12 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
             CUDA_TRY(w.err, cudaGetLastError());
             rc = engine(level_mask[lv], cap);
             if (rc != FXG_OK) return rc;
-            w.ctr.kernel_launches++;
+            CUDA_TRY(w.err, cudaMemsetAsync(C.counts, 0, size_t(kMaxLevelClasses) * 4, st));
+            level_third_kernel<<<wgrid, 256, 0, st>>>(C);
+            CUDA_TRY(w.err, cudaGetLastError());
+            rc = engine(level_mask[lv], cap);                       // (usually nothing is left for it)
+            if (rc != FXG_OK) return rc;
+            w.ctr.kernel_launches += 2;
         }
         level_advance_kernel<<<wgrid, 256, 0, st>>>(C);
         CUDA_TRY(w.err, cudaGetLastError());
