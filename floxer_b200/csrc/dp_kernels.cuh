@@ -483,6 +483,17 @@ __device__ __forceinline__ void dp_task_group(DpLaunch const& L, uint32_t const 
     uint32_t const my_end = __reduce_max_sync(0xffffffffu, have_task ? (T.n + nb - 1) : 0u);
     constexpr uint32_t kNever = 0x7fffffffu;
 
+    // (checkpoint passes) the block of this lane ended with step t - 1: the boundary bits since the last multiple of 32 go
+    // into one more record
+    auto flush_boundary_bits = [&](uint32_t t) {
+        uint32_t const left_over = (t - 1) & 31u;
+        if (left_over) {
+            uint32_t const hb = __brev(S.acc_hp) >> (32 - left_over), nbits = __brev(S.acc_hn) >> (32 - left_over);
+            if constexpr (W == 1) *reinterpret_cast<uint2*>(S.ckp + 2) = make_uint2(hb, nbits);
+            else *reinterpret_cast<uint4*>(S.ckp + 2 * W) = make_uint4(hb, nbits, 0u, 0u);
+        }
+    };
+
     uint32_t my_refill = 0;                                    // first step that would read past this ring's window buffer (0: not planned yet)
     uint32_t t = 1;
     while (t <= my_end) {
@@ -491,15 +502,7 @@ __device__ __forceinline__ void dp_task_group(DpLaunch const& L, uint32_t const 
         uint32_t const r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);
         int32_t const r_sc = __shfl_sync(0xffffffffu, S.score, src_lane);
         if (S.ce >= 0 && int32_t(t) - int32_t(S.b) > S.ce) {
-            if (CKPT) {
-                // the block ended with step t - 1; boundary bits since the last multiple of 32 go into one more record
-                uint32_t const left_over = (t - 1) & 31u;
-                if (left_over) {
-                    uint32_t const hb = __brev(S.acc_hp) >> (32 - left_over), nbits = __brev(S.acc_hn) >> (32 - left_over);
-                    if constexpr (W == 1) *reinterpret_cast<uint2*>(S.ckp + 2) = make_uint2(hb, nbits);
-                    else *reinterpret_cast<uint4*>(S.ckp + 2 * W) = make_uint4(hb, nbits, 0u, 0u);
-                }
-            }
+            if (CKPT) flush_boundary_bits(t);
             S.b += G; set_block(S.b);
         }
         int32_t const j = int32_t(t) - int32_t(S.b);
@@ -585,6 +588,9 @@ __device__ __forceinline__ void dp_task_group(DpLaunch const& L, uint32_t const 
         }
         t = evt;
     }
+    // the blocks that worked up to the warp's very last step never came back to the bookkeeping above: the last block of
+    // the longest task still owes its final boundary bits (the last row's deltas, which range_min_kernel reads)
+    if (CKPT && S.ce >= 0 && int32_t(t) - int32_t(S.b) > S.ce) flush_boundary_bits(t);
     // the lane that owned the last block reports
     uint32_t const owner = last_block % G;
     if (have_task && r == owner) {

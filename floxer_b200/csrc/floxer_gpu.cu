@@ -964,7 +964,9 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
     }
     for (size_t h = 0; h < H; ++h) {
         if (wr[h].cigar_len == 0xffffffffu || wr[h].begin_col < hit_shift[h])
-            return fail(w.err, FXG_ERR_CUDA, "internal: the traceback of an alignment disagrees with its score pass");
+            return fail(w.err, FXG_ERR_CUDA, "internal: the traceback of an alignment disagrees with its score pass (query length %u, window %u, "
+                        "band %d..%d, end column %u, score %u, begin column %u, window shift %llu, %s)", wt[h].m, wt[h].n, wt[h].dlo, wt[h].dhi, wt[h].end_col,
+                        wt[h].score, wr[h].begin_col, (unsigned long long)hit_shift[h], wr[h].cigar_len == 0xffffffffu ? "path cost differs" : "begins before its window");
         RootOut& o = outs[hit_pass[h]];
         o.begin_col = uint32_t(wr[h].begin_col - hit_shift[h]); o.cigar_len = wr[h].cigar_len;     // seen from the member's own window
         o.cigar_offset = wt[h].cigar_base + wt[h].cigar_cap - wr[h].cigar_len;

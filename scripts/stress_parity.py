@@ -54,9 +54,11 @@ def context(env):
     return c
 
 
-def main():
-    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+def main(n_cases=None, seed=None, only=None, oracle_every=4):
+    if n_cases is None:
+        n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+        seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+        only = int(sys.argv[3]) if len(sys.argv) > 3 else None    # run just this case (the others are generated and skipped)
     rng = np.random.default_rng(seed)
     fast = context({})
     plain = context({"FXG_DEVICE_LEVELS": "0", "FXG_INFER_INNER": "0", "FXG_SHARE_ROOTS": "0", "FXG_WORKERS": "2"})
@@ -87,6 +89,15 @@ def main():
         cfg = VerifyConfig(interval_optimization=bool(rng.integers(0, 2)), without_cigar=bool(rng.random() < 0.25),
                            verification_kind=abi.KIND_DIRECT_FULL if rng.random() < 0.15 else abi.KIND_HIERARCHICAL,
                            extra_verification_ratio=float(rng.choice([0.0, 0.05, 0.5, 2.0])))
+        if only is not None and case != only:
+            continue
+        print(f"case {case}: lens {lens} refs {ref_lens} reads {len(batch)} anchors {len(batch.anchors)} spread {spread} cfg {cfg}", flush=True)
+        if only is not None:
+            plain.set_references(refs)
+            jb = plain.verify_reads(batch, cfg)
+            print("  anchors", batch.anchors.tolist())
+            print("  reads", batch.reads.tolist())
+            print("  plain:", alignment_records(*jb.alignments()), jb.stats())
         fast.set_references(refs)
         plain.set_references(refs)
         fast.reset_counters()
@@ -98,7 +109,7 @@ def main():
         for k in totals:
             totals[k] += len(ra) if k == "alignments" else int(ctr[k])
         ok = ra == rb and sa == sb
-        if ok and case % 4 == 0:
+        if ok and oracle_every and case % oracle_every == 0:
             from harness import oracle_verify_batch
             if oracle is None:
                 from oracle import oracle as oracle_module
@@ -106,8 +117,7 @@ def main():
                 oracle = oracle_module
             want, want_stats = oracle_verify_batch(oracle, refs, batch, cfg)
             ok = ra == want and sa == want_stats
-        print(f"case {case}: lens {lens} refs {ref_lens} reads {len(batch)} anchors {len(batch.anchors)} cfg {cfg} -> "
-              f"{len(ra)} alignments {'ok' if ok else 'MISMATCH'}", flush=True)
+        print(f"   -> {len(ra)} alignments {'ok' if ok else 'MISMATCH'}", flush=True)
         if not ok:
             print("  stats fast ", sa)
             print("  stats plain", sb)
@@ -119,6 +129,8 @@ def main():
         ja.free()
         jb.free()
     print(f"{n_cases} cases identical in {time.time() - t0:.1f} s; shortcuts exercised: {totals}")
+    fast.close()
+    plain.close()
     return 0
 
 
