@@ -1,4 +1,4 @@
-"""Randomised differential test of the host queue's shortcuts (run on a GPU box: python scripts/stress_parity.py [cases] [seed]).
+"""Randomised differential test of the host queue's shortcuts (run on a GPU box: python scripts/stress_parity.py [cases] [seed] [only-case|-] [oracle-every]).
 
 Every case is a random batch -- several references (some barely longer than a read, so that windows are clipped at both
 ends), reads of mixed lengths (different trees in one batch), random error rates / seed errors / tree builder, decoys,
@@ -58,7 +58,8 @@ def main(n_cases=None, seed=None, only=None, oracle_every=4):
     if n_cases is None:
         n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
         seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-        only = int(sys.argv[3]) if len(sys.argv) > 3 else None    # run just this case (the others are generated and skipped)
+        only = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3] != "-" else None    # run just this case (the others are generated and skipped)
+        oracle_every = int(sys.argv[4]) if len(sys.argv) > 4 else oracle_every
     rng = np.random.default_rng(seed)
     fast = context({})
     plain = context({"FXG_DEVICE_LEVELS": "0", "FXG_INFER_INNER": "0", "FXG_SHARE_ROOTS": "0", "FXG_WORKERS": "2"})
@@ -66,12 +67,14 @@ def main(n_cases=None, seed=None, only=None, oracle_every=4):
     t0 = time.time()
     totals = {"alignments": 0, "shared_score_passes": 0, "rescored_roots": 0, "inferred_inner": 0, "shared_tracebacks": 0}
     for case in range(n_cases):
-        lens = sorted(int(x) for x in rng.choice([60, 150, 400, 900, 1600, 3000], size=int(rng.integers(1, 4)), replace=False))
+        big = os.environ.get("STRESS_BIG") == "1"             # fewer, larger cases: several parts per batch, longer chains
+        lens = sorted(int(x) for x in rng.choice([2000, 3500, 5000, 8000] if big else [60, 150, 400, 900, 1600, 3000],
+                                                 size=int(rng.integers(1, 4)), replace=False))
         n_refs = int(rng.integers(1, 5))
         refs = []
         for r in range(n_refs):
             # some references barely hold the longest read: every window there is clipped
-            length = int(lens[-1] * 1.3) + int(rng.integers(8, 200)) if rng.random() < 0.4 else int(rng.integers(lens[-1] * 2, 60_000))
+            length = int(lens[-1] * 1.3) + int(rng.integers(8, 200)) if rng.random() < 0.4 else int(rng.integers(lens[-1] * 2, 400_000 if big else 60_000))
             ref = synthetic.random_reference(length, int(rng.integers(1 << 30)))
             if rng.random() < 0.3 and length > 5000:
                 ref = synthetic.plant_repeats(ref, int(rng.integers(1 << 30)), families=3, unit=(200, 800), copies=(2, 5))
@@ -80,7 +83,7 @@ def main(n_cases=None, seed=None, only=None, oracle_every=4):
         batches = []
         for L in lens:
             err = float(rng.choice([0.02, 0.05, 0.08, 0.12]))
-            b = synthetic.make_batch(refs, int(rng.integers(2, 9)), L, err, int(rng.integers(1 << 30)), g.pex_build,
+            b = synthetic.make_batch(refs, int(rng.integers(10, 40)) if big else int(rng.integers(2, 9)), L, err, int(rng.integers(1 << 30)), g.pex_build,
                                      seed_errors=int(rng.integers(0, 4)), decoy_fraction=float(rng.choice([0.0, 0.3, 0.8])),
                                      bottom_up=bool(rng.integers(0, 2)))
             batches.append(b)
