@@ -366,8 +366,8 @@ def main() -> int:
         roofline = {"bound": "int32_alu", "achieved": achieved / 1e9, "peak": int32_peak / 1e9, "unit": "Ginstr/s",
                     "frac": achieved / int32_peak if int32_peak else None,
                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
-                    # (profiles/r01_final_ncu_full_summary.txt: 84.9 MB read, 1.446 GB written -- the checkpoint records)
-                    "traffic": 1535876896,
+                    # (profiles/r01_end_unshared_ncu_full_summary.txt: 84.4 MB read, 1.446 GB written -- the checkpoint records)
+                    "traffic": 1530833704,
                     "kernel": "fxg::dp_kernel<4,true> -- the root-level launch of a step (score pass leaving traceback checkpoints), "
                               "every root window of the batch scored on its own (FXG_SHARE_ROOTS=0 FXG_INFER_INNER=0): the launch that fills the machine",
                     "how": "algorithmic 11 int32 instr per 32-cell word-step x word-steps issued by that launch (band-limited, counted on the "

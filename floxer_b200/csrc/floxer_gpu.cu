@@ -1428,7 +1428,7 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
                 if (n_launch <= Worker::kSide) CUDA_TRY(w.err, cudaStreamWaitEvent(s2, w.ev_fork, 0));
             }
             // (no more CTAs than a few waves of the machine: the CTAs take the task groups in turn)
-            uint32_t const grid = uint32_t(std::min<size_t>((cap + tpw - 1) / tpw, size_t(c->num_sms) * 16));
+            uint32_t const grid = uint32_t(std::min<size_t>((cap + tpw - 1) / tpw, size_t(c->num_sms) * 32));
             CUDA_TRY(w.err, launch_dp(K.widx, false, L, grid, smem, s2));
             w.ctr.kernel_launches++;
             ++n_launch;
