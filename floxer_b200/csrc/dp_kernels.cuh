@@ -918,7 +918,7 @@ struct LevelCtx {
     uint32_t* n_inner; uint64_t* sum_inner; uint64_t* cells_inner;     // statistics per walk, verification.cpp:238-242
     DpTask* tasks; uint32_t* counts;   // class c: tasks + c * n_walks, counts[c]
     const DpResult* results;           // per walk
-    unsigned long long* totals;        // [0] engine tasks, [1] their word-steps, [2] answers inferred
+    unsigned long long* totals;        // [0] engine tasks, [1] their word-steps, [2] answers inferred, [3..5] sums of the statistics
     uint32_t level, infer;
     uint8_t cls_W[16];                 // block width of every class (for the word-step count)
 };
@@ -944,6 +944,48 @@ __device__ __forceinline__ void emit_level_task(LevelCtx const& C, uint32_t i, N
     }
     atomicAdd(C.totals, 1ull);
     atomicAdd(C.totals + 1, ws);
+}
+
+// The walk records straight from the caller's anchors (compact mode of the host's run_levels_on_device): the first node
+// of a walk is its leaf's parent (verification.cpp:66-70).
+struct ReadRec {
+    uint32_t walk_begin;               // first walk (= anchor) of the read within the part
+    uint32_t n_forward;                // its forward anchors come first
+    uint32_t node_base, leaf_base;     // where the read's NodeRecs / LeafRecs begin
+    uint64_t qoff_forward, qoff_reverse;
+};
+struct LeafRec { uint32_t from; uint32_t parent; };          // query_index_from, inner index of the parent (kNoParent: none)
+struct AnchorRec { uint64_t pex_leaf_index, reference_id, reference_position, num_errors; };   // = fxg_anchor
+constexpr uint32_t kNoParent = 0xffffffffu;
+
+__global__ void walk_init_kernel(const AnchorRec* __restrict__ anchors, const ReadRec* __restrict__ reads, uint32_t n_reads,
+                                 const LeafRec* __restrict__ leaves, WalkRec* __restrict__ walks, uint32_t* __restrict__ node, uint32_t n_walks) {
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_walks) return;
+    uint32_t lo = 0, hi = n_reads;                     // last read with walk_begin <= i
+    while (hi - lo > 1) { uint32_t const mid = (lo + hi) >> 1; if (reads[mid].walk_begin <= i) lo = mid; else hi = mid; }
+    ReadRec const R = reads[lo];
+    AnchorRec const A = anchors[i];
+    LeafRec const L = leaves[R.leaf_base + uint32_t(A.pex_leaf_index)];
+    uint32_t const orient = i - R.walk_begin >= R.n_forward ? 1u : 0u;
+    WalkRec w;
+    w.diag = int64_t(A.reference_position) - int64_t(L.from);
+    w.qoff = orient ? R.qoff_reverse : R.qoff_forward;
+    w.node_base = R.node_base; w.ref_id = uint32_t(A.reference_id); w.orient = orient;
+    w.node = (L.parent != kNoParent && L.parent != 0) ? R.node_base + L.parent : kAtRootNode;      // inner[0] is the root
+    walks[i] = w;
+    node[i] = w.node;
+}
+
+// sums of the per-walk statistics (every walk counts when the interval optimisation is off)
+__global__ void level_stats_kernel(LevelCtx const C) {
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long a = 0, b = 0, c = 0;
+    if (i < C.n_walks) { a = C.n_inner[i]; b = C.sum_inner[i]; c = C.cells_inner[i]; }
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, off); b += __shfl_down_sync(0xffffffffu, b, off); c += __shfl_down_sync(0xffffffffu, c, off);
+    }
+    if ((threadIdx.x & 31u) == 0 && (a | b | c)) { atomicAdd(C.totals + 3, a); atomicAdd(C.totals + 4, b); atomicAdd(C.totals + 5, c); }
 }
 
 __global__ void level_begin_kernel(LevelCtx const C) {

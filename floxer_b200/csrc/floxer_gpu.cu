@@ -1268,19 +1268,63 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
     for (uint32_t ri = read_lo; ri < read_hi; ++ri) { node_base[ri - read_lo] = uint32_t(n_nodes); n_nodes += J->reads_p[ri].num_inner; }
     node_base[read_hi - read_lo] = uint32_t(n_nodes);
     if (n_nodes == 0 || n_nodes >= (size_t(1) << 30)) return kNotOnDevice;
+    // In compact mode the walk records are made on the device from the caller's anchors (copied as they are) and small read /
+    // leaf tables, provided the part's anchors lie back to back in the caller's array (walk i of the part = anchor a_lo + i).
+    size_t const n_part_reads = read_hi - read_lo;
+    uint64_t const a_lo = J->reads_p[read_lo].anchor_offset;
+    bool device_init = compact;
+    size_t n_leaves = 0;
+    std::vector<uint32_t> leaf_base(n_part_reads + 1, 0);
+    if (device_init) {
+        uint64_t expect = a_lo;
+        for (uint32_t ri = read_lo; ri < read_hi && device_init; ++ri) {
+            fxg_read const& R = J->reads_p[ri];
+            if (R.anchor_offset != expect) device_init = false;
+            expect += uint64_t(R.num_anchors_forward) + R.num_anchors_reverse;
+            leaf_base[ri - read_lo] = uint32_t(n_leaves); n_leaves += R.num_leaves;
+        }
+        leaf_base[n_part_reads] = uint32_t(n_leaves);
+        if (n_leaves >= (size_t(1) << 30)) device_init = false;
+    }
     size_t const bytes_nodes = n_nodes * sizeof(NodeRec), bytes_walks = n_walks * sizeof(WalkRec), bytes_init = n_walks * 4;
-    if (w.h_lv.ensure(bytes_nodes + bytes_walks + bytes_init + 64) != cudaSuccess) return fail(w.err, FXG_ERR_OUT_OF_MEMORY, "cannot allocate staging for the tree levels");
+    size_t const bytes_reads = (n_part_reads * sizeof(ReadRec) + 15) & ~size_t(15), bytes_leaves = (n_leaves * sizeof(LeafRec) + 15) & ~size_t(15);
+    static_assert(sizeof(AnchorRec) == sizeof(fxg_anchor) && sizeof(ReadRec) == 32 && sizeof(LeafRec) == 8 && sizeof(NodeRec) == 16 && sizeof(WalkRec) == 32, "record layouts");
+    size_t const bytes_anchors = n_walks * sizeof(fxg_anchor);
+    size_t const staging = bytes_nodes + (device_init ? bytes_reads + bytes_leaves + bytes_anchors : bytes_walks + bytes_init);
+    if (w.h_lv.ensure(staging + 64) != cudaSuccess) return fail(w.err, FXG_ERR_OUT_OF_MEMORY, "cannot allocate staging for the tree levels");
     NodeRec* const nrec = w.h_lv.as<NodeRec>();
     WalkRec* const wrec = reinterpret_cast<WalkRec*>(w.h_lv.as<uint8_t>() + bytes_nodes);
     uint32_t* const ninit = reinterpret_cast<uint32_t*>(w.h_lv.as<uint8_t>() + bytes_nodes + bytes_walks);
+    ReadRec* const rrec = reinterpret_cast<ReadRec*>(w.h_lv.as<uint8_t>() + bytes_nodes);                       // (device_init layout)
+    LeafRec* const lrec = reinterpret_cast<LeafRec*>(w.h_lv.as<uint8_t>() + bytes_nodes + bytes_reads);
+    uint8_t* const arec = w.h_lv.as<uint8_t>() + bytes_nodes + bytes_reads + bytes_leaves;
+    size_t max_depth = 0;
     {
         std::vector<uint8_t> memo;
-        const fxg_pex_node* prev = nullptr; uint32_t prev_n = 0, prev_base = 0;
+        const fxg_pex_node* prev = nullptr; uint32_t prev_n = 0, prev_base = 0, prev_leaves = 0, prev_leaf_base = 0;
         for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
             fxg_read const& R = J->reads_p[ri];
             if (R.num_inner >= 0xffff) return kNotOnDevice;
             const fxg_pex_node* inner = J->nodes_p + R.node_offset;
             uint32_t const base = node_base[ri - read_lo];
+            if (device_init) {
+                ReadRec& rr = rrec[ri - read_lo];
+                rr.walk_begin = J->read_walk_begin[ri] - J->read_walk_begin[read_lo]; rr.n_forward = R.num_anchors_forward;
+                rr.node_base = base; rr.leaf_base = leaf_base[ri - read_lo];
+                rr.qoff_forward = R.query_offset; rr.qoff_reverse = J->pool_len + R.query_offset;
+                const fxg_pex_node* leaves = inner + R.num_inner;
+                LeafRec* const lr = lrec + rr.leaf_base;
+                if (prev && prev_n == R.num_inner && prev_leaves == R.num_leaves &&
+                    std::memcmp(prev + prev_n, leaves, size_t(R.num_leaves) * sizeof(fxg_pex_node)) == 0) {
+                    std::memcpy(lr, lrec + prev_leaf_base, size_t(R.num_leaves) * sizeof(LeafRec));
+                } else {
+                    for (uint32_t q = 0; q < R.num_leaves; ++q) {
+                        lr[q].from = uint32_t(leaves[q].query_index_from);
+                        lr[q].parent = leaves[q].parent_id == FXG_NULL_ID ? kNoParent : uint32_t(leaves[q].parent_id);
+                    }
+                }
+                prev_leaves = R.num_leaves; prev_leaf_base = rr.leaf_base;
+            }
             if (prev && prev_n == R.num_inner && std::memcmp(prev, inner, size_t(R.num_inner) * sizeof(fxg_pex_node)) == 0) {
                 std::memcpy(nrec + base, nrec + prev_base, size_t(R.num_inner) * sizeof(NodeRec));   // the same tree as the read before
             } else {
@@ -1306,6 +1350,7 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
                     uint32_t const W = uint32_t(kWidths[classes[r.cls].widx]);
                     classes[r.cls].max_words = std::max(classes[r.cls].max_words, (r.m + 32 * W - 1) / (32 * W) * W);
                     level_mask[r.depth] |= 1u << r.cls;
+                    max_depth = std::max<size_t>(max_depth, r.depth);
                 }
             }
             prev = inner; prev_n = R.num_inner; prev_base = base;
@@ -1332,6 +1377,12 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
             r.node = below_root ? r.node_base + uint32_t(wk.node - inner) : kAtRootNode;
             ninit[i] = r.node;
         }
+    } else if (device_init) {
+        std::memcpy(arec, J->anchors_p + a_lo, bytes_anchors);
+        n_levels = max_depth + 1;                                 // (levels no walk starts at or reaches cost a few empty launches)
+        for (size_t d = 1; d < n_levels; ++d) start_count[d] = 0;
+        start_count[n_levels - 1] = n_walks;                      // grids are sized for every walk at every level
+        if (n_levels < 2) return kNotOnDevice;
     } else {
         size_t i = 0;
         for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
@@ -1365,8 +1416,9 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
     size_t const n_cls = classes.size();
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t const at = off; off += (bytes + 255) & ~size_t(255); return at; };
-    size_t const stats_bytes = n_walks * 4 + n_walks * 8 * 2 + 64;                // n_inner | sum_inner | cells_inner | totals
+    size_t const stats_bytes = n_walks * 4 + n_walks * 8 * 2 + 64;                // n_inner | sum_inner | cells_inner | totals (6 x 8 bytes)
     size_t const o_nodes = carve(bytes_nodes), o_walks = carve(bytes_walks), o_node = carve(bytes_init);
+    size_t const o_reads = carve(device_init ? bytes_reads : 0), o_leaves = carve(device_init ? bytes_leaves : 0), o_anchors = carve(device_init ? bytes_anchors : 0);
     size_t const o_ws = carve(n_walks * 8), o_len = carve(n_walks * 4), o_flag = carve(n_walks);
     size_t const o_rep = carve(n_nodes * 2 * 8), o_rep_min = carve(n_nodes * 2 * 8);
     size_t const o_stats = carve(stats_bytes);
@@ -1380,10 +1432,22 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
     cudaStream_t const st = w.stream;
     if (!before_first_launch()) { gate_rc = FXG_ERR_STATE; return FXG_ERR_STATE; }      // (the caller has set the part's error)
     CUDA_TRY(w.err, cudaMemcpyAsync(D + o_nodes, nrec, bytes_nodes, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(w.err, cudaMemcpyAsync(D + o_walks, wrec, bytes_walks, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(w.err, cudaMemcpyAsync(D + o_node, ninit, bytes_init, cudaMemcpyHostToDevice, st));
+    if (device_init) {
+        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_reads, rrec, bytes_reads, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_leaves, lrec, bytes_leaves, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_anchors, arec, bytes_anchors, cudaMemcpyHostToDevice, st));
+        walk_init_kernel<<<uint32_t((n_walks + 255) / 256), 256, 0, st>>>(reinterpret_cast<const AnchorRec*>(D + o_anchors), reinterpret_cast<const ReadRec*>(D + o_reads),
+                                                                        uint32_t(n_part_reads), reinterpret_cast<const LeafRec*>(D + o_leaves),
+                                                                        reinterpret_cast<WalkRec*>(D + o_walks), reinterpret_cast<uint32_t*>(D + o_node), uint32_t(n_walks));
+        CUDA_TRY(w.err, cudaGetLastError());
+        w.ctr.kernel_launches++;
+        w.ctr.h2d_bytes += bytes_nodes + bytes_reads + bytes_leaves + bytes_anchors;
+    } else {
+        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_walks, wrec, bytes_walks, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_node, ninit, bytes_init, cudaMemcpyHostToDevice, st));
+        w.ctr.h2d_bytes += bytes_nodes + bytes_walks + bytes_init;
+    }
     CUDA_TRY(w.err, cudaMemsetAsync(D + o_stats, 0, (stats_bytes + 255) & ~size_t(255), st));
-    w.ctr.h2d_bytes += bytes_nodes + bytes_walks + bytes_init;
 
     LevelCtx C{};
     C.walks = reinterpret_cast<const WalkRec*>(D + o_walks); C.nodes = reinterpret_cast<const NodeRec*>(D + o_nodes); C.n_walks = uint32_t(n_walks);
@@ -1474,14 +1538,22 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
         w.ctr.waves++;
     }
     CUDA_TRY(w.err, cudaEventRecord(w.ev1, st));
-    // ---- the one synchronisation: where every walk ended up, and its statistics ----
+    // ---- the one synchronisation: where every walk ended up, and its statistics (compact mode: only their sums) ----
     size_t const back_stats = (bytes_init + 15) & ~size_t(15);
     size_t const back_bytes = back_stats + stats_bytes;
     CUDA_TRY(w.err, w.h_lv_back.ensure(back_bytes + 64));
     uint8_t* const B = w.h_lv_back.as<uint8_t>();
     CUDA_TRY(w.err, cudaMemcpyAsync(B, D + o_node, bytes_init, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(w.err, cudaMemcpyAsync(B + back_stats, D + o_stats, o_totals + 24 - o_stats, cudaMemcpyDeviceToHost, st));
-    w.ctr.d2h_bytes += back_bytes;
+    if (compact) {
+        level_stats_kernel<<<wgrid, 256, 0, st>>>(C);
+        CUDA_TRY(w.err, cudaGetLastError());
+        w.ctr.kernel_launches++;
+        CUDA_TRY(w.err, cudaMemcpyAsync(B + back_stats + (o_totals - o_stats), D + o_totals, 48, cudaMemcpyDeviceToHost, st));
+        w.ctr.d2h_bytes += bytes_init + 48;
+    } else {
+        CUDA_TRY(w.err, cudaMemcpyAsync(B + back_stats, D + o_stats, o_totals + 48 - o_stats, cudaMemcpyDeviceToHost, st));
+        w.ctr.d2h_bytes += back_bytes;
+    }
     g_prof.lap(w, 6);
     CUDA_TRY(w.err, w.wait_for(st));
     float ms = 0;
@@ -1510,9 +1582,7 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
         }
     } else {
         // every walk counts (verification.cpp:238-242); only those standing at their root go on
-        uint64_t n_sum = 0, len_sum = 0, cell_sum = 0;
-        for (size_t i = 0; i < n_walks; ++i) { n_sum += n_inner[i]; len_sum += sum_inner[i]; cell_sum += cells_inner[i]; }
-        out.stats.n_aligned_inner += n_sum; out.stats.sum_aligned_inner += len_sum; out.stats.cells_inner += cell_sum;
+        out.stats.n_aligned_inner += totals[3]; out.stats.sum_aligned_inner += totals[4]; out.stats.cells_inner += totals[5];
         walks.clear();
         level.assign(1, std::vector<uint32_t>());
         size_t i = 0;
