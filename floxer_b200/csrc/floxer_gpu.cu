@@ -128,9 +128,10 @@ struct Worker {
     cudaEvent_t ev_sleep = nullptr;
     // Waits for everything queued on `s` so far.  cudaStreamSynchronize spins (measured: 94 ms of CPU per batch, 13 cores'
     // worth, taken from the other workers and the other ranks of the host); a blocking event alone adds its wake-up
-    // latency to every wave (a batch took 14.8 instead of 11.5 ms).  So: poll for a short while, handing the core over
-    // between polls -- most waves of the inner levels end within that -- then sleep on the event.
-    int spin_us = 150;
+    // latency to every wave (a batch took 14.8 instead of 11.5 ms when every tree level was a wait).  So: poll for a short
+    // while, handing the core over between polls, then sleep on the event.  (Since the tree levels run on the device a part
+    // waits five times per batch and the polling time hardly matters: 150 us cost 1 ms of CPU per batch for nothing.)
+    int spin_us = 20;
     cudaError_t wait_for(cudaStream_t s) {
         cudaError_t e = cudaEventRecord(ev_sleep, s);
         if (e != cudaSuccess) return e;
@@ -1302,11 +1303,23 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
     {
         std::vector<uint8_t> memo;
         const fxg_pex_node* prev = nullptr; uint32_t prev_n = 0, prev_base = 0, prev_leaves = 0, prev_leaf_base = 0;
+        // a PEX tree is a function of the read's length and the batch's parameters: reads of equal length have equal trees, and
+        // the records of an equal tree are copied instead of rebuilt (the trees are compared, not assumed equal)
+        std::unordered_map<uint64_t, uint32_t> first_of_shape;
         for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
             fxg_read const& R = J->reads_p[ri];
             if (R.num_inner >= 0xffff) return kNotOnDevice;
             const fxg_pex_node* inner = J->nodes_p + R.node_offset;
             uint32_t const base = node_base[ri - read_lo];
+            {
+                uint64_t const shape = (uint64_t(R.query_len) << 32) ^ (uint64_t(R.num_inner) << 16) ^ R.num_leaves;
+                auto const ins = first_of_shape.emplace(shape, ri);
+                if (!ins.second) {
+                    fxg_read const& Q = J->reads_p[ins.first->second];
+                    prev = J->nodes_p + Q.node_offset; prev_n = Q.num_inner; prev_base = node_base[ins.first->second - read_lo];
+                    prev_leaves = Q.num_leaves; prev_leaf_base = leaf_base[ins.first->second - read_lo];
+                }
+            }
             if (device_init) {
                 ReadRec& rr = rrec[ri - read_lo];
                 rr.walk_begin = J->read_walk_begin[ri] - J->read_walk_begin[read_lo]; rr.n_forward = R.num_anchors_forward;
@@ -2004,7 +2017,7 @@ int fxg_create(int device, fxg_ctx** out) {
                  cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess;
             ok = ok && cudaEventCreate(&w->ev_w0) == cudaSuccess && cudaEventCreate(&w->ev_b0) == cudaSuccess && cudaEventCreate(&w->ev_b1) == cudaSuccess &&
                  cudaEventCreateWithFlags(&w->ev_sleep, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
-            w->spin_us = env_int("FXG_SPIN_US", 150, 0, 1000000);
+            w->spin_us = env_int("FXG_SPIN_US", 20, 0, 1000000);
             for (int q = 0; ok && q < Worker::kWalkSlots; ++q)
                 ok = cudaStreamCreateWithFlags(&w->walk_stream[q], cudaStreamNonBlocking) == cudaSuccess &&
                      cudaEventCreateWithFlags(&w->ev_walk_done[q], cudaEventDisableTiming) == cudaSuccess &&
