@@ -119,13 +119,13 @@ def cpu_arm(refs, batch, cfg, sample_reads: int, threads: int, repeats: int = 1)
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=192)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--interval-optimization", action="store_true", help="floxer --interval-optimization (off by default, as in the reference)")
     ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU sample (0 = sized automatically)")
-    ap.add_argument("--pipeline", type=int, default=16, help="batches in flight per GPU: the library serves FXG_GROUPS (default 16, at most 32) *_run calls at a time")
+    ap.add_argument("--pipeline", type=int, default=32, help="batches in flight per GPU: the library serves FXG_GROUPS (default and at most 32) *_run calls at a time")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -142,7 +142,7 @@ def main() -> int:
                           f"extra verification ratio 0.05, CIGAR output; anchors from the ground-truth stand-in seeder",
               "reads_per_gpu": W["reads"], "read_len": W["read_len"], "error_rate": W["error"],
               "l2": "256 MiB written to HBM between steps (twice the 126 MB L2); the batches in flight run concurrently, so a step never finds its own data in L2",
-              "batches_in_flight": max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "16"))))}
+              "batches_in_flight": max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "32"))))}
 
     # ------------------------------------------------------------------ CPU arm ("reference")
     if args.impl == "reference":
@@ -152,7 +152,8 @@ def main() -> int:
         from floxer_b200 import gpu as g          # host-side PEX builder only (no device needed)
         build.build_native()
         refs, batch = make_workload(args.workload, 0, g.pex_build)
-        n_sample = args.cpu_sample_reads or cpu_sample_size(refs, batch, cfg, threads, target_s=10.0)
+        # every step is a sample of the workload sized so that the K steps together take about two minutes
+        n_sample = args.cpu_sample_reads or cpu_sample_size(refs, batch, cfg, threads, target_s=min(10.0, max(0.3, 120.0 / max(args.steps, 1))))
         times, stats = [], None
         for _ in range(max(args.steps, 1)):
             dt, stats, n_used = cpu_arm(refs, batch, cfg, n_sample, threads)
@@ -213,7 +214,7 @@ def main() -> int:
             dist.barrier()
             torch.cuda.synchronize()
 
-    depth = max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "16"))))
+    depth = max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "32"))))
 
     def run_lanes(step_fns, n_steps):
         """n_steps steps, dealt round-robin to len(step_fns) host threads (batches in flight); returns wall seconds."""

@@ -233,7 +233,7 @@ struct fxg_ctx {
     int num_sms = 0;
     size_t smem_limit = 0;
     static constexpr int kMaxGroups = 32;
-    int n_groups = 16;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
+    int n_groups = 32;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
     WorkerGroup groups[kMaxGroups];
     cudaStream_t stage_stream = nullptr; // uploads of references / query pools, Peq construction
     std::condition_variable group_free;
@@ -1998,7 +1998,7 @@ int fxg_create(int device, fxg_ctx** out) {
     c->share_root_passes = env_int("FXG_SHARE_ROOTS", 1, 0, 1) != 0;
     c->device_levels = env_int("FXG_DEVICE_LEVELS", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
-    c->n_groups = env_int("FXG_GROUPS", 16, 1, fxg_ctx::kMaxGroups);
+    c->n_groups = env_int("FXG_GROUPS", 32, 1, fxg_ctx::kMaxGroups);
     c->workers_busy = default_workers(c->n_groups);
     // a batch that runs alone is split over 8 workers; the lowest free group is taken, so that is always group 0 and only
     // it owns that many.  An explicit FXG_WORKERS is taken literally.

@@ -150,7 +150,7 @@ typedef struct {
 
 /* ---- life cycle ----
  * Environment read by fxg_create (all optional; defaults in brackets):
- *   FXG_GROUPS        [16]  worker groups = *_run / fxg_verify_reads calls served at the same time (1..32)
+ *   FXG_GROUPS        [32]  worker groups = *_run / fxg_verify_reads calls served at the same time (1..32)
  *   FXG_WORKERS       [2 per host core over all groups and local ranks, 1..4; 8 for a call that runs alone]  workers per group
  *   FXG_SPIN_US       [20]  microseconds a worker polls for its launches before it sleeps on the event
  *   FXG_DEVICE_LEVELS [1]   0: the inner tree levels are scheduled from the host, one launch and wait per level

@@ -5,7 +5,7 @@ sys.path.insert(0, os.getcwd())
 import bench
 from floxer_b200 import gpu as g
 from floxer_b200.batch import VerifyConfig
-depth = int(os.environ.get("FXG_GROUPS", "16"))
+depth = int(os.environ.get("FXG_GROUPS", "32"))
 refs, batch = bench.make_workload("config2", 0, g.pex_build)
 ctx = g.Context(0); ctx.set_references(refs)
 jobs = [ctx.stage_verify(batch, VerifyConfig()) for _ in range(depth)]
