@@ -152,8 +152,8 @@ def main() -> int:
         from floxer_b200 import gpu as g          # host-side PEX builder only (no device needed)
         build.build_native()
         refs, batch = make_workload(args.workload, 0, g.pex_build)
-        # every step is a sample of the workload sized so that the K steps together take about two minutes
-        n_sample = args.cpu_sample_reads or cpu_sample_size(refs, batch, cfg, threads, target_s=min(10.0, max(0.3, 120.0 / max(args.steps, 1))))
+        # every step is a sample of the workload sized so that the K steps together take about three minutes
+        n_sample = args.cpu_sample_reads or cpu_sample_size(refs, batch, cfg, threads, target_s=min(10.0, max(0.3, 200.0 / max(args.steps, 1))))
         times, stats = [], None
         for _ in range(max(args.steps, 1)):
             dt, stats, n_used = cpu_arm(refs, batch, cfg, n_sample, threads)

@@ -1112,14 +1112,17 @@ struct RangeMinTask {
     uint32_t n, m; int32_t dlo, dhi;   // the pass
     uint32_t W;                        // its block width (words per lane)
     uint32_t col_from, col_to;         // the member's columns in the pass' numbering (1-based, inclusive)
-    int32_t known_score; uint32_t known_col;   // what the pass reported
+    uint32_t unit;                     // the pass' slot in the engine's result array: the (value, column) it reported
     uint32_t out;
+    uint32_t reserved;
 };
 
-__global__ void range_min_kernel(const RangeMinTask* __restrict__ tasks, uint32_t n_tasks, const uint32_t* __restrict__ ck_all, DpResult* __restrict__ results) {
+__global__ void range_min_kernel(const RangeMinTask* __restrict__ tasks, uint32_t n_tasks, const uint32_t* __restrict__ ck_all,
+                                 const DpResult* __restrict__ unit_results, DpResult* __restrict__ results) {
     uint32_t const id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n_tasks) return;
     RangeMinTask const T = tasks[id];
+    DpResult const known = unit_results[T.unit];
     uint32_t const W = T.W, ROWS = 32 * W, RECW = ck_record_words(W), BO = W == 1 ? 2 : 2 * W;
     uint32_t const nb = (T.m + ROWS - 1) / ROWS, lb = nb - 1;
     uint32_t const pad = nb * ROWS - T.m;
@@ -1148,8 +1151,8 @@ __global__ void range_min_kernel(const RangeMinTask* __restrict__ tasks, uint32_
     };
     DpResult R; R.score = kNoScore; R.end_col = 0;
     int32_t const a = int32_t(T.col_from) > cs ? int32_t(T.col_from) : cs, b = int32_t(T.col_to) < ce ? int32_t(T.col_to) : ce;
-    if (a <= b && T.known_score < kNoScore && int32_t(T.known_col) >= cs && int32_t(T.known_col) <= ce) {
-        int32_t sc = T.known_score - prefix(int32_t(T.known_col)) + prefix(a - 1);        // row m at column a - 1
+    if (a <= b && known.score < kNoScore && int32_t(known.end_col) >= cs && int32_t(known.end_col) <= ce) {
+        int32_t sc = known.score - prefix(int32_t(known.end_col)) + prefix(a - 1);        // row m at column a - 1
         uint2 v = make_uint2(0u, 0u);
         for (int32_t col = a; col <= b; ++col) {
             uint32_t const t = uint32_t(col) + lb, bit = (t - 1) & 31u;

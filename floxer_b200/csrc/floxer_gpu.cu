@@ -514,7 +514,7 @@ void radix_sort(std::vector<uint64_t>& keys, std::vector<uint64_t>& tmp, int lo_
 // records at those offsets of the worker's checkpoint buffer.
 // results points to pinned memory owned by the worker and stays valid until its next call.
 int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const& passes, const uint64_t* ck_bases, uint32_t* ck_buffer,
-               const DpResult** results) {
+               const DpResult** results, std::function<int()> const* after_launch = nullptr) {
     size_t const N = passes.size();
     *results = nullptr;
     if (N == 0) return FXG_OK;
@@ -625,6 +625,10 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     g_prof.lap(w, 6);
     CUDA_TRY(w.err, cudaMemcpyAsync(w.h_results.p, w.d_results.p, N * sizeof(DpResult), cudaMemcpyDeviceToHost, w.stream));
     w.ctr.d2h_bytes += N * sizeof(DpResult);
+    if (after_launch) {                              // more work of the caller's that needs the engine's results on the device only
+        int const rc = (*after_launch)();
+        if (rc != FXG_OK) return rc;
+    }
     CUDA_TRY(w.err, w.wait_for(w.stream));
     float ms = 0;
     CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
@@ -818,12 +822,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         if (k >= Worker::kWalkSlots) CUDA_TRY(w.err, cudaEventSynchronize(w.ev_walk_done[slot]));       // the tracebacks that read this buffer
         CUDA_TRY(w.err, ckb.ensure(used * 4));
         g_prof.lap(w, 10);
-        const DpResult* res = nullptr;
-        int rc = run_passes(c, w, pool, chunk, ck_base.data(), ckb.as<uint32_t>(), &res);
-        if (rc != FXG_OK) return rc;
-        w.ctr.trace_bytes += used * 4;
-        g_prof.start(w);
-        // ---- the members of shared passes: minimum of the last row over their own columns ----
+        // ---- the members of shared passes: minimum of the last row over their own columns, right behind the passes ----
         const DpResult* mres = nullptr;
         if (n_shared) {
             CUDA_TRY(w.err, w.h_rtasks.ensure(n_shared * sizeof(RangeMinTask)));
@@ -840,20 +839,29 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
                     RangeMinTask& t = rt[r];
                     t.ck_base = ck_base[u]; t.n = U.p.n; t.m = U.p.m; t.dlo = U.p.dlo; t.dhi = U.p.dhi; t.W = uint32_t(kWidths[U.cfg.widx]);
                     t.col_from = uint32_t(B.ref_base - U.p.ref_base) + 1; t.col_to = uint32_t(B.ref_base - U.p.ref_base) + B.n;
-                    t.known_score = res[u].score; t.known_col = res[u].end_col; t.out = uint32_t(r);
+                    t.unit = uint32_t(u); t.out = uint32_t(r); t.reserved = 0;
                     ++r;
                 }
             }
             CUDA_TRY(w.err, cudaMemcpyAsync(w.d_rtasks.p, rt, n_shared * sizeof(RangeMinTask), cudaMemcpyHostToDevice, w.stream));
+            w.ctr.h2d_bytes += n_shared * sizeof(RangeMinTask);
+        }
+        std::function<int()> const range_minima = [&]() -> int {
+            if (!n_shared) return FXG_OK;
             range_min_kernel<<<uint32_t((n_shared + 63) / 64), 64, 0, w.stream>>>(w.d_rtasks.as<RangeMinTask>(), uint32_t(n_shared), ckb.as<uint32_t>(),
-                                                                                 w.d_rresults.as<DpResult>());
+                                                                                 w.d_results.as<DpResult>(), w.d_rresults.as<DpResult>());
             CUDA_TRY(w.err, cudaGetLastError());
             CUDA_TRY(w.err, cudaMemcpyAsync(w.h_rresults.p, w.d_rresults.p, n_shared * sizeof(DpResult), cudaMemcpyDeviceToHost, w.stream));
-            CUDA_TRY(w.err, w.wait_for(w.stream));
             w.ctr.kernel_launches++;
-            w.ctr.h2d_bytes += n_shared * sizeof(RangeMinTask); w.ctr.d2h_bytes += n_shared * sizeof(DpResult);
-            mres = w.h_rresults.as<DpResult>();
-        }
+            w.ctr.d2h_bytes += n_shared * sizeof(DpResult);
+            return FXG_OK;
+        };
+        const DpResult* res = nullptr;
+        int rc = run_passes(c, w, pool, chunk, ck_base.data(), ckb.as<uint32_t>(), &res, &range_minima);      // one wait for both
+        if (rc != FXG_OK) return rc;
+        w.ctr.trace_bytes += used * 4;
+        g_prof.start(w);
+        if (n_shared) mres = w.h_rresults.as<DpResult>();
         // ---- tracebacks of the accepted ones on their own stream, one launch per block width ----
         // Alignments of the same query piece that end at the same reference position with the same score -- the usual case:
         // every true anchor of a read leads to the same locus -- have the same traceback, provided every optimal alignment
