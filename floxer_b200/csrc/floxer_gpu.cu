@@ -709,14 +709,21 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
     {
         std::vector<uint32_t> order(N);
         for (size_t i = 0; i < N; ++i) order[i] = uint32_t(i);
-        if (c->share_root_passes)
-            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-                Pass const& x = passes[a]; Pass const& y = passes[b];
-                if (x.query_base != y.query_base) return x.query_base < y.query_base;
-                if (x.m != y.m) return x.m < y.m;
-                if (x.ref_base != y.ref_base) return x.ref_base < y.ref_base;
-                return a < b;
-            });
+        if (c->share_root_passes) {
+            // windows of one query piece are to follow each other by position.  The passes of a read and strand arrive
+            // together (walk order), so runs of equal (query piece, length) are sorted one by one -- a piece that shows up
+            // in two separate runs merely shares less
+            size_t r0 = 0;
+            while (r0 < N) {
+                size_t r1 = r0 + 1;
+                while (r1 < N && passes[r1].query_base == passes[r0].query_base && passes[r1].m == passes[r0].m) ++r1;
+                if (r1 - r0 > 1)
+                    std::sort(order.begin() + long(r0), order.begin() + long(r1), [&](uint32_t a, uint32_t b) {
+                        return passes[a].ref_base != passes[b].ref_base ? passes[a].ref_base < passes[b].ref_base : a < b;
+                    });
+                r0 = r1;
+            }
+        }
         // cost of a pass ~ columns x (diagonals of the band + one block of rows)
         auto cost = [](uint64_t n, uint64_t m, uint64_t k) { return double(n) * double(int64_t(n) - int64_t(m) + 2 * int64_t(k) + 256); };
         size_t i = 0;
@@ -1606,6 +1613,9 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
         out.stats.n_aligned_inner += totals[3]; out.stats.sum_aligned_inner += totals[4]; out.stats.cells_inner += totals[5];
         walks.clear();
         level.assign(1, std::vector<uint32_t>());
+        size_t n_alive = 0;
+        for (size_t q = 0; q < n_walks; ++q) n_alive += end_node[q] != kDeadNode;
+        walks.reserve(n_alive); level[0].reserve(n_alive);
         size_t i = 0;
         for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
             fxg_read const& R = J->reads_p[ri];
@@ -1868,6 +1878,7 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     g_prof.start(w);
     passes.clear(); pass_walk.clear();
     std::vector<uint32_t> root_k;
+    passes.reserve(roots.size()); pass_walk.reserve(roots.size()); root_k.reserve(roots.size());
     bool const want_cigar = !J->cfg.without_cigar;
     for (uint32_t wi : roots) {
         Walk& wk = walks[wi];
