@@ -240,7 +240,8 @@ def main() -> int:
 
     # ---- device-resident arm: inputs staged once (one staged copy per batch in flight), each step = fxg_verify_run ----
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") != "1":      # rank 0 reports its GPU's clocks (one nvidia-smi, not one per rank)
+        sampler.start()
     jobs = [ctx.stage_verify(batch, cfg) for _ in range(depth)]
     run_lanes([j.run for j in jobs], args.warmup * depth)    # both worker groups warm (their buffers are allocated on first use)
 
