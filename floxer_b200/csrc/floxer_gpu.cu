@@ -808,6 +808,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         }
     };
     std::unordered_map<DupKey, uint32_t, DupHash> dup_key;
+    std::vector<std::pair<uint64_t, uint32_t>> unit_seen;           // (end column << 32 | score, member) of the pass at hand
     uint64_t cig_at = w.cig_used;
     size_t H = 0;                            // tracebacks issued so far
     size_t i = 0;
@@ -883,6 +884,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
             size_t r = 0;
             for (size_t u = 0; u < M; ++u) {
                 Unit const& U = units[i + u];
+                unit_seen.clear();
                 for (uint32_t q = 0; q < U.count; ++q) {
                     uint32_t const mem = unit_members[U.first + q];
                     Pass const& B = passes[mem];
@@ -905,9 +907,19 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
                     }
                     dup_of[mem] = kOwnTraceback;
                     if (safe) {
-                        DupKey const key{B.query_base, U.p.ref_base + R.end_col, B.m, uint32_t(R.score), B.flags};
-                        auto const ins = dup_key.emplace(key, mem);
-                        if (!ins.second) { dup_of[mem] = ins.first->second; continue; }      // shares the traceback of an earlier member
+                        if (U.count > 1) {
+                            // the members of a shared pass are one query piece: (end, score) identifies the alignment, and
+                            // a pass sees a handful of different ones at most -- a short list instead of the hash table
+                            uint64_t const ident = (uint64_t(R.end_col) << 32) | uint32_t(R.score);
+                            size_t h = 0;
+                            while (h < unit_seen.size() && unit_seen[h].first != ident) ++h;
+                            if (h < unit_seen.size()) { dup_of[mem] = unit_seen[h].second; continue; }   // shares the traceback of an earlier member
+                            unit_seen.emplace_back(ident, mem);
+                        } else {
+                            DupKey const key{B.query_base, U.p.ref_base + R.end_col, B.m, uint32_t(R.score), B.flags};
+                            auto const ins = dup_key.emplace(key, mem);
+                            if (!ins.second) { dup_of[mem] = ins.first->second; continue; }  // shares the traceback of an earlier pass
+                        }
                     }
                     accepted.push_back(Accepted{mem, uint32_t(u), R.end_col, uint32_t(R.score)});
                 }
