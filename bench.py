@@ -370,6 +370,12 @@ def main() -> int:
                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
                     # (profiles/r01_end_unshared_ncu_full_summary.txt: 84.4 MB read, 1.446 GB written -- the checkpoint records)
                     "traffic": 1530833704,
+                    # the contract's HBM view of the same launch, for the record: the path is not bandwidth-bound
+                    "hbm_view": (lambda peak, src: {"achieved": 1530833704 / root_s * n_roof / 1e9 if root_s > 0 else None, "peak": peak, "unit": "GB/s",
+                                                    "frac": (1530833704 / root_s * n_roof / 1e9) / peak if root_s > 0 else None,
+                                                    "peak_source": src,
+                                                    "note": "DRAM bytes of the launch (ncu) / its CUDA-event time; 5-6 % of the copy bandwidth"})(
+                        *((_measured_peak("hbm_gbs"), "MEASURED_PEAKS.json hbm_gbs") if _measured_peak("hbm_gbs") else (6650.0, "of fallback (B200_PROFILING.md)"))),
                     "kernel": "fxg::dp_kernel<4,true> -- the root-level launch of a step (score pass leaving traceback checkpoints), "
                               "every root window of the batch scored on its own (FXG_SHARE_ROOTS=0 FXG_INFER_INNER=0): the launch that fills the machine",
                     "how": "algorithmic 11 int32 instr per 32-cell word-step x word-steps issued by that launch (band-limited, counted on the "
