@@ -203,21 +203,25 @@ inline double thread_cpu_ms() {
 // host-side phase timing, printed when FXG_PROFILE is set (development aid; worker 0 only)
 struct HostProf {
     bool on = std::getenv("FXG_PROFILE") != nullptr;
-    double acc[16] = {0};
+    double acc[16] = {0}, acc_cpu[16] = {0};     // wall and thread-CPU milliseconds per phase
     const char* names[16] = {"setup", "admission", "build_passes", "plan", "sort", "tasks+h2d", "launch", "root prep", "sync+d2h", "finish",
                              "root chunk", "root sync", "walk issue", "emit", "barrier", "cigars d2h"};
     std::chrono::steady_clock::time_point t0;
-    void start(Worker const& w) { if (on && w.id == 0) t0 = std::chrono::steady_clock::now(); }
+    double c0 = 0;
+    void start(Worker const& w) { if (on && w.id == 0) { t0 = std::chrono::steady_clock::now(); c0 = thread_cpu_ms(); } }
     void lap(Worker const& w, int i) {
         if (!on || w.id != 0) return;
         auto t1 = std::chrono::steady_clock::now();
+        double const c1 = thread_cpu_ms();
         acc[i] += std::chrono::duration<double, std::milli>(t1 - t0).count();
-        t0 = t1;
+        acc_cpu[i] += c1 - c0;
+        t0 = t1; c0 = c1;
     }
     void report() {
         if (!on) return;
-        for (int i = 0; i < 16; ++i) if (names[i][0]) fprintf(stderr, "[fxg] %-14s %8.3f ms\n", names[i], acc[i]);
+        for (int i = 0; i < 16; ++i) if (names[i][0]) fprintf(stderr, "[fxg] %-14s %8.3f ms  (%.3f ms of CPU)\n", names[i], acc[i], acc_cpu[i]);
         for (double& a : acc) a = 0;
+        for (double& a : acc_cpu) a = 0;
     }
 };
 HostProf g_prof;

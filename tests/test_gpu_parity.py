@@ -294,9 +294,10 @@ def test_sharing_knobs_do_not_change_results(gpu, monkeypatch):
     batch = _densified(synthetic.make_batch(refs, 10, 1500, 0.06, 83, gpu.pex_build, seed_errors=2, decoy_fraction=0.3),
                        [120_000], np.random.default_rng(7), 40, 0.7)
     results = []
-    for share, infer in (("1", "1"), ("0", "0")):
+    for share, infer, device in (("1", "1", "1"), ("0", "0", "1"), ("1", "1", "0"), ("0", "0", "0")):
         monkeypatch.setenv("FXG_SHARE_ROOTS", share)
         monkeypatch.setenv("FXG_INFER_INNER", infer)
+        monkeypatch.setenv("FXG_DEVICE_LEVELS", device)
         c2 = gpu.Context(0)
         try:
             c2.set_references(refs)
@@ -309,7 +310,9 @@ def test_sharing_knobs_do_not_change_results(gpu, monkeypatch):
                 job.free()
         finally:
             c2.close()
-    assert results[0] == results[2] and results[1] == results[3] and len(results[0][0]) > 0
+    for k in range(2, len(results)):
+        assert results[k] == results[k % 2]
+    assert len(results[0][0]) > 0
 
 
 def test_config2_shape_against_cpu_port(ctx, gpu):
