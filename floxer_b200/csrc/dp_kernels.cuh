@@ -12,6 +12,11 @@
 //
 // Not a dense contraction: no tensor cores.  The hot loop is LOP3 / IADD3(.X) / SHF on the integer
 // pipes, Eq words and window characters come from shared memory, the carries from SHFL.
+//
+// Around the engine: walk2_kernel (traceback + CIGAR from the checkpoint records a root pass leaves),
+// range_min_kernel (a window's result read off a pass over the union of several windows), the
+// level_*_kernel family (the PEX tree walk's inner levels: windows, per-node election, engine tasks,
+// survivors -- all on the device), build_peq_kernel / pack_nibbles_kernel (input encoding).
 #pragma once
 
 #include <cstdint>

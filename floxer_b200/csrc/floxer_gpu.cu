@@ -3,9 +3,12 @@
 // Host responsibilities (the work of parallelization.cpp:193-293 and verification.cpp:8-245 of the
 // reference, re-organised for a GPU): turn align calls into DP passes, pick a (words-per-lane, ring size)
 // configuration per pass, bucket passes by configuration and length, launch the engine, and drive the
-// leaf -> root walk of every anchor level-synchronously ("waves").  Reads are split over a few host
-// workers, each with its own CUDA stream and buffers, so that one worker's scheduling overlaps the
-// kernels of the others.  No CPU fallback exists: every alignment result comes from dp_kernels.cuh.
+// leaf -> root walk of every anchor level-synchronously ("waves").  The inner tree levels of a batch run
+// on the device from a handful of records per read (run_levels_on_device; the host only enqueues kernels
+// and waits once), the root level -- windows that coincide share one score pass and one traceback
+// (run_root_passes) -- from the host.  Up to 32 batches are in flight at a time (worker groups), each
+// split over one or more host workers with their own CUDA streams and buffers.
+// No CPU fallback exists: every alignment result comes from dp_kernels.cuh.
 #include "../../include/floxer_gpu.h"
 #include "dp_kernels.cuh"
 
