@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = [os.path.join(HERE, "csrc", f) for f in ("floxer_gpu.cu", "pex_tree.cpp", "sam_output.cpp")]
+SOURCES = [os.path.join(HERE, "csrc", f) for f in ("floxer_gpu.cu", "pex_tree.cpp", "sam_output.cpp", "bam_output.cpp")]
 HEADERS = [os.path.join(HERE, "csrc", "dp_kernels.cuh"), os.path.join(os.path.dirname(HERE), "include", "floxer_gpu.h")]
 OUTPUT = os.path.join(HERE, "libfloxer_gpu.so")
 
@@ -27,7 +27,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUTPUT, *SOURCES]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", OUTPUT, *SOURCES, "-lz"]        # zlib: BGZF blocks of the BAM writer
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -21,7 +21,7 @@ EXPORTS = [
     "fxg_verify_stage", "fxg_verify_run", "fxg_job_num_alignments", "fxg_job_alignments", "fxg_job_cigar_len",
     "fxg_job_cigar_pool", "fxg_job_stats", "fxg_job_free", "fxg_verify_reads",
     "fxg_get_counters", "fxg_reset_counters", "fxg_measure_int32_peak",
-    "fxg_pex_build", "fxg_pex_free", "fxg_job_write_sam", "fxg_free",
+    "fxg_pex_build", "fxg_pex_free", "fxg_job_write_sam", "fxg_free", "fxg_write_bam", "fxg_job_write_bam",
 ]
 
 _lib = None
@@ -79,8 +79,43 @@ def lib() -> C.CDLL:
     L.fxg_job_write_sam.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     L.fxg_free.argtypes = [vp]
     L.fxg_free.restype = None
+    L.fxg_write_bam.argtypes = [vp, sz, vp, sz, vp, vp, vp, sz, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+    L.fxg_job_write_bam.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     _lib = L
     return L
+
+
+class _SamQuery(C.Structure):
+    _fields_ = [("id", C.c_char_p), ("quality", C.c_char_p)]
+
+
+def _output_arguments(batch, reference_ids, reference_lengths, query_ids, qualities):
+    n_ref, n = len(reference_ids), len(batch.reads)
+    ref_ids = (C.c_char_p * max(n_ref, 1))(*[r.encode() for r in reference_ids])
+    ref_lens = (C.c_uint64 * max(n_ref, 1))(*[int(x) for x in reference_lengths])
+    qs = (_SamQuery * max(n, 1))()
+    for i in range(n):
+        qs[i].id = query_ids[i].encode()
+        qs[i].quality = (qualities[i] if qualities is not None else "").encode()
+    return n_ref, ref_ids, ref_lens, n, qs
+
+
+def write_bam(alignments, cigars, batch, reference_ids, reference_lengths, query_ids, qualities=None, header: bool = True) -> bytes:
+    """BAM file image (BGZF) of alignment records given as arrays (abi.ALIGNMENT_DTYPE, grouped by read in read order, and
+    their cigar pool): fxg_write_bam, host only -- no context, no GPU."""
+    L = lib()
+    al = np.ascontiguousarray(alignments, dtype=abi.ALIGNMENT_DTYPE)
+    cg = np.ascontiguousarray(cigars, dtype=np.uint32)
+    n_ref, ref_ids, ref_lens, n, qs = _output_arguments(batch, reference_ids, reference_lengths, query_ids, qualities)
+    out, length = C.c_void_p(), C.c_size_t(0)
+    rc = L.fxg_write_bam(al.ctypes.data if len(al) else None, len(al), cg.ctypes.data if len(cg) else None, n_ref, ref_ids, ref_lens,
+                         batch.reads.ctypes.data, n, batch.forward_pool.ctypes.data, qs, int(header), C.byref(out), C.byref(length))
+    if rc != 0:
+        raise FloxerGpuError(rc, "fxg_write_bam failed")
+    try:
+        return C.string_at(out, length.value)
+    finally:
+        L.fxg_free(out)
 
 
 def pex_build(total_len: int, num_errors: int, leaf_max_errors: int, strategy: int = 0):
@@ -158,6 +193,20 @@ class Job:
             return C.string_at(text, length.value).decode()
         finally:
             L.fxg_free(text)
+
+    def bam(self, batch: ReadBatch, reference_ids, reference_lengths, query_ids, qualities=None, header: bool = True) -> bytes:
+        """The same records as a BAM file image (BGZF blocks incl. the end-of-file block): fxg_job_write_bam."""
+        L = lib()
+        n_ref, ref_ids, ref_lens, n, qs = _output_arguments(batch, reference_ids, reference_lengths, query_ids, qualities)
+        out, length = C.c_void_p(), C.c_size_t(0)
+        rc = L.fxg_job_write_bam(self._h, n_ref, ref_ids, ref_lens, batch.reads.ctypes.data, n, batch.forward_pool.ctypes.data,
+                                 qs, int(header), C.byref(out), C.byref(length))
+        if rc != 0:
+            raise FloxerGpuError(rc, "fxg_job_write_bam failed")
+        try:
+            return C.string_at(out, length.value)
+        finally:
+            L.fxg_free(out)
 
     def free(self):
         if self._h:

@@ -221,6 +221,19 @@ int fxg_job_write_sam(const fxg_job* job, size_t n_references, const char* const
                       int with_header, char** text, size_t* text_len);
 void fxg_free(void* p);
 
+/* The same records as a BAM file image (BGZF blocks incl. the end-of-file block; the container the reference writes,
+ * src/lib/output.cpp:197-212 with a .bam path).  fxg_write_bam takes the alignments as arrays -- grouped by read_index in
+ * read order, as fxg_job_alignments returns them -- and needs neither a context nor a GPU; fxg_job_write_bam feeds it a
+ * job's results.  with_header = 0 leaves out the BAM header (magic, text, reference list) so that the record blocks of
+ * several jobs can follow one header.  Writes a malloc'ed buffer; release it with fxg_free. */
+int fxg_write_bam(const fxg_alignment* alignments, size_t n_alignments, const uint32_t* cigar_pool,
+                  size_t n_references, const char* const* reference_ids, const uint64_t* reference_lengths,
+                  const fxg_read* reads, size_t n_reads, const uint8_t* forward_pool, const fxg_sam_query* queries,
+                  int with_header, uint8_t** bytes, size_t* bytes_len);
+int fxg_job_write_bam(const fxg_job* job, size_t n_references, const char* const* reference_ids, const uint64_t* reference_lengths,
+                      const fxg_read* reads, size_t n_reads, const uint8_t* forward_pool, const fxg_sam_query* queries,
+                      int with_header, uint8_t** bytes, size_t* bytes_len);
+
 /* ---- accounting / measurement helpers ---- */
 int fxg_get_counters(const fxg_ctx* ctx, fxg_counters* out);
 int fxg_reset_counters(fxg_ctx* ctx);

@@ -94,6 +94,12 @@ def test_sam_on_a_simulated_batch(gpu):
             assert not header
             assert records == _expected_records(batch, alignment_records(*job.alignments()), names, quals, ["chrA", "chrB"])
             assert sum(1 for r in records if not r[1] & (256 | 4)) == len({r[0] for r in records if not r[1] & 4})
+            # the BAM image of the same job holds the same records
+            from test_bam_output import parse_bam
+            _, bam_refs, bam_records = parse_bam(job.bam(batch, ["chrA", "chrB"], [len(r) for r in refs], names, quals))
+            assert bam_refs == [("chrA", len(refs[0])), ("chrB", len(refs[1]))]
+            assert [(b["name"], b["flag"], "*" if b["ref_id"] < 0 else ["chrA", "chrB"][b["ref_id"]], b["pos"] + 1, b["mapq"], b["cigar"], b["seq"], b["qual"], b["nm"])
+                    for b in bam_records] == records
             job.free()
     finally:
         ctx.close()
