@@ -130,6 +130,8 @@ struct DpLaunch {
     uint32_t* trace;            // trace planes [step][ring lane][word][hp, vp]
     const uint32_t* n_tasks_dev;// if set: the number of tasks is read from here (tasks built on the device; the grid is
                                 // sized for an upper bound and surplus CTAs leave at once)
+    const uint32_t* class_active; // if set: the tasks of class `cls` begin at tasks + class_active[0] + .. + class_active[cls - 1]
+    uint32_t cls;
 };
 
 // S = T + P + carry over CH consecutive words with the hardware carry chain (IADD3.X); one asm
@@ -404,7 +406,7 @@ __device__ __forceinline__ void load_window_chunk(const uint4* __restrict__ pack
 
 // the tasks_per_warp tasks number `group_index` of a launch, on one warp
 template <int W, bool CKPT>
-__device__ __forceinline__ void dp_task_group(DpLaunch const& L, uint32_t const group_index, uint32_t const n_tasks, uint8_t* const smem) {
+__device__ __forceinline__ void dp_task_group(DpLaunch const& L, const DpTask* const tasks, uint32_t const group_index, uint32_t const n_tasks, uint8_t* const smem) {
     uint32_t const lane = threadIdx.x;
     uint32_t const G = L.group;
     uint32_t const tasks_per_warp = 32u / G;
@@ -420,7 +422,7 @@ __device__ __forceinline__ void dp_task_group(DpLaunch const& L, uint32_t const 
                           size_t(have_task ? slot : 0) * kNumSymbols * L.peq_stride;
 
     DpTask T;
-    if (have_task) T = L.tasks[task_id];
+    if (have_task) T = tasks[task_id];
     else { T.n = 0; T.m = 1; T.dlo = 0; T.dhi = 0; T.flags = 0; T.ref_base = 0; T.query_base = 0; T.trace_base = 0; T.out = 0; }
 
     constexpr int ROWS = 32 * W;
@@ -615,8 +617,10 @@ __global__ void __launch_bounds__(32, dp_min_ctas(W)) dp_kernel(DpLaunch const L
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t const tasks_per_warp = 32u / L.group;
     uint32_t const n_tasks = L.n_tasks_dev ? __ldg(L.n_tasks_dev) : L.n_tasks;
+    const DpTask* tasks = L.tasks;
+    if (L.class_active) { for (uint32_t c = 0; c < L.cls; ++c) tasks += __ldg(L.class_active + c); }
     for (uint32_t g = blockIdx.x; g * tasks_per_warp < n_tasks; g += gridDim.x) {
-        dp_task_group<W, CKPT>(L, g, n_tasks, smem);
+        dp_task_group<W, CKPT>(L, tasks, g, n_tasks, smem);
         __syncwarp();                               // the next group reuses the window and Eq buffers
     }
 }
@@ -885,15 +889,19 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Inner tree levels on the device (query_verifier::hierarchical_verification, verification.cpp:66-104).
+// The tree walk on the device (query_verifier::verify, verification.cpp:8-136).
 //
-// The walks of a part climb their trees level by level without the host: per level one kernel computes every waiting
-// walk's window (compute_reference_span_start_and_length, verification.cpp:157-184, extra length 0) and elects per
-// (node, strand) the walk with the rightmost window start; the elected ones become engine tasks, appended per
-// configuration class; after the engine ran, the others take the elected walk's answer where it carries over
-// (host comment in verify_part_score: identical window, or alignment found that ends inside their window) or become
-// tasks of a second engine launch; a last kernel moves the survivors to their parent node.  The host only enqueues
-// kernels -- the engine reads its task counts from device memory -- and synchronises once, before the root level.
+// A batch arrives as compact records made once per job (host: prepare_job): one NodeRec per inner node, one LeafRec per
+// leaf, one ReadRec per read, one AnchorRec16 per anchor (= walk).  The walks climb their trees level by level without the
+// host: per level one kernel computes every waiting walk's window (compute_reference_span_start_and_length,
+// verification.cpp:157-184, extra length 0) and elects per (node, strand) the walk with the rightmost window start; the
+// elected ones become engine tasks (per configuration class, in one array: class c starts where the active walks of the
+// classes before it would end); after the engine ran, the others take the elected walk's answer where it carries over,
+// or become tasks of a second / third engine launch; a last kernel moves the survivors to their parent node.  Then
+// decide_kernel settles, per read and strand in anchor order, which walks count and which verify their root -- the
+// interval optimisation's sequential rule (verification.cpp:119-136) included -- and sums the statistics per member
+// job; the walks that verify their root are handed to the host as a list.  The host only enqueues kernels (the engine
+// reads its task counts from device memory) and synchronises once, before the root level.
 // ---------------------------------------------------------------------------------------------
 struct NodeRec {                       // an inner node of a read's tree
     uint32_t from, m, k;               // query_index_from, piece length, num_errors
@@ -901,42 +909,104 @@ struct NodeRec {                       // an inner node of a read's tree
     uint8_t depth;                     // hops to the root
     uint8_t cls;                       // configuration class of its score passes
 };
+struct LeafRec { uint32_t from; uint32_t parent; };          // query_index_from, inner index of the parent (kNoParent: none)
+struct AnchorRec16 { uint64_t reference_position; uint32_t pex_leaf_index; uint32_t reference_id; };   // search::anchor_t without num_errors
+struct ReadRec {                       // 64 bytes; bases are relative to the job until gather_reads_kernel shifts them
+    uint32_t walk_begin;               // first walk (= anchor) of the read
+    uint32_t n_forward;                // its forward anchors come first
+    uint32_t node_base, leaf_base;     // where the read's NodeRecs / LeafRecs begin
+    uint64_t qoff_forward, qoff_reverse;   // pool position of query[0] per orientation
+    uint32_t root_from, root_m, root_k;    // the root node
+    uint32_t root_extra;               // ceil_eps((m + 2k + 1) * extra_verification_ratio), verification.cpp:165-166
+    uint32_t member;                   // member job the read belongs to (statistics are kept per member)
+    uint32_t n_walks;                  // forward + reverse anchors
+    uint32_t reserved0, reserved1;
+};
 struct WalkRec {
     int64_t diag;                      // anchor position - first query index of its leaf (reference coordinates)
     uint64_t qoff;                     // pool position of query[0] in the walk's orientation
-    uint32_t node;                     // first node to align (index into the part's NodeRec array), or kDeadNode
+    uint32_t node;                     // first node to align (index into the batch's NodeRec array), or kDeadNode / kAtRootNode
     uint32_t node_base;                // where the read's NodeRecs begin
     uint32_t ref_id;
     uint32_t orient;
 };
 constexpr uint32_t kDeadNode = 0xffffffffu;        // the walk failed at an inner level
 constexpr uint32_t kAtRootNode = 0xfffffffeu;      // the walk starts at its root: nothing to do below it
-constexpr uint32_t kMaxDeviceWalks = 1u << 24;      // a walk's index shares a 64-bit word with its window start
+constexpr uint32_t kNoParent = 0xffffffffu;
+constexpr int kWalkBits = 28;                       // a walk's index shares a 64-bit word with its window start (a store position below 2^36)
+constexpr uint32_t kMaxDeviceWalks = 1u << kWalkBits;
+constexpr unsigned long long kWalkMask = (1ull << kWalkBits) - 1;
+constexpr int kMaxLevelClasses = 16;
+
+// a member job's ReadRecs copied into the batch, bases shifted to the member's place in it
+__global__ void gather_reads_kernel(const ReadRec* __restrict__ src, ReadRec* __restrict__ dst, uint32_t n, uint32_t walk0, uint32_t node0,
+                                    uint32_t leaf0, uint64_t pool_shift, uint32_t member) {
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ReadRec r = src[i];
+    r.walk_begin += walk0; r.node_base += node0; r.leaf_base += leaf0;
+    r.qoff_forward += pool_shift; r.qoff_reverse += pool_shift; r.member = member;
+    dst[i] = r;
+}
+
+// last read with walk_begin <= i
+__device__ __forceinline__ uint32_t read_of_walk(const ReadRec* __restrict__ reads, uint32_t n_reads, uint32_t i) {
+    uint32_t lo = 0, hi = n_reads;
+    while (hi - lo > 1) { uint32_t const mid = (lo + hi) >> 1; if (reads[mid].walk_begin <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// The walk records from the anchors: the first node of a walk is its leaf's parent (verification.cpp:66-70), or the root
+// itself for direct_full_verification (verification.cpp:23-42) and for leaves that hang off the root.
+__global__ void walk_init_kernel(const AnchorRec16* __restrict__ anchors, const ReadRec* __restrict__ reads, uint32_t n_reads,
+                                 const LeafRec* __restrict__ leaves, WalkRec* __restrict__ walks, uint32_t* __restrict__ node, uint32_t n_walks,
+                                 uint32_t direct) {
+    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_walks) return;
+    ReadRec const R = reads[read_of_walk(reads, n_reads, i)];
+    AnchorRec16 const A = anchors[i];
+    LeafRec const L = leaves[R.leaf_base + A.pex_leaf_index];
+    uint32_t const orient = i - R.walk_begin >= R.n_forward ? 1u : 0u;
+    WalkRec w;
+    w.diag = int64_t(A.reference_position) - int64_t(L.from);
+    w.qoff = orient ? R.qoff_reverse : R.qoff_forward;
+    w.node_base = R.node_base; w.ref_id = A.reference_id; w.orient = orient;
+    w.node = (!direct && L.parent != kNoParent && L.parent != 0) ? R.node_base + L.parent : kAtRootNode;      // inner[0] is the root
+    walks[i] = w;
+    node[i] = w.node;
+}
 
 struct LevelCtx {
     const WalkRec* walks; const NodeRec* nodes; uint32_t n_walks;
     const uint64_t* ref_base; const uint64_t* ref_len;
     uint32_t* node;                    // per walk: node to align next
     uint64_t* ask_ws; uint32_t* ask_len; uint8_t* flag;
-    unsigned long long* rep;           // per (node, strand): (window start << 24 | walk) of the elected walk, 0 = none
+    unsigned long long* rep;           // per (node, strand): (window start << kWalkBits | walk) of the elected walk, 0 = none
     unsigned long long* rep_min;       // the same for the walk with the leftmost window start (all ones = none)
     uint32_t* n_inner; uint64_t* sum_inner; uint64_t* cells_inner;     // statistics per walk, verification.cpp:238-242
-    DpTask* tasks; uint32_t* counts;   // class c: tasks + c * n_walks, counts[c]
+    DpTask* tasks;                     // one array for all classes: class c begins at class_active[0] + .. + class_active[c-1]
+    uint32_t* counts;                  // tasks appended per class by the phase at hand
+    uint32_t* class_active;            // walks per class that wait at this level (set by level_begin_kernel)
     const DpResult* results;           // per walk
-    unsigned long long* totals;        // [0] engine tasks, [1] their word-steps, [2] answers inferred, [3..5] sums of the statistics
+    unsigned long long* totals;        // [0] engine tasks, [1] their word-steps, [2] answers inferred
     uint32_t level, infer;
-    uint8_t cls_W[16];                 // block width of every class (for the word-step count)
+    uint8_t cls_W[kMaxLevelClasses];   // block width of every class (for the word-step count)
 };
-constexpr int kMaxLevelClasses = 16;
 enum : uint8_t { kWalkActive = 1, kWalkComputed = 2, kWalkYes = 4, kWalkAsksLeftmost = 8 };
 
+__device__ __forceinline__ uint32_t class_offset(const uint32_t* __restrict__ class_active, uint32_t cls) {
+    uint32_t o = 0;
+    for (uint32_t c = 0; c < cls; ++c) o += class_active[c];
+    return o;
+}
+
 __device__ __forceinline__ void emit_level_task(LevelCtx const& C, uint32_t i, NodeRec const& N, uint64_t qoff) {
-    uint32_t const slot = atomicAdd(C.counts + N.cls, 1u);
+    uint32_t const slot = class_offset(C.class_active, N.cls) + atomicAdd(C.counts + N.cls, 1u);
     DpTask t;
     t.ref_base = C.ask_ws[i]; t.query_base = qoff + N.from; t.trace_base = 0;
     t.n = C.ask_len[i]; t.m = N.m; t.dlo = -int32_t(N.k); t.dhi = int32_t(t.n) - int32_t(N.m) + int32_t(N.k);
     t.flags = 0; t.out = i;
-    C.tasks[size_t(N.cls) * C.n_walks + slot] = t;
+    C.tasks[slot] = t;
     // word-steps the engine issues for it (host: word_steps_of): block b works on columns cs(b)..ce(b)
     uint32_t const W = C.cls_W[N.cls], rows = 32 * W, nb = (N.m + rows - 1) / rows;
     int64_t const pad = int64_t(nb) * rows - N.m;
@@ -951,77 +1021,41 @@ __device__ __forceinline__ void emit_level_task(LevelCtx const& C, uint32_t i, N
     atomicAdd(C.totals + 1, ws);
 }
 
-// The walk records straight from the caller's anchors (compact mode of the host's run_levels_on_device): the first node
-// of a walk is its leaf's parent (verification.cpp:66-70).
-struct ReadRec {
-    uint32_t walk_begin;               // first walk (= anchor) of the read within the part
-    uint32_t n_forward;                // its forward anchors come first
-    uint32_t node_base, leaf_base;     // where the read's NodeRecs / LeafRecs begin
-    uint64_t qoff_forward, qoff_reverse;
-};
-struct LeafRec { uint32_t from; uint32_t parent; };          // query_index_from, inner index of the parent (kNoParent: none)
-struct AnchorRec { uint64_t pex_leaf_index, reference_id, reference_position, num_errors; };   // = fxg_anchor
-constexpr uint32_t kNoParent = 0xffffffffu;
-
-__global__ void walk_init_kernel(const AnchorRec* __restrict__ anchors, const ReadRec* __restrict__ reads, uint32_t n_reads,
-                                 const LeafRec* __restrict__ leaves, WalkRec* __restrict__ walks, uint32_t* __restrict__ node, uint32_t n_walks) {
-    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_walks) return;
-    uint32_t lo = 0, hi = n_reads;                     // last read with walk_begin <= i
-    while (hi - lo > 1) { uint32_t const mid = (lo + hi) >> 1; if (reads[mid].walk_begin <= i) lo = mid; else hi = mid; }
-    ReadRec const R = reads[lo];
-    AnchorRec const A = anchors[i];
-    LeafRec const L = leaves[R.leaf_base + uint32_t(A.pex_leaf_index)];
-    uint32_t const orient = i - R.walk_begin >= R.n_forward ? 1u : 0u;
-    WalkRec w;
-    w.diag = int64_t(A.reference_position) - int64_t(L.from);
-    w.qoff = orient ? R.qoff_reverse : R.qoff_forward;
-    w.node_base = R.node_base; w.ref_id = uint32_t(A.reference_id); w.orient = orient;
-    w.node = (L.parent != kNoParent && L.parent != 0) ? R.node_base + L.parent : kAtRootNode;      // inner[0] is the root
-    walks[i] = w;
-    node[i] = w.node;
-}
-
-// sums of the per-walk statistics (every walk counts when the interval optimisation is off)
-__global__ void level_stats_kernel(LevelCtx const C) {
-    uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long a = 0, b = 0, c = 0;
-    if (i < C.n_walks) { a = C.n_inner[i]; b = C.sum_inner[i]; c = C.cells_inner[i]; }
-    for (int off = 16; off > 0; off >>= 1) {
-        a += __shfl_down_sync(0xffffffffu, a, off); b += __shfl_down_sync(0xffffffffu, b, off); c += __shfl_down_sync(0xffffffffu, c, off);
-    }
-    if ((threadIdx.x & 31u) == 0 && (a | b | c)) { atomicAdd(C.totals + 3, a); atomicAdd(C.totals + 4, b); atomicAdd(C.totals + 5, c); }
-}
-
 __global__ void level_begin_kernel(LevelCtx const C) {
     uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C.n_walks) return;
-    uint32_t const nd = C.node[i];
     uint8_t f = 0;
-    if (nd < kAtRootNode) {
-        NodeRec const N = C.nodes[nd];
-        if (N.depth == C.level) {
-            WalkRec const Wk = C.walks[i];
-            int64_t const s = Wk.diag + int64_t(N.from) - int64_t(N.k);
-            uint64_t const offset = s >= 0 ? uint64_t(s) : 0;
-            uint64_t const base = uint64_t(N.m) + 2ull * N.k + 1;
-            uint64_t const room = C.ref_len[Wk.ref_id] - offset;
-            uint64_t const len = base < room ? base : room;
-            C.n_inner[i] += 1; C.sum_inner[i] += len; C.cells_inner[i] += uint64_t(N.m) * len;
-            if (int64_t(N.m) - int64_t(len) > int64_t(N.k)) {
-                C.node[i] = kDeadNode;                   // more insertions needed than errors allowed: no alignment
-            } else {
-                uint64_t const ws = C.ref_base[Wk.ref_id] + offset;
-                C.ask_ws[i] = ws; C.ask_len[i] = uint32_t(len);
-                f = kWalkActive;
-                if (C.infer) {
-                    atomicMax(C.rep + (size_t(nd) * 2 + Wk.orient), (unsigned long long)((ws << 24) | i));
-                    atomicMin(C.rep_min + (size_t(nd) * 2 + Wk.orient), (unsigned long long)((ws << 24) | i));
+    uint32_t cls = 0xffu;
+    if (i < C.n_walks) {
+        uint32_t const nd = C.node[i];
+        if (nd < kAtRootNode) {
+            NodeRec const N = C.nodes[nd];
+            if (N.depth == C.level) {
+                WalkRec const Wk = C.walks[i];
+                int64_t const s = Wk.diag + int64_t(N.from) - int64_t(N.k);
+                uint64_t const offset = s >= 0 ? uint64_t(s) : 0;
+                uint64_t const base = uint64_t(N.m) + 2ull * N.k + 1;
+                uint64_t const room = C.ref_len[Wk.ref_id] - offset;
+                uint64_t const len = base < room ? base : room;
+                C.n_inner[i] += 1; C.sum_inner[i] += len; C.cells_inner[i] += uint64_t(N.m) * len;
+                if (int64_t(N.m) - int64_t(len) > int64_t(N.k)) {
+                    C.node[i] = kDeadNode;                   // more insertions needed than errors allowed: no alignment
+                } else {
+                    uint64_t const ws = C.ref_base[Wk.ref_id] + offset;
+                    C.ask_ws[i] = ws; C.ask_len[i] = uint32_t(len);
+                    f = kWalkActive;
+                    cls = N.cls;
+                    if (C.infer) {
+                        atomicMax(C.rep + (size_t(nd) * 2 + Wk.orient), (unsigned long long)((ws << kWalkBits) | i));
+                        atomicMin(C.rep_min + (size_t(nd) * 2 + Wk.orient), (unsigned long long)((ws << kWalkBits) | i));
+                    }
                 }
             }
         }
+        C.flag[i] = f;
     }
-    C.flag[i] = f;
+    // walks per class (the classes share one task array), one atomic per class and warp
+    uint32_t const peers = __match_any_sync(0xffffffffu, cls);
+    if (cls != 0xffu && (threadIdx.x & 31u) == uint32_t(__ffs(int(peers)) - 1)) atomicAdd(C.class_active + cls, uint32_t(__popc(peers)));
 }
 
 __global__ void level_first_kernel(LevelCtx const C) {
@@ -1029,7 +1063,7 @@ __global__ void level_first_kernel(LevelCtx const C) {
     if (i >= C.n_walks || !(C.flag[i] & kWalkActive)) return;
     uint32_t const nd = C.node[i];
     WalkRec const Wk = C.walks[i];
-    if (C.infer && uint32_t(C.rep[size_t(nd) * 2 + Wk.orient] & 0xffffffull) != i) return;
+    if (C.infer && uint32_t(C.rep[size_t(nd) * 2 + Wk.orient] & kWalkMask) != i) return;
     emit_level_task(C, i, C.nodes[nd], Wk.qoff);
     C.flag[i] |= kWalkComputed;
 }
@@ -1051,7 +1085,7 @@ __global__ void level_second_kernel(LevelCtx const C) {
     NodeRec const N = C.nodes[nd];
     WalkRec const Wk = C.walks[i];
     size_t const key = size_t(nd) * 2 + Wk.orient;
-    uint32_t const a = uint32_t(C.rep[key] & 0xffffffull);
+    uint32_t const a = uint32_t(C.rep[key] & kWalkMask);
     DpResult const R = C.results[a];
     bool const a_yes = R.score <= int32_t(N.k);
     uint64_t const ws = C.ask_ws[i]; uint32_t const len = C.ask_len[i];
@@ -1060,7 +1094,7 @@ __global__ void level_second_kernel(LevelCtx const C) {
     if (a_yes) {
         if (same_ref && ws + len >= C.ask_ws[a] + R.end_col) { C.flag[i] = f | kWalkYes; atomicAdd(C.totals + 2, 1ull); return; }
     } else if (same_ref) {
-        uint32_t const c = uint32_t(C.rep_min[key] & 0xffffffull);
+        uint32_t const c = uint32_t(C.rep_min[key] & kWalkMask);
         if (C.walks[c].ref_id == Wk.ref_id && C.ask_ws[a] - C.ask_ws[c] <= uint64_t(N.k) + 1) {
             if (i != c) { C.flag[i] = f | kWalkAsksLeftmost; return; }
         }
@@ -1079,7 +1113,7 @@ __global__ void level_third_kernel(LevelCtx const C) {
     uint32_t const nd = C.node[i];
     NodeRec const N = C.nodes[nd];
     WalkRec const Wk = C.walks[i];
-    uint32_t const c = uint32_t(C.rep_min[size_t(nd) * 2 + Wk.orient] & 0xffffffull);
+    uint32_t const c = uint32_t(C.rep_min[size_t(nd) * 2 + Wk.orient] & kWalkMask);
     DpResult const R = C.results[c];
     if (R.score > int32_t(N.k)) { atomicAdd(C.totals + 2, 1ull); return; }                    // no alignment in A, none in C: none in B
     uint64_t const ws = C.ask_ws[i]; uint32_t const len = C.ask_len[i];
@@ -1101,6 +1135,169 @@ __global__ void level_advance_kernel(LevelCtx const C) {
     NodeRec const N = C.nodes[nd];
     bool const yes = (f & kWalkComputed) ? C.results[i].score <= int32_t(N.k) : (f & kWalkYes) != 0;
     C.node[i] = yes ? C.walks[i].node_base + N.parent : kDeadNode;      // pex_tree::get_parent_of_child, pex.cpp:70-76
+}
+
+// ---------------------------------------------------------------------------------------------
+// Which walks count, and which of them verify their root (verification.cpp:45-71, 106-109, 119-136).
+//
+// One warp per (read, strand), walks in anchor order -- the order of the reference's anchor loop
+// (parallelization.cpp:230-249).  Without the interval optimisation every walk counts and every walk that stands at its
+// root verifies it.  With it, a walk whose root window, trimmed by the extra length on both sides
+// (half_open_interval::trim_from_both_sides, intervals.cpp:48-58), lies inside the root window of an EARLIER walk of the
+// same reference that reached its root (and was not avoided itself) is avoided: its inner alignments, computed
+// speculatively, do not count, and it verifies nothing (root_was_already_verified, verification.cpp:119-136; the
+// window is inserted whenever the root is reached, even if the root alignment then fails, :106-109).  Whether a walk
+// reaches its root depends on its inner alignments alone, so this one pass decides everything.
+// The windows inserted so far sit in registers (one per lane); beyond 32 they spill to `inserted` (walk indices).
+// ---------------------------------------------------------------------------------------------
+struct DecideCtx {
+    const WalkRec* walks; const uint32_t* node; const ReadRec* reads; uint32_t n_reads;
+    const uint64_t* ref_len;
+    const uint32_t* n_inner; const uint64_t* sum_inner; const uint64_t* cells_inner;
+    uint8_t* root_flag;                // out, per walk: 1 = verifies its root
+    uint32_t* root_count;              // out, per (read, strand): how many do
+    uint32_t* inserted;                // scratch, one entry per walk
+    unsigned long long* member_totals; // per member: n_aligned_inner, sum_aligned_inner, cells_inner, n_avoided_root, sum_avoided_root, 3 spare
+    uint32_t ivopt;
+};
+constexpr int kMemberTotals = 8;
+
+// root window of a walk: [start, start + len) in its reference's coordinates (compute_reference_span_start_and_length)
+__device__ __forceinline__ void root_window(ReadRec const& R, int64_t diag, uint64_t ref_len, uint64_t& start, uint64_t& len) {
+    uint64_t const base = uint64_t(R.root_m) + 2ull * R.root_k + 1;
+    int64_t const s = diag + int64_t(R.root_from) - int64_t(R.root_k) - int64_t(R.root_extra);
+    start = s >= 0 ? uint64_t(s) : 0;
+    uint64_t const full = base + 2ull * R.root_extra, room = ref_len - start;
+    len = full < room ? full : room;
+}
+
+__global__ void decide_kernel(DecideCtx const C) {
+    uint32_t const lane = threadIdx.x & 31u;
+    uint32_t const pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;          // (read, strand)
+    if (pair >= 2 * C.n_reads) return;
+    ReadRec const R = C.reads[pair >> 1];
+    uint32_t const orient = pair & 1u;
+    uint32_t const w0 = R.walk_begin + (orient ? R.n_forward : 0u);
+    uint32_t const w1 = orient ? R.walk_begin + R.n_walks : R.walk_begin + R.n_forward;
+    uint32_t n_ins = 0, n_root = 0;
+    uint32_t ins_ref = 0; uint64_t ins_start = 0, ins_end = 0;                    // entry `lane` of the inserted windows
+    unsigned long long s_n = 0, s_sum = 0, s_cells = 0, s_av = 0, s_avsum = 0;
+    for (uint32_t base = w0; base < w1; base += 32) {
+        uint32_t const i = base + lane;
+        bool const have = i < w1;
+        uint32_t ref = 0; uint64_t rs = 0, len = 0; bool reached = false;
+        if (have) {
+            WalkRec const Wk = C.walks[i];
+            ref = Wk.ref_id;
+            root_window(R, Wk.diag, C.ref_len[ref], rs, len);
+            reached = C.node[i] != kDeadNode;
+        }
+        uint64_t const re = rs + len;
+        // trimmed by the extra length on both sides (intervals.cpp:48-58)
+        uint64_t const e0 = R.root_extra > re ? 0 : re - R.root_extra;
+        uint64_t const te = e0 > rs + 1 ? e0 : rs + 1;
+        uint64_t const ts = te - 1 < rs + R.root_extra ? te - 1 : rs + R.root_extra;
+        bool my_avoided = false, my_root = false;
+        uint32_t const n_here = min(32u, w1 - base);
+        for (uint32_t q = 0; q < n_here; ++q) {
+            uint32_t const q_ref = __shfl_sync(0xffffffffu, ref, q);
+            uint64_t const q_rs = __shfl_sync(0xffffffffu, rs, q), q_re = __shfl_sync(0xffffffffu, re, q);
+            uint64_t const q_ts = __shfl_sync(0xffffffffu, ts, q), q_te = __shfl_sync(0xffffffffu, te, q);
+            bool const q_reached = __shfl_sync(0xffffffffu, int(reached), q) != 0;
+            bool avoided = false;
+            if (C.ivopt) {
+                bool hit = lane < min(n_ins, 32u) && ins_ref == q_ref && ins_start <= q_ts && ins_end >= q_te;
+                for (uint32_t e = 32 + lane; e < n_ins; e += 32) {
+                    WalkRec const Wi = C.walks[C.inserted[w0 + e]];
+                    uint64_t is, il;
+                    root_window(R, Wi.diag, C.ref_len[Wi.ref_id], is, il);
+                    hit |= Wi.ref_id == q_ref && is <= q_ts && is + il >= q_te;
+                }
+                avoided = __any_sync(0xffffffffu, hit);
+            }
+            if (avoided) {
+                if (lane == q) my_avoided = true;
+            } else if (q_reached) {
+                if (lane == q) my_root = true;
+                if (C.ivopt) {
+                    if (n_ins < 32) { if (lane == n_ins) { ins_ref = q_ref; ins_start = q_rs; ins_end = q_re; } }
+                    else { if (lane == 0) C.inserted[w0 + n_ins] = base + q; __syncwarp(); }
+                    ++n_ins;
+                }
+                ++n_root;
+            }
+        }
+        if (have) {
+            C.root_flag[i] = my_root ? 1 : 0;
+            if (my_avoided) { s_av += 1; s_avsum += len; }
+            else { s_n += C.n_inner[i]; s_sum += C.sum_inner[i]; s_cells += C.cells_inner[i]; }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        s_n += __shfl_down_sync(0xffffffffu, s_n, off); s_sum += __shfl_down_sync(0xffffffffu, s_sum, off);
+        s_cells += __shfl_down_sync(0xffffffffu, s_cells, off); s_av += __shfl_down_sync(0xffffffffu, s_av, off);
+        s_avsum += __shfl_down_sync(0xffffffffu, s_avsum, off);
+    }
+    if (lane == 0) {
+        C.root_count[pair] = n_root;
+        unsigned long long* const T = C.member_totals + size_t(R.member) * kMemberTotals;
+        if (s_n | s_sum | s_cells) { atomicAdd(T + 0, s_n); atomicAdd(T + 1, s_sum); atomicAdd(T + 2, s_cells); }
+        if (s_av) { atomicAdd(T + 3, s_av); atomicAdd(T + 4, s_avsum); }
+    }
+}
+
+// exclusive prefix sums of `counts` (one CTA; n is the number of (read, strand) pairs of a batch); total -> *total
+__global__ void scan_counts_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t n, uint32_t* __restrict__ total) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    uint32_t const lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        uint32_t const i = base + threadIdx.x;
+        uint32_t const v = i < n ? counts[i] : 0u;
+        uint32_t x = v;
+        for (int off = 1; off < 32; off <<= 1) { uint32_t const y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= uint32_t(off)) x += y; }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0u;
+            for (int off = 1; off < 32; off <<= 1) { uint32_t const y = __shfl_up_sync(0xffffffffu, s, off); if (lane >= uint32_t(off)) s += y; }
+            warp_sums[lane] = s;                                       // inclusive sums of the warps
+        }
+        __syncthreads();
+        uint32_t const before = carry + (wid ? warp_sums[wid - 1] : 0u);
+        if (i < n) offsets[i] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// the walks that verify their root, in walk order
+struct RootEntry { int64_t diag; uint32_t walk; uint32_t ref_id; };
+__global__ void root_emit_kernel(DecideCtx const C, const uint32_t* __restrict__ offsets, RootEntry* __restrict__ out) {
+    uint32_t const lane = threadIdx.x & 31u;
+    uint32_t const pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pair >= 2 * C.n_reads) return;
+    if (C.root_count[pair] == 0) return;
+    ReadRec const R = C.reads[pair >> 1];
+    uint32_t const orient = pair & 1u;
+    uint32_t const w0 = R.walk_begin + (orient ? R.n_forward : 0u);
+    uint32_t const w1 = orient ? R.walk_begin + R.n_walks : R.walk_begin + R.n_forward;
+    uint32_t at = offsets[pair];
+    for (uint32_t base = w0; base < w1; base += 32) {
+        uint32_t const i = base + lane;
+        bool const is_root = i < w1 && C.root_flag[i] != 0;
+        uint32_t const bal = __ballot_sync(0xffffffffu, is_root);
+        if (is_root) {
+            WalkRec const Wk = C.walks[i];
+            RootEntry e; e.diag = Wk.diag; e.walk = i; e.ref_id = Wk.ref_id;
+            out[at + __popc(bal & ((1u << lane) - 1u))] = e;
+        }
+        at += __popc(bal);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

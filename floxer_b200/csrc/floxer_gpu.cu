@@ -148,10 +148,10 @@ struct Worker {
     // tracebacks are long chains of dependent steps: the root alignments of a wave are cut into chunks, each chunk's
     // tracebacks run on a stream of their own beside the score passes (and tracebacks) of the other chunks
     static constexpr int kWalkSlots = 4;
-    DevBuf d_tasks, d_results, d_ck[kWalkSlots], d_wtasks, d_wresults, d_cigars, d_rtasks, d_rresults, d_lv;
+    DevBuf d_tasks, d_results, d_ck[kWalkSlots], d_wtasks, d_wresults, d_cigars, d_rtasks, d_rresults, d_lv, d_roots;
     cudaStream_t walk_stream[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_walk_done[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr}, ev_w0 = nullptr, ev_w1[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
-    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults, h_rtasks, h_rresults, h_lv, h_lv_back;
+    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults, h_rtasks, h_rresults, h_lv, h_lv_back, h_roots;
     fxg_counters ctr{};
     std::string err;
     std::vector<ConfigCacheEntry> cfg_cache = std::vector<ConfigCacheEntry>(8192);
@@ -159,7 +159,7 @@ struct Worker {
     std::vector<Config> cfgs;
     uint64_t cig_used = 0;               // ops of d_cigars filled by the current run
     void release() {
-        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults, &d_lv}) b->release();
+        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults, &d_lv, &d_roots}) b->release();
         if (ev_w0) { cudaEventDestroy(ev_w0); ev_w0 = nullptr; }
         if (ev_b0) { cudaEventDestroy(ev_b0); ev_b0 = nullptr; }
         if (ev_b1) { cudaEventDestroy(ev_b1); ev_b1 = nullptr; }
@@ -171,7 +171,7 @@ struct Worker {
             if (walk_stream[q]) cudaStreamDestroy(walk_stream[q]);
             ev_walk_done[q] = ev_w1[q] = nullptr; walk_stream[q] = nullptr;
         }
-        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults, &h_rtasks, &h_rresults, &h_lv, &h_lv_back}) b->release();
+        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults, &h_rtasks, &h_rresults, &h_lv, &h_lv_back, &h_roots}) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -193,7 +193,8 @@ struct Worker {
 struct WorkerGroup {
     std::vector<std::unique_ptr<Worker>> workers;
     size_t use_workers = 0;              // decided when the group is acquired
-    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr, ev_staged = nullptr;
+    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr, ev_merged = nullptr;
+    Pool merged;                         // the Peq planes of a batch merged from several jobs (build_merged_pool)
     bool busy = false;
 };
 
@@ -229,6 +230,22 @@ struct HostProf {
 };
 HostProf g_prof;
 
+struct ClassDef { uint8_t widx, G; uint32_t max_words; };   // a (block width, ring size) configuration of the engine and its widest Eq table
+
+// The device-resident records of a job (prepare_job / run_device_walks).
+struct Prepared {
+    bool ok = false;                     // the device-side walk can take the job
+    DevBuf dev; PinnedBuf staging;       // nodes | leaves | reads | anchors, carved at the offsets below
+    size_t o_nodes = 0, o_leaves = 0, o_reads = 0, o_anchors = 0;
+    uint32_t n_nodes = 0, n_leaves = 0, n_walks = 0, n_reads = 0;
+    uint32_t max_depth = 0;
+    uint32_t level_mask[256] = {0};      // classes that occur per tree depth
+    std::vector<ReadRec> hreads;         // the ReadRecs on the host (bases relative to the job)
+    cudaEvent_t ready = nullptr;         // the upload has finished
+};
+
+struct Ticket;
+
 }  // namespace
 
 struct fxg_ctx {
@@ -243,7 +260,6 @@ struct fxg_ctx {
     int n_groups = 32;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
     WorkerGroup groups[kMaxGroups];
     cudaStream_t stage_stream = nullptr; // uploads of references / query pools, Peq construction
-    std::condition_variable group_free;
     DevBuf d_tmp;
     uint64_t trace_budget = 0;
     int workers_busy = 4;                        // workers a group uses when more than a quarter of the groups are busy
@@ -253,7 +269,17 @@ struct fxg_ctx {
     int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
     std::vector<Pool> spare_pools;       // device buffers of freed batches / jobs, reused by the next stage call
     std::vector<PinnedBuf> spare_pinned; // page-locked cigar pools of freed batches / jobs (cudaHostAlloc costs milliseconds)
+    std::vector<DevBuf> spare_dev;       // record buffers of freed jobs
     std::mutex mu;
+    // the queue of fxg_verify_run / fxg_verify_reads calls: a caller that finds a free worker group takes every compatible
+    // job that is waiting with it and runs them as one batch (submit_and_wait)
+    std::vector<Ticket*> pending;
+    std::condition_variable cv;
+    uint64_t merge_max_walks = uint64_t(6) << 20;   // FXG_MERGE_WALKS: anchors of a merged batch at most (a single job may be larger)
+    int merge_max_jobs = 64;                        // FXG_MERGE_JOBS (1 = never merge)
+    std::mutex class_mu;
+    ClassDef classes[kMaxLevelClasses];
+    int n_classes = 0;
 };
 
 struct fxg_batch {
@@ -283,6 +309,9 @@ struct Walk {                 // one query_verifier::verify() call
     bool have_root_span;
     uint32_t n_inner; uint64_t sum_inner, cells_inner;   // its inner-node alignments so far (verification.cpp:238-242)
     uint64_t start_in_reference; uint32_t num_errors; uint64_t cigar_offset; uint32_t cigar_len;
+    uint32_t ref_id, member;  // reference of its anchor; member job of its read
+    uint32_t rm, rk;          // the root node's piece length and errors ...
+    uint64_t rqbase;          // ... and where that piece begins in the pool, in the walk's orientation
 };
 
 struct Group { uint32_t first, count; };   // members are consecutive entries of group_members
@@ -302,20 +331,29 @@ struct fxg_job {
     uint64_t pool_len = 0;
     Pool pool;                           // forward pool followed by the reverse-complement pool
     std::vector<uint32_t> read_walk_begin;   // per read (+1 sentinel): index of its first walk (= anchor) in job order
+    Prepared prep;
+    cudaEvent_t pool_ready = nullptr;    // (fxg_verify_reads) the query pools and their Peq planes are in place
     // results
     std::vector<fxg_alignment> alignments;
     PinnedBuf cigars;                    // page-locked; every worker's cigars arrive here directly from the device
     size_t cigars_len = 0;
+    // a job that ran merged with others reads its cigars out of the batch's pool (kept alive by `shared`)
+    std::shared_ptr<PinnedBuf> shared; const uint32_t* shared_cigars = nullptr;
     fxg_stats stats{};
     bool ran = false;
 };
 
 namespace {
 
+// The text of the calling thread's last failed call (fxg_last_error): calls run concurrently on one context, so the
+// message is kept per thread, not per context.
+thread_local std::string tls_last_error;
+
 int fail(std::string& err, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
     err = buf;
+    tls_last_error = buf;
     return code;
 }
 
@@ -329,7 +367,7 @@ void add_counters(fxg_counters& a, fxg_counters const& b) {
     a.kernel_launches += b.kernel_launches; a.dp_tasks += b.dp_tasks; a.dp_word_steps += b.dp_word_steps;
     a.dp_cells_full += b.dp_cells_full; a.trace_bytes += b.trace_bytes; a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
     a.root_launch_ms += b.root_launch_ms; a.root_launch_word_steps += b.root_launch_word_steps; a.shared_tracebacks += b.shared_tracebacks; a.inferred_inner += b.inferred_inner;
-    a.shared_score_passes += b.shared_score_passes; a.rescored_roots += b.rescored_roots;
+    a.shared_score_passes += b.shared_score_passes; a.rescored_roots += b.rescored_roots; a.batches += b.batches; a.batch_jobs += b.batch_jobs;
     a.trace_word_steps += b.trace_word_steps; a.dp_kernel_ms += b.dp_kernel_ms; a.trace_kernel_ms += b.trace_kernel_ms; a.waves += b.waves; a.run_ms += b.run_ms;
 }
 
@@ -355,10 +393,10 @@ WorkerGroup& acquire_group(fxg_ctx* c, std::unique_lock<std::mutex>& lock) {
             g.use_workers = busy == 0 ? g.workers.size() : std::min(g.workers.size(), size_t(c->workers_busy));
             return g;
         }
-        c->group_free.wait(lock);
+        c->cv.wait(lock);
     }
 }
-void release_group(fxg_ctx* c, WorkerGroup& g) { g.busy = false; c->group_free.notify_one(); }
+void release_group(fxg_ctx* c, WorkerGroup& g) { g.busy = false; c->cv.notify_all(); }
 
 int env_int(const char* name, int dflt, int lo, int hi) {
     if (const char* e = std::getenv(name)) { int const v = std::atoi(e); if (v >= lo && v <= hi) return v; }
@@ -491,10 +529,10 @@ bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
 }
 
 // the same (m, n, band) recurs for every anchor of a read at one tree level: memoise
-bool cached_config(Worker& w, Pass const& p, size_t smem_limit, Config& out) {
+bool cached_config(std::vector<ConfigCacheEntry>& cache, Pass const& p, size_t smem_limit, Config& out) {
     uint64_t h = (uint64_t(p.n) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(p.m) * 0xC2B2AE3D27D4EB4Full) ^ (uint64_t(uint32_t(p.dlo)) << 21) ^ uint64_t(uint32_t(p.dhi));
     h ^= h >> 29;
-    ConfigCacheEntry& e = w.cfg_cache[h & (w.cfg_cache.size() - 1)];
+    ConfigCacheEntry& e = cache[h & (cache.size() - 1)];
     if (e.valid && e.n == p.n && e.m == p.m && e.dlo == p.dlo && e.dhi == p.dhi) { out = e.cfg; return e.ok; }
     e.valid = true; e.n = p.n; e.m = p.m; e.dlo = p.dlo; e.dhi = p.dhi;
     e.ok = choose_config(p, smem_limit, e.cfg);
@@ -533,7 +571,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     w.keys.resize(N);
     for (size_t i = 0; i < N; ++i) {
         Config& cf = w.cfgs[i];
-        if (!cached_config(w, passes[i], c->smem_limit, cf))
+        if (!cached_config(w.cfg_cache, passes[i], c->smem_limit, cf))
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
                         passes[i].m, passes[i].n, passes[i].dlo, passes[i].dhi);
         uint64_t const steps = std::min<uint64_t>(uint64_t(passes[i].n) + cf.nb - 1, (1u << 19) - 1);
@@ -698,7 +736,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
     std::vector<Unit> units;
     std::vector<uint32_t> unit_members;
     auto finish_unit = [&](Unit& u) -> int {
-        if (!cached_config(w, u.p, c->smem_limit, u.cfg))
+        if (!cached_config(w.cfg_cache, u.p, c->smem_limit, u.cfg))
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
                         u.p.m, u.p.n, u.p.dlo, u.p.dhi);
         uint32_t const W = uint32_t(kWidths[u.cfg.widx]);
@@ -756,13 +794,19 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
             } else {
                 Unit u{};
                 u.k = uint32_t(k0); u.first = uint32_t(unit_members.size()); u.count = uint32_t(j - i);
-                for (size_t q = i; q < j; ++q) unit_members.push_back(order[q]);
                 // the union as a window of its own: same band rule as score_pass_for
                 u.p = P0; u.p.n = uint32_t(u_end - u_start);
                 u.p.dlo = -int32_t(k0); u.p.dhi = int32_t(int64_t(u.p.n) - int64_t(u.p.m) + int64_t(k0));
-                int const rc = finish_unit(u);
-                if (rc != FXG_OK) return rc;
-                units.push_back(u);
+                Config probe;
+                if (cached_config(w.cfg_cache, u.p, c->smem_limit, probe)) {
+                    for (size_t q = i; q < j; ++q) unit_members.push_back(order[q]);
+                    int const rc = finish_unit(u);
+                    if (rc != FXG_OK) return rc;
+                    units.push_back(u);
+                } else {
+                    // the union's band is wider than the engine takes although each member's may not be: every member on its own
+                    for (size_t q = i; q < j; ++q) { int const rc = add_single(order[q]); if (rc != FXG_OK) return rc; }
+                }
             }
             i = j;
         }
@@ -774,7 +818,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         cigar_bound += cigar_cap_for(max_errors[i]);
         // a member that has to be scored again on its own must fit the budget as well
         Config cf;
-        if (cached_config(w, passes[i], c->smem_limit, cf)) {
+        if (cached_config(w.cfg_cache, passes[i], c->smem_limit, cf)) {
             uint32_t const W = uint32_t(kWidths[cf.widx]);
             max_words = std::max(max_words, (uint64_t(cf.nb) * ck_records_per_block(int64_t(passes[i].dhi) - int64_t(passes[i].dlo) + 1, 32 * W) * ck_record_words(W) + 3) & ~uint64_t(3));
         }
@@ -1220,18 +1264,6 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
     }
 }
 
-// fxg_verify_reads uploads the query pools while the parts already prepare their first wave on the host: a part waits
-// here before its first launch
-struct StageGate {
-    std::mutex mu; std::condition_variable cv;
-    bool ready = false; int rc = FXG_OK; std::string err;
-    void open(int code, std::string const& message) {
-        { std::lock_guard<std::mutex> lock(mu); ready = true; rc = code; err = message; }
-        cv.notify_all();
-    }
-    int wait() { std::unique_lock<std::mutex> lock(mu); cv.wait(lock, [&] { return ready; }); return rc; }
-};
-
 int validate_reads(fxg_ctx* c, std::string& err, const fxg_read* reads, size_t lo, size_t hi, size_t pool_len,
                    const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors) {
     for (size_t i = lo; i < hi; ++i) {
@@ -1245,6 +1277,15 @@ int validate_reads(fxg_ctx* c, std::string& err, const fxg_read* reads, size_t l
             if (nd[q].query_index_to < nd[q].query_index_from || nd[q].query_index_to >= R.query_len) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: node %u outside the query", i, q);
             if (nd[q].parent_id != FXG_NULL_ID && nd[q].parent_id >= R.num_inner) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: node %u has a bad parent", i, q);
         }
+        // shape of the tree (pex.hpp:59-76): inner[0] is the root, every other inner node hangs below it
+        if (R.num_inner) {
+            if (nd[0].parent_id != FXG_NULL_ID) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: inner node 0 is not the root", i);
+            for (uint32_t q = 1; q < R.num_inner; ++q) {
+                if (nd[q].parent_id == FXG_NULL_ID) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: inner node %u has no parent", i, q);
+                uint64_t p = q; int hops = 0;
+                while (p != 0) { p = nd[p].parent_id; if (p == FXG_NULL_ID || ++hops > 250) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: the parents of inner node %u do not lead to the root", i, q); }
+            }
+        }
         const fxg_anchor* an = anchors + R.anchor_offset;
         for (uint32_t q = 0; q < R.num_anchors_forward + R.num_anchors_reverse; ++q) {
             if (an[q].pex_leaf_index >= R.num_leaves) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: anchor %u names leaf %llu", i, q, (unsigned long long)an[q].pex_leaf_index);
@@ -1256,9 +1297,26 @@ int validate_reads(fxg_ctx* c, std::string& err, const fxg_read* reads, size_t l
 }
 
 struct PartOut {
-    std::vector<fxg_alignment> alignments;   // cigar offsets index the job's cigar pool
-    fxg_stats stats{};
+    std::vector<fxg_alignment> alignments;   // cigar offsets index the batch's cigar pool
+    std::vector<fxg_stats> stats;            // per member job
     int rc = FXG_OK;
+};
+
+// One or more jobs that run together: a job of its own, or the jobs of several callers merged by submit_and_wait.
+struct Member { fxg_job* J; uint32_t read0; uint64_t pool_shift; };
+struct Batch {
+    fxg_verify_config cfg{};
+    std::vector<Member> members;
+    bool device = false;                 // every member has device records: the walks run on the device
+    uint32_t n_reads = 0;
+    std::vector<uint32_t> read_walk_begin;   // per read of the batch (+1 sentinel): its first walk
+    Pool const* pool = nullptr;          // the Peq planes the passes read: the member's own, or the group's merged ones
+    uint64_t pool_len = 0;               // (a job of its own) length of its forward pool
+    cudaEvent_t merged_ready = nullptr;  // the merged planes are in place
+    // results
+    std::vector<fxg_alignment> alignments;
+    PinnedBuf* cigars = nullptr; size_t cigars_len = 0;
+    std::vector<fxg_stats> stats;
 };
 
 // what one part carries from its score phase to its traceback phase
@@ -1267,10 +1325,11 @@ struct PartState {
     uint64_t trace_budget = 0;               // bytes of checkpoint records the part may hold at a time
     std::chrono::steady_clock::time_point t0;
     double cpu0 = 0;                         // the part's thread CPU time at its start (FXG_PROFILE)
+    std::vector<ReadRec> part_reads;         // (device-side walks) the part's ReadRecs as the device sees them
     PartOut out;
 };
 
-// hops from an inner node to the root, memoised per read (the trees are small)
+// hops from an inner node to the root, memoised per read (the trees are small; validate_reads has bounded the chains)
 uint8_t node_dist(const fxg_pex_node* inner, std::vector<uint8_t>& memo, uint64_t id) {
     if (memo[id] != 0xff) return memo[id];
     uint8_t d = 0;
@@ -1278,257 +1337,274 @@ uint8_t node_dist(const fxg_pex_node* inner, std::vector<uint8_t>& memo, uint64_
     return memo[id] = d;
 }
 
-// The inner levels of a part on the device (dp_kernels.cuh: level_*_kernel): the host writes one record per inner node and
-// per walk, enqueues the kernels of every level and synchronises once.
-// General mode (`walks` filled by build_walks, `level[d]` = the walks that start d hops below the root): on return every
-// walk of level[>= 1] is either done or stands at its root and has joined level[0].
-// Compact mode (`walks` empty; no interval optimisation, so every walk counts and no walk needs another's window): the
-// walk records come straight from the anchors, and only the walks that stand at their root afterwards -- one in six in
-// config 2 -- ever get a Walk object; the statistics of all walks go to `out`.
-// Returns FXG_OK, an error, or kNotOnDevice when the part does not fit the device path's limits (the host loop then runs).
-constexpr int kNotOnDevice = 1;
-int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, std::vector<Walk>& walks,
-                         std::vector<std::vector<uint32_t>>& level, bool compact, PartOut& out,
-                         std::function<bool()> const& before_first_launch, int& gate_rc) {
-    size_t const n_walks = J->read_walk_begin[read_hi] - J->read_walk_begin[read_lo];
-    if (n_walks == 0 || n_walks >= kMaxDeviceWalks) return kNotOnDevice;
-    if (!compact && (level.size() < 2 || walks.size() != n_walks)) return kNotOnDevice;
-    g_prof.start(w);
-    // ---- node records (inner nodes of the part's reads, read after read) and their configuration classes ----
-    struct Cls { uint8_t widx, G; uint32_t max_words; };
-    std::vector<Cls> classes;
-    uint32_t level_mask[256] = {0};
-    std::vector<uint32_t> node_base(read_hi - read_lo + 1, 0);
-    size_t n_nodes = 0;
-    for (uint32_t ri = read_lo; ri < read_hi; ++ri) { node_base[ri - read_lo] = uint32_t(n_nodes); n_nodes += J->reads_p[ri].num_inner; }
-    node_base[read_hi - read_lo] = uint32_t(n_nodes);
-    if (n_nodes == 0 || n_nodes >= (size_t(1) << 30)) return kNotOnDevice;
-    // In compact mode the walk records are made on the device from the caller's anchors (copied as they are) and small read /
-    // leaf tables, provided the part's anchors lie back to back in the caller's array (walk i of the part = anchor a_lo + i).
-    size_t const n_part_reads = read_hi - read_lo;
-    uint64_t const a_lo = J->reads_p[read_lo].anchor_offset;
-    bool device_init = compact;
-    size_t n_leaves = 0;
-    std::vector<uint32_t> leaf_base(n_part_reads + 1, 0);
-    if (device_init) {
-        uint64_t expect = a_lo;
-        for (uint32_t ri = read_lo; ri < read_hi && device_init; ++ri) {
-            fxg_read const& R = J->reads_p[ri];
-            if (R.anchor_offset != expect) device_init = false;
-            expect += uint64_t(R.num_anchors_forward) + R.num_anchors_reverse;
-            leaf_base[ri - read_lo] = uint32_t(n_leaves); n_leaves += R.num_leaves;
-        }
-        leaf_base[n_part_reads] = uint32_t(n_leaves);
-        if (n_leaves >= (size_t(1) << 30)) device_init = false;
+// ------------------------------------------------------------------------------------------------ prepared jobs
+//
+// The device-side tree walk (dp_kernels.cuh: walk_init / level_* / decide kernels) reads a job from compact records made
+// ONCE per job, on the caller's thread, and kept in HBM: NodeRec per inner node, LeafRec per leaf, ReadRec per read,
+// AnchorRec16 per anchor.  A run then touches no per-anchor data on the host: it gathers the records of the jobs it was
+// handed (device-to-device), lets the walks climb, and reads back only the walks that verify their root.
+
+// configuration classes are numbered per context, so that the records of different jobs can share a launch
+int class_of(fxg_ctx* c, Config const& cf, uint32_t words) {
+    std::lock_guard<std::mutex> lock(c->class_mu);
+    for (int i = 0; i < c->n_classes; ++i)
+        if (c->classes[i].widx == cf.widx && c->classes[i].G == cf.G) { c->classes[i].max_words = std::max(c->classes[i].max_words, words); return i; }
+    if (c->n_classes == kMaxLevelClasses) return -1;
+    c->classes[c->n_classes] = ClassDef{cf.widx, cf.G, words};
+    return c->n_classes++;
+}
+
+std::vector<ConfigCacheEntry>& thread_config_cache() {
+    thread_local std::vector<ConfigCacheEntry> cache(8192);
+    return cache;
+}
+
+// Builds and uploads the job's records (asynchronously, on the context's staging stream; J->prep.ready marks the end).
+// J->prep.ok tells whether the device-side walk can take the job; if not, the host-driven levels run it.
+int prepare_job(fxg_ctx* c, fxg_job* J, std::string& err, fxg_counters& ctr) {
+    Prepared& P = J->prep;
+    P.ok = false;
+    size_t const n_reads = J->n_reads;
+    if (n_reads == 0 || !c->device_levels) return FXG_OK;
+    uint64_t n_nodes = 0, n_leaves = 0, n_walks = 0;
+    for (size_t ri = 0; ri < n_reads; ++ri) {
+        fxg_read const& R = J->reads_p[ri];
+        if (R.num_inner >= 0xffff) return FXG_OK;
+        n_nodes += R.num_inner; n_leaves += R.num_leaves; n_walks += uint64_t(R.num_anchors_forward) + R.num_anchors_reverse;
     }
-    size_t const bytes_nodes = n_nodes * sizeof(NodeRec), bytes_walks = n_walks * sizeof(WalkRec), bytes_init = n_walks * 4;
-    size_t const bytes_reads = (n_part_reads * sizeof(ReadRec) + 15) & ~size_t(15), bytes_leaves = (n_leaves * sizeof(LeafRec) + 15) & ~size_t(15);
-    static_assert(sizeof(AnchorRec) == sizeof(fxg_anchor) && sizeof(ReadRec) == 32 && sizeof(LeafRec) == 8 && sizeof(NodeRec) == 16 && sizeof(WalkRec) == 32, "record layouts");
-    size_t const bytes_anchors = n_walks * sizeof(fxg_anchor);
-    size_t const staging = bytes_nodes + (device_init ? bytes_reads + bytes_leaves + bytes_anchors : bytes_walks + bytes_init);
-    if (w.h_lv.ensure(staging + 64) != cudaSuccess) return fail(w.err, FXG_ERR_OUT_OF_MEMORY, "cannot allocate staging for the tree levels");
-    NodeRec* const nrec = w.h_lv.as<NodeRec>();
-    WalkRec* const wrec = reinterpret_cast<WalkRec*>(w.h_lv.as<uint8_t>() + bytes_nodes);
-    uint32_t* const ninit = reinterpret_cast<uint32_t*>(w.h_lv.as<uint8_t>() + bytes_nodes + bytes_walks);
-    ReadRec* const rrec = reinterpret_cast<ReadRec*>(w.h_lv.as<uint8_t>() + bytes_nodes);                       // (device_init layout)
-    LeafRec* const lrec = reinterpret_cast<LeafRec*>(w.h_lv.as<uint8_t>() + bytes_nodes + bytes_reads);
-    uint8_t* const arec = w.h_lv.as<uint8_t>() + bytes_nodes + bytes_reads + bytes_leaves;
-    size_t max_depth = 0;
-    {
-        std::vector<uint8_t> memo;
-        const fxg_pex_node* prev = nullptr; uint32_t prev_n = 0, prev_base = 0, prev_leaves = 0, prev_leaf_base = 0;
-        // a PEX tree is a function of the read's length and the batch's parameters: reads of equal length have equal trees, and
-        // the records of an equal tree are copied instead of rebuilt (the trees are compared, not assumed equal)
-        std::unordered_map<uint64_t, uint32_t> first_of_shape;
-        for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
-            fxg_read const& R = J->reads_p[ri];
-            if (R.num_inner >= 0xffff) return kNotOnDevice;
-            const fxg_pex_node* inner = J->nodes_p + R.node_offset;
-            uint32_t const base = node_base[ri - read_lo];
-            {
-                uint64_t const shape = (uint64_t(R.query_len) << 32) ^ (uint64_t(R.num_inner) << 16) ^ R.num_leaves;
-                auto const ins = first_of_shape.emplace(shape, ri);
-                if (!ins.second) {
-                    fxg_read const& Q = J->reads_p[ins.first->second];
-                    prev = J->nodes_p + Q.node_offset; prev_n = Q.num_inner; prev_base = node_base[ins.first->second - read_lo];
-                    prev_leaves = Q.num_leaves; prev_leaf_base = leaf_base[ins.first->second - read_lo];
-                }
-            }
-            if (device_init) {
-                ReadRec& rr = rrec[ri - read_lo];
-                rr.walk_begin = J->read_walk_begin[ri] - J->read_walk_begin[read_lo]; rr.n_forward = R.num_anchors_forward;
-                rr.node_base = base; rr.leaf_base = leaf_base[ri - read_lo];
-                rr.qoff_forward = R.query_offset; rr.qoff_reverse = J->pool_len + R.query_offset;
-                const fxg_pex_node* leaves = inner + R.num_inner;
-                LeafRec* const lr = lrec + rr.leaf_base;
-                if (prev && prev_n == R.num_inner && prev_leaves == R.num_leaves &&
-                    std::memcmp(prev + prev_n, leaves, size_t(R.num_leaves) * sizeof(fxg_pex_node)) == 0) {
-                    std::memcpy(lr, lrec + prev_leaf_base, size_t(R.num_leaves) * sizeof(LeafRec));
-                } else {
-                    for (uint32_t q = 0; q < R.num_leaves; ++q) {
-                        lr[q].from = uint32_t(leaves[q].query_index_from);
-                        lr[q].parent = leaves[q].parent_id == FXG_NULL_ID ? kNoParent : uint32_t(leaves[q].parent_id);
-                    }
-                }
-                prev_leaves = R.num_leaves; prev_leaf_base = rr.leaf_base;
-            }
-            if (prev && prev_n == R.num_inner && std::memcmp(prev, inner, size_t(R.num_inner) * sizeof(fxg_pex_node)) == 0) {
-                std::memcpy(nrec + base, nrec + prev_base, size_t(R.num_inner) * sizeof(NodeRec));   // the same tree as the read before
-            } else {
-                memo.assign(R.num_inner, 0xff);
-                for (uint32_t q = 0; q < R.num_inner; ++q) {
-                    fxg_pex_node const& nd = inner[q];
-                    NodeRec& r = nrec[base + q];
-                    r.from = uint32_t(nd.query_index_from); r.m = uint32_t(nd.query_index_to - nd.query_index_from + 1); r.k = uint32_t(nd.num_errors);
-                    r.parent = nd.parent_id == FXG_NULL_ID ? uint16_t(0) : uint16_t(nd.parent_id);
-                    r.depth = node_dist(inner, memo, q);
-                    Pass p;
-                    uint64_t const n_full = uint64_t(r.m) + 2ull * r.k + 1;
-                    if (!score_pass_for(0, 0, uint32_t(n_full), r.m, r.k, 0, p)) return kNotOnDevice;
-                    Config cf;
-                    if (!cached_config(w, p, c->smem_limit, cf)) return kNotOnDevice;
-                    size_t ci = 0;
-                    while (ci < classes.size() && !(classes[ci].widx == cf.widx && classes[ci].G == cf.G)) ++ci;
-                    if (ci == classes.size()) { if (ci == size_t(kMaxLevelClasses)) return kNotOnDevice; classes.push_back(Cls{cf.widx, cf.G, 0}); }
-                    r.cls = uint8_t(ci);
-                }
-                for (uint32_t q = 0; q < R.num_inner; ++q) {               // (copied trees add nothing new here)
-                    NodeRec const& r = nrec[base + q];
-                    uint32_t const W = uint32_t(kWidths[classes[r.cls].widx]);
-                    classes[r.cls].max_words = std::max(classes[r.cls].max_words, (r.m + 32 * W - 1) / (32 * W) * W);
-                    level_mask[r.depth] |= 1u << r.cls;
-                    max_depth = std::max<size_t>(max_depth, r.depth);
-                }
-            }
-            prev = inner; prev_n = R.num_inner; prev_base = base;
-        }
-    }
-    // ---- walk records; start_count[d] = walks that start d hops below the root ----
-    size_t start_count[256] = {0};
-    size_t n_levels = 1;
-    if (!compact) {
-        n_levels = level.size();
-        for (size_t d = 0; d < n_levels; ++d) start_count[std::min<size_t>(d, 255)] += level[d].size();
-        for (size_t i = 0; i < n_walks; ++i) {
-            Walk const& wk = walks[i];
-            fxg_read const& R = J->reads_p[wk.read];
-            fxg_anchor const& A = J->anchors_p[wk.anchor];
-            const fxg_pex_node* inner = J->nodes_p + R.node_offset;
-            const fxg_pex_node* leaves = inner + R.num_inner;
-            WalkRec& r = wrec[i];
-            r.diag = int64_t(A.reference_position) - int64_t(leaves[A.pex_leaf_index].query_index_from);
-            r.qoff = (wk.orient ? J->pool_len : 0) + R.query_offset;
-            r.node_base = node_base[wk.read - read_lo];
-            r.ref_id = uint32_t(A.reference_id); r.orient = wk.orient;
-            bool const below_root = R.num_inner && wk.node > inner && wk.node < inner + R.num_inner;       // inner[0] is the root
-            r.node = below_root ? r.node_base + uint32_t(wk.node - inner) : kAtRootNode;
-            ninit[i] = r.node;
-        }
-    } else if (device_init) {
-        std::memcpy(arec, J->anchors_p + a_lo, bytes_anchors);
-        n_levels = max_depth + 1;                                 // (levels no walk starts at or reaches cost a few empty launches)
-        for (size_t d = 1; d < n_levels; ++d) start_count[d] = 0;
-        start_count[n_levels - 1] = n_walks;                      // grids are sized for every walk at every level
-        if (n_levels < 2) return kNotOnDevice;
-    } else {
-        size_t i = 0;
-        for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
-            fxg_read const& R = J->reads_p[ri];
-            const fxg_pex_node* leaves = J->nodes_p + R.node_offset + R.num_inner;
-            uint32_t const nb = node_base[ri - read_lo];
-            for (uint32_t orient = 0; orient < 2; ++orient) {
-                uint32_t const a0 = uint32_t(R.anchor_offset) + (orient ? R.num_anchors_forward : 0);
-                uint32_t const na = orient ? R.num_anchors_reverse : R.num_anchors_forward;
-                uint64_t const qoff = (orient ? J->pool_len : 0) + R.query_offset;
-                for (uint32_t q = 0; q < na; ++q, ++i) {
-                    fxg_anchor const& A = J->anchors_p[a0 + q];
-                    fxg_pex_node const& leaf = leaves[A.pex_leaf_index];
-                    WalkRec& r = wrec[i];
-                    r.diag = int64_t(A.reference_position) - int64_t(leaf.query_index_from);
-                    r.qoff = qoff; r.node_base = nb; r.ref_id = uint32_t(A.reference_id); r.orient = orient;
-                    // first node: the leaf's parent (verification.cpp:66-70); the root itself is not an inner level
-                    bool const below_root = leaf.parent_id != FXG_NULL_ID && leaf.parent_id != 0;
-                    r.node = below_root ? nb + uint32_t(leaf.parent_id) : kAtRootNode;
-                    ninit[i] = r.node;
-                    size_t const d = below_root ? nrec[r.node].depth : 0;
-                    start_count[d]++;
-                    n_levels = std::max(n_levels, d + 1);
-                }
-            }
-        }
-        if (n_levels < 2) return kNotOnDevice;
-    }
-    g_prof.lap(w, 2);
-    // ---- device buffers: one allocation, carved up ----
-    size_t const n_cls = classes.size();
+    if (n_walks == 0 || n_walks >= kMaxDeviceWalks || n_nodes >= (1u << 30) || n_leaves >= (1u << 30) || n_reads >= (1u << 30)) return FXG_OK;
+    if (c->refs.total >= (uint64_t(1) << (64 - kWalkBits))) return FXG_OK;
+    static_assert(sizeof(AnchorRec16) == 16 && sizeof(ReadRec) == 64 && sizeof(LeafRec) == 8 && sizeof(NodeRec) == 16 && sizeof(WalkRec) == 32 && sizeof(RootEntry) == 16, "record layouts");
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t const at = off; off += (bytes + 255) & ~size_t(255); return at; };
-    size_t const stats_bytes = n_walks * 4 + n_walks * 8 * 2 + 64;                // n_inner | sum_inner | cells_inner | totals (6 x 8 bytes)
-    size_t const o_nodes = carve(bytes_nodes), o_walks = carve(bytes_walks), o_node = carve(bytes_init);
-    size_t const o_reads = carve(device_init ? bytes_reads : 0), o_leaves = carve(device_init ? bytes_leaves : 0), o_anchors = carve(device_init ? bytes_anchors : 0);
-    size_t const o_ws = carve(n_walks * 8), o_len = carve(n_walks * 4), o_flag = carve(n_walks);
-    size_t const o_rep = carve(n_nodes * 2 * 8), o_rep_min = carve(n_nodes * 2 * 8);
-    size_t const o_stats = carve(stats_bytes);
-    size_t const o_tasks = carve(n_cls * n_walks * sizeof(DpTask));
-    size_t const o_counts = carve(size_t(kMaxLevelClasses) * 4);
-    size_t const o_results = carve(n_walks * sizeof(DpResult));
+    P.o_nodes = carve(n_nodes * sizeof(NodeRec)); P.o_leaves = carve(n_leaves * sizeof(LeafRec));
+    P.o_reads = carve(n_reads * sizeof(ReadRec)); P.o_anchors = carve(n_walks * sizeof(AnchorRec16));
+    if (P.staging.ensure(off + 64) != cudaSuccess) return fail(err, FXG_ERR_OUT_OF_MEMORY, "cannot allocate staging for the job's records");
+    CUDA_TRY(err, P.dev.ensure(off + 64));
+    uint8_t* const H = P.staging.as<uint8_t>();
+    NodeRec* const nrec = reinterpret_cast<NodeRec*>(H + P.o_nodes);
+    LeafRec* const lrec = reinterpret_cast<LeafRec*>(H + P.o_leaves);
+    ReadRec* const rrec = reinterpret_cast<ReadRec*>(H + P.o_reads);
+    AnchorRec16* const arec = reinterpret_cast<AnchorRec16*>(H + P.o_anchors);
+    std::memset(P.level_mask, 0, sizeof P.level_mask);
+    P.max_depth = 0;
+    double const ratio = J->cfg.extra_verification_ratio;
+    std::vector<ConfigCacheEntry>& cache = thread_config_cache();
+    std::vector<uint8_t> memo;
+    // a PEX tree is a function of the read's length and the batch's parameters: reads of equal length have equal trees, and
+    // the records of an equal tree are copied instead of rebuilt (the trees are compared, not assumed equal)
+    std::unordered_map<uint64_t, uint32_t> first_of_shape;
+    uint32_t node_at = 0, leaf_at = 0, walk_at = 0;
+    for (size_t ri = 0; ri < n_reads; ++ri) {
+        fxg_read const& R = J->reads_p[ri];
+        const fxg_pex_node* inner = J->nodes_p + R.node_offset;
+        const fxg_pex_node* leaves = inner + R.num_inner;
+        ReadRec& rr = rrec[ri];
+        rr.walk_begin = walk_at; rr.n_forward = R.num_anchors_forward; rr.node_base = node_at; rr.leaf_base = leaf_at;
+        rr.qoff_forward = R.query_offset; rr.qoff_reverse = J->pool_len + R.query_offset;
+        fxg_pex_node const& root = R.num_inner ? inner[0] : leaves[0];
+        rr.root_from = uint32_t(root.query_index_from); rr.root_m = uint32_t(root.query_index_to - root.query_index_from + 1); rr.root_k = uint32_t(root.num_errors);
+        uint64_t const base = uint64_t(rr.root_m) + 2ull * rr.root_k + 1;
+        uint64_t const extra = ratio == 0.0 ? 0 : ceil_eps(double(base) * ratio);
+        if (extra >= (1u << 30)) return FXG_OK;
+        rr.root_extra = uint32_t(extra);
+        rr.member = 0; rr.n_walks = R.num_anchors_forward + R.num_anchors_reverse; rr.reserved0 = rr.reserved1 = 0;
+        uint64_t const shape = (uint64_t(R.query_len) << 32) ^ (uint64_t(R.num_inner) << 16) ^ R.num_leaves;
+        auto const ins = first_of_shape.emplace(shape, uint32_t(ri));
+        bool copied = false;
+        if (!ins.second) {
+            fxg_read const& Q = J->reads_p[ins.first->second];
+            if (Q.num_inner == R.num_inner && Q.num_leaves == R.num_leaves &&
+                std::memcmp(J->nodes_p + Q.node_offset, inner, (size_t(R.num_inner) + R.num_leaves) * sizeof(fxg_pex_node)) == 0) {
+                ReadRec const& qr = rrec[ins.first->second];
+                std::memcpy(nrec + node_at, nrec + qr.node_base, size_t(R.num_inner) * sizeof(NodeRec));
+                std::memcpy(lrec + leaf_at, lrec + qr.leaf_base, size_t(R.num_leaves) * sizeof(LeafRec));
+                copied = true;
+            }
+        }
+        if (!copied) {
+            memo.assign(R.num_inner, 0xff);
+            for (uint32_t q = 0; q < R.num_inner; ++q) {
+                fxg_pex_node const& nd = inner[q];
+                NodeRec& r = nrec[node_at + q];
+                r.from = uint32_t(nd.query_index_from); r.m = uint32_t(nd.query_index_to - nd.query_index_from + 1); r.k = uint32_t(nd.num_errors);
+                r.parent = nd.parent_id == FXG_NULL_ID ? uint16_t(0) : uint16_t(nd.parent_id);
+                r.depth = node_dist(inner, memo, q);
+                Pass p;
+                uint64_t const n_full = uint64_t(r.m) + 2ull * r.k + 1;
+                if (!score_pass_for(0, 0, uint32_t(n_full), r.m, r.k, 0, p)) return FXG_OK;
+                Config cf;
+                if (!cached_config(cache, p, c->smem_limit, cf)) return FXG_OK;
+                uint32_t const W = uint32_t(kWidths[cf.widx]);
+                int const ci = class_of(c, cf, (r.m + 32 * W - 1) / (32 * W) * W);
+                if (ci < 0) return FXG_OK;
+                r.cls = uint8_t(ci);
+                if (q > 0) {                                       // the root is not an inner level
+                    P.level_mask[r.depth] |= 1u << ci;
+                    P.max_depth = std::max<uint32_t>(P.max_depth, r.depth);
+                }
+            }
+            for (uint32_t q = 0; q < R.num_leaves; ++q) {
+                lrec[leaf_at + q].from = uint32_t(leaves[q].query_index_from);
+                lrec[leaf_at + q].parent = leaves[q].parent_id == FXG_NULL_ID ? kNoParent : uint32_t(leaves[q].parent_id);
+            }
+        }
+        const fxg_anchor* an = J->anchors_p + R.anchor_offset;
+        for (uint32_t q = 0; q < rr.n_walks; ++q) {
+            AnchorRec16& a = arec[walk_at + q];
+            a.reference_position = an[q].reference_position; a.pex_leaf_index = uint32_t(an[q].pex_leaf_index); a.reference_id = uint32_t(an[q].reference_id);
+        }
+        node_at += R.num_inner; leaf_at += R.num_leaves; walk_at += rr.n_walks;
+    }
+    P.n_nodes = node_at; P.n_leaves = leaf_at; P.n_walks = walk_at; P.n_reads = uint32_t(n_reads);
+    P.hreads.assign(rrec, rrec + n_reads);
+    if (!P.ready) CUDA_TRY(err, cudaEventCreateWithFlags(&P.ready, cudaEventDisableTiming));
+    CUDA_TRY(err, cudaMemcpyAsync(P.dev.p, H, off, cudaMemcpyHostToDevice, c->stage_stream));
+    CUDA_TRY(err, cudaEventRecord(P.ready, c->stage_stream));
+    ctr.h2d_bytes += off;
+    P.ok = true;
+    return FXG_OK;
+}
+
+// root window of a walk, as the device computes it (dp_kernels.cuh: root_window) and as compute_span does from the nodes
+inline Span root_span_of(ReadRec const& R, int64_t diag, uint64_t ref_len) {
+    uint64_t const base = uint64_t(R.root_m) + 2ull * R.root_k + 1;
+    int64_t const s = diag + int64_t(R.root_from) - int64_t(R.root_k) - int64_t(R.root_extra);
+    Span r;
+    r.offset = s >= 0 ? uint64_t(s) : 0;
+    r.length = std::min<uint64_t>(base + 2ull * R.root_extra, ref_len - r.offset);
+    r.extra = R.root_extra;
+    return r;
+}
+
+// The tree walks of reads [r0, r1) of a batch on the device.  On return P.walks holds one Walk per anchor that verifies
+// its root (in anchor order, level[0] lists them all), and the statistics of the inner levels and of the interval
+// optimisation have been added to P.out.stats per member.
+int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, PartState& P, std::vector<std::vector<uint32_t>>& level) {
+    g_prof.start(w);
+    PartOut& out = P.out;
+    cudaStream_t const st = w.stream;
+    // ---- the members' slices that make up this part ----
+    struct Slice { uint32_t member, a, b; uint32_t walk0, node0, leaf0, read0, n_walks, n_nodes, n_leaves; };
+    std::vector<Slice> slices;
+    uint32_t n_walks = 0, n_nodes = 0, n_leaves = 0;
+    uint32_t level_mask[256] = {0};
+    uint32_t max_depth = 0;
+    for (size_t mi = 0; mi < B.members.size(); ++mi) {
+        Member const& M = B.members[mi];
+        Prepared const& R = M.J->prep;
+        uint32_t const lo = std::max(r0, M.read0), hi = std::min(r1, M.read0 + R.n_reads);
+        if (lo >= hi) continue;
+        Slice s{};
+        s.member = uint32_t(mi); s.a = lo - M.read0; s.b = hi - M.read0;
+        auto walk_at = [&](uint32_t i) { return i < R.n_reads ? R.hreads[i].walk_begin : R.n_walks; };
+        auto node_at = [&](uint32_t i) { return i < R.n_reads ? R.hreads[i].node_base : R.n_nodes; };
+        auto leaf_at = [&](uint32_t i) { return i < R.n_reads ? R.hreads[i].leaf_base : R.n_leaves; };
+        s.walk0 = n_walks; s.node0 = n_nodes; s.leaf0 = n_leaves; s.read0 = lo - r0;
+        s.n_walks = walk_at(s.b) - walk_at(s.a); s.n_nodes = node_at(s.b) - node_at(s.a); s.n_leaves = leaf_at(s.b) - leaf_at(s.a);
+        n_walks += s.n_walks; n_nodes += s.n_nodes; n_leaves += s.n_leaves;
+        for (uint32_t d = 1; d <= R.max_depth; ++d) level_mask[d] |= R.level_mask[d];
+        max_depth = std::max(max_depth, R.max_depth);
+        slices.push_back(s);
+    }
+    uint32_t const n_reads = r1 - r0;
+    P.walks.clear();
+    level.assign(1, std::vector<uint32_t>());
+    if (n_walks == 0) return FXG_OK;
+    bool const ivopt = B.cfg.interval_optimization != 0;
+    bool const direct = B.cfg.verification_kind == FXG_KIND_DIRECT_FULL;
+    size_t const n_members = B.members.size();
+    // ---- classes (a copy of the context's table as of now: it only grows, and every class of these jobs is in it) ----
+    ClassDef classes[kMaxLevelClasses]; int n_cls = 0;
+    { std::lock_guard<std::mutex> lock(c->class_mu); n_cls = c->n_classes; std::copy(c->classes, c->classes + n_cls, classes); }
+    // ---- device buffers: one allocation, carved up ----
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t const at = off; off += (bytes + 255) & ~size_t(255); return at; };
+    size_t const o_nodes = carve(size_t(n_nodes) * sizeof(NodeRec)), o_leaves = carve(size_t(n_leaves) * sizeof(LeafRec));
+    size_t const o_reads = carve(size_t(n_reads) * sizeof(ReadRec)), o_anchors = carve(size_t(n_walks) * sizeof(AnchorRec16));
+    size_t const o_walks = carve(size_t(n_walks) * sizeof(WalkRec)), o_node = carve(size_t(n_walks) * 4);
+    size_t const o_ws = carve(size_t(n_walks) * 8), o_len = carve(size_t(n_walks) * 4), o_flag = carve(n_walks);
+    size_t const o_rep = carve(size_t(n_nodes) * 2 * 8), o_rep_min = carve(size_t(n_nodes) * 2 * 8);
+    // zeroed together: n_inner | sum_inner | cells_inner | counts | class_active | totals | member totals | n_roots
+    size_t const o_zero = off;
+    size_t const o_ninner = carve(size_t(n_walks) * 4), o_sum = carve(size_t(n_walks) * 8), o_cells = carve(size_t(n_walks) * 8);
+    size_t const o_counts = carve(size_t(kMaxLevelClasses) * 4 * 2);               // counts, then class_active
+    size_t const o_back = carve(64 + n_members * kMemberTotals * 8);                // totals (3) | n_roots | member totals: read back together
+    size_t const zero_bytes = off - o_zero;
+    size_t const o_tasks = carve(size_t(n_walks) * sizeof(DpTask));
+    size_t const o_results = carve(size_t(n_walks) * sizeof(DpResult));
+    size_t const o_rootflag = carve(n_walks), o_rootcnt = carve(size_t(n_reads) * 2 * 4), o_rootoff = carve(size_t(n_reads) * 2 * 4);
+    size_t const o_inserted = carve(ivopt ? size_t(n_walks) * 4 : 0);
     CUDA_TRY(w.err, w.d_lv.ensure(off));
     uint8_t* const D = w.d_lv.as<uint8_t>();
-    size_t const o_sum = o_stats + ((n_walks * 4 + 7) & ~size_t(7));
-    size_t const o_cells = o_sum + n_walks * 8, o_totals = o_cells + n_walks * 8;
-    cudaStream_t const st = w.stream;
-    if (!before_first_launch()) { gate_rc = FXG_ERR_STATE; return FXG_ERR_STATE; }      // (the caller has set the part's error)
-    CUDA_TRY(w.err, cudaMemcpyAsync(D + o_nodes, nrec, bytes_nodes, cudaMemcpyHostToDevice, st));
-    if (device_init) {
-        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_reads, rrec, bytes_reads, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_leaves, lrec, bytes_leaves, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_anchors, arec, bytes_anchors, cudaMemcpyHostToDevice, st));
-        walk_init_kernel<<<uint32_t((n_walks + 255) / 256), 256, 0, st>>>(reinterpret_cast<const AnchorRec*>(D + o_anchors), reinterpret_cast<const ReadRec*>(D + o_reads),
-                                                                        uint32_t(n_part_reads), reinterpret_cast<const LeafRec*>(D + o_leaves),
-                                                                        reinterpret_cast<WalkRec*>(D + o_walks), reinterpret_cast<uint32_t*>(D + o_node), uint32_t(n_walks));
+    size_t const o_member_totals = o_back + 64;
+    // ---- gather the members' records (device to device), bases shifted to their place in this part ----
+    P.part_reads.resize(n_reads);
+    for (Slice const& s : slices) {
+        Member const& M = B.members[s.member];
+        Prepared const& R = M.J->prep;
+        CUDA_TRY(w.err, cudaStreamWaitEvent(st, R.ready, 0));
+        if (M.J->pool_ready) CUDA_TRY(w.err, cudaStreamWaitEvent(st, M.J->pool_ready, 0));
+        const uint8_t* const S = R.dev.as<uint8_t>();
+        ReadRec const& first = R.hreads[s.a];
+        if (s.n_nodes) CUDA_TRY(w.err, cudaMemcpyAsync(D + o_nodes + size_t(s.node0) * sizeof(NodeRec), S + R.o_nodes + size_t(first.node_base) * sizeof(NodeRec),
+                                                       size_t(s.n_nodes) * sizeof(NodeRec), cudaMemcpyDeviceToDevice, st));
+        if (s.n_leaves) CUDA_TRY(w.err, cudaMemcpyAsync(D + o_leaves + size_t(s.leaf0) * sizeof(LeafRec), S + R.o_leaves + size_t(first.leaf_base) * sizeof(LeafRec),
+                                                        size_t(s.n_leaves) * sizeof(LeafRec), cudaMemcpyDeviceToDevice, st));
+        if (s.n_walks) CUDA_TRY(w.err, cudaMemcpyAsync(D + o_anchors + size_t(s.walk0) * sizeof(AnchorRec16), S + R.o_anchors + size_t(first.walk_begin) * sizeof(AnchorRec16),
+                                                       size_t(s.n_walks) * sizeof(AnchorRec16), cudaMemcpyDeviceToDevice, st));
+        uint32_t const n = s.b - s.a;
+        uint32_t const d_walk = s.walk0 - first.walk_begin, d_node = s.node0 - first.node_base, d_leaf = s.leaf0 - first.leaf_base;   // (modulo 2^32)
+        gather_reads_kernel<<<(n + 127) / 128, 128, 0, st>>>(reinterpret_cast<const ReadRec*>(S + R.o_reads) + s.a, reinterpret_cast<ReadRec*>(D + o_reads) + s.read0,
+                                                            n, d_walk, d_node, d_leaf, M.pool_shift, s.member);
         CUDA_TRY(w.err, cudaGetLastError());
         w.ctr.kernel_launches++;
-        w.ctr.h2d_bytes += bytes_nodes + bytes_reads + bytes_leaves + bytes_anchors;
-    } else {
-        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_walks, wrec, bytes_walks, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(w.err, cudaMemcpyAsync(D + o_node, ninit, bytes_init, cudaMemcpyHostToDevice, st));
-        w.ctr.h2d_bytes += bytes_nodes + bytes_walks + bytes_init;
+        for (uint32_t i = 0; i < n; ++i) {                     // the same on the host (the root level reads it)
+            ReadRec r = R.hreads[s.a + i];
+            r.walk_begin += d_walk; r.node_base += d_node; r.leaf_base += d_leaf;
+            r.qoff_forward += M.pool_shift; r.qoff_reverse += M.pool_shift; r.member = s.member;
+            P.part_reads[s.read0 + i] = r;
+        }
     }
-    CUDA_TRY(w.err, cudaMemsetAsync(D + o_stats, 0, (stats_bytes + 255) & ~size_t(255), st));
+    if (B.merged_ready) CUDA_TRY(w.err, cudaStreamWaitEvent(st, B.merged_ready, 0));
+    CUDA_TRY(w.err, cudaMemsetAsync(D + o_zero, 0, zero_bytes, st));
+    walk_init_kernel<<<(n_walks + 255) / 256, 256, 0, st>>>(reinterpret_cast<const AnchorRec16*>(D + o_anchors), reinterpret_cast<const ReadRec*>(D + o_reads), n_reads,
+                                                         reinterpret_cast<const LeafRec*>(D + o_leaves), reinterpret_cast<WalkRec*>(D + o_walks),
+                                                         reinterpret_cast<uint32_t*>(D + o_node), n_walks, direct ? 1u : 0u);
+    CUDA_TRY(w.err, cudaGetLastError());
+    w.ctr.kernel_launches++;
 
     LevelCtx C{};
-    C.walks = reinterpret_cast<const WalkRec*>(D + o_walks); C.nodes = reinterpret_cast<const NodeRec*>(D + o_nodes); C.n_walks = uint32_t(n_walks);
+    C.walks = reinterpret_cast<const WalkRec*>(D + o_walks); C.nodes = reinterpret_cast<const NodeRec*>(D + o_nodes); C.n_walks = n_walks;
     C.ref_base = c->refs.d_base.as<uint64_t>(); C.ref_len = c->refs.d_len.as<uint64_t>();
     C.node = reinterpret_cast<uint32_t*>(D + o_node);
     C.ask_ws = reinterpret_cast<uint64_t*>(D + o_ws); C.ask_len = reinterpret_cast<uint32_t*>(D + o_len); C.flag = D + o_flag;
     C.rep = reinterpret_cast<unsigned long long*>(D + o_rep); C.rep_min = reinterpret_cast<unsigned long long*>(D + o_rep_min);
-    C.n_inner = reinterpret_cast<uint32_t*>(D + o_stats); C.sum_inner = reinterpret_cast<uint64_t*>(D + o_sum); C.cells_inner = reinterpret_cast<uint64_t*>(D + o_cells);
-    C.tasks = reinterpret_cast<DpTask*>(D + o_tasks); C.counts = reinterpret_cast<uint32_t*>(D + o_counts);
+    C.n_inner = reinterpret_cast<uint32_t*>(D + o_ninner); C.sum_inner = reinterpret_cast<uint64_t*>(D + o_sum); C.cells_inner = reinterpret_cast<uint64_t*>(D + o_cells);
+    C.tasks = reinterpret_cast<DpTask*>(D + o_tasks);
+    C.counts = reinterpret_cast<uint32_t*>(D + o_counts); C.class_active = C.counts + kMaxLevelClasses;
     C.results = reinterpret_cast<const DpResult*>(D + o_results);
-    C.totals = reinterpret_cast<unsigned long long*>(D + o_totals);
+    C.totals = reinterpret_cast<unsigned long long*>(D + o_back);
     C.infer = c->infer_inner ? 1u : 0u;
-    for (size_t ci = 0; ci < n_cls; ++ci) C.cls_W[ci] = uint8_t(kWidths[classes[ci].widx]);
+    for (int ci = 0; ci < n_cls; ++ci) C.cls_W[ci] = uint8_t(kWidths[classes[ci].widx]);
 
-    // walks that can stand at level d or deeper: the engine's grids are sized for them
-    std::vector<size_t> at_or_below(n_levels + 1, 0);
-    for (size_t d = n_levels; d-- > 0;) at_or_below[d] = at_or_below[d + 1] + start_count[d];
-
-    uint32_t const wgrid = uint32_t((n_walks + 255) / 256);
-    auto engine = [&](uint32_t mask, size_t cap) -> int {
+    uint32_t const wgrid = (n_walks + 255) / 256;
+    Pool const& pool = *B.pool;
+    auto engine = [&](uint32_t mask) -> int {
         // the classes of a level are independent: the first on the worker's stream, the others beside it
         int n_launch = 0;
         bool forked = false;
-        for (size_t ci = 0; ci < n_cls; ++ci) {
+        for (int ci = 0; ci < n_cls; ++ci) {
             if (!(mask >> ci & 1u)) continue;
-            Cls const& K = classes[ci];
+            ClassDef const& K = classes[ci];
             uint32_t const tpw = 32u / K.G;
             DpLaunch L{};
-            L.tasks = C.tasks + ci * n_walks; L.n_tasks = uint32_t(cap); L.n_tasks_dev = C.counts + ci;
+            L.tasks = C.tasks; L.n_tasks = n_walks; L.n_tasks_dev = C.counts + ci; L.class_active = C.class_active; L.cls = uint32_t(ci);
             L.group = K.G; L.win_stride = kWinBytes; L.two = 2;
-            L.ref_chunks = c->refs.total / 32 + 1; L.inline_chunks = J->pool.inline_len / 32 + 1;
+            L.ref_chunks = c->refs.total / 32 + 1; L.inline_chunks = 1;
             L.peq_stride = peq_stride_for(K.max_words);
-            L.ref_packed = c->refs.packed.as<uint32_t>(); L.inline_packed = J->pool.inline_packed.as<uint32_t>();
-            L.peq_table = J->pool.peq.as<uint32_t>(); L.peq_plane_words = J->pool.plane_words;
+            L.ref_packed = c->refs.packed.as<uint32_t>(); L.inline_packed = nullptr;
+            L.peq_table = pool.peq.as<uint32_t>(); L.peq_plane_words = pool.plane_words;
             L.results = reinterpret_cast<DpResult*>(D + o_results); L.trace = nullptr;
             size_t const smem = size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
             if (smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", smem);
@@ -1539,7 +1615,7 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
                 if (n_launch <= Worker::kSide) CUDA_TRY(w.err, cudaStreamWaitEvent(s2, w.ev_fork, 0));
             }
             // (no more CTAs than a few waves of the machine: the CTAs take the task groups in turn)
-            uint32_t const grid = uint32_t(std::min<size_t>((cap + tpw - 1) / tpw, size_t(c->num_sms) * 32));
+            uint32_t const grid = uint32_t(std::min<size_t>((size_t(n_walks) + tpw - 1) / tpw, size_t(c->num_sms) * 32));
             CUDA_TRY(w.err, launch_dp(K.widx, false, L, grid, smem, s2));
             w.ctr.kernel_launches++;
             ++n_launch;
@@ -1550,32 +1626,32 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
         }
         return FXG_OK;
     };
+    g_prof.lap(w, 2);
     CUDA_TRY(w.err, cudaEventRecord(w.ev0, st));
-    for (size_t lv = n_levels - 1; lv >= 1; --lv) {
-        size_t const cap = at_or_below[lv];
-        if (cap == 0 || level_mask[lv] == 0) continue;
-        C.level = uint32_t(lv);
-        if (C.infer) {
-            CUDA_TRY(w.err, cudaMemsetAsync(C.rep, 0, n_nodes * 2 * 8, st));
-            CUDA_TRY(w.err, cudaMemsetAsync(C.rep_min, 0xff, n_nodes * 2 * 8, st));
+    for (uint32_t lv = direct ? 0 : max_depth; lv >= 1; --lv) {
+        if (level_mask[lv] == 0) continue;
+        C.level = lv;
+        if (C.infer && n_nodes) {
+            CUDA_TRY(w.err, cudaMemsetAsync(C.rep, 0, size_t(n_nodes) * 2 * 8, st));
+            CUDA_TRY(w.err, cudaMemsetAsync(C.rep_min, 0xff, size_t(n_nodes) * 2 * 8, st));
         }
-        CUDA_TRY(w.err, cudaMemsetAsync(C.counts, 0, size_t(kMaxLevelClasses) * 4, st));
+        CUDA_TRY(w.err, cudaMemsetAsync(C.counts, 0, size_t(kMaxLevelClasses) * 4 * 2, st));
         level_begin_kernel<<<wgrid, 256, 0, st>>>(C);
         level_first_kernel<<<wgrid, 256, 0, st>>>(C);
         CUDA_TRY(w.err, cudaGetLastError());
-        int rc = engine(level_mask[lv], cap);
+        int rc = engine(level_mask[lv]);
         if (rc != FXG_OK) return rc;
         w.ctr.kernel_launches += 2;
         if (C.infer) {
             CUDA_TRY(w.err, cudaMemsetAsync(C.counts, 0, size_t(kMaxLevelClasses) * 4, st));
             level_second_kernel<<<wgrid, 256, 0, st>>>(C);
             CUDA_TRY(w.err, cudaGetLastError());
-            rc = engine(level_mask[lv], cap);
+            rc = engine(level_mask[lv]);
             if (rc != FXG_OK) return rc;
             CUDA_TRY(w.err, cudaMemsetAsync(C.counts, 0, size_t(kMaxLevelClasses) * 4, st));
             level_third_kernel<<<wgrid, 256, 0, st>>>(C);
             CUDA_TRY(w.err, cudaGetLastError());
-            rc = engine(level_mask[lv], cap);                       // (usually nothing is left for it)
+            rc = engine(level_mask[lv]);                       // (usually nothing is left for it)
             if (rc != FXG_OK) return rc;
             w.ctr.kernel_launches += 2;
         }
@@ -1585,75 +1661,68 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
         w.ctr.waves++;
     }
     CUDA_TRY(w.err, cudaEventRecord(w.ev1, st));
-    // ---- the one synchronisation: where every walk ended up, and its statistics (compact mode: only their sums) ----
-    size_t const back_stats = (bytes_init + 15) & ~size_t(15);
-    size_t const back_bytes = back_stats + stats_bytes;
-    CUDA_TRY(w.err, w.h_lv_back.ensure(back_bytes + 64));
-    uint8_t* const B = w.h_lv_back.as<uint8_t>();
-    CUDA_TRY(w.err, cudaMemcpyAsync(B, D + o_node, bytes_init, cudaMemcpyDeviceToHost, st));
-    if (compact) {
-        level_stats_kernel<<<wgrid, 256, 0, st>>>(C);
-        CUDA_TRY(w.err, cudaGetLastError());
-        w.ctr.kernel_launches++;
-        CUDA_TRY(w.err, cudaMemcpyAsync(B + back_stats + (o_totals - o_stats), D + o_totals, 48, cudaMemcpyDeviceToHost, st));
-        w.ctr.d2h_bytes += bytes_init + 48;
-    } else {
-        CUDA_TRY(w.err, cudaMemcpyAsync(B + back_stats, D + o_stats, o_totals + 48 - o_stats, cudaMemcpyDeviceToHost, st));
-        w.ctr.d2h_bytes += back_bytes;
-    }
+    // ---- which walks count and which verify their root; statistics per member ----
+    DecideCtx Dc{};
+    Dc.walks = C.walks; Dc.node = C.node; Dc.reads = reinterpret_cast<const ReadRec*>(D + o_reads); Dc.n_reads = n_reads;
+    Dc.ref_len = C.ref_len; Dc.n_inner = C.n_inner; Dc.sum_inner = C.sum_inner; Dc.cells_inner = C.cells_inner;
+    Dc.root_flag = D + o_rootflag; Dc.root_count = reinterpret_cast<uint32_t*>(D + o_rootcnt);
+    Dc.inserted = reinterpret_cast<uint32_t*>(D + o_inserted);
+    Dc.member_totals = reinterpret_cast<unsigned long long*>(D + o_member_totals);
+    Dc.ivopt = ivopt ? 1u : 0u;
+    uint32_t* const d_rootoff = reinterpret_cast<uint32_t*>(D + o_rootoff);
+    uint32_t* const d_nroots = reinterpret_cast<uint32_t*>(D + o_back + 24);
+    uint32_t const pair_grid = (2 * n_reads * 32 + 127) / 128;
+    decide_kernel<<<pair_grid, 128, 0, st>>>(Dc);
+    scan_counts_kernel<<<1, 1024, 0, st>>>(Dc.root_count, d_rootoff, 2 * n_reads, d_nroots);
+    CUDA_TRY(w.err, cudaGetLastError());
+    w.ctr.kernel_launches += 2;
+    size_t const back_bytes = 64 + n_members * kMemberTotals * 8;
+    CUDA_TRY(w.err, w.h_lv_back.ensure(back_bytes));
+    CUDA_TRY(w.err, cudaMemcpyAsync(w.h_lv_back.p, D + o_back, back_bytes, cudaMemcpyDeviceToHost, st));
     g_prof.lap(w, 6);
     CUDA_TRY(w.err, w.wait_for(st));
     float ms = 0;
     CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
     w.ctr.dp_kernel_ms += ms;
-    g_prof.lap(w, 8);
-    const uint32_t* const end_node = reinterpret_cast<const uint32_t*>(B);
-    const uint8_t* const S = B + back_stats;
-    const uint32_t* const n_inner = reinterpret_cast<const uint32_t*>(S);
-    const uint64_t* const sum_inner = reinterpret_cast<const uint64_t*>(S + (o_sum - o_stats));
-    const uint64_t* const cells_inner = reinterpret_cast<const uint64_t*>(S + (o_cells - o_stats));
-    const uint64_t* const totals = reinterpret_cast<const uint64_t*>(S + (o_totals - o_stats));
+    w.ctr.d2h_bytes += back_bytes;
+    const uint64_t* const totals = w.h_lv_back.as<uint64_t>();
     w.ctr.dp_tasks += totals[0]; w.ctr.dp_word_steps += totals[1]; w.ctr.inferred_inner += totals[2];
-    if (!compact) {
-        for (size_t d = 1; d < n_levels; ++d) {
-            for (uint32_t wi : level[d]) {
-                Walk& wk = walks[wi];
-                wk.n_inner = n_inner[wi]; wk.sum_inner = sum_inner[wi]; wk.cells_inner = cells_inner[wi];
-                if (end_node[wi] == kDeadNode) { wk.state = W_DONE; continue; }
-                fxg_read const& R = J->reads_p[wk.read];
-                if (end_node[wi] != node_base[wk.read - read_lo]) return fail(w.err, FXG_ERR_CUDA, "internal: a walk stopped below its root");
-                wk.node = J->nodes_p + R.node_offset;                           // the root
-                level[0].push_back(wi);
-            }
-            level[d].clear();
-        }
-    } else {
-        // every walk counts (verification.cpp:238-242); only those standing at their root go on
-        out.stats.n_aligned_inner += totals[3]; out.stats.sum_aligned_inner += totals[4]; out.stats.cells_inner += totals[5];
-        walks.clear();
-        level.assign(1, std::vector<uint32_t>());
-        size_t n_alive = 0;
-        for (size_t q = 0; q < n_walks; ++q) n_alive += end_node[q] != kDeadNode;
-        walks.reserve(n_alive); level[0].reserve(n_alive);
-        size_t i = 0;
-        for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
-            fxg_read const& R = J->reads_p[ri];
-            uint32_t const nb = node_base[ri - read_lo];
-            for (uint32_t orient = 0; orient < 2; ++orient) {
-                uint32_t const a0 = uint32_t(R.anchor_offset) + (orient ? R.num_anchors_forward : 0);
-                uint32_t const na = orient ? R.num_anchors_reverse : R.num_anchors_forward;
-                for (uint32_t q = 0; q < na; ++q, ++i) {
-                    uint32_t const e = end_node[i];
-                    if (e == kDeadNode) continue;
-                    if (e != kAtRootNode && e != nb) return fail(w.err, FXG_ERR_CUDA, "internal: a walk stopped below its root");
-                    Walk wk{};
-                    wk.read = ri; wk.anchor = a0 + q; wk.orient = uint8_t(orient); wk.state = W_WALKING;
-                    wk.node = J->nodes_p + R.node_offset;                       // the root (inner[0], or the only leaf)
-                    level[0].push_back(uint32_t(walks.size()));
-                    walks.push_back(wk);
-                }
-            }
-        }
+    uint32_t const n_roots = *reinterpret_cast<const uint32_t*>(w.h_lv_back.as<uint8_t>() + 24);
+    const uint64_t* const mt = reinterpret_cast<const uint64_t*>(w.h_lv_back.as<uint8_t>() + 64);
+    for (size_t mi = 0; mi < n_members; ++mi) {
+        fxg_stats& S = out.stats[mi];
+        S.n_aligned_inner += mt[mi * kMemberTotals + 0]; S.sum_aligned_inner += mt[mi * kMemberTotals + 1]; S.cells_inner += mt[mi * kMemberTotals + 2];
+        S.n_avoided_root += mt[mi * kMemberTotals + 3]; S.sum_avoided_root += mt[mi * kMemberTotals + 4];
+    }
+    g_prof.lap(w, 8);
+    if (n_roots == 0) return FXG_OK;
+    if (n_roots > n_walks) return fail(w.err, FXG_ERR_CUDA, "internal: more root walks than walks");
+    // ---- the walks that verify their root, in anchor order ----
+    CUDA_TRY(w.err, w.d_roots.ensure(size_t(n_roots) * sizeof(RootEntry)));
+    CUDA_TRY(w.err, w.h_roots.ensure(size_t(n_roots) * sizeof(RootEntry)));
+    root_emit_kernel<<<pair_grid, 128, 0, st>>>(Dc, d_rootoff, w.d_roots.as<RootEntry>());
+    CUDA_TRY(w.err, cudaGetLastError());
+    w.ctr.kernel_launches++;
+    CUDA_TRY(w.err, cudaMemcpyAsync(w.h_roots.p, w.d_roots.p, size_t(n_roots) * sizeof(RootEntry), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(w.err, w.wait_for(st));
+    w.ctr.d2h_bytes += size_t(n_roots) * sizeof(RootEntry);
+    const RootEntry* const re = w.h_roots.as<RootEntry>();
+    P.walks.resize(n_roots);
+    level[0].resize(n_roots);
+    uint32_t cur = 0;                                          // read of the entry at hand (entries come in walk order)
+    for (uint32_t q = 0; q < n_roots; ++q) {
+        RootEntry const& e = re[q];
+        while (cur + 1 < n_reads && P.part_reads[cur + 1].walk_begin <= e.walk) ++cur;
+        ReadRec const& R = P.part_reads[cur];
+        if (e.walk < R.walk_begin || e.walk >= R.walk_begin + R.n_walks || e.ref_id >= c->refs.len.size())
+            return fail(w.err, FXG_ERR_CUDA, "internal: a root walk outside its read");
+        Walk& wk = P.walks[q];
+        wk = Walk{};
+        wk.read = r0 + cur; wk.anchor = e.walk - R.walk_begin; wk.orient = e.walk - R.walk_begin >= R.n_forward ? 1 : 0;
+        wk.state = W_WALKING; wk.ref_id = e.ref_id; wk.member = R.member;
+        wk.root_span = root_span_of(R, e.diag, c->refs.len[e.ref_id]); wk.have_root_span = true;
+        wk.rm = R.root_m; wk.rk = R.root_k; wk.rqbase = (wk.orient ? R.qoff_reverse : R.qoff_forward) + R.root_from;
+        level[0][q] = q;
     }
     g_prof.lap(w, 9);
     return FXG_OK;
@@ -1673,40 +1742,32 @@ int run_levels_on_device(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, ui
 //    other walk counts, and inserts its window if it reached the root.
 // 3. Root level: one wave for the walks that count and reached the root (with checkpoints + tracebacks when CIGARs
 //    are wanted).
-void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint32_t read_hi, PartState& P, StageGate* gate) {
+void verify_part_score(fxg_ctx* c, Worker& w, Batch& B, uint32_t read_lo, uint32_t read_hi, PartState& P) {
     cudaSetDevice(c->device);
     P.t0 = std::chrono::steady_clock::now();
     if (g_prof.on) P.cpu0 = thread_cpu_ms();
     PartOut& out = P.out;
+    out.stats.assign(B.members.size(), fxg_stats{});
     g_prof.start(w);
-    bool const ivopt = J->cfg.interval_optimization != 0;
+    fxg_job* const J = B.members[0].J;                   // (host-driven levels: the batch is this one job)
+    Pool const& pool = *B.pool;
+    bool const ivopt = B.cfg.interval_optimization != 0;
     std::vector<Walk>& walks = P.walks; std::vector<Group>& groups = P.groups; std::vector<uint32_t>& group_members = P.group_members;
     std::vector<std::vector<uint32_t>> level;            // walks waiting for the wave of their node's level (0 = root)
     std::vector<uint32_t> active;
     std::vector<Pass> passes; std::vector<uint32_t> pass_walk;
     w.cig_used = 0;
 
-    auto pass_through_gate = [&]() -> bool {
-        if (!gate) return true;
-        // the query pools and their Peq planes are being uploaded by the caller's thread: order this worker's stream behind them
-        if (gate->wait() != FXG_OK) { out.rc = gate->rc; w.err = gate->err; return false; }
-        if (cudaStreamWaitEvent(w.stream, w.group->ev_staged, 0) != cudaSuccess) { out.rc = fail(w.err, FXG_ERR_CUDA, "cannot order the worker behind the upload"); return false; }
-        gate = nullptr;
-        return true;
-    };
-
-    // Without the interval optimisation no walk needs to know another's root window and every walk counts: the inner levels
-    // run on the device straight from the anchors, and only the walks that reach their root get a Walk object.
-    bool levels_done = false;
-    if (c->device_levels && !ivopt && J->cfg.verification_kind == FXG_KIND_HIERARCHICAL) {
+    // The walks climb their trees on the device (run_device_walks): what comes back are the walks that verify their root.
+    // A job without device records (limits of prepare_job, or FXG_DEVICE_LEVELS=0) is driven from the host, level by level.
+    bool const on_device = B.device;
+    if (on_device) {
         walks.clear(); groups.clear(); group_members.clear();
-        int gate_rc = FXG_OK;
-        int const rc = run_levels_on_device(c, w, J, read_lo, read_hi, walks, level, true, out, pass_through_gate, gate_rc);
-        if (gate_rc != FXG_OK) return;                                   // out.rc / w.err set by the gate
-        if (rc == FXG_OK) levels_done = true;
-        else if (rc != kNotOnDevice) { out.rc = rc; return; }
-    }
-    if (!levels_done) {
+        out.rc = run_device_walks(c, w, B, read_lo, read_hi, P, level);
+        if (out.rc != FXG_OK) return;
+    } else {
+        // (fxg_verify_reads) the query pools and their Peq planes were enqueued on the staging stream by the caller's thread
+        if (J->pool_ready && cudaStreamWaitEvent(w.stream, J->pool_ready, 0) != cudaSuccess) { out.rc = fail(w.err, FXG_ERR_CUDA, "cannot order the worker behind the upload"); return; }
         build_walks(c, J, read_lo, read_hi, walks, groups, group_members);
         // ---- tree level of every walk's first node ----
         size_t const n_all = walks.size();
@@ -1757,26 +1818,19 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     };
     // (node, strand) -> the ask that goes first, in a table over the node indices this part's reads use
     uint64_t node_lo = UINT64_MAX, node_hi = 0;
-    for (uint32_t ri = read_lo; ri < read_hi; ++ri) {
+    for (uint32_t ri = read_lo; ri < read_hi && !on_device; ++ri) {
         fxg_read const& R = J->reads_p[ri];
         node_lo = std::min<uint64_t>(node_lo, R.node_offset); node_hi = std::max<uint64_t>(node_hi, R.node_offset + R.num_inner + R.num_leaves);
     }
-    bool const infer = c->infer_inner && node_hi > node_lo && (node_hi - node_lo) < (uint64_t(1) << 26);
+    bool const infer = !on_device && c->infer_inner && node_hi > node_lo && (node_hi - node_lo) < (uint64_t(1) << 26);
     std::vector<uint32_t> rep_of, rep_stamp;
     if (infer) { rep_of.assign(size_t(node_hi - node_lo) * 2, 0); rep_stamp.assign(size_t(node_hi - node_lo) * 2, 0); }
     uint32_t stamp = 0;
     std::vector<Ask> asks;
-    if (!levels_done && c->device_levels && level.size() > 1) {
-        int gate_rc = FXG_OK;
-        int const rc = run_levels_on_device(c, w, J, read_lo, read_hi, walks, level, false, out, pass_through_gate, gate_rc);
-        if (gate_rc != FXG_OK) return;                                   // out.rc / w.err set by the gate
-        if (rc == FXG_OK) levels_done = true;
-        else if (rc != kNotOnDevice) { out.rc = rc; return; }
-    }
     std::vector<uint32_t> first, second;                                // asks computed in the first / second launch
     std::vector<int8_t> verdict;                                         // per ask: -1 undecided, 0 no alignment, 1 alignment exists
     std::vector<uint64_t> rep_end;                                       // per ask computed first: reference position where the alignment found ends
-    for (int cur_level = int(level.size()) - 1; cur_level >= 1 && !levels_done; --cur_level) {
+    for (int cur_level = int(level.size()) - 1; cur_level >= 1; --cur_level) {
         g_prof.start(w);
         active.swap(level[size_t(cur_level)]);
         level[size_t(cur_level)].clear();
@@ -1810,9 +1864,8 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
         g_prof.lap(w, 2);
         if (g_prof.on && w.id == 0 && std::getenv("FXG_TRACE_WAVES"))
             fprintf(stderr, "[fxg] level %d: %zu walks, %zu computed first\n", cur_level, active.size(), passes.size());
-        if (!pass_through_gate()) return;
         const DpResult* res = nullptr;
-        out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
+        out.rc = run_passes(c, w, pool, passes, nullptr, nullptr, &res);
         if (out.rc != FXG_OK) return;
         w.ctr.waves++;
         g_prof.start(w);
@@ -1841,7 +1894,7 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
                     cur_level, yes, first.size(), second.size(), same_no);
         }
         if (!passes.empty()) {
-            out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
+            out.rc = run_passes(c, w, pool, passes, nullptr, nullptr, &res);
             if (out.rc != FXG_OK) return;
             for (size_t f = 0; f < second.size(); ++f) verdict[second[f]] = res[f].score <= int32_t(asks[second[f]].k) ? 1 : 0;
         }
@@ -1862,10 +1915,13 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     // ---------------- 2. which walks count, and which of them verify their root ----------------
     g_prof.start(w);
     std::vector<uint32_t> roots;                         // walks standing at the root that count, in walk order
-    if (!ivopt) {
+    fxg_stats& st0 = out.stats[0];
+    if (on_device) {
+        roots.swap(level[0]);                            // decided on the device (decide_kernel), statistics included
+    } else if (!ivopt) {
         roots.swap(level[0]);
         std::sort(roots.begin(), roots.end());
-        for (Walk const& wk : walks) { out.stats.n_aligned_inner += wk.n_inner; out.stats.sum_aligned_inner += wk.sum_inner; out.stats.cells_inner += wk.cells_inner; }
+        for (Walk const& wk : walks) { st0.n_aligned_inner += wk.n_inner; st0.sum_aligned_inner += wk.sum_inner; st0.cells_inner += wk.cells_inner; }
     } else {
         std::vector<uint8_t> at_root(n_walks, 0);
         for (uint32_t wi : level[0]) at_root[wi] = 1;
@@ -1881,15 +1937,25 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
                 for (uint32_t ins : inserted)
                     if (walks[ins].r_start <= wk.t_start && walks[ins].r_end >= wk.t_end) { avoided = true; break; }
                 if (avoided) {                               // root_was_already_verified, verification.cpp:119-136
-                    out.stats.n_avoided_root++; out.stats.sum_avoided_root += wk.root_span.length;
+                    st0.n_avoided_root++; st0.sum_avoided_root += wk.root_span.length;
                     wk.state = W_DONE;
                     continue;
                 }
-                out.stats.n_aligned_inner += wk.n_inner; out.stats.sum_aligned_inner += wk.sum_inner; out.stats.cells_inner += wk.cells_inner;
+                st0.n_aligned_inner += wk.n_inner; st0.sum_aligned_inner += wk.sum_inner; st0.cells_inner += wk.cells_inner;
                 if (at_root[wi]) { inserted.push_back(wi); roots.push_back(wi); }      // verified_intervals.insert, verification.cpp:106-109 / :40-41
             }
         }
         std::sort(roots.begin(), roots.end());
+    }
+    if (!on_device) {
+        // what the root level needs of a walk (the device-side walks come with it)
+        for (uint32_t wi : roots) {
+            Walk& wk = walks[wi];
+            (void)span_of(wk, true);
+            wk.ref_id = uint32_t(J->anchors_p[wk.anchor].reference_id); wk.member = 0;
+            wk.rm = uint32_t(wk.node->query_index_to - wk.node->query_index_from + 1); wk.rk = uint32_t(wk.node->num_errors);
+            wk.rqbase = (wk.orient ? J->pool_len : 0) + J->reads_p[wk.read].query_offset + wk.node->query_index_from;
+        }
     }
     g_prof.lap(w, 1);
 
@@ -1898,29 +1964,25 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
     passes.clear(); pass_walk.clear();
     std::vector<uint32_t> root_k;
     passes.reserve(roots.size()); pass_walk.reserve(roots.size()); root_k.reserve(roots.size());
-    bool const want_cigar = !J->cfg.without_cigar;
+    bool const want_cigar = !B.cfg.without_cigar;
     for (uint32_t wi : roots) {
         Walk& wk = walks[wi];
-        fxg_anchor const& A = J->anchors_p[wk.anchor];
-        Span const sp = span_of(wk, true);
-        uint32_t const m = uint32_t(wk.node->query_index_to - wk.node->query_index_from + 1);
-        uint64_t const qbase = (wk.orient ? J->pool_len : 0) + J->reads_p[wk.read].query_offset + wk.node->query_index_from;
-        out.stats.n_aligned_root++; out.stats.sum_aligned_root += sp.length; out.stats.cells_root += uint64_t(m) * sp.length;
+        Span const& sp = wk.root_span;
+        fxg_stats& S = out.stats[wk.member];
+        S.n_aligned_root++; S.sum_aligned_root += sp.length; S.cells_root += uint64_t(wk.rm) * sp.length;
         Pass p;
-        if (score_pass_for(c->refs.base[A.reference_id] + sp.offset, qbase, uint32_t(sp.length), m, uint32_t(wk.node->num_errors),
-                           want_cigar ? 0u : kFlagReverse, p)) {
-            passes.push_back(p); pass_walk.push_back(wi); root_k.push_back(uint32_t(wk.node->num_errors));
+        if (score_pass_for(c->refs.base[wk.ref_id] + sp.offset, wk.rqbase, uint32_t(sp.length), wk.rm, wk.rk, want_cigar ? 0u : kFlagReverse, p)) {
+            passes.push_back(p); pass_walk.push_back(wi); root_k.push_back(wk.rk);
         }
         wk.state = W_DONE;
     }
     g_prof.lap(w, 2);
     if (g_prof.on && w.id == 0 && std::getenv("FXG_TRACE_WAVES")) fprintf(stderr, "[fxg] root level: %zu walks, %zu passes\n", roots.size(), passes.size());
     if (!passes.empty()) {
-        if (!pass_through_gate()) return;
         if (want_cigar) {
             // score pass with checkpoints, then the traceback of the accepted ones
             std::vector<RootOut> root_outs;
-            out.rc = run_root_passes(c, w, J->pool, passes, root_k, P.trace_budget, root_outs);
+            out.rc = run_root_passes(c, w, pool, passes, root_k, P.trace_budget, root_outs);
             if (out.rc != FXG_OK) return;
             for (size_t q = 0; q < passes.size(); ++q) {
                 if (root_outs[q].score > int32_t(root_k[q])) continue;
@@ -1931,7 +1993,7 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
             }
         } else {
             const DpResult* res = nullptr;
-            out.rc = run_passes(c, w, J->pool, passes, nullptr, nullptr, &res);
+            out.rc = run_passes(c, w, pool, passes, nullptr, nullptr, &res);
             if (out.rc != FXG_OK) return;
             for (size_t q = 0; q < passes.size(); ++q) {
                 if (res[q].score > int32_t(root_k[q])) continue;
@@ -1945,7 +2007,7 @@ void verify_part_score(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t read_lo, uint
 }
 
 // the part's cigars go straight from the device into its region of the job's pool; then the part's alignments
-void verify_part_finish(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t* host_cigars, uint64_t region_base, PartState& P) {
+void verify_part_finish(fxg_ctx* c, Worker& w, uint32_t* host_cigars, uint64_t region_base, PartState& P) {
     (void)c;
     PartOut& out = P.out;
     g_prof.start(w);
@@ -1959,7 +2021,7 @@ void verify_part_finish(fxg_ctx* c, Worker& w, fxg_job* J, uint32_t* host_cigars
         if (!wk.hit) continue;
         fxg_alignment a{};
         a.start_in_reference = wk.start_in_reference; a.cigar_offset = wk.cigar_offset; a.cigar_len = wk.cigar_len;
-        a.num_errors = wk.num_errors; a.read_index = wk.read; a.reference_id = uint32_t(J->anchors_p[wk.anchor].reference_id);
+        a.num_errors = wk.num_errors; a.read_index = wk.read; a.reference_id = wk.ref_id;
         a.orientation = wk.orient;
         out.alignments.push_back(a);
     }
@@ -2036,7 +2098,9 @@ int fxg_create(int device, fxg_ctx** out) {
     c->share_root_passes = env_int("FXG_SHARE_ROOTS", 1, 0, 1) != 0;
     c->device_levels = env_int("FXG_DEVICE_LEVELS", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
-    c->n_groups = env_int("FXG_GROUPS", 32, 1, fxg_ctx::kMaxGroups);
+    c->n_groups = env_int("FXG_GROUPS", 4, 1, fxg_ctx::kMaxGroups);
+    c->merge_max_jobs = env_int("FXG_MERGE_JOBS", 64, 1, 4096);
+    c->merge_max_walks = uint64_t(env_int("FXG_MERGE_WALKS", 6 << 20, 1, int(kMaxDeviceWalks - 1)));
     c->workers_busy = default_workers(c->n_groups);
     // a batch that runs alone is split over 8 workers; the lowest free group is taken, so that is always group 0 and only
     // it owns that many.  An explicit FXG_WORKERS is taken literally.
@@ -2044,7 +2108,7 @@ int fxg_create(int device, fxg_ctx** out) {
     for (int gi = 0; gi < c->n_groups; ++gi) {
         WorkerGroup& g = c->groups[gi];
         ok = ok && cudaEventCreate(&g.ev_run0) == cudaSuccess && cudaEventCreate(&g.ev_run1) == cudaSuccess &&
-             cudaEventCreateWithFlags(&g.ev_staged, cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&g.ev_merged, cudaEventDisableTiming) == cudaSuccess;
         int const nw = gi == 0 ? nw_wide : c->workers_busy;
         for (int i = 0; ok && i < nw; ++i) {
             std::unique_ptr<Worker> w(new (std::nothrow) Worker());
@@ -2079,17 +2143,20 @@ void fxg_destroy(fxg_ctx* c) {
     c->d_tmp.release();
     for (Pool& p : c->spare_pools) p.release();
     for (PinnedBuf& b : c->spare_pinned) b.release();
+    for (DevBuf& b : c->spare_dev) b.release();
+    c->refs.d_base.release(); c->refs.d_len.release();
     for (WorkerGroup& g : c->groups) {
         for (auto& w : g.workers) w->release();
         if (g.ev_run0) cudaEventDestroy(g.ev_run0);
         if (g.ev_run1) cudaEventDestroy(g.ev_run1);
-        if (g.ev_staged) cudaEventDestroy(g.ev_staged);
+        if (g.ev_merged) cudaEventDestroy(g.ev_merged);
+        g.merged.release();
     }
     if (c->stage_stream) cudaStreamDestroy(c->stage_stream);
     delete c;
 }
 
-const char* fxg_last_error(const fxg_ctx* c) { return c ? c->err.c_str() : "no context"; }
+const char* fxg_last_error(const fxg_ctx* c) { return c ? tls_last_error.c_str() : "no context"; }
 
 int fxg_get_counters(const fxg_ctx* c, fxg_counters* out) { if (!c || !out) return FXG_ERR_INVALID_ARGUMENT; *out = c->ctr; return FXG_OK; }
 int fxg_reset_counters(fxg_ctx* c) { if (!c) return FXG_ERR_INVALID_ARGUMENT; c->ctr = fxg_counters{}; return FXG_OK; }
@@ -2098,34 +2165,47 @@ int fxg_set_references(fxg_ctx* c, size_t n_refs, const uint8_t* const* ranks, c
     if (!c || (n_refs && (!ranks || !lens))) return FXG_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(c->mu);
     CUDA_TRY(c->err, cudaSetDevice(c->device));
-    RefStore& R = c->refs;
-    R.base.assign(n_refs, 0); R.len.assign(lens, lens + n_refs);
+    // the store is read by every kernel of every run: it is replaced only while nothing runs or waits
+    for (int i = 0; i < c->n_groups; ++i)
+        if (c->groups[i].busy) return fail(c->err, FXG_ERR_STATE, "fxg_set_references while a run is in flight");
+    if (!c->pending.empty()) return fail(c->err, FXG_ERR_STATE, "fxg_set_references while a run is in flight");
+    // everything new is built beside the old store and takes its place only when every upload has succeeded
+    std::vector<uint64_t> base(n_refs, 0), len(lens, lens + n_refs);
     uint64_t total = 0;
     for (size_t i = 0; i < n_refs; ++i) {
         int rc = check_ranks(c->err, ranks[i], lens[i], "reference");
         if (rc != FXG_OK) return rc;
-        R.base[i] = total;
+        base[i] = total;
         total += (lens[i] + 31) / 32 * 32;
     }
-    R.total = total;
-    CUDA_TRY(c->err, R.packed.ensure(total / 2 + 64));
-    CUDA_TRY(c->err, cudaMemsetAsync(R.packed.p, 0, total / 2 + 64, c->stage_stream));
-    for (size_t i = 0; i < n_refs; ++i) {
-        uint64_t const slice = uint64_t(256) << 20;            // upload in slices so that the temporary stays small
-        for (uint64_t at = 0; at < lens[i]; at += slice) {
-            uint64_t const n = std::min<uint64_t>(slice, lens[i] - at);
-            int rc = upload_packed(c, ranks[i] + at, n, R.packed, (R.base[i] + at) / 8);
-            if (rc != FXG_OK) return rc;
+    DevBuf packed, d_base, d_len;
+    auto build = [&]() -> int {
+        CUDA_TRY(c->err, packed.ensure(total / 2 + 64));
+        CUDA_TRY(c->err, cudaMemsetAsync(packed.p, 0, total / 2 + 64, c->stage_stream));
+        for (size_t i = 0; i < n_refs; ++i) {
+            uint64_t const slice = uint64_t(256) << 20;        // upload in slices so that the temporary stays small
+            for (uint64_t at = 0; at < lens[i]; at += slice) {
+                uint64_t const n = std::min<uint64_t>(slice, lens[i] - at);
+                int rc = upload_packed(c, ranks[i] + at, n, packed, (base[i] + at) / 8);
+                if (rc != FXG_OK) return rc;
+            }
         }
-    }
-    if (n_refs) {
-        CUDA_TRY(c->err, R.d_base.ensure(n_refs * 8));
-        CUDA_TRY(c->err, R.d_len.ensure(n_refs * 8));
-        CUDA_TRY(c->err, cudaMemcpyAsync(R.d_base.p, R.base.data(), n_refs * 8, cudaMemcpyHostToDevice, c->stage_stream));
-        CUDA_TRY(c->err, cudaMemcpyAsync(R.d_len.p, R.len.data(), n_refs * 8, cudaMemcpyHostToDevice, c->stage_stream));
+        CUDA_TRY(c->err, d_base.ensure(std::max<size_t>(n_refs, 1) * 8));
+        CUDA_TRY(c->err, d_len.ensure(std::max<size_t>(n_refs, 1) * 8));
+        if (n_refs) {
+            CUDA_TRY(c->err, cudaMemcpyAsync(d_base.p, base.data(), n_refs * 8, cudaMemcpyHostToDevice, c->stage_stream));
+            CUDA_TRY(c->err, cudaMemcpyAsync(d_len.p, len.data(), n_refs * 8, cudaMemcpyHostToDevice, c->stage_stream));
+        }
         CUDA_TRY(c->err, cudaStreamSynchronize(c->stage_stream));
-    }
+        return FXG_OK;
+    };
+    int const rc = build();
     c->d_tmp.release();
+    if (rc != FXG_OK) { packed.release(); d_base.release(); d_len.release(); return rc; }      // the old store stays as it was
+    RefStore& R = c->refs;
+    R.packed.release(); R.d_base.release(); R.d_len.release();
+    R.packed = packed; R.d_base = d_base; R.d_len = d_len;
+    R.base.swap(base); R.len.swap(len); R.total = total;
     c->have_refs = true;
     refresh_trace_budget(c);
     return FXG_OK;
@@ -2246,7 +2326,7 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
         }
     }
     add_counters(c->ctr, w.ctr);
-    if (rc != FXG_OK) { c->err = w.err; return rc; }
+    if (rc != FXG_OK) { c->err = w.err; tls_last_error = w.err; return rc; }
     b->ran = true;
     return FXG_OK;
 }
@@ -2295,27 +2375,26 @@ void index_walks(fxg_job* j) {
     j->read_walk_begin[j->n_reads] = n_walks_total;
 }
 
-// The body of fxg_verify_run on one worker group, without the context lock (errors and accounting go to the caller's
-// objects).  With a gate the parts validate their own reads first and wait at the gate
-// before their first launch (fxg_verify_reads: the upload runs beside their host-side preparation).
-int verify_run_group(fxg_ctx* c, WorkerGroup& grp, fxg_job* J, StageGate* gate, size_t pool_len, std::string& err, fxg_counters& ctr) {
-    J->alignments.clear(); J->cigars_len = 0; J->stats = fxg_stats{};
-    size_t const n_reads = J->n_reads;
-    if (n_reads == 0) { J->ran = true; return FXG_OK; }
+// One batch on one worker group, without the context lock (errors and accounting go to the caller's objects).
+int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_counters& ctr) {
+    B.alignments.clear(); B.cigars_len = 0; B.stats.assign(B.members.size(), fxg_stats{});
+    size_t const n_reads = B.n_reads;
+    if (n_reads == 0) return FXG_OK;
 
     // ---- split the reads into contiguous parts with similar numbers of anchors, one part per worker ----
-    size_t const n_parts = std::min<size_t>(grp.use_workers, std::max<size_t>(1, std::min<size_t>(n_reads, size_t(J->read_walk_begin[n_reads]) / 256 + 1)));
+    std::vector<uint32_t> const& rwb = B.read_walk_begin;
+    size_t const n_parts = std::min<size_t>(grp.use_workers, std::max<size_t>(1, std::min<size_t>(n_reads, size_t(rwb[n_reads]) / 4096 + 1)));
     std::vector<uint32_t> cut(n_parts + 1, 0);
     for (size_t p = 1; p < n_parts; ++p) {
-        uint64_t const target = uint64_t(J->read_walk_begin[n_reads]) * p / n_parts;
-        auto it = std::lower_bound(J->read_walk_begin.begin(), J->read_walk_begin.begin() + n_reads, uint32_t(target));
-        cut[p] = std::max(cut[p - 1], uint32_t(it - J->read_walk_begin.begin()));
+        uint64_t const target = uint64_t(rwb[n_reads]) * p / n_parts;
+        auto it = std::lower_bound(rwb.begin(), rwb.begin() + long(n_reads), uint32_t(target));
+        cut[p] = std::max(cut[p - 1], uint32_t(it - rwb.begin()));
     }
     cut[n_parts] = uint32_t(n_reads);
     std::vector<PartState> parts(n_parts);
     TracePlan plan;
     plan.n_parts = n_parts; plan.caps.assign(n_parts, 0); plan.bases.assign(n_parts, 0);
-    plan.pool = &J->cigars; plan.pool_len = &J->cigars_len;
+    plan.pool = B.cigars; plan.pool_len = &B.cigars_len;
     auto const vt0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - vt0).count(); };
     uint64_t const budget = trace_budget_bytes(c, n_parts);
@@ -2324,14 +2403,13 @@ int verify_run_group(fxg_ctx* c, WorkerGroup& grp, fxg_job* J, StageGate* gate, 
         Worker& w = *grp.workers[p];
         PartState& P = parts[p];
         P.trace_budget = budget;
-        if (gate) P.out.rc = validate_reads(c, w.err, J->reads_p, cut[p], cut[p + 1], pool_len, J->nodes_p, J->n_nodes, J->anchors_p, J->n_anchors);
-        if (P.out.rc == FXG_OK) verify_part_score(c, w, J, cut[p], cut[p + 1], P, gate);
+        verify_part_score(c, w, B, cut[p], cut[p + 1], P);
         g_prof.start(w);
         plan.arrive_and_wait(p, P.out.rc == FXG_OK ? w.cig_used : 0);        // every part arrives, also a failed one
         g_prof.lap(w, 14);
         if (P.out.rc != FXG_OK) return;
         if (plan.failed) { w.err = plan.err; P.out.rc = FXG_ERR_CUDA; return; }
-        verify_part_finish(c, w, J, J->cigars.as<uint32_t>() + plan.bases[p], plan.bases[p], P);
+        verify_part_finish(c, w, B.cigars->as<uint32_t>() + plan.bases[p], plan.bases[p], P);
     };
     {
         RunTimer run_timer(grp, ctr);
@@ -2349,15 +2427,205 @@ int verify_run_group(fxg_ctx* c, WorkerGroup& grp, fxg_job* J, StageGate* gate, 
     {
         size_t n_al = 0;
         for (size_t p = 0; p < n_parts; ++p) n_al += parts[p].out.alignments.size();
-        J->alignments.reserve(n_al);
+        B.alignments.reserve(n_al);
     }
     for (size_t p = 0; p < n_parts; ++p) {
-        J->alignments.insert(J->alignments.end(), parts[p].out.alignments.begin(), parts[p].out.alignments.end());
-        uint64_t* d = reinterpret_cast<uint64_t*>(&J->stats); const uint64_t* sp = reinterpret_cast<const uint64_t*>(&parts[p].out.stats);
-        for (size_t f = 0; f < sizeof(fxg_stats) / sizeof(uint64_t); ++f) d[f] += sp[f];
+        B.alignments.insert(B.alignments.end(), parts[p].out.alignments.begin(), parts[p].out.alignments.end());
+        for (size_t mi = 0; mi < B.members.size(); ++mi) {
+            uint64_t* d = reinterpret_cast<uint64_t*>(&B.stats[mi]); const uint64_t* sp = reinterpret_cast<const uint64_t*>(&parts[p].out.stats[mi]);
+            for (size_t f = 0; f < sizeof(fxg_stats) / sizeof(uint64_t); ++f) d[f] += sp[f];
+        }
+    }
+    ctr.batches++; ctr.batch_jobs += B.members.size();
+    if (g_prof.on) fprintf(stderr, "[fxg] run_batch: %zu jobs, %zu reads, %u walks, %zu parts; parts done %.3f ms, merged %.3f ms\n", B.members.size(), n_reads,
+                           rwb[n_reads], n_parts, t_join, since());
+    return FXG_OK;
+}
+
+// The Peq planes of the members side by side in the group's merged pool: member j's pool positions [0, 2 * pool_len_j)
+// move to [shift_j, ...), shift_j a multiple of 32, so whole words are copied (device to device, six rows per member).
+// Nothing else of a pool is read by the kernels of a verify run.  Words between the members are never looked at: a pass
+// reads up to one block of rows before its piece and one word after it, and masks those bits (dp_task_group: `wild`).
+int build_merged_pool(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err) {
+    uint64_t at = 0;
+    for (Member& M : B.members) { M.pool_shift = at; at += (2 * M.J->pool_len + 31) / 32 * 32; }
+    Pool& P = grp.merged;
+    P.len = at; P.inline_len = 0;
+    P.plane_words = at / 32 + kPeqFrontPadWords + kPeqBackPadWords;
+    CUDA_TRY(err, P.peq.ensure(P.plane_words * kNumSymbols * 4));
+    cudaStream_t const st = grp.workers[0]->stream;
+    (void)c;
+    for (Member const& M : B.members) {
+        fxg_job const* J = M.J;
+        if (J->pool_ready) CUDA_TRY(err, cudaStreamWaitEvent(st, J->pool_ready, 0));
+        uint64_t const words = (2 * J->pool_len + 31) / 32;
+        if (!words) continue;
+        CUDA_TRY(err, cudaMemcpy2DAsync(P.peq.as<uint32_t>() + kPeqFrontPadWords + M.pool_shift / 32, P.plane_words * 4,
+                                        J->pool.peq.as<uint32_t>() + kPeqFrontPadWords, J->pool.plane_words * 4, words * 4, kNumSymbols,
+                                        cudaMemcpyDeviceToDevice, st));
+    }
+    CUDA_TRY(err, cudaEventRecord(grp.ev_merged, st));
+    B.merged_ready = grp.ev_merged;
+    B.pool = &P;
+    return FXG_OK;
+}
+
+// A call of fxg_verify_run / fxg_verify_reads waiting in the context's queue.
+struct TicketResults {                   // what a merged batch leaves for its members
+    std::vector<fxg_alignment> alignments;
+    std::shared_ptr<PinnedBuf> cigars;
+};
+}  // namespace
+namespace {
+struct Ticket {
+    fxg_job* J = nullptr;
+    int state = 0;                       // 0 waiting, 1 taken by a batch, 2 done
+    int rc = FXG_OK; std::string err;
+    std::shared_ptr<TicketResults> shared; size_t al_begin = 0, al_end = 0; uint32_t read0 = 0; fxg_stats stats{};
+};
+
+bool same_config(fxg_verify_config const& a, fxg_verify_config const& b) {
+    return a.extra_verification_ratio == b.extra_verification_ratio && a.verification_kind == b.verification_kind &&
+           a.interval_optimization == b.interval_optimization && a.without_cigar == b.without_cigar;
+}
+
+WorkerGroup* try_acquire_group(fxg_ctx* c) {
+    int busy = 0;
+    for (int i = 0; i < c->n_groups; ++i) busy += c->groups[i].busy;
+    for (int i = 0; i < c->n_groups; ++i) if (!c->groups[i].busy) {
+        WorkerGroup& g = c->groups[i];
+        g.busy = true;
+        g.use_workers = busy == 0 ? g.workers.size() : std::min(g.workers.size(), size_t(c->workers_busy));
+        return &g;
+    }
+    return nullptr;
+}
+
+// runs the jobs of `mine` as one batch (or, should that fail, one by one) and leaves every ticket its results
+void run_tickets(fxg_ctx* c, WorkerGroup& grp, std::vector<Ticket*> const& mine, PinnedBuf& pinned, fxg_counters& ctr) {
+    auto run_some = [&](size_t lo, size_t hi) -> int {
+        Batch B;
+        B.cfg = mine[lo]->J->cfg;
+        B.device = true;
+        uint32_t read0 = 0;
+        B.read_walk_begin.clear();
+        for (size_t i = lo; i < hi; ++i) {
+            fxg_job* J = mine[i]->J;
+            uint32_t const walk0 = B.read_walk_begin.empty() ? 0u : B.read_walk_begin.back();
+            if (!B.read_walk_begin.empty()) B.read_walk_begin.pop_back();
+            for (uint32_t x : J->read_walk_begin) B.read_walk_begin.push_back(walk0 + x);
+            B.members.push_back(Member{J, read0, 0});
+            B.device = B.device && J->prep.ok;
+            read0 += uint32_t(J->n_reads);
+        }
+        B.n_reads = read0;
+        B.cigars = &pinned;
+        std::string err;
+        int rc = FXG_OK;
+        if (hi - lo == 1) { B.pool = &mine[lo]->J->pool; B.pool_len = mine[lo]->J->pool_len; }
+        else rc = build_merged_pool(c, grp, B, err);
+        if (rc == FXG_OK) rc = run_batch(c, grp, B, err, ctr);
+        if (rc != FXG_OK) {
+            cudaDeviceSynchronize();                     // nothing of the failed batch may still be running when its buffers are reused
+            for (size_t i = lo; i < hi; ++i) { mine[i]->rc = rc; mine[i]->err = err; }
+            return rc;
+        }
+        if (hi - lo == 1) {
+            fxg_job* J = mine[lo]->J;
+            J->alignments = std::move(B.alignments);
+            std::swap(J->cigars, pinned);                // (the job's previous pool goes back to the context with `pinned`)
+            J->cigars_len = B.cigars_len; J->stats = B.stats[0];
+            J->shared.reset(); J->shared_cigars = nullptr;
+            mine[lo]->rc = FXG_OK;
+            return FXG_OK;
+        }
+        auto shared = std::make_shared<TicketResults>();
+        shared->alignments = std::move(B.alignments);
+        shared->cigars = std::shared_ptr<PinnedBuf>(new PinnedBuf(pinned), [c](PinnedBuf* b) {
+            { std::lock_guard<std::mutex> lock(c->mu); give_pinned(c, *b); }
+            delete b;
+        });
+        pinned = PinnedBuf{};
+        std::vector<fxg_alignment> const& al = shared->alignments;
+        size_t at = 0;
+        for (size_t i = lo; i < hi; ++i) {
+            Ticket& T = *mine[i];
+            Member const& M = B.members[i - lo];
+            uint32_t const end_read = M.read0 + uint32_t(T.J->n_reads);
+            T.al_begin = at;
+            while (at < al.size() && al[at].read_index < end_read) ++at;
+            T.al_end = at; T.read0 = M.read0; T.stats = B.stats[i - lo]; T.shared = shared; T.rc = FXG_OK;
+        }
+        return FXG_OK;
+    };
+    if (run_some(0, mine.size()) != FXG_OK && mine.size() > 1) {
+        // one bad job must not fail its neighbours: each on its own
+        for (size_t i = 0; i < mine.size(); ++i) {
+            if (!pinned.p) { std::lock_guard<std::mutex> lock(c->mu); pinned = take_pinned(c); }
+            run_some(i, i + 1);
+        }
+    }
+}
+
+// a member of a merged batch takes its share of the results (on its own thread)
+void take_member_results(fxg_job* J, Ticket& T) {
+    std::vector<fxg_alignment> const& al = T.shared->alignments;
+    J->alignments.assign(al.begin() + long(T.al_begin), al.begin() + long(T.al_end));
+    uint64_t lo = UINT64_MAX, hi = 0;
+    for (fxg_alignment const& a : J->alignments) if (a.cigar_len) { lo = std::min(lo, a.cigar_offset); hi = std::max(hi, a.cigar_offset + a.cigar_len); }
+    if (lo == UINT64_MAX) lo = hi = 0;
+    for (fxg_alignment& a : J->alignments) { a.read_index -= T.read0; if (a.cigar_len) a.cigar_offset -= lo; }
+    J->shared = T.shared->cigars;
+    J->shared_cigars = T.shared->cigars->as<uint32_t>() + lo;
+    J->cigars_len = size_t(hi - lo);
+    J->stats = T.stats;
+}
+
+// Queues the job and returns when it has run.  A caller that finds a free worker group leads: it takes its own job and
+// every compatible one that is waiting (same configuration, device records, within the merge limits) and runs them as
+// ONE batch -- their tree levels share launches, and the host-side cost of a batch is paid once.  With as many callers
+// as the application has threads and FXG_GROUPS batches in flight, the waiting jobs pile up into batches by themselves.
+int submit_and_wait(fxg_ctx* c, fxg_job* J, std::unique_lock<std::mutex>& lock) {
+    Ticket T; T.J = J;
+    c->pending.push_back(&T);
+    for (;;) {
+        if (T.state == 2) break;
+        WorkerGroup* g = T.state == 0 ? try_acquire_group(c) : nullptr;
+        if (!g) { c->cv.wait(lock); continue; }
+        std::vector<Ticket*> mine{&T};
+        T.state = 1;
+        c->pending.erase(std::find(c->pending.begin(), c->pending.end(), &T));
+        if (J->prep.ok && c->merge_max_jobs > 1) {
+            uint64_t walks = J->prep.n_walks, nodes = J->prep.n_nodes, reads = J->prep.n_reads;
+            for (auto it = c->pending.begin(); it != c->pending.end() && mine.size() < size_t(c->merge_max_jobs);) {
+                Ticket* t = *it;
+                Prepared const& Q = t->J->prep;
+                if (t->state == 0 && Q.ok && same_config(t->J->cfg, J->cfg) && walks + Q.n_walks <= c->merge_max_walks &&
+                    nodes + Q.n_nodes < (1u << 30) && reads + Q.n_reads < (1u << 30)) {
+                    walks += Q.n_walks; nodes += Q.n_nodes; reads += Q.n_reads;
+                    t->state = 1; mine.push_back(t);
+                    it = c->pending.erase(it);
+                } else ++it;
+            }
+        }
+        PinnedBuf pinned = take_pinned(c);
+        lock.unlock();
+        fxg_counters ctr{};
+        run_tickets(c, *g, mine, pinned, ctr);
+        lock.lock();
+        add_counters(c->ctr, ctr);
+        give_pinned(c, pinned);
+        for (Ticket* t : mine) t->state = 2;
+        g->busy = false;
+        c->cv.notify_all();
+    }
+    if (T.rc != FXG_OK) { c->err = T.err; tls_last_error = T.err; return T.rc; }
+    if (T.shared) {
+        lock.unlock();
+        take_member_results(J, T);
+        lock.lock();
     }
     J->ran = true;
-    if (g_prof.on) fprintf(stderr, "[fxg] verify_run: parts done %.3f ms, merged %.3f ms\n", t_join, since());
     return FXG_OK;
 }
 
@@ -2368,37 +2636,50 @@ int check_verify_call(fxg_ctx* c, const fxg_verify_config* cfg) {
     return FXG_OK;
 }
 
+void release_job_buffers(fxg_ctx* c, fxg_job* j) {        // call with c->mu held
+    give_pool(c, j->pool); give_pinned(c, j->cigars); give_pinned(c, j->prep.staging);
+    if (j->prep.dev.p && c->spare_dev.size() < size_t(2 * fxg_ctx::kMaxGroups + 64)) c->spare_dev.push_back(j->prep.dev); else j->prep.dev.release();
+    j->prep.dev = DevBuf{};
+}
+
 }  // namespace
 
 int fxg_verify_stage(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* reads, size_t n_reads,
                      const uint8_t* fwd, const uint8_t* rc_pool, size_t pool_len,
                      const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors, fxg_job** out) {
     if (!c || !cfg || !out) return FXG_ERR_INVALID_ARGUMENT;
-    std::lock_guard<std::mutex> lock(c->mu);
+    std::unique_lock<std::mutex> lock(c->mu);
     *out = nullptr;
     int rc = check_verify_call(c, cfg);
     if (rc != FXG_OK) return rc;
     CUDA_TRY(c->err, cudaSetDevice(c->device));
-    rc = validate_reads(c, c->err, reads, 0, n_reads, pool_len, nodes, n_nodes, anchors, n_anchors);
-    if (rc == FXG_OK) rc = check_ranks(c->err, fwd, pool_len, "forward pool");
-    if (rc == FXG_OK) rc = check_ranks(c->err, rc_pool, pool_len, "reverse-complement pool");
-    if (rc != FXG_OK) return rc;
     fxg_job* j = new (std::nothrow) fxg_job();
     if (!j) return FXG_ERR_OUT_OF_MEMORY;
-    j->cfg = *cfg;
-    j->reads.assign(reads, reads + n_reads);
-    j->nodes.assign(nodes, nodes + n_nodes);
-    j->anchors.assign(anchors, anchors + n_anchors);
-    j->reads_p = j->reads.data(); j->nodes_p = j->nodes.data(); j->anchors_p = j->anchors.data();
-    j->n_reads = n_reads; j->n_nodes = n_nodes; j->n_anchors = n_anchors;
-    j->pool_len = pool_len;
     j->pool = take_pool(c);
     j->cigars = take_pinned(c);
-    index_walks(j);
-
-    rc = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, c->err, c->ctr);
-    if (rc == FXG_OK && cudaStreamSynchronize(c->stage_stream) != cudaSuccess) rc = fail(c->err, FXG_ERR_CUDA, "staging failed");
-    if (rc != FXG_OK) { give_pool(c, j->pool); give_pinned(c, j->cigars); delete j; return rc; }
+    j->prep.staging = take_pinned(c);
+    if (!c->spare_dev.empty()) { j->prep.dev = c->spare_dev.back(); c->spare_dev.pop_back(); }
+    lock.unlock();                       // the rest touches only the job (and the staging stream, which is ordered)
+    std::string err; fxg_counters ctr{};
+    rc = validate_reads(c, err, reads, 0, n_reads, pool_len, nodes, n_nodes, anchors, n_anchors);
+    if (rc == FXG_OK) rc = check_ranks(err, fwd, pool_len, "forward pool");
+    if (rc == FXG_OK) rc = check_ranks(err, rc_pool, pool_len, "reverse-complement pool");
+    if (rc == FXG_OK) {
+        j->cfg = *cfg;
+        j->reads.assign(reads, reads + n_reads);
+        j->nodes.assign(nodes, nodes + n_nodes);
+        j->anchors.assign(anchors, anchors + n_anchors);
+        j->reads_p = j->reads.data(); j->nodes_p = j->nodes.data(); j->anchors_p = j->anchors.data();
+        j->n_reads = n_reads; j->n_nodes = n_nodes; j->n_anchors = n_anchors;
+        j->pool_len = pool_len;
+        index_walks(j);
+        rc = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, err, ctr);
+    }
+    if (rc == FXG_OK) rc = prepare_job(c, j, err, ctr);
+    if (rc == FXG_OK && cudaStreamSynchronize(c->stage_stream) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "staging failed");
+    lock.lock();
+    add_counters(c->ctr, ctr);
+    if (rc != FXG_OK) { c->err = err; tls_last_error = err; release_job_buffers(c, j); if (j->prep.ready) cudaEventDestroy(j->prep.ready); delete j; return rc; }
     *out = j;
     return FXG_OK;
 }
@@ -2408,32 +2689,28 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
     std::unique_lock<std::mutex> lock(c->mu);
     if (J->borrowed) return fail(c->err, FXG_ERR_STATE, "a job made by fxg_verify_reads cannot be run again (its inputs belonged to the caller)");
     CUDA_TRY(c->err, cudaSetDevice(c->device));
-    WorkerGroup& grp = acquire_group(c, lock);
-    lock.unlock();                                   // two runs (of different jobs) may be in flight, one per worker group
-    std::string err; fxg_counters ctr{};
-    int const rc = verify_run_group(c, grp, J, nullptr, J->pool_len, err, ctr);
-    lock.lock();
-    add_counters(c->ctr, ctr);
-    if (rc != FXG_OK) c->err = err;
-    release_group(c, grp);
-    return rc;
+    return submit_and_wait(c, J, lock);
 }
 
 size_t fxg_job_num_alignments(const fxg_job* j) { return j ? j->alignments.size() : 0; }
 const fxg_alignment* fxg_job_alignments(const fxg_job* j) { return j ? j->alignments.data() : nullptr; }
 size_t fxg_job_cigar_len(const fxg_job* j) { return j ? j->cigars_len : 0; }
-const uint32_t* fxg_job_cigar_pool(const fxg_job* j) { return j ? j->cigars.as<uint32_t>() : nullptr; }
+const uint32_t* fxg_job_cigar_pool(const fxg_job* j) { return j ? (j->shared_cigars ? j->shared_cigars : j->cigars.as<uint32_t>()) : nullptr; }
 const fxg_stats* fxg_job_stats(const fxg_job* j) { return j ? &j->stats : nullptr; }
 
 void fxg_job_free(fxg_ctx* c, fxg_job* j) {
     if (!j) return;
-    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); give_pool(c, j->pool); give_pinned(c, j->cigars); }
-    else j->cigars.release();
+    j->shared.reset();
+    if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); release_job_buffers(c, j); }
+    else { j->cigars.release(); j->prep.staging.release(); }
+    if (j->prep.ready) cudaEventDestroy(j->prep.ready);
+    if (j->pool_ready) cudaEventDestroy(j->pool_ready);
     delete j;
 }
 
-// stage + run in one call.  The caller's arrays are used in place (they only have to live until the call returns), the
-// query pools go up on the caller's thread while the workers validate their reads and prepare their first wave.
+// stage + run in one call.  The caller's arrays are used in place (they only have to live until the call returns): the
+// query pools and the job's records go up on the caller's thread, asynchronously, and the job joins the queue at once --
+// the batch that takes it orders its streams behind those uploads.
 int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* reads, size_t n_reads,
                      const uint8_t* fwd, const uint8_t* rc_pool, size_t pool_len,
                      const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors, fxg_job** out) {
@@ -2452,39 +2729,47 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     j->pool_len = pool_len;
     j->pool = take_pool(c);
     j->cigars = take_pinned(c);
-    index_walks(j);
-    WorkerGroup& grp = acquire_group(c, lock);
-    lock.unlock();                                   // two calls may be in flight, one per worker group
-
-    StageGate gate;
-    fxg_counters stage_ctr{}, ctr{};
-    std::string err;
-    std::thread stager([&] {
-        cudaSetDevice(c->device);
-        std::string serr;
+    j->prep.staging = take_pinned(c);
+    if (!c->spare_dev.empty()) { j->prep.dev = c->spare_dev.back(); c->spare_dev.pop_back(); }
+    lock.unlock();
+    std::string err; fxg_counters ctr{};
+    rc = validate_reads(c, err, reads, 0, n_reads, pool_len, nodes, n_nodes, anchors, n_anchors);
+    if (rc == FXG_OK) {
+        index_walks(j);
         // (ranks above 5 in the query pools are detected by the Peq builder on the device and reported after the run:
         //  such a byte simply matches nothing, so no kernel can be led astray by it in the meantime)
-        int r = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, serr, stage_ctr, true);
-        if (r == FXG_OK && cudaEventRecord(grp.ev_staged, c->stage_stream) != cudaSuccess) r = fail(serr, FXG_ERR_CUDA, "staging failed");
-        gate.open(r, serr);
-    });
-    rc = verify_run_group(c, grp, j, &gate, pool_len, err, ctr);
-    stager.join();
-    if (gate.rc != FXG_OK) { rc = gate.rc; err = gate.err; }
+        rc = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, err, ctr, true);
+    }
+    if (rc == FXG_OK && cudaEventCreateWithFlags(&j->pool_ready, cudaEventDisableTiming) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "cannot create an event");
+    if (rc == FXG_OK && cudaEventRecord(j->pool_ready, c->stage_stream) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "staging failed");
+    if (rc == FXG_OK) rc = prepare_job(c, j, err, ctr);
+    lock.lock();
+    add_counters(c->ctr, ctr);
+    if (rc == FXG_OK) {
+        rc = submit_and_wait(c, j, lock);
+        if (rc != FXG_OK) err = c->err;
+    }
+    lock.unlock();
     if (rc == FXG_OK) {
         uint32_t bad = 0;
         if (cudaMemcpyAsync(&bad, j->pool.bad_rank.p, 4, cudaMemcpyDeviceToHost, c->stage_stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stage_stream) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "staging failed");
         else if (bad) rc = fail(err, FXG_ERR_INVALID_ARGUMENT, "query pools contain a rank above %d (allowed 0..%d)", FXG_MAX_RANK, FXG_MAX_RANK);
+    } else {
+        cudaStreamSynchronize(c->stage_stream);          // nothing may still read the caller's arrays when the call returns
     }
     // the caller's arrays are not looked at after this point
     j->reads_p = nullptr; j->nodes_p = nullptr; j->anchors_p = nullptr;
-    if (rc != FXG_OK) cudaDeviceSynchronize();
+    if (rc != FXG_OK) j->shared.reset();
     lock.lock();
-    add_counters(c->ctr, stage_ctr);
-    add_counters(c->ctr, ctr);
-    release_group(c, grp);
-    if (rc != FXG_OK) { c->err = err; give_pool(c, j->pool); give_pinned(c, j->cigars); delete j; return rc; }
+    if (rc != FXG_OK) {
+        c->err = err; tls_last_error = err;
+        release_job_buffers(c, j);
+        if (j->prep.ready) cudaEventDestroy(j->prep.ready);
+        if (j->pool_ready) cudaEventDestroy(j->pool_ready);
+        delete j;
+        return rc;
+    }
     *out = j;
     return FXG_OK;
 }

@@ -146,6 +146,8 @@ typedef struct {
     uint64_t inferred_inner;         /* inner-node alignments whose existence followed from another walk of the same node */
     uint64_t shared_score_passes;    /* root windows whose result was read off a score pass over the union of several windows */
     uint64_t rescored_roots;         /* root windows scored again on their own because the shared pass could not vouch for them */
+    uint64_t batches;                /* batches the queue ran for fxg_verify_run / fxg_verify_reads calls ... */
+    uint64_t batch_jobs;             /* ... and the jobs in them (several callers' jobs are merged into one batch) */
 } fxg_counters;
 
 /* ---- life cycle ----

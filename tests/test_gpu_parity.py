@@ -492,6 +492,51 @@ def test_two_batches_in_flight(ctx, gpu, oracle):
         s.free()
 
 
+@pytest.mark.parametrize("ivopt", [False, True])
+def test_merged_batches_match_the_oracle(ctx, gpu, oracle, ivopt):
+    """24 callers at once: the queue merges the jobs that wait into batches (floxer_gpu.cu: submit_and_wait) -- different
+    read sets, read lengths and tree shapes in one launch sequence -- and every caller must still get exactly its own
+    alignments, cigars and statistics.  Staged jobs and the one-call path, several rounds each."""
+    import threading
+    refs = [synthetic.random_reference(150_000, 181), synthetic.plant_repeats(synthetic.random_reference(60_000, 182), 183, families=3, unit=(300, 700), copies=(3, 5))]
+    ctx.set_references(refs)
+    cfg = VerifyConfig(interval_optimization=ivopt)
+    shapes = [(6, 900, 0.06, 1), (3, 1500, 0.05, 2), (9, 400, 0.08, 1), (2, 2400, 0.07, 2), (5, 700, 0.04, 1), (1, 3000, 0.06, 2)]
+    batches = [synthetic.make_batch(refs, n, L, e, 300 + i, gpu.pex_build, seed_errors=se, decoy_fraction=0.4) for i, (n, L, e, se) in enumerate(shapes)]
+    want = [oracle_verify_batch(oracle, refs, b, cfg) for b in batches]
+    n_lanes = 24
+    staged = [ctx.stage_verify(batches[i % len(batches)], cfg) for i in range(n_lanes)]
+    errors = []
+    ctx.reset_counters()
+    start = threading.Barrier(n_lanes)
+
+    def lane(i):
+        try:
+            w = want[i % len(batches)]
+            start.wait()
+            for rnd in range(3):
+                al, cg = staged[i].run().alignments()
+                assert alignment_records(al, cg) == w[0] and staged[i].stats() == w[1], ("staged", i, rnd)
+                j = ctx.verify_reads(batches[i % len(batches)], cfg)
+                al, cg = j.alignments()
+                assert alignment_records(al, cg) == w[0] and j.stats() == w[1], ("one call", i, rnd)
+                j.free()
+        except Exception as e:                                      # noqa: BLE001 -- reported by the main thread
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=lane, args=(i,)) for i in range(n_lanes)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    c = ctx.counters()
+    assert c["batch_jobs"] == n_lanes * 3 * 2
+    assert c["batches"] < c["batch_jobs"], "no two jobs ever shared a batch"
+    for s in staged:
+        s.free()
+
+
 def test_verify_reads_rejects_bad_ranks(ctx, gpu):
     """A rank above 5 in a query pool is an error of fxg_verify_reads (found on the device, reported with the call)."""
     refs = [synthetic.random_reference(50_000, 5)]
