@@ -1,14 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- PEX hierarchical verification throughput (BASELINE.json metric) on N B200s of one node.
 
-One "step" = one pass of the hot path over one batch of synthetic reads (config 2 of BASELINE.json:
-10 Mbp random reference, 1 000 simulated 5 kbp reads at 5 % error, floxer defaults) per GPU.  Reads shard
-across ranks with no data-path collective (weak scaling: every rank verifies its own 1 000-read batch).
+Headline workload: config 2 of BASELINE.json (10 Mbp random reference, 1 000 simulated 5 kbp reads at 5 % error, floxer
+defaults) per GPU.  The library serves many callers at once and merges the jobs that wait into batches, so the bench
+drives it the way floxer's thread pool would: `--lanes` host threads (default 32), each verifying the 1 000-read batch
+over and over.  One STEP = one pass of every lane over its batch (lanes x 1 000 reads per GPU); the timed region is
+exactly K steps, i.e. K back-to-back batches per lane.  Reads shard across ranks with no data-path collective (weak
+scaling: every rank runs its own lanes on its own reads).
+
+The one JSON line also carries, under "sub", the other configs of BASELINE.json on this GPU, each with its own
+device-resident value, end-to-end value, CPU baseline and roofline: config 2 with --interval-optimization, config 3
+(100 Mbp repeat-seeded reference, 10 k reads x 15 kbp at 8 %), a sample of one GPU's shard of config 4 (3.1 Gbp in 24
+records, 20 kbp reads at 10 %; reads sharded over 8 GPUs) -- both settings of the interval optimisation each -- and the
+config-5 microbenchmark (batched edit distance, 2^20 tasks per cell).  `--only config2` runs the headline alone.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA path through the C ABI)
-  python bench.py --impl reference [...]                         CPU arm: the multithreaded CPU port of the
-                                                                 reference path (the reference binary cannot be
-                                                                 built offline) on a bounded sample
+  python bench.py --impl reference [...]                         CPU arm: the multithreaded CPU port of the reference path
+                                                                 (the reference binary cannot be built offline)
 
 Prints ONE JSON line on rank 0.
 """
@@ -22,6 +30,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -33,25 +42,21 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 
-WORKLOADS = {
-    # name: (reference length, reads per GPU, read length, error rate, reference seed, read seed)
-    "config2": dict(ref_len=10_000_000, reads=1000, read_len=5000, error=0.05, ref_seed=20240001, read_seed=20240003),
-    "config2_small": dict(ref_len=2_000_000, reads=64, read_len=5000, error=0.05, ref_seed=20240001, read_seed=20240003),
-}
 MYERS_INSTR_PER_WORD_STEP = 11          # minimal LOP3/IADD3/SHF sequence of one 32-cell word-step
+ROUND1_ANCHORS = dict(seed_errors=2, decoy_fraction=0.25)       # the stand-in seeder of round 1 (kept for the headline's continuity)
 
 
-def make_workload(name: str, rank: int, pex_build):
-    from floxer_b200 import synthetic
-    w = WORKLOADS[name]
-    refs = [synthetic.random_reference(w["ref_len"], w["ref_seed"])]
-    batch = synthetic.make_batch(refs, w["reads"], w["read_len"], w["error"], w["read_seed"] + 1000 * rank, pex_build,
-                                 seed_errors=2, decoy_fraction=0.25)
-    return refs, batch
+def describe(name: str, ivopt: bool, n_reads: int, anchors: str) -> str:
+    from floxer_b200 import workloads as W
+    c = W.CONFIGS[name]
+    ref = f"{sum(c['ref_lens'])} bp in {len(c['ref_lens'])} record(s)" + (f", {c['families']} repeat families" if c.get("families") else ", uniform random")
+    return (f"{name}: reference {ref}; {n_reads} simulated reads x {c['read_len']} bp at {int(c['error'] * 100)} % error per GPU; "
+            f"recursive PEX tree, seed errors 2, hierarchical verification, interval optimization {'on' if ivopt else 'off'}, "
+            f"extra verification ratio 0.05, CIGAR output; anchors: {anchors}")
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -59,7 +64,6 @@ class ClockSampler:
         self.index, self.rows, self.proc, self.windows = index, [], None, []
 
     def window(self, t0: float, t1: float):
-        """A timed region (time.perf_counter values): only samples taken inside one count, if any were."""
         self.windows.append((t0, t1))
 
     def start(self):
@@ -82,7 +86,7 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
         inside = [r for t, r in self.rows if any(a <= t <= b + 0.1 for a, b in self.windows)]
-        rows = inside if inside else [r for _, r in self.rows]      # a region shorter than the sampling period: the warm-up's
+        rows = inside if inside else [r for _, r in self.rows]
         sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -91,90 +95,369 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_sample_size(refs, batch, cfg, threads: int, target_s: float = 12.0) -> int:
-    """Sizes the CPU sample to about `target_s` seconds of wall time from a short probe."""
+# ---------------------------------------------------------------------------------------------------- workloads
+
+def build_workload(name: str, rank: int, pex_build, n_reads: int | None, threads: int):
+    """(references, batch, anchors description) of a named config for this rank."""
+    from floxer_b200 import synthetic, workloads as W
+    refs, table = W.build_references(name, threads=threads)
+    if name == "config2":
+        # the headline keeps round 1's read set and anchors (ground-truth anchors + 25 % random decoys per leaf)
+        c = W.CONFIGS[name]
+        batch = synthetic.make_batch(refs, n_reads or c["reads"], c["read_len"], c["error"], c["read_seed"] + 1000 * rank, pex_build, **ROUND1_ANCHORS)
+        return refs, batch, "ground-truth stand-in seeder of round 1 (true loci at the origin position, 25 % random decoys per leaf)"
+    batch = W.build_reads(name, refs, table, pex_build, n_reads=n_reads, rank=rank, procs=threads)
+    return refs, batch, ("stand-in seeder (floxer_b200/workloads.py): true loci with position jitter, hits at the other copies of "
+                         "overlapped repeats, Poisson false positives at the rate of a uniform text of the references' length, "
+                         "hard cap 500 / soft cap 50 per seed")
+
+
+def digest(al, cg, with_cigars: bool) -> int:
+    """Order-sensitive checksum of a job's alignment records (and, if asked, of every cigar's operations)."""
+    fields = np.stack([al["start_in_reference"].astype(np.uint64), al["num_errors"].astype(np.uint64), al["read_index"].astype(np.uint64),
+                       al["reference_id"].astype(np.uint64), al["orientation"].astype(np.uint64), al["cigar_len"].astype(np.uint64)], axis=1)
+    h = zlib.crc32(np.ascontiguousarray(fields).tobytes())
+    if with_cigars and len(al):
+        off = al["cigar_offset"].astype(np.int64)
+        ln = al["cigar_len"].astype(np.int64)
+        # weighted sums of every cigar's operations (shared cigars are read through every alignment that points at them)
+        csum = np.concatenate([np.zeros(1, dtype=np.uint64), np.cumsum((cg.astype(np.uint64) * np.uint64(2654435761)) & np.uint64(0xffffffff), dtype=np.uint64)])
+        per = csum[off + ln] - csum[off]
+        h = zlib.crc32(per.tobytes(), h)
+    return h
+
+
+def cpu_arm(refs, batch, cfg, threads: int, target_s: float):
+    """Times the multithreaded CPU port on a bounded sample (first reads of the batch); returns a cpu_baseline object."""
     from oracle import cpu_baseline
-    probe = batch.slice(0, min(len(batch), max(4, threads // 2)))
+    probe = batch.slice(0, min(len(batch), max(2, threads // 4)))
     t0 = time.perf_counter()
     cpu_baseline.verify_reads(refs, probe, cfg, threads=threads)
     rate = len(probe) / max(time.perf_counter() - t0, 1e-6)
-    return int(max(min(len(batch), rate * target_s), min(len(batch), threads)))
+    n = int(max(min(len(batch), rate * target_s), min(len(batch), threads)))
+    sample = batch.slice(0, n)
+    t0 = time.perf_counter()
+    _, _, stats = cpu_baseline.verify_reads(refs, sample, cfg, threads=threads)
+    dt = time.perf_counter() - t0
+    cells = stats["cells_inner"] + stats["cells_root"]
+    return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port", "reads_per_s": n / dt,
+            "sample": f"first {n} reads of the batch, all anchors, both strands, CIGARs ({dt:.1f} s)"}
 
 
-def cpu_arm(refs, batch, cfg, sample_reads: int, threads: int, repeats: int = 1):
-    """Times the multithreaded CPU port on the first `sample_reads` reads; returns (seconds, stats)."""
-    from oracle import cpu_baseline
-    if not sample_reads:
-        sample_reads = cpu_sample_size(refs, batch, cfg, threads)
-    sample = batch.slice(0, min(sample_reads, len(batch)))
-    best, stats = None, None
-    for _ in range(repeats):
+def run_lanes(step_fns, n_each: int):
+    """Every lane (host thread) runs its step function n_each times; returns (wall seconds, per-lane completion times)."""
+    errors = []
+    done = [[0.0] * n_each for _ in step_fns]
+    t0_box = [0.0]
+    start = threading.Barrier(len(step_fns) + 1)
+
+    def lane(i):
+        try:
+            start.wait()
+            for s in range(n_each):
+                step_fns[i]()
+                done[i][s] = time.perf_counter() - t0_box[0]
+        except Exception as e:                           # noqa: BLE001 -- re-raised by the main thread
+            errors.append(e)
+            try:
+                start.abort()
+            except Exception:                            # noqa: BLE001
+                pass
+    threads = [threading.Thread(target=lane, args=(i,)) for i in range(len(step_fns))]
+    for t in threads:
+        t.start()
+    t0_box[0] = time.perf_counter()
+    start.wait()
+    for t in threads:
+        t.join()
+    dt = time.perf_counter() - t0_box[0]
+    if errors:
+        raise errors[0]
+    return dt, done
+
+
+def step_spread(done, n_each):
+    """Per-step times: step s ends when the last lane has finished its s-th batch."""
+    ends = [max(d[s] for d in done) for s in range(n_each)]
+    per = [ends[0]] + [ends[s] - ends[s - 1] for s in range(1, n_each)]
+    per_ms = sorted(x * 1e3 for x in per)
+    return {"min": round(per_ms[0], 3), "median": round(per_ms[len(per_ms) // 2], 3), "max": round(per_ms[-1], 3)}
+
+
+def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmup: int, int32_peak: float, sampler, pageable: bool,
+            cpu_threads: int, cpu_target_s: float, rank: int):
+    """Device-resident arm, end-to-end arm (page-locked inputs; pageable as well if asked), result check, roofline and CPU
+    baseline of one workload.  Returns (record for rank 0, [ms_total, e2e_ms_total], [cells, reads])."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident arm: one staged copy of the batch per lane, each step = fxg_verify_run ----
+    jobs = [ctx.stage_verify(batch, cfg) for _ in range(lanes)]
+
+    def resident_step(j):
+        def f():
+            flush.fill_(1)                               # 256 MiB written between steps (queued on torch's stream, no host sync)
+            j.run()
+        return f
+    run_lanes([resident_step(j) for j in jobs], max(warmup, 3))
+    # one batch at a time first: its latency, and its device time between the run's first and last operation
+    lat_ms = []
+    for it in range(3):
+        flush.fill_(it & 0xff)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        _, _, stats = cpu_baseline.verify_reads(refs, sample, cfg, threads=threads)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return best, stats, len(sample)
+        jobs[0].run()
+        lat_ms.append((time.perf_counter() - t0) * 1e3)
+    al0, cg0 = jobs[0].alignments()
+    want = digest(al0, cg0, True)
+    want_fields = digest(al0, cg0, False)
+    stats = jobs[0].stats()
+    n_alignments = len(al0)
+    barrier()
+    ctx.reset_counters()
+    t_region = time.perf_counter()
+    total_s, done = run_lanes([resident_step(j) for j in jobs], steps)
+    barrier()
+    sampler.window(t_region, time.perf_counter())
+    ctr = ctx.counters()
+    # every lane's last result is the staged batch's result
+    bad = 0
+    for j in jobs:
+        a, c = j.alignments(copy=False)
+        bad += digest(a, c, True) != want
+    if bad:
+        raise RuntimeError(f"{bad} of {lanes} lanes of the device-resident arm ended with results that differ from a batch run alone")
+    spread = step_spread(done, steps)
+    for j in jobs:
+        j.free()
+
+    # ---- end-to-end arm: host buffers in, alignments + CIGARs out, every step; every job's records are checked ----
+    def e2e_arm(b):
+        mismatches = [0]
+
+        def e2e_step(i):
+            def f():
+                flush.fill_(2)
+                j2 = ctx.verify_reads(b, cfg)            # host buffers in: H2D, all waves, tracebacks, D2H of alignments + CIGARs
+                a2, c2 = j2.alignments(copy=False)       # what a C caller reads: the job's own result arrays
+                if digest(a2, c2, i % 8 == 0) != (want if i % 8 == 0 else want_fields):
+                    mismatches[0] += 1
+                del a2, c2
+                j2.free()
+            return f
+        run_lanes([e2e_step(i) for i in range(lanes)], 2)        # warm-up (page-locked pools are allocated once)
+        barrier()
+        ctx.reset_counters()
+        t_reg = time.perf_counter()
+        s, d = run_lanes([e2e_step(i) for i in range(lanes)], steps)
+        barrier()
+        sampler.window(t_reg, time.perf_counter())
+        if mismatches[0]:
+            raise RuntimeError(f"{mismatches[0]} end-to-end jobs returned records that differ from the staged batch's")
+        return s, ctx.counters(), step_spread(d, steps)
+
+    pinned = [torch.from_numpy(a).pin_memory() for a in (batch.forward_pool, batch.reverse_pool)]
+    from floxer_b200.batch import ReadBatch
+    pinned_batch = ReadBatch(batch.reads, pinned[0].numpy(), pinned[1].numpy(), batch.nodes, batch.anchors, dict(batch.meta))
+    e2e_s, e2e_ctr, e2e_spread = e2e_arm(pinned_batch)
+    pageable_s = None
+    if pageable:
+        pageable_s, _, _ = e2e_arm(batch)                # the caller's buffers as floxer has them: ordinary std::vector memory
+
+    # max over ranks of the times, sum of the units
+    t = torch.tensor([total_s, e2e_s, pageable_s or 0.0], dtype=torch.float64, device="cuda")
+    cells_batch = stats["cells_inner"] + stats["cells_root"]
+    u = torch.tensor([cells_batch * lanes, len(batch) * lanes], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    total_s, e2e_s, pageable_s = [float(x) for x in t.cpu()]
+    cells_step, reads_step = [float(x) for x in u.cpu()]
+    if rank != 0:
+        return None
+    ms_per_step = total_s * 1e3 / steps
+    e2e_ms = e2e_s * 1e3 / steps
+    n_batches = lanes * steps
+    # roofline of the dominant kernel (the bit-vector DP engine, integer-ALU bound, SURVEY 8d) over the TIMED REGION of
+    # the device-resident arm: every word-step the engine's launches issued in it x 11 instructions / the region's time.
+    ws_region = ctr["dp_word_steps"]
+    achieved = ws_region * MYERS_INSTR_PER_WORD_STEP / total_s
+    rec = {
+        "value": cells_step / (ms_per_step * 1e-3) / 1e9, "unit": "GCUPS", "reads_per_s": reads_step / (ms_per_step * 1e-3),
+        "ms_per_step": ms_per_step, "ms_per_batch": ms_per_step / lanes, "step_ms_spread": spread,
+        "lanes": lanes, "reads_per_step_per_gpu": len(batch) * lanes,
+        "e2e": {"value": cells_step / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "reads_per_s": reads_step / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": e2e_ctr["h2d_bytes"] // steps, "d2h_bytes_per_step": e2e_ctr["d2h_bytes"] // steps,
+                "step_ms_spread": e2e_spread, "inputs": "page-locked host memory",
+                "checked": f"every one of the {n_batches} timed jobs: checksum of its alignment records against the staged batch's; every 8th lane its cigars too"},
+        "gpu_launches": int(ctr["kernel_launches"]),
+        "roofline": {
+            "bound": "int32_alu", "achieved": achieved / 1e9, "peak": int32_peak / 1e9, "unit": "Ginstr/s",
+            "frac": achieved / int32_peak if int32_peak else None,
+            "traffic": _captured_traffic(),
+            "kernel": "fxg::dp_kernel<W, CKPT> -- every launch of the engine in the timed region (inner tree levels and root level)",
+            "how": "algorithmic 11 int32 instructions per 32-cell word-step x the word-steps the engine's launches issued inside the timed "
+                   "region of the device-resident arm (band-limited; counted per task from the band geometry, on the device for the inner "
+                   "levels) / the wall time of that region (barrier + synchronize on both sides, so launches that overlap are not counted "
+                   "twice); peak = LOP3/IADD3/SHF 8:1:2 issue-rate microbenchmark on this GPU in this run.  Everything else of a step "
+                   "(tree-level kernels, tracebacks, copies, host scheduling) is inside the denominator.",
+            "word_steps_per_batch": ws_region / n_batches,
+            "cells_computed_per_batch": ws_region * 32 / n_batches, "cells_full_matrix_per_batch": cells_batch,
+            "launch_event_ms_per_batch": {"engine_waves": ctr["dp_kernel_ms"] / n_batches, "tracebacks": ctr["trace_kernel_ms"] / n_batches,
+                                          "root_launch": ctr["root_launch_ms"] / n_batches,
+                                          "note": "CUDA-event times on the launching streams, summed over workers; launches of different batches overlap"},
+            "root_launch_frac": (ctr["root_launch_word_steps"] * MYERS_INSTR_PER_WORD_STEP / (ctr["root_launch_ms"] * 1e-3) / int32_peak)
+            if int32_peak and ctr["root_launch_ms"] > 0 else None,
+            "checkpoint_bytes_per_batch": ctr["trace_bytes"] / n_batches},
+        "queue": {"batches": int(ctr["batches"]), "jobs": int(ctr["batch_jobs"]), "jobs_per_batch": ctr["batch_jobs"] / max(ctr["batches"], 1),
+                  "launches_per_job": ctr["kernel_launches"] / max(ctr["batch_jobs"], 1)},
+        "shortcuts_per_batch": {k: ctr[k] / n_batches for k in ("shared_score_passes", "rescored_roots", "inferred_inner", "shared_tracebacks")},
+        "batch_latency_alone_ms": [round(x, 3) for x in lat_ms],
+        "alignments_per_batch": n_alignments, "stats_per_batch": stats,
+    }
+    if pageable_s:
+        pms = pageable_s * 1e3 / steps
+        rec["e2e_pageable"] = {"value": cells_step / (pms * 1e-3) / 1e9, "unit": "GCUPS", "reads_per_s": reads_step / (pms * 1e-3), "ms_per_step": pms,
+                               "inputs": "ordinary (pageable) host memory, as floxer's std::vector pools"}
+    rec["cpu_baseline"] = cpu_arm(refs, batch, cfg, cpu_threads, cpu_target_s)
+    return rec
+
+
+def _captured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the engine's dominant launch, from the committed
+    `ncu --set full` capture summary of this round (profiles/r02_traffic.json); null when there is none."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
+def microbench(ctx, g, torch, int32_peak: float, cpu_threads: int, tasks_per_cell: int, distinct: int, cells=None):
+    """Config 5: batched edit distance, query 100..2000 bp x window m + 2k + 1, error 2..15 %, modes exists and CIGAR."""
+    from floxer_b200 import abi, synthetic
+    from oracle import cpu_baseline
+    ref = synthetic.random_reference(10_000_000, 20240006)
+    ctx.set_references([ref])
+    out = []
+    for m in (100, 200, 500, 1000, 2000):
+        for e in (0.02, 0.05, 0.10, 0.15):
+            if cells and (m, e) not in cells:
+                continue
+            base, pool = synthetic.microbench_tasks(ref, [m], [e], distinct, 20240006 + m + int(e * 100), abi.MODE_EXISTS)
+            reps = max(1, tasks_per_cell // distinct)
+            row = {"m": m, "error": e, "k": int(base["max_errors"][0]), "tasks": len(base) * reps}
+            for mode, key in ((abi.MODE_EXISTS, "exists"), (abi.MODE_CIGAR, "cigar")):
+                tasks = np.tile(base, reps)
+                tasks["mode"] = mode
+                b = ctx.stage_align_batch(tasks, pool)
+                b.run()
+                ctx.reset_counters()
+                t0 = time.perf_counter()
+                b.run()
+                dt = time.perf_counter() - t0
+                c = ctx.counters()
+                cells_full = float((tasks["ref_len"].astype(np.float64) * tasks["query_len"]).sum())
+                res, cig = b.fetch()
+                b.free()
+                # parity of the distinct tasks with the CPU port, and its speed on the same
+                one = base.copy()
+                one["mode"] = mode
+                t0 = time.perf_counter()
+                cres, ccig = cpu_baseline.align_batch([ref], one, pool, threads=cpu_threads)
+                cdt = time.perf_counter() - t0
+                same = bool((res["exists"][:distinct] == cres["exists"]).all() and (res["num_errors"][:distinct] == cres["num_errors"]).all()
+                            and (res["start_in_reference"][:distinct] == cres["start_in_reference"]).all())
+                if not same:
+                    raise RuntimeError(f"config 5 cell m={m} e={e} mode={key}: results differ from the CPU port")
+                row[key] = {"gcups": cells_full / dt / 1e9, "tasks_per_s": len(tasks) / dt, "ms": dt * 1e3,
+                            "roofline_frac": c["dp_word_steps"] * MYERS_INSTR_PER_WORD_STEP / dt / int32_peak if int32_peak else None,
+                            "cpu_gcups": float((one["ref_len"].astype(np.float64) * one["query_len"]).sum()) / cdt / 1e9}
+            out.append(row)
+    return {"workload": f"config5: batched edit distance against a 10 Mbp random reference, {tasks_per_cell} tasks per cell ({distinct} distinct "
+                        f"query/window pairs, repeated), 50 % positives; wall time of one fxg_align_batch_run on staged inputs",
+            "cells": out, "cpu_cores": cpu_threads,
+            "parity": "results of the distinct tasks of every cell equal the CPU port's (exists, errors, start)"}
 
 
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=192)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
-    ap.add_argument("--interval-optimization", action="store_true", help="floxer --interval-optimization (off by default, as in the reference)")
-    ap.add_argument("--cpu-sample-reads", type=int, default=0, help="reads in the CPU sample (0 = sized automatically)")
-    ap.add_argument("--pipeline", type=int, default=32, help="batches in flight per GPU: the library serves FXG_GROUPS (default and at most 32) *_run calls at a time")
+    ap.add_argument("--only", default="", help="comma-separated subset of: config2,config2_ivopt,config3,config4_shard,config5")
+    ap.add_argument("--lanes", type=int, default=32, help="host threads that submit batches concurrently (config 2)")
+    ap.add_argument("--config3-reads", type=int, default=10_000)
+    ap.add_argument("--config4-reads", type=int, default=2_500, help="reads of the 12 500-read shard that are generated and verified")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall time of every CPU baseline sample")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    threads = os.cpu_count() or 1
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    threads = max(1, len(os.sched_getaffinity(0)) // max(local_world, 1)) if args.impl == "ours" else (os.cpu_count() or 1)
+    only = set(x for x in args.only.split(",") if x)
+    want = lambda name: not only or name in only
 
     from floxer_b200.batch import VerifyConfig
-    cfg = VerifyConfig(interval_optimization=args.interval_optimization)
-    W = WORKLOADS[args.workload]
-    config = {"workload": f"{args.workload}: {W['ref_len']} bp uniform random reference, {W['reads']} simulated reads x "
-                          f"{W['read_len']} bp at {int(W['error'] * 100)} % error per GPU, recursive PEX tree, seed errors 2, "
-                          f"hierarchical verification, interval optimization {'on' if cfg.interval_optimization else 'off'}, "
-                          f"extra verification ratio 0.05, CIGAR output; anchors from the ground-truth stand-in seeder",
-              "reads_per_gpu": W["reads"], "read_len": W["read_len"], "error_rate": W["error"],
-              "l2": "256 MiB written to HBM between steps (twice the 126 MB L2); the batches in flight run concurrently, so a step never finds its own data in L2",
-              "batches_in_flight": max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "32"))))}
 
     # ------------------------------------------------------------------ CPU arm ("reference")
     if args.impl == "reference":
         if rank != 0:
             return 0
-        from floxer_b200 import build
-        from floxer_b200 import gpu as g          # host-side PEX builder only (no device needed)
-        build.build_native()
-        refs, batch = make_workload(args.workload, 0, g.pex_build)
-        # every step is a sample of the workload sized so that the K steps together take about three minutes
-        n_sample = args.cpu_sample_reads or cpu_sample_size(refs, batch, cfg, threads, target_s=min(10.0, max(0.3, 200.0 / max(args.steps, 1))))
+        from oracle import cpu_baseline, oracle
+        threads = os.cpu_count() or 1
+        cfg = VerifyConfig()
+        refs, batch, anchors = build_workload("config2", 0, oracle.pex_build, None, threads)
+        # every step is a sample of the workload sized so that the K steps together take two to three minutes
+        probe = batch.slice(0, max(4, threads // 2))
+        t0 = time.perf_counter()
+        cpu_baseline.verify_reads(refs, probe, cfg, threads=threads)
+        rate = len(probe) / max(time.perf_counter() - t0, 1e-6)
+        n_sample = int(max(min(len(batch), rate * min(10.0, max(0.3, 150.0 / max(args.steps, 1)))), min(len(batch), threads)))
+        sample = batch.slice(0, n_sample)
         times, stats = [], None
         for _ in range(max(args.steps, 1)):
-            dt, stats, n_used = cpu_arm(refs, batch, cfg, n_sample, threads)
-            times.append(dt)
+            t0 = time.perf_counter()
+            _, _, stats = cpu_baseline.verify_reads(refs, sample, cfg, threads=threads)
+            times.append(time.perf_counter() - t0)
         sec = sum(times) / len(times)
-        cells = stats["cells_inner"] + stats["cells_root"]
-        gcups = cells / sec / 1e9
+        gcups = (stats["cells_inner"] + stats["cells_root"]) / sec / 1e9
         line = {"impl": "reference", "metric": "pex_verification_gcups", "value": gcups, "unit": "GCUPS",
-                "reads_per_s": n_used / sec, "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+                "reads_per_s": n_sample / sec, "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port",
-                                 "sample": f"first {n_used} reads of the workload per step, all anchors, both strands, CIGARs",
-                                 "reads_per_s": n_used / sec},
+                "dtype": "u64", "data": "synthetic",
+                "config": {"workload": describe("config2", False, len(batch), anchors), "lanes": args.lanes},
+                "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port", "reads_per_s": n_sample / sec,
+                                 "sample": f"first {n_sample} reads of the workload per step, all anchors, both strands, CIGARs"},
                 "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "note": "CPU port of floxer 0.2.0 + SeqAn3 edit-distance path (oracle/cpu_baseline.c); the reference binary "
-                        "cannot be built offline"}
+                "note": "CPU port of floxer 0.2.0 + SeqAn3 edit-distance path (oracle/cpu_baseline.c) on all host cores; the reference "
+                        "binary cannot be built offline (DESIGN.md section 2)"}
         print(json.dumps(line))
         return 0
 
     # ------------------------------------------------------------------ our arm
+    # all inputs first: the read generator forks worker processes, and CUDA must not be up by then
+    from floxer_b200 import build
+    from floxer_b200 import gpu as g
+    build.build_native()
+    t_gen = time.perf_counter()
+    made = {}
+    if want("config2") or want("config2_ivopt"):
+        made["config2"] = build_workload("config2", rank, g.pex_build, None, threads)
+    if want("config3"):
+        made["config3"] = build_workload("config3", rank, g.pex_build, args.config3_reads, threads)
+    if want("config4_shard"):
+        made["config4_shard"] = build_workload("config4_shard", rank, g.pex_build, args.config4_reads, threads)
+    gen_s = time.perf_counter() - t_gen
+
     import torch
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
@@ -196,241 +479,59 @@ def main() -> int:
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    from floxer_b200 import build
-    from floxer_b200 import gpu as g
-    build.build_native()
-    refs, batch = make_workload(args.workload, rank, g.pex_build)
-    # the step's inputs live in page-locked host memory (the host->device copies inside the timed e2e region are plain DMA)
-    pinned = [torch.from_numpy(a).pin_memory() for a in (batch.forward_pool, batch.reverse_pool)]
-    batch.forward_pool, batch.reverse_pool = pinned[0].numpy(), pinned[1].numpy()
     ctx = g.Context(local_rank)
-    ctx.set_references(refs)
-    int32_peak = ctx.measure_int32_peak()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    depth = max(1, min(args.pipeline, int(os.environ.get("FXG_GROUPS", "32"))))
-
-    def run_lanes(step_fns, n_steps):
-        """n_steps steps, dealt round-robin to len(step_fns) host threads (batches in flight); returns wall seconds."""
-        counts = [n_steps // len(step_fns) + (1 if i < n_steps % len(step_fns) else 0) for i in range(len(step_fns))]
-        errors = []
-
-        def lane(i):
-            try:
-                for _ in range(counts[i]):
-                    step_fns[i]()
-            except Exception as e:                       # noqa: BLE001 -- re-raised by the main thread
-                errors.append(e)
-        threads = [threading.Thread(target=lane, args=(i,)) for i in range(len(step_fns))]
-        t0 = time.perf_counter()
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        dt = time.perf_counter() - t0
-        if errors:
-            raise errors[0]
-        return dt
-
-    # ---- device-resident arm: inputs staged once (one staged copy per batch in flight), each step = fxg_verify_run ----
     sampler = ClockSampler(local_rank)
     if rank == 0 and os.environ.get("BENCH_NO_SAMPLER") != "1":      # rank 0 reports its GPU's clocks (one nvidia-smi, not one per rank)
         sampler.start()
-    jobs = [ctx.stage_verify(batch, cfg) for _ in range(depth)]
-    run_lanes([j.run for j in jobs], args.warmup * depth)    # both worker groups warm (their buffers are allocated on first use)
-
-    def resident_step(j):
-        def f():
-            flush.fill_(1)                               # 256 MiB written between steps (queued on torch's stream, no host sync)
-            j.run()
-        return f
-    # one step at a time first: the latency of a step, and its device time between the run's first and last operation
-    lat_ms, kernel_ms = [], []
-    for it in range(3):
-        flush.fill_(it & 0xff)
-        torch.cuda.synchronize()
-        c0 = ctx.counters()
-        t0 = time.perf_counter()
-        jobs[0].run()
-        lat_ms.append((time.perf_counter() - t0) * 1e3)
-        kernel_ms.append(ctx.counters()["run_ms"] - c0["run_ms"])
-    barrier()
-    ctx.reset_counters()
-    t_region = time.perf_counter()
-    total_s = run_lanes([resident_step(j) for j in jobs], args.steps)
-    barrier()
-    sampler.window(t_region, time.perf_counter())
-    step_ms = [total_s * 1e3 / args.steps] * args.steps
-    ctr = ctx.counters()
-    stats = jobs[0].stats()
-    al, cg = jobs[0].alignments()
-    n_alignments = len(al)
-    for j in jobs:
-        j.free()
-
-    # ---- end-to-end arm: host buffers in, alignments + CIGARs out, every step ----
-    checksum = [0] * depth
-
-    def e2e_step(i):
-        def f():
-            flush.fill_(2)
-            j2 = ctx.verify_reads(batch, cfg)            # host buffers in: H2D, all waves, tracebacks, D2H of alignments + CIGARs
-            a2, c2 = j2.alignments(copy=False)           # what a C caller reads: the job's own result arrays
-            checksum[i] ^= int(a2["start_in_reference"].sum()) ^ int(a2["num_errors"].sum()) ^ len(c2)
-            del a2, c2
-            j2.free()
-        return f
-    run_lanes([e2e_step(i) for i in range(depth)], 2 * depth)   # warm-up (page-locked pools are allocated once)
-    torch.cuda.synchronize()
-    ctx.reset_counters()
-    n_e2e = args.steps
-    t_region = time.perf_counter()
-    e2e_s = run_lanes([e2e_step(i) for i in range(depth)], n_e2e)
-    torch.cuda.synchronize()
-    sampler.window(t_region, time.perf_counter())
-    clocks = sampler.stop()
-    e2e_ms = [e2e_s * 1e3 / n_e2e] * n_e2e
-    e2e_ctr = ctx.counters()
-
-    # ---- roofline passes (rank 0): one host worker / one stream, so that kernels do not overlap and the
-    #      CUDA-event time of the DP launches is the time of those launches alone ----
-    n_roof = 3
-
-    def roofline_pass(extra_env):
-        env = {"FXG_WORKERS": "1", "FXG_GROUPS": "1", **extra_env}
-        saved_env = {k: os.environ.get(k) for k in env}
-        os.environ.update(env)
-        ctx1 = g.Context(local_rank)
-        for k, v in saved_env.items():
-            if v is None:
-                os.environ.pop(k, None)
+    head, sub = None, {}
+    int32_peak = None
+    plan = [("config2", False, args.lanes, args.steps, True), ("config2", True, args.lanes, args.steps, False),
+            ("config3", False, 3, max(3, args.steps // 4), False), ("config3", True, 3, max(3, args.steps // 4), False),
+            ("config4_shard", False, 2, max(3, args.steps // 5), False), ("config4_shard", True, 2, max(3, args.steps // 5), False)]
+    current = None
+    for name, ivopt, lanes, steps, is_head in plan:
+        key = name + ("_ivopt" if ivopt else "")
+        if name not in made or not (want(key) or (ivopt and want(name) and name != "config2")):
+            continue
+        refs, batch, anchors = made[name]
+        if current != name:
+            ctx.set_references(refs)
+            current = name
+            if int32_peak is None:
+                int32_peak = ctx.measure_int32_peak()
+        cfg = VerifyConfig(interval_optimization=ivopt)
+        rec = measure(ctx, g, torch, dist, refs, batch, cfg, lanes, steps, args.warmup, int32_peak, sampler, pageable=is_head,
+                      cpu_threads=threads, cpu_target_s=args.cpu_seconds, rank=rank)
+        if rec is not None:
+            rec["config"] = {"workload": describe(name, ivopt, len(batch), anchors), "lanes": lanes, "steps": steps,
+                             "l2": "256 MiB written to HBM between batches (twice the 126 MB L2); the lanes run concurrently, so a batch never finds its own data in L2"}
+            if is_head:
+                head = rec
             else:
-                os.environ[k] = v
-        ctx1.set_references(refs)
-        job1 = ctx1.stage_verify(batch, cfg)
-        job1.run()
-        ctx1.reset_counters()
-        for it in range(n_roof):
-            flush.fill_(it & 0xff)
-            torch.cuda.synchronize()
-            job1.run()
-        out = ctx1.counters()
-        job1.free()
-        ctx1.close()
-        return out
-
-    roof_ctr = prod_ctr = None
-    if rank == 0:
-        # the engine on a launch that fills the machine: every root window scored on its own, as when the windows of a
-        # batch do not coincide (14 542 score passes in one launch) ...
-        roof_ctr = roofline_pass({"FXG_SHARE_ROOTS": "0", "FXG_INFER_INNER": "0"})
-        # ... and the launches of the step as benchmarked (coinciding windows share one pass: 7x fewer word-steps)
-        prod_ctr = roofline_pass({})
-
-    # max over ranks
-    my = torch.tensor([sum(step_ms), sum(e2e_ms) / n_e2e * args.steps, sum(kernel_ms)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(my, op=dist.ReduceOp.MAX)
-    total_ms, e2e_total_ms, dev_ms = [float(x) for x in my.cpu()]
-    cells_step = stats["cells_inner"] + stats["cells_root"]
-    units = torch.tensor([cells_step, len(batch)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(units, op=dist.ReduceOp.SUM)
-    cells_all, reads_all = [float(x) for x in units.cpu()]
-
-    ms_per_step = total_ms / args.steps
-    gcups = cells_all / (ms_per_step * 1e-3) / 1e9
-    e2e_ms_per_step = e2e_total_ms / args.steps
-    e2e_gcups = cells_all / (e2e_ms_per_step * 1e-3) / 1e9
-
+                sub[key] = rec
+    if want("config5") and rank == 0:
+        if int32_peak is None:
+            ctx.set_references([np.ones(64, dtype=np.uint8)])
+            int32_peak = ctx.measure_int32_peak()
+        sub["config5"] = microbench(ctx, g, torch, int32_peak, threads, 1 << 20, 1 << 12)
+    clocks = sampler.stop()
     line = None
     if rank == 0:
-        # roofline of the dominant kernel (the bit-vector DP engine): integer-ALU bound, SURVEY 8(d).
-        # `frac` is that of the engine's root-level dp_kernel launch with every root window of the batch scored on its own
-        # (a launch that fills the machine), timed alone with its own CUDA event pair on its stream; `all_launches` is
-        # every score-pass launch of that step over the event time of the waves (small launches and their tails included);
-        # `as_benchmarked` is the same pair of figures for the step the headline numbers time, where coinciding windows
-        # share one pass: one batch alone then leaves most of the machine idle (the launches are chains of dependent
-        # steps, a few hundred warps wide), and the batches in flight fill it together.
-        dp_s = roof_ctr["dp_kernel_ms"] * 1e-3
-        ws = roof_ctr["dp_word_steps"]
-        root_s = roof_ctr["root_launch_ms"] * 1e-3
-        root_ws = roof_ctr["root_launch_word_steps"]
-        achieved = root_ws * MYERS_INSTR_PER_WORD_STEP / root_s if root_s > 0 else 0.0
-        achieved_all = ws * MYERS_INSTR_PER_WORD_STEP / dp_s if dp_s > 0 else 0.0
-        tr_s = roof_ctr["trace_kernel_ms"] * 1e-3
-        roofline = {"bound": "int32_alu", "achieved": achieved / 1e9, "peak": int32_peak / 1e9, "unit": "Ginstr/s",
-                    "frac": achieved / int32_peak if int32_peak else None,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
-                    # (profiles/r01_end_unshared_ncu_full_summary.txt: 84.4 MB read, 1.446 GB written -- the checkpoint records)
-                    "traffic": 1530833704,
-                    # the contract's HBM view of the same launch, for the record: the path is not bandwidth-bound
-                    "hbm_view": (lambda peak, src: {"achieved": 1530833704 / root_s * n_roof / 1e9 if root_s > 0 else None, "peak": peak, "unit": "GB/s",
-                                                    "frac": (1530833704 / root_s * n_roof / 1e9) / peak if root_s > 0 else None,
-                                                    "peak_source": src,
-                                                    "note": "DRAM bytes of the launch (ncu) / its CUDA-event time; 5-6 % of the copy bandwidth"})(
-                        *((_measured_peak("hbm_gbs"), "MEASURED_PEAKS.json hbm_gbs") if _measured_peak("hbm_gbs") else (6650.0, "of fallback (B200_PROFILING.md)"))),
-                    "kernel": "fxg::dp_kernel<4,true> -- the root-level launch of a step (score pass leaving traceback checkpoints), "
-                              "every root window of the batch scored on its own (FXG_SHARE_ROOTS=0 FXG_INFER_INNER=0): the launch that fills the machine",
-                    "how": "algorithmic 11 int32 instr per 32-cell word-step x word-steps issued by that launch (band-limited, counted on the "
-                           "host from the band geometry) / CUDA-event time of the launch on its stream; peak = LOP3/IADD3/SHF 8:1:2 "
-                           "issue-rate microbenchmark on this GPU in this run; HBM traffic is negligible (window + Eq words in, "
-                           "one checkpoint record per block and 32 steps out)",
-                    "word_steps_per_launch": root_ws / n_roof, "launch_ms": roof_ctr["root_launch_ms"] / n_roof,
-                    "all_launches": {"frac": achieved_all / int32_peak if int32_peak else None, "achieved": achieved_all / 1e9,
-                                     "dp_word_steps_per_step": ws / n_roof, "dp_kernel_ms_per_step": roof_ctr["dp_kernel_ms"] / n_roof},
-                    "cells_computed_per_step": ws * 32 / n_roof, "cells_full_matrix_per_step": cells_step,
-                    "gcups_computed_cells_kernel_only": ws * 32 / dp_s / 1e9 if dp_s else None,
-                    "traceback": {"kernel": "fxg::walk2_kernel<4> (one lane per alignment, recomputes the tiles its path crosses)",
-                                  "kernel_ms_per_step": roof_ctr["trace_kernel_ms"] / n_roof,
-                                  "checkpoint_bytes_per_step": roof_ctr["trace_bytes"] / n_roof,
-                                  "note": "latency-bound chain of dependent steps per alignment, not a bandwidth kernel"},
-                    "single_stream_device_ms_per_step": roof_ctr["run_ms"] / n_roof,
-                    "as_benchmarked": {
-                        "note": "one batch on one stream with window sharing on (the production path): launches too small to fill 148 SMs "
-                                "on their own, run concurrently with those of the other batches in flight",
-                        "root_launch_frac": (prod_ctr["root_launch_word_steps"] * MYERS_INSTR_PER_WORD_STEP / (prod_ctr["root_launch_ms"] * 1e-3) / int32_peak)
-                        if int32_peak and prod_ctr["root_launch_ms"] > 0 else None,
-                        "root_launch_ms": prod_ctr["root_launch_ms"] / n_roof,
-                        "root_launch_word_steps": prod_ctr["root_launch_word_steps"] / n_roof,
-                        "all_launches_frac": (prod_ctr["dp_word_steps"] * MYERS_INSTR_PER_WORD_STEP / (prod_ctr["dp_kernel_ms"] * 1e-3) / int32_peak)
-                        if int32_peak and prod_ctr["dp_kernel_ms"] > 0 else None,
-                        "dp_word_steps_per_step": prod_ctr["dp_word_steps"] / n_roof,
-                        "dp_kernel_ms_per_step": prod_ctr["dp_kernel_ms"] / n_roof,
-                        "cells_computed_per_step": prod_ctr["dp_word_steps"] * 32 / n_roof,
-                        "traceback_kernel_ms_per_step": prod_ctr["trace_kernel_ms"] / n_roof,
-                        "checkpoint_bytes_per_step": prod_ctr["trace_bytes"] / n_roof,
-                        "shared_score_passes_per_step": prod_ctr["shared_score_passes"] / n_roof,
-                        "rescored_roots_per_step": prod_ctr["rescored_roots"] / n_roof,
-                        "inferred_inner_per_step": prod_ctr["inferred_inner"] / n_roof,
-                        "shared_tracebacks_per_step": prod_ctr["shared_tracebacks"] / n_roof,
-                        "single_stream_device_ms_per_step": prod_ctr["run_ms"] / n_roof}}
-        cpu_sec, cpu_stats, n_used = cpu_arm(refs, batch, cfg, args.cpu_sample_reads, threads)
-        cpu_cells = cpu_stats["cells_inner"] + cpu_stats["cells_root"]
-        line = {"metric": "pex_verification_gcups", "value": gcups, "unit": "GCUPS", "reads_per_s": reads_all / (ms_per_step * 1e-3),
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        if head is None:                                 # --only without the headline: the first record stands in
+            key = next(iter(sub))
+            head = sub.pop(key)
+        cfg_obj = head.pop("config")
+        line = {"metric": "pex_verification_gcups", "value": head.pop("value"), "unit": "GCUPS", "reads_per_s": head.pop("reads_per_s"),
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head.pop("ms_per_step"),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": config,
+                "config": cfg_obj,
                 "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
-                "e2e": {"value": e2e_gcups, "unit": "GCUPS", "reads_per_s": reads_all / (e2e_ms_per_step * 1e-3),
-                        "ms_per_step": e2e_ms_per_step,
-                        "h2d_bytes_per_step": e2e_ctr["h2d_bytes"] // n_e2e, "d2h_bytes_per_step": e2e_ctr["d2h_bytes"] // n_e2e},
-                "gpu_launches": int(ctr["kernel_launches"]),
-                "roofline": roofline,
-                "cpu_baseline": {"value": cpu_cells / cpu_sec / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
-                                 "sample": f"first {n_used} reads of rank 0's batch, all anchors, both strands, CIGARs",
-                                 "reads_per_s": n_used / cpu_sec},
-                "step_latency_ms": [round(x, 3) for x in lat_ms], "step_latency_device_ms": [round(x, 3) for x in kernel_ms],
-                "host_cores": len(os.sched_getaffinity(0)),
-                "waves_per_step": ctr["waves"] / args.steps,
-                "alignments_per_step": n_alignments,
-                "stats_per_step": stats}
+                "e2e": head.pop("e2e"), "gpu_launches": head.pop("gpu_launches"), "roofline": head.pop("roofline"),
+                "cpu_baseline": head.pop("cpu_baseline")}
+        line.update(head)
+        line["host_cores"] = len(os.sched_getaffinity(0))
+        line["generation_s"] = round(gen_s, 1)
+        line["sub"] = sub
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

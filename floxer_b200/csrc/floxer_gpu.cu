@@ -269,7 +269,8 @@ struct fxg_ctx {
     int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
     std::vector<Pool> spare_pools;       // device buffers of freed batches / jobs, reused by the next stage call
     std::vector<PinnedBuf> spare_pinned; // page-locked cigar pools of freed batches / jobs (cudaHostAlloc costs milliseconds)
-    std::vector<DevBuf> spare_dev;       // record buffers of freed jobs
+    std::vector<DevBuf> spare_dev;       // record buffers of freed jobs ...
+    std::vector<PinnedBuf> spare_staging;// ... and the page-locked memory they were uploaded from
     std::mutex mu;
     // the queue of fxg_verify_run / fxg_verify_reads calls: a caller that finds a free worker group takes every compatible
     // job that is waiting with it and runs them as one batch (submit_and_wait)
@@ -1097,7 +1098,7 @@ Pool take_pool(fxg_ctx* c) {
     return p;
 }
 void give_pool(fxg_ctx* c, Pool& p) {
-    if (c->spare_pools.size() < size_t(2 * c->n_groups)) c->spare_pools.push_back(p); else p.release();   // one per batch in flight and one being staged
+    if (c->spare_pools.size() < 96) c->spare_pools.push_back(p); else p.release();   // one per caller whose job waits or is being staged
     p = Pool{};
 }
 
@@ -1112,7 +1113,16 @@ PinnedBuf take_pinned(fxg_ctx* c) {
     return b;
 }
 void give_pinned(fxg_ctx* c, PinnedBuf& b) {
-    if (b.p && c->spare_pinned.size() < size_t(2 * c->n_groups)) c->spare_pinned.push_back(b); else b.release();
+    if (b.p && c->spare_pinned.size() < size_t(2 * c->n_groups + 8)) c->spare_pinned.push_back(b); else b.release();
+    b = PinnedBuf{};
+}
+PinnedBuf take_staging(fxg_ctx* c) {
+    PinnedBuf b;
+    if (!c->spare_staging.empty()) { b = c->spare_staging.back(); c->spare_staging.pop_back(); }
+    return b;
+}
+void give_staging(fxg_ctx* c, PinnedBuf& b) {
+    if (b.p && c->spare_staging.size() < 96) c->spare_staging.push_back(b); else b.release();
     b = PinnedBuf{};
 }
 
@@ -2144,6 +2154,7 @@ void fxg_destroy(fxg_ctx* c) {
     for (Pool& p : c->spare_pools) p.release();
     for (PinnedBuf& b : c->spare_pinned) b.release();
     for (DevBuf& b : c->spare_dev) b.release();
+    for (PinnedBuf& b : c->spare_staging) b.release();
     c->refs.d_base.release(); c->refs.d_len.release();
     for (WorkerGroup& g : c->groups) {
         for (auto& w : g.workers) w->release();
@@ -2637,7 +2648,7 @@ int check_verify_call(fxg_ctx* c, const fxg_verify_config* cfg) {
 }
 
 void release_job_buffers(fxg_ctx* c, fxg_job* j) {        // call with c->mu held
-    give_pool(c, j->pool); give_pinned(c, j->cigars); give_pinned(c, j->prep.staging);
+    give_pool(c, j->pool); give_pinned(c, j->cigars); give_staging(c, j->prep.staging);
     if (j->prep.dev.p && c->spare_dev.size() < size_t(2 * fxg_ctx::kMaxGroups + 64)) c->spare_dev.push_back(j->prep.dev); else j->prep.dev.release();
     j->prep.dev = DevBuf{};
 }
@@ -2656,8 +2667,7 @@ int fxg_verify_stage(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     fxg_job* j = new (std::nothrow) fxg_job();
     if (!j) return FXG_ERR_OUT_OF_MEMORY;
     j->pool = take_pool(c);
-    j->cigars = take_pinned(c);
-    j->prep.staging = take_pinned(c);
+    j->prep.staging = take_staging(c);
     if (!c->spare_dev.empty()) { j->prep.dev = c->spare_dev.back(); c->spare_dev.pop_back(); }
     lock.unlock();                       // the rest touches only the job (and the staging stream, which is ordered)
     std::string err; fxg_counters ctr{};
@@ -2728,8 +2738,7 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     j->borrowed = true;
     j->pool_len = pool_len;
     j->pool = take_pool(c);
-    j->cigars = take_pinned(c);
-    j->prep.staging = take_pinned(c);
+    j->prep.staging = take_staging(c);
     if (!c->spare_dev.empty()) { j->prep.dev = c->spare_dev.back(); c->spare_dev.pop_back(); }
     lock.unlock();
     std::string err; fxg_counters ctr{};

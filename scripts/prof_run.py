@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd())
 import bench
 from floxer_b200 import gpu as g
 from floxer_b200.batch import VerifyConfig
-refs, batch = bench.make_workload("config2", 0, g.pex_build)
+refs, batch, _ = bench.build_workload("config2", 0, g.pex_build, None, 8)
 ctx = g.Context(0); ctx.set_references(refs)
 job = ctx.stage_verify(batch, VerifyConfig())
 job.run(); 

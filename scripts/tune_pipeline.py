@@ -6,7 +6,7 @@ import bench
 from floxer_b200 import gpu as g
 from floxer_b200.batch import VerifyConfig
 depth = int(os.environ.get("FXG_GROUPS", "32"))
-refs, batch = bench.make_workload("config2", 0, g.pex_build)
+refs, batch, _ = bench.build_workload("config2", 0, g.pex_build, None, 8)
 ctx = g.Context(0); ctx.set_references(refs)
 jobs = [ctx.stage_verify(batch, VerifyConfig()) for _ in range(depth)]
 def lanes(n):

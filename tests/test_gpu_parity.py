@@ -425,7 +425,7 @@ def test_bench_workload_properties_and_sample_parity(gpu):
     the sequences, the counts against the simulation's ground truth, and the first reads bit for bit against the CPU port."""
     import bench
     from oracle import cpu_baseline
-    refs, batch = bench.make_workload("config2", 0, gpu.pex_build)
+    refs, batch, _ = bench.build_workload("config2", 0, gpu.pex_build, None, 8)
     c2 = gpu.Context(0)
     try:
         c2.set_references(refs)
