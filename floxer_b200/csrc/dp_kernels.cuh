@@ -625,6 +625,124 @@ __global__ void __launch_bounds__(32, dp_min_ctas(W)) dp_kernel(DpLaunch const L
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The engine for bands that no ring of one warp can hold (more than ~29 700 diagonals: reads near the 100 kbp limit of
+// input.hpp:42 at 10-15 % errors).  One CTA of kWideThreads threads per task, W = 32: thread l owns block l (1 024 rows)
+// and nothing else -- 128 blocks cover every legal query -- and the hand-over of the horizontal deltas between neighbours
+// goes through shared memory with one barrier per step instead of a shuffle.  Same band rule, same boundary conventions
+// (a block outside its working range publishes "+1 per column"; a fresh block starts from the block above + 1, 2, ...),
+// same checkpoint records as dp_kernel<32, CKPT>, so walk2_kernel<32> and range_min_kernel read its output unchanged.
+// These tasks are rare and long (a 100 kbp root is 1.4e10 cells); the kernel is written for exactness, not for the roofline.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kWideThreads = 128;
+constexpr uint32_t kWideG = 64;                     // marks the wide configuration in the host's (W, G) tables
+__host__ __device__ constexpr size_t wide_smem_bytes() { return size_t(kNumSymbols) * 32 * kWideThreads * 4 + 2 * kWideThreads * 16; }
+
+template <bool CKPT>
+__global__ void __launch_bounds__(kWideThreads, 1) dp_wide_kernel(DpLaunch const L) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int W = 32;
+    constexpr int ROWS = 32 * W;
+    uint32_t* const eq_all = reinterpret_cast<uint32_t*>(smem);                     // Eq[sym][word][thread]
+    uint4* const pub = reinterpret_cast<uint4*>(smem + size_t(kNumSymbols) * 32 * kWideThreads * 4);   // [2][thread]: hp, hn, score
+    uint32_t const l = threadIdx.x;
+    uint32_t const n_tasks = L.n_tasks_dev ? __ldg(L.n_tasks_dev) : L.n_tasks;
+    const DpTask* tasks = L.tasks;
+    if (L.class_active) { for (uint32_t c = 0; c < L.cls; ++c) tasks += __ldg(L.class_active + c); }
+    for (uint32_t task_id = blockIdx.x; task_id < n_tasks; task_id += gridDim.x) {
+        DpTask const T = tasks[task_id];
+        uint32_t const nb = (T.m + ROWS - 1) / ROWS;               // <= kWideThreads (checked by the host)
+        uint32_t const pad = nb * ROWS - T.m;
+        int32_t const dlo = T.dlo - int32_t(pad), dhi = T.dhi - int32_t(pad);
+        bool const reverse = (T.flags & kFlagReverse) != 0;
+        const uint32_t* const packed = (T.flags & kFlagInlineRef) ? L.inline_packed : L.ref_packed;
+        bool const have = l < nb;
+        int32_t cs = 0x7fffffff, ce = -1;
+        if (have) {
+            int32_t const lo = int32_t(ROWS) * int32_t(l) + 1 + dlo, hi = int32_t(ROWS) * int32_t(l + 1) + dhi;
+            int32_t const a = lo < 1 ? 1 : lo, b = hi > int32_t(T.n) ? int32_t(T.n) : hi;
+            if (a <= b) { cs = a; ce = b; }
+        }
+        // ---- Eq rows of this thread's block ----
+        if (have) {
+            for (int w = 0; w < W; ++w) {
+                uint32_t const gw = l * W + uint32_t(w);
+                int32_t const virt = int32_t(pad) - int32_t(32 * gw);
+                uint32_t const wild = virt >= 32 ? 0xffffffffu : (virt > 0 ? ((1u << virt) - 1u) : 0u);
+                for (int sym = 0; sym < kNumSymbols; ++sym) {
+                    const uint32_t* plane = L.peq_table + uint64_t(sym) * L.peq_plane_words;
+                    uint32_t x;
+                    if (!reverse) x = peq_window(plane, int64_t(T.query_base) - int64_t(pad) + int64_t(32 * gw));
+                    else x = __brev(peq_window(plane, int64_t(T.query_base) + int64_t(T.m) - 1 + int64_t(pad) - int64_t(32 * gw) - 31));
+                    eq_all[(uint32_t(sym) * 32 + uint32_t(w)) * kWideThreads + l] = x | wild;
+                }
+            }
+        }
+        uint32_t Pv[W], Mv[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) { Pv[i] = 0; Mv[i] = 0; }
+        int32_t score = 0, best = kNoScore;
+        uint32_t best_col = 0;
+        uint32_t acc_hp = 0xffffffffu, acc_hn = 0;
+        uint32_t const ck_per_block = ck_records_per_block(int64_t(T.dhi) - int64_t(T.dlo) + 1, ROWS);
+        uint32_t* ckp = CKPT ? L.trace + T.trace_base + uint64_t(l) * ck_per_block * ck_record_words(W) : nullptr;
+        pub[l] = make_uint4(0x80000000u, 0u, 0u, 0u);
+        pub[kWideThreads + l] = make_uint4(0x80000000u, 0u, 0u, 0u);
+        __syncthreads();
+        uint32_t const t_end = T.n + nb - 1;
+        bool const is_last = have && l == nb - 1;
+        for (uint32_t t = 1; t <= t_end; ++t) {
+            int32_t const j = int32_t(t) - int32_t(l);
+            uint4 const up = l > 0 ? pub[((t - 1) & 1u) * kWideThreads + l - 1] : make_uint4(0u, 0u, 0u, 0u);   // the block above after step t - 1
+            bool const active = have && j >= cs && j <= ce;
+            uint4 mine = make_uint4(0x80000000u, 0u, uint32_t(score), 0u);         // outside its range a block publishes "+1 per column"
+            if (active) {
+                if (j == cs) {
+                    // column cs - 1 of this block is (bottom of the block above at cs - 1) + 1, 2, ...
+#pragma unroll
+                    for (int i = 0; i < W; ++i) { Pv[i] = 0xffffffffu; Mv[i] = 0; }
+                    if (l == 0) {
+#pragma unroll
+                        for (int i = 0; i < W; ++i) {
+                            int32_t const virt = int32_t(pad) - 32 * i;            // wildcard rows carry value 0: no vertical step there
+                            Pv[i] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
+                        }
+                        score = int32_t(ROWS) - int32_t(pad);
+                    } else {
+                        score = int32_t(up.z) - int32_t(up.x >> 31) + int32_t(up.y >> 31) + ROWS;
+                    }
+                    acc_hp = 0xffffffffu; acc_hn = 0;
+                }
+                // character of column j: window[j - 1] in sweep order
+                uint64_t const pos = reverse ? T.ref_base + uint64_t(T.n) - uint64_t(j) : T.ref_base + uint64_t(j) - 1;
+                uint32_t c = packed_base(packed, pos);
+                if (c >= uint32_t(kNumSymbols)) c = 0;                               // (cannot happen: ranks are checked on upload)
+                uint32_t Eq[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) Eq[w] = eq_all[(c * 32 + uint32_t(w)) * kWideThreads + l];
+                uint32_t hp, hn, no_hp[1];
+                block_column<W, false>(Pv, Mv, Eq, l == 0 ? 0u : up.x, l == 0 ? 0u : up.y, hp, hn, no_hp);
+                score += int32_t(hp >> 31) - int32_t(hn >> 31);
+                if (is_last && score <= best) { best = score; best_col = uint32_t(j); }
+                mine = make_uint4(hp, hn, uint32_t(score), 0u);
+                if (CKPT) {
+                    acc_hp = __funnelshift_l(hp, acc_hp, 1); acc_hn = __funnelshift_l(hn, acc_hn, 1);
+                    if ((t & 31u) == 0) { write_checkpoint<W>(ckp, Pv, Mv, __brev(acc_hp), __brev(acc_hn)); ckp += ck_record_words(W); }
+                    else if (j == ce) {
+                        // the block ends between two multiples of 32: the boundary bits since the last one go into one more record
+                        uint32_t const left_over = t & 31u;
+                        *reinterpret_cast<uint4*>(ckp + 2 * W) = make_uint4(__brev(acc_hp) >> (32 - left_over), __brev(acc_hn) >> (32 - left_over), 0u, 0u);
+                    }
+                }
+            }
+            pub[(t & 1u) * kWideThreads + l] = mine;
+            __syncthreads();
+        }
+        if (is_last) { DpResult res; res.score = best; res.end_col = best_col; L.results[T.out] = res; }
+        __syncthreads();                                   // the next task reuses the Eq rows
+    }
+}
+
 struct WalkResult {
     uint32_t begin_col;     // column where the traceback reached row 0 (sequence1_begin_position)
     uint32_t cigar_len;     // 0xffffffff on overflow / inconsistency; the ops are the LAST cigar_len entries of the slot

@@ -36,17 +36,51 @@ using namespace fxg;
 
 namespace {
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync), on a stream of its own per device:
+// cudaMalloc / cudaFree synchronise the whole device, and with batches of changing sizes in flight a buffer that has to
+// grow would stall every other batch for the length of the kernels that happen to run (measured: steps of 600 ms among
+// steps of 10 ms).  The allocation is waited for on the host, so the memory may be used on any stream afterwards; a
+// buffer is only ever replaced by its owner between two of its uses, when nothing reads it any more.
+inline cudaStream_t alloc_stream() {
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[dev]) {
+        if (cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) { streams[dev] = nullptr; return nullptr; }
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;                    // freed memory stays with the pool instead of going back to the driver
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    return streams[dev];
+}
+inline cudaError_t device_alloc(void** p, size_t bytes) {
+    cudaStream_t const s = alloc_stream();
+    if (!s) return cudaMalloc(p, bytes);
+    cudaError_t e = cudaMallocAsync(p, bytes, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    return e;
+}
+inline void device_free(void* p) {
+    cudaStream_t const s = alloc_stream();
+    if (!s || cudaFreeAsync(p, s) != cudaSuccess) cudaFree(p);
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t const want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
+        if (p) { device_free(p); p = nullptr; }
+        size_t const want = std::max(bytes + bytes / 4 + 256, 2 * cap);      // grows geometrically: few replacements on the way to the steady state
+        cap = 0;
+        cudaError_t e = device_alloc(&p, want);
         if (e != cudaSuccess) {
             (void)cudaGetLastError();
-            e = cudaMalloc(&p, bytes);
+            e = device_alloc(&p, bytes);
             if (e != cudaSuccess) { p = nullptr; return e; }
             cap = bytes;
             return e;
@@ -58,19 +92,19 @@ struct DevBuf {
     cudaError_t ensure_preserving(size_t bytes, size_t keep, cudaStream_t stream) {
         if (bytes <= cap) return cudaSuccess;
         void* np = nullptr;
-        size_t const want = bytes + bytes / 2 + 256;
-        cudaError_t e = cudaMalloc(&np, want);
+        size_t const want = std::max(bytes + bytes / 2 + 256, 2 * cap);
+        cudaError_t e = device_alloc(&np, want);
         if (e != cudaSuccess) return e;
         if (p && keep) {
             e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-            if (e != cudaSuccess) { cudaFree(np); return e; }
+            if (e != cudaSuccess) { device_free(np); return e; }
         }
-        if (p) cudaFree(p);
+        if (p) device_free(p);
         p = np; cap = want;
         return cudaSuccess;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) device_free(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -79,8 +113,9 @@ struct PinnedBuf {                       // page-locked host staging memory
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-        size_t const want = bytes + bytes / 2 + 4096;
+        size_t const want = std::max(bytes + bytes / 2 + 4096, 2 * cap);
+        if (p) { cudaFreeHost(p); p = nullptr; }
+        cap = 0;
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
         if (e != cudaSuccess) { p = nullptr; return e; }
         cap = want;
@@ -266,6 +301,7 @@ struct fxg_ctx {
     bool device_levels = true;                   // FXG_DEVICE_LEVELS=0 runs the inner tree levels from the host (development knob)
     bool share_root_passes = true;               // FXG_SHARE_ROOTS=0 scores every root window on its own (development knob)
     bool infer_inner = true;                     // FXG_INFER_INNER=0 computes every inner window (development knob)
+    bool force_wide = false;                     // FXG_FORCE_WIDE=1 sends every pass to the multi-warp kernel (development knob: tests)
     int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
     std::vector<Pool> spare_pools;       // device buffers of freed batches / jobs, reused by the next stage call
     std::vector<PinnedBuf> spare_pinned; // page-locked cigar pools of freed batches / jobs (cudaHostAlloc costs milliseconds)
@@ -278,6 +314,7 @@ struct fxg_ctx {
     std::condition_variable cv;
     uint64_t merge_max_walks = uint64_t(6) << 20;   // FXG_MERGE_WALKS: anchors of a merged batch at most (a single job may be larger)
     int merge_max_jobs = 64;                        // FXG_MERGE_JOBS (1 = never merge)
+    int merge_wait_us = 300;                        // FXG_MERGE_WAIT_US: how long a job waits for company while other batches run
     std::mutex class_mu;
     ClassDef classes[kMaxLevelClasses];
     int n_classes = 0;
@@ -413,6 +450,11 @@ cudaError_t launch_one(DpLaunch const& L, uint32_t grid, size_t smem, cudaStream
 }
 
 cudaError_t launch_dp(int widx, bool checkpoints, DpLaunch const& L, uint32_t grid, size_t smem, cudaStream_t s) {
+    if (widx < 0) {                                  // the multi-warp kernel for bands no ring of one warp holds
+        if (checkpoints) dp_wide_kernel<true><<<grid, kWideThreads, smem, s>>>(L);
+        else dp_wide_kernel<false><<<grid, kWideThreads, smem, s>>>(L);
+        return cudaGetLastError();
+    }
     switch (widx * 2 + (checkpoints ? 1 : 0)) {
         case 0: return launch_one<1, false>(L, grid, smem, s);
         case 1: return launch_one<1, true>(L, grid, smem, s);
@@ -462,6 +504,10 @@ cudaError_t set_all_smem_attrs(size_t bytes) {
 #define FXG_SET(W) if ((e = set_smem_attr<W>(bytes)) != cudaSuccess) return e;
     FXG_SET(1) FXG_SET(2) FXG_SET(4) FXG_SET(8) FXG_SET(16) FXG_SET(32)
 #undef FXG_SET
+    if (wide_smem_bytes() <= bytes) {
+        if ((e = cudaFuncSetAttribute(dp_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wide_smem_bytes()))) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(dp_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wide_smem_bytes()))) != cudaSuccess) return e;
+    }
     return cudaSuccess;
 }
 
@@ -490,12 +536,12 @@ uint64_t word_steps_of(Pass const& p, uint32_t W, uint32_t nb) {
 // running alone 7.4 -> 6.9 ms, 16 batches in flight unchanged, a machine-filling launch 0.61 -> 0.48 of the issue peak)
 double g_latency_weight = [] { const char* e = std::getenv("FXG_LATENCY_WEIGHT"); return e ? std::atof(e) : 0.0; }();
 
-bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
+bool choose_config(Pass const& p, size_t smem_limit, bool force_wide, Config& out) {
     uint32_t const nw = (p.m + 31) / 32;
     int64_t const B = int64_t(p.dhi) - int64_t(p.dlo) + 1;
     double best_cost = 1e300;
     bool found = false;
-    for (int wi = 0; wi < 6; ++wi) {
+    for (int wi = 0; wi < 6 && !force_wide; ++wi) {
         uint32_t const W = uint32_t(kWidths[wi]);
         uint32_t const nb = (nw + W - 1) / W;
         uint32_t G;
@@ -525,18 +571,23 @@ bool choose_config(Pass const& p, size_t smem_limit, Config& out) {
         cost += g_latency_weight * double(steps) * (30.0 + 12.0 * W);
         if (cost < best_cost) { best_cost = cost; out = Config{uint8_t(wi), uint8_t(G), nb, 0}; found = true; }
     }
+    if (!found) {
+        // no ring of one warp holds this band: the multi-warp kernel (dp_wide_kernel), one block of 1 024 rows per thread
+        uint32_t const nb = (nw + 31) / 32;
+        if (nb <= kWideThreads && wide_smem_bytes() <= smem_limit) { out = Config{5, uint8_t(kWideG), nb, 0}; found = true; }
+    }
     if (found) out.word_steps = word_steps_of(p, uint32_t(kWidths[out.widx]), out.nb);
     return found;
 }
 
 // the same (m, n, band) recurs for every anchor of a read at one tree level: memoise
-bool cached_config(std::vector<ConfigCacheEntry>& cache, Pass const& p, size_t smem_limit, Config& out) {
+bool cached_config(std::vector<ConfigCacheEntry>& cache, Pass const& p, size_t smem_limit, bool force_wide, Config& out) {
     uint64_t h = (uint64_t(p.n) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(p.m) * 0xC2B2AE3D27D4EB4Full) ^ (uint64_t(uint32_t(p.dlo)) << 21) ^ uint64_t(uint32_t(p.dhi));
     h ^= h >> 29;
     ConfigCacheEntry& e = cache[h & (cache.size() - 1)];
     if (e.valid && e.n == p.n && e.m == p.m && e.dlo == p.dlo && e.dhi == p.dhi) { out = e.cfg; return e.ok; }
     e.valid = true; e.n = p.n; e.m = p.m; e.dlo = p.dlo; e.dhi = p.dhi;
-    e.ok = choose_config(p, smem_limit, e.cfg);
+    e.ok = choose_config(p, smem_limit, force_wide, e.cfg);
     out = e.cfg;
     return e.ok;
 }
@@ -572,11 +623,11 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     w.keys.resize(N);
     for (size_t i = 0; i < N; ++i) {
         Config& cf = w.cfgs[i];
-        if (!cached_config(w.cfg_cache, passes[i], c->smem_limit, cf))
+        if (!cached_config(w.cfg_cache, passes[i], c->smem_limit, c->force_wide, cf))
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
                         passes[i].m, passes[i].n, passes[i].dlo, passes[i].dhi);
         uint64_t const steps = std::min<uint64_t>(uint64_t(passes[i].n) + cf.nb - 1, (1u << 19) - 1);
-        uint64_t const cls = uint64_t(5 - cf.widx) * 32 + (32 - cf.G);                                  // 0 = W 32, G 32
+        uint64_t const cls = cf.G == kWideG ? 0 : uint64_t(5 - cf.widx) * 32 + (32 - cf.G) + 1;         // 0 = the multi-warp kernel, 1 = W 32, G 32
         w.keys[i] = (cls << 51) | ((((1ull << 19) - 1) - steps) << 32) | uint64_t(i);
     }
     g_prof.lap(w, 3);
@@ -612,7 +663,8 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
         Config const& c0 = w.cfgs[uint32_t(w.keys[i])];
         int const widx = c0.widx; uint32_t const G = c0.G;
         uint32_t const W = uint32_t(kWidths[widx]);
-        uint32_t const tpw = 32 / G;
+        bool const wide = G == kWideG;
+        uint32_t const tpw = wide ? 1 : 32 / G;
         size_t j = i;
         uint32_t max_words = 0;
         uint64_t work = 0, ws = 0;
@@ -639,10 +691,10 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
         L.peq_plane_words = pool.plane_words;
         L.results = w.d_results.as<DpResult>();
         L.trace = ck_buffer;
-        X.smem = size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
+        X.smem = wide ? wide_smem_bytes() : size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
         if (X.smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", X.smem);
-        X.grid = uint32_t((L.n_tasks + tpw - 1) / tpw);
-        X.widx = widx; X.work = work / tpw; X.word_steps = ws;
+        X.grid = wide ? uint32_t(std::min<size_t>(L.n_tasks, size_t(c->num_sms) * 2)) : uint32_t((L.n_tasks + tpw - 1) / tpw);
+        X.widx = wide ? -1 : widx; X.work = work / tpw; X.word_steps = ws;
         launches.push_back(X);
         i = j;
     }
@@ -737,7 +789,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
     std::vector<Unit> units;
     std::vector<uint32_t> unit_members;
     auto finish_unit = [&](Unit& u) -> int {
-        if (!cached_config(w.cfg_cache, u.p, c->smem_limit, u.cfg))
+        if (!cached_config(w.cfg_cache, u.p, c->smem_limit, c->force_wide, u.cfg))
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
                         u.p.m, u.p.n, u.p.dlo, u.p.dhi);
         uint32_t const W = uint32_t(kWidths[u.cfg.widx]);
@@ -799,7 +851,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
                 u.p = P0; u.p.n = uint32_t(u_end - u_start);
                 u.p.dlo = -int32_t(k0); u.p.dhi = int32_t(int64_t(u.p.n) - int64_t(u.p.m) + int64_t(k0));
                 Config probe;
-                if (cached_config(w.cfg_cache, u.p, c->smem_limit, probe)) {
+                if (cached_config(w.cfg_cache, u.p, c->smem_limit, c->force_wide, probe)) {
                     for (size_t q = i; q < j; ++q) unit_members.push_back(order[q]);
                     int const rc = finish_unit(u);
                     if (rc != FXG_OK) return rc;
@@ -819,7 +871,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         cigar_bound += cigar_cap_for(max_errors[i]);
         // a member that has to be scored again on its own must fit the budget as well
         Config cf;
-        if (cached_config(w.cfg_cache, passes[i], c->smem_limit, cf)) {
+        if (cached_config(w.cfg_cache, passes[i], c->smem_limit, c->force_wide, cf)) {
             uint32_t const W = uint32_t(kWidths[cf.widx]);
             max_words = std::max(max_words, (uint64_t(cf.nb) * ck_records_per_block(int64_t(passes[i].dhi) - int64_t(passes[i].dlo) + 1, 32 * W) * ck_record_words(W) + 3) & ~uint64_t(3));
         }
@@ -1364,8 +1416,10 @@ int class_of(fxg_ctx* c, Config const& cf, uint32_t words) {
     return c->n_classes++;
 }
 
-std::vector<ConfigCacheEntry>& thread_config_cache() {
+std::vector<ConfigCacheEntry>& thread_config_cache(const fxg_ctx* c) {
     thread_local std::vector<ConfigCacheEntry> cache(8192);
+    thread_local const fxg_ctx* owner = nullptr;
+    if (owner != c) { for (ConfigCacheEntry& e : cache) e.valid = false; owner = c; }      // (contexts may differ in their knobs)
     return cache;
 }
 
@@ -1399,72 +1453,101 @@ int prepare_job(fxg_ctx* c, fxg_job* J, std::string& err, fxg_counters& ctr) {
     std::memset(P.level_mask, 0, sizeof P.level_mask);
     P.max_depth = 0;
     double const ratio = J->cfg.extra_verification_ratio;
-    std::vector<ConfigCacheEntry>& cache = thread_config_cache();
-    std::vector<uint8_t> memo;
-    // a PEX tree is a function of the read's length and the batch's parameters: reads of equal length have equal trees, and
-    // the records of an equal tree are copied instead of rebuilt (the trees are compared, not assumed equal)
-    std::unordered_map<uint64_t, uint32_t> first_of_shape;
+    // where every read's records go
     uint32_t node_at = 0, leaf_at = 0, walk_at = 0;
     for (size_t ri = 0; ri < n_reads; ++ri) {
         fxg_read const& R = J->reads_p[ri];
-        const fxg_pex_node* inner = J->nodes_p + R.node_offset;
-        const fxg_pex_node* leaves = inner + R.num_inner;
         ReadRec& rr = rrec[ri];
         rr.walk_begin = walk_at; rr.n_forward = R.num_anchors_forward; rr.node_base = node_at; rr.leaf_base = leaf_at;
-        rr.qoff_forward = R.query_offset; rr.qoff_reverse = J->pool_len + R.query_offset;
-        fxg_pex_node const& root = R.num_inner ? inner[0] : leaves[0];
-        rr.root_from = uint32_t(root.query_index_from); rr.root_m = uint32_t(root.query_index_to - root.query_index_from + 1); rr.root_k = uint32_t(root.num_errors);
-        uint64_t const base = uint64_t(rr.root_m) + 2ull * rr.root_k + 1;
-        uint64_t const extra = ratio == 0.0 ? 0 : ceil_eps(double(base) * ratio);
-        if (extra >= (1u << 30)) return FXG_OK;
-        rr.root_extra = uint32_t(extra);
-        rr.member = 0; rr.n_walks = R.num_anchors_forward + R.num_anchors_reverse; rr.reserved0 = rr.reserved1 = 0;
-        uint64_t const shape = (uint64_t(R.query_len) << 32) ^ (uint64_t(R.num_inner) << 16) ^ R.num_leaves;
-        auto const ins = first_of_shape.emplace(shape, uint32_t(ri));
-        bool copied = false;
-        if (!ins.second) {
-            fxg_read const& Q = J->reads_p[ins.first->second];
-            if (Q.num_inner == R.num_inner && Q.num_leaves == R.num_leaves &&
-                std::memcmp(J->nodes_p + Q.node_offset, inner, (size_t(R.num_inner) + R.num_leaves) * sizeof(fxg_pex_node)) == 0) {
-                ReadRec const& qr = rrec[ins.first->second];
-                std::memcpy(nrec + node_at, nrec + qr.node_base, size_t(R.num_inner) * sizeof(NodeRec));
-                std::memcpy(lrec + leaf_at, lrec + qr.leaf_base, size_t(R.num_leaves) * sizeof(LeafRec));
-                copied = true;
-            }
-        }
-        if (!copied) {
-            memo.assign(R.num_inner, 0xff);
-            for (uint32_t q = 0; q < R.num_inner; ++q) {
-                fxg_pex_node const& nd = inner[q];
-                NodeRec& r = nrec[node_at + q];
-                r.from = uint32_t(nd.query_index_from); r.m = uint32_t(nd.query_index_to - nd.query_index_from + 1); r.k = uint32_t(nd.num_errors);
-                r.parent = nd.parent_id == FXG_NULL_ID ? uint16_t(0) : uint16_t(nd.parent_id);
-                r.depth = node_dist(inner, memo, q);
-                Pass p;
-                uint64_t const n_full = uint64_t(r.m) + 2ull * r.k + 1;
-                if (!score_pass_for(0, 0, uint32_t(n_full), r.m, r.k, 0, p)) return FXG_OK;
-                Config cf;
-                if (!cached_config(cache, p, c->smem_limit, cf)) return FXG_OK;
-                uint32_t const W = uint32_t(kWidths[cf.widx]);
-                int const ci = class_of(c, cf, (r.m + 32 * W - 1) / (32 * W) * W);
-                if (ci < 0) return FXG_OK;
-                r.cls = uint8_t(ci);
-                if (q > 0) {                                       // the root is not an inner level
-                    P.level_mask[r.depth] |= 1u << ci;
-                    P.max_depth = std::max<uint32_t>(P.max_depth, r.depth);
+        rr.n_walks = R.num_anchors_forward + R.num_anchors_reverse;
+        node_at += R.num_inner; leaf_at += R.num_leaves; walk_at += rr.n_walks;
+    }
+    // the records themselves: large jobs on several threads, each over a range of reads
+    struct ChunkOut { uint32_t level_mask[256]; uint32_t max_depth; int status; };   // status: 0 fine, 1 not for the device path
+    auto fill = [&](size_t r_lo, size_t r_hi, ChunkOut& out) {
+        std::memset(out.level_mask, 0, sizeof out.level_mask); out.max_depth = 0; out.status = 0;
+        std::vector<ConfigCacheEntry>& cache = thread_config_cache(c);
+        std::vector<uint8_t> memo;
+        // a PEX tree is a function of the read's length and the batch's parameters: reads of equal length have equal trees, and
+        // the records of an equal tree are copied instead of rebuilt (the trees are compared, not assumed equal)
+        std::unordered_map<uint64_t, uint32_t> first_of_shape;
+        for (size_t ri = r_lo; ri < r_hi; ++ri) {
+            fxg_read const& R = J->reads_p[ri];
+            const fxg_pex_node* inner = J->nodes_p + R.node_offset;
+            const fxg_pex_node* leaves = inner + R.num_inner;
+            ReadRec& rr = rrec[ri];
+            rr.qoff_forward = R.query_offset; rr.qoff_reverse = J->pool_len + R.query_offset;
+            fxg_pex_node const& root = R.num_inner ? inner[0] : leaves[0];
+            rr.root_from = uint32_t(root.query_index_from); rr.root_m = uint32_t(root.query_index_to - root.query_index_from + 1); rr.root_k = uint32_t(root.num_errors);
+            uint64_t const base = uint64_t(rr.root_m) + 2ull * rr.root_k + 1;
+            uint64_t const extra = ratio == 0.0 ? 0 : ceil_eps(double(base) * ratio);
+            if (extra >= (1u << 30)) { out.status = 1; return; }
+            rr.root_extra = uint32_t(extra);
+            rr.member = 0; rr.reserved0 = rr.reserved1 = 0;
+            uint64_t const shape = (uint64_t(R.query_len) << 32) ^ (uint64_t(R.num_inner) << 16) ^ R.num_leaves;
+            auto const ins = first_of_shape.emplace(shape, uint32_t(ri));
+            bool copied = false;
+            if (!ins.second) {
+                fxg_read const& Q = J->reads_p[ins.first->second];
+                if (Q.num_inner == R.num_inner && Q.num_leaves == R.num_leaves &&
+                    std::memcmp(J->nodes_p + Q.node_offset, inner, (size_t(R.num_inner) + R.num_leaves) * sizeof(fxg_pex_node)) == 0) {
+                    ReadRec const& qr = rrec[ins.first->second];
+                    std::memcpy(nrec + rr.node_base, nrec + qr.node_base, size_t(R.num_inner) * sizeof(NodeRec));
+                    std::memcpy(lrec + rr.leaf_base, lrec + qr.leaf_base, size_t(R.num_leaves) * sizeof(LeafRec));
+                    copied = true;
                 }
             }
-            for (uint32_t q = 0; q < R.num_leaves; ++q) {
-                lrec[leaf_at + q].from = uint32_t(leaves[q].query_index_from);
-                lrec[leaf_at + q].parent = leaves[q].parent_id == FXG_NULL_ID ? kNoParent : uint32_t(leaves[q].parent_id);
+            if (!copied) {
+                memo.assign(R.num_inner, 0xff);
+                for (uint32_t q = 0; q < R.num_inner; ++q) {
+                    fxg_pex_node const& nd = inner[q];
+                    NodeRec& r = nrec[rr.node_base + q];
+                    r.from = uint32_t(nd.query_index_from); r.m = uint32_t(nd.query_index_to - nd.query_index_from + 1); r.k = uint32_t(nd.num_errors);
+                    r.parent = nd.parent_id == FXG_NULL_ID ? uint16_t(0) : uint16_t(nd.parent_id);
+                    r.depth = node_dist(inner, memo, q);
+                    Pass p;
+                    uint64_t const n_full = uint64_t(r.m) + 2ull * r.k + 1;
+                    if (!score_pass_for(0, 0, uint32_t(n_full), r.m, r.k, 0, p)) { out.status = 1; return; }
+                    Config cf;
+                    if (!cached_config(cache, p, c->smem_limit, c->force_wide, cf)) { out.status = 1; return; }
+                    uint32_t const W = uint32_t(kWidths[cf.widx]);
+                    int const ci = class_of(c, cf, (r.m + 32 * W - 1) / (32 * W) * W);
+                    if (ci < 0) { out.status = 1; return; }
+                    r.cls = uint8_t(ci);
+                    if (q > 0) {                                   // the root is not an inner level
+                        out.level_mask[r.depth] |= 1u << ci;
+                        out.max_depth = std::max<uint32_t>(out.max_depth, r.depth);
+                    }
+                }
+                for (uint32_t q = 0; q < R.num_leaves; ++q) {
+                    lrec[rr.leaf_base + q].from = uint32_t(leaves[q].query_index_from);
+                    lrec[rr.leaf_base + q].parent = leaves[q].parent_id == FXG_NULL_ID ? kNoParent : uint32_t(leaves[q].parent_id);
+                }
+            }
+            const fxg_anchor* an = J->anchors_p + R.anchor_offset;
+            AnchorRec16* const dst = arec + rr.walk_begin;
+            for (uint32_t q = 0; q < rr.n_walks; ++q) {
+                dst[q].reference_position = an[q].reference_position; dst[q].pex_leaf_index = uint32_t(an[q].pex_leaf_index); dst[q].reference_id = uint32_t(an[q].reference_id);
             }
         }
-        const fxg_anchor* an = J->anchors_p + R.anchor_offset;
-        for (uint32_t q = 0; q < rr.n_walks; ++q) {
-            AnchorRec16& a = arec[walk_at + q];
-            a.reference_position = an[q].reference_position; a.pex_leaf_index = uint32_t(an[q].pex_leaf_index); a.reference_id = uint32_t(an[q].reference_id);
+    };
+    size_t const n_threads = n_walks < (uint64_t(1) << 19) ? 1 : std::min<size_t>({size_t(8), n_reads, std::max<size_t>(1, std::thread::hardware_concurrency() / 2)});
+    std::vector<ChunkOut> outs(n_threads);
+    if (n_threads == 1) fill(0, n_reads, outs[0]);
+    else {
+        std::vector<std::thread> threads;
+        for (size_t t = 0; t < n_threads; ++t) {
+            // (ranges with similar numbers of anchors)
+            auto cut = [&](size_t q) { uint64_t const target = n_walks * q / n_threads; size_t lo = 0, hi = n_reads; while (lo < hi) { size_t const mid = (lo + hi) / 2; if (rrec[mid].walk_begin < target) lo = mid + 1; else hi = mid; } return lo; };
+            size_t const r_lo = t == 0 ? 0 : cut(t), r_hi = t + 1 == n_threads ? n_reads : cut(t + 1);
+            threads.emplace_back(fill, r_lo, r_hi, std::ref(outs[t]));
         }
-        node_at += R.num_inner; leaf_at += R.num_leaves; walk_at += rr.n_walks;
+        for (auto& th : threads) th.join();
+    }
+    for (ChunkOut const& o : outs) {
+        if (o.status) return FXG_OK;
+        for (int d = 0; d < 256; ++d) P.level_mask[d] |= o.level_mask[d];
+        P.max_depth = std::max(P.max_depth, o.max_depth);
     }
     P.n_nodes = node_at; P.n_leaves = leaf_at; P.n_walks = walk_at; P.n_reads = uint32_t(n_reads);
     P.hreads.assign(rrec, rrec + n_reads);
@@ -1607,7 +1690,8 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
         for (int ci = 0; ci < n_cls; ++ci) {
             if (!(mask >> ci & 1u)) continue;
             ClassDef const& K = classes[ci];
-            uint32_t const tpw = 32u / K.G;
+            bool const wide = K.G == kWideG;
+            uint32_t const tpw = wide ? 1u : 32u / K.G;
             DpLaunch L{};
             L.tasks = C.tasks; L.n_tasks = n_walks; L.n_tasks_dev = C.counts + ci; L.class_active = C.class_active; L.cls = uint32_t(ci);
             L.group = K.G; L.win_stride = kWinBytes; L.two = 2;
@@ -1616,7 +1700,7 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
             L.ref_packed = c->refs.packed.as<uint32_t>(); L.inline_packed = nullptr;
             L.peq_table = pool.peq.as<uint32_t>(); L.peq_plane_words = pool.plane_words;
             L.results = reinterpret_cast<DpResult*>(D + o_results); L.trace = nullptr;
-            size_t const smem = size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
+            size_t const smem = wide ? wide_smem_bytes() : size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
             if (smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", smem);
             cudaStream_t s2 = st;
             if (n_launch > 0) {
@@ -1625,8 +1709,8 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
                 if (n_launch <= Worker::kSide) CUDA_TRY(w.err, cudaStreamWaitEvent(s2, w.ev_fork, 0));
             }
             // (no more CTAs than a few waves of the machine: the CTAs take the task groups in turn)
-            uint32_t const grid = uint32_t(std::min<size_t>((size_t(n_walks) + tpw - 1) / tpw, size_t(c->num_sms) * 32));
-            CUDA_TRY(w.err, launch_dp(K.widx, false, L, grid, smem, s2));
+            uint32_t const grid = uint32_t(std::min<size_t>((size_t(n_walks) + tpw - 1) / tpw, size_t(c->num_sms) * (wide ? 2 : 32)));
+            CUDA_TRY(w.err, launch_dp(wide ? -1 : int(K.widx), false, L, grid, smem, s2));
             w.ctr.kernel_launches++;
             ++n_launch;
         }
@@ -2105,11 +2189,13 @@ int fxg_create(int device, fxg_ctx** out) {
     bool ok = cudaStreamCreateWithFlags(&c->stage_stream, cudaStreamNonBlocking) == cudaSuccess && set_all_smem_attrs(c->smem_limit) == cudaSuccess;
     c->root_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64);
     c->infer_inner = env_int("FXG_INFER_INNER", 1, 0, 1) != 0;
+    c->force_wide = env_int("FXG_FORCE_WIDE", 0, 0, 1) != 0;
     c->share_root_passes = env_int("FXG_SHARE_ROOTS", 1, 0, 1) != 0;
     c->device_levels = env_int("FXG_DEVICE_LEVELS", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
     c->n_groups = env_int("FXG_GROUPS", 4, 1, fxg_ctx::kMaxGroups);
     c->merge_max_jobs = env_int("FXG_MERGE_JOBS", 64, 1, 4096);
+    c->merge_wait_us = env_int("FXG_MERGE_WAIT_US", 300, 0, 1000000);
     c->merge_max_walks = uint64_t(env_int("FXG_MERGE_WALKS", 6 << 20, 1, int(kMaxDeviceWalks - 1)));
     c->workers_busy = default_workers(c->n_groups);
     // a batch that runs alone is split over 8 workers; the lowest free group is taken, so that is always group 0 and only
@@ -2491,6 +2577,7 @@ namespace {
 struct Ticket {
     fxg_job* J = nullptr;
     int state = 0;                       // 0 waiting, 1 taken by a batch, 2 done
+    bool waited = false;                 // has spent its accumulation window (submit_and_wait)
     int rc = FXG_OK; std::string err;
     std::shared_ptr<TicketResults> shared; size_t al_begin = 0, al_end = 0; uint32_t read0 = 0; fxg_stats stats{};
 };
@@ -2601,6 +2688,15 @@ int submit_and_wait(fxg_ctx* c, fxg_job* J, std::unique_lock<std::mutex>& lock) 
     c->pending.push_back(&T);
     for (;;) {
         if (T.state == 2) break;
+        if (T.state == 0 && !T.waited && c->merge_wait_us > 0 && c->merge_max_jobs > 1) {
+            // while other batches run, the jobs of the callers they will release arrive within a few hundred microseconds of
+            // each other: a short wait lets them travel together instead of one by one (a call that finds the context
+            // idle starts at once)
+            int busy = 0;
+            for (int i = 0; i < c->n_groups; ++i) busy += c->groups[i].busy;
+            T.waited = true;
+            if (busy > 0) { c->cv.wait_for(lock, std::chrono::microseconds(c->merge_wait_us)); continue; }
+        }
         WorkerGroup* g = T.state == 0 ? try_acquire_group(c) : nullptr;
         if (!g) { c->cv.wait(lock); continue; }
         std::vector<Ticket*> mine{&T};

@@ -315,6 +315,76 @@ def test_sharing_knobs_do_not_change_results(gpu, monkeypatch):
     assert len(results[0][0]) > 0
 
 
+# ----------------------------------------------------------------------------- bands wider than one warp's ring
+
+def test_wide_kernel_matches_oracle_at_small_sizes(gpu, oracle, monkeypatch):
+    """FXG_FORCE_WIDE=1 sends every pass to the multi-warp kernel (dp_wide_kernel), so that it meets the oracle on many
+    random tasks in all three modes (incl. clipped windows, k = 0, inline references with all six ranks) and on whole reads."""
+    monkeypatch.setenv("FXG_FORCE_WIDE", "1")
+    c2 = gpu.Context(0)
+    try:
+        for mode in (abi.MODE_EXISTS, abi.MODE_NO_CIGAR, abi.MODE_CIGAR):
+            for m_range, err_range, n_tasks in (((1, 60), (0.0, 0.3), 120), ((100, 900), (0.0, 0.15), 80), ((900, 2600), (0.02, 0.12), 30)):
+                rng = np.random.default_rng(977 + 17 * mode + m_range[0])
+                ref, tasks, pool = random_align_tasks(rng, n_tasks, m_range, err_range, mode, ref_len=40_000)
+                c2.set_references([ref])
+                res, cig = c2.align_batch(tasks, pool)
+                got = results_as_tuples(res, cig, tasks)
+                want = oracle_align_tasks(oracle, ref, tasks, pool)
+                bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+                assert not bad, (mode, m_range, bad[:5], [(got[i], want[i], tasks[i]) for i in bad[:2]])
+        refs = [synthetic.random_reference(100_000, 5)]
+        c2.set_references(refs)
+        batch = synthetic.make_batch(refs, 5, 1300, 0.07, 41, gpu.pex_build, seed_errors=1, decoy_fraction=0.3)
+        for cfg in (VerifyConfig(), VerifyConfig(interval_optimization=True), VerifyConfig(without_cigar=True)):
+            job = c2.verify_reads(batch, cfg)
+            al, cg = job.alignments()
+            want, want_stats = oracle_verify_batch(oracle, refs, batch, cfg)
+            assert alignment_records(al, cg) == want and job.stats() == want_stats
+            assert len(want) > 0
+            job.free()
+    finally:
+        c2.close()
+
+
+@pytest.mark.parametrize("error_rate", [0.05, 0.10, 0.15])
+def test_reads_at_the_length_limit(ctx, gpu, error_rate):
+    """A 100 kbp read (input.hpp:42) at 5, 10 and 15 %: root bands of 31 000 .. 73 000 diagonals, which no ring of one
+    warp holds (the multi-warp kernel takes them).  Alignment in all three modes and the whole read through verify_reads;
+    the CPU port (bit-vector, checked against the plain-DP oracle in the CPU suite) is the checker at this size."""
+    from oracle import cpu_baseline
+    rng = np.random.default_rng(int(error_rate * 1000))
+    m = 100_000
+    ref = synthetic.random_reference(400_000, 31)
+    k = int(np.ceil(m * error_rate))
+    read, _, _ = synthetic.simulate_read(rng, ref, 150_000, m - 2000, int((m - 2000) * error_rate * 0.9))
+    read = read[:m]
+    extra = synthetic.ceil_eps((len(read) + 2 * k + 1) * 0.05)
+    n = len(read) + 2 * k + 1 + 2 * extra
+    at = 150_000 - k - extra
+    tasks = np.array([(at, at, 0, n, len(read), 0, k, mode, 0, (0,) * 6) for mode in (abi.MODE_EXISTS, abi.MODE_NO_CIGAR, abi.MODE_CIGAR)], dtype=abi.ALIGN_TASK_DTYPE)
+    ctx.set_references([ref])
+    res, cig = ctx.align_batch(tasks, read)
+    cres, ccig = cpu_baseline.align_batch([ref], tasks, read, threads=3)
+    assert results_as_tuples(res, cig, tasks) == results_as_tuples(cres, ccig, tasks)
+    assert res["exists"].all()
+    # the same read with its tree and a handful of anchors
+    inner, leaves = gpu.pex_build(len(read), k, 2, 0)
+    ok = [li for li, lf in enumerate(leaves) if True][:: max(1, len(leaves) // 12)]
+    # (ground truth is not tracked here: anchors at the diagonal of the simulated locus; most leaves carry too many edits,
+    #  which is the common case for a real seeder as well -- the walks that fail at an inner level are part of the test)
+    af = np.array([(li, 0, min(len(ref) - 1, 150_000 + int(leaves[li]["query_index_from"])), 0) for li in ok], dtype=abi.ANCHOR_DTYPE)
+    bb = BatchBuilder()
+    bb.add(read, revcomp(read), inner, leaves, af, np.zeros(0, dtype=abi.ANCHOR_DTYPE))
+    batch = bb.build()
+    cfg = VerifyConfig(interval_optimization=True)
+    job = ctx.verify_reads(batch, cfg)
+    al, cg = job.alignments()
+    wal, wcg, wstats = cpu_baseline.verify_reads([ref], batch, cfg, threads=4)
+    assert alignment_records(al, cg) == alignment_records(wal, wcg) and job.stats() == wstats
+    job.free()
+
+
 def test_config2_shape_against_cpu_port(ctx, gpu):
     """5 kbp reads at 5 % (config 2 shape, fewer reads): the bit-vector CPU port (itself checked against the
     oracle in the CPU suite) is the checker at this size."""
