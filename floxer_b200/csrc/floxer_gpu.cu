@@ -314,6 +314,7 @@ struct fxg_ctx {
     std::condition_variable cv;
     uint64_t merge_max_walks = uint64_t(6) << 20;   // FXG_MERGE_WALKS: anchors of a merged batch at most (a single job may be larger)
     int merge_max_jobs = 64;                        // FXG_MERGE_JOBS (1 = never merge)
+    int merged_parts = 1;                           // FXG_MERGED_PARTS: host workers (and launch sets) of a merged batch
     int merge_wait_us = 300;                        // FXG_MERGE_WAIT_US: how long a job waits for company while other batches run
     std::mutex class_mu;
     ClassDef classes[kMaxLevelClasses];
@@ -375,8 +376,8 @@ struct fxg_job {
     std::vector<fxg_alignment> alignments;
     PinnedBuf cigars;                    // page-locked; every worker's cigars arrive here directly from the device
     size_t cigars_len = 0;
-    // a job that ran merged with others reads its cigars out of the batch's pool (kept alive by `shared`)
-    std::shared_ptr<PinnedBuf> shared; const uint32_t* shared_cigars = nullptr;
+    std::vector<uint32_t> cigars_copy;   // a job that ran merged with others copies its cigars out of the batch's pool
+    bool use_copy = false;
     fxg_stats stats{};
     bool ran = false;
 };
@@ -1168,6 +1169,20 @@ void give_pinned(fxg_ctx* c, PinnedBuf& b) {
     if (b.p && c->spare_pinned.size() < size_t(2 * c->n_groups + 8)) c->spare_pinned.push_back(b); else b.release();
     b = PinnedBuf{};
 }
+// the smallest spare pool that holds `bytes`, else the largest (it will grow)
+PinnedBuf take_pinned_fit(fxg_ctx* c, size_t bytes) {
+    PinnedBuf b;
+    if (c->spare_pinned.empty()) return b;
+    size_t best = SIZE_MAX, largest = 0;
+    for (size_t i = 0; i < c->spare_pinned.size(); ++i) {
+        if (c->spare_pinned[i].cap >= bytes && (best == SIZE_MAX || c->spare_pinned[i].cap < c->spare_pinned[best].cap)) best = i;
+        if (c->spare_pinned[i].cap > c->spare_pinned[largest].cap) largest = i;
+    }
+    size_t const pick = best != SIZE_MAX ? best : largest;
+    b = c->spare_pinned[pick];
+    c->spare_pinned.erase(c->spare_pinned.begin() + long(pick));
+    return b;
+}
 PinnedBuf take_staging(fxg_ctx* c) {
     PinnedBuf b;
     if (!c->spare_staging.empty()) { b = c->spare_staging.back(); c->spare_staging.pop_back(); }
@@ -1388,6 +1403,7 @@ struct PartState {
     std::chrono::steady_clock::time_point t0;
     double cpu0 = 0;                         // the part's thread CPU time at its start (FXG_PROFILE)
     std::vector<ReadRec> part_reads;         // (device-side walks) the part's ReadRecs as the device sees them
+    std::vector<fxg_alignment> hits;         // the part's alignments in anchor order, cigar offsets relative to the part's region
     PartOut out;
 };
 
@@ -1570,10 +1586,10 @@ inline Span root_span_of(ReadRec const& R, int64_t diag, uint64_t ref_len) {
     return r;
 }
 
-// The tree walks of reads [r0, r1) of a batch on the device.  On return P.walks holds one Walk per anchor that verifies
-// its root (in anchor order, level[0] lists them all), and the statistics of the inner levels and of the interval
-// optimisation have been added to P.out.stats per member.
-int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, PartState& P, std::vector<std::vector<uint32_t>>& level) {
+// query_verifier::verify() for every anchor of reads [r0, r1) of a batch: the tree walks on the device, then the root
+// level for the walks that verify their root.  On return P.hits holds the part's alignments in anchor order, and the
+// statistics have been added to P.out.stats per member.
+int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, PartState& P) {
     g_prof.start(w);
     PartOut& out = P.out;
     cudaStream_t const st = w.stream;
@@ -1601,8 +1617,7 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
         slices.push_back(s);
     }
     uint32_t const n_reads = r1 - r0;
-    P.walks.clear();
-    level.assign(1, std::vector<uint32_t>());
+    P.walks.clear(); P.hits.clear();
     if (n_walks == 0) return FXG_OK;
     bool const ivopt = B.cfg.interval_optimization != 0;
     bool const direct = B.cfg.verification_kind == FXG_KIND_DIRECT_FULL;
@@ -1801,8 +1816,11 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     CUDA_TRY(w.err, w.wait_for(st));
     w.ctr.d2h_bytes += size_t(n_roots) * sizeof(RootEntry);
     const RootEntry* const re = w.h_roots.as<RootEntry>();
-    P.walks.resize(n_roots);
-    level[0].resize(n_roots);
+    g_prof.lap(w, 9);
+    // ---- root level (verification.cpp:52-64, 95-109): one score pass per walk that verifies its root, straight from the entries ----
+    std::vector<Pass> passes; std::vector<uint32_t> root_k, pass_read, pass_ref; std::vector<uint64_t> span_off; std::vector<uint32_t> span_len; std::vector<uint8_t> pass_orient;
+    passes.reserve(n_roots); root_k.reserve(n_roots); pass_read.reserve(n_roots); pass_ref.reserve(n_roots); span_off.reserve(n_roots); span_len.reserve(n_roots); pass_orient.reserve(n_roots);
+    bool const want_cigar = !B.cfg.without_cigar;
     uint32_t cur = 0;                                          // read of the entry at hand (entries come in walk order)
     for (uint32_t q = 0; q < n_roots; ++q) {
         RootEntry const& e = re[q];
@@ -1810,15 +1828,45 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
         ReadRec const& R = P.part_reads[cur];
         if (e.walk < R.walk_begin || e.walk >= R.walk_begin + R.n_walks || e.ref_id >= c->refs.len.size())
             return fail(w.err, FXG_ERR_CUDA, "internal: a root walk outside its read");
-        Walk& wk = P.walks[q];
-        wk = Walk{};
-        wk.read = r0 + cur; wk.anchor = e.walk - R.walk_begin; wk.orient = e.walk - R.walk_begin >= R.n_forward ? 1 : 0;
-        wk.state = W_WALKING; wk.ref_id = e.ref_id; wk.member = R.member;
-        wk.root_span = root_span_of(R, e.diag, c->refs.len[e.ref_id]); wk.have_root_span = true;
-        wk.rm = R.root_m; wk.rk = R.root_k; wk.rqbase = (wk.orient ? R.qoff_reverse : R.qoff_forward) + R.root_from;
-        level[0][q] = q;
+        uint32_t const orient = e.walk - R.walk_begin >= R.n_forward ? 1u : 0u;
+        Span const sp = root_span_of(R, e.diag, c->refs.len[e.ref_id]);
+        fxg_stats& S = out.stats[R.member];
+        S.n_aligned_root++; S.sum_aligned_root += sp.length; S.cells_root += uint64_t(R.root_m) * sp.length;
+        Pass p;
+        if (score_pass_for(c->refs.base[e.ref_id] + sp.offset, (orient ? R.qoff_reverse : R.qoff_forward) + R.root_from, uint32_t(sp.length), R.root_m, R.root_k,
+                           want_cigar ? 0u : kFlagReverse, p)) {
+            passes.push_back(p); root_k.push_back(R.root_k); pass_read.push_back(r0 + cur); pass_ref.push_back(e.ref_id);
+            span_off.push_back(sp.offset); span_len.push_back(uint32_t(sp.length)); pass_orient.push_back(uint8_t(orient));
+        }
     }
-    g_prof.lap(w, 9);
+    g_prof.lap(w, 2);
+    if (passes.empty()) return FXG_OK;
+    auto hit = [&](size_t q, uint64_t start, uint32_t errors, uint64_t cigar_offset, uint32_t cigar_len) {
+        fxg_alignment a{};
+        a.start_in_reference = start; a.cigar_offset = cigar_offset; a.cigar_len = cigar_len;       // (the offset is relative to this part's region for now)
+        a.num_errors = errors; a.read_index = pass_read[q]; a.reference_id = pass_ref[q]; a.orientation = pass_orient[q];
+        P.hits.push_back(a);
+    };
+    if (want_cigar) {
+        // score pass with checkpoints, then the traceback of the accepted ones
+        std::vector<RootOut> root_outs;
+        int const rc = run_root_passes(c, w, pool, passes, root_k, P.trace_budget, root_outs);
+        if (rc != FXG_OK) return rc;
+        g_prof.start(w);
+        P.hits.reserve(passes.size());
+        for (size_t q = 0; q < passes.size(); ++q)
+            if (root_outs[q].score <= int32_t(root_k[q]))
+                hit(q, span_off[q] + root_outs[q].begin_col, uint32_t(root_outs[q].score), root_outs[q].cigar_offset, root_outs[q].cigar_len);   // alignment.cpp:175
+    } else {
+        const DpResult* res = nullptr;
+        int const rc = run_passes(c, w, pool, passes, nullptr, nullptr, &res);
+        if (rc != FXG_OK) return rc;
+        g_prof.start(w);
+        for (size_t q = 0; q < passes.size(); ++q)
+            if (res[q].score <= int32_t(root_k[q])) hit(q, span_off[q] + (span_len[q] - res[q].end_col), uint32_t(res[q].score), 0, 0);                // alignment.cpp:135-139
+    }
+    w.ctr.waves++;
+    g_prof.lap(w, 13);
     return FXG_OK;
 }
 
@@ -1857,8 +1905,8 @@ void verify_part_score(fxg_ctx* c, Worker& w, Batch& B, uint32_t read_lo, uint32
     bool const on_device = B.device;
     if (on_device) {
         walks.clear(); groups.clear(); group_members.clear();
-        out.rc = run_device_walks(c, w, B, read_lo, read_hi, P, level);
-        if (out.rc != FXG_OK) return;
+        out.rc = run_device_walks(c, w, B, read_lo, read_hi, P);
+        return;
     } else {
         // (fxg_verify_reads) the query pools and their Peq planes were enqueued on the staging stream by the caller's thread
         if (J->pool_ready && cudaStreamWaitEvent(w.stream, J->pool_ready, 0) != cudaSuccess) { out.rc = fail(w.err, FXG_ERR_CUDA, "cannot order the worker behind the upload"); return; }
@@ -2108,17 +2156,18 @@ void verify_part_finish(fxg_ctx* c, Worker& w, uint32_t* host_cigars, uint64_t r
     out.rc = fetch_cigars(w, host_cigars);
     g_prof.lap(w, 15);
     if (out.rc != FXG_OK) return;
-    for (Walk& wk : P.walks) if (wk.hit && wk.cigar_len) wk.cigar_offset += region_base;
     // ---- emit in anchor order (= insertion order of the reference's single-thread run) ----
     g_prof.start(w);
-    for (Walk const& wk : P.walks) {
+    for (Walk const& wk : P.walks) {                       // (host-driven levels; the device path has filled P.hits itself)
         if (!wk.hit) continue;
         fxg_alignment a{};
         a.start_in_reference = wk.start_in_reference; a.cigar_offset = wk.cigar_offset; a.cigar_len = wk.cigar_len;
         a.num_errors = wk.num_errors; a.read_index = wk.read; a.reference_id = wk.ref_id;
         a.orientation = wk.orient;
-        out.alignments.push_back(a);
+        P.hits.push_back(a);
     }
+    for (fxg_alignment& a : P.hits) if (a.cigar_len) a.cigar_offset += region_base;
+    out.alignments.swap(P.hits);
     g_prof.lap(w, 13);
     if (g_prof.on) fprintf(stderr, "[fxg] worker %d: %zu walks, %.3f ms (%.3f ms of CPU), %llu waves\n", w.id, P.walks.size(),
                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count(), thread_cpu_ms() - P.cpu0,
@@ -2132,6 +2181,7 @@ struct TracePlan {
     size_t arrived = 0, n_parts = 0;
     std::vector<uint64_t> caps, bases;
     PinnedBuf* pool = nullptr; size_t* pool_len = nullptr;
+    fxg_ctx* ctx = nullptr;
     bool failed = false; std::string err;
     void arrive_and_wait(size_t part, uint64_t cap) {
         std::unique_lock<std::mutex> lock(mu);
@@ -2139,7 +2189,13 @@ struct TracePlan {
         if (++arrived == n_parts) {
             uint64_t total = 0;
             for (size_t p = 0; p < n_parts; ++p) { bases[p] = total; total += caps[p]; }
-            cudaError_t const e = pool->ensure(std::max<uint64_t>(total, 1) * 4);
+            size_t const need = std::max<uint64_t>(total, 1) * 4;
+            if (pool->cap < need && ctx) {               // a pool of the right size from the context's spares, if there is one
+                std::lock_guard<std::mutex> ctx_lock(ctx->mu);
+                PinnedBuf fit = take_pinned_fit(ctx, need);
+                if (fit.p) { give_pinned(ctx, *pool); *pool = fit; }
+            }
+            cudaError_t const e = pool->ensure(need);
             if (e != cudaSuccess) { failed = true; err = std::string("cigar pool allocation: ") + cudaGetErrorString(e); }
             *pool_len = size_t(total);
             cv.notify_all();
@@ -2196,6 +2252,7 @@ int fxg_create(int device, fxg_ctx** out) {
     c->n_groups = env_int("FXG_GROUPS", 4, 1, fxg_ctx::kMaxGroups);
     c->merge_max_jobs = env_int("FXG_MERGE_JOBS", 64, 1, 4096);
     c->merge_wait_us = env_int("FXG_MERGE_WAIT_US", 300, 0, 1000000);
+    c->merged_parts = env_int("FXG_MERGED_PARTS", 1, 1, 64);
     c->merge_max_walks = uint64_t(env_int("FXG_MERGE_WALKS", 6 << 20, 1, int(kMaxDeviceWalks - 1)));
     c->workers_busy = default_workers(c->n_groups);
     // a batch that runs alone is split over 8 workers; the lowest free group is taken, so that is always group 0 and only
@@ -2480,7 +2537,9 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
 
     // ---- split the reads into contiguous parts with similar numbers of anchors, one part per worker ----
     std::vector<uint32_t> const& rwb = B.read_walk_begin;
-    size_t const n_parts = std::min<size_t>(grp.use_workers, std::max<size_t>(1, std::min<size_t>(n_reads, size_t(rwb[n_reads]) / 4096 + 1)));
+    // (a batch merged from several callers' jobs runs as few parts as possible: its point is launches that fill the machine)
+    size_t const max_parts = B.members.size() > 1 ? std::min<size_t>(grp.use_workers, size_t(c->merged_parts)) : grp.use_workers;
+    size_t const n_parts = std::min<size_t>(max_parts, std::max<size_t>(1, std::min<size_t>(n_reads, size_t(rwb[n_reads]) / 4096 + 1)));
     std::vector<uint32_t> cut(n_parts + 1, 0);
     for (size_t p = 1; p < n_parts; ++p) {
         uint64_t const target = uint64_t(rwb[n_reads]) * p / n_parts;
@@ -2491,7 +2550,7 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     std::vector<PartState> parts(n_parts);
     TracePlan plan;
     plan.n_parts = n_parts; plan.caps.assign(n_parts, 0); plan.bases.assign(n_parts, 0);
-    plan.pool = B.cigars; plan.pool_len = &B.cigars_len;
+    plan.pool = B.cigars; plan.pool_len = &B.cigars_len; plan.ctx = c;
     auto const vt0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - vt0).count(); };
     uint64_t const budget = trace_budget_bytes(c, n_parts);
@@ -2633,7 +2692,7 @@ void run_tickets(fxg_ctx* c, WorkerGroup& grp, std::vector<Ticket*> const& mine,
             J->alignments = std::move(B.alignments);
             std::swap(J->cigars, pinned);                // (the job's previous pool goes back to the context with `pinned`)
             J->cigars_len = B.cigars_len; J->stats = B.stats[0];
-            J->shared.reset(); J->shared_cigars = nullptr;
+            J->use_copy = false;
             mine[lo]->rc = FXG_OK;
             return FXG_OK;
         }
@@ -2659,7 +2718,6 @@ void run_tickets(fxg_ctx* c, WorkerGroup& grp, std::vector<Ticket*> const& mine,
     if (run_some(0, mine.size()) != FXG_OK && mine.size() > 1) {
         // one bad job must not fail its neighbours: each on its own
         for (size_t i = 0; i < mine.size(); ++i) {
-            if (!pinned.p) { std::lock_guard<std::mutex> lock(c->mu); pinned = take_pinned(c); }
             run_some(i, i + 1);
         }
     }
@@ -2673,8 +2731,9 @@ void take_member_results(fxg_job* J, Ticket& T) {
     for (fxg_alignment const& a : J->alignments) if (a.cigar_len) { lo = std::min(lo, a.cigar_offset); hi = std::max(hi, a.cigar_offset + a.cigar_len); }
     if (lo == UINT64_MAX) lo = hi = 0;
     for (fxg_alignment& a : J->alignments) { a.read_index -= T.read0; if (a.cigar_len) a.cigar_offset -= lo; }
-    J->shared = T.shared->cigars;
-    J->shared_cigars = T.shared->cigars->as<uint32_t>() + lo;
+    J->cigars_copy.resize(size_t(hi - lo));
+    if (hi > lo) std::memcpy(J->cigars_copy.data(), T.shared->cigars->as<uint32_t>() + lo, size_t(hi - lo) * 4);
+    J->use_copy = true;
     J->cigars_len = size_t(hi - lo);
     J->stats = T.stats;
 }
@@ -2715,7 +2774,7 @@ int submit_and_wait(fxg_ctx* c, fxg_job* J, std::unique_lock<std::mutex>& lock) 
                 } else ++it;
             }
         }
-        PinnedBuf pinned = take_pinned(c);
+        PinnedBuf pinned;                                // (picked from the context's spares when the batch knows how much it needs)
         lock.unlock();
         fxg_counters ctr{};
         run_tickets(c, *g, mine, pinned, ctr);
@@ -2730,6 +2789,7 @@ int submit_and_wait(fxg_ctx* c, fxg_job* J, std::unique_lock<std::mutex>& lock) 
     if (T.shared) {
         lock.unlock();
         take_member_results(J, T);
+        T.shared.reset();                                // (the last member hands the batch's pool back to the context: not under the lock)
         lock.lock();
     }
     J->ran = true;
@@ -2801,12 +2861,11 @@ int fxg_verify_run(fxg_ctx* c, fxg_job* J) {
 size_t fxg_job_num_alignments(const fxg_job* j) { return j ? j->alignments.size() : 0; }
 const fxg_alignment* fxg_job_alignments(const fxg_job* j) { return j ? j->alignments.data() : nullptr; }
 size_t fxg_job_cigar_len(const fxg_job* j) { return j ? j->cigars_len : 0; }
-const uint32_t* fxg_job_cigar_pool(const fxg_job* j) { return j ? (j->shared_cigars ? j->shared_cigars : j->cigars.as<uint32_t>()) : nullptr; }
+const uint32_t* fxg_job_cigar_pool(const fxg_job* j) { return j ? (j->use_copy ? j->cigars_copy.data() : j->cigars.as<uint32_t>()) : nullptr; }
 const fxg_stats* fxg_job_stats(const fxg_job* j) { return j ? &j->stats : nullptr; }
 
 void fxg_job_free(fxg_ctx* c, fxg_job* j) {
     if (!j) return;
-    j->shared.reset();
     if (c) { std::lock_guard<std::mutex> lock(c->mu); cudaSetDevice(c->device); release_job_buffers(c, j); }
     else { j->cigars.release(); j->prep.staging.release(); }
     if (j->prep.ready) cudaEventDestroy(j->prep.ready);
@@ -2865,7 +2924,6 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     }
     // the caller's arrays are not looked at after this point
     j->reads_p = nullptr; j->nodes_p = nullptr; j->anchors_p = nullptr;
-    if (rc != FXG_OK) j->shared.reset();
     lock.lock();
     if (rc != FXG_OK) {
         c->err = err; tls_last_error = err;
