@@ -237,26 +237,45 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
         j.free()
 
     # ---- end-to-end arm: host buffers in, alignments + CIGARs out, every step; every job's records are checked ----
+    want_quick = (len(al0), int(al0["start_in_reference"].sum()), int(al0["num_errors"].sum()), int(al0["cigar_len"].sum()))
+
     def e2e_arm(b):
         mismatches = [0]
+        last = [None] * lanes
 
         def e2e_step(i):
             def f():
                 flush.fill_(2)
                 j2 = ctx.verify_reads(b, cfg)            # host buffers in: H2D, all waves, tracebacks, D2H of alignments + CIGARs
                 a2, c2 = j2.alignments(copy=False)       # what a C caller reads: the job's own result arrays
-                if digest(a2, c2, i % 8 == 0) != (want if i % 8 == 0 else want_fields):
+                # every job is checked where it costs microseconds (the interpreter lock serialises the lanes' Python code);
+                # the last job of every lane is kept, and its records and cigars are compared in full after the region
+                if (len(a2), int(a2["start_in_reference"].sum()), int(a2["num_errors"].sum()), int(a2["cigar_len"].sum())) != want_quick:
                     mismatches[0] += 1
                 del a2, c2
-                j2.free()
+                if last[i] is not None:
+                    last[i].free()
+                last[i] = j2
             return f
+
+        def check_and_free():
+            for i, j2 in enumerate(last):
+                if j2 is not None:
+                    a2, c2 = j2.alignments(copy=False)
+                    if digest(a2, c2, True) != want:
+                        mismatches[0] += 1
+                    del a2, c2
+                    j2.free()
+                    last[i] = None
         run_lanes([e2e_step(i) for i in range(lanes)], 2)        # warm-up (page-locked pools are allocated once)
+        check_and_free()
         barrier()
         ctx.reset_counters()
         t_reg = time.perf_counter()
         s, d = run_lanes([e2e_step(i) for i in range(lanes)], steps)
         barrier()
         sampler.window(t_reg, time.perf_counter())
+        check_and_free()
         if mismatches[0]:
             raise RuntimeError(f"{mismatches[0]} end-to-end jobs returned records that differ from the staged batch's")
         return s, ctx.counters(), step_spread(d, steps)
@@ -294,7 +313,8 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
         "e2e": {"value": cells_step / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "reads_per_s": reads_step / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": e2e_ctr["h2d_bytes"] // steps, "d2h_bytes_per_step": e2e_ctr["d2h_bytes"] // steps,
                 "step_ms_spread": e2e_spread, "inputs": "page-locked host memory",
-                "checked": f"every one of the {n_batches} timed jobs: checksum of its alignment records against the staged batch's; every 8th lane its cigars too"},
+                "checked": f"every one of the {n_batches} timed jobs: number of alignments and the sums of their positions, errors and cigar lengths against the "
+                           f"staged batch's; the last job of every lane: checksum of every record and every cigar's operations"},
         "gpu_launches": int(ctr["kernel_launches"]),
         "roofline": {
             "bound": "int32_alu", "achieved": achieved / 1e9, "peak": int32_peak / 1e9, "unit": "Ginstr/s",
@@ -315,7 +335,8 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
             if int32_peak and ctr["root_launch_ms"] > 0 else None,
             "checkpoint_bytes_per_batch": ctr["trace_bytes"] / n_batches},
         "queue": {"batches": int(ctr["batches"]), "jobs": int(ctr["batch_jobs"]), "jobs_per_batch": ctr["batch_jobs"] / max(ctr["batches"], 1),
-                  "launches_per_job": ctr["kernel_launches"] / max(ctr["batch_jobs"], 1)},
+                  "launches_per_job": ctr["kernel_launches"] / max(ctr["batch_jobs"], 1),
+                  "alloc_ms_in_region": ctr["alloc_ms"], "alloc_calls_in_region": int(ctr["alloc_calls"])},
         "shortcuts_per_batch": {k: ctr[k] / n_batches for k in ("shared_score_passes", "rescored_roots", "inferred_inner", "shared_tracebacks")},
         "batch_latency_alone_ms": [round(x, 3) for x in lat_ms],
         "alignments_per_batch": n_alignments, "stats_per_batch": stats,

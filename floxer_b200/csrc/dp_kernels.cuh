@@ -783,25 +783,31 @@ struct Walk2Launch {
     uint32_t two;
 };
 
-// alignments per walk2 CTA (one lane each) and its block size; wide blocks need so much shared memory per lane that
-// fewer lanes share a CTA
-__host__ __device__ constexpr uint32_t walk2_lanes(uint32_t W) { return W <= 8 ? 64u : (W == 16 ? 32u : 16u); }
-__host__ __device__ constexpr uint32_t walk2_threads(uint32_t W) { return walk2_lanes(W) < 32u ? 32u : walk2_lanes(W); }
-// shared memory of a walk2 CTA: per lane the Eq rows of its current block (6 W words) and the HP / VP' bits of its
-// current tile (32 steps x 2 W words), both laid out [word][lane] so that any per-lane index is conflict-free
-__host__ __device__ constexpr size_t walk2_smem_bytes(uint32_t W) { return size_t(kNumSymbols * W + 64 * W) * walk2_lanes(W) * 4; }
+// One GROUP of W lanes per alignment (W = the block width of its score pass: lane w owns word w of the block), 64 / W
+// alignments per CTA.  The tile the traceback stands on is recomputed as a skewed wavefront -- lane w does column step s
+// at time s + w, the carries of word w - 1 arrive by shuffle -- so a tile of 32 steps costs 32 + W single-word steps
+// instead of 32 W-word steps on one lane; only the words at or above the path's row are computed (carries run downwards).
+// The HP / VP' bits of the tile go to shared memory, and every lane of the group follows the path through them in
+// lockstep (same addresses: broadcasts), so that all of them know where the next tile is; lane 0 writes the cigar.
+__host__ __device__ constexpr uint32_t walk2_threads() { return 64u; }
+__host__ __device__ constexpr uint32_t walk2_per_cta(uint32_t W) { return walk2_threads() / W; }
+// shared memory per alignment: HP / VP' of 32 steps x W words (+ 1 word, so that the groups of a warp start in different
+// banks), and the Eq rows of its current block (6 symbols x W words)
+__host__ __device__ constexpr uint32_t walk2_words_per_group(uint32_t W) { return 64 * W + 1 + kNumSymbols * W; }
+__host__ __device__ constexpr size_t walk2_smem_bytes(uint32_t W) { return size_t(walk2_words_per_group(W)) * walk2_per_cta(W) * 4; }
 
 template <int W>
-__global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch const L) {
+__global__ void __launch_bounds__(walk2_threads()) walk2_kernel(Walk2Launch const L) {
     extern __shared__ __align__(16) uint32_t w2_smem[];
     constexpr int ROWS = 32 * W;
     constexpr uint32_t RECW = ck_record_words(W);
-    constexpr uint32_t kWalk2Threads = walk2_lanes(W);                      // stride of the per-lane tables
-    uint32_t const tid = threadIdx.x < kWalk2Threads ? threadIdx.x : 0u;
-    uint32_t* const eq_s = w2_smem + tid;                                    // Eq[sym][w]  at eq_s[(sym * W + w) * kWalk2Threads]
-    uint32_t* const bits = w2_smem + kNumSymbols * W * kWalk2Threads + tid;  // HP / VP' of step p, word w at bits[((p * W + w) * 2 + {0, 1}) * kWalk2Threads]
-    uint32_t const id = blockIdx.x * kWalk2Threads + threadIdx.x;
-    bool const mine = threadIdx.x < kWalk2Threads && id < L.n_tasks;
+    constexpr uint32_t PER_CTA = walk2_per_cta(W);
+    uint32_t const w = threadIdx.x % W;                                    // this lane's word of the block
+    uint32_t const grp = threadIdx.x / W;                                  // alignment within the CTA
+    uint32_t* const bits = w2_smem + grp * walk2_words_per_group(W);       // HP / VP' of step p, word x at bits[(p * W + x) * 2 + {0, 1}]
+    uint32_t* const eq_g = bits + 64 * W + 1;                              // Eq[sym][x] at eq_g[sym * W + x]
+    uint32_t const id = blockIdx.x * PER_CTA + grp;
+    bool const mine = id < L.n_tasks;
     bool done = !mine;
     Walk2Task T;
     if (!done) T = L.tasks[id];
@@ -813,6 +819,7 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
     uint32_t const ck_per_block = ck_records_per_block(int64_t(T.dhi) - int64_t(T.dlo) + 1, ROWS);
     const uint32_t* const ck = L.ck + T.ck_base;
     uint32_t* const slot_end = L.cigars + T.cigar_base + T.cigar_cap;
+    bool const writer = w == 0;
 
     // first / last step of block b in the score pass (block b is at column t - b at step t)
     auto block_steps = [&](uint32_t b, int32_t& ts, int32_t& te) {
@@ -828,17 +835,17 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
     uint32_t chars[4] = {0, 0, 0, 0};                            // window characters of the tile's columns, 4 bits each, step p at nibble p
     auto emit = [&](uint32_t op, uint32_t len) {
         if (op == cur_op) { cur_len += len; return; }
-        if (cur_len) { if (n_runs < T.cigar_cap) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
+        if (cur_len) { if (n_runs < T.cigar_cap) { if (writer) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
         cur_op = op; cur_len = len;
     };
     auto tile_char = [&](uint32_t p) -> uint32_t {               // p in 0 .. 31
-        uint32_t const w = p < 8 ? chars[0] : (p < 16 ? chars[1] : (p < 24 ? chars[2] : chars[3]));
-        return (w >> (4 * (p & 7u))) & 15u;
+        uint32_t const x = p < 8 ? chars[0] : (p < 16 ? chars[1] : (p < 24 ? chars[2] : chars[3]));
+        return (x >> (4 * (p & 7u))) & 15u;
     };
 
-    // inputs of a tile, as loaded: window characters, the block's record at the step before the tile, boundary bits of the
-    // block above for the tile's steps (A) and the 32 steps before (B)
-    struct TileIn { uint32_t raw[5]; uint32_t sh; uint32_t st[2 * W]; uint32_t hpA, hnA, hpB, hnB; };
+    // inputs of a tile, as loaded: window characters, this lane's word of the block's record at the step before the tile,
+    // boundary bits of the block above for the tile's steps (A) and the 32 steps before (B)
+    struct TileIn { uint32_t raw[5]; uint32_t sh; uint32_t pv, mv; uint32_t hpA, hnA, hpB, hnB; };
     TileIn X;
     bool pf_valid = false; uint32_t pf_b = 0, pf_q = 0;
     auto fetch_tile = [&](uint32_t b, uint32_t q, TileIn& Y) {
@@ -849,17 +856,10 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
         Y.sh = uint32_t(pos0 - w0 * 8) * 4;
 #pragma unroll
         for (int k = 0; k < 5; ++k) Y.raw[k] = w0 + k >= 0 ? __ldg(ref + (w0 + k)) : 0u;
+        Y.pv = 0; Y.mv = 0;
         if (t0 >= ts) {
             const uint32_t* rec = ck + (uint64_t(b) * ck_per_block + uint32_t(int32_t(q - 1) - ((ts + 31) >> 5))) * RECW;
-            if constexpr (W == 1) { uint2 const v = *reinterpret_cast<const uint2*>(rec); Y.st[0] = v.x; Y.st[1] = v.y; }
-            else if constexpr (W == 2) { uint4 const v = *reinterpret_cast<const uint4*>(rec); Y.st[0] = v.x; Y.st[1] = v.y; Y.st[2] = v.z; Y.st[3] = v.w; }
-            else {
-#pragma unroll
-                for (int w = 0; w < 2 * W; w += 4) {
-                    uint4 const a = *reinterpret_cast<const uint4*>(rec + w);
-                    Y.st[w] = a.x; Y.st[w + 1] = a.y; Y.st[w + 2] = a.z; Y.st[w + 3] = a.w;
-                }
-            }
+            Y.pv = rec[w]; Y.mv = rec[W + w];
         }
         Y.hpA = 0xffffffffu; Y.hnA = 0; Y.hpB = 0xffffffffu; Y.hnB = 0;
         if (b > 0) {
@@ -878,37 +878,36 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
             if (i == 0) done = true;
             else if (j == 0) { emit(1, i); errors += i; i = 0; done = true; }     // column 0: only "up" remains
         }
+        // ---------------- recompute the tile of (i, j): what this group needs, then the wavefront with the whole warp ----------------
+        uint32_t Pv1[1] = {0}, Mv1[1] = {0};
+        uint32_t top_hp = 0, top_hn = 0;
+        int32_t p_first = 0, n_steps = 0;                                  // the tile's steps p_first .. p_first + n_steps - 1 are computed
+        uint32_t wi0 = 0;                                                  // word of the path's row: words above it are all that is needed
         if (!done) {
-            // ---------------- recompute the tile of (i, j) ----------------
             uint32_t const u = i + pad;                                          // row in the padded numbering (1-based)
             b = (u - 1) / ROWS;
+            wi0 = ((u - 1) % ROWS) >> 5;
             uint32_t const t_cell = j + b;
             q = (t_cell + 31) >> 5;
             int32_t ts, te; block_steps(b, ts, te);
             int32_t const t0 = 32 * int32_t(q - 1);                              // the tile covers steps t0 + 1 .. t0 + 32
             // the path only moves up and left: nothing after the step of (i, j) is needed
             int32_t const t_lo = t0 + 1 > ts ? t0 + 1 : ts, t_hi = int32_t(t_cell) < te ? int32_t(t_cell) : te;
+            p_first = t_lo - t0 - 1; n_steps = t_hi - t_lo + 1;
+            if (n_steps < 0) n_steps = 0;
             // what the tile is computed from: fetched while the previous tile was being walked, if the guess was right
             if (!(pf_valid && pf_b == b && pf_q == q)) fetch_tile(b, q, X);
             pf_valid = false;
-            // window characters of steps t0 + 1 .. t0 + 32 (columns t0 + 1 - b ..), 4 bits each, step p at nibble p
 #pragma unroll
             for (int k = 0; k < 4; ++k) chars[k] = __funnelshift_r(X.raw[k], X.raw[k + 1], X.sh);
-            uint32_t Pv[W], Mv[W];
-            if (t0 >= ts) {
-#pragma unroll
-                for (int w = 0; w < W; ++w) { Pv[w] = X.st[w]; Mv[w] = X.st[W + w]; }
-            } else {
+            if (t0 >= ts) { Pv1[0] = X.pv; Mv1[0] = X.mv; }
+            else {
                 // the block begins inside the tile: "block above + 1, 2, ..." (wildcard rows of block 0 carry value 0)
-#pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    int32_t const virt = b == 0 ? int32_t(pad) - 32 * w : 0;
-                    Pv[w] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
-                    Mv[w] = 0;
-                }
+                int32_t const virt = b == 0 ? int32_t(pad) - 32 * int32_t(w) : 0;
+                Pv1[0] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
+                Mv1[0] = 0;
             }
             // upper boundary: bit p = horizontal delta of the row above the block at step t0 + 1 + p
-            uint32_t top_hp = 0, top_hn = 0;
             if (b > 0) {
                 int32_t us, ue; block_steps(b - 1, us, ue);                      // the block above is one step ahead: its step t - 1
                 top_hp = (X.hpA << 1) | (X.hpB >> 31);
@@ -923,49 +922,49 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
                 top_hp = (top_hp & valid) | ~valid;
                 top_hn &= valid;
             }
-            // Eq rows of this block
+            // Eq rows of this block: every lane its own word
             if (eq_block != b) {
                 eq_block = b;
+                uint32_t const gw = b * W + w;
+                int32_t const virt = int32_t(pad) - int32_t(32 * gw);
+                uint32_t const wild = virt >= 32 ? 0xffffffffu : (virt > 0 ? ((1u << virt) - 1u) : 0u);
 #pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    uint32_t const gw = b * W + w;
-                    int32_t const virt = int32_t(pad) - int32_t(32 * gw);
-                    uint32_t const wild = virt >= 32 ? 0xffffffffu : (virt > 0 ? ((1u << virt) - 1u) : 0u);
-#pragma unroll
-                    for (int sym = 0; sym < kNumSymbols; ++sym) {
-                        const uint32_t* plane = L.peq_table + uint64_t(sym) * L.peq_plane_words;
-                        eq_s[(sym * W + w) * kWalk2Threads] = peq_window(plane, int64_t(T.query_base) - int64_t(pad) + int64_t(32 * gw)) | wild;
-                    }
+                for (int sym = 0; sym < kNumSymbols; ++sym) {
+                    const uint32_t* plane = L.peq_table + uint64_t(sym) * L.peq_plane_words;
+                    eq_g[sym * W + w] = peq_window(plane, int64_t(T.query_base) - int64_t(pad) + int64_t(32 * gw)) | wild;
                 }
             }
-            {
-                uint32_t EqN[W];
-                uint32_t const c0 = tile_char(uint32_t(t_lo - t0 - 1));
-#pragma unroll
-                for (int w = 0; w < W; ++w) EqN[w] = eq_s[(c0 * W + w) * kWalk2Threads];
-                for (int32_t t = t_lo; t <= t_hi; ++t) {
-                    uint32_t const p = uint32_t(t - t0 - 1);
-                    uint32_t Eq[W], hp_all[W];
-#pragma unroll
-                    for (int w = 0; w < W; ++w) Eq[w] = EqN[w];
-                    uint32_t const cn = tile_char((p + 1) & 31u);                // Eq row of the next step, fetched ahead
-#pragma unroll
-                    for (int w = 0; w < W; ++w) EqN[w] = eq_s[(cn * W + w) * kWalk2Threads];
-                    uint32_t hp, hn;
-                    block_column<W, true>(Pv, Mv, Eq, ((top_hp >> p) & 1u) << 31, ((top_hn >> p) & 1u) << 31, hp, hn, hp_all);
+        }
+        __syncwarp();
+        {
+            // lane w computes step s of the tile at time s + w
+            int32_t const my_last = (!done && w <= wi0) ? n_steps - 1 + int32_t(wi0) : -1;
+            int32_t const t_max = __reduce_max_sync(0xffffffffu, my_last);
+            uint32_t out_hp = 0, out_hn = 0;
+            for (int32_t tau = 0; tau <= t_max; ++tau) {
+                uint32_t in_hp = __shfl_up_sync(0xffffffffu, out_hp, 1, W);
+                uint32_t in_hn = __shfl_up_sync(0xffffffffu, out_hn, 1, W);
+                int32_t const sidx = tau - int32_t(w);
+                if (!done && w <= wi0 && sidx >= 0 && sidx < n_steps) {
+                    uint32_t const p = uint32_t(p_first + sidx);
+                    if (w == 0) { in_hp = ((top_hp >> p) & 1u) << 31; in_hn = ((top_hn >> p) & 1u) << 31; }
+                    uint32_t Eq1[1], hp_all[1];
+                    Eq1[0] = eq_g[tile_char(p) * W + w];
+                    block_column<1, true>(Pv1, Mv1, Eq1, in_hp, in_hn, out_hp, out_hn, hp_all);
                     // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
-#pragma unroll
-                    for (int w = 0; w < W; ++w) {
-                        bits[((p * W + w) * 2) * kWalk2Threads] = hp_all[w];
-                        bits[((p * W + w) * 2 + 1) * kWalk2Threads] = Pv[w];
-                    }
+                    bits[(p * W + w) * 2] = hp_all[0];
+                    bits[(p * W + w) * 2 + 1] = Pv1[0];
                 }
             }
-            // the path most likely continues into the same block's previous 32 steps: get that tile's inputs on their
-            // way now, they arrive while this tile is being walked
+        }
+        __syncwarp();
+        // the path most likely continues into the same block's previous 32 steps: get that tile's inputs on their
+        // way now, they arrive while this tile is being walked
+        if (!done) {
+            int32_t ts, te; block_steps(b, ts, te);
             if (q >= 2 && 32 * int32_t(q - 1) >= ts) { fetch_tile(b, q - 1, X); pf_valid = true; pf_b = b; pf_q = q - 1; }
         }
-        // ---------------- follow the path while it stays inside the tile ----------------
+        // ---------------- follow the path while it stays inside the tile (every lane of the group, in lockstep) ----------------
         // trace priority: left > up > diagonal (the one place that encodes it; oracle: FXO_TRACE_PRIORITY)
         if (!done) {
             // position inside the tile: step p (column), row r of the block (0-based); the tile is left when p < 0 (column
@@ -978,15 +977,15 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
             uint32_t ops_err = 0;
             while (p >= p_min && r >= r_min) {
                 uint32_t const wi = uint32_t(r) >> 5, bit = uint32_t(r) & 31u;
-                uint32_t const hpb = (bits[((uint32_t(p) * W + wi) * 2) * kWalk2Threads] >> bit) & 1u;
-                uint32_t const vpb = (bits[((uint32_t(p) * W + wi) * 2 + 1) * kWalk2Threads] >> bit) & 1u;
+                uint32_t const hpb = (bits[(uint32_t(p) * W + wi) * 2] >> bit) & 1u;
+                uint32_t const vpb = (bits[(uint32_t(p) * W + wi) * 2 + 1] >> bit) & 1u;
                 // query[i-1] == window[j-1] is the Eq bit of that row for the column's character
-                uint32_t const match = (eq_s[(tile_char(uint32_t(p)) * W + wi) * kWalk2Threads] >> bit) & 1u;
+                uint32_t const match = (eq_g[tile_char(uint32_t(p)) * W + wi] >> bit) & 1u;
                 uint32_t const op = hpb ? 2u : (vpb ? 1u : (match ? 7u : 8u));     // D, I, =, X
                 ops_err += op != 7u;
                 if (op == cur_op) ++cur_len;
                 else {
-                    if (cur_len) { if (n_runs < T.cigar_cap) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
+                    if (cur_len) { if (n_runs < T.cigar_cap) { if (writer) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
                     cur_op = op; cur_len = 1;
                 }
                 p -= op != 1u;                                                     // left and diagonal move one column back
@@ -997,8 +996,9 @@ __global__ void __launch_bounds__(walk2_threads(W)) walk2_kernel(Walk2Launch con
             j -= uint32_t(p0 - p); i -= uint32_t(r0 - r);
             errors += ops_err;
         }
+        __syncwarp();                                                      // the next tile overwrites the bits
     }
-    if (mine) {
+    if (mine && writer) {
         if (cur_len) { if (n_runs < T.cigar_cap) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
         if (errors != T.score) bad = true;                                       // the path must cost exactly what the score pass found
         WalkResult R; R.begin_col = j; R.cigar_len = bad ? 0xffffffffu : n_runs;

@@ -13,6 +13,7 @@
 #include "dp_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <functional>
 #include <ctime>
@@ -57,7 +58,14 @@ inline cudaStream_t alloc_stream() {
     }
     return streams[dev];
 }
+// time spent allocating (device and page-locked memory), for fxg_counters: in the steady state it must not grow
+std::atomic<uint64_t> g_alloc_ns{0}, g_alloc_calls{0};
+struct AllocTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~AllocTimer() { g_alloc_ns += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count()); g_alloc_calls++; }
+};
 inline cudaError_t device_alloc(void** p, size_t bytes) {
+    AllocTimer timer;
     cudaStream_t const s = alloc_stream();
     if (!s) return cudaMalloc(p, bytes);
     cudaError_t e = cudaMallocAsync(p, bytes, s);
@@ -113,6 +121,7 @@ struct PinnedBuf {                       // page-locked host staging memory
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        AllocTimer timer;
         size_t const want = std::max(bytes + bytes / 2 + 4096, 2 * cap);
         if (p) { cudaFreeHost(p); p = nullptr; }
         cap = 0;
@@ -316,6 +325,7 @@ struct fxg_ctx {
     int merge_max_jobs = 64;                        // FXG_MERGE_JOBS (1 = never merge)
     int merged_parts = 1;                           // FXG_MERGED_PARTS: host workers (and launch sets) of a merged batch
     int merge_wait_us = 300;                        // FXG_MERGE_WAIT_US: how long a job waits for company while other batches run
+    double alloc_ms0 = 0; uint64_t alloc_calls0 = 0;    // allocation time / calls at the last fxg_reset_counters
     std::mutex class_mu;
     ClassDef classes[kMaxLevelClasses];
     int n_classes = 0;
@@ -476,7 +486,7 @@ cudaError_t launch_dp(int widx, bool checkpoints, DpLaunch const& L, uint32_t gr
 template <int W>
 cudaError_t launch_walk_one(Walk2Launch const& L, cudaStream_t s) {
     size_t const smem = walk2_smem_bytes(W);
-    walk2_kernel<W><<<(L.n_tasks + walk2_lanes(W) - 1) / walk2_lanes(W), walk2_threads(W), smem, s>>>(L);
+    walk2_kernel<W><<<(L.n_tasks + walk2_per_cta(W) - 1) / walk2_per_cta(W), walk2_threads(), smem, s>>>(L);
     return cudaGetLastError();
 }
 
@@ -2312,8 +2322,18 @@ void fxg_destroy(fxg_ctx* c) {
 
 const char* fxg_last_error(const fxg_ctx* c) { return c ? tls_last_error.c_str() : "no context"; }
 
-int fxg_get_counters(const fxg_ctx* c, fxg_counters* out) { if (!c || !out) return FXG_ERR_INVALID_ARGUMENT; *out = c->ctr; return FXG_OK; }
-int fxg_reset_counters(fxg_ctx* c) { if (!c) return FXG_ERR_INVALID_ARGUMENT; c->ctr = fxg_counters{}; return FXG_OK; }
+int fxg_get_counters(const fxg_ctx* c, fxg_counters* out) {
+    if (!c || !out) return FXG_ERR_INVALID_ARGUMENT;
+    { std::lock_guard<std::mutex> lock(const_cast<fxg_ctx*>(c)->mu); *out = c->ctr; }
+    out->alloc_ms = double(g_alloc_ns.load()) * 1e-6 - c->alloc_ms0; out->alloc_calls = g_alloc_calls.load() - c->alloc_calls0;
+    return FXG_OK;
+}
+int fxg_reset_counters(fxg_ctx* c) {
+    if (!c) return FXG_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->ctr = fxg_counters{}; c->alloc_ms0 = double(g_alloc_ns.load()) * 1e-6; c->alloc_calls0 = g_alloc_calls.load();
+    return FXG_OK;
+}
 
 int fxg_set_references(fxg_ctx* c, size_t n_refs, const uint8_t* const* ranks, const uint64_t* lens) {
     if (!c || (n_refs && (!ranks || !lens))) return FXG_ERR_INVALID_ARGUMENT;
@@ -2593,6 +2613,13 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
         }
     }
     ctr.batches++; ctr.batch_jobs += B.members.size();
+    static bool const trace_batches = std::getenv("FXG_TRACE_BATCHES") != nullptr;
+    if (trace_batches) {
+        static auto const epoch = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fxg] batch at %.3f ms: %zu jobs, %u walks, %zu parts, %.3f ms (alloc so far %.1f ms in %llu calls)\n",
+                std::chrono::duration<double, std::milli>(vt0 - epoch).count(), B.members.size(), rwb[n_reads], n_parts, since(),
+                double(g_alloc_ns.load()) * 1e-6, (unsigned long long)g_alloc_calls.load());
+    }
     if (g_prof.on) fprintf(stderr, "[fxg] run_batch: %zu jobs, %zu reads, %u walks, %zu parts; parts done %.3f ms, merged %.3f ms\n", B.members.size(), n_reads,
                            rwb[n_reads], n_parts, t_join, since());
     return FXG_OK;

@@ -148,6 +148,8 @@ typedef struct {
     uint64_t rescored_roots;         /* root windows scored again on their own because the shared pass could not vouch for them */
     uint64_t batches;                /* batches the queue ran for fxg_verify_run / fxg_verify_reads calls ... */
     uint64_t batch_jobs;             /* ... and the jobs in them (several callers' jobs are merged into one batch) */
+    double alloc_ms;                 /* host time spent allocating device / page-locked memory (process-wide) ... */
+    uint64_t alloc_calls;            /* ... and the allocations: both stay flat in the steady state */
 } fxg_counters;
 
 /* ---- life cycle ----
