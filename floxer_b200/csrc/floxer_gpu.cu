@@ -321,8 +321,8 @@ struct fxg_ctx {
     // job that is waiting with it and runs them as one batch (submit_and_wait)
     std::vector<Ticket*> pending;
     std::condition_variable cv;
-    uint64_t merge_max_walks = uint64_t(6) << 20;   // FXG_MERGE_WALKS: anchors of a merged batch at most (a single job may be larger)
-    int merge_max_jobs = 64;                        // FXG_MERGE_JOBS (1 = never merge)
+    uint64_t merge_max_walks = uint64_t(1) << 20;   // FXG_MERGE_WALKS: anchors of a merged batch at most (a single job may be larger)
+    int merge_max_jobs = 16;                        // FXG_MERGE_JOBS (1 = never merge)
     int merged_parts = 1;                           // FXG_MERGED_PARTS: host workers (and launch sets) of a merged batch
     int merge_wait_us = 300;                        // FXG_MERGE_WAIT_US: how long a job waits for company while other batches run
     double alloc_ms0 = 0; uint64_t alloc_calls0 = 0;    // allocation time / calls at the last fxg_reset_counters
@@ -1367,10 +1367,19 @@ int validate_reads(fxg_ctx* c, std::string& err, const fxg_read* reads, size_t l
         // shape of the tree (pex.hpp:59-76): inner[0] is the root, every other inner node hangs below it
         if (R.num_inner) {
             if (nd[0].parent_id != FXG_NULL_ID) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: inner node 0 is not the root", i);
+            // depth[q] = hops to the root, 0xff = not known yet; every chain is followed only as far as a node that is known
+            thread_local std::vector<uint8_t> depth;
+            depth.assign(R.num_inner, 0xff);
+            depth[0] = 0;
             for (uint32_t q = 1; q < R.num_inner; ++q) {
-                if (nd[q].parent_id == FXG_NULL_ID) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: inner node %u has no parent", i, q);
                 uint64_t p = q; int hops = 0;
-                while (p != 0) { p = nd[p].parent_id; if (p == FXG_NULL_ID || ++hops > 250) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: the parents of inner node %u do not lead to the root", i, q); }
+                while (depth[p] == 0xff) {
+                    p = nd[p].parent_id;
+                    if (p == FXG_NULL_ID || ++hops > 250) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: the parents of inner node %u do not lead to the root", i, q);
+                }
+                if (int(depth[p]) + hops > 250) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: the tree is deeper than 250 levels", i);
+                int d = int(depth[p]) + hops;
+                for (uint64_t x = q; depth[x] == 0xff; x = nd[x].parent_id) depth[x] = uint8_t(d--);
             }
         }
         const fxg_anchor* an = anchors + R.anchor_offset;
@@ -2260,10 +2269,10 @@ int fxg_create(int device, fxg_ctx** out) {
     c->device_levels = env_int("FXG_DEVICE_LEVELS", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
     c->n_groups = env_int("FXG_GROUPS", 4, 1, fxg_ctx::kMaxGroups);
-    c->merge_max_jobs = env_int("FXG_MERGE_JOBS", 64, 1, 4096);
+    c->merge_max_jobs = env_int("FXG_MERGE_JOBS", 16, 1, 4096);
     c->merge_wait_us = env_int("FXG_MERGE_WAIT_US", 300, 0, 1000000);
     c->merged_parts = env_int("FXG_MERGED_PARTS", 1, 1, 64);
-    c->merge_max_walks = uint64_t(env_int("FXG_MERGE_WALKS", 6 << 20, 1, int(kMaxDeviceWalks - 1)));
+    c->merge_max_walks = uint64_t(env_int("FXG_MERGE_WALKS", 1 << 20, 1, int(kMaxDeviceWalks - 1)));
     c->workers_busy = default_workers(c->n_groups);
     // a batch that runs alone is split over 8 workers; the lowest free group is taken, so that is always group 0 and only
     // it owns that many.  An explicit FXG_WORKERS is taken literally.
