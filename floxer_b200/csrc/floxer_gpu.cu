@@ -11,6 +11,10 @@
 // No CPU fallback exists: every alignment result comes from dp_kernels.cuh.
 #include "../../include/floxer_gpu.h"
 #include "dp_kernels.cuh"
+#include "root_kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <atomic>
@@ -192,10 +196,10 @@ struct Worker {
     // tracebacks are long chains of dependent steps: the root alignments of a wave are cut into chunks, each chunk's
     // tracebacks run on a stream of their own beside the score passes (and tracebacks) of the other chunks
     static constexpr int kWalkSlots = 4;
-    DevBuf d_tasks, d_results, d_ck[kWalkSlots], d_wtasks, d_wresults, d_cigars, d_rtasks, d_rresults, d_lv, d_roots;
+    DevBuf d_tasks, d_results, d_ck[kWalkSlots], d_wtasks, d_wresults, d_cigars, d_rtasks, d_rresults, d_lv, d_roots, d_root, d_cub, d_hits;
     cudaStream_t walk_stream[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_walk_done[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr}, ev_w0 = nullptr, ev_w1[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
-    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults, h_rtasks, h_rresults, h_lv, h_lv_back, h_roots;
+    PinnedBuf h_tasks, h_results, h_wtasks, h_wresults, h_rtasks, h_rresults, h_lv, h_lv_back, h_roots, h_root_back, h_hits;
     fxg_counters ctr{};
     std::string err;
     std::vector<ConfigCacheEntry> cfg_cache = std::vector<ConfigCacheEntry>(8192);
@@ -203,7 +207,7 @@ struct Worker {
     std::vector<Config> cfgs;
     uint64_t cig_used = 0;               // ops of d_cigars filled by the current run
     void release() {
-        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults, &d_lv, &d_roots}) b->release();
+        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults, &d_lv, &d_roots, &d_root, &d_cub, &d_hits}) b->release();
         if (ev_w0) { cudaEventDestroy(ev_w0); ev_w0 = nullptr; }
         if (ev_b0) { cudaEventDestroy(ev_b0); ev_b0 = nullptr; }
         if (ev_b1) { cudaEventDestroy(ev_b1); ev_b1 = nullptr; }
@@ -215,7 +219,7 @@ struct Worker {
             if (walk_stream[q]) cudaStreamDestroy(walk_stream[q]);
             ev_walk_done[q] = ev_w1[q] = nullptr; walk_stream[q] = nullptr;
         }
-        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults, &h_rtasks, &h_rresults, &h_lv, &h_lv_back, &h_roots}) b->release();
+        for (PinnedBuf* b : {&h_tasks, &h_results, &h_wtasks, &h_wresults, &h_rtasks, &h_rresults, &h_lv, &h_lv_back, &h_roots, &h_root_back, &h_hits}) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -310,6 +314,7 @@ struct fxg_ctx {
     bool device_levels = true;                   // FXG_DEVICE_LEVELS=0 runs the inner tree levels from the host (development knob)
     bool share_root_passes = true;               // FXG_SHARE_ROOTS=0 scores every root window on its own (development knob)
     bool infer_inner = true;                     // FXG_INFER_INNER=0 computes every inner window (development knob)
+    bool device_roots = true;                    // FXG_DEVICE_ROOTS=0 runs the root level from the host (development knob)
     bool force_wide = false;                     // FXG_FORCE_WIDE=1 sends every pass to the multi-warp kernel (development knob: tests)
     int root_chunks = 1, root_chunk_min = 512;   // FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN (development knobs, read by fxg_create)
     std::vector<Pool> spare_pools;       // device buffers of freed batches / jobs, reused by the next stage call
@@ -1519,6 +1524,23 @@ int prepare_job(fxg_ctx* c, fxg_job* J, std::string& err, fxg_counters& ctr) {
             if (extra >= (1u << 30)) { out.status = 1; return; }
             rr.root_extra = uint32_t(extra);
             rr.member = 0; rr.reserved0 = rr.reserved1 = 0;
+            {
+                // configuration class of the root's score passes, and the widest union window that class takes (root_cluster_kernel)
+                Pass p;
+                uint64_t const n_root = base + 2 * extra;
+                if (n_root >= (uint64_t(1) << 31) || !score_pass_for(0, 0, uint32_t(n_root), rr.root_m, rr.root_k, 0, p)) { out.status = 1; return; }
+                Config cf;
+                if (!cached_config(cache, p, c->smem_limit, c->force_wide, cf)) { out.status = 1; return; }
+                uint32_t const W = uint32_t(kWidths[cf.widx]);
+                int const ci = class_of(c, cf, (rr.root_m + 32 * W - 1) / (32 * W) * W);
+                if (ci < 0) { out.status = 1; return; }
+                rr.reserved0 = uint32_t(ci);
+                // ring of G lanes: band B = n - m + 2k + 1 must satisfy G >= (B - 4) / (32 W + 1) + 3 (choose_config)
+                // (a lane per block, or the multi-warp kernel: any band)
+                int64_t const n_cap = (cf.G == kWideG || cf.G >= cf.nb) ? int64_t(1) << 30
+                                                                        : int64_t(rr.root_m) - 2 * int64_t(rr.root_k) - 1 + 3 + (int64_t(cf.G) - 2) * (32 * int64_t(W) + 1);
+                rr.reserved1 = uint32_t(std::max<int64_t>(std::min<int64_t>(n_cap, int64_t(1) << 30), int64_t(n_root)));
+            }
             uint64_t const shape = (uint64_t(R.query_len) << 32) ^ (uint64_t(R.num_inner) << 16) ^ R.num_leaves;
             auto const ins = first_of_shape.emplace(shape, uint32_t(ri));
             bool copied = false;
@@ -1603,6 +1625,233 @@ inline Span root_span_of(ReadRec const& R, int64_t diag, uint64_t ref_len) {
     r.length = std::min<uint64_t>(base + 2ull * R.root_extra, ref_len - r.offset);
     r.extra = R.root_extra;
     return r;
+}
+
+// The root level of a part on the device (root_kernels.cuh).  `entries` are the part's root walks on the device, in anchor
+// order.  Returns FXG_OK with P.hits filled, an error, or kRootFallback when the part has to take the host's way
+// (run_root_passes): a member of a shared pass that the pass cannot vouch for, or more checkpoint records than the budget.
+constexpr int kRootFallback = 1;
+int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_reads, PartState& P, const RootEntry* d_entries, uint32_t n_roots,
+                      const ReadRec* d_reads, unsigned long long* d_member_totals, ClassDef const* classes, int n_cls) {
+    cudaStream_t const st = w.stream;
+    bool const want_cigar = !B.cfg.without_cigar;
+    Pool const& pool = *B.pool;
+    size_t const n = n_roots, n_members = B.members.size();
+    // ---- buffers ----
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t const at = off; off += (bytes + 255) & ~size_t(255); return at; };
+    size_t const o_ws = carve(n * 8), o_len = carve(n * 4), o_read = carve(n * 4), o_orient = carve(n), o_key = carve(n * 8), o_idx = carve(n * 4);
+    size_t const o_key_s = carve(n * 8), o_idx_s = carve(n * 4), o_ustart = carve(n * 4), o_uof = carve(n * 4), o_pos = carve(n * 4);
+    size_t const o_score = carve(n * 4), o_end = carve(n * 4), o_flag = carve(n);
+    size_t const o_units = carve(n * sizeof(UnitRec)), o_uwords = carve(n * 8), o_uck = carve(n * 8);
+    size_t const o_key2 = carve(n * 8), o_idx2 = carve(n * 4), o_key2_s = carve(n * 8), o_idx2_s = carve(n * 4);
+    size_t const o_rep = carve(n * 4), o_tbcap = carve(n * 8), o_tbcig = carve(n * 8), o_tbslot = carve(n * 4);
+    size_t const o_hit = carve(n * 4), o_hitat = carve(n * 4), o_ctr = carve(kRootCounters * 4);
+    CUDA_TRY(w.err, w.d_root.ensure(off));
+    uint8_t* const D = w.d_root.as<uint8_t>();
+    size_t tmp_bytes = 0, t1 = 0;
+    {   // temporary storage of the sorts and scans
+        cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, int(n), 0, 64, st); tmp_bytes = std::max(tmp_bytes, t1);
+        cub::DeviceScan::InclusiveSum(nullptr, t1, (const uint32_t*)nullptr, (uint32_t*)nullptr, int(n), st); tmp_bytes = std::max(tmp_bytes, t1);
+        cub::DeviceScan::ExclusiveSum(nullptr, t1, (const uint64_t*)nullptr, (uint64_t*)nullptr, int(n), st); tmp_bytes = std::max(tmp_bytes, t1);
+        cub::DeviceScan::ExclusiveSum(nullptr, t1, (const uint32_t*)nullptr, (uint32_t*)nullptr, int(n), st); tmp_bytes = std::max(tmp_bytes, t1);
+    }
+    CUDA_TRY(w.err, w.d_cub.ensure(tmp_bytes + 256));
+    RootCtx C{};
+    C.entries = d_entries; C.n_roots = n_roots; C.reads = d_reads; C.n_reads = n_reads;
+    C.ref_base = c->refs.d_base.as<uint64_t>(); C.ref_len = c->refs.d_len.as<uint64_t>();
+    for (int ci = 0; ci < n_cls; ++ci) C.classes[ci] = RootClass{uint32_t(kWidths[classes[ci].widx]), classes[ci].G};
+    C.want_cigar = want_cigar ? 1u : 0u; C.share = c->share_root_passes ? 1u : 0u;
+    C.ws = reinterpret_cast<uint64_t*>(D + o_ws); C.len = reinterpret_cast<uint32_t*>(D + o_len); C.read = reinterpret_cast<uint32_t*>(D + o_read); C.orient = D + o_orient;
+    C.key = reinterpret_cast<uint64_t*>(D + o_key); C.idx = reinterpret_cast<uint32_t*>(D + o_idx);
+    C.key_s = reinterpret_cast<uint64_t*>(D + o_key_s); C.idx_s = reinterpret_cast<uint32_t*>(D + o_idx_s);
+    C.unit_start = reinterpret_cast<uint32_t*>(D + o_ustart); C.unit_of = reinterpret_cast<uint32_t*>(D + o_uof); C.pos_of = reinterpret_cast<uint32_t*>(D + o_pos);
+    C.m_score = reinterpret_cast<int32_t*>(D + o_score); C.m_end = reinterpret_cast<uint32_t*>(D + o_end); C.m_flag = D + o_flag;
+    C.units = reinterpret_cast<UnitRec*>(D + o_units); C.unit_words = reinterpret_cast<uint64_t*>(D + o_uwords); C.unit_ck = reinterpret_cast<uint64_t*>(D + o_uck);
+    C.key2 = reinterpret_cast<uint64_t*>(D + o_key2); C.idx2 = reinterpret_cast<uint32_t*>(D + o_idx2);
+    C.key2_s = reinterpret_cast<uint64_t*>(D + o_key2_s); C.idx2_s = reinterpret_cast<uint32_t*>(D + o_idx2_s);
+    C.rep = reinterpret_cast<uint32_t*>(D + o_rep); C.tb_cap = reinterpret_cast<uint64_t*>(D + o_tbcap); C.tb_cig = reinterpret_cast<uint64_t*>(D + o_tbcig);
+    C.tb_slot = reinterpret_cast<uint32_t*>(D + o_tbslot);
+    C.hit = reinterpret_cast<uint32_t*>(D + o_hit); C.hit_at = reinterpret_cast<uint32_t*>(D + o_hitat);
+    C.counters = reinterpret_cast<uint32_t*>(D + o_ctr); C.member_totals = d_member_totals; C.read0 = r0;
+    uint32_t const grid = uint32_t((n + 255) / 256);
+    size_t const back_bytes = kRootCounters * 4 + n_members * kMemberTotals * 8;
+    CUDA_TRY(w.err, w.h_root_back.ensure(back_bytes));
+    auto read_back = [&]() -> int {          // counters (and the members' totals) to the host; waits
+        CUDA_TRY(w.err, cudaMemcpyAsync(w.h_root_back.p, C.counters, kRootCounters * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(w.err, cudaMemcpyAsync(w.h_root_back.as<uint8_t>() + kRootCounters * 4, d_member_totals, n_members * kMemberTotals * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(w.err, w.wait_for(st));
+        w.ctr.d2h_bytes += back_bytes;
+        return FXG_OK;
+    };
+    const uint32_t* const ctr = w.h_root_back.as<uint32_t>();
+    auto ctr64 = [&](int at) { uint64_t v; std::memcpy(&v, ctr + at, 8); return v; };
+
+    // ---- windows, units ----
+    CUDA_TRY(w.err, cudaMemsetAsync(C.counters, 0, kRootCounters * 4, st));
+    CUDA_TRY(w.err, cudaMemsetAsync(C.unit_start, 0, n * 4, st));
+    root_prepare_kernel<<<grid, 256, 0, st>>>(C);
+    CUDA_TRY(w.err, cub::DeviceRadixSort::SortPairs(w.d_cub.p, tmp_bytes, C.key, const_cast<uint64_t*>(C.key_s), C.idx, const_cast<uint32_t*>(C.idx_s), int(n), 0, 64, st));
+    root_cluster_kernel<<<grid, 256, 0, st>>>(C);
+    CUDA_TRY(w.err, cub::DeviceScan::InclusiveSum(w.d_cub.p, tmp_bytes, C.unit_start, const_cast<uint32_t*>(C.unit_of), int(n), st));
+    CUDA_TRY(w.err, cudaMemsetAsync(C.unit_words, 0, n * 8, st));
+    root_units_kernel<<<grid, 256, 0, st>>>(C);
+    CUDA_TRY(w.err, cub::DeviceScan::ExclusiveSum(w.d_cub.p, tmp_bytes, C.unit_words, const_cast<uint64_t*>(C.unit_ck), int(n), st));
+    CUDA_TRY(w.err, cudaGetLastError());
+    w.ctr.kernel_launches += 6;
+    int rc = read_back();
+    if (rc != FXG_OK) return rc;
+    g_prof.lap(w, 7);
+    uint32_t const n_feasible = ctr[kCtrFeasible], n_units = ctr[kCtrUnits];
+    uint64_t const ck_words = ctr64(kCtrCkWords);
+    auto add_root_stats = [&]() {
+        const uint64_t* const mt = reinterpret_cast<const uint64_t*>(w.h_root_back.as<uint8_t>() + kRootCounters * 4);
+        for (size_t mi = 0; mi < n_members; ++mi) {
+            fxg_stats& S = P.out.stats[mi];
+            S.n_aligned_root += mt[mi * kMemberTotals + 5]; S.sum_aligned_root += mt[mi * kMemberTotals + 6]; S.cells_root += mt[mi * kMemberTotals + 7];
+        }
+    };
+    if (n_feasible == 0 || n_units == 0) { add_root_stats(); return FXG_OK; }
+    if (ck_words * 4 > std::max<uint64_t>(P.trace_budget, uint64_t(256) << 20)) return kRootFallback;       // (the host's way works in chunks)
+    uint32_t class_units[kMaxLevelClasses];
+    for (int ci = 0; ci < kMaxLevelClasses; ++ci) class_units[ci] = ctr[kCtrClassUnits + ci];
+
+    // ---- score passes, one launch per class ----
+    CUDA_TRY(w.err, w.d_tasks.ensure(size_t(n_units) * sizeof(DpTask)));
+    CUDA_TRY(w.err, w.d_results.ensure(size_t(n_units) * sizeof(DpResult)));
+    DevBuf& ckb = w.d_ck[0];
+    if (want_cigar) CUDA_TRY(w.err, ckb.ensure(std::max<uint64_t>(ck_words, 4) * 4));
+    C.tasks = w.d_tasks.as<DpTask>(); C.results = w.d_results.as<DpResult>(); C.ck = ckb.as<uint32_t>();
+    root_tasks_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(C, n_units);
+    CUDA_TRY(w.err, cudaGetLastError());
+    w.ctr.kernel_launches++;
+    {
+        // largest class first on the worker's stream, the others beside it
+        int order[kMaxLevelClasses]; int n_used = 0;
+        for (int ci = 0; ci < n_cls; ++ci) if (class_units[ci]) order[n_used++] = ci;
+        std::sort(order, order + n_used, [&](int a, int b) { return class_units[a] > class_units[b]; });
+        uint32_t prefix[kMaxLevelClasses + 1] = {0};
+        for (int ci = 0; ci < kMaxLevelClasses; ++ci) prefix[ci + 1] = prefix[ci] + class_units[ci];
+        if (n_used > 1) {
+            CUDA_TRY(w.err, cudaEventRecord(w.ev_fork, st));
+            for (int q = 0; q < std::min(n_used - 1, int(Worker::kSide)); ++q) CUDA_TRY(w.err, cudaStreamWaitEvent(w.side[q], w.ev_fork, 0));
+        }
+        for (int x = 0; x < n_used; ++x) {
+            int const ci = order[x];
+            ClassDef const& K = classes[ci];
+            bool const wide = K.G == kWideG;
+            uint32_t const tpw = wide ? 1u : 32u / K.G;
+            DpLaunch L{};
+            L.tasks = C.tasks + prefix[ci]; L.n_tasks = class_units[ci];
+            L.group = K.G; L.win_stride = kWinBytes; L.two = 2;
+            L.ref_chunks = c->refs.total / 32 + 1; L.inline_chunks = 1;
+            L.peq_stride = peq_stride_for(K.max_words);
+            L.ref_packed = c->refs.packed.as<uint32_t>(); L.inline_packed = nullptr;
+            L.peq_table = pool.peq.as<uint32_t>(); L.peq_plane_words = pool.plane_words;
+            L.results = w.d_results.as<DpResult>(); L.trace = ckb.as<uint32_t>();
+            size_t const smem = wide ? wide_smem_bytes() : size_t(tpw) * (kWinBytes + size_t(kNumSymbols) * L.peq_stride * 4);
+            if (smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", smem);
+            uint32_t const lgrid = wide ? uint32_t(std::min<size_t>(L.n_tasks, size_t(c->num_sms) * 2)) : (L.n_tasks + tpw - 1) / tpw;
+            cudaStream_t const s2 = x == 0 ? st : w.side[(x - 1) % Worker::kSide];
+            if (x == 0) CUDA_TRY(w.err, cudaEventRecord(w.ev_b0, st));
+            CUDA_TRY(w.err, launch_dp(wide ? -1 : int(K.widx), want_cigar, L, lgrid, smem, s2));
+            if (x == 0) CUDA_TRY(w.err, cudaEventRecord(w.ev_b1, st));
+            w.ctr.kernel_launches++;
+        }
+        for (int q = 0; q < std::min(n_used - 1, int(Worker::kSide)); ++q) {
+            CUDA_TRY(w.err, cudaEventRecord(w.ev_join[q], w.side[q]));
+            CUDA_TRY(w.err, cudaStreamWaitEvent(st, w.ev_join[q], 0));
+        }
+    }
+    // ---- every member's result; which alignments share a traceback ----
+    root_results_kernel<<<grid, 256, 0, st>>>(C);
+    w.ctr.kernel_launches++;
+    if (want_cigar) {
+        CUDA_TRY(w.err, cudaMemsetAsync(C.key2 + n_feasible, 0xff, (n - n_feasible) * 8, st));
+        CUDA_TRY(w.err, cub::DeviceRadixSort::SortPairs(w.d_cub.p, tmp_bytes, C.key2, const_cast<uint64_t*>(C.key2_s), C.idx2, const_cast<uint32_t*>(C.idx2_s), int(n), 0, 64, st));
+        root_dedup_kernel<<<grid, 256, 0, st>>>(C);
+        CUDA_TRY(w.err, cudaMemsetAsync(C.tb_cap + n_feasible, 0, (n - n_feasible) * 8, st));
+        root_walk_count_kernel<<<grid, 256, 0, st>>>(C);
+        CUDA_TRY(w.err, cub::DeviceScan::ExclusiveSum(w.d_cub.p, tmp_bytes, C.tb_cap, const_cast<uint64_t*>(C.tb_cig), int(n), st));
+        w.ctr.kernel_launches += 4;
+    }
+    CUDA_TRY(w.err, cudaGetLastError());
+    rc = read_back();
+    if (rc != FXG_OK) return rc;
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, w.ev_b0, w.ev_b1) == cudaSuccess) { w.ctr.root_launch_ms += ms; }
+    }
+    g_prof.lap(w, 11);
+    if (ctr[kCtrErrors]) return fail(w.err, FXG_ERR_CUDA, "internal: the DP engine lost track of its window buffer");
+    if (ctr[kCtrSlow]) return kRootFallback;             // a shared pass cannot vouch for one of its members: the host's way scores it again
+    uint32_t const n_accepted = ctr[kCtrAccepted], n_tb = ctr[kCtrTracebacks];
+    uint64_t const cig_total = ctr64(kCtrCigars);
+    w.ctr.dp_tasks += n_units; w.ctr.dp_word_steps += ctr64(kCtrWordSteps); w.ctr.trace_bytes += ck_words * 4;
+    w.ctr.root_launch_word_steps += 0;
+    w.ctr.shared_score_passes += ctr[kCtrShared];
+    if (want_cigar) w.ctr.shared_tracebacks += n_accepted - n_tb;
+    w.ctr.waves++;
+    if (n_accepted == 0) { add_root_stats(); return FXG_OK; }
+    // ---- tracebacks of the representatives ----
+    if (want_cigar) {
+        CUDA_TRY(w.err, w.d_wtasks.ensure(size_t(n_tb) * sizeof(Walk2Task)));
+        CUDA_TRY(w.err, w.d_wresults.ensure(size_t(n_tb) * sizeof(WalkResult)));
+        CUDA_TRY(w.err, w.d_cigars.ensure_preserving((w.cig_used + cig_total) * 4, w.cig_used * 4, st));
+        C.wtasks = w.d_wtasks.as<Walk2Task>(); C.wresults = w.d_wresults.as<WalkResult>();
+        root_walks_kernel<<<grid, 256, 0, st>>>(C, w.cig_used);
+        CUDA_TRY(w.err, cudaGetLastError());
+        w.ctr.kernel_launches++;
+        uint32_t width_tb[6], wprefix[7] = {0};
+        for (int wi = 0; wi < 6; ++wi) { width_tb[wi] = ctr[kCtrWidthTb + wi]; wprefix[wi + 1] = wprefix[wi] + width_tb[wi]; }
+        CUDA_TRY(w.err, cudaEventRecord(w.ev_w0, st));
+        CUDA_TRY(w.err, cudaEventRecord(w.ev_fork, st));
+        int n_launch = 0;
+        for (int wi = 0; wi < 6; ++wi) {
+            if (!width_tb[wi]) continue;
+            Walk2Launch WL{};
+            WL.tasks = C.wtasks + wprefix[wi]; WL.n_tasks = width_tb[wi]; WL.ck = ckb.as<uint32_t>();
+            WL.ref_packed = c->refs.packed.as<uint32_t>(); WL.inline_packed = nullptr;
+            WL.peq_table = pool.peq.as<uint32_t>(); WL.peq_plane_words = pool.plane_words;
+            WL.query_pool = nullptr; WL.cigars = w.d_cigars.as<uint32_t>();
+            WL.results = w.d_wresults.as<WalkResult>(); WL.two = 2;
+            cudaStream_t s2 = st;
+            if (n_launch > 0) { s2 = w.side[(n_launch - 1) % Worker::kSide]; CUDA_TRY(w.err, cudaStreamWaitEvent(s2, w.ev_fork, 0)); }
+            CUDA_TRY(w.err, launch_walk(wi, WL, s2));
+            if (n_launch > 0) {
+                int const sq = (n_launch - 1) % Worker::kSide;
+                CUDA_TRY(w.err, cudaEventRecord(w.ev_join[sq], s2));
+                CUDA_TRY(w.err, cudaStreamWaitEvent(st, w.ev_join[sq], 0));
+            }
+            w.ctr.kernel_launches++;
+            ++n_launch;
+        }
+        CUDA_TRY(w.err, cudaEventRecord(w.ev_w1[0], st));
+    }
+    // ---- alignment records in anchor order ----
+    CUDA_TRY(w.err, w.d_hits.ensure(size_t(n_accepted) * sizeof(fxg_alignment)));
+    CUDA_TRY(w.err, w.h_hits.ensure(size_t(n_accepted) * sizeof(fxg_alignment)));
+    C.out = w.d_hits.as<fxg_alignment>();
+    root_hits_kernel<<<grid, 256, 0, st>>>(C);
+    CUDA_TRY(w.err, cub::DeviceScan::ExclusiveSum(w.d_cub.p, tmp_bytes, C.hit, const_cast<uint32_t*>(C.hit_at), int(n), st));
+    root_finish_kernel<<<grid, 256, 0, st>>>(C);
+    CUDA_TRY(w.err, cudaGetLastError());
+    w.ctr.kernel_launches += 3;
+    CUDA_TRY(w.err, cudaMemcpyAsync(w.h_hits.p, w.d_hits.p, size_t(n_accepted) * sizeof(fxg_alignment), cudaMemcpyDeviceToHost, st));
+    w.ctr.d2h_bytes += size_t(n_accepted) * sizeof(fxg_alignment);
+    rc = read_back();
+    if (rc != FXG_OK) return rc;
+    if (want_cigar) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, w.ev_w0, w.ev_w1[0]) == cudaSuccess) w.ctr.trace_kernel_ms += ms;
+    }
+    g_prof.lap(w, 12);
+    if (ctr[kCtrErrors]) return fail(w.err, FXG_ERR_CUDA, "internal: the traceback of an alignment disagrees with its score pass");
+    add_root_stats();
+    P.hits.assign(w.h_hits.as<fxg_alignment>(), w.h_hits.as<fxg_alignment>() + n_accepted);
+    w.cig_used += cig_total;
+    g_prof.lap(w, 13);
+    return FXG_OK;
 }
 
 // query_verifier::verify() for every anchor of reads [r0, r1) of a batch: the tree walks on the device, then the root
@@ -1831,6 +2080,13 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     root_emit_kernel<<<pair_grid, 128, 0, st>>>(Dc, d_rootoff, w.d_roots.as<RootEntry>());
     CUDA_TRY(w.err, cudaGetLastError());
     w.ctr.kernel_launches++;
+    if (c->device_roots && c->refs.total < (uint64_t(1) << kPosBits) && pool.len < (uint64_t(1) << kPosBits) && n_reads < (1u << 27)) {
+        int const rc = root_level_device(c, w, B, r0, n_reads, P, w.d_roots.as<RootEntry>(), n_roots, reinterpret_cast<const ReadRec*>(D + o_reads),
+                                         reinterpret_cast<unsigned long long*>(D + o_member_totals), classes, n_cls);
+        if (rc != kRootFallback) return rc;
+        P.hits.clear();
+    }
+    // ---- the host's way: the entries come back, one score pass per walk that verifies its root (run_root_passes) ----
     CUDA_TRY(w.err, cudaMemcpyAsync(w.h_roots.p, w.d_roots.p, size_t(n_roots) * sizeof(RootEntry), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(w.err, w.wait_for(st));
     w.ctr.d2h_bytes += size_t(n_roots) * sizeof(RootEntry);
@@ -2265,6 +2521,7 @@ int fxg_create(int device, fxg_ctx** out) {
     c->root_chunks = env_int("FXG_ROOT_CHUNKS", 1, 1, 64);
     c->infer_inner = env_int("FXG_INFER_INNER", 1, 0, 1) != 0;
     c->force_wide = env_int("FXG_FORCE_WIDE", 0, 0, 1) != 0;
+    c->device_roots = env_int("FXG_DEVICE_ROOTS", 1, 0, 1) != 0;
     c->share_root_passes = env_int("FXG_SHARE_ROOTS", 1, 0, 1) != 0;
     c->device_levels = env_int("FXG_DEVICE_LEVELS", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);

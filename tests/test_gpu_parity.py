@@ -294,10 +294,11 @@ def test_sharing_knobs_do_not_change_results(gpu, monkeypatch):
     batch = _densified(synthetic.make_batch(refs, 10, 1500, 0.06, 83, gpu.pex_build, seed_errors=2, decoy_fraction=0.3),
                        [120_000], np.random.default_rng(7), 40, 0.7)
     results = []
-    for share, infer, device in (("1", "1", "1"), ("0", "0", "1"), ("1", "1", "0"), ("0", "0", "0")):
+    for share, infer, device, roots in (("1", "1", "1", "1"), ("0", "0", "1", "1"), ("1", "1", "0", "1"), ("0", "0", "0", "1"), ("1", "1", "1", "0"), ("0", "1", "1", "0")):
         monkeypatch.setenv("FXG_SHARE_ROOTS", share)
         monkeypatch.setenv("FXG_INFER_INNER", infer)
         monkeypatch.setenv("FXG_DEVICE_LEVELS", device)
+        monkeypatch.setenv("FXG_DEVICE_ROOTS", roots)
         c2 = gpu.Context(0)
         try:
             c2.set_references(refs)
