@@ -84,6 +84,15 @@ inline void device_free(void* p) {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    // (a buffer that serves merged batches is sized for the largest one the queue forms the first time it has to grow:
+    //  `scale` = that batch's size over this one's)
+    cudaError_t ensure_scaled(size_t bytes, double scale) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t const big = size_t(double(bytes) * std::min(std::max(scale, 1.0), 16.0));
+        if (big > bytes && big <= (size_t(8) << 30) && ensure(big) == cudaSuccess) return cudaSuccess;
+        (void)cudaGetLastError();
+        return ensure(bytes);
+    }
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         if (p) { device_free(p); p = nullptr; }
@@ -123,6 +132,13 @@ struct DevBuf {
 struct PinnedBuf {                       // page-locked host staging memory
     void* p = nullptr;
     size_t cap = 0;
+    cudaError_t ensure_scaled(size_t bytes, double scale) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t const big = size_t(double(bytes) * std::min(std::max(scale, 1.0), 16.0));
+        if (big > bytes && big <= (size_t(1) << 30) && ensure(big) == cudaSuccess) return cudaSuccess;
+        (void)cudaGetLastError();
+        return ensure(bytes);
+    }
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         AllocTimer timer;
@@ -1356,8 +1372,27 @@ void build_walks(fxg_ctx* c, fxg_job const* J, uint32_t read_lo, uint32_t read_h
     }
 }
 
+int validate_reads_range(fxg_ctx* c, std::string& err, const fxg_read* reads, size_t lo, size_t hi, size_t pool_len,
+                         const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors);
+
+// every read's ranges, tree shape and anchors; large batches on several threads
 int validate_reads(fxg_ctx* c, std::string& err, const fxg_read* reads, size_t lo, size_t hi, size_t pool_len,
                    const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors) {
+    size_t const n_threads = (n_nodes + n_anchors) < (size_t(1) << 20) ? 1 : std::min<size_t>({size_t(8), hi - lo, std::max<size_t>(1, std::thread::hardware_concurrency() / 2)});
+    if (n_threads <= 1) return validate_reads_range(c, err, reads, lo, hi, pool_len, nodes, n_nodes, anchors, n_anchors);
+    std::vector<int> rcs(n_threads, FXG_OK); std::vector<std::string> errs(n_threads);
+    std::vector<std::thread> threads;
+    for (size_t t = 0; t < n_threads; ++t) {
+        size_t const a = lo + (hi - lo) * t / n_threads, b = lo + (hi - lo) * (t + 1) / n_threads;
+        threads.emplace_back([&, t, a, b] { rcs[t] = validate_reads_range(c, errs[t], reads, a, b, pool_len, nodes, n_nodes, anchors, n_anchors); });
+    }
+    for (auto& th : threads) th.join();
+    for (size_t t = 0; t < n_threads; ++t) if (rcs[t] != FXG_OK) { err = errs[t]; tls_last_error = err; return rcs[t]; }
+    return FXG_OK;
+}
+
+int validate_reads_range(fxg_ctx* c, std::string& err, const fxg_read* reads, size_t lo, size_t hi, size_t pool_len,
+                         const fxg_pex_node* nodes, size_t n_nodes, const fxg_anchor* anchors, size_t n_anchors) {
     for (size_t i = lo; i < hi; ++i) {
         fxg_read const& R = reads[i];
         if (R.query_offset + R.query_len > pool_len) return fail(err, FXG_ERR_INVALID_ARGUMENT, "read %zu: query outside the pool", i);
@@ -1428,6 +1463,7 @@ struct PartState {
     double cpu0 = 0;                         // the part's thread CPU time at its start (FXG_PROFILE)
     std::vector<ReadRec> part_reads;         // (device-side walks) the part's ReadRecs as the device sees them
     std::vector<fxg_alignment> hits;         // the part's alignments in anchor order, cigar offsets relative to the part's region
+    double scale = 1.0;                      // the largest merged batch over this part (buffers are sized for that batch at once)
     PartOut out;
 };
 
@@ -1454,6 +1490,19 @@ int class_of(fxg_ctx* c, Config const& cf, uint32_t words) {
     if (c->n_classes == kMaxLevelClasses) return -1;
     c->classes[c->n_classes] = ClassDef{cf.widx, cf.G, words};
     return c->n_classes++;
+}
+
+// class_of through a table of the calling thread: the context's mutex is taken only for a class the thread has not seen,
+// or when a node needs a wider Eq table than the thread has reported for the class
+int class_of_cached(fxg_ctx* c, Config const& cf, uint32_t words) {
+    struct Seen { const fxg_ctx* owner = nullptr; int id[6][66]; uint32_t words[kMaxLevelClasses]; };
+    thread_local Seen seen;
+    if (seen.owner != c) { seen.owner = c; for (auto& row : seen.id) for (int& x : row) x = -2; for (uint32_t& x : seen.words) x = 0; }
+    int& id = seen.id[cf.widx][std::min<int>(cf.G, 65)];
+    if (id >= 0 && words <= seen.words[id]) return id;
+    id = class_of(c, cf, words);
+    if (id >= 0) seen.words[id] = std::max(seen.words[id], words);
+    return id;
 }
 
 std::vector<ConfigCacheEntry>& thread_config_cache(const fxg_ctx* c) {
@@ -1532,7 +1581,7 @@ int prepare_job(fxg_ctx* c, fxg_job* J, std::string& err, fxg_counters& ctr) {
                 Config cf;
                 if (!cached_config(cache, p, c->smem_limit, c->force_wide, cf)) { out.status = 1; return; }
                 uint32_t const W = uint32_t(kWidths[cf.widx]);
-                int const ci = class_of(c, cf, (rr.root_m + 32 * W - 1) / (32 * W) * W);
+                int const ci = class_of_cached(c, cf, (rr.root_m + 32 * W - 1) / (32 * W) * W);
                 if (ci < 0) { out.status = 1; return; }
                 rr.reserved0 = uint32_t(ci);
                 // ring of G lanes: band B = n - m + 2k + 1 must satisfy G >= (B - 4) / (32 W + 1) + 3 (choose_config)
@@ -1568,7 +1617,7 @@ int prepare_job(fxg_ctx* c, fxg_job* J, std::string& err, fxg_counters& ctr) {
                     Config cf;
                     if (!cached_config(cache, p, c->smem_limit, c->force_wide, cf)) { out.status = 1; return; }
                     uint32_t const W = uint32_t(kWidths[cf.widx]);
-                    int const ci = class_of(c, cf, (r.m + 32 * W - 1) / (32 * W) * W);
+                    int const ci = class_of_cached(c, cf, (r.m + 32 * W - 1) / (32 * W) * W);
                     if (ci < 0) { out.status = 1; return; }
                     r.cls = uint8_t(ci);
                     if (q > 0) {                                   // the root is not an inner level
@@ -1647,7 +1696,7 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
     size_t const o_key2 = carve(n * 8), o_idx2 = carve(n * 4), o_key2_s = carve(n * 8), o_idx2_s = carve(n * 4);
     size_t const o_rep = carve(n * 4), o_tbcap = carve(n * 8), o_tbcig = carve(n * 8), o_tbslot = carve(n * 4);
     size_t const o_hit = carve(n * 4), o_hitat = carve(n * 4), o_ctr = carve(kRootCounters * 4);
-    CUDA_TRY(w.err, w.d_root.ensure(off));
+    CUDA_TRY(w.err, w.d_root.ensure_scaled(off, P.scale));
     uint8_t* const D = w.d_root.as<uint8_t>();
     size_t tmp_bytes = 0, t1 = 0;
     {   // temporary storage of the sorts and scans
@@ -1656,7 +1705,7 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
         cub::DeviceScan::ExclusiveSum(nullptr, t1, (const uint64_t*)nullptr, (uint64_t*)nullptr, int(n), st); tmp_bytes = std::max(tmp_bytes, t1);
         cub::DeviceScan::ExclusiveSum(nullptr, t1, (const uint32_t*)nullptr, (uint32_t*)nullptr, int(n), st); tmp_bytes = std::max(tmp_bytes, t1);
     }
-    CUDA_TRY(w.err, w.d_cub.ensure(tmp_bytes + 256));
+    CUDA_TRY(w.err, w.d_cub.ensure_scaled(tmp_bytes + 256, P.scale));
     RootCtx C{};
     C.entries = d_entries; C.n_roots = n_roots; C.reads = d_reads; C.n_reads = n_reads;
     C.ref_base = c->refs.d_base.as<uint64_t>(); C.ref_len = c->refs.d_len.as<uint64_t>();
@@ -1717,10 +1766,10 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
     for (int ci = 0; ci < kMaxLevelClasses; ++ci) class_units[ci] = ctr[kCtrClassUnits + ci];
 
     // ---- score passes, one launch per class ----
-    CUDA_TRY(w.err, w.d_tasks.ensure(size_t(n_units) * sizeof(DpTask)));
-    CUDA_TRY(w.err, w.d_results.ensure(size_t(n_units) * sizeof(DpResult)));
+    CUDA_TRY(w.err, w.d_tasks.ensure_scaled(size_t(n_units) * sizeof(DpTask), P.scale));
+    CUDA_TRY(w.err, w.d_results.ensure_scaled(size_t(n_units) * sizeof(DpResult), P.scale));
     DevBuf& ckb = w.d_ck[0];
-    if (want_cigar) CUDA_TRY(w.err, ckb.ensure(std::max<uint64_t>(ck_words, 4) * 4));
+    if (want_cigar) CUDA_TRY(w.err, ckb.ensure_scaled(std::max<uint64_t>(ck_words, 4) * 4, P.scale));
     C.tasks = w.d_tasks.as<DpTask>(); C.results = w.d_results.as<DpResult>(); C.ck = ckb.as<uint32_t>();
     root_tasks_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(C, n_units);
     CUDA_TRY(w.err, cudaGetLastError());
@@ -1795,8 +1844,9 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
     if (n_accepted == 0) { add_root_stats(); return FXG_OK; }
     // ---- tracebacks of the representatives ----
     if (want_cigar) {
-        CUDA_TRY(w.err, w.d_wtasks.ensure(size_t(n_tb) * sizeof(Walk2Task)));
-        CUDA_TRY(w.err, w.d_wresults.ensure(size_t(n_tb) * sizeof(WalkResult)));
+        CUDA_TRY(w.err, w.d_wtasks.ensure_scaled(size_t(n_tb) * sizeof(Walk2Task), P.scale));
+        CUDA_TRY(w.err, w.d_wresults.ensure_scaled(size_t(n_tb) * sizeof(WalkResult), P.scale));
+        if (w.cig_used == 0) CUDA_TRY(w.err, w.d_cigars.ensure_scaled(cig_total * 4, P.scale));
         CUDA_TRY(w.err, w.d_cigars.ensure_preserving((w.cig_used + cig_total) * 4, w.cig_used * 4, st));
         C.wtasks = w.d_wtasks.as<Walk2Task>(); C.wresults = w.d_wresults.as<WalkResult>();
         root_walks_kernel<<<grid, 256, 0, st>>>(C, w.cig_used);
@@ -1829,8 +1879,8 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
         CUDA_TRY(w.err, cudaEventRecord(w.ev_w1[0], st));
     }
     // ---- alignment records in anchor order ----
-    CUDA_TRY(w.err, w.d_hits.ensure(size_t(n_accepted) * sizeof(fxg_alignment)));
-    CUDA_TRY(w.err, w.h_hits.ensure(size_t(n_accepted) * sizeof(fxg_alignment)));
+    CUDA_TRY(w.err, w.d_hits.ensure_scaled(size_t(n_accepted) * sizeof(fxg_alignment), P.scale));
+    CUDA_TRY(w.err, w.h_hits.ensure_scaled(size_t(n_accepted) * sizeof(fxg_alignment), P.scale));
     C.out = w.d_hits.as<fxg_alignment>();
     root_hits_kernel<<<grid, 256, 0, st>>>(C);
     CUDA_TRY(w.err, cub::DeviceScan::ExclusiveSum(w.d_cub.p, tmp_bytes, C.hit, const_cast<uint32_t*>(C.hit_at), int(n), st));
@@ -1911,7 +1961,8 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     size_t const o_results = carve(size_t(n_walks) * sizeof(DpResult));
     size_t const o_rootflag = carve(n_walks), o_rootcnt = carve(size_t(n_reads) * 2 * 4), o_rootoff = carve(size_t(n_reads) * 2 * 4);
     size_t const o_inserted = carve(ivopt ? size_t(n_walks) * 4 : 0);
-    CUDA_TRY(w.err, w.d_lv.ensure(off));
+    P.scale = std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(n_walks, 1)));
+    CUDA_TRY(w.err, w.d_lv.ensure_scaled(off, P.scale));
     uint8_t* const D = w.d_lv.as<uint8_t>();
     size_t const o_member_totals = o_back + 64;
     // ---- gather the members' records (device to device), bases shifted to their place in this part ----
@@ -2075,8 +2126,8 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     if (n_roots == 0) return FXG_OK;
     if (n_roots > n_walks) return fail(w.err, FXG_ERR_CUDA, "internal: more root walks than walks");
     // ---- the walks that verify their root, in anchor order ----
-    CUDA_TRY(w.err, w.d_roots.ensure(size_t(n_roots) * sizeof(RootEntry)));
-    CUDA_TRY(w.err, w.h_roots.ensure(size_t(n_roots) * sizeof(RootEntry)));
+    CUDA_TRY(w.err, w.d_roots.ensure_scaled(size_t(n_roots) * sizeof(RootEntry), P.scale));
+    CUDA_TRY(w.err, w.h_roots.ensure_scaled(size_t(n_roots) * sizeof(RootEntry), P.scale));
     root_emit_kernel<<<pair_grid, 128, 0, st>>>(Dc, d_rootoff, w.d_roots.as<RootEntry>());
     CUDA_TRY(w.err, cudaGetLastError());
     w.ctr.kernel_launches++;
@@ -2457,6 +2508,7 @@ struct TracePlan {
     std::vector<uint64_t> caps, bases;
     PinnedBuf* pool = nullptr; size_t* pool_len = nullptr;
     fxg_ctx* ctx = nullptr;
+    double scale = 1.0;
     bool failed = false; std::string err;
     void arrive_and_wait(size_t part, uint64_t cap) {
         std::unique_lock<std::mutex> lock(mu);
@@ -2470,7 +2522,7 @@ struct TracePlan {
                 PinnedBuf fit = take_pinned_fit(ctx, need);
                 if (fit.p) { give_pinned(ctx, *pool); *pool = fit; }
             }
-            cudaError_t const e = pool->ensure(need);
+            cudaError_t const e = pool->ensure_scaled(need, scale);
             if (e != cudaSuccess) { failed = true; err = std::string("cigar pool allocation: ") + cudaGetErrorString(e); }
             *pool_len = size_t(total);
             cv.notify_all();
@@ -2837,6 +2889,7 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     TracePlan plan;
     plan.n_parts = n_parts; plan.caps.assign(n_parts, 0); plan.bases.assign(n_parts, 0);
     plan.pool = B.cigars; plan.pool_len = &B.cigars_len; plan.ctx = c;
+    plan.scale = std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(rwb[n_reads], 1)));
     auto const vt0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - vt0).count(); };
     uint64_t const budget = trace_budget_bytes(c, n_parts);
@@ -2901,7 +2954,11 @@ int build_merged_pool(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err) 
     Pool& P = grp.merged;
     P.len = at; P.inline_len = 0;
     P.plane_words = at / 32 + kPeqFrontPadWords + kPeqBackPadWords;
-    CUDA_TRY(err, P.peq.ensure(P.plane_words * kNumSymbols * 4));
+    {
+        uint64_t walks = 0;
+        for (Member const& M : B.members) walks += M.J->prep.n_walks;
+        CUDA_TRY(err, P.peq.ensure_scaled(P.plane_words * kNumSymbols * 4, std::max(1.0, double(c->merge_max_walks) / double(std::max<uint64_t>(walks, 1)))));
+    }
     cudaStream_t const st = grp.workers[0]->stream;
     (void)c;
     for (Member const& M : B.members) {
@@ -3190,7 +3247,10 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     if (!c->spare_dev.empty()) { j->prep.dev = c->spare_dev.back(); c->spare_dev.pop_back(); }
     lock.unlock();
     std::string err; fxg_counters ctr{};
+    auto const tp0 = std::chrono::steady_clock::now();
+    auto lap_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count(); };
     rc = validate_reads(c, err, reads, 0, n_reads, pool_len, nodes, n_nodes, anchors, n_anchors);
+    double const t_validate = lap_ms();
     if (rc == FXG_OK) {
         index_walks(j);
         // (ranks above 5 in the query pools are detected by the Peq builder on the device and reported after the run:
@@ -3199,7 +3259,9 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     }
     if (rc == FXG_OK && cudaEventCreateWithFlags(&j->pool_ready, cudaEventDisableTiming) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "cannot create an event");
     if (rc == FXG_OK && cudaEventRecord(j->pool_ready, c->stage_stream) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "staging failed");
+    double const t_stage = lap_ms();
     if (rc == FXG_OK) rc = prepare_job(c, j, err, ctr);
+    double const t_prepare = lap_ms();
     lock.lock();
     add_counters(c->ctr, ctr);
     if (rc == FXG_OK) {
@@ -3207,6 +3269,7 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
         if (rc != FXG_OK) err = c->err;
     }
     lock.unlock();
+    if (g_prof.on) fprintf(stderr, "[fxg] verify_reads: validated %.3f, pools enqueued %.3f, records prepared %.3f, run done %.3f ms\n", t_validate, t_stage, t_prepare, lap_ms());
     if (rc == FXG_OK) {
         uint32_t bad = 0;
         if (cudaMemcpyAsync(&bad, j->pool.bad_rank.p, 4, cudaMemcpyDeviceToHost, c->stage_stream) != cudaSuccess ||
