@@ -1126,7 +1126,7 @@ __device__ __forceinline__ void emit_level_task(LevelCtx const& C, uint32_t i, N
     t.flags = 0; t.out = i;
     C.tasks[slot] = t;
     // word-steps the engine issues for it (host: word_steps_of): block b works on columns cs(b)..ce(b)
-    uint32_t const W = C.cls_W[N.cls], rows = 32 * W, nb = (N.m + rows - 1) / rows;
+    uint32_t const W = C.cls_W[N.cls], rows = 32 * W, nb = W ? (N.m + rows - 1) / rows : 0;
     int64_t const pad = int64_t(nb) * rows - N.m;
     unsigned long long ws = 0;
     for (uint32_t b = 0; b < nb; ++b) {

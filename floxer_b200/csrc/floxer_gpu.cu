@@ -312,7 +312,10 @@ struct Ticket;
 
 }  // namespace
 
+std::atomic<uint64_t> g_ctx_serial{0};
+
 struct fxg_ctx {
+    uint64_t serial = ++g_ctx_serial;     // never reused, unlike the context's address
     int device = 0;
     std::string err;
     RefStore refs;
@@ -1495,9 +1498,10 @@ int class_of(fxg_ctx* c, Config const& cf, uint32_t words) {
 // class_of through a table of the calling thread: the context's mutex is taken only for a class the thread has not seen,
 // or when a node needs a wider Eq table than the thread has reported for the class
 int class_of_cached(fxg_ctx* c, Config const& cf, uint32_t words) {
-    struct Seen { const fxg_ctx* owner = nullptr; int id[6][66]; uint32_t words[kMaxLevelClasses]; };
+    struct Seen { uint64_t owner = 0; int id[6][66]; uint32_t words[kMaxLevelClasses]; };
     thread_local Seen seen;
-    if (seen.owner != c) { seen.owner = c; for (auto& row : seen.id) for (int& x : row) x = -2; for (uint32_t& x : seen.words) x = 0; }
+    // (a new context may live at a freed one's address: contexts are told apart by their serial numbers)
+    if (seen.owner != c->serial) { seen.owner = c->serial; for (auto& row : seen.id) for (int& x : row) x = -2; for (uint32_t& x : seen.words) x = 0; }
     int& id = seen.id[cf.widx][std::min<int>(cf.G, 65)];
     if (id >= 0 && words <= seen.words[id]) return id;
     id = class_of(c, cf, words);
@@ -1507,8 +1511,8 @@ int class_of_cached(fxg_ctx* c, Config const& cf, uint32_t words) {
 
 std::vector<ConfigCacheEntry>& thread_config_cache(const fxg_ctx* c) {
     thread_local std::vector<ConfigCacheEntry> cache(8192);
-    thread_local const fxg_ctx* owner = nullptr;
-    if (owner != c) { for (ConfigCacheEntry& e : cache) e.valid = false; owner = c; }      // (contexts may differ in their knobs)
+    thread_local uint64_t owner = 0;
+    if (owner != c->serial) { for (ConfigCacheEntry& e : cache) e.valid = false; owner = c->serial; }      // (contexts may differ in their knobs)
     return cache;
 }
 
@@ -1937,6 +1941,8 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     uint32_t const n_reads = r1 - r0;
     P.walks.clear(); P.hits.clear();
     if (n_walks == 0) return FXG_OK;
+    for (uint32_t d = 0; d < 256; ++d)
+        if (level_mask[d] >> c->n_classes) return fail(w.err, FXG_ERR_STATE, "internal: a job's records name a configuration class the context does not have");
     bool const ivopt = B.cfg.interval_optimization != 0;
     bool const direct = B.cfg.verification_kind == FXG_KIND_DIRECT_FULL;
     size_t const n_members = B.members.size();
