@@ -88,8 +88,8 @@ struct DevBuf {
     //  `scale` = that batch's size over this one's)
     cudaError_t ensure_scaled(size_t bytes, double scale) {
         if (bytes <= cap) return cudaSuccess;
-        size_t const big = size_t(double(bytes) * std::min(std::max(scale, 1.0), 16.0));
-        if (big > bytes && big <= (size_t(8) << 30) && ensure(big) == cudaSuccess) return cudaSuccess;
+        size_t const big = std::min(size_t(double(bytes) * std::min(std::max(scale, 1.0), 16.0)), std::max(bytes, size_t(2) << 30));
+        if (big > bytes && ensure(big) == cudaSuccess) return cudaSuccess;
         (void)cudaGetLastError();
         return ensure(bytes);
     }
@@ -134,8 +134,8 @@ struct PinnedBuf {                       // page-locked host staging memory
     size_t cap = 0;
     cudaError_t ensure_scaled(size_t bytes, double scale) {
         if (bytes <= cap) return cudaSuccess;
-        size_t const big = size_t(double(bytes) * std::min(std::max(scale, 1.0), 16.0));
-        if (big > bytes && big <= (size_t(1) << 30) && ensure(big) == cudaSuccess) return cudaSuccess;
+        size_t const big = std::min(size_t(double(bytes) * std::min(std::max(scale, 1.0), 16.0)), std::max(bytes, size_t(96) << 20));   // (page-locking is slow: tens of ms per 100 MB)
+        if (big > bytes && ensure(big) == cudaSuccess) return cudaSuccess;
         (void)cudaGetLastError();
         return ensure(bytes);
     }
@@ -1467,6 +1467,8 @@ struct PartState {
     std::vector<ReadRec> part_reads;         // (device-side walks) the part's ReadRecs as the device sees them
     std::vector<fxg_alignment> hits;         // the part's alignments in anchor order, cigar offsets relative to the part's region
     double scale = 1.0;                      // the largest merged batch over this part (buffers are sized for that batch at once)
+    size_t n_parts = 1;
+    double t_mark[6] = {0, 0, 0, 0, 0, 0};   // (FXG_TRACE_BATCHES) ms since the part began: gathered+enqueued, levels done, units known, scores known, records back
     PartOut out;
 };
 
@@ -1754,6 +1756,7 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
     w.ctr.kernel_launches += 6;
     int rc = read_back();
     if (rc != FXG_OK) return rc;
+    P.t_mark[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count();
     g_prof.lap(w, 7);
     uint32_t const n_feasible = ctr[kCtrFeasible], n_units = ctr[kCtrUnits];
     uint64_t const ck_words = ctr64(kCtrCkWords);
@@ -1835,6 +1838,7 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
         float ms = 0;
         if (cudaEventElapsedTime(&ms, w.ev_b0, w.ev_b1) == cudaSuccess) { w.ctr.root_launch_ms += ms; }
     }
+    P.t_mark[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count();
     g_prof.lap(w, 11);
     if (ctr[kCtrErrors]) return fail(w.err, FXG_ERR_CUDA, "internal: the DP engine lost track of its window buffer");
     if (ctr[kCtrSlow]) return kRootFallback;             // a shared pass cannot vouch for one of its members: the host's way scores it again
@@ -1899,6 +1903,7 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
         float ms = 0;
         if (cudaEventElapsedTime(&ms, w.ev_w0, w.ev_w1[0]) == cudaSuccess) w.ctr.trace_kernel_ms += ms;
     }
+    P.t_mark[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count();
     g_prof.lap(w, 12);
     if (ctr[kCtrErrors]) return fail(w.err, FXG_ERR_CUDA, "internal: the traceback of an alignment disagrees with its score pass");
     add_root_stats();
@@ -1967,7 +1972,8 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     size_t const o_results = carve(size_t(n_walks) * sizeof(DpResult));
     size_t const o_rootflag = carve(n_walks), o_rootcnt = carve(size_t(n_reads) * 2 * 4), o_rootoff = carve(size_t(n_reads) * 2 * 4);
     size_t const o_inserted = carve(ivopt ? size_t(n_walks) * 4 : 0);
-    P.scale = std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(n_walks, 1)));
+    // (only the worker that runs merged batches -- one part per batch -- sizes its buffers for the largest of them)
+    P.scale = P.n_parts == 1 ? std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(n_walks, 1))) : 1.0;
     CUDA_TRY(w.err, w.d_lv.ensure_scaled(off, P.scale));
     uint8_t* const D = w.d_lv.as<uint8_t>();
     size_t const o_member_totals = o_back + 64;
@@ -2114,7 +2120,9 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     CUDA_TRY(w.err, w.h_lv_back.ensure(back_bytes));
     CUDA_TRY(w.err, cudaMemcpyAsync(w.h_lv_back.p, D + o_back, back_bytes, cudaMemcpyDeviceToHost, st));
     g_prof.lap(w, 6);
+    P.t_mark[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count();
     CUDA_TRY(w.err, w.wait_for(st));
+    P.t_mark[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count();
     float ms = 0;
     CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev0, w.ev1));
     w.ctr.dp_kernel_ms += ms;
@@ -2883,7 +2891,9 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     std::vector<uint32_t> const& rwb = B.read_walk_begin;
     // (a batch merged from several callers' jobs runs as few parts as possible: its point is launches that fill the machine)
     size_t const max_parts = B.members.size() > 1 ? std::min<size_t>(grp.use_workers, size_t(c->merged_parts)) : grp.use_workers;
-    size_t const n_parts = std::min<size_t>(max_parts, std::max<size_t>(1, std::min<size_t>(n_reads, size_t(rwb[n_reads]) / 4096 + 1)));
+    // (the host's share of a batch is small since the walks and the root level run on the device: parts are worth their split
+    //  launches only where the phases of one part can hide behind another's -- half a million anchors each at least)
+    size_t const n_parts = std::min<size_t>(max_parts, std::max<size_t>(1, std::min<size_t>(n_reads, size_t(rwb[n_reads]) / (B.device ? (size_t(1) << 19) : size_t(4096)) + 1)));
     std::vector<uint32_t> cut(n_parts + 1, 0);
     for (size_t p = 1; p < n_parts; ++p) {
         uint64_t const target = uint64_t(rwb[n_reads]) * p / n_parts;
@@ -2895,7 +2905,7 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     TracePlan plan;
     plan.n_parts = n_parts; plan.caps.assign(n_parts, 0); plan.bases.assign(n_parts, 0);
     plan.pool = B.cigars; plan.pool_len = &B.cigars_len; plan.ctx = c;
-    plan.scale = std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(rwb[n_reads], 1)));
+    plan.scale = n_parts == 1 ? std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(rwb[n_reads], 1))) : 1.0;
     auto const vt0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - vt0).count(); };
     uint64_t const budget = trace_budget_bytes(c, n_parts);
@@ -2903,7 +2913,7 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     auto run_part = [&](size_t p) {
         Worker& w = *grp.workers[p];
         PartState& P = parts[p];
-        P.trace_budget = budget;
+        P.trace_budget = budget; P.n_parts = n_parts;
         verify_part_score(c, w, B, cut[p], cut[p + 1], P);
         g_prof.start(w);
         plan.arrive_and_wait(p, P.out.rc == FXG_OK ? w.cig_used : 0);        // every part arrives, also a failed one
@@ -2941,9 +2951,10 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     static bool const trace_batches = std::getenv("FXG_TRACE_BATCHES") != nullptr;
     if (trace_batches) {
         static auto const epoch = std::chrono::steady_clock::now();
-        fprintf(stderr, "[fxg] batch at %.3f ms: %zu jobs, %u walks, %zu parts, %.3f ms (alloc so far %.1f ms in %llu calls)\n",
+        fprintf(stderr, "[fxg] batch at %.3f ms: %zu jobs, %u walks, %zu parts, %.3f ms (alloc so far %.1f ms in %llu calls); part 0: enqueued %.2f levels %.2f units %.2f scores %.2f records %.2f\n",
                 std::chrono::duration<double, std::milli>(vt0 - epoch).count(), B.members.size(), rwb[n_reads], n_parts, since(),
-                double(g_alloc_ns.load()) * 1e-6, (unsigned long long)g_alloc_calls.load());
+                double(g_alloc_ns.load()) * 1e-6, (unsigned long long)g_alloc_calls.load(),
+                parts[0].t_mark[0], parts[0].t_mark[1], parts[0].t_mark[2], parts[0].t_mark[3], parts[0].t_mark[4]);
     }
     if (g_prof.on) fprintf(stderr, "[fxg] run_batch: %zu jobs, %zu reads, %u walks, %zu parts; parts done %.3f ms, merged %.3f ms\n", B.members.size(), n_reads,
                            rwb[n_reads], n_parts, t_join, since());
