@@ -417,6 +417,7 @@ def main() -> int:
     ap.add_argument("--config3-reads", type=int, default=10_000)
     ap.add_argument("--config4-reads", type=int, default=2_500, help="reads of the 12 500-read shard that are generated and verified")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="wall time of every CPU baseline sample")
+    ap.add_argument("--big-lanes", type=int, default=2, help="host threads that submit batches concurrently (configs 3 and 4: one batch fills the machine)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -507,8 +508,8 @@ def main() -> int:
     head, sub = None, {}
     int32_peak = None
     plan = [("config2", False, args.lanes, args.steps, True), ("config2", True, args.lanes, args.steps, False),
-            ("config3", False, 3, max(3, args.steps // 4), False), ("config3", True, 3, max(3, args.steps // 4), False),
-            ("config4_shard", False, 2, max(3, args.steps // 5), False), ("config4_shard", True, 2, max(3, args.steps // 5), False)]
+            ("config3", False, args.big_lanes, max(3, args.steps // 4), False), ("config3", True, args.big_lanes, max(3, args.steps // 4), False),
+            ("config4_shard", False, args.big_lanes, max(3, args.steps // 5), False), ("config4_shard", True, args.big_lanes, max(3, args.steps // 5), False)]
     current = None
     for name, ivopt, lanes, steps, is_head in plan:
         key = name + ("_ivopt" if ivopt else "")

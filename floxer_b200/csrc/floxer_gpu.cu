@@ -96,7 +96,7 @@ struct DevBuf {
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         if (p) { device_free(p); p = nullptr; }
-        size_t const want = std::max(bytes + bytes / 4 + 256, 2 * cap);      // grows geometrically: few replacements on the way to the steady state
+        size_t const want = ((bytes + (size_t(1) << 20)) >> 20) << 20;        // whole MiB: blocks of like sizes are found again in the pool
         cap = 0;
         cudaError_t e = device_alloc(&p, want);
         if (e != cudaSuccess) {
@@ -222,6 +222,13 @@ struct Worker {
     std::vector<uint64_t> keys, keys_tmp;
     std::vector<Config> cfgs;
     uint64_t cig_used = 0;               // ops of d_cigars filled by the current run
+    // The device buffers go back to the device's memory pool when a batch is done (they are stream-ordered allocations, and
+    // the pool keeps what is freed): the next batch -- on whichever worker -- gets them back in microseconds, and the
+    // footprint is that of the batches in flight, not of every worker's largest batch ever.
+    void release_device() {
+        for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults, &d_lv, &d_roots, &d_root, &d_cub, &d_hits}) b->release();
+        for (int q = 0; q < kWalkSlots; ++q) d_ck[q].release();
+    }
     void release() {
         for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults, &d_lv, &d_roots, &d_root, &d_cub, &d_hits}) b->release();
         if (ev_w0) { cudaEventDestroy(ev_w0); ev_w0 = nullptr; }
@@ -1768,7 +1775,6 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
         }
     };
     if (n_feasible == 0 || n_units == 0) { add_root_stats(); return FXG_OK; }
-    if (ck_words * 4 > std::max<uint64_t>(P.trace_budget, uint64_t(256) << 20)) return kRootFallback;       // (the host's way works in chunks)
     uint32_t class_units[kMaxLevelClasses];
     for (int ci = 0; ci < kMaxLevelClasses; ++ci) class_units[ci] = ctr[kCtrClassUnits + ci];
 
@@ -1776,7 +1782,10 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
     CUDA_TRY(w.err, w.d_tasks.ensure_scaled(size_t(n_units) * sizeof(DpTask), P.scale));
     CUDA_TRY(w.err, w.d_results.ensure_scaled(size_t(n_units) * sizeof(DpResult), P.scale));
     DevBuf& ckb = w.d_ck[0];
-    if (want_cigar) CUDA_TRY(w.err, ckb.ensure_scaled(std::max<uint64_t>(ck_words, 4) * 4, P.scale));
+    if (want_cigar && ckb.ensure_scaled(std::max<uint64_t>(ck_words, 4) * 4, P.scale) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return kRootFallback;                            // no room for all the checkpoint records at once: the host's way works in chunks
+    }
     C.tasks = w.d_tasks.as<DpTask>(); C.results = w.d_results.as<DpResult>(); C.ck = ckb.as<uint32_t>();
     root_tasks_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(C, n_units);
     CUDA_TRY(w.err, cudaGetLastError());
@@ -1973,7 +1982,7 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     size_t const o_rootflag = carve(n_walks), o_rootcnt = carve(size_t(n_reads) * 2 * 4), o_rootoff = carve(size_t(n_reads) * 2 * 4);
     size_t const o_inserted = carve(ivopt ? size_t(n_walks) * 4 : 0);
     // (only the worker that runs merged batches -- one part per batch -- sizes its buffers for the largest of them)
-    P.scale = P.n_parts == 1 ? std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(n_walks, 1))) : 1.0;
+    P.scale = 1.0;
     CUDA_TRY(w.err, w.d_lv.ensure_scaled(off, P.scale));
     uint8_t* const D = w.d_lv.as<uint8_t>();
     size_t const o_member_totals = o_back + 64;
@@ -2931,6 +2940,7 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     }
     double const t_join = since();
     g_prof.report();
+    for (size_t p = 0; p < n_parts; ++p) grp.workers[p]->release_device();
     for (size_t p = 0; p < n_parts; ++p) {
         add_counters(ctr, grp.workers[p]->ctr);
         if (parts[p].out.rc != FXG_OK) { err = grp.workers[p]->err; return parts[p].out.rc; }
