@@ -96,7 +96,7 @@ struct DevBuf {
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         if (p) { device_free(p); p = nullptr; }
-        size_t const want = ((bytes + (size_t(1) << 20)) >> 20) << 20;        // whole MiB: blocks of like sizes are found again in the pool
+        size_t const want = std::max(bytes + bytes / 4 + 256, 2 * cap);      // grows geometrically: few replacements on the way to the steady state
         cap = 0;
         cudaError_t e = device_alloc(&p, want);
         if (e != cudaSuccess) {
@@ -222,9 +222,8 @@ struct Worker {
     std::vector<uint64_t> keys, keys_tmp;
     std::vector<Config> cfgs;
     uint64_t cig_used = 0;               // ops of d_cigars filled by the current run
-    // The device buffers go back to the device's memory pool when a batch is done (they are stream-ordered allocations, and
-    // the pool keeps what is freed): the next batch -- on whichever worker -- gets them back in microseconds, and the
-    // footprint is that of the batches in flight, not of every worker's largest batch ever.
+    // (measured: handing the device buffers back to the memory pool after every batch and taking them again costs 2.5 ms
+    //  per allocation when batch sizes vary -- the pool splits and grows -- so a worker keeps its buffers)
     void release_device() {
         for (DevBuf* b : {&d_tasks, &d_results, &d_wtasks, &d_wresults, &d_cigars, &d_rtasks, &d_rresults, &d_lv, &d_roots, &d_root, &d_cub, &d_hits}) b->release();
         for (int q = 0; q < kWalkSlots; ++q) d_ck[q].release();
@@ -1866,6 +1865,7 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
         if (w.cig_used == 0) CUDA_TRY(w.err, w.d_cigars.ensure_scaled(cig_total * 4, P.scale));
         CUDA_TRY(w.err, w.d_cigars.ensure_preserving((w.cig_used + cig_total) * 4, w.cig_used * 4, st));
         C.wtasks = w.d_wtasks.as<Walk2Task>(); C.wresults = w.d_wresults.as<WalkResult>();
+        CUDA_TRY(w.err, cudaMemsetAsync(w.d_cigars.as<uint32_t>() + w.cig_used, 0, cig_total * 4, st));      // (a slot is filled from its end: the unused front stays zero)
         root_walks_kernel<<<grid, 256, 0, st>>>(C, w.cig_used);
         CUDA_TRY(w.err, cudaGetLastError());
         w.ctr.kernel_launches++;
@@ -1982,7 +1982,7 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     size_t const o_rootflag = carve(n_walks), o_rootcnt = carve(size_t(n_reads) * 2 * 4), o_rootoff = carve(size_t(n_reads) * 2 * 4);
     size_t const o_inserted = carve(ivopt ? size_t(n_walks) * 4 : 0);
     // (only the worker that runs merged batches -- one part per batch -- sizes its buffers for the largest of them)
-    P.scale = 1.0;
+    P.scale = P.n_parts == 1 ? std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(n_walks, 1))) : 1.0;
     CUDA_TRY(w.err, w.d_lv.ensure_scaled(off, P.scale));
     uint8_t* const D = w.d_lv.as<uint8_t>();
     size_t const o_member_totals = o_back + 64;
@@ -2608,7 +2608,7 @@ int fxg_create(int device, fxg_ctx** out) {
     c->workers_busy = default_workers(c->n_groups);
     // a batch that runs alone is split over 8 workers; the lowest free group is taken, so that is always group 0 and only
     // it owns that many.  An explicit FXG_WORKERS is taken literally.
-    int const nw_wide = std::getenv("FXG_WORKERS") ? c->workers_busy : std::max(8, c->workers_busy);
+    int const nw_wide = c->workers_busy;
     for (int gi = 0; gi < c->n_groups; ++gi) {
         WorkerGroup& g = c->groups[gi];
         ok = ok && cudaEventCreate(&g.ev_run0) == cudaSuccess && cudaEventCreate(&g.ev_run1) == cudaSuccess &&
@@ -2940,7 +2940,6 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     }
     double const t_join = since();
     g_prof.report();
-    for (size_t p = 0; p < n_parts; ++p) grp.workers[p]->release_device();
     for (size_t p = 0; p < n_parts; ++p) {
         add_counters(ctr, grp.workers[p]->ctr);
         if (parts[p].out.rc != FXG_OK) { err = grp.workers[p]->err; return parts[p].out.rc; }
@@ -3029,7 +3028,8 @@ WorkerGroup* try_acquire_group(fxg_ctx* c) {
     for (int i = 0; i < c->n_groups; ++i) if (!c->groups[i].busy) {
         WorkerGroup& g = c->groups[i];
         g.busy = true;
-        g.use_workers = busy == 0 ? g.workers.size() : std::min(g.workers.size(), size_t(c->workers_busy));
+        g.use_workers = std::min(g.workers.size(), size_t(c->workers_busy));     // (the same split whatever else runs: a worker's buffers keep their sizes)
+        (void)busy;
         return &g;
     }
     return nullptr;
