@@ -1118,8 +1118,33 @@ __device__ __forceinline__ uint32_t class_offset(const uint32_t* __restrict__ cl
     return o;
 }
 
+// Counters that every thread of a kernel bumps are bumped once per warp: tens of millions of atomics on one address
+// (one per false-positive anchor of a config-4 batch) would otherwise take longer than the alignments themselves.
+// Both may be called from divergent code: the lanes that arrive together share one atomic.
+__device__ __forceinline__ void warp_add(unsigned long long* addr, unsigned long long v) {          // v < 2^50
+    unsigned const active = __activemask();
+    unsigned const lo = __reduce_add_sync(active, unsigned(v & 0xffffffu)), hi = __reduce_add_sync(active, unsigned(v >> 24));
+    if ((threadIdx.x & 31u) == unsigned(__ffs(int(active)) - 1)) atomicAdd(addr, (unsigned long long)lo + ((unsigned long long)hi << 24));
+}
+__device__ __forceinline__ void warp_add_keyed(unsigned long long* base, uint32_t stride, uint32_t key, unsigned long long v) {   // base[key * stride] += v
+    unsigned const active = __activemask();
+    unsigned const peers = __match_any_sync(active, key);
+    unsigned const lo = __reduce_add_sync(peers, unsigned(v & 0xffffffu)), hi = __reduce_add_sync(peers, unsigned(v >> 24));
+    if ((threadIdx.x & 31u) == unsigned(__ffs(int(peers)) - 1)) atomicAdd(base + size_t(key) * stride, (unsigned long long)lo + ((unsigned long long)hi << 24));
+}
+__device__ __forceinline__ uint32_t warp_slot(uint32_t* counters, uint32_t key) {                  // atomicAdd(counters + key, 1), one atomic per key and warp
+    unsigned const active = __activemask();
+    unsigned const peers = __match_any_sync(active, key);
+    unsigned const lane = threadIdx.x & 31u;
+    int const leader = __ffs(int(peers)) - 1;
+    uint32_t base = 0;
+    if (int(lane) == leader) base = atomicAdd(counters + key, uint32_t(__popc(peers)));
+    base = __shfl_sync(peers, base, leader);
+    return base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
+}
+
 __device__ __forceinline__ void emit_level_task(LevelCtx const& C, uint32_t i, NodeRec const& N, uint64_t qoff) {
-    uint32_t const slot = class_offset(C.class_active, N.cls) + atomicAdd(C.counts + N.cls, 1u);
+    uint32_t const slot = class_offset(C.class_active, N.cls) + warp_slot(C.counts, N.cls);
     DpTask t;
     t.ref_base = C.ask_ws[i]; t.query_base = qoff + N.from; t.trace_base = 0;
     t.n = C.ask_len[i]; t.m = N.m; t.dlo = -int32_t(N.k); t.dhi = int32_t(t.n) - int32_t(N.m) + int32_t(N.k);
@@ -1135,8 +1160,8 @@ __device__ __forceinline__ void emit_level_task(LevelCtx const& C, uint32_t i, N
         if (hi > int64_t(t.n)) hi = t.n;
         if (hi >= lo) ws += (unsigned long long)(hi - lo + 1) * W;
     }
-    atomicAdd(C.totals, 1ull);
-    atomicAdd(C.totals + 1, ws);
+    warp_add(C.totals, 1ull);
+    warp_add(C.totals + 1, ws);
 }
 
 __global__ void level_begin_kernel(LevelCtx const C) {
@@ -1210,7 +1235,7 @@ __global__ void level_second_kernel(LevelCtx const C) {
     if (ws == C.ask_ws[a] && len == C.ask_len[a]) { if (a_yes) C.flag[i] = f | kWalkYes; return; }                           // the same window
     bool const same_ref = C.walks[a].ref_id == Wk.ref_id;
     if (a_yes) {
-        if (same_ref && ws + len >= C.ask_ws[a] + R.end_col) { C.flag[i] = f | kWalkYes; atomicAdd(C.totals + 2, 1ull); return; }
+        if (same_ref && ws + len >= C.ask_ws[a] + R.end_col) { C.flag[i] = f | kWalkYes; warp_add(C.totals + 2, 1ull); return; }
     } else if (same_ref) {
         uint32_t const c = uint32_t(C.rep_min[key] & kWalkMask);
         if (C.walks[c].ref_id == Wk.ref_id && C.ask_ws[a] - C.ask_ws[c] <= uint64_t(N.k) + 1) {
@@ -1233,12 +1258,12 @@ __global__ void level_third_kernel(LevelCtx const C) {
     WalkRec const Wk = C.walks[i];
     uint32_t const c = uint32_t(C.rep_min[size_t(nd) * 2 + Wk.orient] & kWalkMask);
     DpResult const R = C.results[c];
-    if (R.score > int32_t(N.k)) { atomicAdd(C.totals + 2, 1ull); return; }                    // no alignment in A, none in C: none in B
+    if (R.score > int32_t(N.k)) { warp_add(C.totals + 2, 1ull); return; }                    // no alignment in A, none in C: none in B
     uint64_t const ws = C.ask_ws[i]; uint32_t const len = C.ask_len[i];
     uint64_t const end = C.ask_ws[c] + R.end_col;                                             // exclusive end of C's alignment
     if ((ws == C.ask_ws[c] && len == C.ask_len[c]) ||
         (end <= ws + len && int64_t(end) - int64_t(N.m) - int64_t(R.score) >= int64_t(ws))) {
-        C.flag[i] = f | kWalkYes; atomicAdd(C.totals + 2, 1ull); return;
+        C.flag[i] = f | kWalkYes; warp_add(C.totals + 2, 1ull); return;
     }
     emit_level_task(C, i, N, Wk.qoff);
     C.flag[i] = f | kWalkComputed;

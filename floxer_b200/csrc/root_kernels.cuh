@@ -98,12 +98,13 @@ __global__ void root_prepare_kernel(RootCtx const C) {
     uint64_t const ws = C.ref_base[e.ref_id] + start;
     C.ws[q] = ws; C.len[q] = uint32_t(len); C.read[q] = r; C.orient[q] = uint8_t(orient);
     // statistics of the root alignment (verification.cpp:238-242): counted whether or not a pass is needed
-    unsigned long long* const T = C.member_totals + size_t(R.member) * kMemberTotals;
-    atomicAdd(T + 5, 1ull); atomicAdd(T + 6, (unsigned long long)len); atomicAdd(T + 7, (unsigned long long)R.root_m * len);
+    warp_add_keyed(C.member_totals + 5, kMemberTotals, R.member, 1ull);
+    warp_add_keyed(C.member_totals + 6, kMemberTotals, R.member, (unsigned long long)len);
+    warp_add_keyed(C.member_totals + 7, kMemberTotals, R.member, (unsigned long long)R.root_m * len);
     bool const feasible = R.root_m != 0 && int64_t(R.root_m) - int64_t(len) <= int64_t(R.root_k);   // else more insertions needed than errors allowed
     C.key[q] = feasible ? ((uint64_t(r * 2 + orient) << kPosBits) | ws) : ~uint64_t(0);
     C.idx[q] = q;
-    if (feasible) atomicAdd(C.counters + kCtrFeasible, 1u);
+    if (feasible) (void)warp_slot(C.counters, kCtrFeasible);
 }
 
 // ---- units: greedy clustering of a read and strand's windows, sorted by start ----
@@ -243,7 +244,7 @@ __global__ void root_results_kernel(RootCtx const C) {
     uint8_t f = 0;
     if (U.count > 1) {
         f |= kMemberMulti;
-        atomicAdd(C.counters + kCtrShared, 1u);
+        (void)warp_slot(C.counters, kCtrShared);
         R = range_min_of(C.ck, U.ck_base, U.n, U.m, -int32_t(U.k), int32_t(U.n) - int32_t(U.m) + int32_t(U.k), C.classes[U.cls].W, shift + 1, shift + len, R);
     }
     if (R.score == kPoisonScore) atomicAdd(C.counters + kCtrErrors, 1u);
@@ -254,7 +255,7 @@ __global__ void root_results_kernel(RootCtx const C) {
         if ((f & kMemberMulti) && !safe) atomicAdd(C.counters + kCtrSlow, 1u);         // the shared pass cannot vouch for it
         else {
             f |= kMemberAccepted | (safe ? kMemberSafe : 0);
-            atomicAdd(C.counters + kCtrAccepted, 1u);
+            (void)warp_slot(C.counters, kCtrAccepted);
             if (safe && C.want_cigar) key2 = (uint64_t(U.pair) << kPosBits) | (U.ws + R.end_col);
         }
     }
