@@ -204,7 +204,12 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
             flush.fill_(1)                               # 256 MiB written between steps (queued on torch's stream, no host sync)
             j.run()
         return f
+    # warm-up: the W steps asked for, and on until two seconds have passed -- the queue's workers size their buffers for
+    # the batches they meet, and the first batches of every size pay for that (page-locking memory takes tens of ms)
+    t_warm = time.perf_counter()
     run_lanes([resident_step(j) for j in jobs], max(warmup, 3))
+    while time.perf_counter() - t_warm < 2.0:
+        run_lanes([resident_step(j) for j in jobs], 2)
     # one batch at a time first: its latency, and its device time between the run's first and last operation
     lat_ms = []
     for it in range(3):
@@ -267,7 +272,10 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
                     del a2, c2
                     j2.free()
                     last[i] = None
-        run_lanes([e2e_step(i) for i in range(lanes)], 2)        # warm-up (page-locked pools are allocated once)
+        t_w = time.perf_counter()
+        run_lanes([e2e_step(i) for i in range(lanes)], 3)        # warm-up (page-locked pools are allocated once)
+        while time.perf_counter() - t_w < 1.0:
+            run_lanes([e2e_step(i) for i in range(lanes)], 2)
         check_and_free()
         barrier()
         ctx.reset_counters()
