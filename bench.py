@@ -48,7 +48,7 @@ ROUND1_ANCHORS = dict(seed_errors=2, decoy_fraction=0.25)       # the stand-in s
 
 def describe(name: str, ivopt: bool, n_reads: int, anchors: str) -> str:
     from floxer_b200 import workloads as W
-    c = W.CONFIGS[name]
+    c = W.CONFIGS[name.replace("_seeded", "")]
     ref = f"{sum(c['ref_lens'])} bp in {len(c['ref_lens'])} record(s)" + (f", {c['families']} repeat families" if c.get("families") else ", uniform random")
     return (f"{name}: reference {ref}; {n_reads} simulated reads x {c['read_len']} bp at {int(c['error'] * 100)} % error per GPU; "
             f"recursive PEX tree, seed errors 2, hierarchical verification, interval optimization {'on' if ivopt else 'off'}, "
@@ -420,7 +420,7 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--only", default="", help="comma-separated subset of: config2,config2_ivopt,config3,config4_shard,config5")
+    ap.add_argument("--only", default="", help="comma-separated subset of: config2,config2_ivopt,config2_seeded,config3,config4_shard,config5")
     ap.add_argument("--lanes", type=int, default=32, help="host threads that submit batches concurrently (config 2)")
     ap.add_argument("--config3-reads", type=int, default=10_000)
     ap.add_argument("--config4-reads", type=int, default=2_500, help="reads of the 12 500-read shard that are generated and verified")
@@ -482,6 +482,17 @@ def main() -> int:
     made = {}
     if want("config2") or want("config2_ivopt"):
         made["config2"] = build_workload("config2", rank, g.pex_build, None, threads)
+    if want("config2_seeded"):
+        # the same reference and read model, anchors from the q-gram seeder (row N2) instead of the ground truth
+        from floxer_b200 import workloads as W
+        refs2 = made["config2"][0] if "config2" in made else W.build_references("config2", threads=threads)[0]
+        seeder = g.Seeder(refs2, q=12)
+        c2 = W.CONFIGS["config2"]
+        made["config2_seeded"] = (refs2, W.make_reads_seeded(refs2, c2["reads"], c2["read_len"], c2["error"], c2["read_seed"] + 1000 * rank, g.pex_build, seeder,
+                                                             threads=threads),
+                                  "q-gram seeder (floxer_b200/csrc/seeder.cpp): every position where a leaf matches within its error budget, both "
+                                  "orientations, hard cap 500 / soft cap 50, erase_useless_anchors")
+        seeder.close()
     if want("config3"):
         made["config3"] = build_workload("config3", rank, g.pex_build, args.config3_reads, threads)
     if want("config4_shard"):
@@ -516,6 +527,7 @@ def main() -> int:
     head, sub = None, {}
     int32_peak = None
     plan = [("config2", False, args.lanes, args.steps, True), ("config2", True, args.lanes, args.steps, False),
+            ("config2_seeded", False, args.lanes, max(3, args.steps // 2), False),
             ("config3", False, args.big_lanes, max(3, args.steps // 4), False), ("config3", True, args.big_lanes, max(3, args.steps // 4), False),
             ("config4_shard", False, args.big_lanes, max(3, args.steps // 5), False), ("config4_shard", True, args.big_lanes, max(3, args.steps // 5), False)]
     current = None

@@ -306,7 +306,7 @@ struct ClassDef { uint8_t widx, G; uint32_t max_words; };   // a (block width, r
 struct Prepared {
     bool ok = false;                     // the device-side walk can take the job
     DevBuf dev; PinnedBuf staging;       // nodes | leaves | reads | anchors, carved at the offsets below
-    size_t o_nodes = 0, o_leaves = 0, o_reads = 0, o_anchors = 0;
+    size_t o_nodes = 0, o_leaves = 0, o_reads = 0, o_anchors = 0, used = 0;   // (64 spare bytes follow the records in `staging`)
     uint32_t n_nodes = 0, n_leaves = 0, n_walks = 0, n_reads = 0;
     uint32_t max_depth = 0;
     uint32_t level_mask[256] = {0};      // classes that occur per tree depth
@@ -1545,6 +1545,7 @@ int prepare_job(fxg_ctx* c, fxg_job* J, std::string& err, fxg_counters& ctr) {
     P.o_nodes = carve(n_nodes * sizeof(NodeRec)); P.o_leaves = carve(n_leaves * sizeof(LeafRec));
     P.o_reads = carve(n_reads * sizeof(ReadRec)); P.o_anchors = carve(n_walks * sizeof(AnchorRec16));
     if (P.staging.ensure(off + 64) != cudaSuccess) return fail(err, FXG_ERR_OUT_OF_MEMORY, "cannot allocate staging for the job's records");
+    P.used = off;
     CUDA_TRY(err, P.dev.ensure(off + 64));
     uint8_t* const H = P.staging.as<uint8_t>();
     NodeRec* const nrec = reinterpret_cast<NodeRec*>(H + P.o_nodes);
@@ -3284,7 +3285,7 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
         //  such a byte simply matches nothing, so no kernel can be led astray by it in the meantime)
         rc = stage_pool(c, j->pool, fwd, pool_len, rc_pool, pool_len, err, ctr, true);
     }
-    if (rc == FXG_OK && cudaEventCreateWithFlags(&j->pool_ready, cudaEventDisableTiming) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "cannot create an event");
+    if (rc == FXG_OK && cudaEventCreateWithFlags(&j->pool_ready, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "cannot create an event");
     if (rc == FXG_OK && cudaEventRecord(j->pool_ready, c->stage_stream) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "staging failed");
     double const t_stage = lap_ms();
     if (rc == FXG_OK) rc = prepare_job(c, j, err, ctr);
@@ -3298,9 +3299,16 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
     lock.unlock();
     if (g_prof.on) fprintf(stderr, "[fxg] verify_reads: validated %.3f, pools enqueued %.3f, records prepared %.3f, run done %.3f ms\n", t_validate, t_stage, t_prepare, lap_ms());
     if (rc == FXG_OK) {
-        uint32_t bad = 0;
-        if (cudaMemcpyAsync(&bad, j->pool.bad_rank.p, 4, cudaMemcpyDeviceToHost, c->stage_stream) != cudaSuccess ||
-            cudaStreamSynchronize(c->stage_stream) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "staging failed");
+        // (waits on an event of its own, asleep: cudaStreamSynchronize would spin -- one core per caller -- until every other
+        //  caller's uploads on the staging stream are through as well)
+        uint32_t bad_pageable = 0;
+        // (into page-locked memory where the job has some: a copy into pageable memory blocks, spinning, as well)
+        uint32_t* const bad_p = j->prep.staging.p && j->prep.used ? reinterpret_cast<uint32_t*>(j->prep.staging.as<uint8_t>() + j->prep.used) : &bad_pageable;
+        if (cudaMemcpyAsync(bad_p, j->pool.bad_rank.p, 4, cudaMemcpyDeviceToHost, c->stage_stream) != cudaSuccess ||
+            cudaEventRecord(j->pool_ready, c->stage_stream) != cudaSuccess ||
+            cudaEventSynchronize(j->pool_ready) != cudaSuccess) rc = fail(err, FXG_ERR_CUDA, "staging failed");
+        uint32_t const bad = *bad_p;
+        if (rc != FXG_OK) {}
         else if (bad) rc = fail(err, FXG_ERR_INVALID_ARGUMENT, "query pools contain a rank above %d (allowed 0..%d)", FXG_MAX_RANK, FXG_MAX_RANK);
     } else {
         cudaStreamSynchronize(c->stage_stream);          // nothing may still read the caller's arrays when the call returns

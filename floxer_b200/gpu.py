@@ -22,6 +22,7 @@ EXPORTS = [
     "fxg_job_cigar_pool", "fxg_job_stats", "fxg_job_free", "fxg_verify_reads",
     "fxg_get_counters", "fxg_reset_counters", "fxg_measure_int32_peak",
     "fxg_pex_build", "fxg_pex_free", "fxg_job_write_sam", "fxg_free", "fxg_write_bam", "fxg_job_write_bam",
+    "fxg_seeder_create", "fxg_seeder_free", "fxg_seeder_search",
 ]
 
 _lib = None
@@ -81,6 +82,10 @@ def lib() -> C.CDLL:
     L.fxg_free.restype = None
     L.fxg_write_bam.argtypes = [vp, sz, vp, sz, vp, vp, vp, sz, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     L.fxg_job_write_bam.argtypes = [vp, sz, vp, vp, vp, sz, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+    L.fxg_seeder_create.argtypes = [sz, vp, vp, C.c_uint32, C.POINTER(vp)]
+    L.fxg_seeder_free.argtypes = [vp]
+    L.fxg_seeder_free.restype = None
+    L.fxg_seeder_search.argtypes = [vp, vp, sz, vp, sz, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     _lib = L
     return L
 
@@ -136,6 +141,47 @@ def pex_build(total_len: int, num_errors: int, leaf_max_errors: int, strategy: i
     L.fxg_pex_free(pi)
     L.fxg_pex_free(pl)
     return inner, leaves
+
+
+class Seeder:
+    """fxg_seeder: the q-gram seeder that stands in for search::searcher::search_seeds (host only)."""
+
+    def __init__(self, references, q: int = 10):
+        refs = [np.ascontiguousarray(r, dtype=np.uint8) for r in references]
+        n = len(refs)
+        ptrs = (C.c_void_p * max(n, 1))(*[r.ctypes.data for r in refs])
+        lens = (C.c_uint64 * max(n, 1))(*[len(r) for r in refs])
+        self._h = C.c_void_p()
+        rc = lib().fxg_seeder_create(n, ptrs, lens, q, C.byref(self._h))
+        if rc != 0:
+            raise FloxerGpuError(rc, "fxg_seeder_create failed")
+
+    def search(self, query, leaves, max_anchors_hard: int = 500, max_anchors_soft: int = 50, erase_useless: bool = True) -> np.ndarray:
+        """Anchors (abi.ANCHOR_DTYPE) of one query orientation, in seed -> reference -> position order."""
+        qy = np.ascontiguousarray(query, dtype=np.uint8)
+        lv = np.ascontiguousarray(leaves, dtype=abi.PEX_NODE_DTYPE)
+        out, n = C.c_void_p(), C.c_size_t(0)
+        rc = lib().fxg_seeder_search(self._h, qy.ctypes.data, len(qy), lv.ctypes.data, len(lv), max_anchors_hard, max_anchors_soft,
+                                     int(erase_useless), C.byref(out), C.byref(n))
+        if rc != 0:
+            raise FloxerGpuError(rc, "fxg_seeder_search failed (a leaf shorter than q * (errors + 1)?)")
+        if n.value == 0:
+            return np.zeros(0, dtype=abi.ANCHOR_DTYPE)
+        try:
+            return np.frombuffer(C.string_at(out, n.value * abi.ANCHOR_DTYPE.itemsize), dtype=abi.ANCHOR_DTYPE).copy()
+        finally:
+            lib().fxg_free(out)
+
+    def close(self):
+        if self._h:
+            lib().fxg_seeder_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Job:

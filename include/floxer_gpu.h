@@ -238,6 +238,19 @@ int fxg_job_write_bam(const fxg_job* job, size_t n_references, const char* const
                       const fxg_read* reads, size_t n_reads, const uint8_t* forward_pool, const fxg_sam_query* queries,
                       int with_header, uint8_t** bytes, size_t* bytes_len);
 
+/* ---- a q-gram seeder behind the anchor interface (host only; row N2 of the scope table) ----
+ * Stands in for search::searcher::search_seeds (src/lib/search.cpp:143-324), whose FM-index library cannot be built
+ * offline: per PEX leaf every reference position where the leaf matches a prefix of the reference with at most
+ * leaf.num_errors edits, as search::anchor_t, after the reference's caps (max_num_anchors_hard / _soft,
+ * include/floxer_cli.hpp:52-53) and erase_useless_anchors (search.cpp:352-389), in seed -> reference -> position order.
+ * q = length of the indexed q-grams (4..14); a leaf must be at least q * (num_errors + 1) long.  The index copies the
+ * references.  fxg_seeder_search writes a malloc'ed array (release with fxg_free) and may be called from several threads. */
+typedef struct fxg_seeder fxg_seeder;
+int fxg_seeder_create(size_t n_references, const uint8_t* const* rank_sequences, const uint64_t* lengths, uint32_t q, fxg_seeder** out);
+void fxg_seeder_free(fxg_seeder* seeder);
+int fxg_seeder_search(const fxg_seeder* seeder, const uint8_t* query, size_t query_len, const fxg_pex_node* leaves, size_t n_leaves,
+                      uint64_t max_anchors_hard, uint64_t max_anchors_soft, int erase_useless_anchors, fxg_anchor** anchors, size_t* n_anchors);
+
 /* ---- accounting / measurement helpers ---- */
 int fxg_get_counters(const fxg_ctx* ctx, fxg_counters* out);
 int fxg_reset_counters(fxg_ctx* ctx);

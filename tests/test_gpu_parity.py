@@ -608,6 +608,26 @@ def test_merged_batches_match_the_oracle(ctx, gpu, oracle, ivopt):
         s.free()
 
 
+def test_verify_with_seeder_anchors(ctx, gpu, oracle):
+    """Anchors from the q-gram seeder (row N2) instead of the ground truth: several anchors per locus a few bases apart,
+    hits in both orientations, repeat copies -- through verify_reads against the oracle, both settings of the interval
+    optimisation."""
+    from floxer_b200 import workloads as W
+    refs = [synthetic.random_reference(90_000, 71), synthetic.plant_repeats(synthetic.random_reference(50_000, 72), 73, families=4, unit=(300, 900), copies=(3, 5))]
+    seeder = gpu.Seeder(refs, q=8)
+    batch = W.make_reads_seeded(refs, 10, 800, 0.06, 74, gpu.pex_build, seeder, seed_errors=1, threads=2)
+    seeder.close()
+    assert len(batch.anchors) > 50
+    ctx.set_references(refs)
+    for cfg in (VerifyConfig(), VerifyConfig(interval_optimization=True)):
+        job = ctx.verify_reads(batch, cfg)
+        al, cg = job.alignments()
+        want, want_stats = oracle_verify_batch(oracle, refs, batch, cfg)
+        assert alignment_records(al, cg) == want and job.stats() == want_stats
+        assert len(want) > 0
+        job.free()
+
+
 def test_verify_reads_rejects_bad_ranks(ctx, gpu):
     """A rank above 5 in a query pool is an error of fxg_verify_reads (found on the device, reported with the call)."""
     refs = [synthetic.random_reference(50_000, 5)]
