@@ -628,6 +628,90 @@ def test_verify_with_seeder_anchors(ctx, gpu, oracle):
         job.free()
 
 
+def test_resident_references_with_n_and_sentinel(ctx, gpu, oracle):
+    """Ranks 0 ($) and 5 (N / invalid) inside RESIDENT references and inside reads, through verify_reads: comparison is plain
+    byte equality (src/lib/alignment.cpp:14), so N matches N and $ matches $."""
+    rng = np.random.default_rng(5150)
+    refs = [synthetic.random_reference(40_000, 61), synthetic.random_reference(25_000, 62)]
+    for r in refs:
+        for at in rng.integers(0, len(r) - 40, size=60):
+            r[at: at + int(rng.integers(1, 30))] = 5                  # runs of N
+        r[rng.integers(0, len(r), size=40)] = 0                       # stray sentinels
+    batch = synthetic.make_batch(refs, 12, 900, 0.06, 63, gpu.pex_build, seed_errors=1, decoy_fraction=0.3)
+    assert (batch.forward_pool == 5).any() and (batch.forward_pool == 0).any()      # the reads carry them too (simulated from the references)
+    ctx.set_references(refs)
+    for cfg in (VerifyConfig(), VerifyConfig(interval_optimization=True), VerifyConfig(without_cigar=True)):
+        job = ctx.verify_reads(batch, cfg)
+        al, cg = job.alignments()
+        want, want_stats = oracle_verify_batch(oracle, refs, batch, cfg)
+        assert alignment_records(al, cg) == want and job.stats() == want_stats
+        assert len(want) > 0
+        job.free()
+
+
+@pytest.mark.parametrize("name,n_reads,read_len,error,fp,ivopt", [
+    ("config3", 8, 15_000, 0.08, 1.0, True), ("config3", 4, 15_000, 0.08, 1.0, False),
+    ("config4", 8, 20_000, 0.10, 3.0, True), ("config4", 3, 20_000, 0.10, 3.0, False),
+])
+def test_config3_and_4_shapes_unthinned(ctx, gpu, name, n_reads, read_len, error, fp, ivopt):
+    """Read shapes of configs 3 and 4 with EVERY anchor of the stand-in seeder (true loci with jitter, hits at repeat copies,
+    false positives) on a repeat-seeded multi-record reference, with and without the interval optimisation, bit for bit
+    against the CPU port (alignments, cigars, order, statistics)."""
+    from floxer_b200 import workloads as W
+    from oracle import cpu_baseline
+    refs = [W.random_reference(900_000, 301, 2), W.random_reference(500_000, 302, 2)]
+    table = W.plant_repeats(refs, 303, families=12, unit=(500, 5000), copies=(4, 9))
+    batch = W.make_reads(refs, n_reads, read_len, error, 304 + int(ivopt), gpu.pex_build, repeats=table, false_positives=fp)
+    assert len(batch.anchors) > 400 * n_reads
+    ctx.set_references(refs)
+    cfg = VerifyConfig(interval_optimization=ivopt)
+    job = ctx.verify_reads(batch, cfg)
+    al, cg = job.alignments()
+    wal, wcg, wstats = cpu_baseline.verify_reads(refs, batch, cfg, threads=16)
+    assert alignment_records(al, cg) == alignment_records(wal, wcg)
+    assert job.stats() == wstats
+    assert len(al) >= n_reads
+    job.free()
+
+
+def test_two_contexts_in_one_process(gpu, oracle):
+    """The shape floxer itself needs (src/main/floxer.cpp:141-171 is ONE process): several contexts driven from the threads of
+    one process -- one per GPU where the box has several, two on the same GPU otherwise -- each verifying its shard of the
+    reads (floxer_b200.sharding.shard), the records gathered in read order and equal to one context's result for all reads."""
+    import threading
+    import torch
+    from floxer_b200 import sharding
+    n_ctx = max(2, min(4, torch.cuda.device_count()))
+    devices = [i % torch.cuda.device_count() for i in range(n_ctx)]
+    refs = [synthetic.random_reference(150_000, 91)]
+    batch = synthetic.make_batch(refs, 23, 1100, 0.06, 92, gpu.pex_build, seed_errors=1, decoy_fraction=0.3)
+    cfg = VerifyConfig(interval_optimization=True)
+    want, want_stats = oracle_verify_batch(oracle, refs, batch, cfg)
+    ctxs = [gpu.Context(d) for d in devices]
+    out, errors = [None] * n_ctx, []
+
+    def lane(r):
+        try:
+            ctxs[r].set_references(refs)
+            part, first = sharding.shard(batch, r, n_ctx)
+            job = ctxs[r].verify_reads(part, cfg)
+            al, cg = job.alignments()
+            out[r] = (sharding.gather_records(alignment_records(al, cg), first), job.stats())
+            job.free()
+        except Exception as e:                                      # noqa: BLE001 -- reported by the main thread
+            errors.append((r, repr(e)))
+    threads = [threading.Thread(target=lane, args=(r,)) for r in range(n_ctx)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for c in ctxs:
+        c.close()
+    assert not errors, errors
+    assert [rec for part in out for rec in part[0]] == want
+    assert {k: sum(part[1][k] for part in out) for k in want_stats} == want_stats
+
+
 def test_verify_reads_rejects_bad_ranks(ctx, gpu):
     """A rank above 5 in a query pool is an error of fxg_verify_reads (found on the device, reported with the call)."""
     refs = [synthetic.random_reference(50_000, 5)]
