@@ -404,8 +404,13 @@ def microbench(ctx, g, torch, int32_peak: float, cpu_threads: int, tasks_per_cel
                             and (res["start_in_reference"][:distinct] == cres["start_in_reference"]).all())
                 if not same:
                     raise RuntimeError(f"config 5 cell m={m} e={e} mode={key}: results differ from the CPU port")
+                dev_s = (c["dp_kernel_ms"] + c["trace_kernel_ms"]) * 1e-3
                 row[key] = {"gcups": cells_full / dt / 1e9, "tasks_per_s": len(tasks) / dt, "ms": dt * 1e3,
                             "roofline_frac": c["dp_word_steps"] * MYERS_INSTR_PER_WORD_STEP / dt / int32_peak if int32_peak else None,
+                            # the same over the CUDA-event time of the call's kernels (the wall time of a call with a million small
+                            # tasks is mostly the host's: one pass, one sort key and one 32-byte result record per task)
+                            "device_ms": dev_s * 1e3, "gcups_device": cells_full / dev_s / 1e9 if dev_s > 0 else None,
+                            "roofline_frac_device": c["dp_word_steps"] * MYERS_INSTR_PER_WORD_STEP / dev_s / int32_peak if int32_peak and dev_s > 0 else None,
                             "cpu_gcups": float((one["ref_len"].astype(np.float64) * one["query_len"]).sum()) / cdt / 1e9}
             out.append(row)
     return {"workload": f"config5: batched edit distance against a 10 Mbp random reference, {tasks_per_cell} tasks per cell ({distinct} distinct "
