@@ -327,7 +327,8 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
         "roofline": {
             "bound": "int32_alu", "achieved": achieved / 1e9, "peak": int32_peak / 1e9, "unit": "Ginstr/s",
             "frac": achieved / int32_peak if int32_peak else None,
-            "traffic": _captured_traffic(),
+            "traffic": (_captured_traffic() or {}).get("bytes_per_launch"),
+            "traffic_source": _captured_traffic(),
             "kernel": "fxg::dp_kernel<W, CKPT> -- every launch of the engine in the timed region (inner tree levels and root level)",
             "how": "algorithmic 11 int32 instructions per 32-cell word-step x the word-steps the engine's launches issued inside the timed "
                    "region of the device-resident arm (band-limited; counted per task from the band geometry, on the device for the inner "
@@ -339,8 +340,17 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
             "launch_event_ms_per_batch": {"engine_waves": ctr["dp_kernel_ms"] / n_batches, "tracebacks": ctr["trace_kernel_ms"] / n_batches,
                                           "root_launch": ctr["root_launch_ms"] / n_batches,
                                           "note": "CUDA-event times on the launching streams, summed over workers; launches of different batches overlap"},
-            "root_launch_frac": (ctr["root_launch_word_steps"] * MYERS_INSTR_PER_WORD_STEP / (ctr["root_launch_ms"] * 1e-3) / int32_peak)
-            if int32_peak and ctr["root_launch_ms"] > 0 else None,
+            # the dominant launch (the root level's largest class, a checkpointed score pass) with its own CUDA-event pair on its
+            # stream, measured live in the timed region: algorithmic instructions per launch / its average duration
+            "dominant_launch": {
+                "kernel": "fxg::dp_kernel<W, true> -- the root level's largest launch of every batch",
+                "launches": int(ctr["root_launches"]),
+                "ms_per_launch": ctr["root_launch_ms"] / max(ctr["root_launches"], 1),
+                "word_steps_per_launch": ctr["root_launch_word_steps"] / max(ctr["root_launches"], 1),
+                "achieved": (ctr["root_launch_word_steps"] * MYERS_INSTR_PER_WORD_STEP / (ctr["root_launch_ms"] * 1e-3) / 1e9) if ctr["root_launch_ms"] > 0 else None,
+                "frac": (ctr["root_launch_word_steps"] * MYERS_INSTR_PER_WORD_STEP / (ctr["root_launch_ms"] * 1e-3) / int32_peak)
+                if int32_peak and ctr["root_launch_ms"] > 0 else None,
+                "note": "launches of other batches run beside it: its duration includes what it waits for them"},
             "checkpoint_bytes_per_batch": ctr["trace_bytes"] / n_batches},
         "queue": {"batches": int(ctr["batches"]), "jobs": int(ctr["batch_jobs"]), "jobs_per_batch": ctr["batch_jobs"] / max(ctr["batches"], 1),
                   "launches_per_job": ctr["kernel_launches"] / max(ctr["batch_jobs"], 1),
@@ -546,7 +556,7 @@ def main() -> int:
             current = name
             if int32_peak is None:
                 int32_peak = ctx.measure_int32_peak()
-        cfg = VerifyConfig(interval_optimization=ivopt)
+        cfg = VerifyConfig(interval_optimization=ivopt, without_cigar=os.environ.get("BENCH_WITHOUT_CIGAR") == "1")      # (development: the path without tracebacks)
         rec = measure(ctx, g, torch, dist, refs, batch, cfg, lanes, steps, args.warmup, int32_peak, sampler, pageable=is_head,
                       cpu_threads=threads, cpu_target_s=args.cpu_seconds, rank=rank)
         if rec is not None:

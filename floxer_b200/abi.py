@@ -59,7 +59,7 @@ class Counters(C.Structure):
                 ("run_ms", C.c_double), ("trace_word_steps", C.c_uint64),
                 ("root_launch_ms", C.c_double), ("root_launch_word_steps", C.c_uint64), ("shared_tracebacks", C.c_uint64), ("inferred_inner", C.c_uint64),
                 ("shared_score_passes", C.c_uint64), ("rescored_roots", C.c_uint64),
-                ("batches", C.c_uint64), ("batch_jobs", C.c_uint64), ("alloc_ms", C.c_double), ("alloc_calls", C.c_uint64)]
+                ("batches", C.c_uint64), ("batch_jobs", C.c_uint64), ("alloc_ms", C.c_double), ("alloc_calls", C.c_uint64), ("root_launches", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -330,7 +330,7 @@ struct fxg_ctx {
     int num_sms = 0;
     size_t smem_limit = 0;
     static constexpr int kMaxGroups = 32;
-    int n_groups = 32;                    // batches that can be in flight (FXG_GROUPS, read by fxg_create)
+    int n_groups = 6;                     // batches that can be in flight (FXG_GROUPS, read by fxg_create)
     WorkerGroup groups[kMaxGroups];
     cudaStream_t stage_stream = nullptr; // uploads of references / query pools, Peq construction
     DevBuf d_tmp;
@@ -446,7 +446,7 @@ void add_counters(fxg_counters& a, fxg_counters const& b) {
     a.kernel_launches += b.kernel_launches; a.dp_tasks += b.dp_tasks; a.dp_word_steps += b.dp_word_steps;
     a.dp_cells_full += b.dp_cells_full; a.trace_bytes += b.trace_bytes; a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
     a.root_launch_ms += b.root_launch_ms; a.root_launch_word_steps += b.root_launch_word_steps; a.shared_tracebacks += b.shared_tracebacks; a.inferred_inner += b.inferred_inner;
-    a.shared_score_passes += b.shared_score_passes; a.rescored_roots += b.rescored_roots; a.batches += b.batches; a.batch_jobs += b.batch_jobs;
+    a.shared_score_passes += b.shared_score_passes; a.rescored_roots += b.rescored_roots; a.batches += b.batches; a.batch_jobs += b.batch_jobs; a.root_launches += b.root_launches;
     a.trace_word_steps += b.trace_word_steps; a.dp_kernel_ms += b.dp_kernel_ms; a.trace_kernel_ms += b.trace_kernel_ms; a.waves += b.waves; a.run_ms += b.run_ms;
 }
 
@@ -780,7 +780,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     if (trace) {
         // the largest launch of a root wave is the engine's dominant launch: timed on its own for the roofline
         CUDA_TRY(w.err, cudaEventElapsedTime(&ms, w.ev_b0, w.ev_b1));
-        w.ctr.root_launch_ms += ms; w.ctr.root_launch_word_steps += launches[0].word_steps;
+        w.ctr.root_launch_ms += ms; w.ctr.root_launch_word_steps += launches[0].word_steps; w.ctr.root_launches++;
     }
     g_prof.lap(w, trace ? 11 : 8);
     *results = w.h_results.as<DpResult>();
@@ -1777,6 +1777,7 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
     if (n_feasible == 0 || n_units == 0) { add_root_stats(); return FXG_OK; }
     uint32_t class_units[kMaxLevelClasses];
     for (int ci = 0; ci < kMaxLevelClasses; ++ci) class_units[ci] = ctr[kCtrClassUnits + ci];
+    int timed_class = 0;                                 // the class of the largest launch: timed with an event pair of its own
 
     // ---- score passes, one launch per class ----
     CUDA_TRY(w.err, w.d_tasks.ensure_scaled(size_t(n_units) * sizeof(DpTask), P.scale));
@@ -1818,7 +1819,7 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
             if (smem > c->smem_limit) return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "internal: launch needs %zu bytes of shared memory", smem);
             uint32_t const lgrid = wide ? uint32_t(std::min<size_t>(L.n_tasks, size_t(c->num_sms) * 2)) : (L.n_tasks + tpw - 1) / tpw;
             cudaStream_t const s2 = x == 0 ? st : w.side[(x - 1) % Worker::kSide];
-            if (x == 0) CUDA_TRY(w.err, cudaEventRecord(w.ev_b0, st));
+            if (x == 0) { timed_class = ci; CUDA_TRY(w.err, cudaEventRecord(w.ev_b0, st)); }
             CUDA_TRY(w.err, launch_dp(wide ? -1 : int(K.widx), want_cigar, L, lgrid, smem, s2));
             if (x == 0) CUDA_TRY(w.err, cudaEventRecord(w.ev_b1, st));
             w.ctr.kernel_launches++;
@@ -1845,7 +1846,7 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
     if (rc != FXG_OK) return rc;
     {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, w.ev_b0, w.ev_b1) == cudaSuccess) { w.ctr.root_launch_ms += ms; }
+        if (cudaEventElapsedTime(&ms, w.ev_b0, w.ev_b1) == cudaSuccess) { w.ctr.root_launch_ms += ms; w.ctr.root_launches++; w.ctr.root_launch_word_steps += ctr64(kCtrClassWs + 2 * timed_class); }
     }
     P.t_mark[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - P.t0).count();
     g_prof.lap(w, 11);
@@ -1854,7 +1855,6 @@ int root_level_device(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t n_r
     uint32_t const n_accepted = ctr[kCtrAccepted], n_tb = ctr[kCtrTracebacks];
     uint64_t const cig_total = ctr64(kCtrCigars);
     w.ctr.dp_tasks += n_units; w.ctr.dp_word_steps += ctr64(kCtrWordSteps); w.ctr.trace_bytes += ck_words * 4;
-    w.ctr.root_launch_word_steps += 0;
     w.ctr.shared_score_passes += ctr[kCtrShared];
     if (want_cigar) w.ctr.shared_tracebacks += n_accepted - n_tb;
     w.ctr.waves++;
@@ -2601,7 +2601,7 @@ int fxg_create(int device, fxg_ctx** out) {
     c->share_root_passes = env_int("FXG_SHARE_ROOTS", 1, 0, 1) != 0;
     c->device_levels = env_int("FXG_DEVICE_LEVELS", 1, 0, 1) != 0;
     c->root_chunk_min = env_int("FXG_ROOT_CHUNK_MIN", 512, 1, 1 << 30);
-    c->n_groups = env_int("FXG_GROUPS", 4, 1, fxg_ctx::kMaxGroups);
+    c->n_groups = env_int("FXG_GROUPS", 6, 1, fxg_ctx::kMaxGroups);
     c->merge_max_jobs = env_int("FXG_MERGE_JOBS", 16, 1, 4096);
     c->merge_wait_us = env_int("FXG_MERGE_WAIT_US", 300, 0, 1000000);
     c->merged_parts = env_int("FXG_MERGED_PARTS", 1, 1, 64);

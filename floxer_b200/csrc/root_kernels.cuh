@@ -83,7 +83,7 @@ struct RootCtx {
 enum : uint8_t { kMemberAccepted = 1, kMemberSafe = 2, kMemberMulti = 4 };
 enum { kCtrFeasible = 0, kCtrUnits = 1, kCtrCkWords = 2, kCtrSlow = 4, kCtrAccepted = 5, kCtrTracebacks = 6, kCtrErrors = 7, kCtrClassUnits = 8,
        kCtrShared = 56,
-       kCtrClassFill = 24, kCtrWidthTb = 40, kCtrWidthFill = 46, kCtrCigars = 52, kCtrWordSteps = 54, kRootCounters = 64 };
+       kCtrClassFill = 24, kCtrWidthTb = 40, kCtrWidthFill = 46, kCtrCigars = 52, kCtrWordSteps = 54, kCtrClassWs = 64 /* 16 x 64-bit */, kRootCounters = 96 };
 
 // ---- windows, statistics, sort keys ----
 __global__ void root_prepare_kernel(RootCtx const C) {
@@ -185,7 +185,8 @@ __global__ void root_tasks_kernel(RootCtx const C, uint32_t n_units) {
         if (hi > int64_t(t.n)) hi = t.n;
         if (hi >= lo) ws += (unsigned long long)(hi - lo + 1) * W;
     }
-    atomicAdd(reinterpret_cast<unsigned long long*>(C.counters + kCtrWordSteps), ws);
+    warp_add(reinterpret_cast<unsigned long long*>(C.counters + kCtrWordSteps), ws);
+    warp_add_keyed(reinterpret_cast<unsigned long long*>(C.counters + kCtrClassWs), 1, U.cls, ws);      // per class: the launches are timed one by one
 }
 
 // minimum of the last row over columns col_from .. col_to of a checkpointed pass, and the rightmost column attaining it,

@@ -150,6 +150,7 @@ typedef struct {
     uint64_t batch_jobs;             /* ... and the jobs in them (several callers' jobs are merged into one batch) */
     double alloc_ms;                 /* host time spent allocating device / page-locked memory (process-wide) ... */
     uint64_t alloc_calls;            /* ... and the allocations: both stay flat in the steady state */
+    uint64_t root_launches;          /* launches that root_launch_ms / root_launch_word_steps cover */
 } fxg_counters;
 
 /* ---- life cycle ----

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert abi.PEX_NODE_DTYPE.itemsize == 32 and abi.ANCHOR_DTYPE.itemsize == 32
     assert abi.ALIGN_TASK_DTYPE.itemsize == 48 and abi.ALIGN_RESULT_DTYPE.itemsize == 32
     assert abi.READ_DTYPE.itemsize == 48 and abi.ALIGNMENT_DTYPE.itemsize == 40
-    assert C.sizeof(abi.VerifyConfig) == 16 and C.sizeof(abi.Stats) == 64 and C.sizeof(abi.Counters) == 176
+    assert C.sizeof(abi.VerifyConfig) == 16 and C.sizeof(abi.Stats) == 64 and C.sizeof(abi.Counters) == 184
 
 
 def test_pex_builder_golden(lib):
