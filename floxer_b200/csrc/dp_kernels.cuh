@@ -1054,7 +1054,7 @@ constexpr uint32_t kNoParent = 0xffffffffu;
 constexpr int kWalkBits = 28;                       // a walk's index shares a 64-bit word with its window start (a store position below 2^36)
 constexpr uint32_t kMaxDeviceWalks = 1u << kWalkBits;
 constexpr unsigned long long kWalkMask = (1ull << kWalkBits) - 1;
-constexpr int kMaxLevelClasses = 16;
+constexpr int kMaxLevelClasses = 32;             // configuration classes of a context (a bit each in the per-depth masks)
 
 // a member job's ReadRecs copied into the batch, bases shifted to the member's place in it
 __global__ void gather_reads_kernel(const ReadRec* __restrict__ src, ReadRec* __restrict__ dst, uint32_t n, uint32_t walk0, uint32_t node0,

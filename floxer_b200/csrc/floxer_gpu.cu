@@ -1498,7 +1498,15 @@ int class_of(fxg_ctx* c, Config const& cf, uint32_t words) {
     std::lock_guard<std::mutex> lock(c->class_mu);
     for (int i = 0; i < c->n_classes; ++i)
         if (c->classes[i].widx == cf.widx && c->classes[i].G == cf.G) { c->classes[i].max_words = std::max(c->classes[i].max_words, words); return i; }
-    if (c->n_classes == kMaxLevelClasses) return -1;
+    if (c->n_classes == kMaxLevelClasses) {
+        // the table is full (a context that has seen every shape of tree): a class of the same block width with a larger
+        // ring runs the pass as well -- the lanes a smaller ring would leave idle cost nothing
+        int best = -1;
+        for (int i = 0; i < c->n_classes; ++i)
+            if (c->classes[i].widx == cf.widx && c->classes[i].G != kWideG && cf.G != kWideG && c->classes[i].G >= cf.G && (best < 0 || c->classes[i].G < c->classes[best].G)) best = i;
+        if (best >= 0) c->classes[best].max_words = std::max(c->classes[best].max_words, words);
+        return best;
+    }
     c->classes[c->n_classes] = ClassDef{cf.widx, cf.G, words};
     return c->n_classes++;
 }
@@ -1957,7 +1965,7 @@ int run_device_walks(fxg_ctx* c, Worker& w, Batch& B, uint32_t r0, uint32_t r1, 
     P.walks.clear(); P.hits.clear();
     if (n_walks == 0) return FXG_OK;
     for (uint32_t d = 0; d < 256; ++d)
-        if (level_mask[d] >> c->n_classes) return fail(w.err, FXG_ERR_STATE, "internal: a job's records name a configuration class the context does not have");
+        if (uint64_t(level_mask[d]) >> c->n_classes) return fail(w.err, FXG_ERR_STATE, "internal: a job's records name a configuration class the context does not have");
     bool const ivopt = B.cfg.interval_optimization != 0;
     bool const direct = B.cfg.verification_kind == FXG_KIND_DIRECT_FULL;
     size_t const n_members = B.members.size();
@@ -2961,8 +2969,8 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     static bool const trace_batches = std::getenv("FXG_TRACE_BATCHES") != nullptr;
     if (trace_batches) {
         static auto const epoch = std::chrono::steady_clock::now();
-        fprintf(stderr, "[fxg] batch at %.3f ms: %zu jobs, %u walks, %zu parts, %.3f ms (alloc so far %.1f ms in %llu calls); part 0: enqueued %.2f levels %.2f units %.2f scores %.2f records %.2f\n",
-                std::chrono::duration<double, std::milli>(vt0 - epoch).count(), B.members.size(), rwb[n_reads], n_parts, since(),
+        fprintf(stderr, "[fxg] batch at %.3f ms: %zu jobs, %u walks, %zu parts%s, %.3f ms (alloc so far %.1f ms in %llu calls); part 0: enqueued %.2f levels %.2f units %.2f scores %.2f records %.2f\n",
+                std::chrono::duration<double, std::milli>(vt0 - epoch).count(), B.members.size(), rwb[n_reads], n_parts, B.device ? "" : " (levels driven from the host)", since(),
                 double(g_alloc_ns.load()) * 1e-6, (unsigned long long)g_alloc_calls.load(),
                 parts[0].t_mark[0], parts[0].t_mark[1], parts[0].t_mark[2], parts[0].t_mark[3], parts[0].t_mark[4]);
     }

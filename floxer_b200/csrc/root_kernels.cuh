@@ -73,17 +73,18 @@ struct RootCtx {
     uint32_t* hit;                                             // per original index: 1 = an alignment -- scan input
     const uint32_t* hit_at;                                    // exclusive scan of hit
     ::fxg_alignment* out;
-    // counters: [0] feasible roots, [1] units, [2] checkpoint words (64-bit: [2..3]), [4] members that need the slow way,
-    // [5] accepted, [6] tracebacks, [7] errors, [8..23] units per class, [24..39] tasks filled per class,
-    // [40..45] tracebacks per block width, [46..51] filled per width, [52..53] cigar slots (64-bit), [54..55] word-steps (64-bit)
+    // counters (kCtr*): feasible roots, units, checkpoint words, members that need the slow way, accepted, tracebacks, errors,
+    // units / tasks filled / word-steps per class, tracebacks / filled per block width, cigar slots, word-steps
     uint32_t* counters;
     unsigned long long* member_totals;
     uint32_t read0;                                            // first read of the part within the batch
 };
 enum : uint8_t { kMemberAccepted = 1, kMemberSafe = 2, kMemberMulti = 4 };
-enum { kCtrFeasible = 0, kCtrUnits = 1, kCtrCkWords = 2, kCtrSlow = 4, kCtrAccepted = 5, kCtrTracebacks = 6, kCtrErrors = 7, kCtrClassUnits = 8,
-       kCtrShared = 56,
-       kCtrClassFill = 24, kCtrWidthTb = 40, kCtrWidthFill = 46, kCtrCigars = 52, kCtrWordSteps = 54, kCtrClassWs = 64 /* 16 x 64-bit */, kRootCounters = 96 };
+enum { kCtrFeasible = 0, kCtrUnits = 1, kCtrCkWords = 2 /* 64-bit */, kCtrSlow = 4, kCtrAccepted = 5, kCtrTracebacks = 6, kCtrErrors = 7,
+       kCtrClassUnits = 8, kCtrClassFill = kCtrClassUnits + kMaxLevelClasses, kCtrWidthTb = kCtrClassFill + kMaxLevelClasses, kCtrWidthFill = kCtrWidthTb + 6,
+       kCtrCigars = kCtrWidthFill + 6 /* 64-bit */, kCtrWordSteps = kCtrCigars + 2 /* 64-bit */, kCtrShared = kCtrWordSteps + 2,
+       kCtrClassWs = kCtrShared + 4 /* kMaxLevelClasses x 64-bit */, kRootCounters = kCtrClassWs + 2 * kMaxLevelClasses };
+static_assert(kCtrCkWords % 2 == 0 && kCtrCigars % 2 == 0 && kCtrWordSteps % 2 == 0 && kCtrClassWs % 2 == 0, "64-bit counters sit on 8-byte boundaries");
 
 // ---- windows, statistics, sort keys ----
 __global__ void root_prepare_kernel(RootCtx const C) {
