@@ -65,11 +65,18 @@ inline cudaStream_t alloc_stream() {
 // time spent allocating (device and page-locked memory), for fxg_counters: in the steady state it must not grow
 std::atomic<uint64_t> g_alloc_ns{0}, g_alloc_calls{0};
 struct AllocTimer {
+    const char* what; size_t bytes;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    ~AllocTimer() { g_alloc_ns += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count()); g_alloc_calls++; }
+    AllocTimer(const char* w, size_t b) : what(w), bytes(b) {}
+    ~AllocTimer() {
+        uint64_t const ns = uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+        g_alloc_ns += ns; g_alloc_calls++;
+        static bool const trace = std::getenv("FXG_TRACE_BATCHES") != nullptr;
+        if (trace && ns > 2000000) fprintf(stderr, "[fxg] alloc %s %.1f MB took %.1f ms\n", what, double(bytes) / 1048576.0, double(ns) * 1e-6);
+    }
 };
 inline cudaError_t device_alloc(void** p, size_t bytes) {
-    AllocTimer timer;
+    AllocTimer timer("device", bytes);
     cudaStream_t const s = alloc_stream();
     if (!s) return cudaMalloc(p, bytes);
     cudaError_t e = cudaMallocAsync(p, bytes, s);
@@ -141,8 +148,8 @@ struct PinnedBuf {                       // page-locked host staging memory
     }
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        AllocTimer timer;
         size_t const want = std::max(bytes + bytes / 2 + 4096, 2 * cap);
+        AllocTimer timer("page-locked", want);
         if (p) { cudaFreeHost(p); p = nullptr; }
         cap = 0;
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
