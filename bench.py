@@ -206,10 +206,21 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
         return f
     # warm-up: the W steps asked for, and on until two seconds have passed -- the queue's workers size their buffers for
     # the batches they meet, and the first batches of every size pay for that (page-locking memory takes tens of ms)
-    t_warm = time.perf_counter()
-    run_lanes([resident_step(j) for j in jobs], max(warmup, 3))
-    while time.perf_counter() - t_warm < 2.0:
-        run_lanes([resident_step(j) for j in jobs], 2)
+    def warm_up(step_fns, first: int, at_least_s: float, at_most_s: float = 10.0):
+        # ... and on while the library still allocates (its counter of allocations moved during the last round), bounded
+        t_warm = time.perf_counter()
+        run_lanes(step_fns, first)
+        calls = ctx.counters()["alloc_calls"]
+        while True:
+            spent = time.perf_counter() - t_warm
+            if spent >= at_most_s:
+                break
+            run_lanes(step_fns, 2)
+            now = ctx.counters()["alloc_calls"]
+            if now == calls and time.perf_counter() - t_warm >= at_least_s:
+                break
+            calls = now
+    warm_up([resident_step(j) for j in jobs], max(warmup, 3), 2.0)
     # one batch at a time first: its latency, and its device time between the run's first and last operation
     lat_ms = []
     for it in range(3):
@@ -272,10 +283,7 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
                     del a2, c2
                     j2.free()
                     last[i] = None
-        t_w = time.perf_counter()
-        run_lanes([e2e_step(i) for i in range(lanes)], 3)        # warm-up (page-locked pools are allocated once)
-        while time.perf_counter() - t_w < 1.0:
-            run_lanes([e2e_step(i) for i in range(lanes)], 2)
+        warm_up([e2e_step(i) for i in range(lanes)], 3, 1.0)     # (page-locked pools are allocated once)
         check_and_free()
         barrier()
         ctx.reset_counters()

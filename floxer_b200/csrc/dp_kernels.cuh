@@ -787,13 +787,15 @@ struct Walk2Launch {
 // alignments per CTA.  The tile the traceback stands on is recomputed as a skewed wavefront -- lane w does column step s
 // at time s + w, the carries of word w - 1 arrive by shuffle -- so a tile of 32 steps costs 32 + W single-word steps
 // instead of 32 W-word steps on one lane; only the words at or above the path's row are computed (carries run downwards).
-// The HP / VP' bits of the tile go to shared memory, and every lane of the group follows the path through them in
-// lockstep (same addresses: broadcasts), so that all of them know where the next tile is; lane 0 writes the cigar.
+// What the path does in a cell -- left, up, match, mismatch, two bits -- goes to shared memory as two bit planes, and every
+// lane of the group follows the path through them in lockstep (same addresses: broadcasts), one 8-byte load per cell, so
+// that all of them know where the next tile is; lane 0 writes the cigar.
 __host__ __device__ constexpr uint32_t walk2_threads() { return 64u; }
 __host__ __device__ constexpr uint32_t walk2_per_cta(uint32_t W) { return walk2_threads() / W; }
-// shared memory per alignment: HP / VP' of 32 steps x W words (+ 1 word, so that the groups of a warp start in different
-// banks), and the Eq rows of its current block (6 symbols x W words)
-__host__ __device__ constexpr uint32_t walk2_words_per_group(uint32_t W) { return 64 * W + 1 + kNumSymbols * W; }
+// shared memory per alignment: the two operation planes of 32 steps x W words (+ 2 words, so that the groups of a warp
+// start in different banks and every pair of plane words stays 8-byte aligned), the Eq rows of its current block
+// (6 symbols x W words) and the tile's 32 window characters as bytes
+__host__ __device__ constexpr uint32_t walk2_words_per_group(uint32_t W) { return 64 * W + 2 + kNumSymbols * W + 8; }
 __host__ __device__ constexpr size_t walk2_smem_bytes(uint32_t W) { return size_t(walk2_words_per_group(W)) * walk2_per_cta(W) * 4; }
 
 template <int W>
@@ -804,8 +806,12 @@ __global__ void __launch_bounds__(walk2_threads()) walk2_kernel(Walk2Launch cons
     constexpr uint32_t PER_CTA = walk2_per_cta(W);
     uint32_t const w = threadIdx.x % W;                                    // this lane's word of the block
     uint32_t const grp = threadIdx.x / W;                                  // alignment within the CTA
-    uint32_t* const bits = w2_smem + grp * walk2_words_per_group(W);       // HP / VP' of step p, word x at bits[(p * W + x) * 2 + {0, 1}]
-    uint32_t* const eq_g = bits + 64 * W + 1;                              // Eq[sym][x] at eq_g[sym * W + x]
+    // operation code of the cell in row bit r of word x at step p: bit r of bits[(p * W + x) * 2] (low) and of the word
+    // after it (high); 0 match, 1 mismatch, 2 up (I), 3 left (D) -- trace priority left > up > diagonal, decided in the
+    // one place that writes the planes (oracle: FXO_TRACE_PRIORITY)
+    uint32_t* const bits = w2_smem + grp * walk2_words_per_group(W);
+    uint32_t* const eq_g = bits + 64 * W + 2;                              // Eq[sym][x] at eq_g[sym * W + x]
+    uint8_t* const tile_chars = reinterpret_cast<uint8_t*>(eq_g + kNumSymbols * W);   // window character of step p of the tile
     uint32_t const id = blockIdx.x * PER_CTA + grp;
     bool const mine = id < L.n_tasks;
     bool done = !mine;
@@ -829,18 +835,21 @@ __global__ void __launch_bounds__(walk2_threads()) walk2_kernel(Walk2Launch cons
     };
 
     uint32_t i = T.m, j = T.end_col;                             // the cell the traceback stands on (row, column; 1-based)
-    uint32_t n_runs = 0, cur_op = 0, cur_len = 0, errors = 0;
+    uint32_t n_runs = 0, cur_code = 0, cur_len = 0, errors = 0;  // the run being collected, by operation code
     bool bad = false;
     uint32_t eq_block = 0xffffffffu;                             // block whose Eq rows are in shared memory
-    uint32_t chars[4] = {0, 0, 0, 0};                            // window characters of the tile's columns, 4 bits each, step p at nibble p
-    auto emit = [&](uint32_t op, uint32_t len) {
-        if (op == cur_op) { cur_len += len; return; }
-        if (cur_len) { if (n_runs < T.cigar_cap) { if (writer) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
-        cur_op = op; cur_len = len;
+    // the cigar operation of a code: =, X, I, D as 7, 8, 1, 2 (output.cpp of the reference writes them as "=XID")
+    auto flush_run = [&]() {
+        if (cur_len) {
+            if (n_runs < T.cigar_cap) { if (writer) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | ((0x2187u >> (4 * cur_code)) & 15u); }
+            else bad = true;
+            ++n_runs;
+        }
     };
-    auto tile_char = [&](uint32_t p) -> uint32_t {               // p in 0 .. 31
-        uint32_t const x = p < 8 ? chars[0] : (p < 16 ? chars[1] : (p < 24 ? chars[2] : chars[3]));
-        return (x >> (4 * (p & 7u))) & 15u;
+    auto emit = [&](uint32_t code, uint32_t len) {
+        if (code == cur_code) { cur_len += len; return; }
+        flush_run();
+        cur_code = code; cur_len = len;
     };
 
     // inputs of a tile, as loaded: window characters, this lane's word of the block's record at the step before the tile,
@@ -876,7 +885,7 @@ __global__ void __launch_bounds__(walk2_threads()) walk2_kernel(Walk2Launch cons
         uint32_t b = 0, q = 0;
         if (!done) {
             if (i == 0) done = true;
-            else if (j == 0) { emit(1, i); errors += i; i = 0; done = true; }     // column 0: only "up" remains
+            else if (j == 0) { emit(2, i); errors += i; i = 0; done = true; }     // column 0: only "up" remains
         }
         // ---------------- recompute the tile of (i, j): what this group needs, then the wavefront with the whole warp ----------------
         uint32_t Pv1[1] = {0}, Mv1[1] = {0};
@@ -898,8 +907,15 @@ __global__ void __launch_bounds__(walk2_threads()) walk2_kernel(Walk2Launch cons
             // what the tile is computed from: fetched while the previous tile was being walked, if the guess was right
             if (!(pf_valid && pf_b == b && pf_q == q)) fetch_tile(b, q, X);
             pf_valid = false;
+            // the tile's window characters, one byte per step: the lanes of the group share the four words of eight
 #pragma unroll
-            for (int k = 0; k < 4; ++k) chars[k] = __funnelshift_r(X.raw[k], X.raw[k + 1], X.sh);
+            for (int k = 0; k < 4; ++k) {
+                if (uint32_t(k) % uint32_t(W) == w % 4u) {
+                    uint32_t lo8, hi8;
+                    unpack8(__funnelshift_r(X.raw[k], X.raw[k + 1], X.sh), lo8, hi8);
+                    *reinterpret_cast<uint2*>(tile_chars + 8 * k) = make_uint2(lo8, hi8);
+                }
+            }
             if (t0 >= ts) { Pv1[0] = X.pv; Mv1[0] = X.mv; }
             else {
                 // the block begins inside the tile: "block above + 1, 2, ..." (wildcard rows of block 0 carry value 0)
@@ -941,19 +957,30 @@ __global__ void __launch_bounds__(walk2_threads()) walk2_kernel(Walk2Launch cons
             int32_t const my_last = (!done && w <= wi0) ? n_steps - 1 + int32_t(wi0) : -1;
             int32_t const t_max = __reduce_max_sync(0xffffffffu, my_last);
             uint32_t out_hp = 0, out_hn = 0;
+            bool const works = !done && w <= wi0;
+            // Eq word of this lane's next step, fetched one step ahead (clamped: the word of a step that is never done is not used)
+            auto eq_of = [&](int32_t sidx) -> uint32_t {
+                int32_t const p = p_first + (sidx < 0 ? 0 : sidx);
+                return eq_g[uint32_t(tile_chars[p > 31 ? 31 : p]) * W + w];
+            };
+            uint32_t eq_next = works ? eq_of(-int32_t(w)) : 0u;
             for (int32_t tau = 0; tau <= t_max; ++tau) {
                 uint32_t in_hp = __shfl_up_sync(0xffffffffu, out_hp, 1, W);
                 uint32_t in_hn = __shfl_up_sync(0xffffffffu, out_hn, 1, W);
                 int32_t const sidx = tau - int32_t(w);
-                if (!done && w <= wi0 && sidx >= 0 && sidx < n_steps) {
+                if (works && sidx >= 0 && sidx < n_steps) {
                     uint32_t const p = uint32_t(p_first + sidx);
                     if (w == 0) { in_hp = ((top_hp >> p) & 1u) << 31; in_hn = ((top_hn >> p) & 1u) << 31; }
                     uint32_t Eq1[1], hp_all[1];
-                    Eq1[0] = eq_g[tile_char(p) * W + w];
+                    Eq1[0] = eq_next;
+                    eq_next = eq_of(sidx + 1);
                     block_column<1, true>(Pv1, Mv1, Eq1, in_hp, in_hn, out_hp, out_hn, hp_all);
-                    // left = HP (D[i][j] = D[i][j-1] + 1), up = new Pv (D[i][j] = D[i-1][j] + 1)
-                    bits[(p * W + w) * 2] = hp_all[0];
-                    bits[(p * W + w) * 2 + 1] = Pv1[0];
+                    // left where HP (D[i][j] = D[i][j-1] + 1), else up where the new Pv (D[i][j] = D[i-1][j] + 1), else the
+                    // diagonal: a match where Eq (query[i-1] == window[j-1]), a mismatch otherwise
+                    uint32_t const hp = hp_all[0], vp = Pv1[0];
+                    uint32_t const low = hp | ~(vp | Eq1[0]);                          // codes 1 and 3
+                    uint32_t const high = hp | vp;                                    // codes 2 and 3
+                    *reinterpret_cast<uint2*>(bits + (p * W + w) * 2) = make_uint2(low, high);
                 }
             }
         }
@@ -965,7 +992,6 @@ __global__ void __launch_bounds__(walk2_threads()) walk2_kernel(Walk2Launch cons
             if (q >= 2 && 32 * int32_t(q - 1) >= ts) { fetch_tile(b, q - 1, X); pf_valid = true; pf_b = b; pf_q = q - 1; }
         }
         // ---------------- follow the path while it stays inside the tile (every lane of the group, in lockstep) ----------------
-        // trace priority: left > up > diagonal (the one place that encodes it; oracle: FXO_TRACE_PRIORITY)
         if (!done) {
             // position inside the tile: step p (column), row r of the block (0-based); the tile is left when p < 0 (column
             // before the tile), r < 0 (row of the block above), or the matrix' row 0 / column 0 is reached
@@ -976,20 +1002,15 @@ __global__ void __launch_bounds__(walk2_threads()) walk2_kernel(Walk2Launch cons
             int32_t const p_min = (int32_t(b) + 1 - 32 * int32_t(q - 1) - 1) > 0 ? (int32_t(b) + 1 - 32 * int32_t(q - 1) - 1) : 0;   // step of column 1
             uint32_t ops_err = 0;
             while (p >= p_min && r >= r_min) {
-                uint32_t const wi = uint32_t(r) >> 5, bit = uint32_t(r) & 31u;
-                uint32_t const hpb = (bits[(uint32_t(p) * W + wi) * 2] >> bit) & 1u;
-                uint32_t const vpb = (bits[(uint32_t(p) * W + wi) * 2 + 1] >> bit) & 1u;
-                // query[i-1] == window[j-1] is the Eq bit of that row for the column's character
-                uint32_t const match = (eq_g[tile_char(uint32_t(p)) * W + wi] >> bit) & 1u;
-                uint32_t const op = hpb ? 2u : (vpb ? 1u : (match ? 7u : 8u));     // D, I, =, X
-                ops_err += op != 7u;
-                if (op == cur_op) ++cur_len;
-                else {
-                    if (cur_len) { if (n_runs < T.cigar_cap) { if (writer) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; } else bad = true; ++n_runs; }
-                    cur_op = op; cur_len = 1;
-                }
-                p -= op != 1u;                                                     // left and diagonal move one column back
-                r -= op != 2u;                                                     // up and diagonal move one row up
+                uint2 const v = *reinterpret_cast<const uint2*>(bits + (uint32_t(p) * W + (uint32_t(r) >> 5)) * 2);
+                uint32_t const bit = uint32_t(r) & 31u;
+                uint32_t const lo1 = (v.x >> bit) & 1u, hi1 = (v.y >> bit) & 1u;
+                uint32_t const code = lo1 | (hi1 << 1);
+                p -= int32_t(code != 2u);                                          // every move but "up" (code 2) goes one column back
+                r -= int32_t(code != 3u);                                          // every move but "left" (code 3) goes one row up
+                ops_err += code != 0u;
+                if (code == cur_code) ++cur_len;
+                else { flush_run(); cur_code = code; cur_len = 1; }
             }
             // back to matrix coordinates
             int32_t const p0 = int32_t(j + b) - 32 * int32_t(q - 1) - 1, r0 = int32_t((u0 - 1) % ROWS);
@@ -999,7 +1020,7 @@ __global__ void __launch_bounds__(walk2_threads()) walk2_kernel(Walk2Launch cons
         __syncwarp();                                                      // the next tile overwrites the bits
     }
     if (mine && writer) {
-        if (cur_len) { if (n_runs < T.cigar_cap) slot_end[-1 - int64_t(n_runs)] = (cur_len << 4) | cur_op; else bad = true; ++n_runs; }
+        flush_run();
         if (errors != T.score) bad = true;                                       // the path must cost exactly what the score pass found
         WalkResult R; R.begin_col = j; R.cigar_len = bad ? 0xffffffffu : n_runs;
         L.results[T.out] = R;

@@ -139,6 +139,7 @@ struct DevBuf {
 struct PinnedBuf {                       // page-locked host staging memory
     void* p = nullptr;
     size_t cap = 0;
+    const char* tag = "page-locked";     // what it holds (FXG_TRACE_BATCHES names slow allocations)
     cudaError_t ensure_scaled(size_t bytes, double scale) {
         if (bytes <= cap) return cudaSuccess;
         size_t const big = std::min(size_t(double(bytes) * std::min(std::max(scale, 1.0), 16.0)), std::max(bytes, size_t(96) << 20));   // (page-locking is slow: tens of ms per 100 MB)
@@ -149,7 +150,7 @@ struct PinnedBuf {                       // page-locked host staging memory
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         size_t const want = std::max(bytes + bytes / 2 + 4096, 2 * cap);
-        AllocTimer timer("page-locked", want);
+        AllocTimer timer(tag, want);
         if (p) { cudaFreeHost(p); p = nullptr; }
         cap = 0;
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
@@ -223,6 +224,12 @@ struct Worker {
     cudaStream_t walk_stream[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_walk_done[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr}, ev_w0 = nullptr, ev_w1[kWalkSlots] = {nullptr, nullptr, nullptr, nullptr};
     PinnedBuf h_tasks, h_results, h_wtasks, h_wresults, h_rtasks, h_rresults, h_lv, h_lv_back, h_roots, h_root_back, h_hits;
+    Worker() {
+        h_tasks.tag = "page-locked tasks"; h_results.tag = "page-locked results"; h_wtasks.tag = "page-locked traceback tasks";
+        h_wresults.tag = "page-locked traceback results"; h_rtasks.tag = "page-locked range tasks"; h_rresults.tag = "page-locked range results";
+        h_lv.tag = "page-locked level records"; h_lv_back.tag = "page-locked level counters"; h_roots.tag = "page-locked root entries";
+        h_root_back.tag = "page-locked root counters"; h_hits.tag = "page-locked alignment records";
+    }
     fxg_counters ctr{};
     std::string err;
     std::vector<ConfigCacheEntry> cfg_cache = std::vector<ConfigCacheEntry>(8192);
@@ -1213,7 +1220,7 @@ PinnedBuf take_pinned(fxg_ctx* c) {
     return b;
 }
 void give_pinned(fxg_ctx* c, PinnedBuf& b) {
-    if (b.p && c->spare_pinned.size() < size_t(2 * c->n_groups + 8)) c->spare_pinned.push_back(b); else b.release();
+    if (b.p && c->spare_pinned.size() < size_t(2 * c->n_groups + 72)) c->spare_pinned.push_back(b); else b.release();   // (one per caller and batch in flight)
     b = PinnedBuf{};
 }
 // the smallest spare pool that holds `bytes`, else the largest (it will grow)
@@ -1559,6 +1566,7 @@ int prepare_job(fxg_ctx* c, fxg_job* J, std::string& err, fxg_counters& ctr) {
     auto carve = [&](size_t bytes) { size_t const at = off; off += (bytes + 255) & ~size_t(255); return at; };
     P.o_nodes = carve(n_nodes * sizeof(NodeRec)); P.o_leaves = carve(n_leaves * sizeof(LeafRec));
     P.o_reads = carve(n_reads * sizeof(ReadRec)); P.o_anchors = carve(n_walks * sizeof(AnchorRec16));
+    P.staging.tag = "page-locked job records";
     if (P.staging.ensure(off + 64) != cudaSuccess) return fail(err, FXG_ERR_OUT_OF_MEMORY, "cannot allocate staging for the job's records");
     P.used = off;
     CUDA_TRY(err, P.dev.ensure(off + 64));
@@ -2930,7 +2938,9 @@ int run_batch(fxg_ctx* c, WorkerGroup& grp, Batch& B, std::string& err, fxg_coun
     TracePlan plan;
     plan.n_parts = n_parts; plan.caps.assign(n_parts, 0); plan.bases.assign(n_parts, 0);
     plan.pool = B.cigars; plan.pool_len = &B.cigars_len; plan.ctx = c;
-    plan.scale = n_parts == 1 ? std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(rwb[n_reads], 1))) : 1.0;
+    // (the pool of a batch of several jobs goes back to the context and serves the next such batch, whatever its size; the
+    //  pool of a job that ran alone stays with the job, which needs the same amount every time)
+    plan.scale = n_parts == 1 && B.members.size() > 1 ? std::max(1.0, double(c->merge_max_walks) / double(std::max<uint32_t>(rwb[n_reads], 1))) : 1.0;
     auto const vt0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - vt0).count(); };
     uint64_t const budget = trace_budget_bytes(c, n_parts);
@@ -3072,7 +3082,10 @@ void run_tickets(fxg_ctx* c, WorkerGroup& grp, std::vector<Ticket*> const& mine,
         B.cigars = &pinned;
         std::string err;
         int rc = FXG_OK;
-        if (hi - lo == 1) { B.pool = &mine[lo]->J->pool; B.pool_len = mine[lo]->J->pool_len; }
+        if (hi - lo == 1) {
+            B.pool = &mine[lo]->J->pool; B.pool_len = mine[lo]->J->pool_len;
+            if (!pinned.p) std::swap(pinned, mine[lo]->J->cigars);     // a job that runs alone writes into the pool of its last run
+        }
         else rc = build_merged_pool(c, grp, B, err);
         if (rc == FXG_OK) rc = run_batch(c, grp, B, err, ctr);
         if (rc != FXG_OK) {
@@ -3168,6 +3181,7 @@ int submit_and_wait(fxg_ctx* c, fxg_job* J, std::unique_lock<std::mutex>& lock) 
             }
         }
         PinnedBuf pinned;                                // (picked from the context's spares when the batch knows how much it needs)
+        pinned.tag = "page-locked cigar pool";
         lock.unlock();
         fxg_counters ctr{};
         run_tickets(c, *g, mine, pinned, ctr);
