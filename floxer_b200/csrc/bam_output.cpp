@@ -73,9 +73,19 @@ int append_record(std::vector<uint8_t>& out, const char* qname, int32_t ref_id, 
                   const uint8_t* seq_ranks, uint32_t l_seq, const char* qual, bool with_nm, uint32_t nm) {
     size_t const l_name = std::strlen(qname) + 1;
     if (l_name > 255) return FXG_ERR_INVALID_ARGUMENT;             // read names hold at most 254 characters
-    if (n_ops > 65535) return FXG_ERR_OVERFLOW;                    // (longer CIGARs need the CG tag convention)
-    int64_t ref_span = 0;
-    for (uint32_t i = 0; i < n_ops; ++i) { uint32_t const op = ops[i] & 15u; if (op == FXG_CIGAR_D || op == FXG_CIGAR_EQ || op == FXG_CIGAR_X) ref_span += ops[i] >> 4; }
+    int64_t ref_span = 0, query_span = 0;
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        uint32_t const op = ops[i] & 15u;
+        if (op == FXG_CIGAR_D || op == FXG_CIGAR_EQ || op == FXG_CIGAR_X) ref_span += ops[i] >> 4;
+        if (op == FXG_CIGAR_I || op == FXG_CIGAR_EQ || op == FXG_CIGAR_X) query_span += ops[i] >> 4;
+    }
+    // n_cigar_op is 16 bits wide: a longer CIGAR (a 100 kbp read at 10 % errors can have one) goes into the CG:B,I tag and
+    // the record carries the placeholder <query length>S<reference length>N (SAM specification, section 4.2.2)
+    bool const long_cigar = n_ops > 65535;
+    if (long_cigar && (query_span >= (int64_t(1) << 28) || ref_span >= (int64_t(1) << 28))) return FXG_ERR_OVERFLOW;
+    uint32_t const placeholder[2] = {uint32_t(query_span) << 4 | 4u /* S */, uint32_t(ref_span) << 4 | 3u /* N */};
+    uint32_t const n_written = long_cigar ? 2u : n_ops;
+    const uint32_t* const written = long_cigar ? placeholder : ops;
     size_t const size_at = out.size();
     put_u32(out, 0);                                               // block_size, patched below
     put_i32(out, ref_id); put_i32(out, pos);
@@ -83,10 +93,10 @@ int append_record(std::vector<uint8_t>& out, const char* qname, int32_t ref_id, 
     // (the binning scheme covers coordinates below 2^29; beyond it -- and for unmapped records -- the bin of "no position")
     int64_t const end = int64_t(pos) + std::max<int64_t>(ref_span, 1);
     put_u16(out, pos < 0 || end > (int64_t(1) << 29) ? 4680u : reg2bin(pos, end));
-    put_u16(out, n_ops); put_u16(out, flag); put_u32(out, l_seq);
+    put_u16(out, n_written); put_u16(out, flag); put_u32(out, l_seq);
     put_i32(out, -1); put_i32(out, -1); put_i32(out, 0);           // no mate
     put_bytes(out, qname, l_name);
-    for (uint32_t i = 0; i < n_ops; ++i) put_u32(out, ops[i]);
+    for (uint32_t i = 0; i < n_written; ++i) put_u32(out, written[i]);
     for (uint32_t p = 0; p < l_seq; p += 2) {
         uint8_t const hi = kRankToNibble[std::min<uint8_t>(seq_ranks[p], 5)];
         uint8_t const lo = p + 1 < l_seq ? kRankToNibble[std::min<uint8_t>(seq_ranks[p + 1], 5)] : 0;
@@ -99,6 +109,11 @@ int append_record(std::vector<uint8_t>& out, const char* qname, int32_t ref_id, 
         if (nm < 256) { out.push_back('C'); out.push_back(uint8_t(nm)); }
         else if (nm < 65536) { out.push_back('S'); put_u16(out, nm); }
         else { out.push_back('I'); put_u32(out, nm); }
+    }
+    if (long_cigar) {
+        out.push_back('C'); out.push_back('G'); out.push_back('B'); out.push_back('I');
+        put_u32(out, n_ops);
+        for (uint32_t i = 0; i < n_ops; ++i) put_u32(out, ops[i]);
     }
     uint32_t const block_size = uint32_t(out.size() - size_at - 4);
     for (int i = 0; i < 4; ++i) out[size_at + size_t(i)] = uint8_t(block_size >> (8 * i));
@@ -115,6 +130,7 @@ int fxg_write_bam(const fxg_alignment* al, size_t n_al, const uint32_t* cigar_po
     if (!bytes || !bytes_len || (n_al && !al) || (n_reads && (!reads || !forward_pool || !queries)) || (n_references && (!reference_ids || !reference_lengths)))
         return FXG_ERR_INVALID_ARGUMENT;
     *bytes = nullptr; *bytes_len = 0;
+    try {
     std::vector<uint8_t> raw;
     raw.reserve(size_t(1) << 20);
     if (with_header) {
@@ -172,6 +188,7 @@ int fxg_write_bam(const fxg_alignment* al, size_t n_al, const uint32_t* cigar_po
     std::memcpy(buf, packed.data(), packed.size());
     *bytes = buf; *bytes_len = packed.size();
     return FXG_OK;
+    } catch (...) { return FXG_ERR_OUT_OF_MEMORY; }              // (std::bad_alloc / length_error of the buffers: nothing crosses the C ABI)
 }
 
 int fxg_job_write_bam(const fxg_job* job, size_t n_references, const char* const* reference_ids, const uint64_t* reference_lengths,

@@ -2799,7 +2799,8 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
     std::unique_lock<std::mutex> lock(c->mu);
     CUDA_TRY(c->err, cudaSetDevice(c->device));
     WorkerGroup& grp = acquire_group(c, lock);
-    struct Release { fxg_ctx* c; WorkerGroup& g; ~Release() { release_group(c, g); } } release{c, grp};   // (the lock is still held when it runs)
+    lock.unlock();                                   // the group is this call's own from here on: other callers run beside it
+    struct Release { fxg_ctx* c; WorkerGroup& g; ~Release() { std::lock_guard<std::mutex> l(c->mu); release_group(c, g); } } release{c, grp};
     Worker& w = *grp.workers[0];
     w.ctr = fxg_counters{};
     // one batch of independent alignments, one or two waits and nothing else for this thread to do meanwhile: poll longer
@@ -2864,8 +2865,8 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
             }
         }
     }
-    add_counters(c->ctr, w.ctr);
-    if (rc != FXG_OK) { c->err = w.err; tls_last_error = w.err; return rc; }
+    { std::lock_guard<std::mutex> l(c->mu); add_counters(c->ctr, w.ctr); if (rc != FXG_OK) c->err = w.err; }
+    if (rc != FXG_OK) { tls_last_error = w.err; return rc; }
     b->ran = true;
     return FXG_OK;
 }

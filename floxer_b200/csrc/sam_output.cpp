@@ -56,6 +56,7 @@ int fxg_job_write_sam(const fxg_job* job, size_t n_references, const char* const
     if (!job || !text || !text_len || (n_reads && (!reads || !forward_pool || !queries)) || (n_references && (!reference_ids || !reference_lengths)))
         return FXG_ERR_INVALID_ARGUMENT;
     *text = nullptr; *text_len = 0;
+    try {
     size_t const n_al = fxg_job_num_alignments(job);
     const fxg_alignment* al = fxg_job_alignments(job);
     const uint32_t* ops = fxg_job_cigar_pool(job);
@@ -117,6 +118,7 @@ int fxg_job_write_sam(const fxg_job* job, size_t n_references, const char* const
     buf[out.size()] = 0;
     *text = buf; *text_len = out.size();
     return FXG_OK;
+    } catch (...) { return FXG_ERR_OUT_OF_MEMORY; }              // (std::bad_alloc / length_error of the text buffer: nothing crosses the C ABI)
 }
 
 void fxg_free(void* p) { std::free(p); }

@@ -14,7 +14,7 @@ from oracle import oracle as o
 from oracle import sam_oracle
 
 NIBBLES = "=ACMGRSVTWYHKDBN"
-OPS = {1: "I", 2: "D", 7: "=", 8: "X"}
+OPS = {1: "I", 2: "D", 3: "N", 4: "S", 7: "=", 8: "X"}
 
 
 @pytest.fixture(scope="module")
@@ -77,6 +77,15 @@ def parse_bam(data: bytes, with_header=True):
         nm = None
         while p < at + 4 + size:
             tag, typ = raw[p:p + 2].decode(), chr(raw[p + 2])
+            if typ == "B":                                                    # the real CIGAR of a record with more than 65 535 operations
+                assert tag == "CG" and chr(raw[p + 3]) == "I"
+                count = struct.unpack_from("<I", raw, p + 4)[0]
+                real = struct.unpack_from(f"<{count}I", raw, p + 8)
+                assert cigar == f"{sum(v >> 4 for v in real if (v & 15) in (1, 7, 8))}S{sum(v >> 4 for v in real if (v & 15) in (2, 7, 8))}N"
+                cigar = "".join(f"{v >> 4}{OPS[v & 15]}" for v in real)
+                span = sum(v >> 4 for v in real if (v & 15) in (2, 7, 8))
+                p += 8 + 4 * count
+                continue
             width = {"C": 1, "S": 2, "I": 4}[typ]
             val = int.from_bytes(raw[p + 3:p + 3 + width], "little")
             p += 3 + width
@@ -185,3 +194,23 @@ def test_bam_many_blocks_and_bad_input(gpu):
         gpu.write_bam(al, cg, batch, ["a"], [10], names)                     # an alignment names reference 1
     with pytest.raises(gpu.FloxerGpuError):
         gpu.write_bam(al, cg, batch, ["a", "b"], [10, 20], ["x" * 300] + names[1:])
+
+
+def test_bam_cigar_with_more_than_65535_operations(gpu):
+    """n_cigar_op is 16 bits wide: a longer CIGAR travels in the CG:B,I tag behind the placeholder <query>S<reference>N
+    (SAM specification 4.2.2) -- a 100 kbp read at 10 % errors can have one."""
+    m = 70_001
+    bb = BatchBuilder()
+    node = np.zeros(1, dtype=abi.PEX_NODE_DTYPE)
+    node["parent_id"] = abi.NULL_ID
+    node["query_index_to"] = m - 1
+    fwd = (np.arange(m) % 4 + 1).astype(np.uint8)
+    bb.add(fwd, fwd[::-1].copy(), node[:0], node, np.zeros(0, dtype=abi.ANCHOR_DTYPE), np.zeros(0, dtype=abi.ANCHOR_DTYPE))
+    ops = np.array([(1 << 4) | (7 if i % 2 == 0 else 8) for i in range(m)], dtype=np.uint32)     # 1=1X1=1X...: 70 001 operations
+    al = np.array([(1234, 0, len(ops), m // 2, 0, 0, 0, (0,) * 7), (99, 0, 3, 5, 0, 0, 1, (0,) * 7)], dtype=abi.ALIGNMENT_DTYPE)
+    data = gpu.write_bam(al, ops, bb.build(), ["chr"], [1 << 20], ["long"])
+    _, _, records = parse_bam(data)
+    assert len(records) == 2
+    assert records[0]["cigar"] == "".join(f"1{'=' if i % 2 == 0 else 'X'}" for i in range(m)) and records[0]["span"] == m
+    assert records[0]["pos"] == 1234 and records[0]["bin"] == reg2bin(1234, 1234 + m) and records[0]["flag"] == 256 and records[0]["nm"] == m // 2
+    assert records[1]["cigar"] == "1=1X1=" and records[1]["flag"] == 16          # fewer errors: the primary record
