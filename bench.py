@@ -305,13 +305,13 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
         pageable_s, _, _ = e2e_arm(batch)                # the caller's buffers as floxer has them: ordinary std::vector memory
 
     # max over ranks of the times, sum of the units
-    t = torch.tensor([total_s, e2e_s, pageable_s or 0.0], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_s, e2e_s, pageable_s or 0.0, ctr["alloc_ms"], e2e_ctr["alloc_ms"]], dtype=torch.float64, device="cuda")
     cells_batch = stats["cells_inner"] + stats["cells_root"]
     u = torch.tensor([cells_batch * lanes, len(batch) * lanes], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
-    total_s, e2e_s, pageable_s = [float(x) for x in t.cpu()]
+    total_s, e2e_s, pageable_s, alloc_ms_worst, e2e_alloc_ms_worst = [float(x) for x in t.cpu()]
     cells_step, reads_step = [float(x) for x in u.cpu()]
     if rank != 0:
         return None
@@ -362,7 +362,8 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
             "checkpoint_bytes_per_batch": ctr["trace_bytes"] / n_batches},
         "queue": {"batches": int(ctr["batches"]), "jobs": int(ctr["batch_jobs"]), "jobs_per_batch": ctr["batch_jobs"] / max(ctr["batches"], 1),
                   "launches_per_job": ctr["kernel_launches"] / max(ctr["batch_jobs"], 1),
-                  "alloc_ms_in_region": ctr["alloc_ms"], "alloc_calls_in_region": int(ctr["alloc_calls"])},
+                  "alloc_ms_in_region": ctr["alloc_ms"], "alloc_calls_in_region": int(ctr["alloc_calls"]),
+                  "alloc_ms_in_region_worst_rank": alloc_ms_worst, "alloc_ms_in_e2e_region_worst_rank": e2e_alloc_ms_worst},
         "shortcuts_per_batch": {k: ctr[k] / n_batches for k in ("shared_score_passes", "rescored_roots", "inferred_inner", "shared_tracebacks")},
         "batch_latency_alone_ms": [round(x, 3) for x in lat_ms],
         "alignments_per_batch": n_alignments, "stats_per_batch": stats,

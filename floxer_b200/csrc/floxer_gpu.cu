@@ -158,6 +158,14 @@ struct PinnedBuf {                       // page-locked host staging memory
         cap = want;
         return e;
     }
+    cudaError_t exactly(size_t bytes) {           // a fresh buffer of exactly this size
+        AllocTimer timer(tag, bytes);
+        release();
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = bytes;
+        return e;
+    }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -647,18 +655,48 @@ bool cached_config(std::vector<ConfigCacheEntry>& cache, Pass const& p, size_t s
     return e.ok;
 }
 
-// LSD radix sort of 64-bit keys on bits [lo_bit, hi_bit)
+// Host loops over a million independent alignments (fxg_align_batch: the verification-only microbenchmark of config 5)
+// are cut into contiguous chunks for up to 8 threads; the loops of a verification batch stay on the caller's thread.
+size_t parallel_threads(size_t n, size_t min_chunk) {
+    size_t const hw = std::max<size_t>(1, std::thread::hardware_concurrency() / 2);
+    return std::max<size_t>(1, std::min<size_t>({size_t(8), hw, n / std::max<size_t>(min_chunk, 1)}));
+}
+template <class F> void parallel_chunks(size_t T, size_t n, F&& f) {         // f(thread, lo, hi); the caller's thread takes the first chunk
+    if (T <= 1) { f(size_t(0), size_t(0), n); return; }
+    std::vector<std::thread> th;
+    th.reserve(T - 1);
+    for (size_t t = 1; t < T; ++t) th.emplace_back([&f, t, T, n] { f(t, n * t / T, n * (t + 1) / T); });
+    f(size_t(0), size_t(0), n / T);
+    for (std::thread& x : th) x.join();
+}
+
+// LSD radix sort of 64-bit keys on bits [lo_bit, hi_bit): per-thread histograms, then every thread scatters its own chunk
+// to where the chunks before it leave off (stable)
 void radix_sort(std::vector<uint64_t>& keys, std::vector<uint64_t>& tmp, int lo_bit, int hi_bit) {
     size_t const N = keys.size();
     tmp.resize(N);
+    size_t const T = parallel_threads(N, size_t(1) << 16);
+    std::vector<uint32_t> hist(T * 2048);
     for (int shift = lo_bit; shift < hi_bit; shift += 11) {
-        uint32_t count[2049] = {0};
-        for (size_t i = 0; i < N; ++i) count[((keys[i] >> shift) & 2047u) + 1]++;
-        for (int i = 0; i < 2048; ++i) count[i + 1] += count[i];
-        for (size_t i = 0; i < N; ++i) tmp[count[(keys[i] >> shift) & 2047u]++] = keys[i];
+        std::fill(hist.begin(), hist.end(), 0u);
+        const uint64_t* const src = keys.data();
+        uint64_t* const dst = tmp.data();
+        parallel_chunks(T, N, [&](size_t t, size_t lo, size_t hi) {
+            uint32_t* const h = hist.data() + t * 2048;
+            for (size_t i = lo; i < hi; ++i) h[(src[i] >> shift) & 2047u]++;
+        });
+        uint32_t running = 0;
+        for (size_t d = 0; d < 2048; ++d)
+            for (size_t t = 0; t < T; ++t) { uint32_t const n = hist[t * 2048 + d]; hist[t * 2048 + d] = running; running += n; }
+        parallel_chunks(T, N, [&](size_t t, size_t lo, size_t hi) {
+            uint32_t* const h = hist.data() + t * 2048;
+            for (size_t i = lo; i < hi; ++i) dst[h[(src[i] >> shift) & 2047u]++] = src[i];
+        });
         keys.swap(tmp);
     }
 }
+
+std::vector<ConfigCacheEntry>& thread_config_cache(const fxg_ctx* c);
 
 // ------------------------------------------------------------------------------------------------ running passes
 
@@ -676,14 +714,23 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     // sort key: configuration (descending cost class), then steps descending, then the pass index
     w.cfgs.resize(N);
     w.keys.resize(N);
-    for (size_t i = 0; i < N; ++i) {
-        Config& cf = w.cfgs[i];
-        if (!cached_config(w.cfg_cache, passes[i], c->smem_limit, c->force_wide, cf))
-            return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
-                        passes[i].m, passes[i].n, passes[i].dlo, passes[i].dhi);
-        uint64_t const steps = std::min<uint64_t>(uint64_t(passes[i].n) + cf.nb - 1, (1u << 19) - 1);
-        uint64_t const cls = cf.G == kWideG ? 0 : uint64_t(5 - cf.widx) * 32 + (32 - cf.G) + 1;         // 0 = the multi-warp kernel, 1 = W 32, G 32
-        w.keys[i] = (cls << 51) | ((((1ull << 19) - 1) - steps) << 32) | uint64_t(i);
+    size_t const T = parallel_threads(N, size_t(1) << 16);
+    {
+        std::vector<size_t> bad(T, SIZE_MAX);
+        parallel_chunks(T, N, [&](size_t t, size_t lo, size_t hi) {
+            std::vector<ConfigCacheEntry>& cache = t == 0 ? w.cfg_cache : thread_config_cache(c);
+            for (size_t i = lo; i < hi; ++i) {
+                Config& cf = w.cfgs[i];
+                if (!cached_config(cache, passes[i], c->smem_limit, c->force_wide, cf)) { bad[t] = i; return; }
+                uint64_t const steps = std::min<uint64_t>(uint64_t(passes[i].n) + cf.nb - 1, (1u << 19) - 1);
+                uint64_t const cls = cf.G == kWideG ? 0 : uint64_t(5 - cf.widx) * 32 + (32 - cf.G) + 1;         // 0 = the multi-warp kernel, 1 = W 32, G 32
+                w.keys[i] = (cls << 51) | ((((1ull << 19) - 1) - steps) << 32) | uint64_t(i);
+            }
+        });
+        for (size_t t = 0; t < T; ++t)
+            if (bad[t] != SIZE_MAX)
+                return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
+                            passes[bad[t]].m, passes[bad[t]].n, passes[bad[t]].dlo, passes[bad[t]].dhi);
     }
     g_prof.lap(w, 3);
     radix_sort(w.keys, w.keys_tmp, 32, 64);
@@ -694,15 +741,23 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
     CUDA_TRY(w.err, w.d_tasks.ensure(N * sizeof(DpTask)));
     CUDA_TRY(w.err, w.d_results.ensure(N * sizeof(DpResult)));
     DpTask* tasks = w.h_tasks.as<DpTask>();
-    for (size_t i = 0; i < N; ++i) {
-        uint32_t const idx = uint32_t(w.keys[i]);
-        Pass const& p = passes[idx];
-        DpTask& t = tasks[i];
-        t.ref_base = p.ref_base; t.query_base = p.query_base;
-        t.trace_base = trace ? ck_bases[idx] : 0;
-        t.n = p.n; t.m = p.m; t.dlo = p.dlo; t.dhi = p.dhi; t.flags = p.flags; t.out = idx;
-        w.ctr.dp_word_steps += w.cfgs[idx].word_steps;
-        w.ctr.dp_cells_full += uint64_t(p.m) * p.n;
+    {
+        std::vector<uint64_t> sums(2 * T, 0);
+        parallel_chunks(T, N, [&](size_t th, size_t lo, size_t hi) {
+            uint64_t ws = 0, cells = 0;
+            for (size_t i = lo; i < hi; ++i) {
+                uint32_t const idx = uint32_t(w.keys[i]);
+                Pass const& p = passes[idx];
+                DpTask& t = tasks[i];
+                t.ref_base = p.ref_base; t.query_base = p.query_base;
+                t.trace_base = trace ? ck_bases[idx] : 0;
+                t.n = p.n; t.m = p.m; t.dlo = p.dlo; t.dhi = p.dhi; t.flags = p.flags; t.out = idx;
+                ws += w.cfgs[idx].word_steps;
+                cells += uint64_t(p.m) * p.n;
+            }
+            sums[2 * th] = ws; sums[2 * th + 1] = cells;
+        });
+        for (size_t th = 0; th < T; ++th) { w.ctr.dp_word_steps += sums[2 * th]; w.ctr.dp_cells_full += sums[2 * th + 1]; }
     }
     w.ctr.dp_tasks += N;
     CUDA_TRY(w.err, cudaMemcpyAsync(w.d_tasks.p, tasks, N * sizeof(DpTask), cudaMemcpyHostToDevice, w.stream));
@@ -2569,8 +2624,23 @@ struct TracePlan {
                 PinnedBuf fit = take_pinned_fit(ctx, need);
                 if (fit.p) { give_pinned(ctx, *pool); *pool = fit; }
             }
+            size_t const cap_before = pool->cap;
             cudaError_t const e = pool->ensure_scaled(need, scale);
             if (e != cudaSuccess) { failed = true; err = std::string("cigar pool allocation: ") + cudaGetErrorString(e); }
+            else if (pool->cap != cap_before && scale > 1.0 && ctx) {
+                // A pool for merged batches had to be made: as many of them are in use at a time as batches run or wait for
+                // their members to pick up their results.  Page-locking takes tens of milliseconds, so the others are made
+                // now, in one go (the first merged batches of a context pay; no batch after them does).
+                size_t have = 0;
+                { std::lock_guard<std::mutex> ctx_lock(ctx->mu); for (PinnedBuf const& b : ctx->spare_pinned) have += b.cap >= pool->cap; }
+                size_t const want = size_t(2 * ctx->n_groups);
+                for (size_t i = have + 1; i < want && pool->cap <= (size_t(64) << 20); ++i) {
+                    PinnedBuf extra; extra.tag = pool->tag;
+                    if (extra.exactly(pool->cap) != cudaSuccess) { (void)cudaGetLastError(); break; }
+                    std::lock_guard<std::mutex> ctx_lock(ctx->mu);
+                    give_pinned(ctx, extra);
+                }
+            }
             *pool_len = size_t(total);
             cv.notify_all();
         } else {
@@ -2811,39 +2881,66 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
     {
         RunTimer run_timer(grp, w.ctr);
         size_t const N = b->tasks.size();
-        b->results.assign(N, fxg_align_result{});
+        b->results.resize(N);
         b->cigars_len = 0;
-        std::vector<Pass> passes, root_passes; passes.reserve(N);
-        std::vector<uint32_t> owner, root_owner, root_k; owner.reserve(N);
-        for (size_t i = 0; i < N; ++i) {
-            fxg_align_task const& t = b->tasks[i];
-            b->results[i].orientation = t.orientation;
-            uint32_t const flags = (t.mode == FXG_MODE_NO_CIGAR ? kFlagReverse : 0u) | (t.ref_id == FXG_REF_INLINE ? kFlagInlineRef : 0u);
-            uint64_t const ref_base = (t.ref_id == FXG_REF_INLINE ? 0 : c->refs.base[t.ref_id]) + t.ref_offset;
-            Pass p;
-            if (t.query_len == 0) {
-                // empty query: aligns with zero errors; the rightmost minimum of an all-zero last row is column n
-                b->results[i].exists = 1;
-                if (t.mode == FXG_MODE_CIGAR) b->results[i].start_in_reference = t.reference_span_offset + t.ref_len;
-                else if (t.mode == FXG_MODE_NO_CIGAR) b->results[i].start_in_reference = t.reference_span_offset;
-                continue;
+        // every task's pass (if it has one), by chunks of tasks; then the passes of every chunk move to their place in
+        // task order: score passes and passes whose CIGAR is wanted (these go through the root level's code)
+        size_t const T = parallel_threads(N, size_t(1) << 16);
+        std::vector<std::vector<Pass>> part_passes(T), part_roots(T);
+        std::vector<std::vector<uint32_t>> part_owner(T), part_root_owner(T);
+        parallel_chunks(T, N, [&](size_t th, size_t lo, size_t hi) {
+            part_passes[th].reserve(hi - lo); part_owner[th].reserve(hi - lo);
+            for (size_t i = lo; i < hi; ++i) {
+                fxg_align_task const& t = b->tasks[i];
+                b->results[i] = fxg_align_result{};
+                b->results[i].orientation = t.orientation;
+                uint32_t const flags = (t.mode == FXG_MODE_NO_CIGAR ? kFlagReverse : 0u) | (t.ref_id == FXG_REF_INLINE ? kFlagInlineRef : 0u);
+                uint64_t const ref_base = (t.ref_id == FXG_REF_INLINE ? 0 : c->refs.base[t.ref_id]) + t.ref_offset;
+                Pass p;
+                if (t.query_len == 0) {
+                    // empty query: aligns with zero errors; the rightmost minimum of an all-zero last row is column n
+                    b->results[i].exists = 1;
+                    if (t.mode == FXG_MODE_CIGAR) b->results[i].start_in_reference = t.reference_span_offset + t.ref_len;
+                    else if (t.mode == FXG_MODE_NO_CIGAR) b->results[i].start_in_reference = t.reference_span_offset;
+                    continue;
+                }
+                if (!score_pass_for(ref_base, t.query_offset, t.ref_len, t.query_len, t.max_errors, flags, p)) continue;
+                if (t.mode == FXG_MODE_CIGAR) { part_roots[th].push_back(p); part_root_owner[th].push_back(uint32_t(i)); }
+                else { part_passes[th].push_back(p); part_owner[th].push_back(uint32_t(i)); }
             }
-            if (!score_pass_for(ref_base, t.query_offset, t.ref_len, t.query_len, t.max_errors, flags, p)) continue;
-            if (t.mode == FXG_MODE_CIGAR) { root_passes.push_back(p); root_owner.push_back(uint32_t(i)); root_k.push_back(t.max_errors); }
-            else { passes.push_back(p); owner.push_back(uint32_t(i)); }
+        });
+        std::vector<Pass> passes, root_passes;
+        std::vector<uint32_t> owner, root_owner, root_k;
+        if (T == 1) { passes.swap(part_passes[0]); owner.swap(part_owner[0]); root_passes.swap(part_roots[0]); root_owner.swap(part_root_owner[0]); }
+        else {
+            std::vector<size_t> at(T + 1, 0), root_at(T + 1, 0);
+            for (size_t th = 0; th < T; ++th) { at[th + 1] = at[th] + part_passes[th].size(); root_at[th + 1] = root_at[th] + part_roots[th].size(); }
+            passes.resize(at[T]); owner.resize(at[T]); root_passes.resize(root_at[T]); root_owner.resize(root_at[T]);
+            parallel_chunks(T, T, [&](size_t, size_t lo, size_t hi) {
+                for (size_t th = lo; th < hi; ++th) {
+                    std::copy(part_passes[th].begin(), part_passes[th].end(), passes.begin() + long(at[th]));
+                    std::copy(part_owner[th].begin(), part_owner[th].end(), owner.begin() + long(at[th]));
+                    std::copy(part_roots[th].begin(), part_roots[th].end(), root_passes.begin() + long(root_at[th]));
+                    std::copy(part_root_owner[th].begin(), part_root_owner[th].end(), root_owner.begin() + long(root_at[th]));
+                }
+            });
         }
+        root_k.resize(root_owner.size());
+        for (size_t q = 0; q < root_owner.size(); ++q) root_k[q] = b->tasks[root_owner[q]].max_errors;
         const DpResult* res = nullptr;
         rc = run_passes(c, w, b->pool, passes, nullptr, nullptr, &res);
         if (rc == FXG_OK) {
-            for (size_t q = 0; q < passes.size(); ++q) {
-                fxg_align_task const& t = b->tasks[owner[q]];
-                fxg_align_result& r = b->results[owner[q]];
-                if (res[q].score > int32_t(t.max_errors)) continue;
-                r.exists = 1;
-                if (t.mode == FXG_MODE_EXISTS) continue;
-                r.num_errors = uint32_t(res[q].score);
-                r.start_in_reference = t.reference_span_offset + (t.ref_len - res[q].end_col);   // alignment.cpp:135-139
-            }
+            parallel_chunks(T, passes.size(), [&](size_t, size_t lo, size_t hi) {
+                for (size_t q = lo; q < hi; ++q) {
+                    fxg_align_task const& t = b->tasks[owner[q]];
+                    fxg_align_result& r = b->results[owner[q]];
+                    if (res[q].score > int32_t(t.max_errors)) continue;
+                    r.exists = 1;
+                    if (t.mode == FXG_MODE_EXISTS) continue;
+                    r.num_errors = uint32_t(res[q].score);
+                    r.start_in_reference = t.reference_span_offset + (t.ref_len - res[q].end_col);   // alignment.cpp:135-139
+                }
+            });
             w.cig_used = 0;
             std::vector<RootOut> outs;
             rc = run_root_passes(c, w, b->pool, root_passes, root_k, trace_budget_bytes(c, 1), outs);
