@@ -135,7 +135,7 @@ struct DpLaunch {
 };
 
 // S = T + P + carry over CH consecutive words with the hardware carry chain (IADD3.X); one asm
-// statement per chunk so that nothing can clobber CC in between.  cin / return value are 0 or 1.
+// statement per chunk so that nothing can clobber CC in between.  cin: zero or anything else (= a carry); the return value is 0 or 1.
 template <int CH, bool COUT> struct Chain;
 template <bool COUT> struct Chain<1, COUT> {
     static __device__ __forceinline__ uint32_t run(uint32_t* S, const uint32_t* T, const uint32_t* P, uint32_t cin) {
@@ -270,13 +270,16 @@ __device__ __forceinline__ void mad_hi_acc(uint32_t& acc, uint32_t a, uint32_t b
 // (Measured on B200: IMAD / IMAD.HI share their issue slots with the ALU pipe, so shifting HP with multiply-adds
 // instead of one funnel shift gains nothing.)
 // KEEP_HP: also hand back HP of every word (the traceback wants HP and the new Pv of each cell).
-template <int W, bool KEEP_HP>
+// RAW_CARRY (the engine): in_hn is either zero or 0x80000000 and goes into the adder's carry chain as it is (any non-zero
+// value is a carry), and out_hn is handed back in the same form -- bit 31 alone -- so that the lane below can use it
+// without a shift or a mask on the ALU pipe.
+template <int W, bool KEEP_HP, bool RAW_CARRY = false>
 __device__ __forceinline__ void block_column(uint32_t (&Pv)[W], uint32_t (&Mv)[W], const uint32_t (&Eq)[W], uint32_t in_hp, uint32_t in_hn,
                                              uint32_t& out_hp, uint32_t& out_hn, uint32_t (&hp_all)[KEEP_HP ? W : 1]) {
     constexpr int CH = W < 8 ? W : 8;
     uint32_t hp_prev = in_hp;
     uint32_t hp_last = in_hp, hn_last = in_hn;
-    uint32_t carry = in_hn >> 31;                         // the adder's carry across a word boundary equals the HN bit there
+    uint32_t carry = RAW_CARRY ? in_hn : in_hn >> 31;     // the adder's carry across a word boundary equals the HN bit there
 #pragma unroll
     for (int c0 = 0; c0 < W; c0 += CH) {
         uint32_t Tt[CH], Sm[CH];
@@ -293,7 +296,7 @@ __device__ __forceinline__ void block_column(uint32_t (&Pv)[W], uint32_t (&Mv)[W
             uint32_t const HP = lop3<0xF1>(mv, pv, D0p);                      // Mv | ~(Pv | D0p)
             uint32_t const HPs = __funnelshift_l(hp_prev, HP, 1);
             hp_prev = HP;
-            if (c0 + i == W - 1) { hp_last = HP; hn_last = pv & D0p; }        // Pv & Mv == 0
+            if (c0 + i == W - 1) { hp_last = HP; hn_last = RAW_CARRY ? lop3<0x80>(pv, D0p, 0x80000000u) : (pv & D0p); }   // Pv & Mv == 0
             Mv[c0 + i] = lop3<0xE0>(HPs, D0p, mv);                            // HPs & (D0p | Mv)
             uint32_t const u = lop3<0xFE>(HPs, D0p, mv);                      // HPs | D0
             Pv[c0 + i] = lop3<0xF3>(HNs, u, 0u);                              // HNs | ~(HPs | D0)
@@ -323,15 +326,21 @@ __device__ __forceinline__ void write_checkpoint(uint32_t* rec, const uint32_t (
 // Steps t .. evt-1 of every lane of the warp: no block starts or ends in this range, so the loop is the recurrence
 // and nothing else -- no divergent branch (inactive lanes run the same instructions on dead state and keep publishing
 // the "+1 per column" boundary), window characters two steps and Eq rows one step ahead of their use.
-// FIRST: some lane is on block 0 (its upper boundary is row 0: no carries come in);
+// What a lane takes from the lane of the block above goes through three masks (Upper): the neighbour's deltas as they
+// are, or zeros (block 0: row 0 of a semi-global matrix is all zeros), or "+1 per column" (the block above has ended:
+// its lane may already be at work on its next block, and what lies beyond a block's last column is bounded by +1 steps).
+// The block above ends with the step before an event, and the step of the event still reads its last column: `peel`
+// (warp-uniform) runs that one step with the masks `first` and the others with `rest`.
 // LAST:  some lane is on the last block (tracks the minimum of the last row);
 // CKPT:  working blocks leave a checkpoint record after every step that is a multiple of 32 (the loop is cut there, so
 //        that the stores stay out of the recurrence).
-template <int W, bool CKPT, bool FIRST, bool LAST>
+struct Upper { uint32_t keep, hp_add; };      // x * keep + hp_add (multiply-add pipe): keep = 1 takes the neighbour's deltas, keep = 0 replaces them; hp_add = 0x80000000: "+1 per column"
+template <int W, bool CKPT, bool LAST>
 __device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t const evt, bool const active, uint32_t const src_lane,
-                                          uint32_t const last_block, const uint8_t* const win0, const uint8_t* const idle_chars, uint32_t const two) {
+                                          uint32_t const last_block, const uint8_t* const win0, const uint8_t* const idle_chars, uint32_t const two,
+                                          Upper const first, Upper const rest, bool peel) {
     uint32_t const inc = active ? 1u : 0u;
-    bool const first = FIRST && S.b == 0;
+    Upper up = peel ? first : rest;
     bool const track = LAST && active && S.b == last_block;
     // character of column j is win0[j - 1] (inside the ring buffer); idle lanes keep reading one valid character
     uint32_t wp = uint32_t(__cvta_generic_to_shared(active ? win0 + (int32_t(t) - int32_t(S.b) - 1) : idle_chars));
@@ -353,9 +362,10 @@ __device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t 
         wp += inc; cn = lds_u8(wp);                       /* character of the step after it */             \
         uint32_t r_hp = __shfl_sync(0xffffffffu, S.o_hp, src_lane);                                        \
         uint32_t r_hn = __shfl_sync(0xffffffffu, S.o_hn, src_lane);                                        \
-        if (first) { r_hp = 0; r_hn = 0; }                /* row 0 of a semi-global matrix is all zeros */ \
+        r_hp = mad_lo(r_hp, up.keep, up.hp_add);          /* only bit 31 is looked at */                   \
+        r_hn = mad_lo(r_hn, up.keep, 0u);                 /* 0 or 0x80000000 */                            \
         uint32_t hp, hn;                                                                                   \
-        block_column<W, false>(S.Pv, S.Mv, EQ_USE, r_hp, r_hn, hp, hn, no_hp);                             \
+        block_column<W, false, true>(S.Pv, S.Mv, EQ_USE, r_hp, r_hn, hp, hn, no_hp);                       \
         S.o_hp = mad_lo(hp, pub_a, pub_hp_b); S.o_hn = mad_lo(hn, pub_a, 0u);                              \
         mad_hi_acc(n_hp, hp, two); mad_hi_acc(n_hn, hn, two);                                        \
         if (LAST) {                                                                                        \
@@ -367,7 +377,7 @@ __device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t 
     }
     while (t < evt) {
         // up to and including the next multiple of 32 (checkpoint passes), or all the way
-        uint32_t const seg = CKPT ? min(evt, ((t + 31u) & ~31u) + 1u) : evt;
+        uint32_t const seg = peel ? t + 1u : (CKPT ? min(evt, ((t + 31u) & ~31u) + 1u) : evt);
         while (t + 1 < seg) { FXG_STEP(EqA, EqB) FXG_STEP(EqB, EqA) }
         if (t < seg) {
             FXG_STEP(EqA, EqB)
@@ -377,9 +387,11 @@ __device__ __forceinline__ void run_steps(LaneState<W>& S, uint32_t t, uint32_t 
         if (CKPT) {
             if (((t - 1) & 31u) == 0 && active) { write_checkpoint<W>(S.ckp, S.Pv, S.Mv, __brev(S.acc_hp), __brev(S.acc_hn)); S.ckp += ck_record_words(W); }
         }
+        if (peel) { peel = false; up = rest; }
     }
 #undef FXG_STEP
-    S.score = score_base + int32_t(n_hp) - int32_t(n_hn);
+    // (a lane that did not work keeps the value its last block ended with: a band of one diagonal starts the block below from it)
+    S.score = active ? score_base + int32_t(n_hp) - int32_t(n_hn) : score_base;
 }
 
 // 32 consecutive window characters (one 16-byte chunk of the packed store) as bytes.  `logical` counts chunks in sweep
@@ -473,9 +485,14 @@ __device__ __forceinline__ void dp_task_group(DpLaunch const& L, const DpTask* c
     S.b = r; S.o_hp = 0x80000000u; S.o_hn = 0;      // an idle lane publishes "the boundary grows by +1 per column"
     S.score = 0; S.best = kNoScore; S.best_col = 0;
     S.eqb = peq;
+    int32_t ce_up = 0;                              // last column of the block above the lane's current block
     auto set_block = [&](uint32_t blk) {
         S.cs = 0x7fffffff; S.ce = -1;
         if (!have_task || blk >= nb) return;
+        {
+            int32_t const hi_up = int32_t(ROWS) * int32_t(blk) + dhi;
+            ce_up = hi_up > int32_t(T.n) ? int32_t(T.n) : hi_up;
+        }
         // (all quantities are far below 2^31: queries are at most FXG_MAX_QUERY_LENGTH long)
         int32_t const lo = int32_t(ROWS) * int32_t(blk) + 1 + dlo;
         int32_t const hi = int32_t(ROWS) * int32_t(blk + 1) + dhi;
@@ -525,7 +542,12 @@ __device__ __forceinline__ void dp_task_group(DpLaunch const& L, const DpTask* c
                     S.Pv[i] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
                 }
                 S.score = int32_t(ROWS) - int32_t(pad);
+            } else if (S.cs - 1 == ce_up) {
+                // a band of a single diagonal (k = 0, window as long as the query): the block above ended at column cs - 1 and
+                // its lane, idle since, still holds that column's value
+                S.score = r_sc + ROWS;
             } else {
+                // the block above has just done column cs: its deltas there lead back to column cs - 1
                 S.score = r_sc - int32_t(r_hp >> 31) + int32_t(r_hn >> 31) + ROWS;
             }
             S.eqb = peq + S.b * (kNumSymbols * W);
@@ -583,16 +605,20 @@ __device__ __forceinline__ void dp_task_group(DpLaunch const& L, const DpTask* c
         // next step at which some lane's block ends (it moves on before the step after) or begins, or a buffer runs out
         uint32_t my_evt = active ? uint32_t(S.ce) + S.b + 1u : (S.cs == 0x7fffffff ? kNever : uint32_t(S.cs) + S.b);
         my_evt = min(my_evt, my_refill);
+        // What the lane takes from the lane of the block above (run_steps): nothing for block 0, "+1 per column" once the
+        // block above has ended.  Its last step is ce_up + b - 1; the step after it is an event (the block's end) and still
+        // reads that last column, the steps after that read the bound.
+        auto upper_at = [&](uint32_t step) {
+            if (S.b == 0) return Upper{0u, 0u};
+            return int32_t(step) - int32_t(S.b) > ce_up ? Upper{0u, 0x80000000u} : Upper{1u, 0u};
+        };
+        Upper const up_first = upper_at(t), up_rest = upper_at(t + 1);
+        bool const peel = __any_sync(0xffffffffu, up_first.keep != up_rest.keep);
+        if (active && S.b > 0 && int32_t(t) - int32_t(S.b) < ce_up) my_evt = min(my_evt, uint32_t(ce_up) + S.b);   // (coincides with the end of the block above)
         uint32_t const evt = min(__reduce_min_sync(0xffffffffu, my_evt), my_end + 1);
-        bool const any_first = __any_sync(0xffffffffu, active && S.b == 0);
         bool const any_last = __any_sync(0xffffffffu, active && S.b == last_block);
-        if (any_first) {
-            if (any_last) run_steps<W, CKPT, true, true>(S, t, evt, active, src_lane, last_block, win0, win, L.two);
-            else run_steps<W, CKPT, true, false>(S, t, evt, active, src_lane, last_block, win0, win, L.two);
-        } else {
-            if (any_last) run_steps<W, CKPT, false, true>(S, t, evt, active, src_lane, last_block, win0, win, L.two);
-            else run_steps<W, CKPT, false, false>(S, t, evt, active, src_lane, last_block, win0, win, L.two);
-        }
+        if (any_last) run_steps<W, CKPT, true>(S, t, evt, active, src_lane, last_block, win0, win, L.two, up_first, up_rest, peel);
+        else run_steps<W, CKPT, false>(S, t, evt, active, src_lane, last_block, win0, win, L.two, up_first, up_rest, peel);
         t = evt;
     }
     // the blocks that worked up to the warp's very last step never came back to the bookkeeping above: the last block of
@@ -708,6 +734,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) dp_wide_kernel(DpLaunch const
                             Pv[i] = virt >= 32 ? 0u : (virt > 0 ? (0xffffffffu << virt) : 0xffffffffu);
                         }
                         score = int32_t(ROWS) - int32_t(pad);
+                    } else if (cs - 1 == (int32_t(ROWS) * int32_t(l) + dhi > int32_t(T.n) ? int32_t(T.n) : int32_t(ROWS) * int32_t(l) + dhi)) {
+                        score = int32_t(up.z) + ROWS;                              // band of a single diagonal: the block above ended at column cs - 1
                     } else {
                         score = int32_t(up.z) - int32_t(up.x >> 31) + int32_t(up.y >> 31) + ROWS;
                     }

@@ -592,12 +592,19 @@ uint64_t word_steps_of(Pass const& p, uint32_t W, uint32_t nb) {
     return ws;
 }
 
-// Picks words-per-lane W and ring size G for one pass.  The ring must be long enough that a lane is idle
-// (and publishes the +1 boundary) whenever the block below still needs a boundary from it:
-//   G > (B - 4) / (32 W + 1) + 2,  B = number of diagonals in the band  (derivation in DESIGN.md).
+// Picks words-per-lane W and ring size G for one pass.  A lane takes its next block (G blocks further down) only after
+// its current one has ended: with R = 32 W rows per block, block b works during the steps (R + 1) b + 1 + dlo ..
+// (R + 1) b + R + dhi, so
+//   (R + 1) G >= R + B - 1,  B = number of diagonals in the band,  i.e.  G >= 2 + (B - 3) / (R + 1).
+// (The block below a block that has ended substitutes the "+1 per column" bound itself -- run_steps, `Upper` -- so the
+// lane above need not stay idle for it; that requirement cost one more lane per ring in round 1.)
 // FXG_LATENCY_WEIGHT > 0 makes the chooser prefer narrower blocks (development knob; measured with 0.3 on config 2: a batch
 // running alone 7.4 -> 6.9 ms, 16 batches in flight unchanged, a machine-filling launch 0.61 -> 0.48 of the issue peak)
 double g_latency_weight = [] { const char* e = std::getenv("FXG_LATENCY_WEIGHT"); return e ? std::atof(e) : 0.0; }();
+
+inline int64_t ring_lanes_needed(int64_t B, uint32_t W) { return B > 4 ? 2 + (B - 3) / (32 * int64_t(W) + 1) : 3; }
+// the widest band a ring of G lanes takes (inverse of ring_lanes_needed)
+inline int64_t ring_band_limit(uint32_t G, uint32_t W) { return 2 + (int64_t(G) - 1) * (32 * int64_t(W) + 1); }
 
 bool choose_config(Pass const& p, size_t smem_limit, bool force_wide, Config& out) {
     uint32_t const nw = (p.m + 31) / 32;
@@ -610,7 +617,7 @@ bool choose_config(Pass const& p, size_t smem_limit, bool force_wide, Config& ou
         uint32_t G;
         if (nb == 1) G = 1;
         else {
-            int64_t const need = (B > 4 ? (B - 4) / (32 * int64_t(W) + 1) : 0) + 3;
+            int64_t const need = ring_lanes_needed(B, W);
             int64_t const g = std::max<int64_t>(std::min<int64_t>(need, nb), 2);
             if (g > 32) continue;
             G = uint32_t(g);
@@ -1675,10 +1682,10 @@ int prepare_job(fxg_ctx* c, fxg_job* J, std::string& err, fxg_counters& ctr) {
                 int const ci = class_of_cached(c, cf, (rr.root_m + 32 * W - 1) / (32 * W) * W);
                 if (ci < 0) { out.status = 1; return; }
                 rr.reserved0 = uint32_t(ci);
-                // ring of G lanes: band B = n - m + 2k + 1 must satisfy G >= (B - 4) / (32 W + 1) + 3 (choose_config)
+                // ring of G lanes: band B = n - m + 2k + 1 <= ring_band_limit(G, W) (choose_config)
                 // (a lane per block, or the multi-warp kernel: any band)
                 int64_t const n_cap = (cf.G == kWideG || cf.G >= cf.nb) ? int64_t(1) << 30
-                                                                        : int64_t(rr.root_m) - 2 * int64_t(rr.root_k) - 1 + 3 + (int64_t(cf.G) - 2) * (32 * int64_t(W) + 1);
+                                                                        : int64_t(rr.root_m) - 2 * int64_t(rr.root_k) - 1 + ring_band_limit(cf.G, W);
                 rr.reserved1 = uint32_t(std::max<int64_t>(std::min<int64_t>(n_cap, int64_t(1) << 30), int64_t(n_root)));
             }
             uint64_t const shape = (uint64_t(R.query_len) << 32) ^ (uint64_t(R.num_inner) << 16) ^ R.num_leaves;

@@ -48,6 +48,32 @@ def test_align_matches_oracle(ctx, oracle, mode, m_range, err_range, n_tasks):
     assert (res["orientation"] == tasks["orientation"]).all()
 
 
+@pytest.mark.parametrize("mode", [abi.MODE_EXISTS, abi.MODE_NO_CIGAR, abi.MODE_CIGAR])
+def test_align_band_of_one_diagonal(ctx, oracle, mode):
+    """k = 0 and a window exactly as long as the query: the band is a single diagonal (queries of several blocks:
+    every block starts where the block above has just ended), with and without one mismatch."""
+    rng = np.random.default_rng(99 + mode)
+    ref = rng.integers(1, 5, size=40_000, dtype=np.uint8)
+    tasks, pool, off = [], [], 0
+    for i, m in enumerate([33, 64, 65, 100, 129, 257, 300, 640, 1025, 1500, 2049, 3000, 5000, 9000]):
+        for flip in (None, 0, m // 2, m - 1):
+            at = int(rng.integers(0, len(ref) - m))
+            q = ref[at:at + m].copy()
+            if flip is not None:
+                q[flip] = 1 + (q[flip] % 4)
+            pool.append(q)
+            tasks.append((at, at, off, m, m, 0, 0, mode, i & 1, (0,) * 6))
+            off += m
+    tasks = np.array(tasks, dtype=abi.ALIGN_TASK_DTYPE)
+    pool = np.concatenate(pool)
+    ctx.set_references([ref])
+    res, cig = ctx.align_batch(tasks, pool)
+    got = results_as_tuples(res, cig, tasks)
+    want = oracle_align_tasks(oracle, ref, tasks, pool)
+    assert got == want
+    assert sum(g[0] for g in got) == len(got) // 4
+
+
 def test_align_inline_reference_and_all_ranks(ctx, oracle):
     """Spans handed over as host bytes (the alignment::align shim) with ranks 0..5 incl. N == N matches."""
     rng = np.random.default_rng(7)
