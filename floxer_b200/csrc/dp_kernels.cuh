@@ -453,7 +453,9 @@ __device__ __forceinline__ void dp_task_group(DpLaunch const& L, const DpTask* c
     uint32_t c_base = 0;
     bool dead = false;                                         // internal inconsistency: the task reports kPoisonScore
     if (have_task) {
-        for (uint32_t c = r; c < kWinChunks; c += G) load_window_chunk(packed, store_chunks, first_chunk, reverse, c, win);
+        // (a short window does not fill the buffer: the sweep reads up to two characters past the window's end and no further)
+        uint32_t const fill = min(kWinChunks, (phase + T.n + 2u + 31u) / 32u);
+        for (uint32_t c = r; c < fill; c += G) load_window_chunk(packed, store_chunks, first_chunk, reverse, c, win);
         // ---- stage the Eq table of the query piece from the pool-level Peq planes: block-major, then symbol, then word ----
         uint32_t const n_words = nb * W;
         for (uint32_t w = r; w < n_words; w += G) {

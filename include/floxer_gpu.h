@@ -155,13 +155,16 @@ typedef struct {
 
 /* ---- life cycle ----
  * Environment read by fxg_create (all optional; defaults in brackets):
- *   FXG_GROUPS        [32]  worker groups = *_run / fxg_verify_reads calls served at the same time (1..32)
+ *   FXG_GROUPS        [6]   worker groups = batches in flight at the same time (1..32); callers beyond that wait in the queue
+ *   FXG_MERGE_JOBS    [16]  / FXG_MERGE_WALKS [1048576] / FXG_MERGE_WAIT_US [300]: how many waiting jobs (and anchors) one batch
+ *                           takes, and how long a job waits for company while other batches run
  *   FXG_WORKERS       [2 per host core over all groups and local ranks, 1..4; 8 for a call that runs alone]  workers per group
  *   FXG_SPIN_US       [20]  microseconds a worker polls for its launches before it sleeps on the event
  *   FXG_DEVICE_LEVELS [1]   0: the inner tree levels are scheduled from the host, one launch and wait per level
  *   FXG_INFER_INNER   [1]   0: every inner-node window is computed (no per-node election)
  *   FXG_SHARE_ROOTS   [1]   0: every root window is scored on its own
- *   FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN, FXG_LATENCY_WEIGHT, FXG_PROFILE, FXG_TRACE_WAVES: development aids
+ *   FXG_ROOT_CHUNKS / FXG_ROOT_CHUNK_MIN, FXG_MERGED_PARTS, FXG_DEVICE_ROOTS, FXG_FORCE_WIDE, FXG_LATENCY_WEIGHT, FXG_PROFILE,
+ *   FXG_TRACE_WAVES, FXG_TRACE_BATCHES: development aids
  * None of them changes a result.  When the library is loaded it sets CUDA_DEVICE_MAX_CONNECTIONS=32 unless the variable is
  * already set. */
 int fxg_create(int device, fxg_ctx** out);
