@@ -175,6 +175,7 @@ struct RefStore {
     std::vector<uint64_t> base, len;
     DevBuf d_base, d_len;                // the same two tables on the device (level kernels)
     uint64_t total = 0;
+    uint64_t version = 0;                // counts the successful fxg_set_references calls (staged batches hold store positions)
 };
 
 // one staged pool of query bytes with its Peq planes (+ optional inline reference pool)
@@ -385,6 +386,11 @@ struct fxg_ctx {
 
 struct fxg_batch {
     std::vector<fxg_align_task> tasks;
+    // the tasks' DP passes, made when the batch is staged (fxg_align_batch_run is device work): score passes and passes whose
+    // CIGAR is wanted, each with the task it belongs to; a task without a pass has its result already
+    std::vector<Pass> passes, root_passes;
+    std::vector<uint32_t> owner, root_owner, root_k;
+    uint64_t passes_refs_version = ~uint64_t(0);     // the reference store the passes' positions refer to
     Pool pool;
     std::vector<fxg_align_result> results;
     PinnedBuf cigars;                    // the device writes the cigars of a run straight into this pool
@@ -2821,13 +2827,50 @@ int fxg_set_references(fxg_ctx* c, size_t n_refs, const uint8_t* const* ranks, c
     RefStore& R = c->refs;
     R.packed.release(); R.d_base.release(); R.d_len.release();
     R.packed = packed; R.d_base = d_base; R.d_len = d_len;
-    R.base.swap(base); R.len.swap(len); R.total = total;
+    R.base.swap(base); R.len.swap(len); R.total = total; R.version++;
     c->have_refs = true;
     refresh_trace_budget(c);
     return FXG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ align batch
+
+// The DP passes of a batch's tasks, in task order: by chunks of tasks on several threads, then the passes of every chunk
+// move to their place.  Called with c->mu held (it reads the reference table).
+void build_batch_passes(fxg_ctx* c, fxg_batch* b, uint64_t refs_version) {
+    size_t const N = b->tasks.size();
+    size_t const T = parallel_threads(N, size_t(1) << 16);
+    std::vector<std::vector<Pass>> part_passes(T), part_roots(T);
+    std::vector<std::vector<uint32_t>> part_owner(T), part_root_owner(T);
+    std::vector<uint64_t> const& ref_bases = c->refs.base;
+    parallel_chunks(T, N, [&](size_t th, size_t lo, size_t hi) {
+        part_passes[th].reserve(hi - lo); part_owner[th].reserve(hi - lo);
+        for (size_t i = lo; i < hi; ++i) {
+            fxg_align_task const& t = b->tasks[i];
+            if (t.query_len == 0) continue;                  // aligns with zero errors (fxg_align_batch_run)
+            uint32_t const flags = (t.mode == FXG_MODE_NO_CIGAR ? kFlagReverse : 0u) | (t.ref_id == FXG_REF_INLINE ? kFlagInlineRef : 0u);
+            uint64_t const ref_base = (t.ref_id == FXG_REF_INLINE ? 0 : ref_bases[t.ref_id]) + t.ref_offset;
+            Pass p;
+            if (!score_pass_for(ref_base, t.query_offset, t.ref_len, t.query_len, t.max_errors, flags, p)) continue;
+            if (t.mode == FXG_MODE_CIGAR) { part_roots[th].push_back(p); part_root_owner[th].push_back(uint32_t(i)); }
+            else { part_passes[th].push_back(p); part_owner[th].push_back(uint32_t(i)); }
+        }
+    });
+    std::vector<size_t> at(T + 1, 0), root_at(T + 1, 0);
+    for (size_t th = 0; th < T; ++th) { at[th + 1] = at[th] + part_passes[th].size(); root_at[th + 1] = root_at[th] + part_roots[th].size(); }
+    b->passes.resize(at[T]); b->owner.resize(at[T]); b->root_passes.resize(root_at[T]); b->root_owner.resize(root_at[T]);
+    parallel_chunks(T, T, [&](size_t, size_t lo, size_t hi) {
+        for (size_t th = lo; th < hi; ++th) {
+            std::copy(part_passes[th].begin(), part_passes[th].end(), b->passes.begin() + long(at[th]));
+            std::copy(part_owner[th].begin(), part_owner[th].end(), b->owner.begin() + long(at[th]));
+            std::copy(part_roots[th].begin(), part_roots[th].end(), b->root_passes.begin() + long(root_at[th]));
+            std::copy(part_root_owner[th].begin(), part_root_owner[th].end(), b->root_owner.begin() + long(root_at[th]));
+        }
+    });
+    b->root_k.resize(b->root_owner.size());
+    for (size_t q = 0; q < b->root_owner.size(); ++q) b->root_k[q] = b->tasks[b->root_owner[q]].max_errors;
+    b->passes_refs_version = refs_version;
+}
 
 int fxg_align_batch_stage(fxg_ctx* c, const fxg_align_task* tasks, size_t n_tasks, const uint8_t* query_pool, size_t query_pool_len,
                           const uint8_t* inline_ref_pool, size_t inline_ref_pool_len, fxg_batch** out) {
@@ -2853,6 +2896,7 @@ int fxg_align_batch_stage(fxg_ctx* c, const fxg_align_task* tasks, size_t n_task
     fxg_batch* b = new (std::nothrow) fxg_batch();
     if (!b) return FXG_ERR_OUT_OF_MEMORY;
     b->tasks.assign(tasks, tasks + n_tasks);
+    build_batch_passes(c, b, c->refs.version);
     b->pool = take_pool(c);
     b->cigars = take_pinned(c);
     rc = stage_pool(c, b->pool, query_pool, query_pool_len, nullptr, 0, c->err, c->ctr);
@@ -2875,6 +2919,7 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
     if (!c || !b) return FXG_ERR_INVALID_ARGUMENT;
     std::unique_lock<std::mutex> lock(c->mu);
     CUDA_TRY(c->err, cudaSetDevice(c->device));
+    if (b->passes_refs_version != c->refs.version) build_batch_passes(c, b, c->refs.version);    // (the references were replaced since the batch was staged)
     WorkerGroup& grp = acquire_group(c, lock);
     lock.unlock();                                   // the group is this call's own from here on: other callers run beside it
     struct Release { fxg_ctx* c; WorkerGroup& g; ~Release() { std::lock_guard<std::mutex> l(c->mu); release_group(c, g); } } release{c, grp};
@@ -2887,55 +2932,37 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
     int rc;
     {
         RunTimer run_timer(grp, w.ctr);
+        auto t_mark = std::chrono::steady_clock::now();
+        auto mark = [&](const char* what) {              // (FXG_PROFILE) host phases of the call
+            if (!g_prof.on) return;
+            auto const now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[fxg] align_batch_run: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_mark).count());
+            t_mark = now;
+        };
         size_t const N = b->tasks.size();
         b->results.resize(N);
         b->cigars_len = 0;
-        // every task's pass (if it has one), by chunks of tasks; then the passes of every chunk move to their place in
-        // task order: score passes and passes whose CIGAR is wanted (these go through the root level's code)
+        std::vector<Pass> const& passes = b->passes; std::vector<Pass> const& root_passes = b->root_passes;
+        std::vector<uint32_t> const& owner = b->owner; std::vector<uint32_t> const& root_owner = b->root_owner; std::vector<uint32_t> const& root_k = b->root_k;
         size_t const T = parallel_threads(N, size_t(1) << 16);
-        std::vector<std::vector<Pass>> part_passes(T), part_roots(T);
-        std::vector<std::vector<uint32_t>> part_owner(T), part_root_owner(T);
-        parallel_chunks(T, N, [&](size_t th, size_t lo, size_t hi) {
-            part_passes[th].reserve(hi - lo); part_owner[th].reserve(hi - lo);
+        parallel_chunks(T, N, [&](size_t, size_t lo, size_t hi) {
             for (size_t i = lo; i < hi; ++i) {
                 fxg_align_task const& t = b->tasks[i];
-                b->results[i] = fxg_align_result{};
-                b->results[i].orientation = t.orientation;
-                uint32_t const flags = (t.mode == FXG_MODE_NO_CIGAR ? kFlagReverse : 0u) | (t.ref_id == FXG_REF_INLINE ? kFlagInlineRef : 0u);
-                uint64_t const ref_base = (t.ref_id == FXG_REF_INLINE ? 0 : c->refs.base[t.ref_id]) + t.ref_offset;
-                Pass p;
+                fxg_align_result r{};
+                r.orientation = t.orientation;
                 if (t.query_len == 0) {
                     // empty query: aligns with zero errors; the rightmost minimum of an all-zero last row is column n
-                    b->results[i].exists = 1;
-                    if (t.mode == FXG_MODE_CIGAR) b->results[i].start_in_reference = t.reference_span_offset + t.ref_len;
-                    else if (t.mode == FXG_MODE_NO_CIGAR) b->results[i].start_in_reference = t.reference_span_offset;
-                    continue;
+                    r.exists = 1;
+                    if (t.mode == FXG_MODE_CIGAR) r.start_in_reference = t.reference_span_offset + t.ref_len;
+                    else if (t.mode == FXG_MODE_NO_CIGAR) r.start_in_reference = t.reference_span_offset;
                 }
-                if (!score_pass_for(ref_base, t.query_offset, t.ref_len, t.query_len, t.max_errors, flags, p)) continue;
-                if (t.mode == FXG_MODE_CIGAR) { part_roots[th].push_back(p); part_root_owner[th].push_back(uint32_t(i)); }
-                else { part_passes[th].push_back(p); part_owner[th].push_back(uint32_t(i)); }
+                b->results[i] = r;
             }
         });
-        std::vector<Pass> passes, root_passes;
-        std::vector<uint32_t> owner, root_owner, root_k;
-        if (T == 1) { passes.swap(part_passes[0]); owner.swap(part_owner[0]); root_passes.swap(part_roots[0]); root_owner.swap(part_root_owner[0]); }
-        else {
-            std::vector<size_t> at(T + 1, 0), root_at(T + 1, 0);
-            for (size_t th = 0; th < T; ++th) { at[th + 1] = at[th] + part_passes[th].size(); root_at[th + 1] = root_at[th] + part_roots[th].size(); }
-            passes.resize(at[T]); owner.resize(at[T]); root_passes.resize(root_at[T]); root_owner.resize(root_at[T]);
-            parallel_chunks(T, T, [&](size_t, size_t lo, size_t hi) {
-                for (size_t th = lo; th < hi; ++th) {
-                    std::copy(part_passes[th].begin(), part_passes[th].end(), passes.begin() + long(at[th]));
-                    std::copy(part_owner[th].begin(), part_owner[th].end(), owner.begin() + long(at[th]));
-                    std::copy(part_roots[th].begin(), part_roots[th].end(), root_passes.begin() + long(root_at[th]));
-                    std::copy(part_root_owner[th].begin(), part_root_owner[th].end(), root_owner.begin() + long(root_at[th]));
-                }
-            });
-        }
-        root_k.resize(root_owner.size());
-        for (size_t q = 0; q < root_owner.size(); ++q) root_k[q] = b->tasks[root_owner[q]].max_errors;
+        mark("results reset");
         const DpResult* res = nullptr;
         rc = run_passes(c, w, b->pool, passes, nullptr, nullptr, &res);
+        mark("score passes");
         if (rc == FXG_OK) {
             parallel_chunks(T, passes.size(), [&](size_t, size_t lo, size_t hi) {
                 for (size_t q = lo; q < hi; ++q) {
@@ -2948,9 +2975,11 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
                     r.start_in_reference = t.reference_span_offset + (t.ref_len - res[q].end_col);   // alignment.cpp:135-139
                 }
             });
+            mark("results of the score passes");
             w.cig_used = 0;
             std::vector<RootOut> outs;
             rc = run_root_passes(c, w, b->pool, root_passes, root_k, trace_budget_bytes(c, 1), outs);
+            mark("passes with tracebacks");
             if (rc == FXG_OK) {
                 cudaError_t const e = b->cigars.ensure(std::max<uint64_t>(w.cig_used, 1) * 4);
                 if (e != cudaSuccess) rc = fail(w.err, FXG_ERR_CUDA, "cigar pool allocation: %s", cudaGetErrorString(e));
@@ -2967,7 +2996,9 @@ int fxg_align_batch_run(fxg_ctx* c, fxg_batch* b) {
                     r.cigar_offset = outs[q].cigar_offset; r.cigar_len = outs[q].cigar_len;
                 }
             }
+            mark("cigars and their results");
         }
+        if (g_prof.on) g_prof.report();
     }
     { std::lock_guard<std::mutex> l(c->mu); add_counters(c->ctr, w.ctr); if (rc != FXG_OK) c->err = w.err; }
     if (rc != FXG_OK) { tls_last_error = w.err; return rc; }
@@ -3459,6 +3490,20 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
         return rc;
     }
     *out = j;
+    return FXG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ engine shape
+
+int fxg_engine_shape(uint32_t n, uint32_t m, uint32_t k, uint32_t* words_per_lane, uint32_t* ring_lanes, uint32_t* blocks, uint64_t* word_steps) {
+    Pass p;
+    if (!score_pass_for(0, 0, n, m, k, 0, p)) return FXG_ERR_INVALID_ARGUMENT;
+    Config cf;
+    if (!choose_config(p, size_t(227) * 1024, false, cf)) return FXG_ERR_INVALID_ARGUMENT;
+    if (words_per_lane) *words_per_lane = uint32_t(kWidths[cf.widx]);
+    if (ring_lanes) *ring_lanes = cf.G;
+    if (blocks) *blocks = cf.nb;
+    if (word_steps) *word_steps = cf.word_steps;
     return FXG_OK;
 }
 

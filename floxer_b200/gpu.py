@@ -20,7 +20,7 @@ EXPORTS = [
     "fxg_align_batch", "fxg_align_batch_stage", "fxg_align_batch_run", "fxg_align_batch_fetch", "fxg_batch_free",
     "fxg_verify_stage", "fxg_verify_run", "fxg_job_num_alignments", "fxg_job_alignments", "fxg_job_cigar_len",
     "fxg_job_cigar_pool", "fxg_job_stats", "fxg_job_free", "fxg_verify_reads",
-    "fxg_get_counters", "fxg_reset_counters", "fxg_measure_int32_peak",
+    "fxg_get_counters", "fxg_reset_counters", "fxg_measure_int32_peak", "fxg_engine_shape",
     "fxg_pex_build", "fxg_pex_free", "fxg_job_write_sam", "fxg_free", "fxg_write_bam", "fxg_job_write_bam",
     "fxg_seeder_create", "fxg_seeder_free", "fxg_seeder_search",
 ]
@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
     L.fxg_get_counters.argtypes = [vp, C.POINTER(abi.Counters)]
     L.fxg_reset_counters.argtypes = [vp]
     L.fxg_measure_int32_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.fxg_engine_shape.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_uint64)]
     L.fxg_pex_build.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(vp), C.POINTER(sz),
                                 C.POINTER(vp), C.POINTER(sz)]
     L.fxg_pex_free.argtypes = [vp]
@@ -141,6 +143,14 @@ def pex_build(total_len: int, num_errors: int, leaf_max_errors: int, strategy: i
     L.fxg_pex_free(pi)
     L.fxg_pex_free(pl)
     return inner, leaves
+
+
+def engine_shape(n: int, m: int, k: int):
+    """(words per lane, lanes per ring, blocks, band-limited word-steps) the engine picks for one align call; None when no
+    alignment is possible.  Host arithmetic only (fxg_engine_shape)."""
+    w, g, nb, ws = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+    rc = lib().fxg_engine_shape(n, m, k, C.byref(w), C.byref(g), C.byref(nb), C.byref(ws))
+    return None if rc != 0 else (w.value, g.value, nb.value, ws.value)
 
 
 class Seeder:

@@ -185,7 +185,9 @@ int fxg_align_batch(fxg_ctx* ctx, const fxg_align_task* tasks, size_t n_tasks,
 int fxg_align_batch_stage(fxg_ctx* ctx, const fxg_align_task* tasks, size_t n_tasks,
                           const uint8_t* query_pool, size_t query_pool_len,
                           const uint8_t* inline_ref_pool, size_t inline_ref_pool_len, fxg_batch** out);
-int fxg_align_batch_run(fxg_ctx* ctx, fxg_batch* batch);  /* device work only; returns after it completed */
+int fxg_align_batch_run(fxg_ctx* ctx, fxg_batch* batch);  /* device work only; returns after it completed.  (The tasks' DP passes are
+                                                            * derived when the batch is staged; they are derived again here if the
+                                                            * references were replaced in between.) */
 int fxg_align_batch_fetch(fxg_ctx* ctx, fxg_batch* batch, fxg_align_result* results,
                           uint32_t* cigar_pool, size_t cigar_capacity, size_t* cigar_used);
 void fxg_batch_free(fxg_ctx* ctx, fxg_batch* batch);
@@ -261,6 +263,12 @@ int fxg_reset_counters(fxg_ctx* ctx);
 /* issue-rate microbenchmark: dependent-free LOP3/IADD3/SHF stream in the 8:1:2 mix of one Myers word-step;
  * returns thread-instructions per second (the int32 roofline denominator) */
 int fxg_measure_int32_peak(fxg_ctx* ctx, double* thread_instructions_per_second);
+
+/* the engine's shape for one alignment::align call of a query of length m against a window of length n with at most k
+ * errors: 32-bit words per lane (block height / 32), lanes per ring (64: the multi-warp kernel), blocks of the query and
+ * the band-limited word-steps of the pass.  Needs no device (tests check the ring rule of DESIGN.md 4.1 on it).
+ * FXG_ERR_INVALID_ARGUMENT if no alignment is possible (m = 0 or m - n > k). */
+int fxg_engine_shape(uint32_t n, uint32_t m, uint32_t k, uint32_t* words_per_lane, uint32_t* ring_lanes, uint32_t* blocks, uint64_t* word_steps);
 
 #ifdef __cplusplus
 }
