@@ -197,7 +197,7 @@ constexpr int kWidths[6] = {1, 2, 4, 8, 16, 32};
 
 struct Config { uint8_t widx; uint8_t G; uint32_t nb; uint64_t word_steps; };
 
-struct ConfigCacheEntry { uint32_t n, m; int32_t dlo, dhi; Config cfg; bool ok; bool valid; };
+struct ConfigCacheEntry { uint32_t n, m; int32_t dlo, dhi; Config cfg; bool ok; bool valid; bool traced; };
 
 // Everything one host worker needs to run passes on its own stream.
 struct WorkerGroup;
@@ -612,7 +612,7 @@ inline int64_t ring_lanes_needed(int64_t B, uint32_t W) { return B > 4 ? 2 + (B 
 // the widest band a ring of G lanes takes (inverse of ring_lanes_needed)
 inline int64_t ring_band_limit(uint32_t G, uint32_t W) { return 2 + (int64_t(G) - 1) * (32 * int64_t(W) + 1); }
 
-bool choose_config(Pass const& p, size_t smem_limit, bool force_wide, Config& out) {
+bool choose_config(Pass const& p, size_t smem_limit, bool force_wide, Config& out, bool traced = false) {
     uint32_t const nw = (p.m + 31) / 32;
     int64_t const B = int64_t(p.dhi) - int64_t(p.dlo) + 1;
     double best_cost = 1e300;
@@ -645,6 +645,12 @@ bool choose_config(Pass const& p, size_t smem_limit, bool force_wide, Config& ou
         cost += 2.0 * nb * 100.0 / std::sqrt(double(tpw));
         // a task is also a chain of `steps` dependent steps, each as long as the dependent instructions of one column
         cost += g_latency_weight * double(steps) * (30.0 + 12.0 * W);
+        // A pass whose CIGAR is wanted is followed by its traceback (walk2_kernel<W>): the tiles (block x 32 steps) the path
+        // crosses are recomputed by a group of W lanes, 32 + W single-word steps of ~25 instructions each.  Counted as if
+        // every pass were traced: where few are (repeat-rich references) the pass itself is long and this term is small.
+        // Measured on config 2 (profiles/r02_config2_issue_share_final.txt): pass + traceback 133 k + 36 k ALU-pipe warp
+        // instructions per read at W = 4 against 125 k + 60 k at W = 8.
+        if (traced) cost += (double(p.n) / 32.0 + nb) * (32.0 + W) * 25.0 * 0.5 * (double(W) / 32.0);
         if (cost < best_cost) { best_cost = cost; out = Config{uint8_t(wi), uint8_t(G), nb, 0}; found = true; }
     }
     if (!found) {
@@ -657,13 +663,13 @@ bool choose_config(Pass const& p, size_t smem_limit, bool force_wide, Config& ou
 }
 
 // the same (m, n, band) recurs for every anchor of a read at one tree level: memoise
-bool cached_config(std::vector<ConfigCacheEntry>& cache, Pass const& p, size_t smem_limit, bool force_wide, Config& out) {
+bool cached_config(std::vector<ConfigCacheEntry>& cache, Pass const& p, size_t smem_limit, bool force_wide, Config& out, bool traced = false) {
     uint64_t h = (uint64_t(p.n) * 0x9E3779B97F4A7C15ull) ^ (uint64_t(p.m) * 0xC2B2AE3D27D4EB4Full) ^ (uint64_t(uint32_t(p.dlo)) << 21) ^ uint64_t(uint32_t(p.dhi));
     h ^= h >> 29;
-    ConfigCacheEntry& e = cache[h & (cache.size() - 1)];
-    if (e.valid && e.n == p.n && e.m == p.m && e.dlo == p.dlo && e.dhi == p.dhi) { out = e.cfg; return e.ok; }
-    e.valid = true; e.n = p.n; e.m = p.m; e.dlo = p.dlo; e.dhi = p.dhi;
-    e.ok = choose_config(p, smem_limit, force_wide, e.cfg);
+    ConfigCacheEntry& e = cache[(h + (traced ? 1 : 0)) & (cache.size() - 1)];
+    if (e.valid && e.traced == traced && e.n == p.n && e.m == p.m && e.dlo == p.dlo && e.dhi == p.dhi) { out = e.cfg; return e.ok; }
+    e.valid = true; e.traced = traced; e.n = p.n; e.m = p.m; e.dlo = p.dlo; e.dhi = p.dhi;
+    e.ok = choose_config(p, smem_limit, force_wide, e.cfg, traced);
     out = e.cfg;
     return e.ok;
 }
@@ -734,7 +740,7 @@ int run_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> const&
             std::vector<ConfigCacheEntry>& cache = t == 0 ? w.cfg_cache : thread_config_cache(c);
             for (size_t i = lo; i < hi; ++i) {
                 Config& cf = w.cfgs[i];
-                if (!cached_config(cache, passes[i], c->smem_limit, c->force_wide, cf)) { bad[t] = i; return; }
+                if (!cached_config(cache, passes[i], c->smem_limit, c->force_wide, cf, trace)) { bad[t] = i; return; }
                 uint64_t const steps = std::min<uint64_t>(uint64_t(passes[i].n) + cf.nb - 1, (1u << 19) - 1);
                 uint64_t const cls = cf.G == kWideG ? 0 : uint64_t(5 - cf.widx) * 32 + (32 - cf.G) + 1;         // 0 = the multi-warp kernel, 1 = W 32, G 32
                 w.keys[i] = (cls << 51) | ((((1ull << 19) - 1) - steps) << 32) | uint64_t(i);
@@ -912,7 +918,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
     std::vector<Unit> units;
     std::vector<uint32_t> unit_members;
     auto finish_unit = [&](Unit& u) -> int {
-        if (!cached_config(w.cfg_cache, u.p, c->smem_limit, c->force_wide, u.cfg))
+        if (!cached_config(w.cfg_cache, u.p, c->smem_limit, c->force_wide, u.cfg, true))
             return fail(w.err, FXG_ERR_INVALID_ARGUMENT, "alignment of query length %u against window %u with band %d..%d exceeds the supported size",
                         u.p.m, u.p.n, u.p.dlo, u.p.dhi);
         uint32_t const W = uint32_t(kWidths[u.cfg.widx]);
@@ -974,7 +980,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
                 u.p = P0; u.p.n = uint32_t(u_end - u_start);
                 u.p.dlo = -int32_t(k0); u.p.dhi = int32_t(int64_t(u.p.n) - int64_t(u.p.m) + int64_t(k0));
                 Config probe;
-                if (cached_config(w.cfg_cache, u.p, c->smem_limit, c->force_wide, probe)) {
+                if (cached_config(w.cfg_cache, u.p, c->smem_limit, c->force_wide, probe, true)) {
                     for (size_t q = i; q < j; ++q) unit_members.push_back(order[q]);
                     int const rc = finish_unit(u);
                     if (rc != FXG_OK) return rc;
@@ -994,7 +1000,7 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         cigar_bound += cigar_cap_for(max_errors[i]);
         // a member that has to be scored again on its own must fit the budget as well
         Config cf;
-        if (cached_config(w.cfg_cache, passes[i], c->smem_limit, c->force_wide, cf)) {
+        if (cached_config(w.cfg_cache, passes[i], c->smem_limit, c->force_wide, cf, true)) {
             uint32_t const W = uint32_t(kWidths[cf.widx]);
             max_words = std::max(max_words, (uint64_t(cf.nb) * ck_records_per_block(int64_t(passes[i].dhi) - int64_t(passes[i].dlo) + 1, 32 * W) * ck_record_words(W) + 3) & ~uint64_t(3));
         }
@@ -1683,7 +1689,7 @@ int prepare_job(fxg_ctx* c, fxg_job* J, std::string& err, fxg_counters& ctr) {
                 uint64_t const n_root = base + 2 * extra;
                 if (n_root >= (uint64_t(1) << 31) || !score_pass_for(0, 0, uint32_t(n_root), rr.root_m, rr.root_k, 0, p)) { out.status = 1; return; }
                 Config cf;
-                if (!cached_config(cache, p, c->smem_limit, c->force_wide, cf)) { out.status = 1; return; }
+                if (!cached_config(cache, p, c->smem_limit, c->force_wide, cf, !J->cfg.without_cigar)) { out.status = 1; return; }   // (with its traceback, if CIGARs are wanted)
                 uint32_t const W = uint32_t(kWidths[cf.widx]);
                 int const ci = class_of_cached(c, cf, (rr.root_m + 32 * W - 1) / (32 * W) * W);
                 if (ci < 0) { out.status = 1; return; }
