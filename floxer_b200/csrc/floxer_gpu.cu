@@ -933,6 +933,9 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         if (rc == FXG_OK) units.push_back(u);
         return rc;
     };
+    // (sized up front: members scored again are appended while units are referenced, and a million growing push_backs
+    //  cost more than the passes of a batch of small alignments)
+    units.reserve(2 * N); unit_members.reserve(2 * N);
     {
         std::vector<uint32_t> order(N);
         for (size_t i = 0; i < N; ++i) order[i] = uint32_t(i);
@@ -993,7 +996,6 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
             i = j;
         }
     }
-    units.reserve(units.size() + N); unit_members.reserve(unit_members.size() + N);      // members scored again are appended while units are referenced
     uint64_t total_words = 0, max_words = 0, cigar_bound = 0;
     for (Unit const& u : units) { total_words += u.words; max_words = std::max(max_words, u.words); }
     for (size_t i = 0; i < N; ++i) {
@@ -1041,6 +1043,8 @@ int run_root_passes(fxg_ctx* c, Worker& w, Pool const& pool, std::vector<Pass> c
         }
     };
     std::unordered_map<DupKey, uint32_t, DupHash> dup_key;
+    dup_key.reserve(N);
+    hit_pass.reserve(N); hit_shift.reserve(N); hit_widx.reserve(N); accepted.reserve(N);
     std::vector<std::pair<uint64_t, uint32_t>> unit_seen;           // (end column << 32 | score, member) of the pass at hand
     uint64_t cig_at = w.cig_used;
     size_t H = 0;                            // tracebacks issued so far
