@@ -6,6 +6,9 @@
 // (W 32-bit words held in registers per lane); lane r of the ring owns blocks r, r+G, r+2G, ...;
 // block b processes column j at step t = j + b, so the only cross-lane traffic is the two
 // horizontal-delta bits (and the running score) of the block above, handed down with warp shuffles.
+// A lane takes its next block as soon as its own has ended; the block below a block that has ended
+// substitutes the "+1 per column" bound for the neighbour's deltas itself (run_steps: Upper), so a
+// ring needs G >= 2 + (B - 3) / (32 W + 1) lanes for a band of B diagonals and no more.
 // Only the cells inside the diagonal band [dlo, dhi] that can lie on an alignment with <= k errors
 // are computed (a block is active for columns cs(b)..ce(b)); outside values are replaced by upper
 // bounds (+1 steps), which keeps every value <= k exact.
