@@ -360,6 +360,25 @@ def test_wide_kernel_matches_oracle_at_small_sizes(gpu, oracle, monkeypatch):
                 want = oracle_align_tasks(oracle, ref, tasks, pool)
                 bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
                 assert not bad, (mode, m_range, bad[:5], [(got[i], want[i], tasks[i]) for i in bad[:2]])
+        # bands of a single diagonal over several of the kernel's 1 024-row blocks
+        rng = np.random.default_rng(31)
+        ref = rng.integers(1, 5, size=20_000, dtype=np.uint8)
+        c2.set_references([ref])
+        for mode in (abi.MODE_EXISTS, abi.MODE_NO_CIGAR, abi.MODE_CIGAR):
+            tasks, pool, off = [], [], 0
+            for m in (1025, 2049, 3000, 5000):
+                for flip in (None, 0, m // 2, m - 1):
+                    at = int(rng.integers(0, len(ref) - m))
+                    q = ref[at:at + m].copy()
+                    if flip is not None:
+                        q[flip] = 1 + (q[flip] % 4)
+                    pool.append(q)
+                    tasks.append((at, at, off, m, m, 0, 0, mode, 0, (0,) * 6))
+                    off += m
+            tasks = np.array(tasks, dtype=abi.ALIGN_TASK_DTYPE)
+            pool = np.concatenate(pool)
+            res, cig = c2.align_batch(tasks, pool)
+            assert results_as_tuples(res, cig, tasks) == oracle_align_tasks(oracle, ref, tasks, pool)
         refs = [synthetic.random_reference(100_000, 5)]
         c2.set_references(refs)
         batch = synthetic.make_batch(refs, 5, 1300, 0.07, 41, gpu.pex_build, seed_errors=1, decoy_fraction=0.3)
