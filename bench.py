@@ -337,6 +337,7 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
             "frac": achieved / int32_peak if int32_peak else None,
             "traffic": (_captured_traffic() or {}).get("bytes_per_launch"),
             "traffic_source": _captured_traffic(),
+            "hbm_view": _hbm_view(ctr, n_batches, total_s),
             "kernel": "fxg::dp_kernel<W, CKPT> -- every launch of the engine in the timed region (inner tree levels and root level)",
             "how": "algorithmic 11 int32 instructions per 32-cell word-step x the word-steps the engine's launches issued inside the timed "
                    "region of the device-resident arm (band-limited; counted per task from the band geometry, on the device for the inner "
@@ -374,6 +375,23 @@ def measure(ctx, g, torch, dist, refs, batch, cfg, lanes: int, steps: int, warmu
                                "inputs": "ordinary (pageable) host memory, as floxer's std::vector pools"}
     rec["cpu_baseline"] = cpu_arm(refs, batch, cfg, cpu_threads, cpu_target_s)
     return rec
+
+
+def _hbm_view(ctr, n_batches, region_s):
+    """The same path seen from HBM: the bytes the engine's checkpoint records take in the timed region (counter trace_bytes:
+    the dominant algorithmic traffic, written once and read by the tracebacks) over the region's wall time, and the captured
+    launch's DRAM bytes over its duration, against the measured copy bandwidth -- far from the bound, which is why the
+    roofline above is the integer issue rate."""
+    peak = _measured_peak("hbm_gbs") or 6500.0           # fallback: the recipe's B200 copy bandwidth
+    cap = _captured_traffic() or {}
+    out = {"peak_gbs": peak, "peak_source": "MEASURED_PEAKS.json" if _measured_peak("hbm_gbs") else "fallback of B200_PROFILING.md",
+           "region_checkpoint_gbs": ctr["trace_bytes"] / region_s / 1e9 if region_s > 0 else None}
+    if out["region_checkpoint_gbs"] is not None:
+        out["region_frac"] = out["region_checkpoint_gbs"] / peak
+    if cap.get("bytes_per_launch") and cap.get("launch_ms_under_ncu"):
+        out["captured_launch_gbs"] = cap["bytes_per_launch"] / (cap["launch_ms_under_ncu"] * 1e-3) / 1e9
+        out["captured_launch_frac"] = out["captured_launch_gbs"] / peak
+    return out
 
 
 def _captured_traffic():
