@@ -3505,11 +3505,12 @@ int fxg_verify_reads(fxg_ctx* c, const fxg_verify_config* cfg, const fxg_read* r
 
 // ------------------------------------------------------------------------------------------------ engine shape
 
-int fxg_engine_shape(uint32_t n, uint32_t m, uint32_t k, uint32_t* words_per_lane, uint32_t* ring_lanes, uint32_t* blocks, uint64_t* word_steps) {
+int fxg_engine_shape(uint32_t n, uint32_t m, uint32_t k, int with_traceback, uint32_t* words_per_lane, uint32_t* ring_lanes, uint32_t* blocks,
+                     uint64_t* word_steps) {
     Pass p;
     if (!score_pass_for(0, 0, n, m, k, 0, p)) return FXG_ERR_INVALID_ARGUMENT;
     Config cf;
-    if (!choose_config(p, size_t(227) * 1024, false, cf)) return FXG_ERR_INVALID_ARGUMENT;
+    if (!choose_config(p, size_t(227) * 1024, false, cf, with_traceback != 0)) return FXG_ERR_INVALID_ARGUMENT;
     if (words_per_lane) *words_per_lane = uint32_t(kWidths[cf.widx]);
     if (ring_lanes) *ring_lanes = cf.G;
     if (blocks) *blocks = cf.nb;

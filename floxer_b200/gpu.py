@@ -73,8 +73,8 @@ def lib() -> C.CDLL:
     L.fxg_get_counters.argtypes = [vp, C.POINTER(abi.Counters)]
     L.fxg_reset_counters.argtypes = [vp]
     L.fxg_measure_int32_peak.argtypes = [vp, C.POINTER(C.c_double)]
-    L.fxg_engine_shape.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
-                                   C.POINTER(C.c_uint64)]
+    L.fxg_engine_shape.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.fxg_pex_build.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(vp), C.POINTER(sz),
                                 C.POINTER(vp), C.POINTER(sz)]
     L.fxg_pex_free.argtypes = [vp]
@@ -145,11 +145,11 @@ def pex_build(total_len: int, num_errors: int, leaf_max_errors: int, strategy: i
     return inner, leaves
 
 
-def engine_shape(n: int, m: int, k: int):
-    """(words per lane, lanes per ring, blocks, band-limited word-steps) the engine picks for one align call; None when no
-    alignment is possible.  Host arithmetic only (fxg_engine_shape)."""
+def engine_shape(n: int, m: int, k: int, with_traceback: bool = False):
+    """(words per lane, lanes per ring, blocks, band-limited word-steps) the engine picks for one align call (with_traceback:
+    a pass whose CIGAR is wanted); None when no alignment is possible.  Host arithmetic only (fxg_engine_shape)."""
     w, g, nb, ws = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
-    rc = lib().fxg_engine_shape(n, m, k, C.byref(w), C.byref(g), C.byref(nb), C.byref(ws))
+    rc = lib().fxg_engine_shape(n, m, k, int(with_traceback), C.byref(w), C.byref(g), C.byref(nb), C.byref(ws))
     return None if rc != 0 else (w.value, g.value, nb.value, ws.value)
 
 

@@ -267,8 +267,10 @@ int fxg_measure_int32_peak(fxg_ctx* ctx, double* thread_instructions_per_second)
 /* the engine's shape for one alignment::align call of a query of length m against a window of length n with at most k
  * errors: 32-bit words per lane (block height / 32), lanes per ring (64: the multi-warp kernel), blocks of the query and
  * the band-limited word-steps of the pass.  Needs no device (tests check the ring rule of DESIGN.md 4.1 on it).
+ * with_traceback != 0: a pass whose CIGAR is wanted -- the block width is chosen with the traceback's cost in the sum.
  * FXG_ERR_INVALID_ARGUMENT if no alignment is possible (m = 0 or m - n > k). */
-int fxg_engine_shape(uint32_t n, uint32_t m, uint32_t k, uint32_t* words_per_lane, uint32_t* ring_lanes, uint32_t* blocks, uint64_t* word_steps);
+int fxg_engine_shape(uint32_t n, uint32_t m, uint32_t k, int with_traceback, uint32_t* words_per_lane, uint32_t* ring_lanes, uint32_t* blocks,
+                     uint64_t* word_steps);
 
 #ifdef __cplusplus
 }

@@ -39,8 +39,8 @@ def shapes(rng, count):
 def test_ring_rule_holds_for_the_chosen_shapes(gpu):
     rng = np.random.default_rng(5)
     seen_rings = 0
-    for n, m, k in shapes(rng, 4000):
-        shape = gpu.engine_shape(n, m, k)
+    for count, (n, m, k) in enumerate(shapes(rng, 4000)):
+        shape = gpu.engine_shape(n, m, k, with_traceback=bool(count & 1))
         if m - n > k:
             assert shape is None
             continue
@@ -84,3 +84,20 @@ def test_rings_are_as_short_as_the_rule_allows(gpu):
         need = max(2, -(-(R + B - 1) // (R + 1))) if B > 4 else 3
         assert G >= min(need, nb)
         assert G == 32 // (32 // max(min(need, nb), 2)), (n, m, k, W, G, need)
+
+
+def root_window(m, k, ratio=0.05):
+    base = m + 2 * k + 1
+    return base + 2 * int(np.ceil(base * ratio - 1e-9))
+
+
+def test_traced_passes_count_their_traceback(gpu):
+    """Config 2's root (5 kbp at 5 %): four tasks per warp at W = 8 beat two at W = 4 for the pass alone, but the traceback that
+    follows every such pass costs more at W = 8 than the pass gains (profiles/r02_config2_issue_share_final.txt); the long
+    roots of configs 3 and 4 keep their width either way."""
+    n = root_window(5000, 250)
+    assert gpu.engine_shape(n, 5000, 250)[:2] == (8, 8)
+    assert gpu.engine_shape(n, 5000, 250, with_traceback=True)[:2] == (4, 16)
+    for m, k in ((15000, 1200), (20000, 2000)):
+        n = root_window(m, k)
+        assert gpu.engine_shape(n, m, k)[0] == gpu.engine_shape(n, m, k, with_traceback=True)[0]
